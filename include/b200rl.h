@@ -1,0 +1,174 @@
+/* b200rl.h — C ABI of libb200rl.so: the Blackwell (sm_100a) vectorised RL inner loop that
+ * sits behind ReinforcementLearning.jl's `Base.run(policy, env, stop, hook)` surface.
+ *
+ * The reference has no FFI: its extension mechanism is Julia multiple dispatch on
+ * `AbstractEnv` / `AbstractPolicy` (src/ReinforcementLearningBase/src/interface.jl:27,67).
+ * "Drop-in" therefore means new Julia subtypes whose methods `ccall` the entry points below
+ * (see INTEGRATION.md and reinforcementlearning.jl_b200/julia/B200RL.jl).  Each entry point
+ * cites the reference method(s) it stands in for; paths are relative to /root/reference/src.
+ *
+ * Conventions
+ *  - every function returns 0 (B200RL_OK) or a negative b200rl_status; nothing throws across
+ *    the ABI; b200rl_last_error() returns a thread-local message for the last failure.
+ *  - plain pointers and sizes only.  Host arrays are borrowed for the duration of the call.
+ *    Arrays use Julia's column-major convention: env state is (NS, N), rollout tensors are
+ *    (N, T) env-fastest.
+ *  - the library owns all device memory behind the opaque handles.  Each ctx owns one CUDA
+ *    stream; calls are asynchronous on it except *_get / *_sync and calls taking host arrays.
+ *  - handles are not thread-safe (one driver task per ctx, like the reference's
+ *    single-threaded _run, RLCore/src/core/run.jl:36-78).
+ *  - there is NO CPU fallback: every entry point fails with B200RL_ERR_CUDA when no sm_100
+ *    device is usable.
+ */
+#ifndef B200RL_H
+#define B200RL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B200RL_OK = 0,
+    B200RL_ERR_INVALID = -1,        /* bad argument / handle */
+    B200RL_ERR_CUDA = -2,           /* CUDA runtime / launch failure */
+    B200RL_ERR_UNSUPPORTED = -3,    /* configuration outside the hot-path scope */
+    B200RL_ERR_ACTION = -4,         /* an action outside action_space(env) was seen (replaces `@assert a in action_space(env)`) */
+    B200RL_ERR_NCCL = -5,
+    B200RL_ERR_OOM = -6
+} b200rl_status;
+
+typedef struct b200rl_ctx b200rl_ctx;
+typedef struct b200rl_env b200rl_env;
+typedef struct b200rl_traj b200rl_traj;
+typedef struct b200rl_net b200rl_net;
+
+/* ---------------------------------------------------------------- context ---------- */
+int b200rl_init(int device, b200rl_ctx** out);
+void b200rl_destroy(b200rl_ctx* ctx);
+const char* b200rl_last_error(void);
+int b200rl_sync(b200rl_ctx* ctx);                   /* cudaStreamSynchronize(ctx stream) */
+int b200rl_abi_version(void);
+/* raw CUDA stream of the ctx (cudaStream_t as void*) so a host can order its own work */
+int b200rl_stream(b200rl_ctx* ctx, void** stream_out);
+/* device timing on the ctx stream (CUDA events) for hosts without a CUDA binding */
+int b200rl_timer_start(b200rl_ctx* ctx);
+int b200rl_timer_stop_ms(b200rl_ctx* ctx, float* ms_out);   /* synchronises */
+/* device / pinned-host buffers for hosts without a CUDA binding (Julia without CUDA.jl) */
+int b200rl_malloc(b200rl_ctx* ctx, size_t bytes, void** dptr_out);
+int b200rl_free(b200rl_ctx* ctx, void* dptr);
+int b200rl_host_alloc(b200rl_ctx* ctx, size_t bytes, void** hptr_out);   /* pinned */
+int b200rl_host_free(b200rl_ctx* ctx, void* hptr);
+int b200rl_memcpy_h2d(b200rl_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, int async);
+int b200rl_memcpy_d2h(b200rl_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes, int async);
+int b200rl_memset(b200rl_ctx* ctx, void* dst_dev, int value, size_t bytes);
+/* number of kernels this ctx has launched so far (bench `gpu_launches`) */
+int b200rl_launch_count(b200rl_ctx* ctx, uint64_t* count_out);
+/* write > L2-capacity bytes so the next kernel starts from a cold L2 (bench hygiene) */
+int b200rl_flush_l2(b200rl_ctx* ctx);
+
+/* ---------------------------------------------------------------- vector env ------- */
+typedef enum { B200RL_ENV_CARTPOLE = 0, B200RL_ENV_PENDULUM = 1, B200RL_ENV_MOUNTAINCAR = 2 } b200rl_env_kind;
+typedef enum { B200RL_F32 = 0, B200RL_F64 = 1 } b200rl_dtype;
+typedef enum {
+    B200RL_FIELD_STATE = 0,     /* (NS, N) T      env.state                                      */
+    B200RL_FIELD_OBS = 1,       /* (NOBS, N) T    state(env)  (Pendulum: [sin th, cos th, thdot]) */
+    B200RL_FIELD_REWARD = 2,    /* (N,) T         reward(env)                                    */
+    B200RL_FIELD_TERMINAL = 3,  /* (N,) uint8     is_terminated(env)                             */
+    B200RL_FIELD_T = 4,         /* (N,) int32     env.t                                          */
+    B200RL_FIELD_RNG = 5,       /* (4, N) uint64  raw Xoshiro256++ state s0..s3 per env          */
+    B200RL_FIELD_FLAGS = 6,     /* (N,) uint8     bit0 terminal, bit1 already auto-reset         */
+    B200RL_FIELD_ACTION = 7     /* (N,) int32 | T last action                                    */
+} b200rl_field;
+
+/* Final field values of the reference's params structs (already rounded to T by the
+ * reference constructor; double embeds Float32 exactly).  Pass NULL for the defaults. */
+typedef struct {   /* CartPoleEnvParams{T}: RLEnvs/src/environments/examples/CartPoleEnv.jl:3-46 */
+    double gravity, masscart, masspole, totalmass, halflength, polemasslength, forcemag, dt,
+        thetathreshold, xthreshold;
+    int64_t max_steps;
+} b200rl_cartpole_params;
+typedef struct {   /* PendulumEnvParams{T} + n_actions + continuous: PendulumEnv.jl:3-66 */
+    double max_speed, max_torque, g, m, l, dt;
+    int64_t max_steps, n_actions;
+    int32_t continuous;
+} b200rl_pendulum_params;
+typedef struct {   /* MountainCarEnvParams{T}: MountainCarEnv.jl:3-40 */
+    double min_pos, max_pos, max_speed, goal_pos, goal_velocity, power, gravity;
+    int64_t max_steps;
+} b200rl_mountaincar_params;
+
+/* Replaces N x `CartPoleEnv(; T, rng)` / `PendulumEnv` / `MountainCarEnv` constructors
+ * (CartPoleEnv.jl:74-79, PendulumEnv.jl:41-66, MountainCarEnv.jl:67-81) and the absent
+ * `MultiThreadEnv([...])`.  `rng_state` = (4, N) uint64 host array: raw Xoshiro state per
+ * env (Julia side: `Xoshiro(seed_i)` fields s0..s3).  Like the reference constructors it
+ * performs one reset!() per env.  Supported: CartPole f32|f64 discrete; Pendulum f32
+ * continuous|discrete; MountainCar f32 discrete. */
+int b200rl_env_create(b200rl_ctx* ctx, int kind, int dtype, int64_t n_envs, const void* params,
+                      const uint64_t* rng_state, b200rl_env** out);
+int b200rl_env_destroy(b200rl_env* env);
+/* Base.copy(env) (RLBase/src/interface.jl:443): deep copy incl. RNG streams */
+int b200rl_env_copy(b200rl_env* env, b200rl_env** out);
+/* Random.seed!(env, seed) (CartPoleEnv.jl:83): replace the raw RNG states */
+int b200rl_env_seed(b200rl_env* env, const uint64_t* rng_state);
+/* RLBase.reset!(env) (CartPoleEnv.jl:98-104, PendulumEnv.jl:84-92, MountainCarEnv.jl:99-105).
+ * force_all != 0: every env; 0: only envs that are terminated and not yet re-initialised
+ * (MultiThreadEnv's soft reset). */
+int b200rl_env_reset(b200rl_env* env, int force_all);
+/* RLBase.act!(env, a) for all N envs in one kernel (CartPoleEnv.jl:112-140,
+ * PendulumEnv.jl:94-118, MountainCarEnv.jl:113-135).  actions: int32 (N,) 1-based for
+ * discrete spaces, T (N,) for Pendulum continuous.  auto_reset != 0 fuses the soft reset of
+ * envs that just terminated into the same launch (reward/terminal keep the terminating
+ * step's values; state/obs become the fresh episode's). */
+int b200rl_env_step(b200rl_env* env, const void* actions, int actions_on_device, int auto_reset);
+/* plan!(RandomPolicy(), env) + act!(env, a) fused (RLCore/src/policies/random_policy.jl:29-32):
+ * the action is drawn from each env's own Xoshiro stream with rand(rng, Base.OneTo(n)),
+ * i.e. the reference default where policy and env share Random.default_rng(). */
+int b200rl_env_step_random(b200rl_env* env, int auto_reset);
+/* state(env) / reward(env) / is_terminated(env) ...: synchronous copy-out to host */
+int b200rl_env_get(b200rl_env* env, int field, void* host_dst, size_t bytes);
+int b200rl_env_set(b200rl_env* env, int field, const void* host_src, size_t bytes);
+/* zero-copy device pointer of a field for fused consumers */
+int b200rl_env_ptr(b200rl_env* env, int field, void** dptr_out);
+/* raises B200RL_ERR_ACTION if any launch since the last check saw an out-of-space action */
+int b200rl_env_check(b200rl_env* env);
+/* device-side hooks: per-env episode statistics accumulated by the step kernel, the batched
+ * form of TotalRewardPerEpisode / BatchStepsPerEpisode (RLCore/src/core/hooks.jl:146-231).
+ * out[0] = finished episodes, out[1] = sum of their returns, out[2] = sum of their lengths,
+ * out[3] = total env-steps taken.  reset_after != 0 zeroes the counters. */
+int b200rl_env_episode_stats(b200rl_env* env, double* out4, int reset_after);
+
+/* ---------------------------------------------------------------- returns ---------- */
+/* generalized_advantage_estimation / discount_rewards / discount_rewards_reduced
+ * (RLCore/src/utils/basic.jl:334-417, :138-235, :237-319).  rewards is an (R, C)
+ * column-major matrix; dims = 1: each column is a series (time along dim 1), dims = 2: each
+ * row is a series (time along dim 2, the PPO (N, T) layout).  values has one extra entry
+ * along the time dim.  terminal (uint8, same shape) and init (one per series) may be NULL.
+ * on_device = 0: pointers are host arrays (copied in/out, synchronous); 1: device pointers
+ * (asynchronous on the ctx stream).  Results are bit-identical to the reference's serial
+ * loop (same operation order, no FMA contraction). */
+int b200rl_gae_f32(b200rl_ctx* ctx, float* adv, const float* rewards, const float* values,
+                   const uint8_t* terminal, float gamma, float lambda, int64_t R, int64_t C,
+                   int dims, int on_device);
+int b200rl_gae_f64(b200rl_ctx* ctx, double* adv, const double* rewards, const double* values,
+                   const uint8_t* terminal, double gamma, double lambda, int64_t R, int64_t C,
+                   int dims, int on_device);
+int b200rl_discount_rewards_f32(b200rl_ctx* ctx, float* out, const float* rewards,
+                                const uint8_t* terminal, const float* init, float gamma,
+                                int64_t R, int64_t C, int dims, int on_device);
+int b200rl_discount_rewards_f64(b200rl_ctx* ctx, double* out, const double* rewards,
+                                const uint8_t* terminal, const double* init, double gamma,
+                                int64_t R, int64_t C, int dims, int on_device);
+int b200rl_discount_rewards_reduced_f32(b200rl_ctx* ctx, float* out, const float* rewards,
+                                        const uint8_t* terminal, const float* init, float gamma,
+                                        int64_t R, int64_t C, int dims, int on_device);
+int b200rl_discount_rewards_reduced_f64(b200rl_ctx* ctx, double* out, const double* rewards,
+                                        const uint8_t* terminal, const double* init, double gamma,
+                                        int64_t R, int64_t C, int dims, int on_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H */

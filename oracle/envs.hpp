@@ -1,0 +1,216 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see jl_math.hpp header).
+//
+// Scalar, one-object-per-env restatement of the reference's classic-control envs, with
+// Julia's promotion rules spelled out.  Follows
+//   CartPoleEnv.jl:22-46 (params), :84-86 (reward/terminated/state), :98-104 (reset!),
+//                  :112-116 (act!), :118-140 (_step!)
+//   PendulumEnv.jl:41-66, :70-71, :80-92, :94-122
+//   MountainCarEnv.jl:19-40, :95-105, :113-135
+// under /root/reference/src/ReinforcementLearningEnvironments/src/environments/examples/.
+// Compile with -ffp-contract=off: Julia never contracts a*b+c outside explicit muladd.
+// PARITY UNPINNED by the reference (no golden trajectories exist); pinned by
+// the source-derived known answers of SURVEY Appendix C (tests/test_oracle_envs.py).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "jl_math.hpp"
+#include "jl_rng.hpp"
+
+namespace oracle {
+
+// Final field values of the reference's params structs (already converted to T by the
+// reference constructor; carried as double, which embeds Float32 exactly).
+struct CartPoleParams {  // CartPoleEnvParams{T}, CartPoleEnv.jl:3-15
+    double gravity, masscart, masspole, totalmass, halflength, polemasslength, forcemag, dt,
+        thetathreshold, xthreshold;
+    int64_t max_steps;
+};
+template <class T> inline CartPoleParams cartpole_default_params() {
+    // CartPoleEnvParams{T}(; ...) CartPoleEnv.jl:22-46: derived fields computed in Float64,
+    // every field converted to T by the struct constructor.
+    CartPoleParams p;
+    p.gravity = (T)9.8; p.masscart = (T)1.0; p.masspole = (T)0.1;
+    p.totalmass = (T)(1.0 + 0.1); p.halflength = (T)0.5; p.polemasslength = (T)(0.1 * 0.5);
+    p.forcemag = (T)10.0; p.dt = (T)0.02; p.thetathreshold = (T)(12.0 * jl::PI_D / 180);
+    p.xthreshold = (T)2.4; p.max_steps = 200;
+    return p;
+}
+
+template <class T> struct CartPole {
+    static constexpr int NS = 4, NOBS = 4, NACT = 2;
+    T g, M, m, l, pml, fmag, dt, ththr, xthr;
+    int64_t max_steps;
+    std::vector<T> state;  // heap vector per env, like the reference's Vector{T}
+    int64_t action = 0;
+    bool done = false;
+    int64_t t = 0;
+    jl::Xoshiro rng;
+
+    CartPole(const CartPoleParams& p, jl::Xoshiro r, bool do_reset = true) : state(4, (T)0), rng(r) {
+        g = (T)p.gravity; M = (T)p.totalmass; m = (T)p.masspole; l = (T)p.halflength;
+        pml = (T)p.polemasslength; fmag = (T)p.forcemag; dt = (T)p.dt;
+        ththr = (T)p.thetathreshold; xthr = (T)p.xthreshold; max_steps = p.max_steps;
+        if (do_reset) reset();  // CartPoleEnv.jl:77
+    }
+    void reset() {  // CartPoleEnv.jl:98-104
+        T u[4];
+        jl::rand_array4(rng, u);  // rand(rng, T, 4)
+        for (int k = 0; k < 4; ++k) state[k] = (T)0.1 * u[k] - (T)0.05;
+        t = 0;
+        action = jl::rand_oneto(rng, 2);  // rand(rng, Base.OneTo(2)) — consumes the stream
+        done = false;
+    }
+    bool act(int64_t a) {  // CartPoleEnv.jl:112-116; returns false on `@assert` failure
+        if (a < 1 || a > 2) return false;
+        action = a;
+        step(a == 2 ? 1 : -1);
+        return true;
+    }
+    void step(int a) {  // CartPoleEnv.jl:118-140
+        t += 1;
+        T force = (T)a * fmag;
+        T x = state[0], xdot = state[1], theta = state[2], thetadot = state[3];
+        T c = jl::jcos(theta), s = jl::jsin(theta);
+        T tmp = (force + (pml * (thetadot * thetadot)) * s) / M;
+        // `4 / 3` is a Float64 literal expression: everything touching it is Float64.
+        double den = (double)l * (4.0 / 3.0 - (double)((m * (c * c)) / M));
+        double thetaacc = (double)(g * s - c * tmp) / den;
+        double xacc = (double)tmp - (((double)pml * thetaacc) * (double)c) / (double)M;
+        state[0] = x + dt * xdot;
+        state[1] = (T)((double)xdot + (double)dt * xacc);
+        state[2] = theta + dt * thetadot;
+        state[3] = (T)((double)thetadot + (double)dt * thetaacc);
+        done = std::fabs(state[0]) > xthr || std::fabs(state[2]) > ththr || t > max_steps;
+    }
+    T reward() const { return done ? (T)0 : (T)1; }  // CartPoleEnv.jl:84
+    void obs(T* out) const { for (int k = 0; k < 4; ++k) out[k] = state[k]; }
+};
+
+struct PendulumParams {  // PendulumEnvParams{T}, PendulumEnv.jl:3-11 (+ n_actions, continuous)
+    double max_speed, max_torque, g, m, l, dt;
+    int64_t max_steps;
+    int64_t n_actions;
+    int32_t continuous;
+};
+inline PendulumParams pendulum_default_params() {
+    return PendulumParams{8, 2, 10, 1, 1, (double)0.05f, 200, 3, 1};
+}
+
+// Float32 only: Float64 Pendulum is in no BASELINE config (needs the double rem_pio2 tree).
+struct Pendulum {
+    using T = float;
+    static constexpr int NS = 2, NOBS = 3;
+    T max_speed, max_torque, g, m, l, dt;
+    int64_t max_steps, n_actions;
+    bool continuous;
+    std::vector<T> state;
+    T action = 0, rew = 0;
+    bool done = false;
+    int64_t t = 0;
+    jl::Xoshiro rng;
+
+    Pendulum(const PendulumParams& p, jl::Xoshiro r, bool do_reset = true) : state(2, 0.f), rng(r) {
+        max_speed = (T)p.max_speed; max_torque = (T)p.max_torque; g = (T)p.g; m = (T)p.m;
+        l = (T)p.l; dt = (T)p.dt; max_steps = p.max_steps; n_actions = p.n_actions;
+        continuous = p.continuous != 0;
+        if (do_reset) reset();  // PendulumEnv.jl:64
+    }
+    void reset() {  // PendulumEnv.jl:84-92; two scalar rand(rng, T) draws
+        T u1 = jl::rand_f32(rng);
+        state[0] = (T)((2 * jl::PI_D) * (double)(u1 - 1.0f));  // 2*pi is Float64
+        T u2 = jl::rand_f32(rng);
+        state[1] = 2.0f * (u2 - 1.0f);
+        action = 0; t = 0; done = false; rew = 0;
+    }
+    // continuous: a in -2.0..2.0 (PendulumEnv.jl:73,95,122)
+    bool act_continuous(double a) {
+        if (!(a >= -2.0 && a <= 2.0)) return false;
+        action = (T)a;
+        step(action);
+        return true;
+    }
+    // discrete: a in 1..n_actions, torque() PendulumEnv.jl:120-121 (Float64, stored as T)
+    bool act_discrete(int64_t a) {
+        if (a < 1 || a > n_actions) return false;
+        double tq = (4.0 / (double)(n_actions - 1)) * ((double)a - (double)(n_actions - 1) / 2 - 1);
+        action = (T)tq;
+        step(action);
+        return true;
+    }
+    void step(T a) {  // PendulumEnv.jl:100-118
+        t += 1;
+        T th = state[0], thdot = state[1];
+        a = jl::jclamp(a, -max_torque, max_torque);
+        // angle_normalize: Float32 + pi -> Float32; mod(Float32, Float64) -> Float64
+        double an = jl::jmod((double)(th + (T)jl::PI_D), 2 * jl::PI_D) - jl::PI_D;
+        double costs = (an * an + 0.1 * (double)(thdot * thdot)) + 0.001 * (double)(a * a);
+        T newthdot = thdot + ((((-3.0f * g) / (2.0f * l)) * jl::jsin(th + (T)jl::PI_D)) +
+                              ((3.0f * a) / (m * (l * l)))) * dt;
+        th = th + newthdot * dt;
+        newthdot = jl::jclamp(newthdot, -max_speed, max_speed);
+        state[0] = th; state[1] = newthdot;
+        done = t >= max_steps;
+        rew = (T)(-costs);
+    }
+    T reward() const { return rew; }
+    void obs(T* out) const {  // pendulum_observation PendulumEnv.jl:70
+        out[0] = jl::jsin(state[0]); out[1] = jl::jcos(state[0]); out[2] = state[1];
+    }
+};
+
+struct MountainCarParams {  // MountainCarEnvParams{T}, MountainCarEnv.jl:3-12
+    double min_pos, max_pos, max_speed, goal_pos, goal_velocity, power, gravity;
+    int64_t max_steps;
+};
+inline MountainCarParams mountaincar_default_params() {
+    using T = float;
+    return MountainCarParams{(T)-1.2, (T)0.6, (T)0.07, (T)0.5, (T)0.0, (T)0.001, (T)0.0025, 200};
+}
+
+// Float32, discrete actions (1..3).  Continuous variant is a SURVEY §8f "next" item.
+struct MountainCar {
+    using T = float;
+    static constexpr int NS = 2, NOBS = 2, NACT = 3;
+    T min_pos, max_pos, max_speed, goal_pos, goal_velocity, power, gravity;
+    int64_t max_steps;
+    std::vector<T> state;
+    int64_t action = 0;
+    bool done = false;
+    int64_t t = 0;
+    jl::Xoshiro rng;
+
+    MountainCar(const MountainCarParams& p, jl::Xoshiro r, bool do_reset = true) : state(2, 0.f), rng(r) {
+        min_pos = (T)p.min_pos; max_pos = (T)p.max_pos; max_speed = (T)p.max_speed;
+        goal_pos = (T)p.goal_pos; goal_velocity = (T)p.goal_velocity; power = (T)p.power;
+        gravity = (T)p.gravity; max_steps = p.max_steps;
+        if (do_reset) reset();  // MountainCarEnv.jl:79
+    }
+    void reset() {  // MountainCarEnv.jl:99-105 (0.2 and 0.6 are Float64 literals)
+        T u = jl::rand_f32(rng);
+        state[0] = (T)(0.2 * (double)u - 0.6);
+        state[1] = 0;
+        done = false; t = 0;
+    }
+    bool act(int64_t a) {  // MountainCarEnv.jl:113-117
+        if (a < 1 || a > 3) return false;
+        action = a;
+        step((int)a - 2);
+        return true;
+    }
+    void step(int force) {  // MountainCarEnv.jl:119-135
+        t += 1;
+        T x = state[0], v = state[1];
+        v = v + ((T)force * power + jl::jcos(3.0f * x) * (-gravity));
+        v = jl::jclamp(v, -max_speed, max_speed);
+        x = x + v;
+        x = jl::jclamp(x, min_pos, max_pos);
+        if (x == min_pos && v < 0) v = 0;
+        done = (x >= goal_pos && v >= goal_velocity) || t >= max_steps;
+        state[0] = x; state[1] = v;
+    }
+    T reward() const { return done ? (T)0 : (T)-1; }  // MountainCarEnv.jl:95
+    void obs(T* out) const { out[0] = state[0]; out[1] = state[1]; }
+};
+
+}  // namespace oracle

@@ -1,0 +1,194 @@
+"""ctypes binding of libb200rl.so (include/b200rl.h).  No torch types cross this boundary.
+
+The library is built in-tree by ``build.py`` (nvcc, sm_100a).  There is no CPU fallback: if
+the shared object is missing, or no sm_100 device is usable, calls fail loudly."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libb200rl.so")
+
+OK = 0
+ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_ACTION, ERR_NCCL, ERR_OOM = -1, -2, -3, -4, -5, -6
+
+ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR = 0, 1, 2
+F32, F64 = 0, 1
+FIELD_STATE, FIELD_OBS, FIELD_REWARD, FIELD_TERMINAL, FIELD_T, FIELD_RNG, FIELD_FLAGS, FIELD_ACTION = range(8)
+
+
+class B200RLError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"b200rl status {status}: {msg}")
+        self.status = status
+
+
+class CartPoleParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("gravity", "masscart", "masspole", "totalmass", "halflength", "polemasslength",
+                                          "forcemag", "dt", "thetathreshold", "xthreshold")] + [("max_steps", C.c_int64)]
+
+
+class PendulumParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("max_speed", "max_torque", "g", "m", "l", "dt")] + [
+        ("max_steps", C.c_int64), ("n_actions", C.c_int64), ("continuous", C.c_int32)]
+
+
+class MountainCarParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("min_pos", "max_pos", "max_speed", "goal_pos", "goal_velocity", "power", "gravity")] + [
+        ("max_steps", C.c_int64)]
+
+
+_vp, _i32, _i64, _u64, _f32, _f64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_double, C.c_size_t
+_pp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes).  Must list every symbol include/b200rl.h declares
+# (tests/test_abi.py checks header <-> table <-> exported symbols).
+SIGNATURES = {
+    "b200rl_init": (_i32, [_i32, _pp]),
+    "b200rl_destroy": (None, [_vp]),
+    "b200rl_last_error": (C.c_char_p, []),
+    "b200rl_sync": (_i32, [_vp]),
+    "b200rl_abi_version": (_i32, []),
+    "b200rl_stream": (_i32, [_vp, _pp]),
+    "b200rl_timer_start": (_i32, [_vp]),
+    "b200rl_timer_stop_ms": (_i32, [_vp, C.POINTER(_f32)]),
+    "b200rl_malloc": (_i32, [_vp, _sz, _pp]),
+    "b200rl_free": (_i32, [_vp, _vp]),
+    "b200rl_host_alloc": (_i32, [_vp, _sz, _pp]),
+    "b200rl_host_free": (_i32, [_vp, _vp]),
+    "b200rl_memcpy_h2d": (_i32, [_vp, _vp, _vp, _sz, _i32]),
+    "b200rl_memcpy_d2h": (_i32, [_vp, _vp, _vp, _sz, _i32]),
+    "b200rl_memset": (_i32, [_vp, _vp, _i32, _sz]),
+    "b200rl_flush_l2": (_i32, [_vp]),
+    "b200rl_launch_count": (_i32, [_vp, C.POINTER(_u64)]),
+    "b200rl_env_create": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _pp]),
+    "b200rl_env_destroy": (_i32, [_vp]),
+    "b200rl_env_copy": (_i32, [_vp, _pp]),
+    "b200rl_env_seed": (_i32, [_vp, _vp]),
+    "b200rl_env_reset": (_i32, [_vp, _i32]),
+    "b200rl_env_step": (_i32, [_vp, _vp, _i32, _i32]),
+    "b200rl_env_step_random": (_i32, [_vp, _i32]),
+    "b200rl_env_get": (_i32, [_vp, _i32, _vp, _sz]),
+    "b200rl_env_set": (_i32, [_vp, _i32, _vp, _sz]),
+    "b200rl_env_ptr": (_i32, [_vp, _i32, _pp]),
+    "b200rl_env_check": (_i32, [_vp]),
+    "b200rl_env_episode_stats": (_i32, [_vp, _vp, _i32]),
+    "b200rl_gae_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _f32, _i64, _i64, _i32, _i32]),
+    "b200rl_gae_f64": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _f64, _i64, _i64, _i32, _i32]),
+    "b200rl_discount_rewards_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _i64, _i32, _i32]),
+    "b200rl_discount_rewards_f64": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i32, _i32]),
+    "b200rl_discount_rewards_reduced_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _i64, _i32, _i32]),
+    "b200rl_discount_rewards_reduced_f64": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i32, _i32]),
+}
+
+_LIB = None
+
+
+def load():
+    """dlopen libb200rl.so and attach the signatures.  Loading needs no GPU; calling does."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(
+            f"{SO_PATH} is missing: build it with `python reinforcementlearning.jl_b200/build.py` "
+            "(there is no CPU fallback for the b200rl hot path)")
+    lib = C.CDLL(SO_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _LIB = lib
+    return lib
+
+
+def check(status):
+    if status != OK:
+        raise B200RLError(status, load().b200rl_last_error().decode(errors="replace"))
+
+
+def ptr(a):
+    """void* of a numpy array (None -> NULL) or pass an int device pointer through."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    if isinstance(a, C.c_void_p):
+        return a
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """b200rl_ctx: one device + one stream."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        check(self.lib.b200rl_init(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200rl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.lib.b200rl_sync(self.h))
+
+    def stream(self):
+        s = C.c_void_p()
+        check(self.lib.b200rl_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    def timer_start(self):
+        check(self.lib.b200rl_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        check(self.lib.b200rl_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        check(self.lib.b200rl_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def flush_l2(self):
+        check(self.lib.b200rl_flush_l2(self.h))
+
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        check(self.lib.b200rl_malloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, dptr):
+        check(self.lib.b200rl_free(self.h, C.c_void_p(dptr)))
+
+    def h2d(self, dptr, arr, async_=False):
+        arr = np.ascontiguousarray(arr)
+        check(self.lib.b200rl_memcpy_h2d(self.h, C.c_void_p(dptr), ptr(arr), arr.nbytes, int(async_)))
+
+    def d2h(self, arr, dptr, async_=False):
+        assert arr.flags.c_contiguous or arr.flags.f_contiguous
+        check(self.lib.b200rl_memcpy_d2h(self.h, ptr(arr), C.c_void_p(dptr), arr.nbytes, int(async_)))
+        return arr
+
+    def host_alloc(self, shape, dtype):
+        """Pinned host numpy array (freed with host_free)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        check(self.lib.b200rl_host_alloc(self.h, n, C.byref(p)))
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        return arr, p.value
+
+    def host_free(self, address):
+        check(self.lib.b200rl_host_free(self.h, C.c_void_p(address)))

@@ -1,0 +1,221 @@
+"""Host mirror of the reference's run loop, stages, hooks and stop conditions for a batched
+env (RLCore/src/core/run.jl:22-78, stages.jl:13-37, hooks.jl, stop_conditions.jl,
+reset_conditions.jl).  This is the control plane the Julia glue (julia/B200RL.jl) keeps in
+Julia; it is restated in Python only so the path can be driven and tested without Julia.
+
+Control flow = the historical ``_run(policy, env::MultiThreadEnv, ...)``: no
+episode stages, ``is_terminated(env)`` is a vector, finished sub-envs are soft-reset at the
+top of every iteration (or inside the step kernel when ``env.auto_reset``)."""
+import time
+
+import numpy as np
+
+# stages (stages.jl:13-28)
+PreExperimentStage, PostExperimentStage = "PreExperimentStage", "PostExperimentStage"
+PreEpisodeStage, PostEpisodeStage = "PreEpisodeStage", "PostEpisodeStage"
+PreActStage, PostActStage = "PreActStage", "PostActStage"
+
+
+class AbstractHook:
+    def push(self, stage, policy, env):  # Base.push!(hook, stage, policy, env) (hooks.jl:32-35)
+        pass
+
+    def __add__(self, other):  # ComposedHook via `+` (hooks.jl:54-56)
+        return ComposedHook(self, other)
+
+
+class EmptyHook(AbstractHook):
+    pass
+
+
+class ComposedHook(AbstractHook):
+    def __init__(self, *hooks):
+        self.hooks = hooks
+
+    def push(self, stage, policy, env):
+        for h in self.hooks:
+            h.push(stage, policy, env)
+
+
+class BatchStepsPerEpisode(AbstractHook):
+    """hooks.jl:202-231 — per-env episode lengths from the vector ``is_terminated(env)``."""
+
+    def __init__(self, batchsize):
+        self.steps = [[] for _ in range(batchsize)]
+        self.step = np.zeros(batchsize, dtype=np.int64)
+
+    def __getitem__(self, _):
+        return self.steps
+
+    def push(self, stage, policy, env):
+        if stage != PostActStage:
+            return
+        term = env.is_terminated()
+        self.step += 1
+        for i in np.nonzero(term)[0]:
+            self.steps[i].append(int(self.step[i]))
+            self.step[i] = 0
+
+
+class TotalBatchRewardPerEpisode(AbstractHook):
+    """Batched TotalRewardPerEpisode (hooks.jl:146-173): per-env running reward, pushed on termination."""
+
+    def __init__(self, batchsize):
+        self.rewards = [[] for _ in range(batchsize)]
+        self.reward = np.zeros(batchsize, dtype=np.float64)
+
+    def push(self, stage, policy, env):
+        if stage != PostActStage:
+            return
+        self.reward += env.reward()
+        for i in np.nonzero(env.is_terminated())[0]:
+            self.rewards[i].append(float(self.reward[i]))
+            self.reward[i] = 0.0
+
+
+class DeviceEpisodeStats(AbstractHook):
+    """Device-side reduction of the two hooks above: no per-step D2H copy; reads
+    four numbers at the end of the experiment."""
+
+    def __init__(self):
+        self.stats = None
+
+    def push(self, stage, policy, env):
+        if stage == PreExperimentStage:
+            env.episode_stats(reset=True)
+        elif stage == PostExperimentStage:
+            self.stats = env.episode_stats()
+
+
+class TimePerStep(AbstractHook):
+    """hooks.jl:243-262 (wall-clock per loop iteration)."""
+
+    def __init__(self, max_steps=100):
+        self.times = []
+        self.max_steps = max_steps
+        self.t = time.perf_counter()
+
+    def push(self, stage, policy, env):
+        if stage == PostActStage:
+            now = time.perf_counter()
+            self.times.append(now - self.t)
+            self.times = self.times[-self.max_steps:]
+            self.t = now
+
+
+class DoEveryNSteps(AbstractHook):
+    """hooks.jl:270-288."""
+
+    def __init__(self, f, n=1, t=0):
+        self.f, self.n, self.t = f, n, t
+
+    def push(self, stage, policy, env):
+        if stage == PostActStage:
+            self.t += 1
+            if self.t % self.n == 0:
+                self.f(self.t, policy, env)
+
+
+# ---- stop conditions (stop_conditions.jl) -------------------------------------------------
+class StopAfterNSteps:
+    """stop_conditions.jl:40-76: true on its n-th check (n loop iterations = n*N env-steps)."""
+
+    def __init__(self, step, cur=1):
+        self.step, self.cur = step, cur
+
+    def check(self, policy, env):
+        res = self.cur >= self.step
+        self.cur += 1
+        return res
+
+
+class StopAfterNEpisodes:
+    """stop_conditions.jl:82-118, batched: counts every finished sub-env episode."""
+
+    def __init__(self, episode, cur=0):
+        self.episode, self.cur = episode, cur
+
+    def check(self, policy, env):
+        self.cur += int(np.count_nonzero(env.is_terminated()))
+        return self.cur >= self.episode
+
+
+class StopAfterNSeconds:
+    """stop_conditions.jl:203-224."""
+
+    def __init__(self, budget):
+        self.deadline = time.time() + budget
+
+    def check(self, policy, env):
+        return time.time() > self.deadline
+
+
+class StopSignal:
+    """stop_conditions.jl:185-200."""
+
+    def __init__(self):
+        self.is_stop = False
+
+    def check(self, policy, env):
+        return self.is_stop
+
+
+# ---- policies -----------------------------------------------------------------------------
+class AbstractPolicy:
+    def plan(self, env):  # RLBase.plan!(policy, env)
+        raise NotImplementedError
+
+    def push(self, stage, env, action=None):  # Base.push!(policy, stage, env[, action])
+        pass
+
+    def optimise(self, stage):  # RLBase.optimise!(policy, stage)
+        pass
+
+
+class FusedAction:
+    """Token returned by a policy whose action selection is fused into the env kernel."""
+
+    def __init__(self, kind):
+        self.kind = kind
+
+
+class RandomPolicy(AbstractPolicy):
+    """RandomPolicy() with the reference default of sharing the env's RNG stream
+    (random_policy.jl:18-32): the draw happens inside the step kernel (K2)."""
+
+    def plan(self, env):
+        return FusedAction("random")
+
+
+def run(policy, env, stop_condition=None, hook=None):
+    """Base.run(policy, env, stop_condition, hook) for a B200VecEnv (run.jl:22-78 with the
+    MultiThreadEnv control flow).  Returns the hook."""
+    stop_condition = stop_condition or StopAfterNEpisodes(1)
+    hook = hook or EmptyHook()
+    hook.push(PreExperimentStage, policy, env)
+    policy.push(PreExperimentStage, env)
+    env.reset_(is_force=True)  # run.jl:46
+    is_stop = False
+    while not is_stop:
+        if not env.auto_reset:
+            env.reset_(is_force=False)  # soft reset of finished sub-envs
+        policy.push(PreActStage, env)
+        policy.optimise(PreActStage)
+        hook.push(PreActStage, policy, env)
+        action = policy.plan(env)
+        if isinstance(action, FusedAction):
+            if action.kind == "random":
+                env.act_random_()
+            else:
+                policy.act_fused(env)
+        else:
+            env.act_(action)
+        policy.push(PostActStage, env, action)
+        policy.optimise(PostActStage)
+        hook.push(PostActStage, policy, env)
+        if stop_condition.check(policy, env):
+            is_stop = True
+    policy.push(PostExperimentStage, env)
+    hook.push(PostExperimentStage, policy, env)
+    env.check()
+    return hook

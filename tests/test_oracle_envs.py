@@ -1,0 +1,144 @@
+"""Pin the oracle's env restatement: SURVEY Appendix C known answers (derived from the
+formulas at CartPoleEnv.jl:118-140), the reference's conformance properties
+(RLBase/src/base.jl:86-152: same-seed copies stay identical, states stay in state_space) and
+RNG-consumption rules (Appendix A.4).  The reference itself has no golden trajectories."""
+import numpy as np
+
+import oracle_lib as O
+
+
+def _fresh(kind, n, dtype="f32", seed=1, **kw):
+    return O.OracleVecEnv(kind, n, O.splitmix_states_fast(n, seed), dtype=dtype, **kw)
+
+
+def test_cartpole_f64_known_answers():
+    e = _fresh(O.KIND_CARTPOLE, 1, "f64")
+    e.set(O.F_STATE, np.zeros((1, 4)))
+    e.set(O.F_T, np.zeros(1, np.int32))
+    e.step([2])
+    assert e.get(O.F_STATE)[0].tolist() == [0.0, 0.1951219512195122, 0.0, -0.2926829268292683]
+    e.step([2]); e.step([2])
+    assert e.get(O.F_STATE)[0].tolist() == [0.011707317073170733, 0.585447355516259, -0.0175609756097561, -0.8798869825388553]
+    assert e.get(O.F_REWARD)[0] == 1.0 and e.get(O.F_TERMINAL)[0] == 0 and e.get(O.F_T)[0] == 3
+
+
+def test_cartpole_f32_known_answers_bits():
+    e = _fresh(O.KIND_CARTPOLE, 1)
+    e.set(O.F_STATE, np.zeros((1, 4), np.float32))
+    e.set(O.F_T, np.zeros(1, np.int32))
+    e.step([2])
+    assert e.get(O.F_STATE)[0].view(np.uint32).tolist() == [0x00000000, 0x3E47CE0C, 0x00000000, 0xBE95DA89]
+    e.step([2]); e.step([2])
+    assert e.get(O.F_STATE)[0].view(np.uint32).tolist() == [0x3C3FD00B, 0x3F15DFE0, 0xBC8FDC08, 0xBF614045]
+
+
+def test_cartpole_threshold_and_time_limit():
+    q = O.default_params(O.KIND_CARTPOLE, "f32")
+    assert q[8] == 0.20943951606750488  # Float32(12*pi/180)
+    # time limit: done at t = 201 (t > max_steps), reward of the terminating step is 0
+    e = _fresh(O.KIND_CARTPOLE, 1)
+    for k in range(1, 400):
+        e.set(O.F_STATE, np.zeros((1, 4), np.float32))  # keep it balanced
+        e.step([1 + (k % 2)])
+        if e.get(O.F_TERMINAL)[0]:
+            break
+    assert e.get(O.F_T)[0] == 201 and e.get(O.F_REWARD)[0] == 0.0
+
+
+def test_pendulum_mountaincar_time_limit_is_geq():
+    for kind, act in ((O.KIND_PENDULUM, np.float32(0.0)), (O.KIND_MOUNTAINCAR, 2)):
+        e = _fresh(kind, 1)
+        n = 0
+        while not e.get(O.F_TERMINAL)[0]:
+            e.step([act]); n += 1
+            assert n <= 200
+        assert e.get(O.F_T)[0] == 200 or kind == O.KIND_MOUNTAINCAR
+
+
+def test_reset_consumes_rng_like_reference():
+    """CartPole reset! = rand(rng,T,4) [2 u64 for Float32, 4 for Float64] + rand(OneTo(2)) [1 u64]."""
+    L = O.lib()
+    for dtype, ndraws in (("f32", 3), ("f64", 5)):
+        seeds = O.splitmix_states_fast(1, 7)
+        e = O.OracleVecEnv(O.KIND_CARTPOLE, 1, seeds, dtype=dtype)  # constructor resets once
+        s = seeds[0].copy()
+        for _ in range(ndraws):
+            L.orc_rng_next(O._p(s))
+        assert np.array_equal(e.get(O.F_RNG)[0], s)
+        st = e.get(O.F_STATE)[0]
+        assert np.all(st >= -0.05) and np.all(st < 0.05)
+    # Pendulum: 2 draws, theta in [-2pi, 0), thetadot in [-2, 0); MountainCar: 1 draw, x in [-0.6,-0.4)
+    e = _fresh(O.KIND_PENDULUM, 64)
+    st = e.get(O.F_STATE)
+    assert np.all(st[:, 0] >= -2 * np.pi - 1e-6) and np.all(st[:, 0] <= 0) and np.all(st[:, 1] >= -2) and np.all(st[:, 1] <= 0)
+    e = _fresh(O.KIND_MOUNTAINCAR, 64)
+    st = e.get(O.F_STATE)
+    assert np.all(st[:, 0] >= -0.6 - 1e-7) and np.all(st[:, 0] < -0.4) and np.all(st[:, 1] == 0)
+
+
+def test_rand_oneto_is_top_bit_for_n2_and_uniform_for_n3():
+    L = O.lib()
+    s = O.splitmix_states_fast(1, 11)[0].copy()
+    s2 = s.copy()
+    for _ in range(200):
+        u = L.orc_rng_next(O._p(s))
+        a = L.orc_rng_oneto(O._p(s2), 2)
+        assert a == (u >> 63) + 1
+    counts = np.zeros(4, int)
+    for _ in range(3000):
+        counts[L.orc_rng_oneto(O._p(s), 3)] += 1
+    assert counts[0] == 0 and counts[1:].min() > 850
+
+
+def test_same_seed_copies_stay_identical_and_in_space():
+    """RLBase.test_interfaces! determinism + state in state_space (base.jl:86-152), 1000 random steps (test_runnable!)."""
+    for kind in (O.KIND_CARTPOLE, O.KIND_MOUNTAINCAR):
+        a, b = _fresh(kind, 8, seed=888), _fresh(kind, 8, seed=888)
+        for _ in range(1000):
+            a.step_random(auto_reset=True); b.step_random(auto_reset=True)
+            assert np.array_equal(a.get(O.F_STATE), b.get(O.F_STATE))
+        st = a.get(O.F_STATE)
+        if kind == O.KIND_CARTPOLE:
+            assert np.all(np.abs(st[:, 0]) <= 4.8) and np.all(np.abs(st[:, 2]) <= 2 * 0.20943951606750488)
+        else:
+            assert np.all(st[:, 0] >= np.float32(-1.2)) and np.all(st[:, 0] <= np.float32(0.6)) and np.all(np.abs(st[:, 1]) <= np.float32(0.07))
+
+
+def test_soft_reset_and_auto_reset_agree():
+    """Fused auto-reset == step, then soft reset at the top of the next iteration (same RNG order)."""
+    n = 32
+    a, b = _fresh(O.KIND_CARTPOLE, n, seed=5), _fresh(O.KIND_CARTPOLE, n, seed=5)
+    rng = np.random.default_rng(0)
+    for _ in range(400):
+        act = rng.integers(1, 3, n)
+        a.step(act, auto_reset=True)
+        b.reset(force=False)
+        b.step(act, auto_reset=False)
+        assert np.array_equal(a.get(O.F_REWARD), b.get(O.F_REWARD))
+        assert np.array_equal(a.get(O.F_TERMINAL), b.get(O.F_TERMINAL))
+    b.reset(force=False)
+    assert np.array_equal(a.get(O.F_STATE), b.get(O.F_STATE))
+    assert np.array_equal(a.get(O.F_RNG), b.get(O.F_RNG))
+
+
+def test_pendulum_reward_and_obs_formulas():
+    e = _fresh(O.KIND_PENDULUM, 16, seed=3)
+    st0 = e.get(O.F_STATE).astype(np.float64)
+    act = np.linspace(-2, 2, 16).astype(np.float32)
+    e.step(act)
+    th, thd = st0[:, 0], st0[:, 1]
+    an = np.mod(np.float32(th.astype(np.float32) + np.float32(np.pi)).astype(np.float64), 2 * np.pi) - np.pi
+    cost = an ** 2 + 0.1 * thd ** 2 + 0.001 * act.astype(np.float64) ** 2
+    np.testing.assert_allclose(e.get(O.F_REWARD), -cost, rtol=1e-6, atol=1e-6)
+    st = e.get(O.F_STATE).astype(np.float64)
+    obs = e.get(O.F_OBS)
+    np.testing.assert_allclose(obs[:, 0], np.sin(st[:, 0]), atol=1e-6)
+    np.testing.assert_allclose(obs[:, 1], np.cos(st[:, 0]), atol=1e-6)
+    assert np.array_equal(obs[:, 2], e.get(O.F_STATE)[:, 1])
+
+
+def test_invalid_actions_are_rejected():
+    e = _fresh(O.KIND_CARTPOLE, 4)
+    assert e.step([1, 2, 3, 0]) == 2
+    p = _fresh(O.KIND_PENDULUM, 2)
+    assert p.step(np.array([2.5, np.nan], np.float32)) == 2
