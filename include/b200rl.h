@@ -168,6 +168,119 @@ int b200rl_discount_rewards_reduced_f64(b200rl_ctx* ctx, double* out, const doub
                                         const uint8_t* terminal, const double* init, double gamma,
                                         int64_t R, int64_t C, int dims, int on_device);
 
+/* ---------------------------------------------------------------- trajectory ------- */
+/* Device-resident CircularArraySARTSTraces (+ CircularPrioritizedTraces) with a BatchSampler
+ * (ReinforcementLearningTrajectories 0.4, external to the reference tree; call sites
+ * RLCore/src/policies/agent/agent_base.jl:45-59, agent_srt_cache.jl:30-50; layout
+ * docs/src/How_to_implement_a_new_algorithm.md:84-112).  A ring of capacity+1 frames, each
+ * frame holding `lanes` sub-envs (lanes = 1 is the reference's single stream).  sampler_rng:
+ * (4, batch_size) uint64 host array, one Xoshiro stream per batch slot. */
+int b200rl_traj_create(b200rl_ctx* ctx, int ns, int64_t lanes, int64_t capacity, int prioritized, float default_priority,
+                       const uint64_t* sampler_rng, int64_t batch_size, b200rl_traj** out);
+int b200rl_traj_destroy(b200rl_traj* traj);
+/* length(trajectory.container) in frames (x lanes transitions): 0 after the first state, 1 after
+ * the first transition (RLCore/test/policies/agent.jl:27-34) */
+int b200rl_traj_length(b200rl_traj* traj, int64_t* frames_out);
+/* push!(trajectory, (state = s0,))  — agent_base.jl:45-47.  obs: (ns, lanes) */
+int b200rl_traj_push_state(b200rl_traj* traj, const float* obs, int on_device);
+/* push!(trajectory, (state = s', action, reward, terminal)) — agent_base.jl:56-59 */
+int b200rl_traj_push(b200rl_traj* traj, const int32_t* action, const float* reward, const uint8_t* terminal, const float* next_obs,
+                     int on_device);
+/* the same, reading the env's device fields directly (no host round trip) */
+int b200rl_traj_push_env(b200rl_traj* traj, b200rl_env* env, int first_state_only);
+/* sample(trajectory): with replacement, uniform or proportional to priority (sum-tree descent);
+ * the batch (state, action, reward, terminal, next_state, key, priority, weight) stays on device.
+ * beta: importance-weight exponent, w = (n p / total)^-beta / max w */
+int b200rl_traj_sample(b200rl_traj* traj, float beta);
+/* field: 0 state (ns,B) | 1 action (B) i32 | 2 reward | 3 terminal u8 | 4 next_state | 5 key i64 |
+ * 6 priority | 7 weight | 8 sampler rng (4,B) u64 */
+int b200rl_traj_batch_get(b200rl_traj* traj, int field, void* host_dst, size_t bytes);
+/* priority write-back for the keys of the last sampled batch (trajectory[:priority, keys] = p) */
+int b200rl_traj_update_priority(b200rl_traj* traj, const float* priority, int on_device);
+int b200rl_traj_total_priority(b200rl_traj* traj, float* out);
+
+/* ---------------------------------------------------------------- networks --------- */
+/* kind 0: ActorCritic(actor -> n_out logits, critic -> 1)   (RLCore/src/utils/networks.jl:15-20, 405-432)
+ * kind 1: ActorCritic(GaussianNetwork mu/sigma heads, 1-d action; sigma = clamp(softplus(raw)))  (networks.jl:44-116)
+ * kind 2: Q-network n_in -> hidden -> hidden -> n_out with a TargetNetwork copy (target_network.jl:27-88)
+ * Trunks are Dense(n_in,hidden,act) -> Dense(hidden,hidden,act); act 0 relu, 1 tanh; hidden 64|128.
+ * Parameters are one flat fp32 vector in Flux.destructure order (weights (out,in) column-major). */
+typedef struct { int32_t n_in, hidden, act, n_out, kind; } b200rl_net_desc;
+int b200rl_net_nparams(const b200rl_net_desc* desc, int64_t* out);
+/* FluxApproximator(model, Adam) (RLCore/src/policies/learners/flux_approximator.jl:11-46) */
+int b200rl_net_create(b200rl_ctx* ctx, const b200rl_net_desc* desc, const float* params_host, b200rl_net** out);
+int b200rl_net_destroy(b200rl_net* net);
+int b200rl_net_configure_optimizer(b200rl_net* net, float lr, float beta1, float beta2, float eps, float max_grad_norm);
+/* export / import (checkpoint hooks, docs/src/How_to_use_hooks.md:124-167).
+ * which: 0 params | 1 last gradient | 2 Adam m | 3 Adam v | 4 beta^t (2) | 5 target params */
+int b200rl_net_get(b200rl_net* net, int which, float* host_dst, int64_t count);
+int b200rl_net_set(b200rl_net* net, int which, const float* host_src, int64_t count);
+int b200rl_net_ptr(b200rl_net* net, int which, void** dptr_out);
+/* optimise!(::TargetNetwork): target = rho*target + (1-rho)*model (target_network.jl:70-88) */
+int b200rl_net_target_sync(b200rl_net* net, float rho);
+/* plan!(policy, obs batch): obs (n_in, N); rng_dev (4, N) uint64 DEVICE streams (advanced);
+ * action int32 1-based (kind 0) or float (kind 1), log-prob, V(s), raw head outputs (n_head, N).
+ * Outputs may be NULL; on_device applies to obs and outputs. */
+int b200rl_net_act(b200rl_net* net, const float* obs, int64_t n, uint64_t* rng_dev, void* action_out, float* logp_out, float* value_out,
+                   float* heads_out, int on_device);
+/* critic V(s) -> (N) for kinds 0/1, Q(s, .) -> (n_out, N) for kind 2 */
+int b200rl_net_values(b200rl_net* net, const float* obs, int64_t n, float* out, int use_target, int on_device);
+/* QBasedPolicy + EpsilonGreedyExplorer (q_based_policy.jl:13-49, explorers/epsilon_greedy_explorer.jl:69-131); DEVICE pointers */
+int b200rl_net_q_act(b200rl_net* net, const float* obs_dev, int64_t n, uint64_t* rng_dev, float epsilon, int32_t* action_out_dev);
+
+/* ---------------------------------------------------------------- on-policy agent -- */
+/* PPO (clipped surrogate) / A2C hyper-parameters; defaults of the in-tree example
+ * docs/homepage/blog/a_practical_introduction_to_RL.jl/index.html:15238-15286:
+ * gamma .99 lambda .95 clip .1 max_grad_norm .5 w 1/.5/.001 Adam(1e-3) update_freq 32 epochs 4 microbatches 4 */
+typedef struct {
+    float gamma, lambda, clip_range, max_grad_norm, w_actor, w_critic, w_entropy;
+    float lr, beta1, beta2, eps;
+    float min_sigma, max_sigma;
+    int32_t normalize_advantage, n_epochs, n_microbatches, update_freq;
+    int32_t algo;   /* 0 PPO, 1 A2C (GAE advantage, discounted-gain critic target) */
+} b200rl_onpolicy_config;
+typedef struct b200rl_onpolicy b200rl_onpolicy;
+/* one optimiser step on explicit HOST minibatch arrays (generic / test entry).
+ * losses_out[6] = actor_loss, critic_loss, entropy, loss, grad_norm, 0 */
+int b200rl_net_ac_step(b200rl_net* net, const b200rl_onpolicy_config* cfg, const float* states, const void* actions,
+                       const float* logp_old, const float* adv, const float* ret, int64_t total, const int32_t* idx, int64_t batch,
+                       float adv_mean, float adv_inv_std, int apply_update, float* losses_out);
+/* Agent(PPOPolicy | A2CPolicy, PPOTrajectory): rollout tensors (N, T) on the device */
+int b200rl_onpolicy_create(b200rl_ctx* ctx, b200rl_net* net, b200rl_env* env, const b200rl_onpolicy_config* cfg,
+                           const uint64_t* policy_rng, b200rl_onpolicy** out);
+int b200rl_onpolicy_destroy(b200rl_onpolicy* agent);
+/* plan!(agent, env)  (agent_base.jl:52-54): actions_host (N) may be NULL */
+int b200rl_onpolicy_plan(b200rl_onpolicy* agent, void* actions_host);
+/* act!(env, planned action) without leaving the device */
+int b200rl_onpolicy_act(b200rl_onpolicy* agent);
+/* push!(agent, PostActStage, env, action)  (agent_base.jl:56-59) */
+int b200rl_onpolicy_push(b200rl_onpolicy* agent);
+int b200rl_onpolicy_collect(b200rl_onpolicy* agent, int n_steps);
+int b200rl_onpolicy_fill(b200rl_onpolicy* agent, int* t_out, int* T_out);
+/* optimise!(agent): GAE + n_epochs x n_microbatches optimiser steps; see algo.cu */
+int b200rl_onpolicy_update(b200rl_onpolicy* agent, const int32_t* perm_host, float* stats_host);
+/* field: 0 state (ns,N,T+1) | 1 action | 2 logp | 3 reward | 4 terminal u8 | 5 value (N,T+1) |
+ * 6 advantage | 7 return | 8 policy rng (4,N) u64 | 9 {adv mean, inv std} */
+int b200rl_onpolicy_get(b200rl_onpolicy* agent, int field, void* host_dst, size_t bytes);
+
+/* ---------------------------------------------------------------- DQN -------------- */
+typedef struct {
+    float gamma, lr, beta1, beta2, eps, max_grad_norm, rho;
+    float per_alpha, per_beta, per_eps;
+    int32_t huber, double_dqn, target_update_freq;
+} b200rl_dqn_config;
+/* optimise!(DQNLearner / PrioritizedDQNLearner): sample, TD loss + backward, clip + Adam,
+ * priority write-back, target sync.  stats_host[4] = loss, grad_norm, mean|td|, n_updates (NULL: async) */
+int b200rl_dqn_update(b200rl_net* net, b200rl_traj* traj, const b200rl_dqn_config* cfg, float* stats_host);
+int b200rl_dqn_last_td(b200rl_net* net, b200rl_traj* traj, float* host_dst, int64_t count);
+
+/* ---------------------------------------------------------------- multi-GPU -------- */
+/* env-index data parallelism: one process per GPU, one sum all-reduce of the flat gradient per
+ * optimiser step over NCCL / NVLink.  rank 0 makes the 128-byte id. */
+int b200rl_comm_unique_id(void* id128_out);
+int b200rl_comm_init(b200rl_ctx* ctx, int nranks, int rank, const void* id128);
+int b200rl_comm_allreduce_f32(b200rl_ctx* ctx, float* dev_buf, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

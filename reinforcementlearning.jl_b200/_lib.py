@@ -34,6 +34,21 @@ class PendulumParams(C.Structure):
         ("max_steps", C.c_int64), ("n_actions", C.c_int64), ("continuous", C.c_int32)]
 
 
+class NetDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_in", "hidden", "act", "n_out", "kind")]
+
+
+class OnPolicyConfig(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("gamma", "lambda_", "clip_range", "max_grad_norm", "w_actor", "w_critic", "w_entropy", "lr",
+                                         "beta1", "beta2", "eps", "min_sigma", "max_sigma")] + [
+        (n, C.c_int32) for n in ("normalize_advantage", "n_epochs", "n_microbatches", "update_freq", "algo")]
+
+
+class DQNConfig(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("gamma", "lr", "beta1", "beta2", "eps", "max_grad_norm", "rho", "per_alpha", "per_beta",
+                                         "per_eps")] + [(n, C.c_int32) for n in ("huber", "double_dqn", "target_update_freq")]
+
+
 class MountainCarParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("min_pos", "max_pos", "max_speed", "goal_pos", "goal_velocity", "power", "gravity")] + [
         ("max_steps", C.c_int64)]
@@ -80,6 +95,42 @@ SIGNATURES = {
     "b200rl_discount_rewards_f64": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i32, _i32]),
     "b200rl_discount_rewards_reduced_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _i64, _i32, _i32]),
     "b200rl_discount_rewards_reduced_f64": (_i32, [_vp, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i32, _i32]),
+    "b200rl_traj_create": (_i32, [_vp, _i32, _i64, _i64, _i32, _f32, _vp, _i64, _pp]),
+    "b200rl_traj_destroy": (_i32, [_vp]),
+    "b200rl_traj_length": (_i32, [_vp, C.POINTER(_i64)]),
+    "b200rl_traj_push_state": (_i32, [_vp, _vp, _i32]),
+    "b200rl_traj_push": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32]),
+    "b200rl_traj_push_env": (_i32, [_vp, _vp, _i32]),
+    "b200rl_traj_sample": (_i32, [_vp, _f32]),
+    "b200rl_traj_batch_get": (_i32, [_vp, _i32, _vp, _sz]),
+    "b200rl_traj_update_priority": (_i32, [_vp, _vp, _i32]),
+    "b200rl_traj_total_priority": (_i32, [_vp, C.POINTER(_f32)]),
+    "b200rl_net_nparams": (_i32, [_vp, C.POINTER(_i64)]),
+    "b200rl_net_create": (_i32, [_vp, _vp, _vp, _pp]),
+    "b200rl_net_destroy": (_i32, [_vp]),
+    "b200rl_net_configure_optimizer": (_i32, [_vp, _f32, _f32, _f32, _f32, _f32]),
+    "b200rl_net_get": (_i32, [_vp, _i32, _vp, _i64]),
+    "b200rl_net_set": (_i32, [_vp, _i32, _vp, _i64]),
+    "b200rl_net_ptr": (_i32, [_vp, _i32, _pp]),
+    "b200rl_net_target_sync": (_i32, [_vp, _f32]),
+    "b200rl_net_act": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "b200rl_net_values": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32]),
+    "b200rl_net_q_act": (_i32, [_vp, _vp, _i64, _vp, _f32, _vp]),
+    "b200rl_net_ac_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _f32, _f32, _i32, _vp]),
+    "b200rl_onpolicy_create": (_i32, [_vp, _vp, _vp, _vp, _vp, _pp]),
+    "b200rl_onpolicy_destroy": (_i32, [_vp]),
+    "b200rl_onpolicy_plan": (_i32, [_vp, _vp]),
+    "b200rl_onpolicy_act": (_i32, [_vp]),
+    "b200rl_onpolicy_push": (_i32, [_vp]),
+    "b200rl_onpolicy_collect": (_i32, [_vp, _i32]),
+    "b200rl_onpolicy_fill": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
+    "b200rl_onpolicy_update": (_i32, [_vp, _vp, _vp]),
+    "b200rl_onpolicy_get": (_i32, [_vp, _i32, _vp, _sz]),
+    "b200rl_dqn_update": (_i32, [_vp, _vp, _vp, _vp]),
+    "b200rl_dqn_last_td": (_i32, [_vp, _vp, _vp, _i64]),
+    "b200rl_comm_unique_id": (_i32, [_vp]),
+    "b200rl_comm_init": (_i32, [_vp, _i32, _i32, _vp]),
+    "b200rl_comm_allreduce_f32": (_i32, [_vp, _vp, _i64]),
 }
 
 _LIB = None

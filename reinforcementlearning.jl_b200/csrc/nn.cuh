@@ -1,0 +1,62 @@
+// nn.cuh — shared declarations of the learner kernels (nn.cu) for algo.cu.
+//
+// Network = Dense(in,H,act) -> Dense(H,H,act) -> head(s); parameters flat in
+// Flux.destructure order, weights (out,in) column-major (W[o + out*i]):
+//   W1 (H x in), b1 (H), W2 (H x H), b2 (H), then
+//   single head:     W3 (n_out x H), b3 (n_out)                      [categorical logits / value / Q]
+//   gaussian heads:  Wmu (1 x H), bmu (1), Wsig (1 x H), bsig (1)    [GaussianNetwork mu / sigma, 1-d action]
+// (ActorCritic RLCore/src/utils/networks.jl:15-20, GaussianNetwork :44-116.)
+#pragma once
+#include "common.cuh"
+
+constexpr int kInMax = 4;    // observation width <= 4 (CartPole 4, Pendulum 3, MountainCar 2)
+constexpr int kOutMax = 4;   // head width <= 4
+
+enum { B200RL_ACT_RELU = 0, B200RL_ACT_TANH = 1 };
+
+struct MlpDesc {
+    int in, H, act, nout, heads2;  // heads2: two 1-wide heads (gaussian mu / sigma)
+    __host__ __device__ int64_t nparams() const { return (int64_t)H * in + H + (int64_t)H * H + H + (int64_t)nout * H + nout; }
+};
+
+struct AcHyper {  // scalars of the actor-critic losses
+    float clip_range, w_actor, w_critic, w_entropy, min_sigma, max_sigma;
+    int normalize_adv;
+    int algo;  // 0 PPO clipped surrogate, 1 A2C (logp * advantage)
+};
+
+// One minibatch of the on-policy update: sample j is flat index perm(j) into the rollout
+// arrays (states (ns, total) column-major; actions / logp_old / adv / ret (total)).
+struct AcBatch {
+    const float* states; int ns;
+    const void* actions;        // int32 (1-based) or float
+    const float* logp_old; const float* adv; const float* ret;
+    const int32_t* idx;         // explicit permutation slice, or null ->
+    uint32_t perm_n, perm_key, perm_offset;  // ... Feistel permutation of [0, perm_n), slice start
+    int64_t B;                  // samples in this minibatch (local)
+    float inv_B;                // 1 / (global minibatch size)  — gradients are sums * inv_B
+    const float* norm2;         // device {mean, inv_std} for advantage normalisation
+};
+
+int nn_grid_ctas(b200rl_ctx* ctx, int H);  // persistent CTAs per role
+int nn_dqn_max_partials(b200rl_ctx* ctx, int H);
+// forward (rollout inference).  obs (in, N) column-major.  Any output may be null.
+int nn_policy_act(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
+                  const float* obs, int64_t N, unsigned long long* rng, void* action_out, float* logp_out, float* value_out,
+                  float* head_out /* (nout, N) raw head outputs, for tests */, float* state_copy /* (in, N) */);
+int nn_mlp_forward(b200rl_ctx* ctx, const MlpDesc& net, const float* params, const float* obs, int64_t N, float* out /* (nout, N) */);
+// loss + backward: writes per-CTA partial gradients/losses; nn_reduce sums them in CTA order.
+int nn_ac_loss_grad(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
+                    const AcBatch& b, float* partial /* [ctas][np] */, float* loss_partial /* [2*ctas][4] */);
+int nn_reduce_partials(b200rl_ctx* ctx, const float* partial, int n_partials, int64_t np, float* grad, const float* loss_partial,
+                       int n_loss_partials, float* loss_out4);
+// clip_by_global_norm! + Optimisers Adam on a flat gradient (single CTA, deterministic)
+int nn_clip_adam(b200rl_ctx* ctx, float* params, float* grad, float* m, float* v, float* beta_t /* device [2] */, int64_t np,
+                 float max_grad_norm, float lr, float b1, float b2, float eps, float grad_scale, float* gnorm_out /* device */);
+int nn_target_sync(b200rl_ctx* ctx, float* target, const float* model, int64_t np, float rho);
+// DQN: TD loss + backward on a gathered batch (device arrays s (in,B), a, r, t, s2, w)
+int nn_dqn_loss_grad(b200rl_ctx* ctx, const MlpDesc& q, const float* params, const float* target, const float* s, const int32_t* a,
+                     const float* r, const uint8_t* t, const float* s2, const float* w, int64_t B, float inv_B, float gamma, int huber,
+                     int double_dqn, float* partial, float* loss_partial, float* td_out);
+int nn_q_act(b200rl_ctx* ctx, const MlpDesc& q, const float* params, const float* obs, int64_t N, unsigned long long* rng, float epsilon,
+             int32_t* action_out, float* q_out);

@@ -1,0 +1,295 @@
+"""Host mirror of the learner side: network handle (FluxApproximator + TargetNetwork,
+RLCore/src/policies/learners/flux_approximator.jl:11-46, target_network.jl:27-88), the
+on-policy agent (Agent + PPOPolicy/A2C, RLCore/src/policies/agent/agent_base.jl:18-66 and the
+absent RLZoo learners), the device trajectory (CircularArraySARTSTraces + samplers) and the
+DQN learner.  Thin ctypes calls only."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .core import AbstractPolicy, FusedAction, PostActStage
+
+ACT_RELU, ACT_TANH = 0, 1
+KIND_CATEGORICAL, KIND_GAUSSIAN, KIND_Q = 0, 1, 2
+NET_PARAMS, NET_GRAD, NET_M, NET_V, NET_BETA_T, NET_TARGET = range(6)
+
+
+def onpolicy_config(gamma=0.99, lambda_=0.95, clip_range=0.1, max_grad_norm=0.5, w_actor=1.0, w_critic=0.5, w_entropy=0.001,
+                    lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, min_sigma=0.0, max_sigma=float("inf"), normalize_advantage=True,
+                    n_epochs=4, n_microbatches=4, update_freq=32, algo="ppo"):
+    """Defaults = the in-tree PPO example (docs/homepage/blog/a_practical_introduction_to_RL.jl/index.html:15238-15286)."""
+    return L.OnPolicyConfig(gamma, lambda_, clip_range, max_grad_norm, w_actor, w_critic, w_entropy, lr, beta1, beta2, eps, min_sigma,
+                            max_sigma, int(normalize_advantage), n_epochs, n_microbatches, update_freq, {"ppo": 0, "a2c": 1}[algo])
+
+
+def dqn_config(gamma=0.99, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, max_grad_norm=0.0, rho=0.0, per_alpha=0.6, per_beta=0.4,
+               per_eps=1e-6, huber=True, double_dqn=False, target_update_freq=100):
+    return L.DQNConfig(gamma, lr, beta1, beta2, eps, max_grad_norm, rho, per_alpha, per_beta, per_eps, int(huber), int(double_dqn),
+                       target_update_freq)
+
+
+class Network:
+    """b200rl_net: parameters + Adam state (+ target copy) on the device."""
+
+    def __init__(self, ctx, n_in, hidden, n_out, params, act=ACT_RELU, kind=KIND_CATEGORICAL):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.desc = L.NetDesc(n_in, hidden, act, n_out, kind)
+        n = C.c_int64()
+        L.check(self.lib.b200rl_net_nparams(C.byref(self.desc), C.byref(n)))
+        self.nparams = n.value
+        params = np.ascontiguousarray(params, dtype=np.float32)
+        if params.size != self.nparams:
+            raise ValueError(f"expected {self.nparams} parameters, got {params.size}")
+        h = C.c_void_p()
+        L.check(self.lib.b200rl_net_create(ctx.h, C.byref(self.desc), L.ptr(params), C.byref(h)))
+        self.h = h
+        self.kind, self.n_in, self.n_out = kind, n_in, n_out
+
+    @staticmethod
+    def count_params(ctx, n_in, hidden, n_out, act=ACT_RELU, kind=KIND_CATEGORICAL):
+        d = L.NetDesc(n_in, hidden, act, n_out, kind)
+        n = C.c_int64()
+        L.check(ctx.lib.b200rl_net_nparams(C.byref(d), C.byref(n)))
+        return n.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200rl_net_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def configure_optimizer(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, max_grad_norm=0.5):
+        L.check(self.lib.b200rl_net_configure_optimizer(self.h, lr, beta1, beta2, eps, max_grad_norm))
+
+    def get(self, which=NET_PARAMS):
+        out = np.empty(2 if which == NET_BETA_T else self.nparams, np.float32)
+        L.check(self.lib.b200rl_net_get(self.h, which, L.ptr(out), out.size))
+        return out
+
+    def set(self, which, arr):
+        arr = np.ascontiguousarray(arr, np.float32)
+        L.check(self.lib.b200rl_net_set(self.h, which, L.ptr(arr), arr.size))
+
+    def device_ptr(self, which=NET_PARAMS):
+        p = C.c_void_p()
+        L.check(self.lib.b200rl_net_ptr(self.h, which, C.byref(p)))
+        return p.value
+
+    def target_sync(self, rho=0.0):
+        L.check(self.lib.b200rl_net_target_sync(self.h, rho))
+
+    def act(self, obs, rng_dev):
+        """obs (n_in, N) host array; rng_dev: device pointer to (4, N) policy streams."""
+        obs = np.asfortranarray(obs, np.float32)
+        n = obs.shape[1]
+        action = np.empty(n, np.float32 if self.kind == KIND_GAUSSIAN else np.int32)
+        logp = np.empty(n, np.float32); value = np.empty(n, np.float32)
+        nh = 2 if self.kind == KIND_GAUSSIAN else self.n_out
+        heads = np.empty((nh, n), np.float32, order="F")
+        L.check(self.lib.b200rl_net_act(self.h, L.ptr(obs), n, C.c_void_p(rng_dev), L.ptr(action), L.ptr(logp), L.ptr(value), L.ptr(heads), 0))
+        return dict(action=action, logp=logp, value=value, heads=heads)
+
+    def values(self, obs, use_target=False):
+        obs = np.asfortranarray(obs, np.float32)
+        n = obs.shape[1]
+        out = np.empty((self.n_out, n), np.float32, order="F") if self.kind == KIND_Q else np.empty(n, np.float32)
+        L.check(self.lib.b200rl_net_values(self.h, L.ptr(obs), n, L.ptr(out), int(use_target), 0))
+        return out
+
+    def ac_step(self, cfg, states, actions, logp_old, adv, ret, idx=None, adv_mean=0.0, adv_inv_std=1.0, apply_update=True):
+        states = np.asfortranarray(states, np.float32)
+        total = states.shape[1]
+        actions = np.ascontiguousarray(actions)
+        assert actions.dtype in (np.int32, np.float32)
+        idx = None if idx is None else np.ascontiguousarray(idx, np.int32)
+        losses = np.zeros(6, np.float32)
+        L.check(self.lib.b200rl_net_ac_step(
+            self.h, C.byref(cfg), L.ptr(states), L.ptr(actions), L.ptr(None if logp_old is None else np.ascontiguousarray(logp_old, np.float32)),
+            L.ptr(np.ascontiguousarray(adv, np.float32)), L.ptr(np.ascontiguousarray(ret, np.float32)), total, L.ptr(idx),
+            0 if idx is None else idx.size, adv_mean, adv_inv_std, int(apply_update), L.ptr(losses)))
+        return dict(actor_loss=losses[0], critic_loss=losses[1], entropy=losses[2], loss=losses[3], grad_norm=losses[4])
+
+
+ROLL_STATE, ROLL_ACTION, ROLL_LOGP, ROLL_REWARD, ROLL_TERMINAL, ROLL_VALUE, ROLL_ADV, ROLL_RET, ROLL_RNG, ROLL_NORM = range(10)
+
+
+class OnPolicyAgent(AbstractPolicy):
+    """Agent(policy = PPOPolicy | A2CPolicy, trajectory = PPOTrajectory) on the device.
+
+    Two ways to drive it: the reference's stage protocol (``plan`` returns host actions, the run
+    loop calls ``env.act_``, ``push`` / ``optimise`` follow — host buffers every step), or the fused
+    path (``collect(n)`` / ``update()``), where actions never leave the device."""
+
+    def __init__(self, ctx, net, env, cfg, policy_rng, host_actions=True):
+        self.ctx, self.lib, self.net, self.env, self.cfg = ctx, ctx.lib, net, env, cfg
+        self.n, self.T = env.n, cfg.update_freq
+        self.host_actions = host_actions
+        policy_rng = np.ascontiguousarray(policy_rng, np.uint64).reshape(self.n, 4)
+        h = C.c_void_p()
+        L.check(self.lib.b200rl_onpolicy_create(ctx.h, net.h, env.h, C.byref(cfg), L.ptr(policy_rng), C.byref(h)))
+        self.h = h
+        self.continuous = env.continuous
+        self._act_buf = np.empty(self.n, np.float32 if self.continuous else np.int32)
+        self.last_stats = None
+        self.n_updates = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200rl_onpolicy_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- stage protocol (run.jl:52-68) -------------------------------------------------------
+    def plan(self, env):
+        if self.host_actions:
+            L.check(self.lib.b200rl_onpolicy_plan(self.h, L.ptr(self._act_buf)))
+            if self.continuous:
+                return np.clip(self._act_buf, -2.0, 2.0)  # the env asserts a in -2.0..2.0
+            return self._act_buf
+        L.check(self.lib.b200rl_onpolicy_plan(self.h, None))
+        return FusedAction("policy")
+
+    def act_fused(self, env):
+        L.check(self.lib.b200rl_onpolicy_act(self.h))
+
+    def push(self, stage, env, action=None):
+        if stage == PostActStage:
+            L.check(self.lib.b200rl_onpolicy_push(self.h))
+
+    def optimise(self, stage):
+        if stage == PostActStage and self.fill()[0] == self.T:
+            self.update()
+
+    # ---- fused path --------------------------------------------------------------------------
+    def collect(self, n_steps):
+        L.check(self.lib.b200rl_onpolicy_collect(self.h, n_steps))
+
+    def fill(self):
+        t, T = C.c_int(), C.c_int()
+        L.check(self.lib.b200rl_onpolicy_fill(self.h, C.byref(t), C.byref(T)))
+        return t.value, T.value
+
+    def update(self, perm=None, want_stats=False):
+        rows = self.cfg.n_epochs * self.cfg.n_microbatches
+        stats = np.zeros((rows, 6), np.float32) if want_stats else None
+        if perm is not None:
+            perm = np.ascontiguousarray(perm, np.int32)
+            assert perm.shape == (self.cfg.n_epochs, self.n * self.T)
+        L.check(self.lib.b200rl_onpolicy_update(self.h, L.ptr(perm), L.ptr(stats)))
+        self.n_updates += 1
+        self.last_stats = stats
+        return stats
+
+    def rollout(self, field):
+        n, T, ns = self.n, self.T, self.net.n_in
+        spec = {
+            ROLL_STATE: ((ns, n, T + 1), np.float32), ROLL_ACTION: ((n, T), np.float32 if self.continuous else np.int32),
+            ROLL_LOGP: ((n, T), np.float32), ROLL_REWARD: ((n, T), np.float32), ROLL_TERMINAL: ((n, T), np.uint8),
+            ROLL_VALUE: ((n, T + 1), np.float32), ROLL_ADV: ((n, T), np.float32), ROLL_RET: ((n, T), np.float32),
+            ROLL_RNG: ((4, n), np.uint64), ROLL_NORM: ((2,), np.float32),
+        }[field]
+        out = np.empty(spec[0], dtype=spec[1], order="F")
+        L.check(self.lib.b200rl_onpolicy_get(self.h, field, L.ptr(out), out.nbytes))
+        return out
+
+
+BATCH_STATE, BATCH_ACTION, BATCH_REWARD, BATCH_TERMINAL, BATCH_NEXT_STATE, BATCH_KEY, BATCH_PRIORITY, BATCH_WEIGHT, BATCH_RNG = range(9)
+
+
+class Trajectory:
+    """Trajectory(container = CircularArraySARTSTraces(capacity) [+ CircularPrioritizedTraces],
+    sampler = BatchSampler(batch_size)) resident on the device."""
+
+    def __init__(self, ctx, ns, capacity, lanes=1, batch_size=0, sampler_rng=None, prioritized=False, default_priority=1.0):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.ns, self.lanes, self.capacity, self.batch_size, self.prioritized = ns, lanes, capacity, batch_size, prioritized
+        if batch_size:
+            sampler_rng = np.ascontiguousarray(sampler_rng, np.uint64).reshape(batch_size, 4)
+        h = C.c_void_p()
+        L.check(self.lib.b200rl_traj_create(ctx.h, ns, lanes, capacity, int(prioritized), default_priority, L.ptr(sampler_rng), batch_size, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200rl_traj_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        n = C.c_int64()
+        L.check(self.lib.b200rl_traj_length(self.h, C.byref(n)))
+        return n.value
+
+    def push_state(self, obs):
+        obs = np.asfortranarray(obs, np.float32)
+        L.check(self.lib.b200rl_traj_push_state(self.h, L.ptr(obs), 0))
+
+    def push(self, action, reward, terminal, next_obs):
+        L.check(self.lib.b200rl_traj_push(self.h, L.ptr(np.ascontiguousarray(action, np.int32)), L.ptr(np.ascontiguousarray(reward, np.float32)),
+                                          L.ptr(np.ascontiguousarray(terminal, np.uint8)), L.ptr(np.asfortranarray(next_obs, np.float32)), 0))
+
+    def push_env(self, env, first_state_only=False):
+        L.check(self.lib.b200rl_traj_push_env(self.h, env.h, int(first_state_only)))
+
+    def sample(self, beta=0.4, fetch=True):
+        L.check(self.lib.b200rl_traj_sample(self.h, beta))
+        return self.batch() if fetch else None
+
+    def batch(self):
+        B, ns = self.batch_size, self.ns
+        spec = {"state": (BATCH_STATE, (ns, B), np.float32), "action": (BATCH_ACTION, (B,), np.int32), "reward": (BATCH_REWARD, (B,), np.float32),
+                "terminal": (BATCH_TERMINAL, (B,), np.uint8), "next_state": (BATCH_NEXT_STATE, (ns, B), np.float32),
+                "key": (BATCH_KEY, (B,), np.int64), "priority": (BATCH_PRIORITY, (B,), np.float32), "weight": (BATCH_WEIGHT, (B,), np.float32)}
+        out = {}
+        for k, (f, shape, dt) in spec.items():
+            a = np.empty(shape, dt, order="F")
+            L.check(self.lib.b200rl_traj_batch_get(self.h, f, L.ptr(a), a.nbytes))
+            out[k] = a
+        return out
+
+    def sampler_rng(self):
+        a = np.empty((self.batch_size, 4), np.uint64)
+        L.check(self.lib.b200rl_traj_batch_get(self.h, BATCH_RNG, L.ptr(a), a.nbytes))
+        return a
+
+    def update_priority(self, prio):
+        prio = np.ascontiguousarray(prio, np.float32)
+        L.check(self.lib.b200rl_traj_update_priority(self.h, L.ptr(prio), 0))
+
+    def total_priority(self):
+        v = C.c_float()
+        L.check(self.lib.b200rl_traj_total_priority(self.h, C.byref(v)))
+        return v.value
+
+
+class DQNLearner:
+    """DQNLearner / PrioritizedDQNLearner update on a device Trajectory."""
+
+    def __init__(self, ctx, net, traj, cfg):
+        self.ctx, self.lib, self.net, self.traj, self.cfg = ctx, ctx.lib, net, traj, cfg
+
+    def update(self, want_stats=False):
+        stats = np.zeros(4, np.float32) if want_stats else None
+        L.check(self.lib.b200rl_dqn_update(self.net.h, self.traj.h, C.byref(self.cfg), L.ptr(stats)))
+        return None if stats is None else dict(loss=stats[0], grad_norm=stats[1], mean_abs_td=stats[2], n_updates=int(stats[3]))
+
+    def last_td(self):
+        out = np.empty(self.traj.batch_size, np.float32)
+        L.check(self.lib.b200rl_dqn_last_td(self.net.h, self.traj.h, L.ptr(out), out.size))
+        return out

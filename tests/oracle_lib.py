@@ -47,6 +47,22 @@ def lib():
         "orc_discount_f64": (None, [vp, vp, vp, vp, f64, i64, i64, i32]),
         "orc_discount_reduced_f32": (None, [vp, vp, vp, vp, f32, i64, i64, i32]),
         "orc_discount_reduced_f64": (None, [vp, vp, vp, vp, f64, i64, i64, i32]),
+        "orc_ac_nparams": (i64, [vp]), "orc_q_nparams": (i64, [vp]),
+        "orc_perm_index": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint32]),
+        "orc_act_discrete": (None, [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
+        "orc_act_gaussian": (None, [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]),
+        "orc_critic_values": (None, [vp, vp, vp, i64, vp]), "orc_q_values": (None, [vp, vp, vp, i64, vp]),
+        "orc_ac_loss_grad": (None, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, f32, f32, vp, vp]),
+        "orc_clip_by_global_norm": (f32, [vp, i64, f32]),
+        "orc_adam_step": (None, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32]),
+        "orc_target_sync": (None, [vp, vp, i64, f32]),
+        "orc_dqn_loss_grad": (None, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, f32, i32, i32, vp, vp, vp]),
+        "orc_adv_norm": (None, [vp, i64, vp]),
+        "orc_traj_create": (vp, [i32, i64, i64, i32, f32]), "orc_traj_destroy": (None, [vp]),
+        "orc_traj_length": (i64, [vp]), "orc_traj_push_state": (None, [vp, vp]),
+        "orc_traj_push": (None, [vp, vp, vp, vp, vp]),
+        "orc_traj_sample": (None, [vp, i32, vp, i64, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "orc_traj_update_priority": (None, [vp, vp, vp, i64]), "orc_traj_total_priority": (f32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -191,3 +207,163 @@ def discount_rewards(rewards, gamma, terminal=None, init=None, dims=None, dtype=
     out = np.zeros(rf.shape, dtype=dtype, order="F")
     getattr(lib(), "orc_discount_" + sfx)(_p(out), _p(rf), _p(tf), _p(i2), ct(gamma), rf.shape[0], rf.shape[1], d)
     return out.reshape(r.shape) if r.ndim == 1 else np.array(out)
+
+
+# ---- learner side ---------------------------------------------------------------------------
+ACT_RELU, ACT_TANH = 0, 1
+HYPER_KEYS = ("gamma", "lambda_", "clip_range", "max_grad_norm", "w_actor", "w_critic", "w_entropy", "lr", "beta1", "beta2", "eps",
+              "min_sigma", "max_sigma", "normalize_adv")
+HYPER_DEFAULT = dict(gamma=0.99, lambda_=0.95, clip_range=0.1, max_grad_norm=0.5, w_actor=1.0, w_critic=0.5, w_entropy=0.001,
+                     lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, min_sigma=0.0, max_sigma=float("inf"), normalize_adv=1)
+
+
+def hyper_array(**kw):
+    h = dict(HYPER_DEFAULT); h.update(kw)
+    return np.array([h[k] for k in HYPER_KEYS], dtype=np.float32)
+
+
+def ac_desc(n_in, hidden, n_out, act=ACT_RELU, gaussian=False):
+    return np.array([n_in, hidden, act, n_out, int(gaussian)], dtype=np.int32)
+
+
+def ac_nparams(desc):
+    return int(lib().orc_ac_nparams(_p(desc)))
+
+
+def q_nparams(desc):
+    return int(lib().orc_q_nparams(_p(desc)))
+
+
+def glorot_params(desc, seed, q_net=False):
+    """Flux Dense default init: glorot_uniform weights U(+-sqrt(6/(in+out))), zero bias, in
+    Flux.destructure order (weights (out,in) column-major).  numpy Generator stream — the
+    parameters are passed in by the host, so only the shapes/order matter for parity."""
+    n_in, H, _, n_out, gauss = [int(x) for x in desc]
+    rng = np.random.default_rng(seed)
+    def dense(o, i):
+        lim = np.sqrt(6.0 / (i + o))
+        return [rng.uniform(-lim, lim, (o, i)).astype(np.float32).ravel(order="F"), np.zeros(o, np.float32)]
+    def mlp(heads):
+        parts = dense(H, n_in) + dense(H, H)
+        for d in heads:
+            parts += dense(d, H)
+        return parts
+    if q_net:
+        return np.concatenate(mlp([n_out]))
+    return np.concatenate(mlp([n_out, n_out] if gauss else [n_out]) + mlp([1]))
+
+
+def act_discrete(desc, params, obs, rng_states):
+    n = obs.shape[1]
+    obs = np.asfortranarray(obs, dtype=np.float32)
+    rng_states = np.ascontiguousarray(rng_states, dtype=np.uint64).copy()
+    na = int(desc[3])
+    action = np.empty(n, np.int32); logp = np.empty(n, np.float32); value = np.empty(n, np.float32)
+    logits = np.empty((na, n), np.float32, order="F"); margin = np.empty(n, np.float64)
+    lib().orc_act_discrete(_p(desc), _p(params), _p(obs), _p(rng_states), n, _p(action), _p(logp), _p(value), _p(logits), _p(margin))
+    return dict(action=action, logp=logp, value=value, logits=logits, margin=margin, rng=rng_states)
+
+
+def act_gaussian(desc, hyper, params, obs, rng_states):
+    n = obs.shape[1]
+    obs = np.asfortranarray(obs, dtype=np.float32)
+    rng_states = np.ascontiguousarray(rng_states, dtype=np.uint64).copy()
+    action = np.empty(n, np.float32); logp = np.empty(n, np.float32); value = np.empty(n, np.float32)
+    ms = np.empty((n, 2), np.float32)
+    lib().orc_act_gaussian(_p(desc), _p(hyper), _p(params), _p(obs), _p(rng_states), n, _p(action), _p(logp), _p(value), _p(ms))
+    return dict(action=action, logp=logp, value=value, mu=ms[:, 0].copy(), sigma=ms[:, 1].copy(), rng=rng_states)
+
+
+def critic_values(desc, params, obs):
+    obs = np.asfortranarray(obs, dtype=np.float32)
+    out = np.empty(obs.shape[1], np.float32)
+    lib().orc_critic_values(_p(desc), _p(params), _p(obs), obs.shape[1], _p(out))
+    return out
+
+
+def q_values(desc, params, obs):
+    obs = np.asfortranarray(obs, dtype=np.float32)
+    out = np.empty((int(desc[3]), obs.shape[1]), np.float32, order="F")
+    lib().orc_q_values(_p(desc), _p(params), _p(obs), obs.shape[1], _p(out))
+    return out
+
+
+def ac_loss_grad(algo, desc, hyper, params, states, actions, logp_old, adv, ret, idx=None, adv_mean=0.0, adv_inv_std=1.0):
+    states = np.asfortranarray(states, dtype=np.float32)
+    B = len(idx) if idx is not None else states.shape[1]
+    idx = None if idx is None else np.ascontiguousarray(idx, dtype=np.int32)
+    grad = np.zeros(ac_nparams(desc), np.float64); losses = np.zeros(4, np.float64)
+    logp_old = None if logp_old is None else np.ascontiguousarray(logp_old, np.float32)
+    lib().orc_ac_loss_grad(algo, _p(desc), _p(hyper), _p(params), _p(states), _p(np.ascontiguousarray(actions)), _p(logp_old),
+                           _p(np.ascontiguousarray(adv, np.float32)), _p(np.ascontiguousarray(ret, np.float32)), _p(idx), B,
+                           C.c_float(adv_mean), C.c_float(adv_inv_std), _p(grad), _p(losses))
+    return grad, dict(actor_loss=losses[0], critic_loss=losses[1], entropy=losses[2], loss=losses[3])
+
+
+def clip_by_global_norm(g, clip):
+    g = np.ascontiguousarray(g, np.float32).copy()
+    gn = lib().orc_clip_by_global_norm(_p(g), g.size, C.c_float(clip))
+    return g, gn
+
+
+def adam_step(p, g, m, v, beta_t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    lib().orc_adam_step(_p(p), _p(np.ascontiguousarray(g, np.float32)), _p(m), _p(v), _p(beta_t), p.size, C.c_float(lr), C.c_float(b1),
+                        C.c_float(b2), C.c_float(eps))
+
+
+def dqn_loss_grad(desc, p, p_target, s, a, r, t, s2, w=None, gamma=0.99, huber=True, double_dqn=False):
+    s = np.asfortranarray(s, np.float32); s2 = np.asfortranarray(s2, np.float32)
+    B = s.shape[1]
+    grad = np.zeros(q_nparams(desc), np.float64); loss = np.zeros(1, np.float64); td = np.empty(B, np.float32)
+    w = None if w is None else np.ascontiguousarray(w, np.float32)
+    lib().orc_dqn_loss_grad(_p(desc), _p(p), _p(p_target), _p(s), _p(np.ascontiguousarray(a, np.int32)), _p(np.ascontiguousarray(r, np.float32)),
+                            _p(np.ascontiguousarray(t, np.uint8)), _p(s2), _p(w), B, C.c_float(gamma), int(huber), int(double_dqn),
+                            _p(grad), _p(loss), _p(td))
+    return grad, float(loss[0]), td
+
+
+def adv_norm(adv):
+    adv = np.ascontiguousarray(adv, np.float32)
+    out = np.empty(2, np.float32)
+    lib().orc_adv_norm(_p(adv), adv.size, _p(out))
+    return float(out[0]), float(out[1])
+
+
+def perm_index(q, n, key):
+    return int(lib().orc_perm_index(q, n, key))
+
+
+class OracleTraj:
+    def __init__(self, ns, lanes, cap, prioritized=False, default_priority=1.0):
+        self.L = lib()
+        self.ns, self.lanes, self.cap = ns, lanes, cap
+        self.h = self.L.orc_traj_create(ns, lanes, cap, int(prioritized), C.c_float(default_priority))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_traj_destroy(self.h); self.h = None
+
+    def __len__(self):
+        return int(self.L.orc_traj_length(self.h))
+
+    def push_state(self, obs):
+        self.L.orc_traj_push_state(self.h, _p(np.asfortranarray(obs, np.float32)))
+
+    def push(self, a, r, t, next_obs):
+        self.L.orc_traj_push(self.h, _p(np.ascontiguousarray(a, np.int32)), _p(np.ascontiguousarray(r, np.float32)),
+                             _p(np.ascontiguousarray(t, np.uint8)), _p(np.asfortranarray(next_obs, np.float32)))
+
+    def sample(self, slots, B, prioritized=False, beta=0.4):
+        slots = np.ascontiguousarray(slots, np.uint64)
+        s = np.empty((self.ns, B), np.float32, order="F"); s2 = np.empty((self.ns, B), np.float32, order="F")
+        a = np.empty(B, np.int32); r = np.empty(B, np.float32); t = np.empty(B, np.uint8)
+        key = np.empty(B, np.int64); prio = np.empty(B, np.float32); w = np.empty(B, np.float32)
+        self.L.orc_traj_sample(self.h, int(prioritized), _p(slots), B, C.c_float(beta), _p(s), _p(a), _p(r), _p(t), _p(s2), _p(key), _p(prio), _p(w))
+        return dict(state=s, action=a, reward=r, terminal=t, next_state=s2, key=key, priority=prio, weight=w)
+
+    def update_priority(self, key, prio):
+        key = np.ascontiguousarray(key, np.int64); prio = np.ascontiguousarray(prio, np.float32)
+        self.L.orc_traj_update_priority(self.h, _p(key), _p(prio), key.size)
+
+    def total_priority(self):
+        return float(self.L.orc_traj_total_priority(self.h))
