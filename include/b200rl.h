@@ -263,6 +263,10 @@ int b200rl_onpolicy_update(b200rl_onpolicy* agent, const int32_t* perm_host, flo
  * 6 advantage | 7 return | 8 policy rng (4,N) u64 | 9 {adv mean, inv std} */
 int b200rl_onpolicy_get(b200rl_onpolicy* agent, int field, void* host_dst, size_t bytes);
 
+/* measurement aid: average device ms of `reps` back-to-back launches of one hot-path kernel on the
+ * agent's tensors (0 loss+backward, 1 policy inference, 2 env step, 3 GAE, 4 reduce+clip+Adam) */
+int b200rl_onpolicy_time_kernel(b200rl_onpolicy* agent, int which, int reps, float* avg_ms_out);
+
 /* ---------------------------------------------------------------- DQN -------------- */
 typedef struct {
     float gamma, lr, beta1, beta2, eps, max_grad_norm, rho;

@@ -126,6 +126,7 @@ SIGNATURES = {
     "b200rl_onpolicy_fill": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "b200rl_onpolicy_update": (_i32, [_vp, _vp, _vp]),
     "b200rl_onpolicy_get": (_i32, [_vp, _i32, _vp, _sz]),
+    "b200rl_onpolicy_time_kernel": (_i32, [_vp, _i32, _i32, C.POINTER(_f32)]),
     "b200rl_dqn_update": (_i32, [_vp, _vp, _vp, _vp]),
     "b200rl_dqn_last_td": (_i32, [_vp, _vp, _vp, _i64]),
     "b200rl_comm_unique_id": (_i32, [_vp]),

@@ -560,6 +560,58 @@ int b200rl_onpolicy_get(b200rl_onpolicy* a, int field, void* host_dst, size_t by
     return B200RL_OK;
 }
 
+/* Measurement aid (bench.py roofline): average device time of `reps` back-to-back launches of one
+ * hot-path kernel on the agent's current tensors, CUDA events on the ctx stream.
+ * which: 0 loss+backward minibatch kernel (K7) | 1 policy inference (K6) | 2 env step (K1, mutates the env) |
+ * 3 fused GAE (K5) | 4 partial reduce + clip + Adam (K8) */
+int b200rl_onpolicy_time_kernel(b200rl_onpolicy* a, int which, int reps, float* avg_ms_out) {
+    REQUIRE(a && avg_ms_out && reps >= 1, B200RL_ERR_INVALID, "bad argument");
+    TRY(ctx_bind(a->ctx));
+    b200rl_ctx* ctx = a->ctx;
+    b200rl_net* n = a->net;
+    const b200rl_onpolicy_config& c = a->cfg;
+    int64_t N = a->N, T = a->T, NT_ = N * T, B = NT_ / c.n_microbatches;
+    AcHyper hp{c.clip_range, c.w_actor, c.w_critic, c.w_entropy, c.min_sigma, c.max_sigma, c.normalize_advantage, c.algo};
+    const float* obs = (const float*)env_field(a->env, B200RL_FIELD_OBS);
+    int ctas = nn_grid_ctas(ctx, n->actor.H);
+    void* rng_copy = nullptr;
+    if (which == 1) {
+        TRY(ctx_scratch(ctx, (size_t)N * 32 + (size_t)N * 12 + 256, &rng_copy));
+        CUDA_TRY(cudaMemcpyAsync(rng_copy, a->rng, (size_t)N * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    auto once = [&]() -> int {
+        switch (which) {
+            case 0: {
+                AcBatch b{a->states, a->ns, a->actions, a->logp, a->adv, a->ret, nullptr, (uint32_t)NT_, 12345u, 0u, B, 1.0f / (float)B,
+                          a->norm2};
+                return nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
+            }
+            case 1: {
+                float* o = (float*)((char*)rng_copy + (size_t)N * 32);
+                return nn_policy_act(ctx, n->actor, n->critic, n->params, hp, obs, N, (unsigned long long*)rng_copy, o, o + N, o + 2 * N, nullptr, nullptr);
+            }
+            case 2: return b200rl_env_step(a->env, a->actions, 1, 1);
+            case 3: return b200rl_gae_fused_internal(ctx, a->adv, a->ret, a->rewards, a->values, a->terminals, c.gamma, c.lambda, N, T, a->norm_partials, nullptr);
+            case 4: {
+                TRY(nn_reduce_partials(ctx, n->partial, ctas, n->np, n->grad, n->loss_partial, 2 * ctas, n->loss4));
+                return nn_clip_adam(ctx, n->params, n->grad, n->m, n->v, n->beta_t, n->np, c.max_grad_norm, 0.0f, c.beta1, c.beta2, c.eps, 1.0f, n->gnorm);
+            }
+        }
+        b200rl_set_error("unknown kernel id");
+        return B200RL_ERR_INVALID;
+    };
+    REQUIRE(!(which == 2 && a->continuous), B200RL_ERR_UNSUPPORTED, "env-step timing uses the discrete action column");
+    TRY(once());  // warm-up
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int r = 0; r < reps; ++r) TRY(once());
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *avg_ms_out = ms / (float)reps;
+    return B200RL_OK;
+}
+
 // ------------------------------------------------------------------ DQN ---------------------
 /* push!(trajectory, env): append the env's last transition (action, reward, terminal, next obs) — all on device */
 int b200rl_traj_push_env(b200rl_traj* t, b200rl_env* env, int first_state_only) {

@@ -209,7 +209,7 @@ int b200rl_gae_fused_internal(b200rl_ctx* ctx, float* adv, float* ret, const flo
                               float gamma, float lambda, int64_t S, int64_t n_time, double* partials, float* norm2) {
     unsigned grid = grid_for(S, kBlock);
     scan_series_fastest<float, 2><<<grid, kBlock, 0, ctx->stream>>>(adv, r, v, term, nullptr, gamma, lambda, S, n_time, ret,
-                                                                  norm2 ? partials : nullptr);
+                                                                  partials);
     LAUNCH_CHECK(ctx);
     if (norm2) {
         finalize_norm_kernel<<<1, 32, 0, ctx->stream>>>(partials, (int)grid, (double)S * (double)n_time, norm2);

@@ -1,0 +1,270 @@
+# B200RL.jl — the Julia side of the drop-in: new `AbstractEnv` / `AbstractPolicy` subtypes whose
+# methods `ccall` libb200rl.so (include/b200rl.h).  Pure ccall: no CUDA.jl, no codegen.
+#
+# STATUS: written against ReinforcementLearning.jl v0.11 (RLBase 0.13.1 / RLCore 0.15.4) but NOT
+# executed — the build image has no `julia` binary (DESIGN.md §1).  The Python mirror in this
+# package drives the identical C ABI and is what the tests and bench exercise.
+#
+# Usage (what replaces `MultiThreadEnv([CartPoleEnv(T=Float32, rng=...) for i in 1:N])` + PPOPolicy):
+#
+#   using ReinforcementLearning, Random
+#   include("B200RL.jl"); using .B200RL
+#   ctx  = B200Context(0)
+#   env  = B200VecEnv(ctx, :CartPole, 65_536; seeds = [Xoshiro(hash(123 + i)) for i in 1:65_536], auto_reset = true)
+#   net  = B200Network(ctx, n_in = 4, hidden = 64, n_out = 2, params = Flux.destructure(model)[1])
+#   agent = B200OnPolicyAgent(ctx, net, env; update_freq = 32, n_epochs = 4, n_microbatches = 4,
+#                             policy_seeds = [Xoshiro(hash(7 + i)) for i in 1:65_536])
+#   run(agent, env, StopAfterNSteps(10_000), BatchStepsPerEpisode(65_536))
+module B200RL
+
+using Random
+import ReinforcementLearningBase as RLBase
+import ReinforcementLearningCore as RLCore
+using ReinforcementLearningBase: AbstractEnv, AbstractPolicy, Observation, DefaultPlayer
+using ReinforcementLearningCore: AbstractStage, PreExperimentStage, PostExperimentStage, PreActStage, PostActStage,
+    AbstractStopCondition, AbstractHook, AbstractResetCondition, ResetIfEnvTerminated, StopAfterNEpisodes
+
+export B200Context, B200VecEnv, B200Network, B200OnPolicyAgent, B200RandomPolicy
+
+const LIB = get(ENV, "B200RL_LIB", joinpath(@__DIR__, "..", "libb200rl.so"))
+
+# ---- error convention: every entry point returns 0 or a negative status ---------------------
+function check(status::Cint)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:b200rl_last_error, LIB), Cstring, ()))
+    error("b200rl status $status: $msg")
+end
+
+mutable struct B200Context
+    h::Ptr{Cvoid}
+    function B200Context(device::Integer = 0)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:b200rl_init, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, out))
+        ctx = new(out[])
+        finalizer(c -> (c.h == C_NULL || ccall((:b200rl_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.h); c.h = C_NULL), ctx)
+    end
+end
+sync(ctx::B200Context) = check(ccall((:b200rl_sync, LIB), Cint, (Ptr{Cvoid},), ctx.h))
+
+# raw Xoshiro256++ state of a Julia `Xoshiro` (fields s0..s3) -> (4, N) UInt64
+raw_states(rngs::AbstractVector{Xoshiro}) = reduce(hcat, [UInt64[r.s0, r.s1, r.s2, r.s3] for r in rngs])
+
+# ---- params structs: pass the FINAL field values of the reference's own constructors ----------
+struct CartPoleParamsC
+    gravity::Cdouble; masscart::Cdouble; masspole::Cdouble; totalmass::Cdouble; halflength::Cdouble
+    polemasslength::Cdouble; forcemag::Cdouble; dt::Cdouble; thetathreshold::Cdouble; xthreshold::Cdouble
+    max_steps::Int64
+end
+# built from RLEnvs' own CartPoleEnvParams{T}(; kwargs...) so the reference constructor stays the source of truth:
+#   p = ReinforcementLearningEnvironments.CartPoleEnvParams{T}(; kwargs...)
+#   CartPoleParamsC(p.gravity, p.masscart, p.masspole, p.totalmass, p.halflength, p.polemasslength,
+#                   p.forcemag, p.dt, p.thetathreshold, p.xthreshold, p.max_steps)
+
+const KINDS = Dict(:CartPole => 0, :Pendulum => 1, :MountainCar => 2)
+const NS = Dict(0 => 4, 1 => 2, 2 => 2)
+const NOBS = Dict(0 => 4, 1 => 3, 2 => 2)
+@enum Field STATE = 0 OBS = 1 REWARD = 2 TERMINAL = 3 TSTEP = 4 RNG = 5 FLAGS = 6 ACTION = 7
+
+"""
+    B200VecEnv(ctx, kind, N; T = Float32, seeds, auto_reset = true, params = C_NULL)
+
+N classic-control envs stepped by one kernel launch.  Plays the role of `MultiThreadEnv`:
+`state(env)` is `(NOBS, N)`, `reward(env)` / `is_terminated(env)` are length-N vectors.
+"""
+mutable struct B200VecEnv{T} <: AbstractEnv
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    kind::Int
+    n::Int
+    auto_reset::Bool
+    continuous::Bool
+    # host mirrors, refreshed lazily (state(env) may alias a reused buffer: interface.jl:515-517)
+    obs::Matrix{T}
+    rewards::Vector{T}
+    terminals::Vector{UInt8}
+end
+
+function B200VecEnv(ctx::B200Context, kind::Symbol, n::Integer; T = Float32, seeds::AbstractVector{Xoshiro},
+                    auto_reset::Bool = true, params = C_NULL, continuous::Bool = (kind == :Pendulum))
+    length(seeds) == n || throw(ArgumentError("need one Xoshiro per env"))
+    k = KINDS[kind]
+    st = raw_states(seeds)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve st params check(ccall((:b200rl_env_create, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{UInt64}, Ref{Ptr{Cvoid}}),
+        ctx.h, k, T === Float64 ? 1 : 0, n, params === C_NULL ? C_NULL : pointer_from_objref(params), st, out))
+    env = B200VecEnv{T}(ctx, out[], k, n, auto_reset, continuous, zeros(T, NOBS[k], n), zeros(T, n), zeros(UInt8, n))
+    finalizer(e -> (e.h == C_NULL || ccall((:b200rl_env_destroy, LIB), Cint, (Ptr{Cvoid},), e.h); e.h = C_NULL), env)
+end
+
+function fetch!(env::B200VecEnv, field::Field, dst::Array)
+    GC.@preserve dst check(ccall((:b200rl_env_get, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t),
+                                 env.h, Int(field), dst, sizeof(dst)))
+    dst
+end
+
+# ---- RLBase verbs (interface.jl:435-597) -------------------------------------------------------
+RLBase.reset!(env::B200VecEnv; is_force::Bool = true) =
+    check(ccall((:b200rl_env_reset, LIB), Cint, (Ptr{Cvoid}, Cint), env.h, is_force))
+
+function RLBase.act!(env::B200VecEnv, actions::AbstractVector{<:Integer})
+    a = convert(Vector{Int32}, actions)                     # device dtype is Int32, 1-based like Base.OneTo(n)
+    GC.@preserve a check(ccall((:b200rl_env_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint), env.h, a, 0, env.auto_reset))
+end
+function RLBase.act!(env::B200VecEnv, actions::AbstractVector{<:AbstractFloat})
+    a = convert(Vector{Float32}, actions)
+    GC.@preserve a check(ccall((:b200rl_env_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint), env.h, a, 0, env.auto_reset))
+end
+struct FusedRandomAction end                                  # plan!(B200RandomPolicy) token
+RLBase.act!(env::B200VecEnv, ::FusedRandomAction) =
+    check(ccall((:b200rl_env_step_random, LIB), Cint, (Ptr{Cvoid}, Cint), env.h, env.auto_reset))
+
+RLBase.state(env::B200VecEnv, ::Observation, ::DefaultPlayer) = fetch!(env, OBS, env.obs)
+RLBase.state(env::B200VecEnv) = fetch!(env, OBS, env.obs)
+RLBase.reward(env::B200VecEnv) = fetch!(env, REWARD, env.rewards)
+RLBase.is_terminated(env::B200VecEnv) = (fetch!(env, TERMINAL, env.terminals); env.terminals .!= 0)
+RLBase.action_space(env::B200VecEnv) =
+    env.kind == 0 ? Base.OneTo(2) : env.kind == 2 ? Base.OneTo(3) : (-2.0 .. 2.0)
+Base.length(env::B200VecEnv) = env.n
+function Random.seed!(env::B200VecEnv, seeds::AbstractVector{Xoshiro})
+    st = raw_states(seeds)
+    GC.@preserve st check(ccall((:b200rl_env_seed, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt64}), env.h, st))
+end
+function Base.copy(env::B200VecEnv{T}) where {T}
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:b200rl_env_copy, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), env.h, out))
+    B200VecEnv{T}(env.ctx, out[], env.kind, env.n, env.auto_reset, env.continuous, copy(env.obs), copy(env.rewards), copy(env.terminals))
+end
+
+# ---- run-loop impedance (SURVEY §7 "Run-loop impedance") --------------------------------------
+# the kernel resets finished sub-envs itself; the scalar reset condition must never fire
+RLCore.check!(::ResetIfEnvTerminated, ::AbstractPolicy, ::B200VecEnv) = false
+# StopAfterNEpisodes counts every finished sub-episode (stop_conditions.jl:104-118 for a vector env)
+function RLCore.check!(s::StopAfterNEpisodes{Nothing}, agent, env::B200VecEnv)
+    s.cur += count(RLBase.is_terminated(env))
+    s.cur >= s.episode
+end
+# the historical MultiThreadEnv `_run` (no episode stages), run.jl:36-78 specialised on the env type
+function RLCore._run(policy::AbstractPolicy, env::B200VecEnv, stop_condition::AbstractStopCondition, hook::AbstractHook,
+                     reset_condition::AbstractResetCondition)
+    push!(hook, PreExperimentStage(), policy, env)
+    push!(policy, PreExperimentStage(), env)
+    RLBase.reset!(env; is_force = true)
+    while true
+        env.auto_reset || RLBase.reset!(env; is_force = false)
+        push!(policy, PreActStage(), env)
+        RLBase.optimise!(policy, PreActStage())
+        push!(hook, PreActStage(), policy, env)
+        action = RLBase.plan!(policy, env)
+        RLBase.act!(env, action)
+        push!(policy, PostActStage(), env, action)
+        RLBase.optimise!(policy, PostActStage())
+        push!(hook, PostActStage(), policy, env)
+        RLCore.check!(stop_condition, policy, env) && break
+    end
+    push!(policy, PostExperimentStage(), env)
+    push!(hook, PostExperimentStage(), policy, env)
+    check(ccall((:b200rl_env_check, LIB), Cint, (Ptr{Cvoid},), env.h))   # the reference's `@assert a in action_space(env)`
+    hook
+end
+
+# ---- policies ---------------------------------------------------------------------------------
+"RandomPolicy() sharing each env's RNG stream (random_policy.jl:18-32): the draw is fused into the step kernel."
+struct B200RandomPolicy <: AbstractPolicy end
+RLBase.plan!(::B200RandomPolicy, ::B200VecEnv) = FusedRandomAction()
+
+struct NetDescC
+    n_in::Int32; hidden::Int32; act::Int32; n_out::Int32; kind::Int32
+end
+mutable struct B200Network
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    desc::NetDescC
+end
+"FluxApproximator stand-in: `params` is `Flux.destructure(ActorCritic(actor, critic))[1]` (Float32)."
+function B200Network(ctx::B200Context; n_in, hidden, n_out, params::Vector{Float32}, act::Symbol = :relu, kind::Symbol = :categorical)
+    d = NetDescC(n_in, hidden, act === :relu ? 0 : 1, n_out, kind === :categorical ? 0 : kind === :gaussian ? 1 : 2)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve params check(ccall((:b200rl_net_create, LIB), Cint, (Ptr{Cvoid}, Ref{NetDescC}, Ptr{Float32}, Ref{Ptr{Cvoid}}),
+                                    ctx.h, Ref(d), params, out))
+    net = B200Network(ctx, out[], d)
+    finalizer(n -> (n.h == C_NULL || ccall((:b200rl_net_destroy, LIB), Cint, (Ptr{Cvoid},), n.h); n.h = C_NULL), net)
+end
+"Read back parameters / optimiser state (JLD2 checkpoint hooks, docs/src/How_to_use_hooks.md:124-167)."
+function Base.getindex(net::B200Network, which::Integer, n::Integer)
+    out = Vector{Float32}(undef, n)
+    GC.@preserve out check(ccall((:b200rl_net_get, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Int64), net.h, which, out, n))
+    out
+end
+
+struct OnPolicyConfigC
+    gamma::Cfloat; lambda::Cfloat; clip_range::Cfloat; max_grad_norm::Cfloat; w_actor::Cfloat; w_critic::Cfloat; w_entropy::Cfloat
+    lr::Cfloat; beta1::Cfloat; beta2::Cfloat; eps::Cfloat; min_sigma::Cfloat; max_sigma::Cfloat
+    normalize_advantage::Int32; n_epochs::Int32; n_microbatches::Int32; update_freq::Int32; algo::Int32
+end
+
+"Agent(policy = PPOPolicy | A2C, trajectory = PPOTrajectory) living on the device."
+mutable struct B200OnPolicyAgent <: AbstractPolicy
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    net::B200Network
+    env::B200VecEnv
+    T::Int
+    t::Int
+    actions::Vector{Int32}
+    stats::Matrix{Float32}
+end
+function B200OnPolicyAgent(ctx, net::B200Network, env::B200VecEnv; policy_seeds::AbstractVector{Xoshiro},
+        γ = 0.99f0, λ = 0.95f0, clip_range = 0.1f0, max_grad_norm = 0.5f0, actor_loss_weight = 1f0, critic_loss_weight = 0.5f0,
+        entropy_loss_weight = 0.001f0, lr = 1f-3, update_freq = 32, n_epochs = 4, n_microbatches = 4, normalize_advantage = true,
+        algo::Symbol = :ppo)
+    cfg = OnPolicyConfigC(γ, λ, clip_range, max_grad_norm, actor_loss_weight, critic_loss_weight, entropy_loss_weight, lr, 0.9f0, 0.999f0,
+                          1f-8, 0f0, Inf32, normalize_advantage, n_epochs, n_microbatches, update_freq, algo === :ppo ? 0 : 1)
+    st = raw_states(policy_seeds)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve st check(ccall((:b200rl_onpolicy_create, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{OnPolicyConfigC}, Ptr{UInt64}, Ref{Ptr{Cvoid}}), ctx.h, net.h, env.h, Ref(cfg), st, out))
+    a = B200OnPolicyAgent(ctx, out[], net, env, update_freq, 0, zeros(Int32, env.n), zeros(Float32, 6, n_epochs * n_microbatches))
+    finalizer(x -> (x.h == C_NULL || ccall((:b200rl_onpolicy_destroy, LIB), Cint, (Ptr{Cvoid},), x.h); x.h = C_NULL), a)
+end
+# plan!(agent, env) (agent_base.jl:52-54): K6 on the current observation; actions come back to the host
+function RLBase.plan!(a::B200OnPolicyAgent, ::B200VecEnv)
+    GC.@preserve a check(ccall((:b200rl_onpolicy_plan, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), a.h, a.actions))
+    a.actions
+end
+# push!(agent, PostActStage, env, action) (agent_base.jl:56-59): reward/terminal were written in-kernel
+function Base.push!(a::B200OnPolicyAgent, ::PostActStage, ::B200VecEnv, action)
+    check(ccall((:b200rl_onpolicy_push, LIB), Cint, (Ptr{Cvoid},), a.h))
+    a.t += 1
+end
+Base.push!(::B200OnPolicyAgent, ::AbstractStage, ::B200VecEnv) = nothing
+# optimise!(agent, PostActStage) (agent_base.jl:34-41): GAE + n_epochs x n_microbatches updates once the rollout is full
+function RLBase.optimise!(a::B200OnPolicyAgent, ::PostActStage)
+    a.t == a.T || return nothing
+    GC.@preserve a check(ccall((:b200rl_onpolicy_update, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float32}), a.h, C_NULL, a.stats))
+    a.t = 0
+    nothing
+end
+RLBase.optimise!(::B200OnPolicyAgent, ::AbstractStage) = nothing
+
+# ---- pure-function drop-ins (utils/basic.jl:138-417) --------------------------------------------
+"`generalized_advantage_estimation(rewards, values, γ, λ; dims, terminal)` on the GPU (Float32 / Float64 matrices)."
+function generalized_advantage_estimation(ctx::B200Context, rewards::Matrix{T}, values::Matrix{T}, γ::T, λ::T;
+                                          dims::Int, terminal::Union{Nothing,Matrix{Bool}} = nothing) where {T<:Union{Float32,Float64}}
+    adv = similar(rewards)
+    term = terminal === nothing ? C_NULL : convert(Matrix{UInt8}, terminal)
+    f = T === Float32 ? :b200rl_gae_f32 : :b200rl_gae_f64
+    R, C = size(rewards)
+    GC.@preserve adv rewards values term begin
+        if T === Float32
+            check(ccall((:b200rl_gae_f32, LIB), Cint, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{UInt8}, T, T, Int64, Int64, Cint, Cint),
+                        ctx.h, adv, rewards, values, term, γ, λ, R, C, dims, 0))
+        else
+            check(ccall((:b200rl_gae_f64, LIB), Cint, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{UInt8}, T, T, Int64, Int64, Cint, Cint),
+                        ctx.h, adv, rewards, values, term, γ, λ, R, C, dims, 0))
+        end
+    end
+    adv
+end
+
+end # module

@@ -135,20 +135,30 @@ class OnPolicyAgent(AbstractPolicy):
         L.check(self.lib.b200rl_onpolicy_create(ctx.h, net.h, env.h, C.byref(cfg), L.ptr(policy_rng), C.byref(h)))
         self.h = h
         self.continuous = env.continuous
-        self._act_buf = np.empty(self.n, np.float32 if self.continuous else np.int32)
+        # pinned host buffer for the per-step action round trip of the stage protocol
+        self._act_buf, self._act_buf_addr = ctx.host_alloc((self.n,), np.float32 if self.continuous else np.int32)
         self.last_stats = None
         self.n_updates = 0
+        self.fetch_stats = False   # read the per-minibatch losses back after every update (a sync)
+        self._t = 0                # host mirror of the rollout fill level (no device query per step)
 
     def close(self):
         if getattr(self, "h", None):
             self.lib.b200rl_onpolicy_destroy(self.h)
             self.h = None
+            self._act_buf = None
+            self.ctx.host_free(self._act_buf_addr)
 
     def __del__(self):
         try:
             self.close()
         except Exception:
             pass
+
+    def time_kernel(self, which, reps=20):
+        ms = C.c_float()
+        L.check(self.lib.b200rl_onpolicy_time_kernel(self.h, which, reps, C.byref(ms)))
+        return ms.value
 
     # ---- stage protocol (run.jl:52-68) -------------------------------------------------------
     def plan(self, env):
@@ -168,12 +178,16 @@ class OnPolicyAgent(AbstractPolicy):
             L.check(self.lib.b200rl_onpolicy_push(self.h))
 
     def optimise(self, stage):
-        if stage == PostActStage and self.fill()[0] == self.T:
-            self.update()
+        if stage == PostActStage:
+            self._t += 1
+            if self._t == self.T:
+                self._t = 0
+                self.update(want_stats=self.fetch_stats)
 
     # ---- fused path --------------------------------------------------------------------------
     def collect(self, n_steps):
         L.check(self.lib.b200rl_onpolicy_collect(self.h, n_steps))
+        self._t = (self._t + n_steps)
 
     def fill(self):
         t, T = C.c_int(), C.c_int()
@@ -187,6 +201,7 @@ class OnPolicyAgent(AbstractPolicy):
             perm = np.ascontiguousarray(perm, np.int32)
             assert perm.shape == (self.cfg.n_epochs, self.n * self.T)
         L.check(self.lib.b200rl_onpolicy_update(self.h, L.ptr(perm), L.ptr(stats)))
+        self._t = 0
         self.n_updates += 1
         self.last_stats = stats
         return stats

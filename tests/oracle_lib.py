@@ -63,6 +63,7 @@ def lib():
         "orc_traj_push": (None, [vp, vp, vp, vp, vp]),
         "orc_traj_sample": (None, [vp, i32, vp, i64, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "orc_traj_update_priority": (None, [vp, vp, vp, i64]), "orc_traj_total_priority": (f32, [vp]),
+        "orc_ppo_iteration": (f64, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_uint32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -367,3 +368,10 @@ class OracleTraj:
 
     def total_priority(self):
         return float(self.L.orc_traj_total_priority(self.h))
+
+
+def ppo_iteration(env, desc, hyper, params, m, v, beta_t, policy_rng, T=32, E=4, M=4, update_counter=0, want_stats=False):
+    """One full CPU PPO iteration on an OracleVecEnv (in-place on params / optimiser state / rng). Returns (seconds, stats)."""
+    stats = np.zeros((E * M, 5), np.float32) if want_stats else None
+    sec = lib().orc_ppo_iteration(env.h, _p(desc), _p(hyper), _p(params), _p(m), _p(v), _p(beta_t), _p(policy_rng), T, E, M, update_counter, _p(stats))
+    return sec, stats
