@@ -158,29 +158,12 @@ def run_own(args):
             torch.cuda.synchronize()
 
     n_total = args.envs
-    assert n_total % world == 0
     n = n_total // world
     T = T_ROLLOUT
-    # test-harness seeding of SURVEY §8d: env i gets splitmix64 outputs of seed ^ i (global index)
-    def states(seed):
-        M = np.uint64(0xFFFFFFFFFFFFFFFF)
-        x = (np.uint64(seed) ^ np.arange(rank * n, (rank + 1) * n, dtype=np.uint64))
-        out = np.empty((n, 4), dtype=np.uint64)
-        with np.errstate(over="ignore"):
-            for k in range(4):
-                x = (x + np.uint64(0x9E3779B97F4A7C15)) & M
-                z = x.copy()
-                z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M
-                z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M
-                out[:, k] = z ^ (z >> np.uint64(31))
-        return out
-
-    def glorot(seed):  # Flux glorot_uniform, zero bias, Flux.destructure order; identical on every rank
-        r = np.random.default_rng(seed)
-        def dense(o, i):
-            lim = np.sqrt(6.0 / (i + o))
-            return [r.uniform(-lim, lim, (o, i)).astype(np.float32).ravel(order="F"), np.zeros(o, np.float32)]
-        return np.concatenate(dense(HIDDEN, 4) + dense(HIDDEN, HIDDEN) + dense(2, HIDDEN) + dense(HIDDEN, 4) + dense(HIDDEN, HIDDEN) + dense(1, HIDDEN))
+    from b200rl import sharding
+    lo, hi = sharding.shard_range(n_total, rank, world)
+    states = lambda seed: sharding.splitmix_states(seed, lo, hi)      # streams keyed by GLOBAL env index
+    glorot = lambda seed: sharding.glorot_actor_critic(seed, 4, HIDDEN, 2)
 
     cfg = pkg.onpolicy_config(update_freq=T, n_epochs=N_EPOCHS, n_microbatches=N_MICRO)
 

@@ -29,6 +29,7 @@
 namespace oracle {
 
 enum Act { ACT_RELU = 0, ACT_TANH = 1 };
+constexpr int kMaxH = 256;  // per-sample scratch lives on the stack (no malloc in the hot loops)
 
 struct MLP {
     int in, H, act, nheads;
@@ -73,7 +74,8 @@ static inline void mlp_forward(const MLP& n, const float* p, const float* x, flo
 // backward: accumulate d(loss)/d(params) into g (double), given dout
 static inline void mlp_backward(const MLP& n, const float* p, const float* x, const float* h1, const float* h2, const float* dout,
                                 double* g) {
-    std::vector<float> dh2(n.H, 0.f), dh1(n.H, 0.f);
+    float dh2[kMaxH], dh1[kMaxH];
+    for (int i = 0; i < n.H; ++i) { dh2[i] = 0.f; dh1[i] = 0.f; }
     int off = 0;
     for (int k = 0; k < n.nheads; ++k) {
         const float* W = p + n.oHead(k);
@@ -166,7 +168,8 @@ struct Hyper {
 // policy inference for one sample (rollout): discrete -> action (1-based), logp, value
 static inline void act_discrete(const ActorCritic& ac, const float* p, const float* x, jl::Xoshiro& g, int32_t* action, float* logp,
                                 float* value, float* logits_out, double* margin) {
-    std::vector<float> h1(std::max(ac.actor.H, ac.critic.H)), h2(h1.size());
+    float h1s[kMaxH], h2s[kMaxH];
+    struct { float* p; float* data() { return p; } } h1{h1s}, h2{h2s};
     float z[8], lp[8], v;
     mlp_forward(ac.actor, p, x, h1.data(), h2.data(), z);
     int na = ac.actor.hd[0];
@@ -181,7 +184,8 @@ static inline void act_discrete(const ActorCritic& ac, const float* p, const flo
 // Gaussian (1-d action): action = mu + sigma*n (unclamped; the env clamps the torque)
 static inline void act_gaussian(const ActorCritic& ac, const Hyper& hp, const float* p, const float* x, jl::Xoshiro& g, float* action,
                                 float* logp, float* value, float* mu_sigma_out) {
-    std::vector<float> h1(std::max(ac.actor.H, ac.critic.H)), h2(h1.size());
+    float h1s[kMaxH], h2s[kMaxH];
+    struct { float* p; float* data() { return p; } } h1{h1s}, h2{h2s};
     float z[2], v;
     mlp_forward(ac.actor, p, x, h1.data(), h2.data(), z);
     float mu = z[0];

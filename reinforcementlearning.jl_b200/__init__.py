@@ -10,7 +10,7 @@ from .core import (AbstractHook, AbstractPolicy, BatchStepsPerEpisode, ComposedH
 from .envs import B200VecEnv, cartpole_params, mountaincar_params, pendulum_params
 from .learners import (ACT_RELU, ACT_TANH, KIND_CATEGORICAL, KIND_GAUSSIAN, KIND_Q, DQNLearner, Network, OnPolicyAgent, Trajectory,
                        dqn_config, onpolicy_config)
-from . import learners
+from . import learners, sharding
 from .returns import discount_rewards, discount_rewards_reduced, generalized_advantage_estimation
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -224,7 +224,8 @@ class Context:
         check(self.lib.b200rl_free(self.h, C.c_void_p(dptr)))
 
     def h2d(self, dptr, arr, async_=False):
-        arr = np.ascontiguousarray(arr)
+        if not (arr.flags.c_contiguous or arr.flags.f_contiguous):
+            arr = np.ascontiguousarray(arr)   # F-ordered (Julia-shaped) arrays are copied as they lie in memory
         check(self.lib.b200rl_memcpy_h2d(self.h, C.c_void_p(dptr), ptr(arr), arr.nbytes, int(async_)))
 
     def d2h(self, arr, dptr, async_=False):

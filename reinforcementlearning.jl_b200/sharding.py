@@ -1,0 +1,44 @@
+"""Host-side sharding rules for the multi-GPU path: envs are partitioned by index,
+rank r of G owns [r*N/G, (r+1)*N/G); RNG streams are keyed by the GLOBAL env index so a sharded
+run owns exactly the streams the single-GPU run would; gradients are local sums scaled by
+1/(B_local * G) and summed across ranks (one all-reduce per optimiser step); the advantage
+normalisation uses globally reduced sums.  No compute here — index arithmetic only."""
+import numpy as np
+
+
+def shard_range(n_total, rank, world):
+    if n_total % world:
+        raise ValueError("the number of envs must be divisible by the number of GPUs")
+    n = n_total // world
+    return rank * n, (rank + 1) * n
+
+
+def splitmix_states(seed, lo, hi):
+    """Test-harness seeding: env i gets four successive splitmix64 outputs of seed ^ i.
+    Returns (hi - lo, 4) uint64 raw Xoshiro256++ states for global env indices lo..hi-1.
+    (The Julia glue passes `Xoshiro(hash(seed + i))` states instead.)"""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    x = np.uint64(seed) ^ np.arange(lo, hi, dtype=np.uint64)
+    out = np.empty((hi - lo, 4), dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for k in range(4):
+            x = (x + np.uint64(0x9E3779B97F4A7C15)) & M
+            z = x.copy()
+            z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M
+            z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M
+            out[:, k] = z ^ (z >> np.uint64(31))
+    return out
+
+
+def glorot_actor_critic(seed, n_in, hidden, n_out):
+    """Flux `glorot_uniform` Dense init (U(+-sqrt(6/(in+out))), zero bias) in Flux.destructure order
+    for ActorCritic(actor n_in-H-H-n_out, critic n_in-H-H-1); identical on every rank."""
+    r = np.random.default_rng(seed)
+
+    def dense(o, i):
+        lim = np.sqrt(6.0 / (i + o))
+        return [r.uniform(-lim, lim, (o, i)).astype(np.float32).ravel(order="F"), np.zeros(o, np.float32)]
+
+    parts = dense(hidden, n_in) + dense(hidden, hidden) + dense(n_out, hidden)
+    parts += dense(hidden, n_in) + dense(hidden, hidden) + dense(1, hidden)
+    return np.concatenate(parts)
