@@ -1,0 +1,78 @@
+"""Distil gpurun_out/*.ncu-rep + launches.csv into tracked summaries under profiles/ (run on the CPU box)."""
+import collections, csv, io, json, os, re, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum", "smsp__cycles_active.avg",
+        "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio", "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+        "smsp__average_warp_latency_issue_stalled_barrier.ratio", "smsp__average_warp_latency_issue_stalled_mio_throttle.ratio",
+        "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio", "smsp__average_warp_latency_issue_stalled_not_selected.ratio",
+        "smsp__average_warp_latency_issue_stalled_wait.ratio", "smsp__average_warp_latency_issue_stalled_dispatch_stall.ratio"]
+
+def raw(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr = rows[0]
+    out = []
+    for r in rows[2:]:
+        out.append(dict(zip(hdr, r)))
+    return hdr, rows[1], out
+
+lines = ["# ncu summaries (%s)" % TAG, "", "Captured with `profiles/run_profiles.sh` under gpurun on one B200 (`--set full --clock-control none`);",
+         "per-launch times are cold-cache / serialised — compare shares, not absolutes.", ""]
+traffic = {}
+for name in ("prof_loss", "prof_fwd", "prof_env", "prof_gae"):
+    rep = os.path.join(OUT, name + ".ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    hdr, units, recs = raw(rep)
+    for rec in recs:
+        kn = re.sub(r"\(.*", "", rec.get("Kernel Name", "?"))
+        lines.append("## %s — `%s`" % (name, kn))
+        lines.append("")
+        lines.append("| metric | value | unit |")
+        lines.append("|---|---|---|")
+        ui = dict(zip(hdr, units))
+        for k in KEYS:
+            if k in rec:
+                lines.append("| %s | %s | %s |" % (k, rec[k], ui.get(k, "")))
+        try:
+            t = float(rec["dram__bytes_read.sum"].replace(",", "")) + float(rec["dram__bytes_write.sum"].replace(",", ""))
+            u = ui.get("dram__bytes_read.sum", "byte")
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            traffic[kn.split("<")[0].split("::")[-1]] = t * mult
+            lines.append("| dram traffic (read+write) | %.3f | MB |" % (t * mult / 1e6))
+        except Exception as e:
+            pass
+        lines.append("")
+        break  # first captured launch is enough
+# launch list
+lp = os.path.join(OUT, "launches.csv")
+if os.path.exists(lp):
+    rows = list(csv.reader(open(lp, errors="replace")))
+    hdr = None; data = []
+    for r in rows:
+        if "Kernel Name" in r: hdr = r; continue
+        if hdr and len(r) == len(hdr): data.append(dict(zip(hdr, r)))
+    tot = collections.defaultdict(float); cnt = collections.Counter()
+    for d in data:
+        nm = re.sub(r"\(.*", "", d["Kernel Name"]); nm = re.sub(r"^.*::", "", nm)
+        v = float(d["Metric Value"].replace(",", "")); u = d["Metric Unit"]
+        v *= {"ns": 1, "nsecond": 1, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6}.get(u, 1)
+        tot[nm] += v; cnt[nm] += 1
+    T = sum(tot.values())
+    lines += ["## launch list (`ncu --metrics gpu__time_duration.sum`, python bench.py --steps 2 --warmup 1)", "",
+              "| kernel | launches | total ms | avg us | share |", "|---|---|---|---|---|"]
+    for k, v in sorted(tot.items(), key=lambda x: -x[1]):
+        lines.append("| %s | %d | %.3f | %.2f | %.1f%% |" % (k, cnt[k], v / 1e6, v / cnt[k] / 1e3, 100 * v / T))
+    lines.append("")
+open(os.path.join(ROOT, "profiles", TAG + "_ncu_summary.md"), "w").write("\n".join(lines))
+if traffic:
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+print("\n".join(lines))

@@ -1,0 +1,76 @@
+// umma_selftest.cu — diagnostic entry point that pins down the tcgen05 operand-layout / TMEM
+// mapping conventions on real hardware: the host supplies raw shared-memory images of the A and B
+// operands plus descriptor parameters; the kernel issues the MMAs and dumps TMEM lanes 0..127.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+struct SelfTestArgs {
+    const uint8_t* a_img; uint32_t a_bytes;
+    const uint8_t* b_img; uint32_t b_bytes;
+    uint32_t a_lbo, a_sbo, b_lbo, b_sbo;      // descriptor byte offsets
+    uint32_t a_kadv, b_kadv;                  // start-address advance per K step (bytes)
+    uint32_t idesc; int ksteps; int ncols;    // instruction descriptor, # MMA instructions, D columns to dump
+    float* d_out;                             // [128][ncols]
+};
+
+__global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    uint8_t* sa = smem;
+    uint8_t* sb = smem + ((a.a_bytes + 1023) / 1024) * 1024;
+    for (uint32_t k = threadIdx.x; k < a.a_bytes / 4; k += blockDim.x) ((uint32_t*)sa)[k] = ((const uint32_t*)a.a_img)[k];
+    for (uint32_t k = threadIdx.x; k < a.b_bytes / 4; k += blockDim.x) ((uint32_t*)sb)[k] = ((const uint32_t*)a.b_img)[k];
+    umma::fence_proxy_async();
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 64);
+    if (threadIdx.x == 32) umma::mbar_init(&s_bar, 1);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < a.ksteps; ++k) {
+            uint64_t da = umma::make_desc(umma::smem_u32(sa) + k * a.a_kadv, a.a_lbo, a.a_sbo);
+            uint64_t db = umma::make_desc(umma::smem_u32(sb) + k * a.b_kadv, a.b_lbo, a.b_sbo);
+            umma::mma_tf32(tmem, da, db, a.idesc, k > 0 ? 1u : 0u);
+        }
+        umma::commit(&s_bar);
+    }
+    umma::mbar_wait(&s_bar, 0);
+    umma::fence_after_sync();
+    for (int c0 = 0; c0 < a.ncols; c0 += 32) {
+        float v[32];
+        umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        int lane = warp * 32 + (threadIdx.x & 31);
+        for (int c = 0; c < 32; ++c) a.d_out[lane * a.ncols + c0 + c] = v[c];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 64);
+}
+}  // namespace
+
+extern "C" int b200rl_selftest_umma(b200rl_ctx* ctx, const void* a_img_host, uint32_t a_bytes, const void* b_img_host, uint32_t b_bytes,
+                                    const uint32_t* desc8 /* a_lbo,a_sbo,b_lbo,b_sbo,a_kadv,b_kadv,idesc,ksteps */, int ncols,
+                                    float* d_out_host /* [128][ncols] */) {
+    TRY(ctx_bind(ctx));
+    REQUIRE(a_img_host && b_img_host && desc8 && d_out_host, B200RL_ERR_INVALID, "null argument");
+    REQUIRE(ncols == 32 || ncols == 64, B200RL_ERR_INVALID, "ncols must be 32 or 64");
+    REQUIRE(a_bytes % 4 == 0 && b_bytes % 4 == 0 && a_bytes + b_bytes < 200 * 1024, B200RL_ERR_INVALID, "bad image sizes");
+    void* sc;
+    size_t a_pad = ((size_t)a_bytes + 1023) / 1024 * 1024, b_pad = ((size_t)b_bytes + 1023) / 1024 * 1024;
+    TRY(ctx_scratch(ctx, a_pad + b_pad + (size_t)128 * ncols * 4 + 1024, &sc));
+    uint8_t* da = (uint8_t*)sc; uint8_t* db = da + a_pad; float* dd = (float*)(db + b_pad);
+    CUDA_TRY(cudaMemcpyAsync(da, a_img_host, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(db, b_img_host, b_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SelfTestArgs a{da, a_bytes, db, b_bytes, desc8[0], desc8[1], desc8[2], desc8[3], desc8[4], desc8[5], desc8[6], (int)desc8[7], ncols, dd};
+    size_t smem = a_pad + b_pad;
+    CUDA_TRY(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<<<1, 128, smem, ctx->stream>>>(a);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(cudaMemcpyAsync(d_out_host, dd, (size_t)128 * ncols * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200RL_OK;
+}
