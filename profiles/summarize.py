@@ -46,7 +46,8 @@ for name in ("prof_loss", "prof_fwd", "prof_env", "prof_gae"):
             t = float(rec["dram__bytes_read.sum"].replace(",", "")) + float(rec["dram__bytes_write.sum"].replace(",", ""))
             u = ui.get("dram__bytes_read.sum", "byte")
             mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-            traffic[kn.split("<")[0].split("::")[-1]] = t * mult
+            mk = re.search(r"(ac_loss_grad_kernel|forward_kernel|env_step_kernel|scan_series_fastest|dqn_loss_grad_kernel)", kn)
+            traffic[mk.group(1) if mk else kn] = t * mult
             lines.append("| dram traffic (read+write) | %.3f | MB |" % (t * mult / 1e6))
         except Exception as e:
             pass
