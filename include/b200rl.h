@@ -278,6 +278,8 @@ typedef struct {
 int b200rl_dqn_update(b200rl_net* net, b200rl_traj* traj, const b200rl_dqn_config* cfg, float* stats_host);
 int b200rl_dqn_last_td(b200rl_net* net, b200rl_traj* traj, float* host_dst, int64_t count);
 
+/* select the tcgen05 tensor-core kernels (default, H = 64) or the FP32 CUDA-core kernels for the dense layers */
+int b200rl_set_tensor_cores(int enable);
 /* diagnostic: run tcgen05.mma kind::tf32 on host-supplied shared-memory operand images and dump
  * TMEM (pins the operand-layout conventions of the tensor-core path; tests/test_umma_gpu.py).
  * desc8 = {a_lbo, a_sbo, b_lbo, b_sbo, a_kadvance, b_kadvance, idesc, ksteps}; d_out (128, ncols) row-major */

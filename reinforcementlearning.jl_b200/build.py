@@ -22,7 +22,7 @@ SOURCES = [
     ("returns.cu", ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]),
     ("comm.cu", []),
 ]
-OPTIONAL = [("traj.cu", []), ("nn.cu", []), ("algo.cu", []), ("umma_selftest.cu", [])]
+OPTIONAL = [("traj.cu", []), ("nn.cu", []), ("algo.cu", []), ("umma_selftest.cu", []), ("nn_tc.cu", [])]
 
 
 def _nvcc():

@@ -843,6 +843,16 @@ template <class K> int set_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+static int g_tc = -1;
+bool nn_tc_enabled() {
+    if (g_tc < 0) {
+        const char* e = getenv("B200RL_TC");
+        g_tc = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_tc != 0;
+}
+extern "C" int b200rl_set_tensor_cores(int enable) { g_tc = enable ? 1 : 0; return B200RL_OK; }
+
 int nn_grid_ctas(b200rl_ctx* ctx, int H) { return H == 64 ? ctx->sm_count : ctx->sm_count / 2; }
 
 template <int H>
@@ -895,6 +905,8 @@ int nn_policy_act(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& critic, 
     int ctas = nn_grid_ctas(ctx, actor.H);
     int nt = tiles_for(actor.H, N);
     if (ctas > nt) ctas = nt;
+    if (nn_tc_enabled() && nn_tc_supported(actor) && nn_tc_supported(critic))
+        return nn_tc_forward(ctx, 2 * ctas, actor, critic, params, hp, 0, obs, N, rng, action_out, logp_out, value_out, head_out, state_copy);
     if (actor.H == 64) return launch_forward<64>(ctx, 2 * ctas, actor, critic, params, hp, 0, obs, N, rng, action_out, logp_out, value_out, head_out, state_copy);
     return launch_forward<128>(ctx, 2 * ctas, actor, critic, params, hp, 0, obs, N, rng, action_out, logp_out, value_out, head_out, state_copy);
 }
@@ -905,6 +917,8 @@ int nn_mlp_forward(b200rl_ctx* ctx, const MlpDesc& net, const float* params, con
     int nt = tiles_for(net.H, N);
     if (ctas > nt) ctas = nt;
     AcHyper hp{};
+    if (nn_tc_enabled() && nn_tc_supported(net))
+        return nn_tc_forward(ctx, ctas, net, net, params, hp, 1, obs, N, nullptr, nullptr, nullptr, nullptr, out, nullptr);
     if (net.H == 64) return launch_forward<64>(ctx, ctas, net, net, params, hp, 1, obs, N, nullptr, nullptr, nullptr, nullptr, out, nullptr);
     return launch_forward<128>(ctx, ctas, net, net, params, hp, 1, obs, N, nullptr, nullptr, nullptr, nullptr, out, nullptr);
 }

@@ -60,3 +60,10 @@ int nn_dqn_loss_grad(b200rl_ctx* ctx, const MlpDesc& q, const float* params, con
                      int double_dqn, float* partial, float* loss_partial, float* td_out);
 int nn_q_act(b200rl_ctx* ctx, const MlpDesc& q, const float* params, const float* obs, int64_t N, unsigned long long* rng, float epsilon,
              int32_t* action_out, float* q_out);
+
+// tensor-core (tcgen05) variants, nn_tc.cu.  Used for H = 64 unless disabled (B200RL_TC=0 or b200rl_set_tensor_cores(0)).
+bool nn_tc_enabled();
+bool nn_tc_supported(const MlpDesc& d);
+int nn_tc_forward(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp, int mode,
+                  const float* obs, int64_t N, unsigned long long* rng, void* action_out, float* logp_out, float* value_out, float* head_out,
+                  float* state_copy);

@@ -64,17 +64,23 @@ __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* mbar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}\n" ::"r"(smem_u32(mbar)), "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(mbar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// bounded wait: a lost completion traps (reported as a CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(mbar, parity); ++spin)
+        if (spin > (1u << 24)) __trap();
 }
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns (thread t gets lane base+t)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
