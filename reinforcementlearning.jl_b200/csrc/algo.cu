@@ -301,8 +301,8 @@ int b200rl_net_ac_step(b200rl_net* n, const b200rl_onpolicy_config* cfg, const f
     AcBatch b{(const float*)(base + o_s), ns, base + o_a, logp_old ? (const float*)(base + o_l) : nullptr, (const float*)(base + o_ad),
               (const float*)(base + o_r), (const int32_t*)(base + o_i), (uint32_t)total, 0u, 0u, Beff, 1.0f / (float)Beff,
               (const float*)(base + o_n)};
-    TRY(nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial));
-    int ctas = nn_grid_ctas(ctx, n->actor.H);
+    int ctas = nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
+    if (ctas < 0) return ctas;
     TRY(nn_reduce_partials(ctx, n->partial, ctas, n->np, n->grad, n->loss_partial, 2 * ctas, n->loss4));
     if (apply_update) {
         TRY(nn_clip_adam(ctx, n->params, n->grad, n->m, n->v, n->beta_t, n->np, cfg->max_grad_norm, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, 1.0f, n->gnorm));
@@ -494,7 +494,6 @@ int b200rl_onpolicy_update(b200rl_onpolicy* a, const int32_t* perm_host, float* 
     }
     AcHyper hp{c.clip_range, c.w_actor, c.w_critic, c.w_entropy, c.min_sigma, c.max_sigma, c.normalize_advantage, c.algo};
     int64_t B = NT_ / c.n_microbatches;
-    int ctas = nn_grid_ctas(ctx, n->actor.H);
     int row = 0;
     for (int e = 0; e < c.n_epochs; ++e) {
         for (int mb = 0; mb < c.n_microbatches; ++mb, ++row) {
@@ -502,7 +501,8 @@ int b200rl_onpolicy_update(b200rl_onpolicy* a, const int32_t* perm_host, float* 
                       perm_host ? a->perm_dev + (size_t)e * NT_ + (size_t)mb * B : nullptr,
                       (uint32_t)NT_, (uint32_t)(a->n_updates * 1000003u + (uint32_t)e * 7919u + 12345u), (uint32_t)(mb * B), B,
                       1.0f / ((float)B * (float)world), a->norm2};
-            TRY(nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial));
+            int ctas = nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
+            if (ctas < 0) return ctas;
             TRY(nn_reduce_partials(ctx, n->partial, ctas, n->np, n->grad, n->loss_partial, 2 * ctas, n->loss4));
             if (world > 1) {
                 TRY(b200rl_comm_allreduce_internal(ctx, n->grad, n->np, 0));
@@ -573,7 +573,7 @@ int b200rl_onpolicy_time_kernel(b200rl_onpolicy* a, int which, int reps, float* 
     int64_t N = a->N, T = a->T, NT_ = N * T, B = NT_ / c.n_microbatches;
     AcHyper hp{c.clip_range, c.w_actor, c.w_critic, c.w_entropy, c.min_sigma, c.max_sigma, c.normalize_advantage, c.algo};
     const float* obs = (const float*)env_field(a->env, B200RL_FIELD_OBS);
-    int ctas = nn_grid_ctas(ctx, n->actor.H);
+    int ctas = (nn_tc_enabled() && nn_tc_bwd_supported(n->actor, n->critic)) ? ctx->sm_count / 2 : nn_grid_ctas(ctx, n->actor.H);
     void* rng_copy = nullptr;
     if (which == 1) {
         TRY(ctx_scratch(ctx, (size_t)N * 32 + (size_t)N * 12 + 256, &rng_copy));
@@ -584,7 +584,8 @@ int b200rl_onpolicy_time_kernel(b200rl_onpolicy* a, int which, int reps, float* 
             case 0: {
                 AcBatch b{a->states, a->ns, a->actions, a->logp, a->adv, a->ret, nullptr, (uint32_t)NT_, 12345u, 0u, B, 1.0f / (float)B,
                           a->norm2};
-                return nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
+                int st = nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
+                return st < 0 ? st : B200RL_OK;
             }
             case 1: {
                 float* o = (float*)((char*)rng_copy + (size_t)N * 32);

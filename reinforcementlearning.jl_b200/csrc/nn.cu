@@ -929,8 +929,16 @@ int nn_ac_loss_grad(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& critic
     REQUIRE(actor.H == critic.H && actor.in == critic.in, B200RL_ERR_UNSUPPORTED, "actor and critic must share widths");
     int ctas = nn_grid_ctas(ctx, actor.H);
     int64_t np = actor.nparams() + critic.nparams();
-    if (actor.H == 64) return launch_ac<64>(ctx, 2 * ctas, actor, critic, params, hp, b, partial, loss_partial, np);
-    return launch_ac<128>(ctx, 2 * ctas, actor, critic, params, hp, b, partial, loss_partial, np);
+    int st;
+    if (nn_tc_enabled() && nn_tc_bwd_supported(actor, critic)) {
+        ctas = ctx->sm_count / 2;  // one 512-thread CTA per SM, roles alternate
+        st = nn_tc_ac_loss_grad(ctx, 2 * ctas, actor, critic, params, hp, b, partial, loss_partial, np);
+    } else if (actor.H == 64) {
+        st = launch_ac<64>(ctx, 2 * ctas, actor, critic, params, hp, b, partial, loss_partial, np);
+    } else {
+        st = launch_ac<128>(ctx, 2 * ctas, actor, critic, params, hp, b, partial, loss_partial, np);
+    }
+    return st != B200RL_OK ? st : ctas;  // number of gradient partials written (loss rows = 2x)
 }
 
 int nn_reduce_partials(b200rl_ctx* ctx, const float* partial, int n_partials, int64_t np, float* grad, const float* loss_partial,

@@ -46,6 +46,7 @@ int nn_policy_act(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& critic, 
                   float* head_out /* (nout, N) raw head outputs, for tests */, float* state_copy /* (in, N) */);
 int nn_mlp_forward(b200rl_ctx* ctx, const MlpDesc& net, const float* params, const float* obs, int64_t N, float* out /* (nout, N) */);
 // loss + backward: writes per-CTA partial gradients/losses; nn_reduce sums them in CTA order.
+// Returns the number of gradient partials written (> 0; loss rows = 2x that) or a negative status.
 int nn_ac_loss_grad(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
                     const AcBatch& b, float* partial /* [ctas][np] */, float* loss_partial /* [2*ctas][4] */);
 int nn_reduce_partials(b200rl_ctx* ctx, const float* partial, int n_partials, int64_t np, float* grad, const float* loss_partial,
@@ -67,3 +68,6 @@ bool nn_tc_supported(const MlpDesc& d);
 int nn_tc_forward(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp, int mode,
                   const float* obs, int64_t N, unsigned long long* rng, void* action_out, float* logp_out, float* value_out, float* head_out,
                   float* state_copy);
+bool nn_tc_bwd_supported(const MlpDesc& actor, const MlpDesc& critic);
+int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
+                       const AcBatch& b, float* partial, float* loss_partial, int64_t np);

@@ -269,6 +269,460 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
     if (warp == 0) umma::tmem_dealloc(tmem, 64);
 }
 
+
+// =====================================================================================================
+// K7 on tensor cores: PPO / A2C loss + backward for one minibatch.
+//   GEMM1  H2pre = H1 x W2^T            tcgen05 (3xTF32), D1 in TMEM
+//   GEMM2  dH1   = dP2 x W2             tcgen05 (3xTF32), D2 in TMEM, runs WHILE the CUDA cores do
+//   dW2   += dP2^T x H1                 FP32 FFMA straight from the operand images (samples are the
+//                                       contraction index: an MN-major tf32 operand is not available
+//                                       without swizzle)
+// One CTA per SM (512 threads), CTA role (actor / critic) = blockIdx & 1, persistent over tiles.
+// Thread <-> data: warp w: TMEM lane quadrant q = w % 4, feature block c = w / 4 (16 features);
+// thread = sample s = 32q + lane.  Shared memory: A (H1 full), P (dP2 full), LO (H1_lo, then dP2_lo,
+// then dP1 plain), two W2 operand images (full + lo each).
+constexpr int NT7 = 512;
+constexpr int G_F7 = 144;                  // chunk stride padded by 16 B: the FFMA reads of 16 chunks spread over the banks
+constexpr int G_S7 = 16 * G_F7 + 16;
+constexpr int IMG7 = 16 * G_S7;            // 37,120 B
+constexpr int LDP = 132;                   // dP1 plain [f][s] row stride (floats)
+
+struct SmemBwd {
+    alignas(128) uint8_t A[IMG7];          // H1 full
+    alignas(128) uint8_t P[IMG7];          // dP2 full
+    alignas(128) uint8_t LO[IMG7];         // lo parts / dP1 plain
+    alignas(128) uint8_t B1_full[WIMG_BYTES];  // (n = out o, k = in i)  = W2[o + 64 i]
+    alignas(128) uint8_t B1_lo[WIMG_BYTES];
+    alignas(128) uint8_t B2_full[WIMG_BYTES];  // (n = in i,  k = out j) = W2[j + 64 i]
+    alignas(128) uint8_t B2_lo[WIMG_BYTES];
+    float W1[kInMax * H];
+    float b1[H], b2[H];
+    float W3[H * kOutMax];
+    float b3[kOutMax];
+    float X[kInMax * TM];
+    float Zp[4 * kOutMax * TM];            // head partials [c][o][s]
+    float Dz[kOutMax * TM];
+    float Aux[4 * TM];
+    float Red[32];
+    alignas(8) uint64_t bar1;
+    alignas(8) uint64_t bar2;
+    uint32_t tmem;
+};
+__device__ __forceinline__ uint32_t img7_off(int s, int f) { return (uint32_t)((s >> 3) * G_S7 + (f >> 2) * G_F7 + (s & 7) * 16 + (f & 3) * 4); }
+__device__ __forceinline__ float dact_f(int act, float h) { return act == B200RL_ACT_RELU ? (h > 0.f ? 1.f : 0.f) : 1.f - h * h; }
+
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ uint32_t perm_index(uint32_t q, uint32_t n, uint32_t key) {
+    int bits = 2;
+    while ((1ull << bits) < n) bits += 2;
+    int hb = bits / 2;
+    uint32_t mask = (1u << hb) - 1;
+    uint32_t x = q;
+    do {
+        uint32_t l = x >> hb, r = x & mask;
+#pragma unroll
+        for (uint32_t round = 0; round < 4; ++round) {
+            uint32_t t = l ^ (mix32(r + key + round * 0x9E3779B9u) & mask);
+            l = r; r = t;
+        }
+        x = (l << hb) | r;
+    } while (x >= n);
+    return x;
+}
+__device__ __forceinline__ float block_sum512(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < NT7 / 32; ++k) t += red[k];
+    return t;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(NT7, 1)
+ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, AcBatch b, float* __restrict__ partial,
+                       float* __restrict__ loss_partial, int64_t np_total) {
+    extern __shared__ unsigned char smem_raw[];
+    SmemBwd& sm = *reinterpret_cast<SmemBwd*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int role = blockIdx.x & 1;
+    const int cta = blockIdx.x >> 1, nctas = gridDim.x >> 1;
+    const MlpDesc d = role ? critic : actor;
+    const int64_t poff = role ? actor.nparams() : 0;
+    const float* __restrict__ p = params + poff;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, c = warp >> 2;
+    const int s = 32 * q + lane;
+    {   // weights: small ones plain, W2 as two operand images
+        const float* b1 = p + (int64_t)H * d.in;
+        const float* W2 = b1 + H;
+        const float* b2 = W2 + (int64_t)H * H;
+        for (int k = tid; k < kInMax * H; k += NT7) sm.W1[k] = (k / H) < d.in ? p[k] : 0.f;
+        for (int k = tid; k < H; k += NT7) { sm.b1[k] = b1[k]; sm.b2[k] = b2[k]; }
+        for (int k = tid; k < H * kOutMax; k += NT7) {
+            int j = k / kOutMax, o = k % kOutMax;
+            sm.W3[k] = o < d.nout ? p[head_w(d, o, j)] : 0.f;
+        }
+        if (tid < kOutMax) sm.b3[tid] = tid < d.nout ? p[head_b(d, tid)] : 0.f;
+        for (int k = tid; k < H * H; k += NT7) {
+            int o = k % H, i = k / H;
+            float w = W2[k], wl = w - hi_part(w);
+            *reinterpret_cast<float*>(sm.B1_full + wimg_off(o, i)) = w;
+            *reinterpret_cast<float*>(sm.B1_lo + wimg_off(o, i)) = wl;
+            *reinterpret_cast<float*>(sm.B2_full + wimg_off(i, o)) = w;
+            *reinterpret_cast<float*>(sm.B2_lo + wimg_off(i, o)) = wl;
+        }
+    }
+    if (warp == 0) umma::tmem_alloc(&sm.tmem, 128);
+    if (tid == 32) { umma::mbar_init(&sm.bar1, 1); umma::mbar_init(&sm.bar2, 1); }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = sm.tmem;
+    const uint32_t idesc = umma::make_idesc_tf32(128, 64, 0, 0);
+
+    // persistent gradient accumulators
+    float g3[2][16];                 // dW3[o][16c + k] partial over this thread's sample slot
+    float w2acc[8][4];               // dW2[8jc + a][4ic + bb] partial over sample group sg
+    float db2acc[8];                 // (ic == 0 threads) sum_s dP2[s][8jc + a]
+    float w1acc = 0.f, db1acc = 0.f, gb3 = 0.f;
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) g3[o][k] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        db2acc[a] = 0.f;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) w2acc[a][bb] = 0.f;
+    }
+    const int sg = tid >> 7, jc = (tid & 127) >> 4, ic = tid & 15;
+    float l0 = 0.f, l1 = 0.f;
+    float mean = 0.f, inv_std = 1.f;
+    if (hp.normalize_adv && b.norm2) { mean = b.norm2[0]; inv_std = b.norm2[1]; }
+    const int64_t ntiles = (b.B + TM - 1) / TM;
+    uint32_t ph1 = 0, ph2 = 0;
+    for (int64_t tile = cta; tile < ntiles; tile += nctas) {
+        // ---- P0: gather ------------------------------------------------------------------------
+        if (tid < TM) {
+            int64_t j = tile * TM + tid;
+            bool valid = j < b.B;
+            int64_t gidx = 0;
+            if (valid) gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index((uint32_t)(b.perm_offset + j), b.perm_n, b.perm_key);
+            float x[kInMax] = {0.f, 0.f, 0.f, 0.f};
+            if (valid) {
+                if (b.ns == 4) {
+                    float4 v4 = reinterpret_cast<const float4*>(b.states)[gidx];
+                    x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[3] = v4.w;
+                } else {
+                    for (int i = 0; i < b.ns; ++i) x[i] = b.states[(int64_t)b.ns * gidx + i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kInMax; ++i) sm.X[i * TM + tid] = x[i];
+            float a_bits = 0.f, lp = 0.f, adv = 0.f, ret = 0.f;
+            if (valid) {
+                if (role == 0) {
+                    a_bits = reinterpret_cast<const float*>(b.actions)[gidx];
+                    lp = b.logp_old ? b.logp_old[gidx] : 0.f;
+                    adv = hp.normalize_adv ? (b.adv[gidx] - mean) * inv_std : b.adv[gidx];
+                } else {
+                    ret = b.ret[gidx];
+                }
+            }
+            sm.Aux[tid] = a_bits; sm.Aux[TM + tid] = lp; sm.Aux[2 * TM + tid] = adv; sm.Aux[3 * TM + tid] = ret;
+        }
+        __syncthreads();
+        // ---- P1: layer 1 -> H1 images -------------------------------------------------------------
+        {
+            float x[kInMax];
+#pragma unroll
+            for (int k = 0; k < kInMax; ++k) x[k] = sm.X[k * TM + s];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                const int f0 = 16 * c + 4 * ch;
+                float4 bb = *reinterpret_cast<const float4*>(sm.b1 + f0);
+                float h[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int k = 0; k < kInMax; ++k) {
+                    float4 w = *reinterpret_cast<const float4*>(sm.W1 + k * H + f0);
+                    h[0] = fmaf(w.x, x[k], h[0]); h[1] = fmaf(w.y, x[k], h[1]); h[2] = fmaf(w.z, x[k], h[2]); h[3] = fmaf(w.w, x[k], h[3]);
+                }
+                float l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { h[e] = act_f(d.act, h[e]); l[e] = h[e] - hi_part(h[e]); }
+                const uint32_t off = img7_off(s, f0);
+                *reinterpret_cast<float4*>(sm.A + off) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(sm.LO + off) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+        }
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        // ---- P2: GEMM1 on the tensor core -----------------------------------------------------------
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_gemm_3x(tmem, sm.A, sm.LO, G_F7, G_S7, 2 * G_F7, sm.B1_full, sm.B1_lo, G_F, GW_S, 2 * G_F, idesc, 8, false);
+            umma::commit(&sm.bar1);
+        }
+        umma::mbar_wait(&sm.bar1, ph1);
+        ph1 ^= 1u;
+        umma::fence_after_sync();
+        // ---- P3: H2 = act(D1 + b2) (registers) + head partials ---------------------------------------
+        float h2[16];
+        {
+            float v[16];
+            umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + 16 * c, v);
+            float zp[kOutMax] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int f = 16 * c + k;
+                h2[k] = act_f(d.act, v[k] + sm.b2[f]);
+                float4 w = *reinterpret_cast<const float4*>(sm.W3 + f * kOutMax);
+                zp[0] = fmaf(w.x, h2[k], zp[0]); zp[1] = fmaf(w.y, h2[k], zp[1]); zp[2] = fmaf(w.z, h2[k], zp[2]); zp[3] = fmaf(w.w, h2[k], zp[3]);
+            }
+#pragma unroll
+            for (int o = 0; o < kOutMax; ++o) sm.Zp[(c * kOutMax + o) * TM + s] = zp[o];
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        // ---- P4: loss stage (one thread per sample) -> dz ---------------------------------------------
+        if (tid < TM) {
+            const int ss = tid;
+            bool valid = (tile * TM + ss) < b.B;
+            float dz[kOutMax] = {0.f, 0.f, 0.f, 0.f};
+            if (valid) {
+                float z[kOutMax];
+#pragma unroll
+                for (int o = 0; o < kOutMax; ++o)
+                    z[o] = sm.b3[o] + ((sm.Zp[o * TM + ss] + sm.Zp[(kOutMax + o) * TM + ss]) + (sm.Zp[(2 * kOutMax + o) * TM + ss] + sm.Zp[(3 * kOutMax + o) * TM + ss]));
+                if (role == 1) {
+                    float err = sm.Aux[3 * TM + ss] - z[0];
+                    l0 += err * err;
+                    dz[0] = -2.0f * hp.w_critic * b.inv_B * err;
+                } else {
+                    float A = sm.Aux[2 * TM + ss];
+                    float lp_old = sm.Aux[TM + ss];
+                    float logp_a, gsel;
+                    if (!actor.heads2) {
+                        int na = actor.nout;
+                        float lp[kOutMax], pr[kOutMax];
+                        float m = -3.4e38f;
+#pragma unroll
+                        for (int o = 0; o < kOutMax; ++o) if (o < na) m = fmaxf(m, z[o]);
+                        float se = 0.f;
+#pragma unroll
+                        for (int o = 0; o < kOutMax; ++o) if (o < na) se += expf(z[o] - m);
+                        float ls = logf(se);
+                        float Hent = 0.f;
+#pragma unroll
+                        for (int o = 0; o < kOutMax; ++o) {
+                            lp[o] = (z[o] - m) - ls;
+                            pr[o] = o < na ? expf(lp[o]) : 0.f;
+                            if (o < na) Hent -= pr[o] * lp[o];
+                        }
+                        int a = __float_as_int(sm.Aux[ss]) - 1;
+                        logp_a = 0.f;
+#pragma unroll
+                        for (int o = 0; o < kOutMax; ++o) if (o == a) logp_a = lp[o];
+                        l1 += Hent;
+                        if (hp.algo == 0) {
+                            float ratio = expf(logp_a - lp_old);
+                            float u = ratio * A;
+                            float rc = fminf(fmaxf(ratio, 1.0f - hp.clip_range), 1.0f + hp.clip_range);
+                            float cc = rc * A;
+                            l0 += -fminf(u, cc);
+                            bool inside = ratio >= 1.0f - hp.clip_range && ratio <= 1.0f + hp.clip_range;
+                            gsel = (u < cc || inside) ? u : 0.f;
+                        } else {
+                            l0 += -(logp_a * A);
+                            gsel = A;
+                        }
+                        float dlogp = -hp.w_actor * b.inv_B * gsel;
+#pragma unroll
+                        for (int o = 0; o < kOutMax; ++o)
+                            if (o < na) dz[o] = dlogp * ((o == a ? 1.f : 0.f) - pr[o]) + hp.w_entropy * b.inv_B * pr[o] * (lp[o] + Hent);
+                    } else {
+                        float mu = z[0], raw = z[1];
+                        float sp = softplus_f(raw);
+                        float sigma = fminf(fmaxf(sp, hp.min_sigma), hp.max_sigma);
+                        bool clamped = sp < hp.min_sigma || sp > hp.max_sigma;
+                        float a = sm.Aux[ss];
+                        logp_a = normlogpdf1(mu, sigma, a);
+                        float Hent = logf(sigma) + 0.5f * (kLog2Pi + 1.0f);
+                        l1 += Hent;
+                        if (hp.algo == 0) {
+                            float ratio = expf(logp_a - lp_old);
+                            float u = ratio * A;
+                            float rc = fminf(fmaxf(ratio, 1.0f - hp.clip_range), 1.0f + hp.clip_range);
+                            float cc = rc * A;
+                            l0 += -fminf(u, cc);
+                            bool inside = ratio >= 1.0f - hp.clip_range && ratio <= 1.0f + hp.clip_range;
+                            gsel = (u < cc || inside) ? u : 0.f;
+                        } else {
+                            l0 += -(logp_a * A);
+                            gsel = A;
+                        }
+                        float dlogp = -hp.w_actor * b.inv_B * gsel;
+                        float sgm = sigma + 1e-8f, dd = a - mu;
+                        dz[0] = dlogp * (dd / (sgm * sgm));
+                        float dsig = dlogp * (-1.0f / sgm + (dd * dd) / (sgm * sgm * sgm)) - hp.w_entropy * b.inv_B * (1.0f / sigma);
+                        dz[1] = clamped ? 0.f : dsig * sigmoid_f(raw);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < kOutMax; ++o) sm.Dz[o * TM + ss] = dz[o];
+        }
+        __syncthreads();
+        // ---- P5: dW3 partials, dP2 = (W3^T dz) .* act'(H2) -> images -----------------------------------
+        {
+            float dz[kOutMax];
+#pragma unroll
+            for (int o = 0; o < kOutMax; ++o) dz[o] = sm.Dz[o * TM + s];
+            if (tid < d.nout) {
+                float a = 0.f;
+                for (int k = 0; k < TM; ++k) a += sm.Dz[tid * TM + k];
+                gb3 += a;
+            }
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                float dp[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = 4 * ch + e, f = 16 * c + k;
+                    float4 w = *reinterpret_cast<const float4*>(sm.W3 + f * kOutMax);
+                    float dh = fmaf(w.x, dz[0], fmaf(w.y, dz[1], fmaf(w.z, dz[2], w.w * dz[3])));
+                    dp[e] = dh * dact_f(d.act, h2[k]);
+                    lo[e] = dp[e] - hi_part(dp[e]);
+                    g3[0][k] = fmaf(dz[0], h2[k], g3[0][k]);
+                    g3[1][k] = fmaf(dz[1], h2[k], g3[1][k]);
+                }
+                const uint32_t off = img7_off(s, 16 * c + 4 * ch);
+                *reinterpret_cast<float4*>(sm.P + off) = make_float4(dp[0], dp[1], dp[2], dp[3]);
+                *reinterpret_cast<float4*>(sm.LO + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        // ---- P6: GEMM2 on the tensor core, overlapped with dW2 / db2 on the CUDA cores -------------------
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_gemm_3x(tmem + 64, sm.P, sm.LO, G_F7, G_S7, 2 * G_F7, sm.B2_full, sm.B2_lo, G_F, GW_S, 2 * G_F, idesc, 8, false);
+            umma::commit(&sm.bar2);
+        }
+        {
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+                const int ss = 32 * sg + k;
+                const uint32_t base = (uint32_t)((ss >> 3) * G_S7 + (ss & 7) * 16);
+                float4 p0 = *reinterpret_cast<const float4*>(sm.P + base + (2 * jc) * G_F7);
+                float4 p1 = *reinterpret_cast<const float4*>(sm.P + base + (2 * jc + 1) * G_F7);
+                float4 hh = *reinterpret_cast<const float4*>(sm.A + base + ic * G_F7);
+                const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                const float hv[4] = {hh.x, hh.y, hh.z, hh.w};
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) w2acc[a][bb] = fmaf(pv[a], hv[bb], w2acc[a][bb]);
+                    if (ic == 0) db2acc[a] += pv[a];
+                }
+            }
+        }
+        umma::mbar_wait(&sm.bar2, ph2);
+        ph2 ^= 1u;
+        umma::fence_after_sync();
+        // ---- P7: dP1 = D2 .* act'(H1) -> plain [f][s] in LO -------------------------------------------
+        {
+            float v[16];
+            umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + 64 + 16 * c, v);
+            float* dp1 = reinterpret_cast<float*>(sm.LO);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                float4 h1 = *reinterpret_cast<const float4*>(sm.A + img7_off(s, 16 * c + 4 * ch));
+                const float hv[4] = {h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dp1[(16 * c + 4 * ch + e) * LDP + s] = v[4 * ch + e] * dact_f(d.act, hv[e]);
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        // ---- P8: dW1 / db1 ------------------------------------------------------------------------------
+        if (tid < kInMax * H) {
+            const int i = tid >> 6, f = tid & 63;
+            const float* dp = reinterpret_cast<const float*>(sm.LO) + f * LDP;
+            const float* x = sm.X + i * TM;
+            float a = 0.f, bs = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < TM; k += 4) {
+                float4 p4 = *reinterpret_cast<const float4*>(dp + k);
+                float4 x4 = *reinterpret_cast<const float4*>(x + k);
+                a = fmaf(p4.x, x4.x, a); a = fmaf(p4.y, x4.y, a); a = fmaf(p4.z, x4.z, a); a = fmaf(p4.w, x4.w, a);
+                bs += (p4.x + p4.y) + (p4.z + p4.w);
+            }
+            w1acc += a;
+            if (i == 0) db1acc += bs;
+        }
+        __syncthreads();
+    }
+    // ---- write this CTA's gradient partial (fixed-order reductions through shared memory) -----------------
+    float* out = partial + (int64_t)cta * np_total + poff;
+    float* gW1 = out;
+    float* gb1 = out + (int64_t)H * d.in;
+    float* gW2 = gb1 + H;
+    float* gb2 = gW2 + (int64_t)H * H;
+    if (tid < kInMax * H) {
+        const int i = tid >> 6, f = tid & 63;
+        if (i < d.in) gW1[f + H * i] = w1acc;
+        if (i == 0) gb1[f] = db1acc;
+    }
+    float* red = reinterpret_cast<float*>(sm.A);  // A and P are contiguous: 2 * IMG7 bytes = 18,560 floats >= 4 * 4096
+    static_assert(2 * IMG7 >= 4 * 4096 * 4 + 4 * 64 * 4, "reduction scratch too small");
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) red[sg * 4096 + (8 * jc + a) + 64 * (4 * ic + bb)] = w2acc[a][bb];
+    if (ic == 0) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) red[4 * 4096 + sg * 64 + 8 * jc + a] = db2acc[a];
+    }
+    __syncthreads();
+    for (int k = tid; k < H * H; k += NT7) gW2[k] = (red[k] + red[4096 + k]) + (red[2 * 4096 + k] + red[3 * 4096 + k]);
+    if (tid < H) gb2[tid] = (red[4 * 4096 + tid] + red[4 * 4096 + 64 + tid]) + (red[4 * 4096 + 128 + tid] + red[4 * 4096 + 192 + tid]);
+    __syncthreads();
+    // dW3: [sample slot][o][f] -> sum over the 128 slots
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {   // static index: keeps g3 in registers
+        if (o < d.nout) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) red[s * 64 + 16 * c + k] = g3[o][k];
+        }
+        __syncthreads();
+        if (o < d.nout && tid < H) {
+            float a = 0.f;
+            for (int ss = 0; ss < TM; ++ss) a += red[ss * 64 + tid];
+            out[head_w(d, o, tid)] = a;
+        }
+        __syncthreads();
+    }
+    if (tid < d.nout) out[head_b(d, tid)] = gb3;
+    float t0 = block_sum512(l0, sm.Red);
+    float t1 = block_sum512(l1, sm.Red);
+    if (tid == 0) {
+        float* lp = loss_partial + (int64_t)blockIdx.x * 4;
+        lp[0] = role ? 0.f : t0; lp[1] = role ? 0.f : t1; lp[2] = role ? t0 : 0.f; lp[3] = 0.f;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 128);
+}
 }  // namespace
 
 bool nn_tc_supported(const MlpDesc& d) { return d.H == 64 && d.in <= kInMax && d.nout <= kOutMax; }
@@ -280,6 +734,18 @@ int nn_tc_forward(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc
     CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     forward_tc_kernel<<<grid, NT, smem, ctx->stream>>>(actor, critic, params, hp, mode, obs, N, rng, action_out, logp_out, value_out, head_out,
                                                        state_copy);
+    LAUNCH_CHECK(ctx);
+    return B200RL_OK;
+}
+
+bool nn_tc_bwd_supported(const MlpDesc& actor, const MlpDesc& critic) {
+    return actor.H == 64 && critic.H == 64 && actor.in <= kInMax && actor.nout <= 2 && critic.nout == 1;
+}
+int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
+                       const AcBatch& b, float* partial, float* loss_partial, int64_t np) {
+    size_t smem = sizeof(SmemBwd) + 128;
+    CUDA_TRY(cudaFuncSetAttribute(ac_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ac_loss_grad_tc_kernel<<<grid, NT7, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np);
     LAUNCH_CHECK(ctx);
     return B200RL_OK;
 }

@@ -261,3 +261,30 @@ def test_run_loop_with_host_actions_matches_fused_path(pkg, ctx):
         outs.append((net.get(), env.internal_state(), hook.stats))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert outs[0][2] == outs[1][2] and outs[0][2]["env_steps"] == 3 * T * n
+
+
+def test_tensor_core_and_cuda_core_paths_agree(pkg, ctx):
+    """K6/K7 exist as tcgen05 (3xTF32, H = 64) and FP32-FFMA kernels; both must meet the oracle
+    and each other well inside the 1e-5 bar."""
+    net, desc, params = make_net(pkg, ctx, 4, 64, 2, 0, 0, 17)
+    rng = np.random.default_rng(3)
+    total, B = 5000, 4096
+    states = rng.standard_normal((4, total)).astype(np.float32)
+    actions = rng.integers(1, 3, total).astype(np.int32)
+    logp_old = (-0.7 + 0.2 * rng.standard_normal(total)).astype(np.float32)
+    adv = rng.standard_normal(total).astype(np.float32); ret = rng.standard_normal(total).astype(np.float32)
+    idx = rng.permutation(total)[:B].astype(np.int32)
+    cfg = pkg.onpolicy_config(clip_range=0.2, w_entropy=0.01)
+    g_ref, l_ref = O.ac_loss_grad(0, desc, O.hyper_array(clip_range=0.2, w_entropy=0.01), params, states, actions, logp_old, adv, ret, idx, 0.1, 0.9)
+    out = {}
+    try:
+        for tc in (0, 1):
+            pkg._lib.check(ctx.lib.b200rl_set_tensor_cores(tc))
+            got = net.ac_step(cfg, states, actions, logp_old, adv, ret, idx, 0.1, 0.9, apply_update=False)
+            out[tc] = (net.get(pkg.learners.NET_GRAD), got, net.values(states[:, :1000]))
+            assert rel_err(out[tc][0], g_ref) < REL, tc
+            assert got["loss"] == pytest.approx(l_ref["loss"], rel=REL, abs=1e-6), tc
+    finally:
+        pkg._lib.check(ctx.lib.b200rl_set_tensor_cores(1))
+    assert rel_err(out[1][0], out[0][0]) < 5e-6
+    assert rel_err(out[1][2], out[0][2]) < 5e-6
