@@ -188,13 +188,17 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
         umma::fence_proxy_async();     // generic-proxy stores -> visible to the tensor core
         umma::fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_gemm_3x(tmem, sm.A_full, sm.A_lo, G_F, G_S, 2 * G_F, sm.B_full, sm.B_lo, G_F, GW_S, 2 * G_F, idesc, 8, false);
-            umma::commit(&sm.bar);
+        if (warp == 0) {  // warp 0 issues (one lane) and alone polls the mbarrier; everyone else parks on the CTA barrier
+            if (lane == 0) {
+                umma::fence_after_sync();
+                issue_gemm_3x(tmem, sm.A_full, sm.A_lo, G_F, G_S, 2 * G_F, sm.B_full, sm.B_lo, G_F, GW_S, 2 * G_F, idesc, 8, false);
+                umma::commit(&sm.bar);
+            }
+            __syncwarp();
+            umma::mbar_wait(&sm.bar, phase);
         }
-        umma::mbar_wait(&sm.bar, phase);
         phase ^= 1u;
+        __syncthreads();
         umma::fence_after_sync();
         {   // epilogue: H2 = act(D + b2); head partial over this thread's 32 features
             float v[32];
@@ -466,13 +470,17 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         umma::fence_before_sync();
         __syncthreads();
         // ---- P2: GEMM1 on the tensor core -----------------------------------------------------------
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_gemm_3x(tmem, sm.A, sm.LO, G_F7, G_S7, 2 * G_F7, sm.B1_full, sm.B1_lo, G_F, GW_S, 2 * G_F, idesc, 8, false);
-            umma::commit(&sm.bar1);
+        if (warp == 0) {
+            if (lane == 0) {
+                umma::fence_after_sync();
+                issue_gemm_3x(tmem, sm.A, sm.LO, G_F7, G_S7, 2 * G_F7, sm.B1_full, sm.B1_lo, G_F, GW_S, 2 * G_F, idesc, 8, false);
+                umma::commit(&sm.bar1);
+            }
+            __syncwarp();
+            umma::mbar_wait(&sm.bar1, ph1);
         }
-        umma::mbar_wait(&sm.bar1, ph1);
         ph1 ^= 1u;
+        __syncthreads();
         umma::fence_after_sync();
         // ---- P3: H2 = act(D1 + b2) (registers) + head partials ---------------------------------------
         float h2[16];
@@ -613,10 +621,13 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         umma::fence_before_sync();
         __syncthreads();
         // ---- P6: GEMM2 on the tensor core, overlapped with dW2 / db2 on the CUDA cores -------------------
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_gemm_3x(tmem + 64, sm.P, sm.LO, G_F7, G_S7, 2 * G_F7, sm.B2_full, sm.B2_lo, G_F, GW_S, 2 * G_F, idesc, 8, false);
-            umma::commit(&sm.bar2);
+        if (warp == 0) {
+            if (lane == 0) {
+                umma::fence_after_sync();
+                issue_gemm_3x(tmem + 64, sm.P, sm.LO, G_F7, G_S7, 2 * G_F7, sm.B2_full, sm.B2_lo, G_F, GW_S, 2 * G_F, idesc, 8, false);
+                umma::commit(&sm.bar2);
+            }
+            __syncwarp();
         }
         {
 #pragma unroll 4
@@ -636,8 +647,9 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 }
             }
         }
-        umma::mbar_wait(&sm.bar2, ph2);
+        if (warp == 0) umma::mbar_wait(&sm.bar2, ph2);
         ph2 ^= 1u;
+        __syncthreads();
         umma::fence_after_sync();
         // ---- P7: dP1 = D2 .* act'(H1) -> plain [f][s] in LO -------------------------------------------
         {

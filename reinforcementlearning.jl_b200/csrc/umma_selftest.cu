@@ -11,6 +11,7 @@ struct SelfTestArgs {
     uint32_t a_lbo, a_sbo, b_lbo, b_sbo;      // descriptor byte offsets
     uint32_t a_kadv, b_kadv;                  // start-address advance per K step (bytes)
     uint32_t idesc; int ksteps; int ncols;    // instruction descriptor, # MMA instructions, D columns to dump
+    int a_from_tmem;                           // 1: copy the (K-major, 64-wide) A image into TMEM columns 64.. and use the .ts form
     float* d_out;                             // [128][ncols]
 };
 
@@ -24,19 +25,41 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
     for (uint32_t k = threadIdx.x; k < a.b_bytes / 4; k += blockDim.x) ((uint32_t*)sb)[k] = ((const uint32_t*)a.b_img)[k];
     umma::fence_proxy_async();
     const int warp = threadIdx.x >> 5;
-    if (warp == 0) umma::tmem_alloc(&s_tmem, 64);
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 128);
     if (threadIdx.x == 32) umma::mbar_init(&s_bar, 1);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = s_tmem;
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < a.ksteps; ++k) {
-            uint64_t da = umma::make_desc(umma::smem_u32(sa) + k * a.a_kadv, a.a_lbo, a.a_sbo);
-            uint64_t db = umma::make_desc(umma::smem_u32(sb) + k * a.b_kadv, a.b_lbo, a.b_sbo);
-            umma::mma_tf32(tmem, da, db, a.idesc, k > 0 ? 1u : 0u);
+    if (a.a_from_tmem) {  // thread t <-> row m = t: A[m][k] (k < 64) read from the K-major image, stored to TMEM lane m, column 64 + k
+        const int m = threadIdx.x;
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            float v[16];
+            for (int k = 0; k < 16; ++k) {
+                int kk = c0 + k;
+                v[k] = *reinterpret_cast<const float*>(sa + (m / 8) * a.a_sbo + (kk / 4) * a.a_lbo + (m % 8) * 16 + (kk % 4) * 4);
+            }
+            umma::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 64 + c0, v);
         }
-        umma::commit(&s_bar);
+        umma::tmem_st_wait();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+    }
+    if (warp == 0) {
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < a.ksteps; ++k) {
+                uint64_t db = umma::make_desc(umma::smem_u32(sb) + k * a.b_kadv, a.b_lbo, a.b_sbo);
+                if (a.a_from_tmem) {
+                    umma::mma_tf32_ts(tmem, tmem + 64 + k * a.a_kadv, db, a.idesc, k > 0 ? 1u : 0u);
+                } else {
+                    uint64_t da = umma::make_desc(umma::smem_u32(sa) + k * a.a_kadv, a.a_lbo, a.a_sbo);
+                    umma::mma_tf32(tmem, da, db, a.idesc, k > 0 ? 1u : 0u);
+                }
+            }
+            umma::commit(&s_bar);
+        }
+        __syncwarp();
     }
     umma::mbar_wait(&s_bar, 0);
     umma::fence_after_sync();
@@ -48,12 +71,12 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 64);
+    if (warp == 0) umma::tmem_dealloc(tmem, 128);
 }
 }  // namespace
 
 extern "C" int b200rl_selftest_umma(b200rl_ctx* ctx, const void* a_img_host, uint32_t a_bytes, const void* b_img_host, uint32_t b_bytes,
-                                    const uint32_t* desc8 /* a_lbo,a_sbo,b_lbo,b_sbo,a_kadv,b_kadv,idesc,ksteps */, int ncols,
+                                    const uint32_t* desc8 /* a_lbo,a_sbo,b_lbo,b_sbo,a_kadv,b_kadv,idesc,ksteps | (a_from_tmem << 16) */, int ncols,
                                     float* d_out_host /* [128][ncols] */) {
     TRY(ctx_bind(ctx));
     REQUIRE(a_img_host && b_img_host && desc8 && d_out_host, B200RL_ERR_INVALID, "null argument");
@@ -65,7 +88,7 @@ extern "C" int b200rl_selftest_umma(b200rl_ctx* ctx, const void* a_img_host, uin
     uint8_t* da = (uint8_t*)sc; uint8_t* db = da + a_pad; float* dd = (float*)(db + b_pad);
     CUDA_TRY(cudaMemcpyAsync(da, a_img_host, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(db, b_img_host, b_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    SelfTestArgs a{da, a_bytes, db, b_bytes, desc8[0], desc8[1], desc8[2], desc8[3], desc8[4], desc8[5], desc8[6], (int)desc8[7], ncols, dd};
+    SelfTestArgs a{da, a_bytes, db, b_bytes, desc8[0], desc8[1], desc8[2], desc8[3], desc8[4], desc8[5], desc8[6], (int)(desc8[7] & 0xFFFF), ncols, dd, (int)(desc8[7] >> 16)};
     size_t smem = a_pad + b_pad;
     CUDA_TRY(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_selftest_kernel<<<1, 128, smem, ctx->stream>>>(a);
