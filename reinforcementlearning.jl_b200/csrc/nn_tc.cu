@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(NT, 2)
 forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, int mode, const float* __restrict__ obs,
                   int64_t N, unsigned long long* __restrict__ rng, void* __restrict__ action_out, float* __restrict__ logp_out,
                   float* __restrict__ value_out, float* __restrict__ head_out, float* __restrict__ state_copy) {
-    extern __shared__ unsigned char smem_raw[];
-    SmemFwd& sm = *reinterpret_cast<SmemFwd*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];   // keep the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
+    SmemFwd& sm = *reinterpret_cast<SmemFwd*>(smem_raw);
     const int nroles = mode == 0 ? 2 : 1;
     const int role = mode == 0 ? (blockIdx.x & 1) : 0;
     const int cta = blockIdx.x / nroles, nctas = gridDim.x / nroles;
@@ -352,8 +352,8 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 __global__ void __launch_bounds__(NT7, 1)
 ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, AcBatch b, float* __restrict__ partial,
                        float* __restrict__ loss_partial, int64_t np_total) {
-    extern __shared__ unsigned char smem_raw[];
-    SmemBwd& sm = *reinterpret_cast<SmemBwd*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    SmemBwd& sm = *reinterpret_cast<SmemBwd*>(smem_raw);
     const int role = blockIdx.x & 1;
     const int cta = blockIdx.x >> 1, nctas = gridDim.x >> 1;
     const MlpDesc d = role ? critic : actor;
@@ -630,20 +630,24 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             __syncwarp();
         }
         {
-#pragma unroll 4
-            for (int k = 0; k < 32; ++k) {
-                const int ss = 32 * sg + k;
-                const uint32_t base = (uint32_t)((ss >> 3) * G_S7 + (ss & 7) * 16);
-                float4 p0 = *reinterpret_cast<const float4*>(sm.P + base + (2 * jc) * G_F7);
-                float4 p1 = *reinterpret_cast<const float4*>(sm.P + base + (2 * jc + 1) * G_F7);
-                float4 hh = *reinterpret_cast<const float4*>(sm.A + base + ic * G_F7);
-                const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-                const float hv[4] = {hh.x, hh.y, hh.z, hh.w};
+            const uint8_t* pP = sm.P + (4 * sg) * G_S7 + (2 * jc) * G_F7;   // sample group sg = 4 eight-sample row groups
+            const uint8_t* pH = sm.A + (4 * sg) * G_S7 + ic * G_F7;
 #pragma unroll
-                for (int a = 0; a < 8; ++a) {
+            for (int g8 = 0; g8 < 4; ++g8) {
 #pragma unroll
-                    for (int bb = 0; bb < 4; ++bb) w2acc[a][bb] = fmaf(pv[a], hv[bb], w2acc[a][bb]);
-                    if (ic == 0) db2acc[a] += pv[a];
+                for (int r = 0; r < 8; ++r) {
+                    const int off = g8 * G_S7 + r * 16;
+                    float4 p0 = *reinterpret_cast<const float4*>(pP + off);
+                    float4 p1 = *reinterpret_cast<const float4*>(pP + off + G_F7);
+                    float4 hh = *reinterpret_cast<const float4*>(pH + off);
+                    const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                    const float hv[4] = {hh.x, hh.y, hh.z, hh.w};
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) {
+#pragma unroll
+                        for (int bb = 0; bb < 4; ++bb) w2acc[a][bb] = fmaf(pv[a], hv[bb], w2acc[a][bb]);
+                        db2acc[a] += pv[a];     // only the ic == 0 threads' sums are used
+                    }
                 }
             }
         }

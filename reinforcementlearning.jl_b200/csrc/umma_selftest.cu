@@ -88,7 +88,7 @@ extern "C" int b200rl_selftest_umma(b200rl_ctx* ctx, const void* a_img_host, uin
     uint8_t* da = (uint8_t*)sc; uint8_t* db = da + a_pad; float* dd = (float*)(db + b_pad);
     CUDA_TRY(cudaMemcpyAsync(da, a_img_host, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(db, b_img_host, b_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    SelfTestArgs a{da, a_bytes, db, b_bytes, desc8[0], desc8[1], desc8[2], desc8[3], desc8[4], desc8[5], desc8[6], (int)(desc8[7] & 0xFFFF), ncols, dd, (int)(desc8[7] >> 16)};
+    SelfTestArgs a{da, a_bytes, db, b_bytes, desc8[0], desc8[1], desc8[2], desc8[3], desc8[4], desc8[5], desc8[6], (int)(desc8[7] & 0xFFFF), ncols, (int)(desc8[7] >> 16), dd};
     size_t smem = a_pad + b_pad;
     CUDA_TRY(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_selftest_kernel<<<1, 128, smem, ctx->stream>>>(a);
