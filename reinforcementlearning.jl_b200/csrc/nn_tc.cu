@@ -275,26 +275,25 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
 
 
 // =====================================================================================================
-// K7 on tensor cores: PPO / A2C loss + backward for one minibatch.
-//   GEMM1  H2pre = H1 x W2^T            tcgen05 (3xTF32), D1 in TMEM
-//   GEMM2  dH1   = dP2 x W2             tcgen05 (3xTF32), D2 in TMEM, runs WHILE the CUDA cores do
-//   dW2   += dP2^T x H1                 FP32 FFMA straight from the operand images (samples are the
-//                                       contraction index: an MN-major tf32 operand is not available
-//                                       without swizzle)
-// One CTA per SM (512 threads), CTA role (actor / critic) = blockIdx & 1, persistent over tiles.
-// Thread <-> data: warp w: TMEM lane quadrant q = w % 4, feature block c = w / 4 (16 features);
-// thread = sample s = 32q + lane.  Shared memory: A (H1 full), P (dP2 full), LO (H1_lo, then dP2_lo,
-// then dP1 plain), two W2 operand images (full + lo each).
+// K7 on tensor cores: PPO / A2C loss + backward for one minibatch, all three 64x64 GEMMs on tcgen05.
+//   GEMM1  H2pre[s][o] = sum_i H1[s][i]  W2[o][i]     A = H1 (TMEM, written by tcgen05.st), B = W2 image (smem)
+//   GEMM2  dH1[s][i]   = sum_j dP2[s][j] W2[j][i]     A = dP2 (TMEM),                        B = W2^T image (smem)
+//   GEMM3  dW2[j][i]  += sum_s dP2[s][j] H1[s][i]     A = dP2^T, B = H1^T: feature-major K-major images (smem),
+//                                                     accumulated in TMEM across ALL tiles of the CTA, read once.
+// every product 3xTF32 (full*full + full*lo + lo*full; the tensor core ignores the low 13 mantissa bits).
+// GEMM3 of tile t is only awaited right before tile t+1 overwrites its operand images, so it overlaps
+// with the next gather / layer-1.  One CTA per SM (512 threads, role = blockIdx & 1), persistent.
+// Thread <-> data: warp w: TMEM lane quadrant q = w % 4, feature block c = w / 4; thread = sample s = 32q + lane.
 constexpr int NT7 = 512;
-constexpr int G_F7 = 144;                  // chunk stride padded by 16 B: the FFMA reads of 16 chunks spread over the banks
-constexpr int G_S7 = 16 * G_F7 + 16;
-constexpr int IMG7 = 16 * G_S7;            // 37,120 B
-constexpr int LDP = 132;                   // dP1 plain [f][s] row stride (floats)
+constexpr int GS_T = 32 * G_F + 16;       // feature-major image: stride between 8-feature row groups (32 sample chunks + pad)
+constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples]
+constexpr uint32_t COL_D1 = 0, COL_D2 = 64, COL_D3 = 128, COL_AF = 192, COL_AL = 256;
 
 struct SmemBwd {
-    alignas(128) uint8_t A[IMG7];          // H1 full
-    alignas(128) uint8_t P[IMG7];          // dP2 full
-    alignas(128) uint8_t LO[IMG7];         // lo parts / dP1 plain
+    alignas(128) uint8_t FP_full[FIMG];    // dP2^T  (rows = feature j, K = sample)
+    alignas(128) uint8_t FP_lo[FIMG];
+    alignas(128) uint8_t FH_full[FIMG];    // H1^T
+    alignas(128) uint8_t FH_lo[FIMG];
     alignas(128) uint8_t B1_full[WIMG_BYTES];  // (n = out o, k = in i)  = W2[o + 64 i]
     alignas(128) uint8_t B1_lo[WIMG_BYTES];
     alignas(128) uint8_t B2_full[WIMG_BYTES];  // (n = in i,  k = out j) = W2[j + 64 i]
@@ -310,9 +309,10 @@ struct SmemBwd {
     float Red[32];
     alignas(8) uint64_t bar1;
     alignas(8) uint64_t bar2;
+    alignas(8) uint64_t bar3;
     uint32_t tmem;
 };
-__device__ __forceinline__ uint32_t img7_off(int s, int f) { return (uint32_t)((s >> 3) * G_S7 + (f >> 2) * G_F7 + (s & 7) * 16 + (f & 3) * 4); }
+__device__ __forceinline__ uint32_t fimg_off(int f, int s) { return (uint32_t)((f >> 3) * GS_T + (s >> 2) * G_F + (f & 7) * 16 + (s & 3) * 4); }
 __device__ __forceinline__ float dact_f(int act, float h) { return act == B200RL_ACT_RELU ? (h > 0.f ? 1.f : 0.f) : 1.f - h * h; }
 
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
@@ -349,6 +349,40 @@ __device__ __forceinline__ float block_sum512(float v, float* red) {
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
+// A from TMEM (AF / AL columns), B from smem images; 3xTF32
+__device__ __forceinline__ void issue_gemm_ts_3x(uint32_t d_tmem, uint32_t a_full, uint32_t a_lo, const uint8_t* b_full, const uint8_t* b_lo,
+                                                 uint32_t idesc) {
+    const uint32_t bf = umma::smem_u32(b_full), bl = umma::smem_u32(b_lo);
+    uint32_t acc = 0u;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = pass == 2 ? a_lo : a_full;
+        const uint32_t b = pass == 1 ? bl : bf;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            umma::mma_tf32_ts(d_tmem, a + 8 * k, umma::make_desc(b + k * 2 * G_F, G_F, GW_S), idesc, acc);
+            acc = 1u;
+        }
+    }
+}
+
+// sum over the 32 lanes of NV values each (NV a power of two <= 32... here 32): lane L ends with the totals of
+// values 2L*(NV/64).. — for NV = 32: lane L holds the total of value index L in v[0].
+__device__ __forceinline__ float lane_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+        const int half = 16 >> st, off = 16 >> st;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int n = 0; n < half; ++n) {
+            float send = upper ? v[n] : v[n + half];
+            float keep = upper ? v[n + half] : v[n];
+            v[n] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];   // value index = lane
+}
+
 __global__ void __launch_bounds__(NT7, 1)
 ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, AcBatch b, float* __restrict__ partial,
                        float* __restrict__ loss_partial, int64_t np_total) {
@@ -362,7 +396,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, c = warp >> 2;
     const int s = 32 * q + lane;
-    {   // weights: small ones plain, W2 as two operand images
+    {   // weights: small ones plain, W2 as two operand images; H1^T image row 64.. are never read (N = 64)
         const float* b1 = p + (int64_t)H * d.in;
         const float* W2 = b1 + H;
         const float* b2 = W2 + (int64_t)H * H;
@@ -382,36 +416,30 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             *reinterpret_cast<float*>(sm.B2_lo + wimg_off(i, o)) = wl;
         }
     }
-    if (warp == 0) umma::tmem_alloc(&sm.tmem, 128);
-    if (tid == 32) { umma::mbar_init(&sm.bar1, 1); umma::mbar_init(&sm.bar2, 1); }
+    if (warp == 0) umma::tmem_alloc(&sm.tmem, 512);
+    if (tid == 32) { umma::mbar_init(&sm.bar1, 1); umma::mbar_init(&sm.bar2, 1); umma::mbar_init(&sm.bar3, 1); }
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = sm.tmem;
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     const uint32_t idesc = umma::make_idesc_tf32(128, 64, 0, 0);
 
-    // persistent gradient accumulators
-    float g3[2][16];                 // dW3[o][16c + k] partial over this thread's sample slot
-    float w2acc[8][4];               // dW2[8jc + a][4ic + bb] partial over sample group sg
-    float db2acc[8];                 // (ic == 0 threads) sum_s dP2[s][8jc + a]
-    float w1acc = 0.f, db1acc = 0.f, gb3 = 0.f;
+    // persistent per-thread gradient partials (over this thread's sample slot), reduced once at the end
+    float g3[2][16];                  // dW3[o][16c + k]
+    float db2acc[16], db1acc[16];     // sum_s dP2 / dP1 [16c + k]
+    float w1p0 = 0.f, w1p1 = 0.f;     // after the lane transpose-reduce: dW1 entries n = lane (features 16c..16c+7) / n = lane (16c+8..)
+    float gb3 = 0.f;
 #pragma unroll
-    for (int o = 0; o < 2; ++o)
-#pragma unroll
-        for (int k = 0; k < 16; ++k) g3[o][k] = 0.f;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        db2acc[a] = 0.f;
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) w2acc[a][bb] = 0.f;
-    }
-    const int sg = tid >> 7, jc = (tid & 127) >> 4, ic = tid & 15;
+    for (int k = 0; k < 16; ++k) { g3[0][k] = 0.f; g3[1][k] = 0.f; db2acc[k] = 0.f; db1acc[k] = 0.f; }
     float l0 = 0.f, l1 = 0.f;
     float mean = 0.f, inv_std = 1.f;
     if (hp.normalize_adv && b.norm2) { mean = b.norm2[0]; inv_std = b.norm2[1]; }
     const int64_t ntiles = (b.B + TM - 1) / TM;
-    uint32_t ph1 = 0, ph2 = 0;
+    uint32_t ph1 = 0, ph2 = 0, ph3 = 0;
+    bool gemm3_pending = false;
+    uint32_t d3_acc = 0u;
     for (int64_t tile = cta; tile < ntiles; tile += nctas) {
         // ---- P0: gather ------------------------------------------------------------------------
         if (tid < TM) {
@@ -442,12 +470,17 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             }
             sm.Aux[tid] = a_bits; sm.Aux[TM + tid] = lp; sm.Aux[2 * TM + tid] = adv; sm.Aux[3 * TM + tid] = ret;
         }
+        if (warp == 0 && gemm3_pending) umma::mbar_wait(&sm.bar3, ph3);   // previous tile's GEMM3 has consumed the F images
+        if (gemm3_pending) ph3 ^= 1u;
         __syncthreads();
-        // ---- P1: layer 1 -> H1 images -------------------------------------------------------------
+        umma::fence_after_sync();
+        // ---- P1: layer 1 -> H1 (registers), TMEM A operand, H1^T image -----------------------------
+        float h1[16];
+        float x[kInMax];   // kept in registers: the next tile's gather may overwrite sm.X before this tile's P7 runs
         {
-            float x[kInMax];
 #pragma unroll
             for (int k = 0; k < kInMax; ++k) x[k] = sm.X[k * TM + s];
+            float lo[16];
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 const int f0 = 16 * c + 4 * ch;
@@ -458,22 +491,31 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                     float4 w = *reinterpret_cast<const float4*>(sm.W1 + k * H + f0);
                     h[0] = fmaf(w.x, x[k], h[0]); h[1] = fmaf(w.y, x[k], h[1]); h[2] = fmaf(w.z, x[k], h[2]); h[3] = fmaf(w.w, x[k], h[3]);
                 }
-                float l[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { h[e] = act_f(d.act, h[e]); l[e] = h[e] - hi_part(h[e]); }
-                const uint32_t off = img7_off(s, f0);
-                *reinterpret_cast<float4*>(sm.A + off) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(sm.LO + off) = make_float4(l[0], l[1], l[2], l[3]);
+                for (int e = 0; e < 4; ++e) {
+                    float hv = act_f(d.act, h[e]);
+                    h1[4 * ch + e] = hv;
+                    lo[4 * ch + e] = hv - hi_part(hv);
+                }
             }
+            umma::tmem_st16(tmem + lane_base + COL_AF + 16 * c, h1);
+            umma::tmem_st16(tmem + lane_base + COL_AL + 16 * c, lo);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t off = fimg_off(16 * c + k, s);
+                *reinterpret_cast<float*>(sm.FH_full + off) = h1[k];
+                *reinterpret_cast<float*>(sm.FH_lo + off) = lo[k];
+            }
+            umma::tmem_st_wait();
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
         __syncthreads();
-        // ---- P2: GEMM1 on the tensor core -----------------------------------------------------------
+        // ---- GEMM1 ------------------------------------------------------------------------------------
         if (warp == 0) {
             if (lane == 0) {
                 umma::fence_after_sync();
-                issue_gemm_3x(tmem, sm.A, sm.LO, G_F7, G_S7, 2 * G_F7, sm.B1_full, sm.B1_lo, G_F, GW_S, 2 * G_F, idesc, 8, false);
+                issue_gemm_ts_3x(tmem + COL_D1, tmem + COL_AF, tmem + COL_AL, sm.B1_full, sm.B1_lo, idesc);
                 umma::commit(&sm.bar1);
             }
             __syncwarp();
@@ -486,7 +528,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         float h2[16];
         {
             float v[16];
-            umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + 16 * c, v);
+            umma::tmem_ld16(tmem + lane_base + COL_D1 + 16 * c, v);
             float zp[kOutMax] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -589,7 +631,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             for (int o = 0; o < kOutMax; ++o) sm.Dz[o * TM + ss] = dz[o];
         }
         __syncthreads();
-        // ---- P5: dW3 partials, dP2 = (W3^T dz) .* act'(H2) -> images -----------------------------------
+        // ---- P5: dW3 / db2 partials, dP2 = (W3^T dz) .* act'(H2) -> TMEM A operand + dP2^T image ----------
         {
             float dz[kOutMax];
 #pragma unroll
@@ -599,134 +641,129 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 for (int k = 0; k < TM; ++k) a += sm.Dz[tid * TM + k];
                 gb3 += a;
             }
+            float dp[16], lo[16];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                float dp[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = 4 * ch + e, f = 16 * c + k;
-                    float4 w = *reinterpret_cast<const float4*>(sm.W3 + f * kOutMax);
-                    float dh = fmaf(w.x, dz[0], fmaf(w.y, dz[1], fmaf(w.z, dz[2], w.w * dz[3])));
-                    dp[e] = dh * dact_f(d.act, h2[k]);
-                    lo[e] = dp[e] - hi_part(dp[e]);
-                    g3[0][k] = fmaf(dz[0], h2[k], g3[0][k]);
-                    g3[1][k] = fmaf(dz[1], h2[k], g3[1][k]);
-                }
-                const uint32_t off = img7_off(s, 16 * c + 4 * ch);
-                *reinterpret_cast<float4*>(sm.P + off) = make_float4(dp[0], dp[1], dp[2], dp[3]);
-                *reinterpret_cast<float4*>(sm.LO + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            for (int k = 0; k < 16; ++k) {
+                const int f = 16 * c + k;
+                float4 w = *reinterpret_cast<const float4*>(sm.W3 + f * kOutMax);
+                float dh = fmaf(w.x, dz[0], fmaf(w.y, dz[1], fmaf(w.z, dz[2], w.w * dz[3])));
+                dp[k] = dh * dact_f(d.act, h2[k]);
+                lo[k] = dp[k] - hi_part(dp[k]);
+                db2acc[k] += dp[k];
+                g3[0][k] = fmaf(dz[0], h2[k], g3[0][k]);
+                g3[1][k] = fmaf(dz[1], h2[k], g3[1][k]);
             }
+            umma::tmem_st16(tmem + lane_base + COL_AF + 16 * c, dp);   // GEMM1 (the previous reader of AF/AL) has completed
+            umma::tmem_st16(tmem + lane_base + COL_AL + 16 * c, lo);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t off = fimg_off(16 * c + k, s);
+                *reinterpret_cast<float*>(sm.FP_full + off) = dp[k];
+                *reinterpret_cast<float*>(sm.FP_lo + off) = lo[k];
+            }
+            umma::tmem_st_wait();
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
         __syncthreads();
-        // ---- P6: GEMM2 on the tensor core, overlapped with dW2 / db2 on the CUDA cores -------------------
+        // ---- GEMM2 (awaited) and GEMM3 (awaited lazily at the top of the next tile) --------------------
         if (warp == 0) {
             if (lane == 0) {
                 umma::fence_after_sync();
-                issue_gemm_3x(tmem + 64, sm.P, sm.LO, G_F7, G_S7, 2 * G_F7, sm.B2_full, sm.B2_lo, G_F, GW_S, 2 * G_F, idesc, 8, false);
+                issue_gemm_ts_3x(tmem + COL_D2, tmem + COL_AF, tmem + COL_AL, sm.B2_full, sm.B2_lo, idesc);
                 umma::commit(&sm.bar2);
-            }
-            __syncwarp();
-        }
-        {
-            const uint8_t* pP = sm.P + (4 * sg) * G_S7 + (2 * jc) * G_F7;   // sample group sg = 4 eight-sample row groups
-            const uint8_t* pH = sm.A + (4 * sg) * G_S7 + ic * G_F7;
+                // dW2 += dP2^T x H1 : K = 128 samples in 16 steps of 8 (two 4-sample chunks)
+                const uint32_t af = umma::smem_u32(sm.FP_full), al = umma::smem_u32(sm.FP_lo);
+                const uint32_t bf = umma::smem_u32(sm.FH_full), bl = umma::smem_u32(sm.FH_lo);
+                uint32_t acc = d3_acc;
+#pragma unroll 1
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a = pass == 2 ? al : af;
+                    const uint32_t bb = pass == 1 ? bl : bf;
 #pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int off = g8 * G_S7 + r * 16;
-                    float4 p0 = *reinterpret_cast<const float4*>(pP + off);
-                    float4 p1 = *reinterpret_cast<const float4*>(pP + off + G_F7);
-                    float4 hh = *reinterpret_cast<const float4*>(pH + off);
-                    const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-                    const float hv[4] = {hh.x, hh.y, hh.z, hh.w};
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) {
-#pragma unroll
-                        for (int bb = 0; bb < 4; ++bb) w2acc[a][bb] = fmaf(pv[a], hv[bb], w2acc[a][bb]);
-                        db2acc[a] += pv[a];     // only the ic == 0 threads' sums are used
+                    for (int k = 0; k < 16; ++k) {
+                        umma::mma_tf32(tmem + COL_D3, umma::make_desc(a + k * 2 * G_F, G_F, GS_T), umma::make_desc(bb + k * 2 * G_F, G_F, GS_T), idesc, acc);
+                        acc = 1u;
                     }
                 }
+                umma::commit(&sm.bar3);
             }
+            __syncwarp();
+            umma::mbar_wait(&sm.bar2, ph2);
         }
-        if (warp == 0) umma::mbar_wait(&sm.bar2, ph2);
+        d3_acc = 1u;
+        gemm3_pending = true;
         ph2 ^= 1u;
         __syncthreads();
         umma::fence_after_sync();
-        // ---- P7: dP1 = D2 .* act'(H1) -> plain [f][s] in LO -------------------------------------------
+        // ---- P7: dP1 = D2 .* act'(H1); dW1 / db1 partials (no shared memory) ----------------------------
         {
             float v[16];
-            umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + 64 + 16 * c, v);
-            float* dp1 = reinterpret_cast<float*>(sm.LO);
+            umma::tmem_ld16(tmem + lane_base + COL_D2 + 16 * c, v);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                float4 h1 = *reinterpret_cast<const float4*>(sm.A + img7_off(s, 16 * c + 4 * ch));
-                const float hv[4] = {h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) dp1[(16 * c + 4 * ch + e) * LDP + s] = v[4 * ch + e] * dact_f(d.act, hv[e]);
+            for (int k = 0; k < 16; ++k) {
+                v[k] = v[k] * dact_f(d.act, h1[k]);
+                db1acc[k] += v[k];
             }
+            // dW1[f][i] = sum_s dP1[s][f] x[s][i]: transpose-reduce over the warp's 32 samples, 8 features (32 values) at a time
+            float t[32];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int i = 0; i < kInMax; ++i) t[4 * k + i] = v[k] * x[i];
+            w1p0 += lane_transpose_reduce32(t, lane);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int i = 0; i < kInMax; ++i) t[4 * k + i] = v[8 + k] * x[i];
+            w1p1 += lane_transpose_reduce32(t, lane);
         }
         umma::fence_before_sync();
-        __syncthreads();
-        // ---- P8: dW1 / db1 ------------------------------------------------------------------------------
-        if (tid < kInMax * H) {
-            const int i = tid >> 6, f = tid & 63;
-            const float* dp = reinterpret_cast<const float*>(sm.LO) + f * LDP;
-            const float* x = sm.X + i * TM;
-            float a = 0.f, bs = 0.f;
-#pragma unroll 4
-            for (int k = 0; k < TM; k += 4) {
-                float4 p4 = *reinterpret_cast<const float4*>(dp + k);
-                float4 x4 = *reinterpret_cast<const float4*>(x + k);
-                a = fmaf(p4.x, x4.x, a); a = fmaf(p4.y, x4.y, a); a = fmaf(p4.z, x4.z, a); a = fmaf(p4.w, x4.w, a);
-                bs += (p4.x + p4.y) + (p4.z + p4.w);
-            }
-            w1acc += a;
-            if (i == 0) db1acc += bs;
-        }
-        __syncthreads();
     }
-    // ---- write this CTA's gradient partial (fixed-order reductions through shared memory) -----------------
+    // ---- drain: last GEMM3, then write this CTA's gradient partial (fixed-order reductions) ---------------
+    if (warp == 0 && gemm3_pending) umma::mbar_wait(&sm.bar3, ph3);
+    __syncthreads();
+    umma::fence_after_sync();
     float* out = partial + (int64_t)cta * np_total + poff;
     float* gW1 = out;
     float* gb1 = out + (int64_t)H * d.in;
     float* gW2 = gb1 + H;
     float* gb2 = gW2 + (int64_t)H * H;
-    if (tid < kInMax * H) {
-        const int i = tid >> 6, f = tid & 63;
-        if (i < d.in) gW1[f + H * i] = w1acc;
-        if (i == 0) gb1[f] = db1acc;
+    if (q < 2) {   // D3 rows j = TMEM lanes 0..63
+        float v[16];
+        if (gemm3_pending) umma::tmem_ld16(tmem + lane_base + COL_D3 + 16 * c, v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) gW2[s + H * (16 * c + k)] = gemm3_pending ? v[k] : 0.f;
     }
-    float* red = reinterpret_cast<float*>(sm.A);  // A and P are contiguous: 2 * IMG7 bytes = 18,560 floats >= 4 * 4096
-    static_assert(2 * IMG7 >= 4 * 4096 * 4 + 4 * 64 * 4, "reduction scratch too small");
+    float* red = reinterpret_cast<float*>(sm.FP_full);   // 4 * FIMG bytes contiguous, all MMAs are done
+    // per-sample-slot partials -> [slot][64] in shared memory -> column sums in slot order
+    for (int pass = 0; pass < 4; ++pass) {
+        // pass 0: db2, 1: db1, 2: dW3[0], 3: dW3[1]
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) red[sg * 4096 + (8 * jc + a) + 64 * (4 * ic + bb)] = w2acc[a][bb];
-    if (ic == 0) {
-#pragma unroll
-        for (int a = 0; a < 8; ++a) red[4 * 4096 + sg * 64 + 8 * jc + a] = db2acc[a];
-    }
-    __syncthreads();
-    for (int k = tid; k < H * H; k += NT7) gW2[k] = (red[k] + red[4096 + k]) + (red[2 * 4096 + k] + red[3 * 4096 + k]);
-    if (tid < H) gb2[tid] = (red[4 * 4096 + tid] + red[4 * 4096 + 64 + tid]) + (red[4 * 4096 + 128 + tid] + red[4 * 4096 + 192 + tid]);
-    __syncthreads();
-    // dW3: [sample slot][o][f] -> sum over the 128 slots
-#pragma unroll
-    for (int o = 0; o < 2; ++o) {   // static index: keeps g3 in registers
-        if (o < d.nout) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) red[s * 64 + 16 * c + k] = g3[o][k];
+        for (int k = 0; k < 16; ++k) {
+            float val = pass == 0 ? db2acc[k] : pass == 1 ? db1acc[k] : pass == 2 ? g3[0][k] : g3[1][k];
+            red[s * 64 + 16 * c + k] = val;
         }
         __syncthreads();
-        if (o < d.nout && tid < H) {
+        if (tid < H) {
             float a = 0.f;
             for (int ss = 0; ss < TM; ++ss) a += red[ss * 64 + tid];
-            out[head_w(d, o, tid)] = a;
+            if (pass == 0) gb2[tid] = a;
+            else if (pass == 1) gb1[tid] = a;
+            else if (pass - 2 < d.nout) out[head_w(d, pass - 2, tid)] = a;
         }
         __syncthreads();
+    }
+    // dW1: lane holds entry n = lane of feature half h (n = 4*k + i, k < 8): sum the 4 quadrant warps of block c
+    red[(q * 4 + c) * 64 + lane] = w1p0;
+    red[(q * 4 + c) * 64 + 32 + lane] = w1p1;
+    __syncthreads();
+    if (tid < kInMax * H) {
+        const int cc = tid >> 6, n = tid & 63;            // feature block, entry within the block (half*32 + 4*k + i)
+        const int half = n >> 5, kk = (n & 31) >> 2, i = n & 3;
+        const int f = 16 * cc + 8 * half + kk;
+        float a = (red[(0 * 4 + cc) * 64 + n] + red[(1 * 4 + cc) * 64 + n]) + (red[(2 * 4 + cc) * 64 + n] + red[(3 * 4 + cc) * 64 + n]);
+        if (i < d.in) gW1[f + H * i] = a;
     }
     if (tid < d.nout) out[head_b(d, tid)] = gb3;
     float t0 = block_sum512(l0, sm.Red);
@@ -737,8 +774,9 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 128);
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
+
 }  // namespace
 
 bool nn_tc_supported(const MlpDesc& d) { return d.H == 64 && d.in <= kInMax && d.nout <= kOutMax; }
