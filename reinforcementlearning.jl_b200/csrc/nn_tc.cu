@@ -285,7 +285,9 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
 // with the next gather / layer-1.  One CTA per SM (512 threads, role = blockIdx & 1), persistent.
 // Thread <-> data: warp w: TMEM lane quadrant q = w % 4, feature block c = w / 4; thread = sample s = 32q + lane.
 constexpr int NT7 = 512;
-constexpr int GS_T = 32 * G_F + 16;       // feature-major image: stride between 8-feature row groups (32 sample chunks + pad)
+constexpr int GF_T = 144;                 // feature-major image: stride between 4-sample chunks; 144 = 128 + 16 makes the 32 lanes'
+                                          // 4-byte transposed stores hit 32 different banks (with 128 they would 8-way conflict)
+constexpr int GS_T = 32 * GF_T + 16;      // stride between 8-feature row groups
 constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples]
 constexpr uint32_t COL_D1 = 0, COL_D2 = 64, COL_D3 = 128, COL_AF = 192, COL_AL = 256;
 
@@ -312,7 +314,7 @@ struct SmemBwd {
     alignas(8) uint64_t bar3;
     uint32_t tmem;
 };
-__device__ __forceinline__ uint32_t fimg_off(int f, int s) { return (uint32_t)((f >> 3) * GS_T + (s >> 2) * G_F + (f & 7) * 16 + (s & 3) * 4); }
+__device__ __forceinline__ uint32_t fimg_off(int f, int s) { return (uint32_t)((f >> 3) * GS_T + (s >> 2) * GF_T + (f & 7) * 16 + (s & 3) * 4); }
 __device__ __forceinline__ float dact_f(int act, float h) { return act == B200RL_ACT_RELU ? (h > 0.f ? 1.f : 0.f) : 1.f - h * h; }
 
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
@@ -682,7 +684,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                     const uint32_t bb = pass == 1 ? bl : bf;
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
-                        umma::mma_tf32(tmem + COL_D3, umma::make_desc(a + k * 2 * G_F, G_F, GS_T), umma::make_desc(bb + k * 2 * G_F, G_F, GS_T), idesc, acc);
+                        umma::mma_tf32(tmem + COL_D3, umma::make_desc(a + k * 2 * GF_T, GF_T, GS_T), umma::make_desc(bb + k * 2 * GF_T, GF_T, GS_T), idesc, acc);
                         acc = 1u;
                     }
                 }
