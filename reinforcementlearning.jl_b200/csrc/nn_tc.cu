@@ -312,6 +312,8 @@ struct SmemBwd {
     alignas(8) uint64_t bar1;
     alignas(8) uint64_t bar2;
     alignas(8) uint64_t bar3;
+    alignas(8) uint64_t ready1;
+    alignas(8) uint64_t ready2;
     uint32_t tmem;
 };
 __device__ __forceinline__ uint32_t fimg_off(int f, int s) { return (uint32_t)((f >> 3) * GS_T + (s >> 2) * GF_T + (f & 7) * 16 + (s & 3) * 4); }
@@ -385,7 +387,118 @@ __device__ __forceinline__ float lane_transpose_reduce32(float (&v)[32], int lan
     return v[0];   // value index = lane
 }
 
-__global__ void __launch_bounds__(NT7, 1)
+// issue `ksteps` MMAs whose operands advance by a fixed amount per step: descriptors differ only in the
+// 14-bit start-address field, so the loop body is one 32-bit add per descriptor + the MMA itself
+__device__ __forceinline__ void issue_ss(uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t a_adv16, uint32_t b_adv16, int ksteps, uint32_t idesc,
+                                         uint32_t& acc) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (k < ksteps) {
+            umma::mma_tf32(d_tmem, a0 + (uint64_t)(k * a_adv16), b0 + (uint64_t)(k * b_adv16), idesc, acc);
+            acc = 1u;
+        }
+    }
+}
+__device__ __forceinline__ void issue_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b0, uint32_t b_adv16, uint32_t idesc, uint32_t& acc) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        umma::mma_tf32_ts(d_tmem, a_tmem + 8 * k, b0 + (uint64_t)(k * b_adv16), idesc, acc);
+        acc = 1u;
+    }
+}
+
+// worker-only barrier (the MMA warp never joins it)
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(mbar)) : "memory");
+}
+
+// per-sample loss and d(loss)/d(head outputs); identical arithmetic on every thread that evaluates a sample
+struct LossOut { float dz[kOutMax]; float l0, l1; };
+__device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, const AcHyper& hp, float inv_B, const float (&z)[kOutMax],
+                                               float a_bits, float lp_old, float A, float ret) {
+    LossOut r;
+#pragma unroll
+    for (int o = 0; o < kOutMax; ++o) r.dz[o] = 0.f;
+    r.l0 = 0.f; r.l1 = 0.f;
+    if (role == 1) {
+        float err = ret - z[0];
+        r.l0 = err * err;
+        r.dz[0] = -2.0f * hp.w_critic * inv_B * err;
+        return r;
+    }
+    float logp_a, gsel;
+    if (!actor.heads2) {
+        int na = actor.nout;
+        float lp[kOutMax], pr[kOutMax];
+        float m = -3.4e38f;
+#pragma unroll
+        for (int o = 0; o < kOutMax; ++o) if (o < na) m = fmaxf(m, z[o]);
+        float se = 0.f;
+#pragma unroll
+        for (int o = 0; o < kOutMax; ++o) if (o < na) se += expf(z[o] - m);
+        float ls = logf(se);
+        float Hent = 0.f;
+#pragma unroll
+        for (int o = 0; o < kOutMax; ++o) {
+            lp[o] = (z[o] - m) - ls;
+            pr[o] = o < na ? expf(lp[o]) : 0.f;
+            if (o < na) Hent -= pr[o] * lp[o];
+        }
+        int a = __float_as_int(a_bits) - 1;
+        logp_a = 0.f;
+#pragma unroll
+        for (int o = 0; o < kOutMax; ++o) if (o == a) logp_a = lp[o];
+        r.l1 = Hent;
+        if (hp.algo == 0) {
+            float ratio = expf(logp_a - lp_old);
+            float u = ratio * A;
+            float rc = fminf(fmaxf(ratio, 1.0f - hp.clip_range), 1.0f + hp.clip_range);
+            float cc = rc * A;
+            r.l0 = -fminf(u, cc);
+            bool inside = ratio >= 1.0f - hp.clip_range && ratio <= 1.0f + hp.clip_range;
+            gsel = (u < cc || inside) ? u : 0.f;
+        } else {
+            r.l0 = -(logp_a * A);
+            gsel = A;
+        }
+        float dlogp = -hp.w_actor * inv_B * gsel;
+#pragma unroll
+        for (int o = 0; o < kOutMax; ++o)
+            if (o < na) r.dz[o] = dlogp * ((o == a ? 1.f : 0.f) - pr[o]) + hp.w_entropy * inv_B * pr[o] * (lp[o] + Hent);
+    } else {
+        float mu = z[0], raw = z[1];
+        float sp = softplus_f(raw);
+        float sigma = fminf(fmaxf(sp, hp.min_sigma), hp.max_sigma);
+        bool clamped = sp < hp.min_sigma || sp > hp.max_sigma;
+        float a = a_bits;
+        logp_a = normlogpdf1(mu, sigma, a);
+        float Hent = logf(sigma) + 0.5f * (kLog2Pi + 1.0f);
+        r.l1 = Hent;
+        if (hp.algo == 0) {
+            float ratio = expf(logp_a - lp_old);
+            float u = ratio * A;
+            float rc = fminf(fmaxf(ratio, 1.0f - hp.clip_range), 1.0f + hp.clip_range);
+            float cc = rc * A;
+            r.l0 = -fminf(u, cc);
+            bool inside = ratio >= 1.0f - hp.clip_range && ratio <= 1.0f + hp.clip_range;
+            gsel = (u < cc || inside) ? u : 0.f;
+        } else {
+            r.l0 = -(logp_a * A);
+            gsel = A;
+        }
+        float dlogp = -hp.w_actor * inv_B * gsel;
+        float sgm = sigma + 1e-8f, dd = a - mu;
+        r.dz[0] = dlogp * (dd / (sgm * sgm));
+        float dsig = dlogp * (-1.0f / sgm + (dd * dd) / (sgm * sgm * sgm)) - hp.w_entropy * inv_B * (1.0f / sigma);
+        r.dz[1] = clamped ? 0.f : dsig * sigmoid_f(raw);
+    }
+    return r;
+}
+
+constexpr int NT7_ALL = NT7;        // 16 warps; warp 0 lane 0 also feeds the tensor core (descriptors prebuilt: ~2 instructions per MMA)
+
+__global__ void __launch_bounds__(NT7_ALL, 1)
 ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, AcBatch b, float* __restrict__ partial,
                        float* __restrict__ loss_partial, int64_t np_total) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -396,9 +509,10 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     const int64_t poff = role ? actor.nparams() : 0;
     const float* __restrict__ p = params + poff;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, c = warp >> 2;
+    const bool is_mma_warp = false;
+    const int q = warp & 3, c = (warp >> 2) & 3;
     const int s = 32 * q + lane;
-    {   // weights: small ones plain, W2 as two operand images; H1^T image row 64.. are never read (N = 64)
+    if (!is_mma_warp) {   // weights: small ones plain, W2 as two operand images
         const float* b1 = p + (int64_t)H * d.in;
         const float* W2 = b1 + H;
         const float* b2 = W2 + (int64_t)H * H;
@@ -419,62 +533,108 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         }
     }
     if (warp == 0) umma::tmem_alloc(&sm.tmem, 512);
-    if (tid == 32) { umma::mbar_init(&sm.bar1, 1); umma::mbar_init(&sm.bar2, 1); umma::mbar_init(&sm.bar3, 1); }
+    if (tid == 32) {
+        umma::mbar_init(&sm.bar1, 1); umma::mbar_init(&sm.bar2, 1); umma::mbar_init(&sm.bar3, 1);
+        umma::mbar_init(&sm.ready1, 1); umma::mbar_init(&sm.ready2, 1);
+    }
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = sm.tmem;
-    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     const uint32_t idesc = umma::make_idesc_tf32(128, 64, 0, 0);
+    const int64_t ntiles = (b.B + TM - 1) / TM;
 
+    if (is_mma_warp) {
+        // ================= MMA-issue warp: waits for operands, feeds the tensor core, signals completion =========
+        uint32_t ph = 0;
+        uint32_t d3_acc = 0u;
+        for (int64_t tile = cta; tile < ntiles; tile += nctas) {
+            umma::mbar_wait(&sm.ready1, ph);
+            umma::fence_after_sync();
+            if (lane == 0) {
+                issue_gemm_ts_3x(tmem + COL_D1, tmem + COL_AF, tmem + COL_AL, sm.B1_full, sm.B1_lo, idesc);
+                umma::commit(&sm.bar1);
+            }
+            __syncwarp();
+            umma::mbar_wait(&sm.ready2, ph);
+            umma::fence_after_sync();
+            if (lane == 0) {
+                issue_gemm_ts_3x(tmem + COL_D2, tmem + COL_AF, tmem + COL_AL, sm.B2_full, sm.B2_lo, idesc);
+                umma::commit(&sm.bar2);
+                // dW2 += dP2^T x H1 : K = 128 samples in 16 steps of 8 (two 4-sample chunks)
+                const uint32_t af = umma::smem_u32(sm.FP_full), al = umma::smem_u32(sm.FP_lo);
+                const uint32_t bf = umma::smem_u32(sm.FH_full), bl = umma::smem_u32(sm.FH_lo);
+                uint32_t acc = d3_acc;
+#pragma unroll 1
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a = pass == 2 ? al : af;
+                    const uint32_t bb = pass == 1 ? bl : bf;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        umma::mma_tf32(tmem + COL_D3, umma::make_desc(a + k * 2 * GF_T, GF_T, GS_T), umma::make_desc(bb + k * 2 * GF_T, GF_T, GS_T), idesc, acc);
+                        acc = 1u;
+                    }
+                }
+                umma::commit(&sm.bar3);
+            }
+            __syncwarp();
+            d3_acc = 1u;
+            ph ^= 1u;
+        }
+    } else {
+    // ================= 16 worker warps =======================================================================
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     // persistent per-thread gradient partials (over this thread's sample slot), reduced once at the end
     float g3[2][16];                  // dW3[o][16c + k]
     float db2acc[16], db1acc[16];     // sum_s dP2 / dP1 [16c + k]
-    float w1p0 = 0.f, w1p1 = 0.f;     // after the lane transpose-reduce: dW1 entries n = lane (features 16c..16c+7) / n = lane (16c+8..)
-    float gb3 = 0.f;
+    float w1p0 = 0.f, w1p1 = 0.f;     // after the lane transpose-reduce: dW1 entries n = lane of feature half 0 / 1
+    float gb3a0 = 0.f, gb3a1 = 0.f;   // (c == 0 threads) sum_s dz[o]
 #pragma unroll
     for (int k = 0; k < 16; ++k) { g3[0][k] = 0.f; g3[1][k] = 0.f; db2acc[k] = 0.f; db1acc[k] = 0.f; }
     float l0 = 0.f, l1 = 0.f;
     float mean = 0.f, inv_std = 1.f;
     if (hp.normalize_adv && b.norm2) { mean = b.norm2[0]; inv_std = b.norm2[1]; }
-    const int64_t ntiles = (b.B + TM - 1) / TM;
     uint32_t ph1 = 0, ph2 = 0, ph3 = 0;
-    bool gemm3_pending = false;
-    uint32_t d3_acc = 0u;
-    for (int64_t tile = cta; tile < ntiles; tile += nctas) {
-        // ---- P0: gather ------------------------------------------------------------------------
-        if (tid < TM) {
-            int64_t j = tile * TM + tid;
-            bool valid = j < b.B;
-            int64_t gidx = 0;
-            if (valid) gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index((uint32_t)(b.perm_offset + j), b.perm_n, b.perm_key);
-            float x[kInMax] = {0.f, 0.f, 0.f, 0.f};
-            if (valid) {
-                if (b.ns == 4) {
-                    float4 v4 = reinterpret_cast<const float4*>(b.states)[gidx];
-                    x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[3] = v4.w;
-                } else {
-                    for (int i = 0; i < b.ns; ++i) x[i] = b.states[(int64_t)b.ns * gidx + i];
-                }
-            }
+    // random gather of one sample (x[0..3], action bits, logp_old, normalised advantage, return) into registers;
+    // issued one tile ahead so the L2 / HBM latency hides behind the previous tile's GEMMs
+    float pf[8];
+    bool have_pf = false;
+    auto gather_tile = [&](int64_t t, float (&o)[8]) {
+        int64_t j = t * TM + tid;
+        bool valid = j < b.B;
 #pragma unroll
-            for (int i = 0; i < kInMax; ++i) sm.X[i * TM + tid] = x[i];
-            float a_bits = 0.f, lp = 0.f, adv = 0.f, ret = 0.f;
-            if (valid) {
-                if (role == 0) {
-                    a_bits = reinterpret_cast<const float*>(b.actions)[gidx];
-                    lp = b.logp_old ? b.logp_old[gidx] : 0.f;
-                    adv = hp.normalize_adv ? (b.adv[gidx] - mean) * inv_std : b.adv[gidx];
-                } else {
-                    ret = b.ret[gidx];
-                }
-            }
-            sm.Aux[tid] = a_bits; sm.Aux[TM + tid] = lp; sm.Aux[2 * TM + tid] = adv; sm.Aux[3 * TM + tid] = ret;
+        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+        if (!valid) return;
+        int64_t gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index((uint32_t)(b.perm_offset + j), b.perm_n, b.perm_key);
+        if (b.ns == 4) {
+            float4 v4 = reinterpret_cast<const float4*>(b.states)[gidx];
+            o[0] = v4.x; o[1] = v4.y; o[2] = v4.z; o[3] = v4.w;
+        } else {
+            for (int i = 0; i < b.ns; ++i) o[i] = b.states[(int64_t)b.ns * gidx + i];
+        }
+        if (role == 0) {
+            o[4] = reinterpret_cast<const float*>(b.actions)[gidx];
+            o[5] = b.logp_old ? b.logp_old[gidx] : 0.f;
+            o[6] = hp.normalize_adv ? (b.adv[gidx] - mean) * inv_std : b.adv[gidx];
+        } else {
+            o[7] = b.ret[gidx];
+        }
+    };
+    bool gemm3_pending = false;
+    uint32_t d3_acc = 0u;   // meaningful on the issuing lane only
+    for (int64_t tile = cta; tile < ntiles; tile += nctas) {
+        // ---- P0: publish this tile's gathered samples (prefetched during the previous tile), prefetch the next ----
+        if (tid < TM) {
+            if (!have_pf) gather_tile(tile, pf);
+#pragma unroll
+            for (int i = 0; i < kInMax; ++i) sm.X[i * TM + tid] = pf[i];
+            sm.Aux[tid] = pf[4]; sm.Aux[TM + tid] = pf[5]; sm.Aux[2 * TM + tid] = pf[6]; sm.Aux[3 * TM + tid] = pf[7];
+            if (tile + nctas < ntiles) { gather_tile(tile + nctas, pf); have_pf = true; } else have_pf = false;
         }
         if (warp == 0 && gemm3_pending) umma::mbar_wait(&sm.bar3, ph3);   // previous tile's GEMM3 has consumed the F images
         if (gemm3_pending) ph3 ^= 1u;
-        __syncthreads();
+        worker_sync();
         umma::fence_after_sync();
         // ---- P1: layer 1 -> H1 (registers), TMEM A operand, H1^T image -----------------------------
         float h1[16];
@@ -512,19 +672,22 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
-        __syncthreads();
-        // ---- GEMM1 ------------------------------------------------------------------------------------
+        worker_sync();
         if (warp == 0) {
             if (lane == 0) {
                 umma::fence_after_sync();
-                issue_gemm_ts_3x(tmem + COL_D1, tmem + COL_AF, tmem + COL_AL, sm.B1_full, sm.B1_lo, idesc);
+                uint32_t acc = 0u;
+                const uint64_t dB1f = umma::make_desc(umma::smem_u32(sm.B1_full), G_F, GW_S), dB1l = umma::make_desc(umma::smem_u32(sm.B1_lo), G_F, GW_S);
+                issue_ts(tmem + COL_D1, tmem + COL_AF, dB1f, 2 * G_F / 16, idesc, acc);
+                issue_ts(tmem + COL_D1, tmem + COL_AF, dB1l, 2 * G_F / 16, idesc, acc);
+                issue_ts(tmem + COL_D1, tmem + COL_AL, dB1f, 2 * G_F / 16, idesc, acc);
                 umma::commit(&sm.bar1);
             }
             __syncwarp();
             umma::mbar_wait(&sm.bar1, ph1);
         }
         ph1 ^= 1u;
-        __syncthreads();
+        worker_sync();
         umma::fence_after_sync();
         // ---- P3: H2 = act(D1 + b2) (registers) + head partials ---------------------------------------
         float h2[16];
@@ -543,106 +706,20 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             for (int o = 0; o < kOutMax; ++o) sm.Zp[(c * kOutMax + o) * TM + s] = zp[o];
         }
         umma::fence_before_sync();
-        __syncthreads();
-        // ---- P4: loss stage (one thread per sample) -> dz ---------------------------------------------
-        if (tid < TM) {
-            const int ss = tid;
-            bool valid = (tile * TM + ss) < b.B;
-            float dz[kOutMax] = {0.f, 0.f, 0.f, 0.f};
-            if (valid) {
-                float z[kOutMax];
-#pragma unroll
-                for (int o = 0; o < kOutMax; ++o)
-                    z[o] = sm.b3[o] + ((sm.Zp[o * TM + ss] + sm.Zp[(kOutMax + o) * TM + ss]) + (sm.Zp[(2 * kOutMax + o) * TM + ss] + sm.Zp[(3 * kOutMax + o) * TM + ss]));
-                if (role == 1) {
-                    float err = sm.Aux[3 * TM + ss] - z[0];
-                    l0 += err * err;
-                    dz[0] = -2.0f * hp.w_critic * b.inv_B * err;
-                } else {
-                    float A = sm.Aux[2 * TM + ss];
-                    float lp_old = sm.Aux[TM + ss];
-                    float logp_a, gsel;
-                    if (!actor.heads2) {
-                        int na = actor.nout;
-                        float lp[kOutMax], pr[kOutMax];
-                        float m = -3.4e38f;
-#pragma unroll
-                        for (int o = 0; o < kOutMax; ++o) if (o < na) m = fmaxf(m, z[o]);
-                        float se = 0.f;
-#pragma unroll
-                        for (int o = 0; o < kOutMax; ++o) if (o < na) se += expf(z[o] - m);
-                        float ls = logf(se);
-                        float Hent = 0.f;
-#pragma unroll
-                        for (int o = 0; o < kOutMax; ++o) {
-                            lp[o] = (z[o] - m) - ls;
-                            pr[o] = o < na ? expf(lp[o]) : 0.f;
-                            if (o < na) Hent -= pr[o] * lp[o];
-                        }
-                        int a = __float_as_int(sm.Aux[ss]) - 1;
-                        logp_a = 0.f;
-#pragma unroll
-                        for (int o = 0; o < kOutMax; ++o) if (o == a) logp_a = lp[o];
-                        l1 += Hent;
-                        if (hp.algo == 0) {
-                            float ratio = expf(logp_a - lp_old);
-                            float u = ratio * A;
-                            float rc = fminf(fmaxf(ratio, 1.0f - hp.clip_range), 1.0f + hp.clip_range);
-                            float cc = rc * A;
-                            l0 += -fminf(u, cc);
-                            bool inside = ratio >= 1.0f - hp.clip_range && ratio <= 1.0f + hp.clip_range;
-                            gsel = (u < cc || inside) ? u : 0.f;
-                        } else {
-                            l0 += -(logp_a * A);
-                            gsel = A;
-                        }
-                        float dlogp = -hp.w_actor * b.inv_B * gsel;
-#pragma unroll
-                        for (int o = 0; o < kOutMax; ++o)
-                            if (o < na) dz[o] = dlogp * ((o == a ? 1.f : 0.f) - pr[o]) + hp.w_entropy * b.inv_B * pr[o] * (lp[o] + Hent);
-                    } else {
-                        float mu = z[0], raw = z[1];
-                        float sp = softplus_f(raw);
-                        float sigma = fminf(fmaxf(sp, hp.min_sigma), hp.max_sigma);
-                        bool clamped = sp < hp.min_sigma || sp > hp.max_sigma;
-                        float a = sm.Aux[ss];
-                        logp_a = normlogpdf1(mu, sigma, a);
-                        float Hent = logf(sigma) + 0.5f * (kLog2Pi + 1.0f);
-                        l1 += Hent;
-                        if (hp.algo == 0) {
-                            float ratio = expf(logp_a - lp_old);
-                            float u = ratio * A;
-                            float rc = fminf(fmaxf(ratio, 1.0f - hp.clip_range), 1.0f + hp.clip_range);
-                            float cc = rc * A;
-                            l0 += -fminf(u, cc);
-                            bool inside = ratio >= 1.0f - hp.clip_range && ratio <= 1.0f + hp.clip_range;
-                            gsel = (u < cc || inside) ? u : 0.f;
-                        } else {
-                            l0 += -(logp_a * A);
-                            gsel = A;
-                        }
-                        float dlogp = -hp.w_actor * b.inv_B * gsel;
-                        float sgm = sigma + 1e-8f, dd = a - mu;
-                        dz[0] = dlogp * (dd / (sgm * sgm));
-                        float dsig = dlogp * (-1.0f / sgm + (dd * dd) / (sgm * sgm * sgm)) - hp.w_entropy * b.inv_B * (1.0f / sigma);
-                        dz[1] = clamped ? 0.f : dsig * sigmoid_f(raw);
-                    }
-                }
-            }
-#pragma unroll
-            for (int o = 0; o < kOutMax; ++o) sm.Dz[o * TM + ss] = dz[o];
-        }
-        __syncthreads();
-        // ---- P5: dW3 / db2 partials, dP2 = (W3^T dz) .* act'(H2) -> TMEM A operand + dP2^T image ----------
+        worker_sync();
+        // ---- P4+P5: loss (evaluated by all four feature-block threads of a sample: no exchange, no idle warps),
+        //            dW3 / db2 partials, dP2 = (W3^T dz) .* act'(H2) -> TMEM A operand + dP2^T image -------------
         {
+            float z[kOutMax];
+#pragma unroll
+            for (int o = 0; o < kOutMax; ++o)
+                z[o] = sm.b3[o] + ((sm.Zp[o * TM + s] + sm.Zp[(kOutMax + o) * TM + s]) + (sm.Zp[(2 * kOutMax + o) * TM + s] + sm.Zp[(3 * kOutMax + o) * TM + s]));
+            const bool valid = (tile * TM + s) < b.B;
+            LossOut lo_ = sample_loss(actor, role, hp, b.inv_B, z, sm.Aux[s], sm.Aux[TM + s], sm.Aux[2 * TM + s], sm.Aux[3 * TM + s]);
             float dz[kOutMax];
 #pragma unroll
-            for (int o = 0; o < kOutMax; ++o) dz[o] = sm.Dz[o * TM + s];
-            if (tid < d.nout) {
-                float a = 0.f;
-                for (int k = 0; k < TM; ++k) a += sm.Dz[tid * TM + k];
-                gb3 += a;
-            }
+            for (int o = 0; o < kOutMax; ++o) dz[o] = valid ? lo_.dz[o] : 0.f;
+            if (c == 0 && valid) { l0 += lo_.l0; l1 += lo_.l1; gb3a0 += dz[0]; gb3a1 += dz[1]; }
             float dp[16], lo[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -667,36 +744,30 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
-        __syncthreads();
-        // ---- GEMM2 (awaited) and GEMM3 (awaited lazily at the top of the next tile) --------------------
+        worker_sync();
         if (warp == 0) {
             if (lane == 0) {
                 umma::fence_after_sync();
-                issue_gemm_ts_3x(tmem + COL_D2, tmem + COL_AF, tmem + COL_AL, sm.B2_full, sm.B2_lo, idesc);
+                uint32_t acc = 0u;
+                const uint64_t dB2f = umma::make_desc(umma::smem_u32(sm.B2_full), G_F, GW_S), dB2l = umma::make_desc(umma::smem_u32(sm.B2_lo), G_F, GW_S);
+                const uint64_t dFPf = umma::make_desc(umma::smem_u32(sm.FP_full), GF_T, GS_T), dFPl = umma::make_desc(umma::smem_u32(sm.FP_lo), GF_T, GS_T);
+                const uint64_t dFHf = umma::make_desc(umma::smem_u32(sm.FH_full), GF_T, GS_T), dFHl = umma::make_desc(umma::smem_u32(sm.FH_lo), GF_T, GS_T);
+                issue_ts(tmem + COL_D2, tmem + COL_AF, dB2f, 2 * G_F / 16, idesc, acc);
+                issue_ts(tmem + COL_D2, tmem + COL_AF, dB2l, 2 * G_F / 16, idesc, acc);
+                issue_ts(tmem + COL_D2, tmem + COL_AL, dB2f, 2 * G_F / 16, idesc, acc);
                 umma::commit(&sm.bar2);
-                // dW2 += dP2^T x H1 : K = 128 samples in 16 steps of 8 (two 4-sample chunks)
-                const uint32_t af = umma::smem_u32(sm.FP_full), al = umma::smem_u32(sm.FP_lo);
-                const uint32_t bf = umma::smem_u32(sm.FH_full), bl = umma::smem_u32(sm.FH_lo);
-                uint32_t acc = d3_acc;
-#pragma unroll 1
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t a = pass == 2 ? al : af;
-                    const uint32_t bb = pass == 1 ? bl : bf;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        umma::mma_tf32(tmem + COL_D3, umma::make_desc(a + k * 2 * GF_T, GF_T, GS_T), umma::make_desc(bb + k * 2 * GF_T, GF_T, GS_T), idesc, acc);
-                        acc = 1u;
-                    }
-                }
+                // dW2 += dP2^T x H1 : K = 128 samples in 16 steps of 8 (two 4-sample chunks); awaited lazily (next tile)
+                issue_ss(tmem + COL_D3, dFPf, dFHf, 2 * GF_T / 16, 2 * GF_T / 16, 16, idesc, d3_acc);
+                issue_ss(tmem + COL_D3, dFPf, dFHl, 2 * GF_T / 16, 2 * GF_T / 16, 16, idesc, d3_acc);
+                issue_ss(tmem + COL_D3, dFPl, dFHf, 2 * GF_T / 16, 2 * GF_T / 16, 16, idesc, d3_acc);
                 umma::commit(&sm.bar3);
             }
             __syncwarp();
             umma::mbar_wait(&sm.bar2, ph2);
         }
-        d3_acc = 1u;
         gemm3_pending = true;
         ph2 ^= 1u;
-        __syncthreads();
+        worker_sync();
         umma::fence_after_sync();
         // ---- P7: dP1 = D2 .* act'(H1); dW1 / db1 partials (no shared memory) ----------------------------
         {
@@ -724,7 +795,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     }
     // ---- drain: last GEMM3, then write this CTA's gradient partial (fixed-order reductions) ---------------
     if (warp == 0 && gemm3_pending) umma::mbar_wait(&sm.bar3, ph3);
-    __syncthreads();
+    worker_sync();
     umma::fence_after_sync();
     float* out = partial + (int64_t)cta * np_total + poff;
     float* gW1 = out;
@@ -746,7 +817,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             float val = pass == 0 ? db2acc[k] : pass == 1 ? db1acc[k] : pass == 2 ? g3[0][k] : g3[1][k];
             red[s * 64 + 16 * c + k] = val;
         }
-        __syncthreads();
+        worker_sync();
         if (tid < H) {
             float a = 0.f;
             for (int ss = 0; ss < TM; ++ss) a += red[ss * 64 + tid];
@@ -754,12 +825,13 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             else if (pass == 1) gb1[tid] = a;
             else if (pass - 2 < d.nout) out[head_w(d, pass - 2, tid)] = a;
         }
-        __syncthreads();
+        worker_sync();
     }
     // dW1: lane holds entry n = lane of feature half h (n = 4*k + i, k < 8): sum the 4 quadrant warps of block c
     red[(q * 4 + c) * 64 + lane] = w1p0;
     red[(q * 4 + c) * 64 + 32 + lane] = w1p1;
-    __syncthreads();
+    if (c == 0) { red[4096 + s] = gb3a0; red[4096 + TM + s] = gb3a1; }
+    worker_sync();
     if (tid < kInMax * H) {
         const int cc = tid >> 6, n = tid & 63;            // feature block, entry within the block (half*32 + 4*k + i)
         const int half = n >> 5, kk = (n & 31) >> 2, i = n & 3;
@@ -767,13 +839,25 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         float a = (red[(0 * 4 + cc) * 64 + n] + red[(1 * 4 + cc) * 64 + n]) + (red[(2 * 4 + cc) * 64 + n] + red[(3 * 4 + cc) * 64 + n]);
         if (i < d.in) gW1[f + H * i] = a;
     }
-    if (tid < d.nout) out[head_b(d, tid)] = gb3;
-    float t0 = block_sum512(l0, sm.Red);
-    float t1 = block_sum512(l1, sm.Red);
-    if (tid == 0) {
-        float* lp = loss_partial + (int64_t)blockIdx.x * 4;
-        lp[0] = role ? 0.f : t0; lp[1] = role ? 0.f : t1; lp[2] = role ? t0 : 0.f; lp[3] = 0.f;
+    if (tid < d.nout) {
+        float a = 0.f;
+        for (int ss = 0; ss < TM; ++ss) a += red[4096 + tid * TM + ss];
+        out[head_b(d, tid)] = a;
     }
+    // loss sums (worker-only block reduction)
+    float t0 = l0, t1 = l1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
+    worker_sync();
+    if (lane == 0) { sm.Red[warp] = t0; sm.Red[16 + warp] = t1; }
+    worker_sync();
+    if (tid == 0) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int k = 0; k < 16; ++k) { a0 += sm.Red[k]; a1 += sm.Red[16 + k]; }
+        float* lp = loss_partial + (int64_t)blockIdx.x * 4;
+        lp[0] = role ? 0.f : a0; lp[1] = role ? 0.f : a1; lp[2] = role ? a0 : 0.f; lp[3] = 0.f;
+    }
+    }  // worker warps
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
@@ -801,7 +885,7 @@ int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const Ml
                        const AcBatch& b, float* partial, float* loss_partial, int64_t np) {
     size_t smem = sizeof(SmemBwd) + 128;
     CUDA_TRY(cudaFuncSetAttribute(ac_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ac_loss_grad_tc_kernel<<<grid, NT7, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np);
+    ac_loss_grad_tc_kernel<<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np);
     LAUNCH_CHECK(ctx);
     return B200RL_OK;
 }
