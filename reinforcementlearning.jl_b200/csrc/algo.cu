@@ -67,6 +67,7 @@ struct b200rl_net {
     float *params, *grad, *m, *v, *beta_t, *target;
     float* partial; int n_partials;
     float* loss_partial; float* loss4; float* gnorm;
+    double* cta_sumsq; unsigned int* counter2; unsigned int fused_launches;
     float lr, b1, b2, eps, max_grad_norm;
     uint64_t n_updates;
 };
@@ -99,7 +100,7 @@ int b200rl_net_destroy(b200rl_net* n) {
     cudaSetDevice(n->ctx->device);
     cudaStreamSynchronize(n->ctx->stream);
     cudaFree(n->params); cudaFree(n->grad); cudaFree(n->m); cudaFree(n->v); cudaFree(n->beta_t); cudaFree(n->target);
-    cudaFree(n->partial); cudaFree(n->loss_partial); cudaFree(n->loss4); cudaFree(n->gnorm);
+    cudaFree(n->partial); cudaFree(n->loss_partial); cudaFree(n->loss4); cudaFree(n->gnorm); cudaFree(n->cta_sumsq); cudaFree(n->counter2);
     delete n;
     return B200RL_OK;
 }
@@ -127,6 +128,8 @@ int b200rl_net_create(b200rl_ctx* ctx, const b200rl_net_desc* d, const float* pa
     NET_TRY(cudaMalloc(&n->partial, (size_t)n->n_partials * bytes));
     NET_TRY(cudaMalloc(&n->loss_partial, (size_t)n_loss_rows * 4 * sizeof(float)));
     NET_TRY(cudaMalloc(&n->loss4, 4 * sizeof(float))); NET_TRY(cudaMalloc(&n->gnorm, sizeof(float)));
+    NET_TRY(cudaMalloc(&n->cta_sumsq, 256 * sizeof(double))); NET_TRY(cudaMalloc(&n->counter2, 2 * sizeof(unsigned int)));
+    NET_TRY(cudaMemsetAsync(n->counter2, 0, 2 * sizeof(unsigned int), ctx->stream));
     NET_TRY(cudaMemcpyAsync(n->params, params_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (n->kind == 2) NET_TRY(cudaMemcpyAsync(n->target, params_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     NET_TRY(cudaMemsetAsync(n->grad, 0, bytes, ctx->stream)); NET_TRY(cudaMemsetAsync(n->m, 0, bytes, ctx->stream));
@@ -503,12 +506,15 @@ int b200rl_onpolicy_update(b200rl_onpolicy* a, const int32_t* perm_host, float* 
                       1.0f / ((float)B * (float)world), a->norm2};
             int ctas = nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
             if (ctas < 0) return ctas;
-            TRY(nn_reduce_partials(ctx, n->partial, ctas, n->np, n->grad, n->loss_partial, 2 * ctas, n->loss4));
             if (world > 1) {
+                TRY(nn_reduce_partials(ctx, n->partial, ctas, n->np, n->grad, n->loss_partial, 2 * ctas, n->loss4));
                 TRY(b200rl_comm_allreduce_internal(ctx, n->grad, n->np, 0));
                 TRY(b200rl_comm_allreduce_internal(ctx, n->loss4, 4, 0));
+                TRY(nn_clip_adam(ctx, n->params, n->grad, n->m, n->v, n->beta_t, n->np, c.max_grad_norm, c.lr, c.beta1, c.beta2, c.eps, 1.0f, n->gnorm));
+            } else {
+                TRY(nn_reduce_clip_adam(ctx, n->partial, ctas, n->np, n->params, n->grad, n->m, n->v, n->beta_t, n->loss_partial, 2 * ctas, n->loss4,
+                                        c.max_grad_norm, c.lr, c.beta1, c.beta2, c.eps, n->gnorm, n->cta_sumsq, n->counter2, &n->fused_launches));
             }
-            TRY(nn_clip_adam(ctx, n->params, n->grad, n->m, n->v, n->beta_t, n->np, c.max_grad_norm, c.lr, c.beta1, c.beta2, c.eps, 1.0f, n->gnorm));
             stats_row_kernel<<<1, 32, 0, ctx->stream>>>(a->stats_dev + (size_t)row * 8, n->loss4, n->gnorm);
             LAUNCH_CHECK(ctx);
             n->n_updates += 1;

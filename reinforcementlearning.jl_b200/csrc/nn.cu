@@ -731,6 +731,68 @@ __global__ void __launch_bounds__(1024) clip_adam_kernel(float* __restrict__ p, 
     if (threadIdx.x == 0) { beta_t[0] = bt1 * b1; beta_t[1] = bt2 * b2; }
 }
 
+// Fused K8 for the single-GPU path: partial reduce -> global norm -> clip -> Adam in ONE launch.  The CTAs meet at a
+// device-wide counter (all ceil(np/256) <= 148 CTAs are co-resident), every CTA then sums the per-CTA sum-of-squares in
+// CTA order, so the result is bit-identical to the two-kernel path and run-to-run deterministic.
+__global__ void __launch_bounds__(256) reduce_clip_adam_kernel(const float* __restrict__ partial, int n_partials, int64_t np, float* __restrict__ p,
+                                                              float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                              float* __restrict__ beta_t, const float* __restrict__ loss_partial, int n_loss,
+                                                              float* __restrict__ loss_out4, float max_norm, float lr, float b1, float b2, float eps,
+                                                              float* __restrict__ gnorm_out, double* __restrict__ cta_sumsq,
+                                                              unsigned int* __restrict__ counter, unsigned int target) {
+    __shared__ double red[8];
+    __shared__ float s_scale;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float gk = 0.f;
+    if (k < np) {
+        for (int c = 0; c < n_partials; ++c) gk += partial[(int64_t)c * np + k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 4 && loss_out4) {
+        float a = 0.f;
+        for (int c = 0; c < n_loss; ++c) a += loss_partial[c * 4 + threadIdx.x];
+        loss_out4[threadIdx.x] = a;
+    }
+    double acc = (double)gk * (double)gk;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        cta_sumsq[blockIdx.x] = t;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int spins = 0;
+        while (*reinterpret_cast<volatile unsigned int*>(counter) < target)
+            if (++spins > (1u << 26)) __trap();
+        __threadfence();
+        double tot = 0.0;
+        for (unsigned int c = 0; c < gridDim.x; ++c) tot += *reinterpret_cast<volatile double*>(cta_sumsq + c);
+        float gn = (float)sqrt(tot);
+        float sc = 1.0f;
+        if (max_norm > 0.f && max_norm <= gn) sc = max_norm / fmaxf(max_norm, gn);
+        s_scale = sc;
+        if (blockIdx.x == 0 && gnorm_out) *gnorm_out = gn;
+    }
+    __syncthreads();
+    const float bt1 = beta_t[0], bt2 = beta_t[1];
+    if (k < np) {
+        gk *= s_scale;
+        g[k] = gk;
+        float mk = b1 * m[k] + (1.0f - b1) * gk;
+        float vk = b2 * v[k] + (1.0f - b2) * (gk * gk);
+        m[k] = mk; v[k] = vk;
+        p[k] -= mk / (1.0f - bt1) / (sqrtf(vk / (1.0f - bt2)) + eps) * lr;
+    }
+    // beta^t advances once every CTA has read it: the last CTA to pass a second counter does it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(counter + 1, 1u) + 1u == target) { beta_t[0] = bt1 * b1; beta_t[1] = bt2 * b2; }
+    }
+}
+
 __global__ void target_sync_kernel(float* __restrict__ target, const float* __restrict__ model, int64_t np, float rho) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < np) target[k] = rho * target[k] + (1.0f - rho) * model[k];
@@ -951,6 +1013,18 @@ int nn_reduce_partials(b200rl_ctx* ctx, const float* partial, int n_partials, in
 int nn_clip_adam(b200rl_ctx* ctx, float* params, float* grad, float* m, float* v, float* beta_t, int64_t np, float max_grad_norm, float lr,
                  float b1, float b2, float eps, float grad_scale, float* gnorm_out) {
     clip_adam_kernel<<<1, 1024, 0, ctx->stream>>>(params, grad, m, v, beta_t, np, max_grad_norm, lr, b1, b2, eps, grad_scale, gnorm_out);
+    LAUNCH_CHECK(ctx);
+    return B200RL_OK;
+}
+
+int nn_reduce_clip_adam(b200rl_ctx* ctx, const float* partial, int n_partials, int64_t np, float* params, float* grad, float* m, float* v,
+                        float* beta_t, const float* loss_partial, int n_loss, float* loss_out4, float max_grad_norm, float lr, float b1, float b2,
+                        float eps, float* gnorm_out, double* cta_sumsq, unsigned int* counter2, unsigned int* launches) {
+    unsigned grid = grid_for(np, 256);
+    REQUIRE((int)grid <= ctx->sm_count, B200RL_ERR_UNSUPPORTED, "fused reduce+Adam needs all CTAs co-resident");
+    *launches += 1;
+    reduce_clip_adam_kernel<<<grid, 256, 0, ctx->stream>>>(partial, n_partials, np, params, grad, m, v, beta_t, loss_partial, n_loss, loss_out4,
+                                                          max_grad_norm, lr, b1, b2, eps, gnorm_out, cta_sumsq, counter2, *launches * grid);
     LAUNCH_CHECK(ctx);
     return B200RL_OK;
 }

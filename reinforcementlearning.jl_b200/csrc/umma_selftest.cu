@@ -12,6 +12,7 @@ struct SelfTestArgs {
     uint32_t a_kadv, b_kadv;                  // start-address advance per K step (bytes)
     uint32_t idesc; int ksteps; int ncols;    // instruction descriptor, # MMA instructions, D columns to dump
     int a_from_tmem;                           // 1: copy the (K-major, 64-wide) A image into TMEM columns 64.. and use the .ts form
+    int repeat;                                // timing: issue the whole k-loop this many times; cycles -> d_out[last]
     float* d_out;                             // [128][ncols]
 };
 
@@ -46,15 +47,17 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
         __syncthreads();
         umma::fence_after_sync();
     }
+    long long t0 = clock64();
     if (warp == 0) {
         if (threadIdx.x == 0) {
+            for (int rep = 0; rep < a.repeat; ++rep)
             for (int k = 0; k < a.ksteps; ++k) {
                 uint64_t db = umma::make_desc(umma::smem_u32(sb) + k * a.b_kadv, a.b_lbo, a.b_sbo);
                 if (a.a_from_tmem) {
-                    umma::mma_tf32_ts(tmem, tmem + 64 + k * a.a_kadv, db, a.idesc, k > 0 ? 1u : 0u);
+                    umma::mma_tf32_ts(tmem, tmem + 64 + k * a.a_kadv, db, a.idesc, (k > 0 || rep > 0) ? 1u : 0u);
                 } else {
                     uint64_t da = umma::make_desc(umma::smem_u32(sa) + k * a.a_kadv, a.a_lbo, a.a_sbo);
-                    umma::mma_tf32(tmem, da, db, a.idesc, k > 0 ? 1u : 0u);
+                    umma::mma_tf32(tmem, da, db, a.idesc, (k > 0 || rep > 0) ? 1u : 0u);
                 }
             }
             umma::commit(&s_bar);
@@ -62,6 +65,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
         __syncwarp();
     }
     umma::mbar_wait(&s_bar, 0);
+    long long t1 = clock64();
     umma::fence_after_sync();
     for (int c0 = 0; c0 < a.ncols; c0 += 32) {
         float v[32];
@@ -69,6 +73,8 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
         int lane = warp * 32 + (threadIdx.x & 31);
         for (int c = 0; c < 32; ++c) a.d_out[lane * a.ncols + c0 + c] = v[c];
     }
+    __syncthreads();
+    if (threadIdx.x == 0) a.d_out[128 * a.ncols - 1] = (float)(t1 - t0);
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, 128);
@@ -88,7 +94,7 @@ extern "C" int b200rl_selftest_umma(b200rl_ctx* ctx, const void* a_img_host, uin
     uint8_t* da = (uint8_t*)sc; uint8_t* db = da + a_pad; float* dd = (float*)(db + b_pad);
     CUDA_TRY(cudaMemcpyAsync(da, a_img_host, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(db, b_img_host, b_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    SelfTestArgs a{da, a_bytes, db, b_bytes, desc8[0], desc8[1], desc8[2], desc8[3], desc8[4], desc8[5], desc8[6], (int)(desc8[7] & 0xFFFF), ncols, (int)(desc8[7] >> 16), dd};
+    SelfTestArgs a{da, a_bytes, db, b_bytes, desc8[0], desc8[1], desc8[2], desc8[3], desc8[4], desc8[5], desc8[6], (int)(desc8[7] & 0xFFFF), ncols, (int)((desc8[7] >> 16) & 1), (int)(desc8[7] >> 20) ? (int)(desc8[7] >> 20) : 1, dd};
     size_t smem = a_pad + b_pad;
     CUDA_TRY(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_selftest_kernel<<<1, 128, smem, ctx->stream>>>(a);
