@@ -133,7 +133,7 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
     const int q = warp & 3, c = warp >> 2;
     const int s = 32 * q + lane;
     load_small_weights(sm, d, params + poff);
-    if (warp == 0) umma::tmem_alloc(&sm.tmem, 64);
+    if (warp == 0) umma::tmem_alloc(&sm.tmem, 256);   // three 64-column accumulators (independent MMA chains)
     if (tid == 32) umma::mbar_init(&sm.bar, 1);
     umma::fence_proxy_async();
     umma::fence_before_sync();
@@ -191,7 +191,17 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
         if (warp == 0) {  // warp 0 issues (one lane) and alone polls the mbarrier; everyone else parks on the CTA barrier
             if (lane == 0) {
                 umma::fence_after_sync();
-                issue_gemm_3x(tmem, sm.A_full, sm.A_lo, G_F, G_S, 2 * G_F, sm.B_full, sm.B_lo, G_F, GW_S, 2 * G_F, idesc, 8, false);
+                const uint64_t dAf = umma::make_desc(umma::smem_u32(sm.A_full), G_F, G_S), dAl = umma::make_desc(umma::smem_u32(sm.A_lo), G_F, G_S);
+                const uint64_t dBf = umma::make_desc(umma::smem_u32(sm.B_full), G_F, GW_S), dBl = umma::make_desc(umma::smem_u32(sm.B_lo), G_F, GW_S);
+                uint32_t acc = 0u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {   // hi*hi, hi*lo, lo*hi into three accumulators, round-robin (see COL_D12 note)
+                    const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
+                    umma::mma_tf32(tmem, dAf + adv, dBf + adv, idesc, acc);
+                    umma::mma_tf32(tmem + 64, dAf + adv, dBl + adv, idesc, acc);
+                    umma::mma_tf32(tmem + 128, dAl + adv, dBf + adv, idesc, acc);
+                    acc = 1u;
+                }
                 umma::commit(&sm.bar);
             }
             __syncwarp();
@@ -202,7 +212,16 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
         umma::fence_after_sync();
         {   // epilogue: H2 = act(D + b2); head partial over this thread's 32 features
             float v[32];
-            umma::tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 32 * c, v);
+            {
+                float v2[32];
+                umma::tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 32 * c, v);
+                umma::tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 64 + 32 * c, v2);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] += v2[k];
+                umma::tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 128 + 32 * c, v2);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] += v2[k];
+            }
             float zp[kOutMax] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
@@ -289,7 +308,10 @@ constexpr int GF_T = 144;                 // feature-major image: stride between
                                           // 4-byte transposed stores hit 32 different banks (with 128 they would 8-way conflict)
 constexpr int GS_T = 32 * GF_T + 16;      // stride between 8-feature row groups
 constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples]
-constexpr uint32_t COL_D1 = 0, COL_D2 = 64, COL_D3 = 128, COL_AF = 192, COL_AL = 256;
+// Back-to-back tcgen05.mma on ONE accumulator serialise at ~120 cycles each (measured, profiles/umma_probe4.py) although a
+// 128x64x8 tf32 MMA is only ~32 cycles of tensor work, so the three 3xTF32 passes go to three separate accumulators
+// (independent dependency chains, issued round-robin) and are summed in the epilogue.
+constexpr uint32_t COL_D12 = 0 /* 3 x 64: GEMM1, then GEMM2 */, COL_D3 = 192 /* 3 x 64 */, COL_AF = 384, COL_AL = 448;
 
 struct SmemBwd {
     alignas(128) uint8_t FP_full[FIMG];    // dP2^T  (rows = feature j, K = sample)
@@ -509,10 +531,9 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     const int64_t poff = role ? actor.nparams() : 0;
     const float* __restrict__ p = params + poff;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool is_mma_warp = false;
     const int q = warp & 3, c = (warp >> 2) & 3;
     const int s = 32 * q + lane;
-    if (!is_mma_warp) {   // weights: small ones plain, W2 as two operand images
+    {   // weights: small ones plain, W2 as two operand images
         const float* b1 = p + (int64_t)H * d.in;
         const float* W2 = b1 + H;
         const float* b2 = W2 + (int64_t)H * H;
@@ -545,44 +566,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     const uint32_t idesc = umma::make_idesc_tf32(128, 64, 0, 0);
     const int64_t ntiles = (b.B + TM - 1) / TM;
 
-    if (is_mma_warp) {
-        // ================= MMA-issue warp: waits for operands, feeds the tensor core, signals completion =========
-        uint32_t ph = 0;
-        uint32_t d3_acc = 0u;
-        for (int64_t tile = cta; tile < ntiles; tile += nctas) {
-            umma::mbar_wait(&sm.ready1, ph);
-            umma::fence_after_sync();
-            if (lane == 0) {
-                issue_gemm_ts_3x(tmem + COL_D1, tmem + COL_AF, tmem + COL_AL, sm.B1_full, sm.B1_lo, idesc);
-                umma::commit(&sm.bar1);
-            }
-            __syncwarp();
-            umma::mbar_wait(&sm.ready2, ph);
-            umma::fence_after_sync();
-            if (lane == 0) {
-                issue_gemm_ts_3x(tmem + COL_D2, tmem + COL_AF, tmem + COL_AL, sm.B2_full, sm.B2_lo, idesc);
-                umma::commit(&sm.bar2);
-                // dW2 += dP2^T x H1 : K = 128 samples in 16 steps of 8 (two 4-sample chunks)
-                const uint32_t af = umma::smem_u32(sm.FP_full), al = umma::smem_u32(sm.FP_lo);
-                const uint32_t bf = umma::smem_u32(sm.FH_full), bl = umma::smem_u32(sm.FH_lo);
-                uint32_t acc = d3_acc;
-#pragma unroll 1
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t a = pass == 2 ? al : af;
-                    const uint32_t bb = pass == 1 ? bl : bf;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        umma::mma_tf32(tmem + COL_D3, umma::make_desc(a + k * 2 * GF_T, GF_T, GS_T), umma::make_desc(bb + k * 2 * GF_T, GF_T, GS_T), idesc, acc);
-                        acc = 1u;
-                    }
-                }
-                umma::commit(&sm.bar3);
-            }
-            __syncwarp();
-            d3_acc = 1u;
-            ph ^= 1u;
-        }
-    } else {
+    {
     // ================= 16 worker warps =======================================================================
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     // persistent per-thread gradient partials (over this thread's sample slot), reduced once at the end
@@ -678,9 +662,14 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 umma::fence_after_sync();
                 uint32_t acc = 0u;
                 const uint64_t dB1f = umma::make_desc(umma::smem_u32(sm.B1_full), G_F, GW_S), dB1l = umma::make_desc(umma::smem_u32(sm.B1_lo), G_F, GW_S);
-                issue_ts(tmem + COL_D1, tmem + COL_AF, dB1f, 2 * G_F / 16, idesc, acc);
-                issue_ts(tmem + COL_D1, tmem + COL_AF, dB1l, 2 * G_F / 16, idesc, acc);
-                issue_ts(tmem + COL_D1, tmem + COL_AL, dB1f, 2 * G_F / 16, idesc, acc);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {   // three independent accumulator chains, round-robin
+                    const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
+                    umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB1f + adv, idesc, acc);
+                    umma::mma_tf32_ts(tmem + COL_D12 + 64, tmem + COL_AF + 8 * k, dB1l + adv, idesc, acc);
+                    umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB1f + adv, idesc, acc);
+                    acc = 1u;
+                }
                 umma::commit(&sm.bar1);
             }
             __syncwarp();
@@ -692,8 +681,14 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         // ---- P3: H2 = act(D1 + b2) (registers) + head partials ---------------------------------------
         float h2[16];
         {
-            float v[16];
-            umma::tmem_ld16(tmem + lane_base + COL_D1 + 16 * c, v);
+            float v[16], v2[16];
+            umma::tmem_ld16(tmem + lane_base + COL_D12 + 16 * c, v);
+            umma::tmem_ld16(tmem + lane_base + COL_D12 + 64 + 16 * c, v2);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] += v2[k];
+            umma::tmem_ld16(tmem + lane_base + COL_D12 + 128 + 16 * c, v2);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] += v2[k];
             float zp[kOutMax] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -752,14 +747,23 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 const uint64_t dB2f = umma::make_desc(umma::smem_u32(sm.B2_full), G_F, GW_S), dB2l = umma::make_desc(umma::smem_u32(sm.B2_lo), G_F, GW_S);
                 const uint64_t dFPf = umma::make_desc(umma::smem_u32(sm.FP_full), GF_T, GS_T), dFPl = umma::make_desc(umma::smem_u32(sm.FP_lo), GF_T, GS_T);
                 const uint64_t dFHf = umma::make_desc(umma::smem_u32(sm.FH_full), GF_T, GS_T), dFHl = umma::make_desc(umma::smem_u32(sm.FH_lo), GF_T, GS_T);
-                issue_ts(tmem + COL_D2, tmem + COL_AF, dB2f, 2 * G_F / 16, idesc, acc);
-                issue_ts(tmem + COL_D2, tmem + COL_AF, dB2l, 2 * G_F / 16, idesc, acc);
-                issue_ts(tmem + COL_D2, tmem + COL_AL, dB2f, 2 * G_F / 16, idesc, acc);
-                umma::commit(&sm.bar2);
-                // dW2 += dP2^T x H1 : K = 128 samples in 16 steps of 8 (two 4-sample chunks); awaited lazily (next tile)
-                issue_ss(tmem + COL_D3, dFPf, dFHf, 2 * GF_T / 16, 2 * GF_T / 16, 16, idesc, d3_acc);
-                issue_ss(tmem + COL_D3, dFPf, dFHl, 2 * GF_T / 16, 2 * GF_T / 16, 16, idesc, d3_acc);
-                issue_ss(tmem + COL_D3, dFPl, dFHf, 2 * GF_T / 16, 2 * GF_T / 16, 16, idesc, d3_acc);
+                // GEMM2 (dH1, awaited now) interleaved with the first half of GEMM3 (dW2 += dP2^T x H1, K = 128 samples): six chains
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k == 8) umma::commit(&sm.bar2);
+                    if (k < 8) {
+                        const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
+                        umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB2f + adv, idesc, acc);
+                        umma::mma_tf32_ts(tmem + COL_D12 + 64, tmem + COL_AF + 8 * k, dB2l + adv, idesc, acc);
+                        umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB2f + adv, idesc, acc);
+                        acc = 1u;
+                    }
+                    const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
+                    umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc, d3_acc);
+                    umma::mma_tf32(tmem + COL_D3 + 64, dFPf + adt, dFHl + adt, idesc, d3_acc);
+                    umma::mma_tf32(tmem + COL_D3 + 128, dFPl + adt, dFHf + adt, idesc, d3_acc);
+                    d3_acc = 1u;
+                }
                 umma::commit(&sm.bar3);
             }
             __syncwarp();
@@ -772,7 +776,16 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         // ---- P7: dP1 = D2 .* act'(H1); dW1 / db1 partials (no shared memory) ----------------------------
         {
             float v[16];
-            umma::tmem_ld16(tmem + lane_base + COL_D2 + 16 * c, v);
+            {
+                float v2[16];
+                umma::tmem_ld16(tmem + lane_base + COL_D12 + 16 * c, v);
+                umma::tmem_ld16(tmem + lane_base + COL_D12 + 64 + 16 * c, v2);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] += v2[k];
+                umma::tmem_ld16(tmem + lane_base + COL_D12 + 128 + 16 * c, v2);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] += v2[k];
+            }
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 v[k] = v[k] * dact_f(d.act, h1[k]);
@@ -803,8 +816,16 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     float* gW2 = gb1 + H;
     float* gb2 = gW2 + (int64_t)H * H;
     if (q < 2) {   // D3 rows j = TMEM lanes 0..63
-        float v[16];
-        if (gemm3_pending) umma::tmem_ld16(tmem + lane_base + COL_D3 + 16 * c, v);
+        float v[16], v2[16];
+        if (gemm3_pending) {
+            umma::tmem_ld16(tmem + lane_base + COL_D3 + 16 * c, v);
+            umma::tmem_ld16(tmem + lane_base + COL_D3 + 64 + 16 * c, v2);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] += v2[k];
+            umma::tmem_ld16(tmem + lane_base + COL_D3 + 128 + 16 * c, v2);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] += v2[k];
+        }
 #pragma unroll
         for (int k = 0; k < 16; ++k) gW2[s + H * (16 * c + k)] = gemm3_pending ? v[k] : 0.f;
     }
