@@ -289,7 +289,7 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 64);
+    if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
 
 
