@@ -13,7 +13,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio", "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
         "smsp__average_warp_latency_issue_stalled_barrier.ratio", "smsp__average_warp_latency_issue_stalled_mio_throttle.ratio",
         "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio", "smsp__average_warp_latency_issue_stalled_not_selected.ratio",
-        "smsp__average_warp_latency_issue_stalled_wait.ratio", "smsp__average_warp_latency_issue_stalled_dispatch_stall.ratio"]
+        "smsp__average_warp_latency_issue_stalled_wait.ratio", "smsp__average_warp_latency_issue_stalled_dispatch_stall.ratio",
+        "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active"]
 
 def raw(rep):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -46,7 +47,7 @@ for name in ("prof_loss", "prof_fwd", "prof_env", "prof_gae"):
             t = float(rec["dram__bytes_read.sum"].replace(",", "")) + float(rec["dram__bytes_write.sum"].replace(",", ""))
             u = ui.get("dram__bytes_read.sum", "byte")
             mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-            mk = re.search(r"(ac_loss_grad_kernel|forward_kernel|env_step_kernel|scan_series_fastest|dqn_loss_grad_kernel)", kn)
+            mk = re.search(r"(ac_loss_grad_tc_kernel|ac_loss_grad_kernel|forward_tc_kernel|forward_kernel|env_step_kernel|scan_series_fastest|dqn_loss_grad_kernel)", kn)
             traffic[mk.group(1) if mk else kn] = t * mult
             lines.append("| dram traffic (read+write) | %.3f | MB |" % (t * mult / 1e6))
         except Exception as e:

@@ -27,3 +27,9 @@ for form, name in ((0, "SS"), (1, "TS")):
         print(name, "MMAs", 8 * rep, "cycles", cyc, "per MMA", cyc / (8 * rep), "check", D[0, 0], "(expect", 64 * rep, ")")
 for N in (64, 128, 256):
     pass
+print("--- N scaling (SS form, 48 MMAs each) ---")
+for N in (64, 128, 192, 256):
+    Bn = np.ones((N, 64), np.float32)
+    bi = image(Bn, G_S, G_F, (N // 8) * G_S + 64)
+    D = run(a_img, bi, [G_F, G_S, G_F, G_S, 2 * G_F, 2 * G_F, idesc(128, N), 8 | (6 << 20)], ncols=64)
+    print("N", N, "cycles/MMA", D[127, 63] / 48, "check", D[0, 0])

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
     for (uint32_t k = threadIdx.x; k < a.b_bytes / 4; k += blockDim.x) ((uint32_t*)sb)[k] = ((const uint32_t*)a.b_img)[k];
     umma::fence_proxy_async();
     const int warp = threadIdx.x >> 5;
-    if (warp == 0) umma::tmem_alloc(&s_tmem, 128);
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
     if (threadIdx.x == 32) umma::mbar_init(&s_bar, 1);
     umma::fence_before_sync();
     __syncthreads();
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
                 int kk = c0 + k;
                 v[k] = *reinterpret_cast<const float*>(sa + (m / 8) * a.a_sbo + (kk / 4) * a.a_lbo + (m % 8) * 16 + (kk % 4) * 4);
             }
-            umma::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 64 + c0, v);
+            umma::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c0, v);
         }
         umma::tmem_st_wait();
         umma::fence_before_sync();
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
             for (int k = 0; k < a.ksteps; ++k) {
                 uint64_t db = umma::make_desc(umma::smem_u32(sb) + k * a.b_kadv, a.b_lbo, a.b_sbo);
                 if (a.a_from_tmem) {
-                    umma::mma_tf32_ts(tmem, tmem + 64 + k * a.a_kadv, db, a.idesc, (k > 0 || rep > 0) ? 1u : 0u);
+                    umma::mma_tf32_ts(tmem, tmem + 256 + k * a.a_kadv, db, a.idesc, (k > 0 || rep > 0) ? 1u : 0u);
                 } else {
                     uint64_t da = umma::make_desc(umma::smem_u32(sa) + k * a.a_kadv, a.a_lbo, a.a_sbo);
                     umma::mma_tf32(tmem, da, db, a.idesc, (k > 0 || rep > 0) ? 1u : 0u);
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
     if (threadIdx.x == 0) a.d_out[128 * a.ncols - 1] = (float)(t1 - t0);
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 128);
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 }  // namespace
 
