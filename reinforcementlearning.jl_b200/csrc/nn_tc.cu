@@ -140,7 +140,7 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = sm.tmem;
-    const uint32_t idesc = umma::make_idesc_tf32(128, 64, 0, 0);
+    const uint32_t idesc = umma::make_idesc_tf32(128, 64, 0, 0), idesc128 = umma::make_idesc_tf32(128, 128, 0, 0);
     const int64_t ntiles = (N + TM - 1) / TM;
     uint32_t phase = 0;
     for (int64_t tile = cta; tile < ntiles; tile += nctas) {
@@ -197,8 +197,7 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {   // hi*hi, hi*lo, lo*hi into three accumulators, round-robin (see COL_D12 note)
                     const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                    umma::mma_tf32(tmem, dAf + adv, dBf + adv, idesc, acc);
-                    umma::mma_tf32(tmem + 64, dAf + adv, dBl + adv, idesc, acc);
+                    umma::mma_tf32(tmem, dAf + adv, dBf + adv, idesc128, acc);        // B_full | B_lo adjacent: one N = 128 operand
                     umma::mma_tf32(tmem + 128, dAl + adv, dBf + adv, idesc, acc);
                     acc = 1u;
                 }
@@ -314,6 +313,7 @@ constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples]
 constexpr uint32_t COL_D12 = 0 /* 3 x 64: GEMM1, then GEMM2 */, COL_D3 = 192 /* 3 x 64 */, COL_AF = 384, COL_AL = 448;
 
 struct SmemBwd {
+    static_assert(FIMG % 128 == 0 && WIMG_BYTES % 128 == 0, "full/lo images must be adjacent to form one N = 128 operand");
     alignas(128) uint8_t FP_full[FIMG];    // dP2^T  (rows = feature j, K = sample)
     alignas(128) uint8_t FP_lo[FIMG];
     alignas(128) uint8_t FH_full[FIMG];    // H1^T
@@ -563,7 +563,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = sm.tmem;
-    const uint32_t idesc = umma::make_idesc_tf32(128, 64, 0, 0);
+    const uint32_t idesc = umma::make_idesc_tf32(128, 64, 0, 0), idesc128 = umma::make_idesc_tf32(128, 128, 0, 0);
     const int64_t ntiles = (b.B + TM - 1) / TM;
 
     {
@@ -665,8 +665,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {   // three independent accumulator chains, round-robin
                     const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                    umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB1f + adv, idesc, acc);
-                    umma::mma_tf32_ts(tmem + COL_D12 + 64, tmem + COL_AF + 8 * k, dB1l + adv, idesc, acc);
+                    umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB1f + adv, idesc128, acc);        // [full*full | full*lo]: B_full and B_lo are adjacent = one N = 128 operand
                     umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB1f + adv, idesc, acc);
                     acc = 1u;
                 }
@@ -753,14 +752,12 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                     if (k == 8) umma::commit(&sm.bar2);
                     if (k < 8) {
                         const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                        umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB2f + adv, idesc, acc);
-                        umma::mma_tf32_ts(tmem + COL_D12 + 64, tmem + COL_AF + 8 * k, dB2l + adv, idesc, acc);
+                        umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB2f + adv, idesc128, acc);
                         umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB2f + adv, idesc, acc);
                         acc = 1u;
                     }
                     const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
-                    umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc, d3_acc);
-                    umma::mma_tf32(tmem + COL_D3 + 64, dFPf + adt, dFHl + adt, idesc, d3_acc);
+                    umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc128, d3_acc);   // FH_full and FH_lo adjacent: N = 128
                     umma::mma_tf32(tmem + COL_D3 + 128, dFPl + adt, dFHf + adt, idesc, d3_acc);
                     d3_acc = 1u;
                 }
