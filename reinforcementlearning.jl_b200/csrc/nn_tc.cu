@@ -134,7 +134,7 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
     const int s = 32 * q + lane;
     load_small_weights(sm, d, params + poff);
     if (warp == 0) umma::tmem_alloc(&sm.tmem, 256);   // three 64-column accumulators (independent MMA chains)
-    if (tid == 32) umma::mbar_init(&sm.bar, 2);   // two issuing threads (one per MMA chain) commit to it
+    if (tid == 32) umma::mbar_init(&sm.bar, 1);
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
@@ -188,25 +188,23 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
         umma::fence_proxy_async();     // generic-proxy stores -> visible to the tensor core
         umma::fence_before_sync();
         __syncthreads();
-        // A single thread sustains only ~1 tcgen05.mma per ~140 cycles (4x the 32-cycle tensor time of a 128x64x8 tf32 MMA), so the
-        // two independent chains are issued by two different warps; each commits its own MMAs to the (count 2) mbarrier.
-        if (warp == 0 || warp == 4) {
+        if (warp == 0) {  // warp 0 issues (one lane) and alone polls the mbarrier; everyone else parks on the CTA barrier
             if (lane == 0) {
                 umma::fence_after_sync();
                 const uint64_t dAf = umma::make_desc(umma::smem_u32(sm.A_full), G_F, G_S), dAl = umma::make_desc(umma::smem_u32(sm.A_lo), G_F, G_S);
-                const uint64_t dBf = umma::make_desc(umma::smem_u32(sm.B_full), G_F, GW_S);
+                const uint64_t dBf = umma::make_desc(umma::smem_u32(sm.B_full), G_F, GW_S), dBl = umma::make_desc(umma::smem_u32(sm.B_lo), G_F, GW_S);
                 uint32_t acc = 0u;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 8; ++k) {   // hi*hi, hi*lo, lo*hi into three accumulators, round-robin (see COL_D12 note)
                     const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                    if (warp == 0) umma::mma_tf32(tmem, dAf + adv, dBf + adv, idesc128, acc);          // [full*full | full*lo]: B_full | B_lo adjacent = one N = 128 operand
-                    else umma::mma_tf32(tmem + 128, dAl + adv, dBf + adv, idesc, acc);                 // lo*full
+                    umma::mma_tf32(tmem, dAf + adv, dBf + adv, idesc128, acc);        // B_full | B_lo adjacent: one N = 128 operand
+                    umma::mma_tf32(tmem + 128, dAl + adv, dBf + adv, idesc, acc);
                     acc = 1u;
                 }
                 umma::commit(&sm.bar);
             }
             __syncwarp();
-            if (warp == 0) umma::mbar_wait(&sm.bar, phase);
+            umma::mbar_wait(&sm.bar, phase);
         }
         phase ^= 1u;
         __syncthreads();
@@ -557,7 +555,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     }
     if (warp == 0) umma::tmem_alloc(&sm.tmem, 512);
     if (tid == 32) {
-        umma::mbar_init(&sm.bar1, 2); umma::mbar_init(&sm.bar2, 2); umma::mbar_init(&sm.bar3, 2);   // two issuing threads per GEMM
+        umma::mbar_init(&sm.bar1, 1); umma::mbar_init(&sm.bar2, 1); umma::mbar_init(&sm.bar3, 1);
         umma::mbar_init(&sm.ready1, 1); umma::mbar_init(&sm.ready2, 1);
     }
     umma::fence_proxy_async();
@@ -659,22 +657,22 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         umma::fence_proxy_async();
         umma::fence_before_sync();
         worker_sync();
-        if (warp == 0 || warp == 4) {   // one issuing thread per independent MMA chain (a thread sustains ~1 MMA / 140 cycles)
+        if (warp == 0) {
             if (lane == 0) {
                 umma::fence_after_sync();
                 uint32_t acc = 0u;
-                const uint64_t dB1f = umma::make_desc(umma::smem_u32(sm.B1_full), G_F, GW_S);
+                const uint64_t dB1f = umma::make_desc(umma::smem_u32(sm.B1_full), G_F, GW_S), dB1l = umma::make_desc(umma::smem_u32(sm.B1_lo), G_F, GW_S);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 8; ++k) {   // three independent accumulator chains, round-robin
                     const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                    if (warp == 0) umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB1f + adv, idesc128, acc);   // [full*full | full*lo]
-                    else umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB1f + adv, idesc, acc);          // lo*full
+                    umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB1f + adv, idesc128, acc);        // [full*full | full*lo]: B_full and B_lo are adjacent = one N = 128 operand
+                    umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB1f + adv, idesc, acc);
                     acc = 1u;
                 }
                 umma::commit(&sm.bar1);
             }
             __syncwarp();
-            if (warp == 0) umma::mbar_wait(&sm.bar1, ph1);
+            umma::mbar_wait(&sm.bar1, ph1);
         }
         ph1 ^= 1u;
         worker_sync();
@@ -741,35 +739,32 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         umma::fence_proxy_async();
         umma::fence_before_sync();
         worker_sync();
-        if ((warp & 3) == 0) {   // warps 0, 4: GEMM2 chains (awaited now); warps 8, 12: GEMM3 chains (awaited at the top of the next tile)
+        if (warp == 0) {
             if (lane == 0) {
                 umma::fence_after_sync();
-                if (warp < 8) {
-                    uint32_t acc = 0u;
-                    const uint64_t dB2f = umma::make_desc(umma::smem_u32(sm.B2_full), G_F, GW_S);
+                uint32_t acc = 0u;
+                const uint64_t dB2f = umma::make_desc(umma::smem_u32(sm.B2_full), G_F, GW_S), dB2l = umma::make_desc(umma::smem_u32(sm.B2_lo), G_F, GW_S);
+                const uint64_t dFPf = umma::make_desc(umma::smem_u32(sm.FP_full), GF_T, GS_T), dFPl = umma::make_desc(umma::smem_u32(sm.FP_lo), GF_T, GS_T);
+                const uint64_t dFHf = umma::make_desc(umma::smem_u32(sm.FH_full), GF_T, GS_T), dFHl = umma::make_desc(umma::smem_u32(sm.FH_lo), GF_T, GS_T);
+                // GEMM2 (dH1, awaited now) interleaved with the first half of GEMM3 (dW2 += dP2^T x H1, K = 128 samples): six chains
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 16; ++k) {
+                    if (k == 8) umma::commit(&sm.bar2);
+                    if (k < 8) {
                         const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                        if (warp == 0) umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB2f + adv, idesc128, acc);
-                        else umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB2f + adv, idesc, acc);
+                        umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB2f + adv, idesc128, acc);
+                        umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB2f + adv, idesc, acc);
                         acc = 1u;
                     }
-                    umma::commit(&sm.bar2);
-                } else {   // dW2 += dP2^T x H1, K = 128 samples in 16 steps of 8
-                    const uint64_t dFPf = umma::make_desc(umma::smem_u32(sm.FP_full), GF_T, GS_T), dFPl = umma::make_desc(umma::smem_u32(sm.FP_lo), GF_T, GS_T);
-                    const uint64_t dFHf = umma::make_desc(umma::smem_u32(sm.FH_full), GF_T, GS_T);
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
-                        if (warp == 8) umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc128, d3_acc);   // FH_full | FH_lo adjacent: N = 128
-                        else umma::mma_tf32(tmem + COL_D3 + 128, dFPl + adt, dFHf + adt, idesc, d3_acc);
-                        d3_acc = 1u;
-                    }
-                    umma::commit(&sm.bar3);
+                    const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
+                    umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc128, d3_acc);   // FH_full and FH_lo adjacent: N = 128
+                    umma::mma_tf32(tmem + COL_D3 + 128, dFPl + adt, dFHf + adt, idesc, d3_acc);
+                    d3_acc = 1u;
                 }
+                umma::commit(&sm.bar3);
             }
             __syncwarp();
-            if (warp == 0) umma::mbar_wait(&sm.bar2, ph2);
+            umma::mbar_wait(&sm.bar2, ph2);
         }
         gemm3_pending = true;
         ph2 ^= 1u;
