@@ -85,6 +85,55 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def usable_cores():
+    """Host threads this process may really use: scheduler affinity capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return n
+
+
+def cpu_arm_setup(O, n):
+    """Build the oracle-port PPO job on `n` envs and pick the OpenMP thread count that runs it fastest
+    (one short calibration iteration per candidate: an over-subscribed or quota-limited box is slower
+    with every hardware thread than with fewer).  Returns (step_fn, cores)."""
+    env = O.OracleVecEnv(O.KIND_CARTPOLE, n, O.splitmix_states_fast(n, 1))
+    env.reset(True)
+    desc = O.ac_desc(4, HIDDEN, 2)
+    p = O.glorot_params(desc, 123); m = np.zeros_like(p); v = np.zeros_like(p); bt = np.array([0.9, 0.999], np.float32)
+    prng = O.splitmix_states_fast(n, 2).copy()
+    hyper = O.hyper_array()
+    counter = [0]
+
+    def step(T=T_ROLLOUT):
+        s, _ = O.ppo_iteration(env, desc, hyper, p, m, v, bt, prng, T, N_EPOCHS, N_MICRO, counter[0])
+        counter[0] += 1
+        return s
+
+    top = max(1, min(usable_cores(), O.lib().orc_max_threads()))
+    cands = sorted({top, max(1, top // 2), max(1, top // 4), min(top, 32), min(top, 16), min(top, 8)}, reverse=True)
+    best, best_s = top, None
+    for c in cands:
+        O.lib().orc_set_threads(c)
+        s = step(T=4)            # 4-step rollout + full update shape: a fraction of a second
+        if best_s is None or s < best_s:
+            best, best_s = c, s
+    O.lib().orc_set_threads(best)
+    return step, best
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path cannot run here (Julia absent, RLZoo /
     MultiThreadEnv not in the snapshot): this arm times the oracle port — per-env heap objects,
@@ -96,19 +145,10 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     n = args.cpu_envs
-    cores = O.lib().orc_max_threads()
-    env = O.OracleVecEnv(O.KIND_CARTPOLE, n, O.splitmix_states_fast(n, 1))
-    env.reset(True)
-    desc = O.ac_desc(4, HIDDEN, 2)
-    p = O.glorot_params(desc, 123); m = np.zeros_like(p); v = np.zeros_like(p); bt = np.array([0.9, 0.999], np.float32)
-    prng = O.splitmix_states_fast(n, 2).copy()
-    hyper = O.hyper_array()
+    step, cores = cpu_arm_setup(O, n)
     for w in range(args.warmup):
-        O.ppo_iteration(env, desc, hyper, p, m, v, bt, prng, T_ROLLOUT, N_EPOCHS, N_MICRO, w)
-    secs = []
-    for k in range(args.steps):
-        s, _ = O.ppo_iteration(env, desc, hyper, p, m, v, bt, prng, T_ROLLOUT, N_EPOCHS, N_MICRO, args.warmup + k)
-        secs.append(s)
+        step()
+    secs = [step() for _ in range(args.steps)]
     total = float(np.sum(secs))
     value = n * T_ROLLOUT * args.steps / total
     sample = f"{n} of {N_ENVS} envs per step (same T, epochs, minibatches)"
@@ -267,17 +307,12 @@ def run_own(args):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as O
         nc = args.cpu_envs
-        cores = O.lib().orc_max_threads()
-        oenv = O.OracleVecEnv(O.KIND_CARTPOLE, nc, O.splitmix_states_fast(nc, 1)); oenv.reset(True)
-        desc = O.ac_desc(4, HIDDEN, 2)
-        p = O.glorot_params(desc, 123); m = np.zeros_like(p); v = np.zeros_like(p); bt = np.array([0.9, 0.999], np.float32)
-        prng = O.splitmix_states_fast(nc, 2).copy()
-        hyper = O.hyper_array()
-        s0, _ = O.ppo_iteration(oenv, desc, hyper, p, m, v, bt, prng, T, N_EPOCHS, N_MICRO, 0)
+        step, cores = cpu_arm_setup(O, nc)
+        s0 = step()
         reps = int(max(2, min(20, 12.0 / max(s0, 1e-3))))
-        secs = [O.ppo_iteration(oenv, desc, hyper, p, m, v, bt, prng, T, N_EPOCHS, N_MICRO, 1 + k)[0] for k in range(reps)]
+        secs = [step() for _ in range(reps)]
         cpu = {"value": nc * T * reps / float(np.sum(secs)), "unit": "env-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{reps} PPO iterations on {nc} of {N_ENVS} envs (same T / epochs / minibatches), OpenMP over per-env heap objects"}
+               "sample": f"{reps} PPO iterations on {nc} of {N_ENVS} envs (same T / epochs / minibatches), OpenMP over per-env heap objects, thread count picked by calibration"}
 
     if rank == 0:
         line = {

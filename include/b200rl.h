@@ -70,7 +70,11 @@ int b200rl_launch_count(b200rl_ctx* ctx, uint64_t* count_out);
 int b200rl_flush_l2(b200rl_ctx* ctx);
 
 /* ---------------------------------------------------------------- vector env ------- */
-typedef enum { B200RL_ENV_CARTPOLE = 0, B200RL_ENV_PENDULUM = 1, B200RL_ENV_MOUNTAINCAR = 2 } b200rl_env_kind;
+typedef enum {
+    B200RL_ENV_CARTPOLE = 0, B200RL_ENV_PENDULUM = 1, B200RL_ENV_MOUNTAINCAR = 2,
+    B200RL_ENV_CARTPOLE_CONTINUOUS = 3,     /* CartPoleEnv(continuous = true): Float32 action in -1.0..1.0 (CartPoleEnv.jl:74-79,106-110) */
+    B200RL_ENV_MOUNTAINCAR_CONTINUOUS = 4   /* ContinuousMountainCarEnv (MountainCarEnv.jl:73-74,83,107-111); params as mountaincar */
+} b200rl_env_kind;
 typedef enum { B200RL_F32 = 0, B200RL_F64 = 1 } b200rl_dtype;
 typedef enum {
     B200RL_FIELD_STATE = 0,     /* (NS, N) T      env.state                                      */
@@ -105,10 +109,14 @@ typedef struct {   /* MountainCarEnvParams{T}: MountainCarEnv.jl:3-40 */
  * `MultiThreadEnv([...])`.  `rng_state` = (4, N) uint64 host array: raw Xoshiro state per
  * env (Julia side: `Xoshiro(seed_i)` fields s0..s3).  Like the reference constructors it
  * performs one reset!() per env.  Supported: CartPole f32|f64 discrete; Pendulum f32
- * continuous|discrete; MountainCar f32 discrete. */
+ * continuous|discrete; MountainCar f32 discrete; the two *_CONTINUOUS kinds f32. */
 int b200rl_env_create(b200rl_ctx* ctx, int kind, int dtype, int64_t n_envs, const void* params,
                       const uint64_t* rng_state, b200rl_env** out);
 int b200rl_env_destroy(b200rl_env* env);
+/* MaxTimeoutEnv(env, max_t) (RLEnvs/src/environments/wrappers/MaxTimeoutEnv.jl:17-28): is_terminated(env)
+ * also when the wrapper's current_t (= env.t + 1) exceeds max_t; reward(env) still forwards to the wrapped
+ * env.  max_t = 0 removes the wrapper. */
+int b200rl_env_set_max_timeout(b200rl_env* env, int64_t max_t);
 /* Base.copy(env) (RLBase/src/interface.jl:443): deep copy incl. RNG streams */
 int b200rl_env_copy(b200rl_env* env, b200rl_env** out);
 /* Random.seed!(env, seed) (CartPoleEnv.jl:83): replace the raw RNG states */

@@ -37,8 +37,11 @@ template <class T> inline CartPoleParams cartpole_default_params() {
     return p;
 }
 
-template <class T> struct CartPole {
+// CONT = true is CartPoleEnv(continuous = true): ACT = T, action_space -1.0..1.0
+// (CartPoleEnv.jl:74-79,96,106-110).
+template <class T, bool CONT = false> struct CartPole {
     static constexpr int NS = 4, NOBS = 4, NACT = 2;
+    T action_f = 0;  // env.action for the continuous variant
     T g, M, m, l, pml, fmag, dt, ththr, xthr;
     int64_t max_steps;
     std::vector<T> state;  // heap vector per env, like the reference's Vector{T}
@@ -58,8 +61,20 @@ template <class T> struct CartPole {
         jl::rand_array4(rng, u);  // rand(rng, T, 4)
         for (int k = 0; k < 4; ++k) state[k] = (T)0.1 * u[k] - (T)0.05;
         t = 0;
-        action = jl::rand_oneto(rng, 2);  // rand(rng, Base.OneTo(2)) — consumes the stream
+        if (CONT) {
+            // rand(rng, -1.0..1.0): DomainSets' interval sampler (external, UNPINNED) — restated as
+            // leftendpoint + rand(rng, Float64) * width, i.e. one Float64 draw = one 64-bit output.
+            action_f = (T)(-1.0 + jl::rand_f64(rng) * 2.0);
+        } else {
+            action = jl::rand_oneto(rng, 2);  // rand(rng, Base.OneTo(2)) — consumes the stream
+        }
         done = false;
+    }
+    bool act_continuous(T a) {  // CartPoleEnv.jl:106-110; `a in -1.0..1.0` (NaN fails)
+        if (!(a >= (T)-1 && a <= (T)1)) return false;
+        action_f = a;
+        step_force(a * fmag);  // _step!(env, a): force = a * forcemag
+        return true;
     }
     bool act(int64_t a) {  // CartPoleEnv.jl:112-116; returns false on `@assert` failure
         if (a < 1 || a > 2) return false;
@@ -67,9 +82,9 @@ template <class T> struct CartPole {
         step(a == 2 ? 1 : -1);
         return true;
     }
-    void step(int a) {  // CartPoleEnv.jl:118-140
+    void step(int a) { step_force((T)a * fmag); }
+    void step_force(T force) {  // CartPoleEnv.jl:118-140
         t += 1;
-        T force = (T)a * fmag;
         T x = state[0], xdot = state[1], theta = state[2], thetadot = state[3];
         T c = jl::jcos(theta), s = jl::jsin(theta);
         T tmp = (force + (pml * (thetadot * thetadot)) * s) / M;
@@ -168,8 +183,14 @@ inline MountainCarParams mountaincar_default_params() {
     return MountainCarParams{(T)-1.2, (T)0.6, (T)0.07, (T)0.5, (T)0.0, (T)0.001, (T)0.0025, 200};
 }
 
-// Float32, discrete actions (1..3).  Continuous variant is a SURVEY §8f "next" item.
+inline MountainCarParams mountaincar_continuous_default_params() {  // MountainCarEnv.jl:73-74
+    using T = float;
+    return MountainCarParams{(T)-1.2, (T)0.6, (T)0.07, (T)0.45, (T)0.0, (T)0.0015, (T)0.0025, 200};
+}
+
+// Float32; discrete actions (1..3) or, for ContinuousMountainCarEnv, a Float32 force in -1.0..1.0.
 struct MountainCar {
+    float action_f = 0;
     using T = float;
     static constexpr int NS = 2, NOBS = 2, NACT = 3;
     T min_pos, max_pos, max_speed, goal_pos, goal_velocity, power, gravity;
@@ -198,10 +219,17 @@ struct MountainCar {
         step((int)a - 2);
         return true;
     }
-    void step(int force) {  // MountainCarEnv.jl:119-135
+    bool act_continuous(float a) {  // MountainCarEnv.jl:107-111 with a::Float32: all-Float32 arithmetic
+        if (!(a >= -1.0f && a <= 1.0f)) return false;
+        action_f = a;
+        step_force(a);
+        return true;
+    }
+    void step(int force) { step_force((T)force); }
+    void step_force(T force) {  // MountainCarEnv.jl:119-135
         t += 1;
         T x = state[0], v = state[1];
-        v = v + ((T)force * power + jl::jcos(3.0f * x) * (-gravity));
+        v = v + (force * power + jl::jcos(3.0f * x) * (-gravity));
         v = jl::jclamp(v, -max_speed, max_speed);
         x = x + v;
         x = jl::jclamp(x, min_pos, max_pos);

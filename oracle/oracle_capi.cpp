@@ -66,7 +66,7 @@ void orc_cartpole_default_params(int dtype, double* out /*11*/) {
 }
 
 // ---- vector env ----------------------------------------------------------------------
-// kind: 0 CartPole, 1 Pendulum, 2 MountainCar; dtype: 0 f32, 1 f64 (CartPole only)
+// kind: 0 CartPole, 1 Pendulum, 2 MountainCar, 3 continuous CartPole, 4 ContinuousMountainCar; dtype: 0 f32, 1 f64 (CartPole only)
 // params: CartPole 11 doubles (above order); Pendulum 9 (max_speed,max_torque,g,m,l,dt,
 // max_steps,n_actions,continuous); MountainCar 8 (min_pos,max_pos,max_speed,goal_pos,
 // goal_velocity,power,gravity,max_steps).
@@ -82,9 +82,16 @@ void* orc_vecenv_create(int kind, int dtype, int64_t N, const double* q, const u
     } else if (kind == 2) {
         MountainCarParams p{q[0], q[1], q[2], q[3], q[4], q[5], q[6], (int64_t)q[7]};
         return (VecEnvBase*)new VecMountainCar(N, p, rng);
+    } else if (kind == 3) {   // CartPoleEnv(continuous = true), Float32
+        CartPoleParams p{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], (int64_t)q[10]};
+        return (VecEnvBase*)new VecCartPoleC(N, p, rng);
+    } else if (kind == 4) {   // ContinuousMountainCarEnv, Float32
+        MountainCarParams p{q[0], q[1], q[2], q[3], q[4], q[5], q[6], (int64_t)q[7]};
+        return (VecEnvBase*)new VecMountainCarC(N, p, rng);
     }
     return nullptr;
 }
+void orc_vecenv_set_max_timeout(void* h, int64_t max_t) { ((VecEnvBase*)h)->max_timeout = max_t; }
 void orc_vecenv_destroy(void* h) { delete (VecEnvBase*)h; }
 void orc_vecenv_reset(void* h, int force) { ((VecEnvBase*)h)->reset(force); }
 int orc_vecenv_step(void* h, const void* actions, int auto_reset) { return ((VecEnvBase*)h)->step(actions, auto_reset); }

@@ -28,6 +28,10 @@ struct VecEnvBase {
     virtual void get(int field, void* dst) const = 0;
     virtual void set(int field, const void* src) = 0;
     virtual int64_t size() const = 0;
+    // MaxTimeoutEnv(env, max_t) (wrappers/MaxTimeoutEnv.jl:17-28): is_terminated also when
+    // current_t > max_t; current_t starts at 1 with every reset! and counts act! calls, so
+    // current_t == env.t + 1.  reward(env) still forwards to the wrapped env.  0 = no wrapper.
+    int64_t max_timeout = 0;
 };
 
 template <class E, class T, class ActT> struct VecEnv : VecEnvBase {
@@ -55,8 +59,9 @@ template <class E, class T, class ActT> struct VecEnv : VecEnvBase {
     void post(int64_t i, int auto_reset) {
         E& e = *envs[i];
         rewards[i] = e.reward();
-        uint8_t f = e.done ? 1 : 0;
-        if (auto_reset && e.done) { e.reset(); f = 3; }
+        bool term = e.done || (max_timeout > 0 && e.t + 1 > max_timeout);
+        uint8_t f = term ? 1 : 0;
+        if (auto_reset && term) { e.reset(); f = 3; }
         flags[i] = f;
     }
     int step(const void* actions, int auto_reset) override {
@@ -113,12 +118,20 @@ using VecCartPoleF64 = VecEnv<CartPole<double>, double, int32_t>;
 using VecPendulumC = VecEnv<Pendulum, float, float>;     // continuous torque
 using VecPendulumD = VecEnv<Pendulum, float, int32_t>;   // discrete torque index
 using VecMountainCar = VecEnv<MountainCar, float, int32_t>;
+using VecCartPoleC = VecEnv<CartPole<float, true>, float, float>;   // CartPoleEnv(continuous = true)
+using VecMountainCarC = VecEnv<MountainCar, float, float>;          // ContinuousMountainCarEnv
 
 template <> inline bool VecCartPoleF32::do_act(CartPole<float>& e, int32_t a) { return e.act(a); }
 template <> inline bool VecCartPoleF64::do_act(CartPole<double>& e, int32_t a) { return e.act(a); }
 template <> inline bool VecPendulumC::do_act(Pendulum& e, float a) { return e.act_continuous((double)a); }
 template <> inline bool VecPendulumD::do_act(Pendulum& e, int32_t a) { return e.act_discrete(a); }
 template <> inline bool VecMountainCar::do_act(MountainCar& e, int32_t a) { return e.act(a); }
+template <> inline bool VecCartPoleC::do_act(CartPole<float, true>& e, float a) { return e.act_continuous(a); }
+template <> inline bool VecMountainCarC::do_act(MountainCar& e, float a) { return e.act_continuous(a); }
+template <> inline int64_t VecCartPoleC::n_random_actions(const CartPole<float, true>&) { return 0; }
+template <> inline int64_t VecMountainCarC::n_random_actions(const MountainCar&) { return 0; }
+template <> inline void VecCartPoleC::do_act_discrete(CartPole<float, true>&, int64_t) {}
+template <> inline void VecMountainCarC::do_act_discrete(MountainCar&, int64_t) {}
 template <> inline int64_t VecCartPoleF32::n_random_actions(const CartPole<float>&) { return 2; }
 template <> inline int64_t VecCartPoleF64::n_random_actions(const CartPole<double>&) { return 2; }
 template <> inline int64_t VecPendulumC::n_random_actions(const Pendulum& e) { return e.n_actions; }

@@ -13,7 +13,7 @@ SO_PATH = os.path.join(HERE, "libb200rl.so")
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_ACTION, ERR_NCCL, ERR_OOM = -1, -2, -3, -4, -5, -6
 
-ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR = 0, 1, 2
+ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR, ENV_CARTPOLE_CONTINUOUS, ENV_MOUNTAINCAR_CONTINUOUS = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
 FIELD_STATE, FIELD_OBS, FIELD_REWARD, FIELD_TERMINAL, FIELD_T, FIELD_RNG, FIELD_FLAGS, FIELD_ACTION = range(8)
 
@@ -79,6 +79,7 @@ SIGNATURES = {
     "b200rl_launch_count": (_i32, [_vp, C.POINTER(_u64)]),
     "b200rl_env_create": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _pp]),
     "b200rl_env_destroy": (_i32, [_vp]),
+    "b200rl_env_set_max_timeout": (_i32, [_vp, _i64]),
     "b200rl_env_copy": (_i32, [_vp, _pp]),
     "b200rl_env_seed": (_i32, [_vp, _vp]),
     "b200rl_env_reset": (_i32, [_vp, _i32]),

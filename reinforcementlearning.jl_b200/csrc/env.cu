@@ -34,6 +34,7 @@ struct EnvArrays {
     // optional fused trajectory push targets (column t of the rollout buffers); may be null
     void* traj_reward;
     uint8_t* traj_terminal;
+    int max_timeout;  // MaxTimeoutEnv(env, max_t) (wrappers/MaxTimeoutEnv.jl:17-28); 0 = not wrapped
 };
 
 __device__ __forceinline__ Xo load_rng(const unsigned long long* rng, int64_t i) {
@@ -48,16 +49,20 @@ __device__ __forceinline__ void store_rng(unsigned long long* rng, int64_t i, co
 }
 
 // ------------------------------------------------------------------ CartPole ----------
-template <class T> struct CartPoleD {
+// CONT: CartPoleEnv(continuous = true) — ACT = T, action_space -1.0..1.0 (CartPoleEnv.jl:74-79,96,106-110)
+template <class T, bool CONT = false> struct CartPoleD {
     using real = T;
-    using act_t = int32_t;
+    using act_t = typename std::conditional<CONT, T, int32_t>::type;
     static constexpr int NS = 4, NOBS = 4;
     static constexpr bool kObsIsState = true;
     struct P { T g, M, m, l, pml, fmag, dt, ththr, xthr; int max_steps; };
     struct S { T x, xd, th, thd; };
     __device__ static S load(const void* st, int64_t i);
     __device__ static void store(void* st, int64_t i, const S& s);
-    __device__ static bool valid(const P&, act_t a) { return a == 1 || a == 2; }
+    __device__ static bool valid(const P&, act_t a) {
+        if (CONT) return (T)a >= (T)-1 && (T)a <= (T)1;   // a in -1.0..1.0 (NaN fails)
+        return a == 1 || a == 2;
+    }
     __device__ static unsigned long long n_random(const P&) { return 2; }
     __device__ static act_t from_index(const P&, long long a) { return (act_t)a; }
     // reset!: CartPoleEnv.jl:98-104 — rand(rng, T, 4) then rand(rng, Base.OneTo(2))
@@ -68,13 +73,16 @@ template <class T> struct CartPoleD {
         s.xd = (T)0.1 * u[1] - (T)0.05;
         s.th = (T)0.1 * u[2] - (T)0.05;
         s.thd = (T)0.1 * u[3] - (T)0.05;
-        last_action = (act_t)jld::rand_oneto(g, 2);
+        // discrete: rand(rng, Base.OneTo(2)); continuous: rand(rng, -1.0..1.0) restated as
+        // -1 + rand(Float64) * 2 (DomainSets sampler, external/unpinned) — one 64-bit output either way
+        if (CONT) last_action = (act_t)(-1.0 + jld::rand_f64(g) * 2.0);
+        else last_action = (act_t)jld::rand_oneto(g, 2);
     }
     // _step!: CartPoleEnv.jl:118-140.  `4 / 3` is Float64, so thetaacc, xacc and the two
     // velocity updates are Float64 for T = Float32; x and theta updates stay in T.
     __device__ static void step(const P& p, S& s, int& t, act_t a, bool& done, T& reward) {
         t += 1;
-        T force = (T)(a == 2 ? 1 : -1) * p.fmag;
+        T force = CONT ? (T)a * p.fmag : (T)(a == 2 ? 1 : -1) * p.fmag;
         T c = jld::jcos(s.th), sn = jld::jsin(s.th);
         T tmp = (force + (p.pml * (s.thd * s.thd)) * sn) / p.M;
         double den = (double)p.l * (4.0 / 3.0 - (double)((p.m * (c * c)) / p.M));
@@ -90,22 +98,28 @@ template <class T> struct CartPoleD {
     }
     __device__ static void write_obs(void*, int64_t, int64_t, const S&) {}
 };
-template <> __device__ __forceinline__ CartPoleD<float>::S CartPoleD<float>::load(const void* st, int64_t i) {
+template <class S> __device__ __forceinline__ S cp_load(const float* st, int64_t i) {
     float4 v = reinterpret_cast<const float4*>(st)[i];
     return S{v.x, v.y, v.z, v.w};
 }
-template <> __device__ __forceinline__ void CartPoleD<float>::store(void* st, int64_t i, const S& s) {
-    reinterpret_cast<float4*>(st)[i] = make_float4(s.x, s.xd, s.th, s.thd);
-}
-template <> __device__ __forceinline__ CartPoleD<double>::S CartPoleD<double>::load(const void* st, int64_t i) {
+template <class S> __device__ __forceinline__ S cp_load(const double* st, int64_t i) {
     const double2* p = reinterpret_cast<const double2*>(st) + 2 * i;
     double2 a = p[0], b = p[1];
     return S{a.x, a.y, b.x, b.y};
 }
-template <> __device__ __forceinline__ void CartPoleD<double>::store(void* st, int64_t i, const S& s) {
+template <class S> __device__ __forceinline__ void cp_store(float* st, int64_t i, const S& s) {
+    reinterpret_cast<float4*>(st)[i] = make_float4(s.x, s.xd, s.th, s.thd);
+}
+template <class S> __device__ __forceinline__ void cp_store(double* st, int64_t i, const S& s) {
     double2* p = reinterpret_cast<double2*>(st) + 2 * i;
     p[0] = make_double2(s.x, s.xd);
     p[1] = make_double2(s.th, s.thd);
+}
+template <class T, bool CONT> __device__ __forceinline__ typename CartPoleD<T, CONT>::S CartPoleD<T, CONT>::load(const void* st, int64_t i) {
+    return cp_load<S>(reinterpret_cast<const T*>(st), i);
+}
+template <class T, bool CONT> __device__ __forceinline__ void CartPoleD<T, CONT>::store(void* st, int64_t i, const S& s) {
+    cp_store<S>(reinterpret_cast<T*>(st), i, s);
 }
 
 // ------------------------------------------------------------------ Pendulum ----------
@@ -168,9 +182,10 @@ template <bool CONT> struct PendulumD {
 };
 
 // ---------------------------------------------------------------- MountainCar ---------
-struct MountainCarD {
+// CONT: ContinuousMountainCarEnv — Float32 force in -1.0..1.0 (MountainCarEnv.jl:73-74,83,93,107-111)
+template <bool CONT = false> struct MountainCarD {
     using real = float;
-    using act_t = int32_t;
+    using act_t = typename std::conditional<CONT, float, int32_t>::type;
     static constexpr int NS = 2, NOBS = 2;
     static constexpr bool kObsIsState = true;
     struct P { float min_pos, max_pos, max_speed, goal_pos, goal_velocity, power, gravity; int max_steps; };
@@ -182,7 +197,10 @@ struct MountainCarD {
     __device__ static void store(void* st, int64_t i, const S& s) {
         reinterpret_cast<float2*>(st)[i] = make_float2(s.x, s.v);
     }
-    __device__ static bool valid(const P&, act_t a) { return a >= 1 && a <= 3; }
+    __device__ static bool valid(const P&, act_t a) {
+        if (CONT) return (float)a >= -1.0f && (float)a <= 1.0f;
+        return a >= 1 && a <= 3;
+    }
     __device__ static unsigned long long n_random(const P&) { return 3; }
     __device__ static act_t from_index(const P&, long long a) { return (act_t)a; }
     // reset!: MountainCarEnv.jl:99-105 (Float64 literals 0.2, 0.6)
@@ -195,7 +213,8 @@ struct MountainCarD {
     __device__ static void step(const P& p, S& s, int& t, act_t a, bool& done, float& reward) {
         t += 1;
         float x = s.x, v = s.v;
-        v = v + ((float)(a - 2) * p.power + jld::jcos(3.0f * x) * (-p.gravity));
+        float force = CONT ? (float)a : (float)((int)a - 2);   // act!(env, a::Int) -> _step!(env, a - 2)
+        v = v + (force * p.power + jld::jcos(3.0f * x) * (-p.gravity));
         v = jld::jclamp(v, -p.max_speed, p.max_speed);
         x = x + v;
         x = jld::jclamp(x, p.min_pos, p.max_pos);
@@ -267,6 +286,8 @@ __global__ void __launch_bounds__(kBlock) env_step_kernel(typename Env::P p, Env
             bool done;
             T rew;
             Env::step(p, s, t, act, done, rew);
+            // MaxTimeoutEnv: terminated also when current_t (= t + 1) > max_t; reward untouched
+            if (a.max_timeout > 0 && t + 1 > a.max_timeout) done = true;
             float ret = a.ep_ret[i] + (float)rew;
             uint8_t f = done ? 1 : 0;
             if (done && !((prev & 1) && !(prev & 2))) { finished = true; fin_ret = ret; fin_len = t; }
@@ -327,7 +348,7 @@ struct b200rl_env {
         CartPoleD<float>::P cp32;
         CartPoleD<double>::P cp64;
         PendP pend;
-        MountainCarD::P mc;
+        MountainCarD<false>::P mc;
     } p;
     EnvArrays a;
     uint64_t steps_launched;
@@ -356,12 +377,24 @@ static int dispatch_step(b200rl_env* e, const void* actions, bool random, bool a
     switch (e->kind) {
         case B200RL_ENV_CARTPOLE:
             if (e->dtype == B200RL_F64) return launch_step<CartPoleD<double>>(e, e->p.cp64, actions, random, auto_reset);
+            if (e->continuous && !random) {
+                CartPoleD<float, true>::P q;
+                static_assert(sizeof(q) == sizeof(e->p.cp32), "same params layout");
+                memcpy(&q, &e->p.cp32, sizeof q);
+                return launch_step<CartPoleD<float, true>>(e, q, actions, random, auto_reset);
+            }
             return launch_step<CartPoleD<float>>(e, e->p.cp32, actions, random, auto_reset);
         case B200RL_ENV_PENDULUM:
             if (e->continuous && !random) return launch_step<PendulumD<true>>(e, e->p.pend, actions, random, auto_reset);
             return launch_step<PendulumD<false>>(e, e->p.pend, actions, random, auto_reset);
         case B200RL_ENV_MOUNTAINCAR:
-            return launch_step<MountainCarD>(e, e->p.mc, actions, random, auto_reset);
+            if (e->continuous && !random) {
+                MountainCarD<true>::P q;
+                static_assert(sizeof(q) == sizeof(e->p.mc), "same params layout");
+                memcpy(&q, &e->p.mc, sizeof q);
+                return launch_step<MountainCarD<true>>(e, q, actions, random, auto_reset);
+            }
+            return launch_step<MountainCarD<false>>(e, e->p.mc, actions, random, auto_reset);
     }
     return B200RL_ERR_INVALID;
 }
@@ -369,9 +402,14 @@ static int dispatch_reset(b200rl_env* e, int force) {
     switch (e->kind) {
         case B200RL_ENV_CARTPOLE:
             if (e->dtype == B200RL_F64) return launch_reset<CartPoleD<double>>(e, e->p.cp64, force);
+            if (e->continuous) {
+                CartPoleD<float, true>::P q;
+                memcpy(&q, &e->p.cp32, sizeof q);
+                return launch_reset<CartPoleD<float, true>>(e, q, force);
+            }
             return launch_reset<CartPoleD<float>>(e, e->p.cp32, force);
         case B200RL_ENV_PENDULUM: return launch_reset<PendulumD<true>>(e, e->p.pend, force);
-        case B200RL_ENV_MOUNTAINCAR: return launch_reset<MountainCarD>(e, e->p.mc, force);
+        case B200RL_ENV_MOUNTAINCAR: return launch_reset<MountainCarD<false>>(e, e->p.mc, force);
     }
     return B200RL_ERR_INVALID;
 }
@@ -437,11 +475,15 @@ int b200rl_env_create(b200rl_ctx* ctx, int kind, int dtype, int64_t n_envs, cons
     TRY(ctx_bind(ctx));
     REQUIRE(out && rng_state, B200RL_ERR_INVALID, "null out / rng_state");
     REQUIRE(n_envs > 0, B200RL_ERR_INVALID, "n_envs must be positive");
-    REQUIRE(dtype == B200RL_F32 || (dtype == B200RL_F64 && kind == B200RL_ENV_CARTPOLE), B200RL_ERR_UNSUPPORTED,
+    REQUIRE(dtype == B200RL_F32 || (dtype == B200RL_F64 && (kind == B200RL_ENV_CARTPOLE || kind == B200RL_ENV_CARTPOLE_CONTINUOUS)), B200RL_ERR_UNSUPPORTED,
             "Float64 is supported for CartPole only (no BASELINE config uses Float64 Pendulum/MountainCar)");
     b200rl_env* e = new b200rl_env();
     memset(&e->a, 0, sizeof e->a);
-    e->ctx = ctx; e->kind = kind; e->dtype = dtype; e->N = n_envs; e->continuous = false;
+    bool cont_kind = kind == B200RL_ENV_CARTPOLE_CONTINUOUS || kind == B200RL_ENV_MOUNTAINCAR_CONTINUOUS;
+    if (cont_kind && dtype != B200RL_F32) { delete e; REQUIRE(false, B200RL_ERR_UNSUPPORTED, "continuous-action variants are Float32 only"); }
+    if (kind == B200RL_ENV_CARTPOLE_CONTINUOUS) kind = B200RL_ENV_CARTPOLE;
+    if (kind == B200RL_ENV_MOUNTAINCAR_CONTINUOUS) kind = B200RL_ENV_MOUNTAINCAR;
+    e->ctx = ctx; e->kind = kind; e->dtype = dtype; e->N = n_envs; e->continuous = cont_kind;
     e->tsize = dtype == B200RL_F64 ? 8 : 4;
     e->steps_launched = 0;
     if (kind == B200RL_ENV_CARTPOLE) {
@@ -468,11 +510,14 @@ int b200rl_env_create(b200rl_ctx* ctx, int kind, int dtype, int64_t n_envs, cons
         e->p.pend = PendP{(float)d.max_speed, (float)d.max_torque, (float)d.g, (float)d.m, (float)d.l, (float)d.dt,
                                         (int)d.max_steps, (int)d.n_actions};
     } else if (kind == B200RL_ENV_MOUNTAINCAR) {
+        // ContinuousMountainCarEnv defaults: goal_pos = 0.45, power = 0.0015 (MountainCarEnv.jl:73-74)
         b200rl_mountaincar_params d = params ? *(const b200rl_mountaincar_params*)params
-                                             : b200rl_mountaincar_params{(float)-1.2, (float)0.6, (float)0.07, (float)0.5, 0.0,
-                                                                         (float)0.001, (float)0.0025, 200};
+                                      : cont_kind ? b200rl_mountaincar_params{(float)-1.2, (float)0.6, (float)0.07, (float)0.45, 0.0,
+                                                                              (float)0.0015, (float)0.0025, 200}
+                                                  : b200rl_mountaincar_params{(float)-1.2, (float)0.6, (float)0.07, (float)0.5, 0.0,
+                                                                              (float)0.001, (float)0.0025, 200};
         e->ns = 2; e->nobs = 2;
-        e->p.mc = MountainCarD::P{(float)d.min_pos, (float)d.max_pos, (float)d.max_speed, (float)d.goal_pos, (float)d.goal_velocity,
+        e->p.mc = MountainCarD<false>::P{(float)d.min_pos, (float)d.max_pos, (float)d.max_speed, (float)d.goal_pos, (float)d.goal_velocity,
                                   (float)d.power, (float)d.gravity, (int)d.max_steps};
     } else {
         delete e;
@@ -505,6 +550,7 @@ int b200rl_env_copy(b200rl_env* src, b200rl_env** out) {
     TRY(ctx_bind(src->ctx));
     b200rl_env* e = new b200rl_env(*src);
     memset(&e->a, 0, sizeof e->a);
+    e->a.max_timeout = src->a.max_timeout;
     int s = env_alloc(e);
     if (s != B200RL_OK) { b200rl_env_destroy(e); return s; }
     cudaStream_t st = src->ctx->stream;
@@ -548,10 +594,17 @@ int b200rl_env_step(b200rl_env* e, const void* actions, int actions_on_device, i
     return B200RL_OK;
 }
 
+int b200rl_env_set_max_timeout(b200rl_env* e, int64_t max_t) {
+    REQUIRE(e, B200RL_ERR_INVALID, "null env");
+    REQUIRE(max_t >= 0 && max_t < (1ll << 31), B200RL_ERR_INVALID, "max_t out of range");
+    e->a.max_timeout = (int)max_t;
+    return B200RL_OK;
+}
+
 int b200rl_env_step_random(b200rl_env* e, int auto_reset) {
     REQUIRE(e, B200RL_ERR_INVALID, "null env");
-    REQUIRE(!(e->kind == B200RL_ENV_PENDULUM && e->continuous), B200RL_ERR_UNSUPPORTED,
-            "RandomPolicy on a continuous interval (DomainSets sampler) is not restated; use a discrete Pendulum");
+    REQUIRE(!e->continuous, B200RL_ERR_UNSUPPORTED,
+            "RandomPolicy on a continuous interval (DomainSets sampler) is not restated; use a discrete-action env");
     TRY(ctx_bind(e->ctx));
     e->steps_launched += 1;
     return dispatch_step(e, nullptr, true, auto_reset != 0);

@@ -13,7 +13,9 @@ import numpy as np
 
 from . import _lib as L
 
-_KINDS = {"CartPole": L.ENV_CARTPOLE, "Pendulum": L.ENV_PENDULUM, "MountainCar": L.ENV_MOUNTAINCAR}
+_KINDS = {"CartPole": L.ENV_CARTPOLE, "Pendulum": L.ENV_PENDULUM, "MountainCar": L.ENV_MOUNTAINCAR,
+          "ContinuousCartPole": L.ENV_CARTPOLE_CONTINUOUS, "ContinuousMountainCar": L.ENV_MOUNTAINCAR_CONTINUOUS}
+_BASE = {L.ENV_CARTPOLE_CONTINUOUS: L.ENV_CARTPOLE, L.ENV_MOUNTAINCAR_CONTINUOUS: L.ENV_MOUNTAINCAR}
 _NS = {L.ENV_CARTPOLE: 4, L.ENV_PENDULUM: 2, L.ENV_MOUNTAINCAR: 2}
 _NOBS = {L.ENV_CARTPOLE: 4, L.ENV_PENDULUM: 3, L.ENV_MOUNTAINCAR: 2}
 
@@ -47,7 +49,8 @@ class B200VecEnv:
 
     def __init__(self, ctx, kind, n_envs, rng_state, T=np.float32, params=None, auto_reset=False, **kwargs):
         self.ctx, self.lib = ctx, ctx.lib
-        self.kind = _KINDS[kind] if isinstance(kind, str) else int(kind)
+        create_kind = _KINDS[kind] if isinstance(kind, str) else int(kind)
+        self.kind = _BASE.get(create_kind, create_kind)     # kind of dynamics; `continuous` carries the action type
         self.n = int(n_envs)
         self.T = np.dtype(T).type
         self.auto_reset = bool(auto_reset)
@@ -56,13 +59,15 @@ class B200VecEnv:
                 params = cartpole_params(T=self.T, **kwargs)
             elif self.kind == L.ENV_PENDULUM:
                 params = pendulum_params(**kwargs)
+            elif create_kind == L.ENV_MOUNTAINCAR_CONTINUOUS:  # MountainCarEnv.jl:73-74
+                params = mountaincar_params(**{"goal_pos": 0.45, "power": 0.0015, **kwargs})
             else:
                 params = mountaincar_params(**kwargs)
         self.params = params
-        self.continuous = self.kind == L.ENV_PENDULUM and bool(params.continuous)
+        self.continuous = create_kind in _BASE or (self.kind == L.ENV_PENDULUM and bool(params.continuous))
         rng_state = np.ascontiguousarray(rng_state, dtype=np.uint64).reshape(self.n, 4)
         h = C.c_void_p()
-        L.check(self.lib.b200rl_env_create(ctx.h, self.kind, L.F64 if self.T is np.float64 else L.F32, self.n,
+        L.check(self.lib.b200rl_env_create(ctx.h, create_kind, L.F64 if self.T is np.float64 else L.F32, self.n,
                                            C.byref(params), L.ptr(rng_state), C.byref(h)))
         self.h = h
 
@@ -102,6 +107,10 @@ class B200VecEnv:
             if a.shape != (self.n,):
                 raise ValueError(f"expected {self.n} actions, got shape {a.shape}")
             L.check(self.lib.b200rl_env_step(self.h, L.ptr(a), 0, int(self.auto_reset)))
+
+    def set_max_timeout(self, max_t):
+        """MaxTimeoutEnv(env, max_t) (wrappers/MaxTimeoutEnv.jl:17-28); 0 removes the wrapper."""
+        L.check(self.lib.b200rl_env_set_max_timeout(self.h, int(max_t)))
 
     def act_random_(self):
         """plan!(RandomPolicy(), env) + act!(env, a) fused: each env draws from its own stream."""
@@ -169,9 +178,9 @@ class B200VecEnv:
     # ---- spaces (shape information only) ---------------------------------------------
     def action_space(self):
         if self.kind == L.ENV_CARTPOLE:
-            return range(1, 3)
+            return (-1.0, 1.0) if self.continuous else range(1, 3)
         if self.kind == L.ENV_MOUNTAINCAR:
-            return range(1, 4)
+            return (-1.0, 1.0) if self.continuous else range(1, 4)
         return (-2.0, 2.0) if self.continuous else range(1, int(self.params.n_actions) + 1)
 
     def state_space(self):

@@ -11,9 +11,9 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_ROOT, "oracle", "liboracle.so")
 
 F_STATE, F_OBS, F_REWARD, F_TERMINAL, F_T, F_RNG, F_FLAGS = 0, 1, 2, 3, 4, 5, 6
-KIND_CARTPOLE, KIND_PENDULUM, KIND_MOUNTAINCAR = 0, 1, 2
-NS = {0: 4, 1: 2, 2: 2}
-NOBS = {0: 4, 1: 3, 2: 2}
+KIND_CARTPOLE, KIND_PENDULUM, KIND_MOUNTAINCAR, KIND_CARTPOLE_CONT, KIND_MOUNTAINCAR_CONT = 0, 1, 2, 3, 4
+NS = {0: 4, 1: 2, 2: 2, 3: 4, 4: 2}
+NOBS = {0: 4, 1: 3, 2: 2, 3: 4, 4: 2}
 
 
 def build():
@@ -38,6 +38,7 @@ def lib():
         "orc_seed_splitmix": (None, [u64, vp]),
         "orc_cartpole_default_params": (None, [i32, vp]),
         "orc_vecenv_create": (vp, [i32, i32, i64, vp, vp]), "orc_vecenv_destroy": (None, [vp]),
+        "orc_vecenv_set_max_timeout": (None, [vp, i64]),
         "orc_vecenv_reset": (None, [vp, i32]), "orc_vecenv_step": (i32, [vp, vp, i32]),
         "orc_vecenv_step_random": (i32, [vp, i32, vp]), "orc_vecenv_get": (None, [vp, i32, vp]),
         "orc_vecenv_set": (None, [vp, i32, vp]), "orc_vecenv_bench_random": (f64, [vp, i32]),
@@ -104,13 +105,15 @@ def splitmix_states_fast(n, seed=0x9E3779B97F4A7C15):
 
 def default_params(kind, dtype="f32"):
     L = lib()
-    if kind == KIND_CARTPOLE:
+    if kind in (KIND_CARTPOLE, KIND_CARTPOLE_CONT):
         q = np.empty(11, dtype=np.float64)
         L.orc_cartpole_default_params(1 if dtype == "f64" else 0, _p(q))
         return q
     if kind == KIND_PENDULUM:
         return np.array([8, 2, 10, 1, 1, float(np.float32(0.05)), 200, 3, 1], dtype=np.float64)
     f = lambda v: float(np.float32(v))
+    if kind == KIND_MOUNTAINCAR_CONT:  # MountainCarEnv.jl:73-74
+        return np.array([f(-1.2), f(0.6), f(0.07), f(0.45), 0.0, f(0.0015), f(0.0025), 200], dtype=np.float64)
     return np.array([f(-1.2), f(0.6), f(0.07), f(0.5), 0.0, f(0.001), f(0.0025), 200], dtype=np.float64)
 
 
@@ -121,7 +124,7 @@ class OracleVecEnv:
         self.np_t = np.float64 if dtype == "f64" else np.float32
         self.params = default_params(kind, dtype) if params is None else np.asarray(params, np.float64)
         rng_states = np.ascontiguousarray(rng_states, dtype=np.uint64).reshape(n, 4)
-        self.continuous = kind == KIND_PENDULUM and self.params[8] != 0
+        self.continuous = (kind == KIND_PENDULUM and self.params[8] != 0) or kind in (KIND_CARTPOLE_CONT, KIND_MOUNTAINCAR_CONT)
         self.h = self.L.orc_vecenv_create(kind, 1 if dtype == "f64" else 0, n, _p(self.params), _p(rng_states))
         assert self.h
 
@@ -136,6 +139,9 @@ class OracleVecEnv:
     def step(self, actions, auto_reset=False):
         a = np.ascontiguousarray(actions, dtype=np.float32 if self.continuous else np.int32)
         return self.L.orc_vecenv_step(self.h, _p(a), int(auto_reset))
+
+    def set_max_timeout(self, max_t):
+        self.L.orc_vecenv_set_max_timeout(self.h, int(max_t))
 
     def step_random(self, auto_reset=False):
         a = np.empty(self.n, dtype=np.int32)

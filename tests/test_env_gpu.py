@@ -9,7 +9,8 @@ import oracle_lib as O
 
 pytestmark = pytest.mark.gpu
 
-KINDS = {"CartPole": O.KIND_CARTPOLE, "Pendulum": O.KIND_PENDULUM, "MountainCar": O.KIND_MOUNTAINCAR}
+KINDS = {"CartPole": O.KIND_CARTPOLE, "Pendulum": O.KIND_PENDULUM, "MountainCar": O.KIND_MOUNTAINCAR,
+         "ContinuousCartPole": O.KIND_CARTPOLE_CONT, "ContinuousMountainCar": O.KIND_MOUNTAINCAR_CONT}
 
 
 def bits(a):
@@ -93,6 +94,69 @@ def test_given_actions_soft_reset_bit_exact(pkg, ctx, kind, continuous):
         if s % 50 == 0 or s >= steps - 2:
             assert_same(env, ref, f"{kind} step {s}")
     env.check()
+
+
+@pytest.mark.parametrize("kind", ["ContinuousCartPole", "ContinuousMountainCar"])
+@pytest.mark.parametrize("auto_reset", [False, True])
+def test_continuous_action_variants_bit_exact(pkg, ctx, kind, auto_reset):
+    """CartPoleEnv(continuous = true) (CartPoleEnv.jl:74-79,106-110) and ContinuousMountainCarEnv
+    (MountainCarEnv.jl:73-74,107-111) with Float32 forces in -1.0..1.0."""
+    n, steps = 4099, 420
+    seeds = O.splitmix_states_fast(n, seed=311)
+    env = pkg.B200VecEnv(ctx, kind, n, seeds, auto_reset=auto_reset)
+    ref = O.OracleVecEnv(KINDS[kind], n, seeds)
+    assert env.continuous and env.action_space() == (-1.0, 1.0)
+    assert_same(env, ref, "after construction")
+    rng = np.random.default_rng(17)
+    for s in range(steps):
+        act = rng.uniform(-1, 1, n).astype(np.float32)
+        act[::7] = np.float32(1.0); act[3::11] = np.float32(-1.0)   # closed interval end points are valid
+        if not auto_reset:
+            env.reset_(is_force=False); ref.reset(force=False)
+        env.act_(act); assert ref.step(act, auto_reset=auto_reset) == 0
+        if s % 60 == 0 or s >= steps - 2:
+            assert_same(env, ref, f"{kind} step {s}")
+    env.check()
+    assert env.episode_stats()["episodes"] > 0
+    # `@assert a in action_space(env)`: 1.5 and NaN are rejected, the env is left untouched
+    before = env.internal_state().copy()
+    bad = np.zeros(n, np.float32); bad[5] = 1.5; bad[9] = np.nan
+    env.act_(bad)
+    with pytest.raises(pkg.B200RLError):
+        env.check()
+    after = env.internal_state()
+    assert np.array_equal(bits(before[:, [5, 9]]), bits(after[:, [5, 9]]))
+    with pytest.raises(pkg.B200RLError):
+        env.act_random_()       # RandomPolicy over an interval is not restated
+    env.close()
+
+
+@pytest.mark.parametrize("kind,max_t", [("CartPole", 7), ("MountainCar", 50), ("Pendulum", 33)])
+def test_max_timeout_wrapper_bit_exact(pkg, ctx, kind, max_t):
+    """MaxTimeoutEnv(env, max_t) (wrappers/MaxTimeoutEnv.jl:17-28): terminal once current_t > max_t,
+    reward still the wrapped env's."""
+    n, steps = 2000, 180
+    seeds = O.splitmix_states_fast(n, seed=5)
+    kw = dict(continuous=False, n_actions=3) if kind == "Pendulum" else {}
+    env = pkg.B200VecEnv(ctx, kind, n, seeds, auto_reset=True, **kw)
+    params = None
+    if kind == "Pendulum":
+        params = O.default_params(O.KIND_PENDULUM); params[7], params[8] = 3, 0.0
+    ref = O.OracleVecEnv(KINDS[kind], n, seeds, params=params)
+    env.set_max_timeout(max_t); ref.set_max_timeout(max_t)
+    saw_timeout = False
+    for s in range(steps):
+        env.act_random_(); ref.step_random(auto_reset=True)
+        assert_same(env, ref, f"{kind} step {s}")
+        if s == max_t - 1:
+            term = env.is_terminated()
+            if kind == "CartPole":      # at the timeout step the wrapped env still pays 1 where it is not itself done
+                assert term.all() and (env.reward() == 1).any()
+            saw_timeout = term.all()
+    assert saw_timeout
+    cp = env.copy(); cp.act_random_(); ref.step_random(auto_reset=True)
+    assert_same(cp, ref, "copy keeps the wrapper")
+    env.close(); cp.close()
 
 
 def test_device_resident_actions_and_auto_reset_given_actions(pkg, ctx):

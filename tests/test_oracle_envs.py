@@ -142,3 +142,82 @@ def test_invalid_actions_are_rejected():
     assert e.step([1, 2, 3, 0]) == 2
     p = _fresh(O.KIND_PENDULUM, 2)
     assert p.step(np.array([2.5, np.nan], np.float32)) == 2
+
+
+def test_continuous_cartpole_matches_discrete_at_unit_force_and_kat():
+    """CartPoleEnv(continuous = true): _step!(env, a) with force = a * forcemag (CartPoleEnv.jl:106-110,118-120).
+    a = +-1.0 is the discrete env's action 2 / 1 bit for bit; reset! consumes the same three 64-bit draws."""
+    n = 64
+    seeds = O.splitmix_states_fast(n, 21)
+    d = O.OracleVecEnv(O.KIND_CARTPOLE, n, seeds)
+    c = O.OracleVecEnv(O.KIND_CARTPOLE_CONT, n, seeds)
+    assert np.array_equal(d.get(O.F_RNG), c.get(O.F_RNG)) and np.array_equal(d.get(O.F_STATE), c.get(O.F_STATE))
+    rng = np.random.default_rng(0)
+    for _ in range(250):
+        a = rng.integers(1, 3, n).astype(np.int32)
+        d.step(a, auto_reset=True)
+        assert c.step(np.where(a == 2, 1.0, -1.0).astype(np.float32), auto_reset=True) == 0
+        for f in (O.F_STATE, O.F_REWARD, O.F_FLAGS, O.F_T, O.F_RNG):
+            assert np.array_equal(d.get(f), c.get(f))
+    # known answer from the formula at the zero state, a = 0.5 (Float32 env; `4/3` sub-expressions Float64)
+    e = O.OracleVecEnv(O.KIND_CARTPOLE_CONT, 1, O.splitmix_states_fast(1, 3))
+    e.set(O.F_STATE, np.zeros((1, 4), np.float32)); e.set(O.F_T, np.zeros(1, np.int32))
+    assert e.step(np.array([0.5], np.float32)) == 0
+    f32 = np.float32
+    q = O.default_params(O.KIND_CARTPOLE, "f32")
+    M, m, l, pml, fmag, dt = f32(q[3]), f32(q[2]), f32(q[4]), f32(q[5]), f32(q[6]), f32(q[7])
+    tmp = f32(f32(0.5) * fmag) / M
+    den = float(l) * (4.0 / 3.0 - float(f32(m * f32(1)) / M))
+    thacc = float(f32(f32(0) - f32(1) * tmp)) / den
+    xacc = float(tmp) - (float(pml) * thacc) * 1.0 / float(M)
+    want = np.array([0, f32(float(dt) * xacc), 0, f32(float(dt) * thacc)], np.float32)
+    assert np.array_equal(e.get(O.F_STATE)[0].view(np.uint32), want.view(np.uint32))
+    # out-of-interval / NaN actions fail the `@assert a in action_space(env)`
+    assert e.step(np.array([1.0000001], np.float32)) == 1 and e.step(np.array([np.nan], np.float32)) == 1
+
+
+def test_continuous_mountaincar_defaults_and_equivalence():
+    """ContinuousMountainCarEnv: goal_pos 0.45, power 0.0015 (MountainCarEnv.jl:73-74); with the discrete
+    params a force of a - 2 as Float32 reproduces the discrete env bit for bit."""
+    q = O.default_params(O.KIND_MOUNTAINCAR_CONT)
+    assert q[3] == float(np.float32(0.45)) and q[5] == float(np.float32(0.0015))
+    n = 50
+    seeds = O.splitmix_states_fast(n, 8)
+    d = O.OracleVecEnv(O.KIND_MOUNTAINCAR, n, seeds)
+    c = O.OracleVecEnv(O.KIND_MOUNTAINCAR_CONT, n, seeds, params=O.default_params(O.KIND_MOUNTAINCAR))
+    rng = np.random.default_rng(1)
+    for _ in range(450):
+        a = rng.integers(1, 4, n).astype(np.int32)
+        d.step(a, auto_reset=True); c.step((a - 2).astype(np.float32), auto_reset=True)
+        for f in (O.F_STATE, O.F_REWARD, O.F_FLAGS, O.F_T, O.F_RNG):
+            assert np.array_equal(d.get(f), c.get(f))
+    # default continuous params: full throttle right from the valley reaches the goal before the time limit
+    e = O.OracleVecEnv(O.KIND_MOUNTAINCAR_CONT, 1, O.splitmix_states_fast(1, 2))
+    x0 = e.get(O.F_STATE)[0]
+    assert -0.6 <= x0[0] < -0.4 and x0[1] == 0
+    e.step(np.array([1.0], np.float32))
+    v1 = np.float32(np.float32(0) + (np.float32(1.0) * np.float32(0.0015) + np.float32(np.cos(np.float64(np.float32(3.0) * x0[0]))) * -np.float32(0.0025)))
+    assert abs(float(e.get(O.F_STATE)[0][1]) - float(v1)) <= 1e-9 and e.get(O.F_REWARD)[0] == -1.0
+
+
+def test_max_timeout_wrapper_counts_like_the_reference_test():
+    """RLEnvs/test/environments/wrappers/wrappers.jl:36-52: with MaxTimeoutEnv(env, n) the loop
+    `while !is_terminated(env′); act!; n -= 1; @test n >= 0` ends after exactly n interactions."""
+    for kind, max_t in ((O.KIND_PENDULUM, 100), (O.KIND_MOUNTAINCAR, 37)):
+        e = _fresh(kind, 1)
+        e.set_max_timeout(max_t)
+        k = 0
+        act = np.float32(0.0) if kind == O.KIND_PENDULUM else 2
+        while not e.get(O.F_TERMINAL)[0]:
+            e.step([act]); k += 1
+            assert k <= max_t
+        assert k == max_t and e.get(O.F_T)[0] == max_t
+        if kind == O.KIND_MOUNTAINCAR:
+            assert e.get(O.F_REWARD)[0] == -1.0    # reward(env) forwards to the wrapped env, which is not done
+        e.reset(force=False)                       # reset!(env′): current_t = 1, not terminated
+        assert e.get(O.F_TERMINAL)[0] == 0 and e.get(O.F_T)[0] == 0
+    # wrapped CartPole: the inner termination still wins and pays 0
+    e = _fresh(O.KIND_CARTPOLE, 256); e.set_max_timeout(150)
+    for _ in range(150):
+        e.step_random(auto_reset=False)
+    assert e.get(O.F_TERMINAL).all()
