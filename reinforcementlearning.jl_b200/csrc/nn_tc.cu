@@ -310,7 +310,7 @@ constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples]
 // Back-to-back tcgen05.mma on ONE accumulator serialise at ~120 cycles each (measured, profiles/umma_probe4.py) although a
 // 128x64x8 tf32 MMA is only ~32 cycles of tensor work, so the three 3xTF32 passes go to three separate accumulators
 // (independent dependency chains, issued round-robin) and are summed in the epilogue.
-constexpr uint32_t COL_D12 = 0 /* 3 x 64: GEMM1, then GEMM2 */, COL_D3 = 192 /* 3 x 64 */, COL_AF = 384, COL_AL = 448;
+constexpr uint32_t COL_D12 = 0 /* 3 x 64: GEMM1, then GEMM2 */, COL_D3 = 192 /* 128 lanes x 128 */, COL_AF = 384, COL_AL = 448;
 
 struct SmemBwd {
     static_assert(FIMG % 128 == 0 && WIMG_BYTES % 128 == 0, "full/lo images must be adjacent to form one N = 128 operand");
@@ -746,19 +746,24 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 const uint64_t dB2f = umma::make_desc(umma::smem_u32(sm.B2_full), G_F, GW_S), dB2l = umma::make_desc(umma::smem_u32(sm.B2_lo), G_F, GW_S);
                 const uint64_t dFPf = umma::make_desc(umma::smem_u32(sm.FP_full), GF_T, GS_T), dFPl = umma::make_desc(umma::smem_u32(sm.FP_lo), GF_T, GS_T);
                 const uint64_t dFHf = umma::make_desc(umma::smem_u32(sm.FH_full), GF_T, GS_T), dFHl = umma::make_desc(umma::smem_u32(sm.FH_lo), GF_T, GS_T);
-                // GEMM2 (dH1, awaited now) interleaved with the first half of GEMM3 (dW2 += dP2^T x H1, K = 128 samples): six chains
+                // GEMM2 (dH1, awaited below) first: MMAs pace at ~130 cycles each whatever their dependencies, so anything
+                // issued ahead of its commit only delays P7.
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
+                    umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB2f + adv, idesc128, acc);
+                    umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB2f + adv, idesc, acc);
+                    acc = 1u;
+                }
+                umma::commit(&sm.bar2);
+                // GEMM3 (dW2 += dP2^T x H1, K = 128 samples), ONE M = 128 x N = 128 MMA per k-step: FP_full|FP_lo are adjacent
+                // row groups (A rows 0..63 = full, 64..127 = lo) and FH_full|FH_lo adjacent column groups, so
+                // D3[0:64][0:64] = full*full, D3[0:64][64:128] = full*lo, D3[64:128][0:64] = lo*full (and lo*lo, unused).
+                // It overlaps P7 and the next tile's gather / layer 1.
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    if (k == 8) umma::commit(&sm.bar2);
-                    if (k < 8) {
-                        const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                        umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB2f + adv, idesc128, acc);
-                        umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB2f + adv, idesc, acc);
-                        acc = 1u;
-                    }
                     const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
-                    umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc128, d3_acc);   // FH_full and FH_lo adjacent: N = 128
-                    umma::mma_tf32(tmem + COL_D3 + 128, dFPl + adt, dFHf + adt, idesc, d3_acc);
+                    umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc128, d3_acc);
                     d3_acc = 1u;
                 }
                 umma::commit(&sm.bar3);
@@ -812,21 +817,27 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     float* gb1 = out + (int64_t)H * d.in;
     float* gW2 = gb1 + H;
     float* gb2 = gW2 + (int64_t)H * H;
-    if (q < 2) {   // D3 rows j = TMEM lanes 0..63
+    float* red = reinterpret_cast<float*>(sm.FP_full);   // 4 * FIMG bytes contiguous, all MMAs are done
+    {   // D3 rows 0..63 (q < 2): [full*full | full*lo] of dW2 row j = s; rows 64..127 (q >= 2): lo*full of row j = s - 64
         float v[16], v2[16];
         if (gemm3_pending) {
             umma::tmem_ld16(tmem + lane_base + COL_D3 + 16 * c, v);
-            umma::tmem_ld16(tmem + lane_base + COL_D3 + 64 + 16 * c, v2);
+            if (q < 2) {
+                umma::tmem_ld16(tmem + lane_base + COL_D3 + 64 + 16 * c, v2);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] += v2[k];
-            umma::tmem_ld16(tmem + lane_base + COL_D3 + 128 + 16 * c, v2);
+                for (int k = 0; k < 16; ++k) v[k] += v2[k];
+            } else {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] += v2[k];
+                for (int k = 0; k < 16; ++k) red[(s - 64) * 65 + 16 * c + k] = v[k];
+            }
         }
+        worker_sync();
+        if (q < 2) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) gW2[s + H * (16 * c + k)] = gemm3_pending ? v[k] : 0.f;
+            for (int k = 0; k < 16; ++k) gW2[s + H * (16 * c + k)] = gemm3_pending ? v[k] + red[s * 65 + 16 * c + k] : 0.f;
+        }
+        worker_sync();
     }
-    float* red = reinterpret_cast<float*>(sm.FP_full);   // 4 * FIMG bytes contiguous, all MMAs are done
     // per-sample-slot partials -> [slot][64] in shared memory -> column sums in slot order
     for (int pass = 0; pass < 4; ++pass) {
         // pass 0: db2, 1: db1, 2: dW3[0], 3: dW3[1]
