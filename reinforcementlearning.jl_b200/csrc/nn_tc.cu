@@ -310,7 +310,9 @@ constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples]
 // Back-to-back tcgen05.mma on ONE accumulator serialise at ~120 cycles each (measured, profiles/umma_probe4.py) although a
 // 128x64x8 tf32 MMA is only ~32 cycles of tensor work, so the three 3xTF32 passes go to three separate accumulators
 // (independent dependency chains, issued round-robin) and are summed in the epilogue.
-constexpr uint32_t COL_D12 = 0 /* 3 x 64: GEMM1, then GEMM2 */, COL_D3 = 192 /* 128 lanes x 128 */, COL_AF = 384, COL_AL = 448;
+// TMEM columns: R1 = D1 of GEMM1 ([ff+lf | fl]), then (same lanes/columns, after P3 consumed it) the dP2 A operand (full | lo) of GEMM2;
+// D2 = GEMM2 accumulator; D3 = GEMM3 accumulator (all tiles); AH = H1 A operand (full | lo) of GEMM1.
+constexpr uint32_t COL_R1 = 0, COL_D2 = 128, COL_D3 = 256, COL_AH = 384;
 
 struct SmemBwd {
     static_assert(FIMG % 128 == 0 && WIMG_BYTES % 128 == 0, "full/lo images must be adjacent to form one N = 128 operand");
@@ -607,102 +609,110 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     };
     bool gemm3_pending = false;
     uint32_t d3_acc = 0u;   // meaningful on the issuing lane only
-    for (int64_t tile = cta; tile < ntiles; tile += nctas) {
-        // ---- P0: publish this tile's gathered samples (prefetched during the previous tile), prefetch the next ----
+    // ---- software pipeline (one tile = 128 samples; tensor core and CUDA cores work on different tiles / phases) ----
+    //   CUDA cores : ... P3(t) P45(t) | P0(t+1) P1(t+1) | P7(t) | P3(t+1) ...
+    //   tensor core:              G2(t) .......... G1(t+1) G3(t) ..........
+    // G1(t+1) is queued before the CUDA cores start P7(t), so its ~2k cycles hide behind P7; G3(t) hides behind
+    // P3/P45(t+1); only part of G2(t) (behind P0/P1(t+1)) is ever waited for.
+    auto publish = [&](int64_t t) {   // P0: this tile's gathered samples -> shared memory, prefetch the following tile
         if (tid < TM) {
-            if (!have_pf) gather_tile(tile, pf);
+            if (!have_pf) gather_tile(t, pf);
 #pragma unroll
             for (int i = 0; i < kInMax; ++i) sm.X[i * TM + tid] = pf[i];
             sm.Aux[tid] = pf[4]; sm.Aux[TM + tid] = pf[5]; sm.Aux[2 * TM + tid] = pf[6]; sm.Aux[3 * TM + tid] = pf[7];
-            if (tile + nctas < ntiles) { gather_tile(tile + nctas, pf); have_pf = true; } else have_pf = false;
+            if (t + nctas < ntiles) { gather_tile(t + nctas, pf); have_pf = true; } else have_pf = false;
         }
-        if (warp == 0 && gemm3_pending) umma::mbar_wait(&sm.bar3, ph3);   // previous tile's GEMM3 has consumed the F images
-        if (gemm3_pending) ph3 ^= 1u;
+    };
+    auto layer1 = [&](float (&xo)[kInMax]) {   // P1: H1 = act(W1 x + b1) -> TMEM A operand (full | lo); x stays in registers for P7
+#pragma unroll
+        for (int k = 0; k < kInMax; ++k) xo[k] = sm.X[k * TM + s];
+        float h1[16], lo[16];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            const int f0 = 16 * c + 4 * ch;
+            float4 bb = *reinterpret_cast<const float4*>(sm.b1 + f0);
+            float h[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int k = 0; k < kInMax; ++k) {
+                float4 w = *reinterpret_cast<const float4*>(sm.W1 + k * H + f0);
+                h[0] = fmaf(w.x, xo[k], h[0]); h[1] = fmaf(w.y, xo[k], h[1]); h[2] = fmaf(w.z, xo[k], h[2]); h[3] = fmaf(w.w, xo[k], h[3]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float hv = act_f(d.act, h[e]);
+                h1[4 * ch + e] = hv;
+                lo[4 * ch + e] = hv - hi_part(hv);
+            }
+        }
+        umma::tmem_st16(tmem + lane_base + COL_AH + 16 * c, h1);
+        umma::tmem_st16(tmem + lane_base + COL_AH + 64 + 16 * c, lo);
+        umma::tmem_st_wait();
+    };
+    const uint64_t dB1f = umma::make_desc(umma::smem_u32(sm.B1_full), G_F, GW_S);
+    const uint64_t dB2f = umma::make_desc(umma::smem_u32(sm.B2_full), G_F, GW_S);
+    const uint64_t dFPf = umma::make_desc(umma::smem_u32(sm.FP_full), GF_T, GS_T);
+    const uint64_t dFHf = umma::make_desc(umma::smem_u32(sm.FH_full), GF_T, GS_T);
+    // 3xTF32 product of a TMEM A operand (full at a_col, lo at a_col + 64) with a [B_full | B_lo] weight image:
+    // MMA 1 (N = 128): D[0:64) = full*full, D[64:128) = full*lo;  MMA 2 (N = 64): D[0:64) += lo*full
+    auto issue_ts3 = [&](uint32_t d_col, uint32_t a_col, uint64_t dB) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
+            umma::mma_tf32_ts(tmem + d_col, tmem + a_col + 8 * k, dB + adv, idesc128, k ? 1u : 0u);
+            umma::mma_tf32_ts(tmem + d_col, tmem + a_col + 64 + 8 * k, dB + adv, idesc, 1u);
+        }
+    };
+    // GEMM3 (dW2 += dP2^T x H1, K = 128 samples), ONE M = 128 x N = 128 MMA per k-step: FP_full|FP_lo are adjacent row
+    // groups (A rows 0..63 = full, 64..127 = lo) and FH_full|FH_lo adjacent column groups, so D3[0:64][0:64] = full*full,
+    // D3[0:64][64:128] = full*lo, D3[64:128][0:64] = lo*full (and lo*lo, unused).
+    auto issue_g3 = [&]() {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
+            umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc128, d3_acc);
+            d3_acc = 1u;
+        }
+    };
+    float x[kInMax];
+    if (cta < ntiles) {   // prologue: P0 / P1 / G1 of the first tile
+        publish(cta);
         worker_sync();
-        umma::fence_after_sync();
-        // ---- P1: layer 1 -> H1 (registers), TMEM A operand, H1^T image -----------------------------
-        float h1[16];
-        float x[kInMax];   // kept in registers: the next tile's gather may overwrite sm.X before this tile's P7 runs
-        {
-#pragma unroll
-            for (int k = 0; k < kInMax; ++k) x[k] = sm.X[k * TM + s];
-            float lo[16];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const int f0 = 16 * c + 4 * ch;
-                float4 bb = *reinterpret_cast<const float4*>(sm.b1 + f0);
-                float h[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                for (int k = 0; k < kInMax; ++k) {
-                    float4 w = *reinterpret_cast<const float4*>(sm.W1 + k * H + f0);
-                    h[0] = fmaf(w.x, x[k], h[0]); h[1] = fmaf(w.y, x[k], h[1]); h[2] = fmaf(w.z, x[k], h[2]); h[3] = fmaf(w.w, x[k], h[3]);
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float hv = act_f(d.act, h[e]);
-                    h1[4 * ch + e] = hv;
-                    lo[4 * ch + e] = hv - hi_part(hv);
-                }
-            }
-            umma::tmem_st16(tmem + lane_base + COL_AF + 16 * c, h1);
-            umma::tmem_st16(tmem + lane_base + COL_AL + 16 * c, lo);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t off = fimg_off(16 * c + k, s);
-                *reinterpret_cast<float*>(sm.FH_full + off) = h1[k];
-                *reinterpret_cast<float*>(sm.FH_lo + off) = lo[k];
-            }
-            umma::tmem_st_wait();
-        }
-        umma::fence_proxy_async();
+        layer1(x);
         umma::fence_before_sync();
         worker_sync();
-        if (warp == 0) {
-            if (lane == 0) {
-                umma::fence_after_sync();
-                uint32_t acc = 0u;
-                const uint64_t dB1f = umma::make_desc(umma::smem_u32(sm.B1_full), G_F, GW_S), dB1l = umma::make_desc(umma::smem_u32(sm.B1_lo), G_F, GW_S);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {   // three independent accumulator chains, round-robin
-                    const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                    umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB1f + adv, idesc128, acc);        // [full*full | full*lo]: B_full and B_lo are adjacent = one N = 128 operand
-                    umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB1f + adv, idesc, acc);
-                    acc = 1u;
-                }
-                umma::commit(&sm.bar1);
-            }
-            __syncwarp();
-            umma::mbar_wait(&sm.bar1, ph1);
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_ts3(COL_R1, COL_AH, dB1f);
+            umma::commit(&sm.bar1);
         }
-        ph1 ^= 1u;
-        worker_sync();
-        umma::fence_after_sync();
+        __syncwarp();
+    }
+    for (int64_t tile = cta; tile < ntiles; tile += nctas) {
+        const bool has_next = tile + nctas < ntiles;
         // ---- P3: H2 = act(D1 + b2) (registers) + head partials ---------------------------------------
+        umma::mbar_wait(&sm.bar1, ph1);
+        ph1 ^= 1u;
+        umma::fence_after_sync();
         float h2[16];
         {
             float v[16], v2[16];
-            umma::tmem_ld16(tmem + lane_base + COL_D12 + 16 * c, v);
-            umma::tmem_ld16(tmem + lane_base + COL_D12 + 64 + 16 * c, v2);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] += v2[k];
-            umma::tmem_ld16(tmem + lane_base + COL_D12 + 128 + 16 * c, v2);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] += v2[k];
+            umma::tmem_ld16(tmem + lane_base + COL_R1 + 16 * c, v);
+            umma::tmem_ld16(tmem + lane_base + COL_R1 + 64 + 16 * c, v2);
             float zp[kOutMax] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int f = 16 * c + k;
-                h2[k] = act_f(d.act, v[k] + sm.b2[f]);
+                h2[k] = act_f(d.act, (v[k] + v2[k]) + sm.b2[f]);
                 float4 w = *reinterpret_cast<const float4*>(sm.W3 + f * kOutMax);
                 zp[0] = fmaf(w.x, h2[k], zp[0]); zp[1] = fmaf(w.y, h2[k], zp[1]); zp[2] = fmaf(w.z, h2[k], zp[2]); zp[3] = fmaf(w.w, h2[k], zp[3]);
             }
 #pragma unroll
             for (int o = 0; o < kOutMax; ++o) sm.Zp[(c * kOutMax + o) * TM + s] = zp[o];
         }
-        umma::fence_before_sync();
         worker_sync();
         // ---- P4+P5: loss (evaluated by all four feature-block threads of a sample: no exchange, no idle warps),
-        //            dW3 / db2 partials, dP2 = (W3^T dz) .* act'(H2) -> TMEM A operand + dP2^T image -------------
+        //            dW3 / db2 partials, dP2 = (W3^T dz) .* act'(H2) -> TMEM A operand (over D1, which this thread
+        //            has just consumed) + dP2^T / H1^T images for GEMM3 ----------------------------------------------
         {
             float z[kOutMax];
 #pragma unroll
@@ -726,71 +736,74 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 g3[0][k] = fmaf(dz[0], h2[k], g3[0][k]);
                 g3[1][k] = fmaf(dz[1], h2[k], g3[1][k]);
             }
-            umma::tmem_st16(tmem + lane_base + COL_AF + 16 * c, dp);   // GEMM1 (the previous reader of AF/AL) has completed
-            umma::tmem_st16(tmem + lane_base + COL_AL + 16 * c, lo);
+            umma::tmem_st16(tmem + lane_base + COL_R1 + 16 * c, dp);
+            umma::tmem_st16(tmem + lane_base + COL_R1 + 64 + 16 * c, lo);
+            if (gemm3_pending) {   // the previous tile's GEMM3 must have consumed the images before they are overwritten
+                umma::mbar_wait(&sm.bar3, ph3);
+                ph3 ^= 1u;
+                umma::fence_after_sync();
+            }
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const uint32_t off = fimg_off(16 * c + k, s);
                 *reinterpret_cast<float*>(sm.FP_full + off) = dp[k];
                 *reinterpret_cast<float*>(sm.FP_lo + off) = lo[k];
             }
+            // H1 of this tile (full | lo) back from its TMEM operand -> H1^T image
+            umma::tmem_ld16(tmem + lane_base + COL_AH + 16 * c, dp);
+            umma::tmem_ld16(tmem + lane_base + COL_AH + 64 + 16 * c, lo);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t off = fimg_off(16 * c + k, s);
+                *reinterpret_cast<float*>(sm.FH_full + off) = dp[k];
+                *reinterpret_cast<float*>(sm.FH_lo + off) = lo[k];
+            }
             umma::tmem_st_wait();
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
         worker_sync();
-        if (warp == 0) {
-            if (lane == 0) {
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_ts3(COL_D2, COL_R1, dB2f);     // GEMM2: dH1 = dP2 x W2
+            umma::commit(&sm.bar2);
+            if (!has_next) { issue_g3(); umma::commit(&sm.bar3); }
+        }
+        __syncwarp();
+        float xn[kInMax];
+        if (has_next) {
+            publish(tile + nctas);
+            worker_sync();
+            layer1(xn);
+            umma::fence_before_sync();
+            worker_sync();
+            if (tid == 0) {
                 umma::fence_after_sync();
-                uint32_t acc = 0u;
-                const uint64_t dB2f = umma::make_desc(umma::smem_u32(sm.B2_full), G_F, GW_S), dB2l = umma::make_desc(umma::smem_u32(sm.B2_lo), G_F, GW_S);
-                const uint64_t dFPf = umma::make_desc(umma::smem_u32(sm.FP_full), GF_T, GS_T), dFPl = umma::make_desc(umma::smem_u32(sm.FP_lo), GF_T, GS_T);
-                const uint64_t dFHf = umma::make_desc(umma::smem_u32(sm.FH_full), GF_T, GS_T), dFHl = umma::make_desc(umma::smem_u32(sm.FH_lo), GF_T, GS_T);
-                // GEMM2 (dH1, awaited below) first: MMAs pace at ~130 cycles each whatever their dependencies, so anything
-                // issued ahead of its commit only delays P7.
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                    umma::mma_tf32_ts(tmem + COL_D12, tmem + COL_AF + 8 * k, dB2f + adv, idesc128, acc);
-                    umma::mma_tf32_ts(tmem + COL_D12 + 128, tmem + COL_AL + 8 * k, dB2f + adv, idesc, acc);
-                    acc = 1u;
-                }
-                umma::commit(&sm.bar2);
-                // GEMM3 (dW2 += dP2^T x H1, K = 128 samples), ONE M = 128 x N = 128 MMA per k-step: FP_full|FP_lo are adjacent
-                // row groups (A rows 0..63 = full, 64..127 = lo) and FH_full|FH_lo adjacent column groups, so
-                // D3[0:64][0:64] = full*full, D3[0:64][64:128] = full*lo, D3[64:128][0:64] = lo*full (and lo*lo, unused).
-                // It overlaps P7 and the next tile's gather / layer 1.
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
-                    umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc128, d3_acc);
-                    d3_acc = 1u;
-                }
+                issue_ts3(COL_R1, COL_AH, dB1f);   // GEMM1 of the next tile (in order behind GEMM2, which reads R1)
+                umma::commit(&sm.bar1);
+                issue_g3();
                 umma::commit(&sm.bar3);
             }
             __syncwarp();
-            umma::mbar_wait(&sm.bar2, ph2);
         }
         gemm3_pending = true;
+        // ---- P7: dP1 = D2 .* act'(H1); dW1 / db1 partials ------------------------------------------------
+        umma::mbar_wait(&sm.bar2, ph2);
         ph2 ^= 1u;
-        worker_sync();
         umma::fence_after_sync();
-        // ---- P7: dP1 = D2 .* act'(H1); dW1 / db1 partials (no shared memory) ----------------------------
         {
             float v[16];
             {
                 float v2[16];
-                umma::tmem_ld16(tmem + lane_base + COL_D12 + 16 * c, v);
-                umma::tmem_ld16(tmem + lane_base + COL_D12 + 64 + 16 * c, v2);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] += v2[k];
-                umma::tmem_ld16(tmem + lane_base + COL_D12 + 128 + 16 * c, v2);
+                umma::tmem_ld16(tmem + lane_base + COL_D2 + 16 * c, v);
+                umma::tmem_ld16(tmem + lane_base + COL_D2 + 64 + 16 * c, v2);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) v[k] += v2[k];
             }
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                v[k] = v[k] * dact_f(d.act, h1[k]);
+                const float h1k = *reinterpret_cast<const float*>(sm.FH_full + fimg_off(16 * c + k, s));   // this tile's H1 (image still intact)
+                v[k] = v[k] * dact_f(d.act, h1k);
                 db1acc[k] += v[k];
             }
             // dW1[f][i] = sum_s dP1[s][f] x[s][i]: transpose-reduce over the warp's 32 samples, 8 features (32 values) at a time
@@ -807,11 +820,15 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             w1p1 += lane_transpose_reduce32(t, lane);
         }
         umma::fence_before_sync();
+        if (has_next) {
+#pragma unroll
+            for (int k = 0; k < kInMax; ++k) x[k] = xn[k];
+        }
     }
     // ---- drain: last GEMM3, then write this CTA's gradient partial (fixed-order reductions) ---------------
-    if (warp == 0 && gemm3_pending) umma::mbar_wait(&sm.bar3, ph3);
-    worker_sync();
+    if (gemm3_pending) umma::mbar_wait(&sm.bar3, ph3);
     umma::fence_after_sync();
+    worker_sync();
     float* out = partial + (int64_t)cta * np_total + poff;
     float* gW1 = out;
     float* gb1 = out + (int64_t)H * d.in;
