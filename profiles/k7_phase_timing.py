@@ -1,0 +1,62 @@
+"""Per-phase cycle breakdown of the tensor-core K7 kernel (ac_loss_grad_tc_kernel) as seen by CTA 0 / thread 0.
+
+Build step (here, no GPU):   python profiles/k7_phase_timing.py --build
+Run step (on the GPU box):   python profiles/k7_phase_timing.py
+The debug library is the normal one with nn_tc.cu recompiled with -DB200RL_K7_TIMING (clock64 marks); it is
+not the product library and is never loaded by the package unless this script swaps it in."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "reinforcementlearning.jl_b200")
+DBG = os.path.join(PKG, "build", "libb200rl_dbg.so")
+NAMES = ["wait G1 (bar1)", "P3 (D1 -> H2, head partials)", "sync a", "P45 loss + dP2 (compute, tmem_st)", "wait G3 prev (bar3)",
+         "P45 image stores (FP, FH)", "sync b", "issue G2", "P0 publish + prefetch", "sync c", "P1 layer 1 + tmem_st", "sync d",
+         "issue G1(next) + G3", "wait G2 (bar2)", "P7 (D2 -> dP1, dW1)", "(tile count)", "  P0a: publish stores (waits for the prefetch)", "  P0b: perm_index", ]
+
+
+def build():
+    sys.path.insert(0, PKG)
+    import build as B
+    B.build()
+    objs = [os.path.join(B.BUILD, s.replace(".cu", ".o")) for s, _ in B.SOURCES + B.OPTIONAL if s != "nn_tc.cu"]
+    dbg_o = os.path.join(B.BUILD, "nn_tc_dbg.o")
+    nvcc = B._nvcc()
+    subprocess.check_call([nvcc, "-ccbin", "/usr/bin/g++"] + B.ARCH + B.COMMON + ["-DB200RL_K7_TIMING", "-c", os.path.join(B.CSRC, "nn_tc.cu"), "-o", dbg_o])
+    subprocess.check_call([nvcc, "-ccbin", "/usr/bin/g++"] + B.ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", DBG] + objs + [dbg_o, "-ldl"])
+    print(DBG)
+
+
+def run():
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import __graft_entry__ as g
+    b = g.load_package()
+    b._lib._LIB = None                  # swap in the instrumented library before anything is loaded
+    b._lib.SO_PATH = DBG
+    lib = b._lib.load()
+    assert hasattr(lib, "b200rl_debug_k7_phases"), "debug library not loaded"
+    ctx = b.Context(0)
+    n = 65536
+    env = b.B200VecEnv(ctx, "CartPole", n, b.sharding.splitmix_states(1, 0, n), auto_reset=True)
+    net = b.Network(ctx, 4, 64, 2, b.sharding.glorot_actor_critic(123, 4, 64, 2))
+    agent = b.OnPolicyAgent(ctx, net, env, b.onpolicy_config(update_freq=32), b.sharding.splitmix_states(2, 0, n))
+    b.run(agent, env, b.StopAfterNSteps(64), b.DeviceEpisodeStats())     # two full PPO iterations (warm-up)
+    out = (C.c_ulonglong * 24)()
+    lib.b200rl_debug_k7_phases.argtypes = [C.c_void_p, C.c_int]
+    lib.b200rl_debug_k7_phases(out, 1)
+    b.run(agent, env, b.StopAfterNSteps(32), b.DeviceEpisodeStats())     # 16 minibatch launches
+    lib.b200rl_debug_k7_phases(out, 0)
+    v = list(out)
+    tiles = max(1, v[15])
+    tot = sum(v[:15])
+    print(f"tiles seen by CTA 0: {tiles}; cycles per tile: {tot / tiles:.0f}")
+    for k in list(range(15)) + [16, 17]:
+        print(f"  {NAMES[k]:48s} {v[k] / tiles:8.0f} cyc/tile  {100.0 * v[k] / tot:5.1f}%")
+    print("  (P0 row = loads issued after perm_index; P0a/P0b are its first two parts)")
+
+
+if __name__ == "__main__":
+    build() if "--build" in sys.argv else run()

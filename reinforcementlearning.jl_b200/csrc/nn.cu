@@ -14,6 +14,7 @@
 // distributions.jl:9-34), clip_by_global_norm! (basic.jl:19-29), TargetNetwork sync
 // (policies/learners/target_network.jl:70-88).
 #include "nn.cuh"
+#include "perm.cuh"
 
 namespace {
 
@@ -54,24 +55,9 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
     return h;
 }
-// keyed 4-round Feistel bijection on [0, n) with cycle walking (minibatch permutation)
-__device__ __forceinline__ uint32_t perm_index(uint32_t q, uint32_t n, uint32_t key) {
-    int bits = 2;
-    while ((1ull << bits) < n) bits += 2;
-    int hb = bits / 2;
-    uint32_t mask = (1u << hb) - 1;
-    uint32_t x = q;
-    do {
-        uint32_t l = x >> hb, r = x & mask;
-#pragma unroll
-        for (uint32_t round = 0; round < 4; ++round) {
-            uint32_t t = l ^ (mix32(r + key + round * 0x9E3779B9u) & mask);
-            l = r; r = t;
-        }
-        x = (l << hb) | r;
-    } while (x >= n);
-    return x;
-}
+// minibatch permutation: perm.cuh
+using b200perm::perm_index;
+using b200perm::perm_index_bits;
 
 // head parameter addressing inside the flat parameter vector
 __device__ __forceinline__ int64_t head_base(const MlpDesc& d) { return (int64_t)d.H * d.in + d.H + (int64_t)d.H * d.H + d.H; }

@@ -9,6 +9,7 @@
 // (the hardware ignores those bits, so the FULL fp32 image doubles as the hi operand) — measured
 // 5e-7 relative (profiles/umma_probe.py).  Layer 1 (K <= 4) and the heads (N <= 4) stay on FFMA.
 #include "nn.cuh"
+#include "perm.cuh"
 #include "umma.cuh"
 
 namespace {
@@ -347,23 +348,8 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
     return h;
 }
-__device__ __forceinline__ uint32_t perm_index(uint32_t q, uint32_t n, uint32_t key) {
-    int bits = 2;
-    while ((1ull << bits) < n) bits += 2;
-    int hb = bits / 2;
-    uint32_t mask = (1u << hb) - 1;
-    uint32_t x = q;
-    do {
-        uint32_t l = x >> hb, r = x & mask;
-#pragma unroll
-        for (uint32_t round = 0; round < 4; ++round) {
-            uint32_t t = l ^ (mix32(r + key + round * 0x9E3779B9u) & mask);
-            l = r; r = t;
-        }
-        x = (l << hb) | r;
-    } while (x >= n);
-    return x;
-}
+using b200perm::perm_index;
+using b200perm::perm_index_bits;
 __device__ __forceinline__ float block_sum512(float v, float* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -520,6 +506,12 @@ __device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, c
     return r;
 }
 
+#ifdef B200RL_K7_TIMING   // debug build only (profiles/k7_phase_timing.py): per-phase cycle sums seen by CTA 0 / thread 0
+__device__ unsigned long long g_k7_phase[24];
+#define K7_T(i) do { if (tid == 0 && blockIdx.x == 0) { long long now_ = clock64(); g_k7_phase[i] += (unsigned long long)(now_ - tprev_); tprev_ = now_; } } while (0)
+#else
+#define K7_T(i) do { } while (0)
+#endif
 constexpr int NT7_ALL = NT7;        // 16 warps; warp 0 lane 0 also feeds the tensor core (descriptors prebuilt: ~2 instructions per MMA)
 
 __global__ void __launch_bounds__(NT7_ALL, 1)
@@ -582,29 +574,38 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     float mean = 0.f, inv_std = 1.f;
     if (hp.normalize_adv && b.norm2) { mean = b.norm2[0]; inv_std = b.norm2[1]; }
     uint32_t ph1 = 0, ph2 = 0, ph3 = 0;
-    // random gather of one sample (x[0..3], action bits, logp_old, normalised advantage, return) into registers;
-    // issued one tile ahead so the L2 / HBM latency hides behind the previous tile's GEMMs
-    float pf[8];
+    // random gather of one tile into registers, spread over all 512 threads: thread (sample s, block c) loads part c of
+    // sample s — c = 0: the state (up to 4 floats), 1: action bits, 2: logp_old (actor) / return (critic), 3: advantage —
+    // so nobody has more than one dependent load chain.  Issued one tile ahead: the L2 / HBM latency hides behind the
+    // previous tile.  No arithmetic on the loaded values here (that would stall on them).
+#ifdef B200RL_K7_TIMING
+    long long tprev_ = 0;
+#endif
+    float pf[kInMax];
     bool have_pf = false;
-    auto gather_tile = [&](int64_t t, float (&o)[8]) {
-        int64_t j = t * TM + tid;
-        bool valid = j < b.B;
+    const int pbits = b200perm::perm_bits(b.perm_n);
+    auto gather_tile = [&](int64_t t, float (&o)[kInMax]) {
+        int64_t j = t * TM + s;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = 0.f;
-        if (!valid) return;
-        int64_t gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index((uint32_t)(b.perm_offset + j), b.perm_n, b.perm_key);
-        if (b.ns == 4) {
-            float4 v4 = reinterpret_cast<const float4*>(b.states)[gidx];
-            o[0] = v4.x; o[1] = v4.y; o[2] = v4.z; o[3] = v4.w;
-        } else {
-            for (int i = 0; i < b.ns; ++i) o[i] = b.states[(int64_t)b.ns * gidx + i];
-        }
-        if (role == 0) {
-            o[4] = reinterpret_cast<const float*>(b.actions)[gidx];
-            o[5] = b.logp_old ? b.logp_old[gidx] : 0.f;
-            o[6] = hp.normalize_adv ? (b.adv[gidx] - mean) * inv_std : b.adv[gidx];
-        } else {
-            o[7] = b.ret[gidx];
+        for (int k = 0; k < kInMax; ++k) o[k] = 0.f;
+        if (j >= b.B) return;
+        int64_t gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index_bits((uint32_t)(b.perm_offset + j), b.perm_n, b.perm_key, pbits);
+        K7_T(17);
+        if (c == 0) {
+            if (b.ns == 4) {
+                float4 v4 = reinterpret_cast<const float4*>(b.states)[gidx];
+                o[0] = v4.x; o[1] = v4.y; o[2] = v4.z; o[3] = v4.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < kInMax; ++i)    // static indices only: a runtime-indexed o[] would live in local memory
+                    if (i < b.ns) o[i] = b.states[(int64_t)b.ns * gidx + i];   // and every prefetch would stall on its spill store
+            }
+        } else if (role == 0) {
+            if (c == 1) o[0] = reinterpret_cast<const float*>(b.actions)[gidx];
+            else if (c == 2) o[0] = b.logp_old ? b.logp_old[gidx] : 0.f;
+            else o[0] = b.adv[gidx];
+        } else if (c == 2) {
+            o[0] = b.ret[gidx];
         }
     };
     bool gemm3_pending = false;
@@ -615,13 +616,20 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     // G1(t+1) is queued before the CUDA cores start P7(t), so its ~2k cycles hide behind P7; G3(t) hides behind
     // P3/P45(t+1); only part of G2(t) (behind P0/P1(t+1)) is ever waited for.
     auto publish = [&](int64_t t) {   // P0: this tile's gathered samples -> shared memory, prefetch the following tile
-        if (tid < TM) {
-            if (!have_pf) gather_tile(t, pf);
+        if (!have_pf) gather_tile(t, pf);
+        if (c == 0) {
 #pragma unroll
-            for (int i = 0; i < kInMax; ++i) sm.X[i * TM + tid] = pf[i];
-            sm.Aux[tid] = pf[4]; sm.Aux[TM + tid] = pf[5]; sm.Aux[2 * TM + tid] = pf[6]; sm.Aux[3 * TM + tid] = pf[7];
-            if (t + nctas < ntiles) { gather_tile(t + nctas, pf); have_pf = true; } else have_pf = false;
+            for (int i = 0; i < kInMax; ++i) sm.X[i * TM + s] = pf[i];
+        } else if (c == 1) {
+            sm.Aux[s] = pf[0];
+        } else if (c == 2) {
+            sm.Aux[(role == 0 ? TM : 3 * TM) + s] = pf[0];     // logp_old | return
+            if (role == 0) sm.Aux[3 * TM + s] = 0.f; else sm.Aux[TM + s] = 0.f;
+        } else {
+            sm.Aux[2 * TM + s] = (role == 0 && hp.normalize_adv) ? (pf[0] - mean) * inv_std : pf[0];
         }
+        K7_T(16);
+        if (t + nctas < ntiles) { gather_tile(t + nctas, pf); have_pf = true; } else have_pf = false;
     };
     auto layer1 = [&](float (&xo)[kInMax]) {   // P1: H1 = act(W1 x + b1) -> TMEM A operand (full | lo); x stays in registers for P7
 #pragma unroll
@@ -673,6 +681,11 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             d3_acc = 1u;
         }
     };
+    // Issuing a tcgen05.mma costs the issuing thread ~60 cycles (more once the queue is full), so the three GEMMs are fed by
+    // lane 0 of three different warps: no single warp falls ~3k cycles behind the others at the next barrier.  Cross-thread
+    // order (GEMM2(t) reads R1 before GEMM1(t+1) overwrites it) comes from tcgen05 fences around the CTA barriers between them.
+    constexpr int kIssueG2 = 0, kIssueG1 = 5 * 32, kIssueG3 = 10 * 32;
+    bool g3_ready = false;   // FP / FH images of the previous tile are complete and its GEMM3 has not been issued yet
     float x[kInMax];
     if (cta < ntiles) {   // prologue: P0 / P1 / G1 of the first tile
         publish(cta);
@@ -680,19 +693,29 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         layer1(x);
         umma::fence_before_sync();
         worker_sync();
-        if (tid == 0) {
+        if (tid == kIssueG1) {
             umma::fence_after_sync();
             issue_ts3(COL_R1, COL_AH, dB1f);
             umma::commit(&sm.bar1);
         }
         __syncwarp();
     }
+#ifdef B200RL_K7_TIMING
+    tprev_ = clock64();
+#endif
     for (int64_t tile = cta; tile < ntiles; tile += nctas) {
         const bool has_next = tile + nctas < ntiles;
         // ---- P3: H2 = act(D1 + b2) (registers) + head partials ---------------------------------------
         umma::mbar_wait(&sm.bar1, ph1);
         ph1 ^= 1u;
         umma::fence_after_sync();
+        K7_T(0);
+        if (g3_ready) {   // GEMM3 of the previous tile: the tensor core is idle from here until this tile's GEMM2
+            if (tid == kIssueG3) { issue_g3(); umma::commit(&sm.bar3); }
+            __syncwarp();
+            g3_ready = false;
+            gemm3_pending = true;
+        }
         float h2[16];
         {
             float v[16], v2[16];
@@ -709,7 +732,9 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
 #pragma unroll
             for (int o = 0; o < kOutMax; ++o) sm.Zp[(c * kOutMax + o) * TM + s] = zp[o];
         }
+        K7_T(1);
         worker_sync();
+        K7_T(2);
         // ---- P4+P5: loss (evaluated by all four feature-block threads of a sample: no exchange, no idle warps),
         //            dW3 / db2 partials, dP2 = (W3^T dz) .* act'(H2) -> TMEM A operand (over D1, which this thread
         //            has just consumed) + dP2^T / H1^T images for GEMM3 ----------------------------------------------
@@ -738,11 +763,14 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             }
             umma::tmem_st16(tmem + lane_base + COL_R1 + 16 * c, dp);
             umma::tmem_st16(tmem + lane_base + COL_R1 + 64 + 16 * c, lo);
+            K7_T(3);
             if (gemm3_pending) {   // the previous tile's GEMM3 must have consumed the images before they are overwritten
                 umma::mbar_wait(&sm.bar3, ph3);
                 ph3 ^= 1u;
                 umma::fence_after_sync();
+                gemm3_pending = false;
             }
+            K7_T(4);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const uint32_t off = fimg_off(16 * c + k, s);
@@ -760,37 +788,49 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             }
             umma::tmem_st_wait();
         }
+        K7_T(5);
         umma::fence_proxy_async();
         umma::fence_before_sync();
         worker_sync();
-        if (tid == 0) {
+        K7_T(6);
+        if (tid == kIssueG2) {
             umma::fence_after_sync();
             issue_ts3(COL_D2, COL_R1, dB2f);     // GEMM2: dH1 = dP2 x W2
             umma::commit(&sm.bar2);
-            if (!has_next) { issue_g3(); umma::commit(&sm.bar3); }
+        }
+        if (!has_next && tid == kIssueG3) {
+            umma::fence_after_sync();
+            issue_g3();
+            umma::commit(&sm.bar3);
         }
         __syncwarp();
+        if (has_next) g3_ready = true; else gemm3_pending = true;
+        K7_T(7);
         float xn[kInMax];
         if (has_next) {
             publish(tile + nctas);
+            K7_T(8);
+            umma::fence_before_sync();   // orders this thread's GEMM2 issue before GEMM1(next), issued by another thread after two barriers
             worker_sync();
+            K7_T(9);
             layer1(xn);
             umma::fence_before_sync();
+            K7_T(10);
             worker_sync();
-            if (tid == 0) {
+            K7_T(11);
+            if (tid == kIssueG1) {
                 umma::fence_after_sync();
-                issue_ts3(COL_R1, COL_AH, dB1f);   // GEMM1 of the next tile (in order behind GEMM2, which reads R1)
+                issue_ts3(COL_R1, COL_AH, dB1f);   // GEMM1 of the next tile (ordered behind GEMM2, which reads R1)
                 umma::commit(&sm.bar1);
-                issue_g3();
-                umma::commit(&sm.bar3);
             }
             __syncwarp();
         }
-        gemm3_pending = true;
+        K7_T(12);
         // ---- P7: dP1 = D2 .* act'(H1); dW1 / db1 partials ------------------------------------------------
         umma::mbar_wait(&sm.bar2, ph2);
         ph2 ^= 1u;
         umma::fence_after_sync();
+        K7_T(13);
         {
             float v[16];
             {
@@ -819,6 +859,10 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 for (int i = 0; i < kInMax; ++i) t[4 * k + i] = v[8 + k] * x[i];
             w1p1 += lane_transpose_reduce32(t, lane);
         }
+        K7_T(14);
+#ifdef B200RL_K7_TIMING
+        if (tid == 0 && blockIdx.x == 0) g_k7_phase[15] += 1;
+#endif
         umma::fence_before_sync();
         if (has_next) {
 #pragma unroll
@@ -826,6 +870,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         }
     }
     // ---- drain: last GEMM3, then write this CTA's gradient partial (fixed-order reductions) ---------------
+    const bool d3_valid = cta < ntiles;   // at least one tile went through GEMM3
     if (gemm3_pending) umma::mbar_wait(&sm.bar3, ph3);
     umma::fence_after_sync();
     worker_sync();
@@ -837,7 +882,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     float* red = reinterpret_cast<float*>(sm.FP_full);   // 4 * FIMG bytes contiguous, all MMAs are done
     {   // D3 rows 0..63 (q < 2): [full*full | full*lo] of dW2 row j = s; rows 64..127 (q >= 2): lo*full of row j = s - 64
         float v[16], v2[16];
-        if (gemm3_pending) {
+        if (d3_valid) {
             umma::tmem_ld16(tmem + lane_base + COL_D3 + 16 * c, v);
             if (q < 2) {
                 umma::tmem_ld16(tmem + lane_base + COL_D3 + 64 + 16 * c, v2);
@@ -851,7 +896,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         worker_sync();
         if (q < 2) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) gW2[s + H * (16 * c + k)] = gemm3_pending ? v[k] + red[s * 65 + 16 * c + k] : 0.f;
+            for (int k = 0; k < 16; ++k) gW2[s + H * (16 * c + k)] = d3_valid ? v[k] + red[s * 65 + 16 * c + k] : 0.f;
         }
         worker_sync();
     }
@@ -935,3 +980,12 @@ int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const Ml
     LAUNCH_CHECK(ctx);
     return B200RL_OK;
 }
+
+#ifdef B200RL_K7_TIMING
+extern "C" int b200rl_debug_k7_phases(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, g_k7_phase, sizeof(unsigned long long) * 24) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(g_k7_phase, z, sizeof z); }
+    return 0;
+}
+#endif

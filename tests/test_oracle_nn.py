@@ -174,7 +174,7 @@ def test_gumbel_max_sampling_distribution_and_logp():
 
 
 def test_perm_index_is_a_bijection():
-    for n in (1, 2, 7, 64, 1000, 4096):
+    for n in (1, 2, 3, 7, 64, 1000, 4096, 5000, 8192):   # even and odd bit counts, with and without cycle walking
         for key in (0, 12345):
             assert sorted(O.perm_index(q, n, key) for q in range(n)) == list(range(n))
     a = [O.perm_index(q, 4096, 1) for q in range(4096)]
