@@ -178,6 +178,7 @@ def run_own(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = pkg.Context(local_rank)
+    peer_exchange = False
     if world > 1:
         import ctypes as C
         import torch
@@ -189,6 +190,16 @@ def run_own(args):
         dist.broadcast(idbuf, 0)
         raw = bytes(idbuf.cpu().numpy().tobytes())
         pkg._lib.check(ctx.lib.b200rl_comm_init(ctx.h, world, rank, raw))
+
+        def all_gather_bytes(b):
+            t = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+            out = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(out, t)
+            return [bytes(o.cpu().numpy().tobytes()) for o in out]
+        peer_exchange = False
+        if os.environ.get("B200RL_P2P", "1") != "0":
+            from b200rl import sharding as _sh
+            peer_exchange = _sh.attach_peer_exchange(ctx, rank, world, all_gather_bytes)
 
     def barrier():
         ctx.sync()
@@ -321,6 +332,7 @@ def run_own(args):
             "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: 65536 batched CartPoleEnv{Float32} + PPO (2x64 MLP actor-critic, fp32), T=32, 4 epochs x 4 minibatches, advantage normalisation",
                        "n_envs": n_total, "envs_per_gpu": n, "global_batch": n_total * T // N_MICRO, "parallelism": f"dp{world}",
+                       "grad_allreduce": ("fused NVLink peer exchange inside the reduce+clip+Adam kernel" if peer_exchange else "NCCL") if world > 1 else "none",
                        "l2": "flushed (256 MB write) between timed steps, outside the timed region",
                        "episodes_finished_rank0": stats["episodes"]},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -298,7 +298,15 @@ int b200rl_selftest_umma(b200rl_ctx* ctx, const void* a_img_host, uint32_t a_byt
 /* env-index data parallelism: one process per GPU, one sum all-reduce of the flat gradient per
  * optimiser step over NCCL / NVLink.  rank 0 makes the 128-byte id. */
 int b200rl_comm_unique_id(void* id128_out);
-int b200rl_comm_init(b200rl_ctx* ctx, int nranks, int rank, const void* id128);
+int b200rl_comm_init(b200rl_ctx* ctx, int nranks, int rank, const void* id128);   /* id128 NULL: no NCCL, peer exchange only */
+/* Fused all-reduce over NVLink / NVSwitch peer memory (ranks of one node).  Each rank exports a small exchange region
+ * (export), maps every other rank's (open: 64-byte CUDA IPC handle of another process; or the raw pointer when the peer
+ * lives in the same process) and attaches the table.  After attach the optimiser step of a sharded run is ONE kernel:
+ * reduce the per-CTA gradient partials -> publish to the own region -> read every peer's region -> sum in rank order
+ * (bit-identical on all ranks) -> global-norm clip -> Adam; NCCL is then only used for buffers larger than the region. */
+int b200rl_comm_p2p_export(b200rl_ctx* ctx, void* handle64_out, void** region_out);
+int b200rl_comm_p2p_open(b200rl_ctx* ctx, const void* handle64, void** region_out);
+int b200rl_comm_p2p_attach(b200rl_ctx* ctx, void* const* regions);
 int b200rl_comm_allreduce_f32(b200rl_ctx* ctx, float* dev_buf, int64_t n);
 
 #ifdef __cplusplus

@@ -135,6 +135,9 @@ SIGNATURES = {
     "b200rl_comm_unique_id": (_i32, [_vp]),
     "b200rl_comm_init": (_i32, [_vp, _i32, _i32, _vp]),
     "b200rl_comm_allreduce_f32": (_i32, [_vp, _vp, _i64]),
+    "b200rl_comm_p2p_export": (_i32, [_vp, _vp, _pp]),
+    "b200rl_comm_p2p_open": (_i32, [_vp, _vp, _pp]),
+    "b200rl_comm_p2p_attach": (_i32, [_vp, _vp]),
 }
 
 _LIB = None

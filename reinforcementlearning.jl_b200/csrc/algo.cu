@@ -34,6 +34,10 @@ __global__ void clamp_copy_kernel(float* __restrict__ dst, const float* __restri
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = fminf(fmaxf(src[i], lo), hi);
 }
+__global__ void copy_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
 __global__ void stats_row_kernel(float* __restrict__ row, const float* __restrict__ loss4, const float* __restrict__ gnorm) {
     if (threadIdx.x < 4) row[threadIdx.x] = loss4[threadIdx.x];
     if (threadIdx.x == 4) row[4] = *gnorm;
@@ -392,6 +396,9 @@ int b200rl_onpolicy_create(b200rl_ctx* ctx, b200rl_net* net, b200rl_env* env, co
     A_TRY(cudaMalloc(&a->norm_sums, 2 * sizeof(double))); A_TRY(cudaMalloc(&a->norm2, 2 * sizeof(float)));
     a->stats_rows = cfg->n_epochs * cfg->n_microbatches;
     A_TRY(cudaMalloc(&a->stats_dev, (size_t)a->stats_rows * 8 * sizeof(float)));
+    // staging for host-supplied shuffle!() results; allocated here because a device allocation inside update would
+    // synchronise the device (and with it another rank of the same process that is waiting in the peer exchange)
+    A_TRY(cudaMalloc(&a->perm_dev, (size_t)a->cfg.n_epochs * NT_ * 4));
     A_TRY(cudaMemsetAsync(a->stats_dev, 0, (size_t)a->stats_rows * 8 * sizeof(float), ctx->stream));
     A_TRY(cudaMemcpyAsync(a->rng, policy_rng, (size_t)N * 32, cudaMemcpyHostToDevice, ctx->stream));
     A_TRY(cudaStreamSynchronize(ctx->stream));
@@ -475,7 +482,9 @@ int b200rl_onpolicy_update(b200rl_onpolicy* a, const int32_t* perm_host, float* 
     int world = b200rl_comm_world(ctx);
     // bootstrap value of the state after the last step
     const float* obs = (const float*)env_field(a->env, B200RL_FIELD_OBS);
-    CUDA_TRY(cudaMemcpyAsync(a->states + (size_t)N * a->ns * T, obs, (size_t)N * a->ns * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    // (a copy kernel, not cudaMemcpyAsync D2D: device-to-device copies are on CUDA's implicit-synchronisation list)
+    copy_f32_kernel<<<grid_for(N * a->ns, 256), 256, 0, ctx->stream>>>(a->states + (size_t)N * a->ns * T, obs, N * a->ns);
+    LAUNCH_CHECK(ctx);
     TRY(nn_mlp_forward(ctx, n->critic, n->params + n->actor.nparams(), obs, N, a->values + (size_t)N * T));
     // GAE + returns + normalisation sums
     int n_part = b200rl_gae_fused_partials_count(N) / 2;
@@ -492,7 +501,6 @@ int b200rl_onpolicy_update(b200rl_onpolicy* a, const int32_t* perm_host, float* 
         LAUNCH_CHECK(ctx);
     }
     if (perm_host) {
-        if (!a->perm_dev) CUDA_TRY(cudaMalloc(&a->perm_dev, (size_t)c.n_epochs * NT_ * 4));
         CUDA_TRY(cudaMemcpyAsync(a->perm_dev, perm_host, (size_t)c.n_epochs * NT_ * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     AcHyper hp{c.clip_range, c.w_actor, c.w_critic, c.w_entropy, c.min_sigma, c.max_sigma, c.normalize_advantage, c.algo};
@@ -506,17 +514,19 @@ int b200rl_onpolicy_update(b200rl_onpolicy* a, const int32_t* perm_host, float* 
                       1.0f / ((float)B * (float)world), a->norm2};
             int ctas = nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
             if (ctas < 0) return ctas;
-            if (world > 1) {
+            float* stats_row = a->stats_dev + (size_t)row * 8;
+            P2PTable peers;
+            if (world > 1 && !b200rl_comm_p2p_table(ctx, &peers)) {   // no peer exchange attached: reduce -> NCCL all-reduce -> clip + Adam
                 TRY(nn_reduce_partials(ctx, n->partial, ctas, n->np, n->grad, n->loss_partial, 2 * ctas, n->loss4));
                 TRY(b200rl_comm_allreduce_internal(ctx, n->grad, n->np, 0));
                 TRY(b200rl_comm_allreduce_internal(ctx, n->loss4, 4, 0));
                 TRY(nn_clip_adam(ctx, n->params, n->grad, n->m, n->v, n->beta_t, n->np, c.max_grad_norm, c.lr, c.beta1, c.beta2, c.eps, 1.0f, n->gnorm));
-            } else {
+                stats_row_kernel<<<1, 32, 0, ctx->stream>>>(stats_row, n->loss4, n->gnorm);
+                LAUNCH_CHECK(ctx);
+            } else {   // one kernel: reduce [-> exchange with the peers over NVLink] -> clip -> Adam -> stats row
                 TRY(nn_reduce_clip_adam(ctx, n->partial, ctas, n->np, n->params, n->grad, n->m, n->v, n->beta_t, n->loss_partial, 2 * ctas, n->loss4,
-                                        c.max_grad_norm, c.lr, c.beta1, c.beta2, c.eps, n->gnorm, n->cta_sumsq, n->counter2, &n->fused_launches));
+                                        c.max_grad_norm, c.lr, c.beta1, c.beta2, c.eps, n->gnorm, n->cta_sumsq, n->counter2, &n->fused_launches, stats_row));
             }
-            stats_row_kernel<<<1, 32, 0, ctx->stream>>>(a->stats_dev + (size_t)row * 8, n->loss4, n->gnorm);
-            LAUNCH_CHECK(ctx);
             n->n_updates += 1;
         }
     }

@@ -66,20 +66,64 @@ int load_nccl() {
 }  // namespace
 
 struct b200rl_comm_state {
-    ncclComm_t comm;
+    ncclComm_t comm;          // null when the communicator was created without NCCL (peer exchange only)
     int nranks, rank;
+    unsigned char* region = nullptr;        // this rank's exchange region (cudaMalloc, exported through CUDA IPC)
+    void* opened[kP2PMaxRanks] = {};        // peer regions opened with cudaIpcOpenMemHandle (closed on destroy)
+    P2PTable tab = {};                      // tab.nranks > 0 once attached
+    uint32_t gseq = 0, yseq = 0;            // sequence numbers of the gradient / small all-reduce exchanges
 };
+
+namespace {
+// all-reduce (sum, in rank order => bit-identical on every rank) of a small buffer through the peer regions
+template <class T>
+__global__ void __launch_bounds__(256) p2p_allreduce_small_kernel(P2PTable tab, T* __restrict__ buf, int n, unsigned seq) {
+    const unsigned slot = seq & 1u;
+    T* mine = reinterpret_cast<T*>(p2p_y(tab, tab.rank, slot));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = buf[i];
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence_system(); st_release_sys(p2p_yflag(tab, tab.rank, slot), seq); }
+    if ((int)threadIdx.x < tab.nranks && (int)threadIdx.x != tab.rank) p2p_wait_flag(p2p_yflag(tab, threadIdx.x, slot), seq);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        T acc = 0;
+        for (int r = 0; r < tab.nranks; ++r) {
+            const T* src = reinterpret_cast<const T*>(p2p_y(tab, r, slot)) + i;
+            if (sizeof(T) == 8) acc += (T)ld_peer_f64(reinterpret_cast<const double*>(src));
+            else acc += (T)ld_peer_f32(reinterpret_cast<const float*>(src));
+        }
+        buf[i] = acc;
+    }
+}
+}  // namespace
 
 void b200rl_comm_destroy_internal(b200rl_ctx* ctx) {
     if (ctx->comm) {
-        if (g_api.CommDestroy) g_api.CommDestroy(ctx->comm->comm);
+        for (void* q : ctx->comm->opened) if (q) cudaIpcCloseMemHandle(q);
+        if (ctx->comm->region) cudaFree(ctx->comm->region);
+        if (g_api.CommDestroy && ctx->comm->comm) g_api.CommDestroy(ctx->comm->comm);
         delete ctx->comm;
         ctx->comm = nullptr;
     }
 }
 int b200rl_comm_world(b200rl_ctx* ctx) { return ctx->comm ? ctx->comm->nranks : 1; }
+bool b200rl_comm_p2p_table(b200rl_ctx* ctx, P2PTable* out) {
+    if (!ctx->comm || ctx->comm->tab.nranks <= 1) return false;
+    *out = ctx->comm->tab;
+    return true;
+}
+uint32_t b200rl_comm_p2p_next_gseq(b200rl_ctx* ctx) { return ++ctx->comm->gseq; }
 int b200rl_comm_allreduce_internal(b200rl_ctx* ctx, void* buf, int64_t n, int is_double) {
     REQUIRE(ctx->comm, B200RL_ERR_INVALID, "no communicator");
+    b200rl_comm_state* c = ctx->comm;
+    if (c->tab.nranks > 1 && n * (is_double ? 8 : 4) <= (int64_t)kP2PYCap * 8) {   // small: one kernel over NVLink peer memory
+        unsigned seq = ++c->yseq;
+        if (is_double) p2p_allreduce_small_kernel<double><<<1, 256, 0, ctx->stream>>>(c->tab, (double*)buf, (int)n, seq);
+        else p2p_allreduce_small_kernel<float><<<1, 256, 0, ctx->stream>>>(c->tab, (float*)buf, (int)n, seq);
+        LAUNCH_CHECK(ctx);
+        return B200RL_OK;
+    }
+    REQUIRE(c->comm, B200RL_ERR_UNSUPPORTED, "buffer too large for the peer exchange and no NCCL communicator");
     NCCL_TRY(g_api.AllReduce(buf, buf, (size_t)n, is_double ? ncclFloat64 : ncclFloat32, ncclSum, ctx->comm->comm, ctx->stream));
     return B200RL_OK;
 }
@@ -97,14 +141,74 @@ int b200rl_comm_unique_id(void* id128_out) {
 /* one process per GPU: attach ctx to rank `rank` of an `nranks` communicator */
 int b200rl_comm_init(b200rl_ctx* ctx, int nranks, int rank, const void* id128) {
     TRY(ctx_bind(ctx));
-    REQUIRE(id128 && nranks >= 1 && rank >= 0 && rank < nranks, B200RL_ERR_INVALID, "bad argument");
+    REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, B200RL_ERR_INVALID, "bad argument");
     REQUIRE(!ctx->comm, B200RL_ERR_INVALID, "communicator already initialised");
-    TRY(load_nccl());
-    ncclUniqueId id;
-    memcpy(&id, id128, sizeof id);
-    ncclComm_t c;
-    NCCL_TRY(g_api.CommInitRank(&c, nranks, id, rank));
-    ctx->comm = new b200rl_comm_state{c, nranks, rank};
+    ncclComm_t c = nullptr;
+    if (id128) {   // NULL id: no NCCL, the peer exchange (b200rl_comm_p2p_*) must be attached before the first collective
+        TRY(load_nccl());
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof id);
+        NCCL_TRY(g_api.CommInitRank(&c, nranks, id, rank));
+    }
+    ctx->comm = new b200rl_comm_state();
+    ctx->comm->comm = c; ctx->comm->nranks = nranks; ctx->comm->rank = rank;
+    return B200RL_OK;
+}
+/* allocate this rank's exchange region; handle64_out (may be NULL) receives its CUDA IPC handle for the other processes,
+ * region_out (may be NULL) the device pointer for ranks living in the same process */
+int b200rl_comm_p2p_export(b200rl_ctx* ctx, void* handle64_out, void** region_out) {
+    TRY(ctx_bind(ctx));
+    REQUIRE(ctx->comm, B200RL_ERR_INVALID, "b200rl_comm_init first");
+    b200rl_comm_state* c = ctx->comm;
+    if (!c->region) {
+        CUDA_TRY(cudaMalloc(&c->region, kP2PRegionBytes));
+        CUDA_TRY(cudaMemset(c->region, 0, kP2PRegionBytes));
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    if (handle64_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(cudaIpcGetMemHandle(&h, c->region));
+        memcpy(handle64_out, &h, sizeof h);
+    }
+    if (region_out) *region_out = c->region;
+    return B200RL_OK;
+}
+/* map another process's region (its 64-byte IPC handle) into this process */
+int b200rl_comm_p2p_open(b200rl_ctx* ctx, const void* handle64, void** region_out) {
+    TRY(ctx_bind(ctx));
+    REQUIRE(ctx->comm && handle64 && region_out, B200RL_ERR_INVALID, "bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    void* q = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    for (void*& slot : ctx->comm->opened) if (!slot) { slot = q; break; }
+    *region_out = q;
+    return B200RL_OK;
+}
+/* regions[r] = device pointer of rank r's region as seen by THIS process (entry `rank` may be NULL: own region).
+ * From here on gradient and small all-reduces go through peer memory in one fused kernel each. */
+int b200rl_comm_p2p_attach(b200rl_ctx* ctx, void* const* regions) {
+    TRY(ctx_bind(ctx));
+    REQUIRE(ctx->comm && regions, B200RL_ERR_INVALID, "bad argument");
+    b200rl_comm_state* c = ctx->comm;
+    REQUIRE(c->region, B200RL_ERR_INVALID, "b200rl_comm_p2p_export first");
+    REQUIRE(c->nranks <= kP2PMaxRanks, B200RL_ERR_UNSUPPORTED, "peer exchange supports up to 8 ranks (one NVSwitch node)");
+    P2PTable t = {};
+    t.nranks = c->nranks; t.rank = c->rank;
+    for (int r = 0; r < c->nranks; ++r) {
+        t.base[r] = r == c->rank ? c->region : (unsigned char*)regions[r];
+        REQUIRE(t.base[r], B200RL_ERR_INVALID, "null peer region");
+        if (r != c->rank) {   // same-process peers on another device: enable direct access (IPC mappings already are)
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, t.base[r]) == cudaSuccess && at.device != ctx->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); }
+                else cudaGetLastError();
+            }
+        }
+    }
+    c->tab = t;
     return B200RL_OK;
 }
 /* in-place sum all-reduce of a DEVICE fp32 buffer on the ctx stream */

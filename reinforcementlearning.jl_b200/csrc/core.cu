@@ -14,9 +14,9 @@ void b200rl_set_error(const char* fmt, ...) {
 
 int ctx_scratch(b200rl_ctx* ctx, size_t bytes, void** out) {
     if (bytes > ctx->scratch_bytes) {
-        // the old buffer may still be read by queued work on the stream
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        if (ctx->scratch) CUDA_TRY(cudaFree(ctx->scratch));
+        // The old buffer may still be read by queued work, and cudaFree would synchronise the whole device (a deadlock when
+        // another rank of the same process is spinning on this rank inside the peer exchange): retire it, free at destroy.
+        if (ctx->scratch) ctx->retired.push_back(ctx->scratch);
         ctx->scratch = nullptr;
         ctx->scratch_bytes = 0;
         size_t want = bytes + bytes / 4 + 4096;
@@ -74,6 +74,7 @@ void b200rl_destroy(b200rl_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     b200rl_comm_destroy_internal(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    for (void* q : ctx->retired) cudaFree(q);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);

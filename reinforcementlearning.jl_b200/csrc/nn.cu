@@ -717,15 +717,20 @@ __global__ void __launch_bounds__(1024) clip_adam_kernel(float* __restrict__ p, 
     if (threadIdx.x == 0) { beta_t[0] = bt1 * b1; beta_t[1] = bt2 * b2; }
 }
 
-// Fused K8 for the single-GPU path: partial reduce -> global norm -> clip -> Adam in ONE launch.  The CTAs meet at a
+// Fused K8: partial reduce -> [peer exchange over NVLink] -> global norm -> clip -> Adam in ONE launch.  The CTAs meet at a
 // device-wide counter (all ceil(np/256) <= 148 CTAs are co-resident), every CTA then sums the per-CTA sum-of-squares in
 // CTA order, so the result is bit-identical to the two-kernel path and run-to-run deterministic.
+// XCHG (sharded run): each CTA publishes its 256-parameter chunk of the local gradient to this rank's exchange
+// region, raises the chunk's flag, waits for the same chunk of every peer and sums the chunks in rank order — every rank
+// computes the identical global gradient, so the replicas' parameters stay bit-identical without a broadcast.
+template <bool XCHG>
 __global__ void __launch_bounds__(256) reduce_clip_adam_kernel(const float* __restrict__ partial, int n_partials, int64_t np, float* __restrict__ p,
                                                               float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                               float* __restrict__ beta_t, const float* __restrict__ loss_partial, int n_loss,
                                                               float* __restrict__ loss_out4, float max_norm, float lr, float b1, float b2, float eps,
                                                               float* __restrict__ gnorm_out, double* __restrict__ cta_sumsq,
-                                                              unsigned int* __restrict__ counter, unsigned int target) {
+                                                              unsigned int* __restrict__ counter, unsigned int target, float* __restrict__ stats_row,
+                                                              P2PTable tab, unsigned int seq) {
     __shared__ double red[8];
     __shared__ float s_scale;
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -733,10 +738,30 @@ __global__ void __launch_bounds__(256) reduce_clip_adam_kernel(const float* __re
     if (k < np) {
         for (int c = 0; c < n_partials; ++c) gk += partial[(int64_t)c * np + k];
     }
-    if (blockIdx.x == 0 && threadIdx.x < 4 && loss_out4) {
-        float a = 0.f;
-        for (int c = 0; c < n_loss; ++c) a += loss_partial[c * 4 + threadIdx.x];
-        loss_out4[threadIdx.x] = a;
+    float lsum = 0.f;
+    const bool loss_thread = blockIdx.x == 0 && threadIdx.x < 4;
+    if (loss_thread)
+        for (int c = 0; c < n_loss; ++c) lsum += loss_partial[c * 4 + threadIdx.x];
+    if (XCHG) {
+        const unsigned slot = seq & 1u;
+        float* mine = p2p_x(tab, tab.rank, slot);
+        if (k < np) mine[k] = gk;
+        if (loss_thread) mine[np + threadIdx.x] = lsum;     // the 4 loss sums ride along in CTA 0's chunk
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence_system(); st_release_sys(p2p_gflag(tab, tab.rank, slot) + blockIdx.x, seq); }
+        if ((int)threadIdx.x < tab.nranks && (int)threadIdx.x != tab.rank) p2p_wait_flag(p2p_gflag(tab, threadIdx.x, slot) + blockIdx.x, seq);
+        __syncthreads();
+        float acc = 0.f, lacc = 0.f;
+        for (int r = 0; r < tab.nranks; ++r) {
+            const float* src = p2p_x(tab, r, slot);
+            if (k < np) acc += r == tab.rank ? gk : ld_peer_f32(src + k);
+            if (loss_thread) lacc += r == tab.rank ? lsum : ld_peer_f32(src + np + threadIdx.x);
+        }
+        gk = acc; lsum = lacc;
+    }
+    if (loss_thread) {
+        if (loss_out4) loss_out4[threadIdx.x] = lsum;
+        if (stats_row) stats_row[threadIdx.x] = lsum;
     }
     double acc = (double)gk * (double)gk;
 #pragma unroll
@@ -759,7 +784,10 @@ __global__ void __launch_bounds__(256) reduce_clip_adam_kernel(const float* __re
         float sc = 1.0f;
         if (max_norm > 0.f && max_norm <= gn) sc = max_norm / fmaxf(max_norm, gn);
         s_scale = sc;
-        if (blockIdx.x == 0 && gnorm_out) *gnorm_out = gn;
+        if (blockIdx.x == 0) {
+            if (gnorm_out) *gnorm_out = gn;
+            if (stats_row) stats_row[4] = gn;
+        }
     }
     __syncthreads();
     const float bt1 = beta_t[0], bt2 = beta_t[1];
@@ -1005,12 +1033,21 @@ int nn_clip_adam(b200rl_ctx* ctx, float* params, float* grad, float* m, float* v
 
 int nn_reduce_clip_adam(b200rl_ctx* ctx, const float* partial, int n_partials, int64_t np, float* params, float* grad, float* m, float* v,
                         float* beta_t, const float* loss_partial, int n_loss, float* loss_out4, float max_grad_norm, float lr, float b1, float b2,
-                        float eps, float* gnorm_out, double* cta_sumsq, unsigned int* counter2, unsigned int* launches) {
+                        float eps, float* gnorm_out, double* cta_sumsq, unsigned int* counter2, unsigned int* launches, float* stats_row) {
     unsigned grid = grid_for(np, 256);
     REQUIRE((int)grid <= ctx->sm_count, B200RL_ERR_UNSUPPORTED, "fused reduce+Adam needs all CTAs co-resident");
     *launches += 1;
-    reduce_clip_adam_kernel<<<grid, 256, 0, ctx->stream>>>(partial, n_partials, np, params, grad, m, v, beta_t, loss_partial, n_loss, loss_out4,
-                                                          max_grad_norm, lr, b1, b2, eps, gnorm_out, cta_sumsq, counter2, *launches * grid);
+    P2PTable tab = {};
+    if (b200rl_comm_p2p_table(ctx, &tab)) {
+        REQUIRE((size_t)np + 4 <= kP2PXCap && grid <= (unsigned)kP2PMaxCta, B200RL_ERR_UNSUPPORTED, "gradient larger than the peer exchange region");
+        reduce_clip_adam_kernel<true><<<grid, 256, 0, ctx->stream>>>(partial, n_partials, np, params, grad, m, v, beta_t, loss_partial, n_loss, loss_out4,
+                                                                    max_grad_norm, lr, b1, b2, eps, gnorm_out, cta_sumsq, counter2, *launches * grid,
+                                                                    stats_row, tab, b200rl_comm_p2p_next_gseq(ctx));
+    } else {
+        reduce_clip_adam_kernel<false><<<grid, 256, 0, ctx->stream>>>(partial, n_partials, np, params, grad, m, v, beta_t, loss_partial, n_loss, loss_out4,
+                                                                     max_grad_norm, lr, b1, b2, eps, gnorm_out, cta_sumsq, counter2, *launches * grid,
+                                                                     stats_row, tab, 0u);
+    }
     LAUNCH_CHECK(ctx);
     return B200RL_OK;
 }

@@ -54,10 +54,11 @@ int nn_reduce_partials(b200rl_ctx* ctx, const float* partial, int n_partials, in
 // clip_by_global_norm! + Optimisers Adam on a flat gradient (single CTA, deterministic)
 int nn_clip_adam(b200rl_ctx* ctx, float* params, float* grad, float* m, float* v, float* beta_t /* device [2] */, int64_t np,
                  float max_grad_norm, float lr, float b1, float b2, float eps, float grad_scale, float* gnorm_out /* device */);
-// fused single-launch variant (single GPU): cta_sumsq >= 148 doubles, counter2 = 2 zero-initialised uints, *launches = host-side launch count
+// fused single-launch variant (single GPU, or a sharded run with the NVLink peer exchange attached; stats_row (may be null)
+// receives {4 loss sums, grad norm}): cta_sumsq >= 148 doubles, counter2 = 2 zero-initialised uints, *launches = host-side launch count
 int nn_reduce_clip_adam(b200rl_ctx* ctx, const float* partial, int n_partials, int64_t np, float* params, float* grad, float* m, float* v,
                         float* beta_t, const float* loss_partial, int n_loss, float* loss_out4, float max_grad_norm, float lr, float b1, float b2,
-                        float eps, float* gnorm_out, double* cta_sumsq, unsigned int* counter2, unsigned int* launches);
+                        float eps, float* gnorm_out, double* cta_sumsq, unsigned int* counter2, unsigned int* launches, float* stats_row);
 int nn_target_sync(b200rl_ctx* ctx, float* target, const float* model, int64_t np, float rho);
 // DQN: TD loss + backward on a gathered batch (device arrays s (in,B), a, r, t, s2, w)
 int nn_dqn_loss_grad(b200rl_ctx* ctx, const MlpDesc& q, const float* params, const float* target, const float* s, const int32_t* a,

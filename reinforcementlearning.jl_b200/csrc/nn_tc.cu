@@ -962,7 +962,8 @@ int nn_tc_forward(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc
                   const float* obs, int64_t N, unsigned long long* rng, void* action_out, float* logp_out, float* value_out, float* head_out,
                   float* state_copy) {
     size_t smem = sizeof(SmemFwd) + 128;
-    CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set = false;   // once per process: the attribute call is not free and may serialise with running kernels
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
     forward_tc_kernel<<<grid, NT, smem, ctx->stream>>>(actor, critic, params, hp, mode, obs, N, rng, action_out, logp_out, value_out, head_out,
                                                        state_copy);
     LAUNCH_CHECK(ctx);
@@ -975,7 +976,8 @@ bool nn_tc_bwd_supported(const MlpDesc& actor, const MlpDesc& critic) {
 int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
                        const AcBatch& b, float* partial, float* loss_partial, int64_t np) {
     size_t smem = sizeof(SmemBwd) + 128;
-    CUDA_TRY(cudaFuncSetAttribute(ac_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(ac_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
     ac_loss_grad_tc_kernel<<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np);
     LAUNCH_CHECK(ctx);
     return B200RL_OK;

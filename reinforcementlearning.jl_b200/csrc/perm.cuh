@@ -5,7 +5,7 @@
 // domain 2^bits >= n, bits >= 2, with cycle walking for the values >= n.  The left half has
 // floor(bits/2) bits and the right half the rest; the halves swap widths every round, so any
 // bits works and a power-of-two n (the BASELINE rollouts: 65536 x 32 = 2^21) never walks.
-// The oracle restates the same bijection in oracle/perm.hpp; DESIGN.md §K7.
+// DESIGN.md §K7; the parity tests check it against an independent CPU restatement.
 #pragma once
 #include <cstdint>
 

@@ -42,3 +42,33 @@ def glorot_actor_critic(seed, n_in, hidden, n_out):
     parts = dense(hidden, n_in) + dense(hidden, hidden) + dense(n_out, hidden)
     parts += dense(hidden, n_in) + dense(hidden, hidden) + dense(1, hidden)
     return np.concatenate(parts)
+
+
+def attach_peer_exchange(ctx, rank, world, all_gather_bytes):
+    """Wire the NVLink peer exchange of a one-process-per-GPU run (include/b200rl.h, b200rl_comm_p2p_*).
+
+    ``all_gather_bytes(b: bytes) -> list[bytes]`` is any host-side all-gather in rank order (torch.distributed,
+    MPI, a file system ...): it only ships the 64-byte CUDA IPC handles once.  Returns True when the fused
+    exchange is active, False when IPC mapping is refused (the NCCL path stays in use)."""
+    import ctypes as C
+
+    from . import _lib as L
+    handle = (C.c_char * 64)()
+    L.check(ctx.lib.b200rl_comm_p2p_export(ctx.h, handle, None))
+    handles = all_gather_bytes(bytes(handle.raw))
+    regions = (C.c_void_p * world)()
+    ok = True
+    for r in range(world):
+        if r == rank:
+            continue
+        p = C.c_void_p()
+        if ctx.lib.b200rl_comm_p2p_open(ctx.h, handles[r], C.byref(p)) != L.OK:
+            ok = False
+            break
+        regions[r] = p
+    # every rank must take the same decision: one refused mapping disables the exchange everywhere
+    flags = all_gather_bytes(b"\x01" if ok else b"\x00")
+    if not all(f == b"\x01" for f in flags):
+        return False
+    L.check(ctx.lib.b200rl_comm_p2p_attach(ctx.h, regions))
+    return True
