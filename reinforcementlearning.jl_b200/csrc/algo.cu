@@ -609,9 +609,16 @@ int b200rl_onpolicy_time_kernel(b200rl_onpolicy* a, int which, int reps, float* 
             }
             case 2: return b200rl_env_step(a->env, a->actions, 1, 1);
             case 3: return b200rl_gae_fused_internal(ctx, a->adv, a->ret, a->rewards, a->values, a->terminals, c.gamma, c.lambda, N, T, a->norm_partials, nullptr);
-            case 4: {
-                TRY(nn_reduce_partials(ctx, n->partial, ctas, n->np, n->grad, n->loss_partial, 2 * ctas, n->loss4));
-                return nn_clip_adam(ctx, n->params, n->grad, n->m, n->v, n->beta_t, n->np, c.max_grad_norm, 0.0f, c.beta1, c.beta2, c.eps, 1.0f, n->gnorm);
+            case 4: {   // the optimiser step as update() runs it (lr = 0: parameters stay put), incl. the peer exchange of a sharded run
+                P2PTable peers;
+                if (b200rl_comm_world(ctx) > 1 && !b200rl_comm_p2p_table(ctx, &peers)) {
+                    TRY(nn_reduce_partials(ctx, n->partial, ctas, n->np, n->grad, n->loss_partial, 2 * ctas, n->loss4));
+                    TRY(b200rl_comm_allreduce_internal(ctx, n->grad, n->np, 0));
+                    TRY(b200rl_comm_allreduce_internal(ctx, n->loss4, 4, 0));
+                    return nn_clip_adam(ctx, n->params, n->grad, n->m, n->v, n->beta_t, n->np, c.max_grad_norm, 0.0f, c.beta1, c.beta2, c.eps, 1.0f, n->gnorm);
+                }
+                return nn_reduce_clip_adam(ctx, n->partial, ctas, n->np, n->params, n->grad, n->m, n->v, n->beta_t, n->loss_partial, 2 * ctas, n->loss4,
+                                           c.max_grad_norm, 0.0f, c.beta1, c.beta2, c.eps, n->gnorm, n->cta_sumsq, n->counter2, &n->fused_launches, nullptr);
             }
         }
         b200rl_set_error("unknown kernel id");

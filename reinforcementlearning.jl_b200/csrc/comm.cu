@@ -75,22 +75,25 @@ struct b200rl_comm_state {
 };
 
 namespace {
-// all-reduce (sum, in rank order => bit-identical on every rank) of a small buffer through the peer regions
+// all-reduce (sum, in rank order => bit-identical on every rank) of a small buffer through the peer inboxes
 template <class T>
 __global__ void __launch_bounds__(256) p2p_allreduce_small_kernel(P2PTable tab, T* __restrict__ buf, int n, unsigned seq) {
     const unsigned slot = seq & 1u;
-    T* mine = reinterpret_cast<T*>(p2p_y(tab, tab.rank, slot));
-    for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = buf[i];
-    __syncthreads();
-    if (threadIdx.x == 0) { __threadfence_system(); st_release_sys(p2p_yflag(tab, tab.rank, slot), seq); }
-    if ((int)threadIdx.x < tab.nranks && (int)threadIdx.x != tab.rank) p2p_wait_flag(p2p_yflag(tab, threadIdx.x, slot), seq);
-    __syncthreads();
+    constexpr int W = sizeof(T) / 4;   // 32-bit words per element
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        T mine = buf[i];
+        unsigned w[2] = {0u, 0u};
+        memcpy(w, &mine, sizeof(T));
+        for (int h = 0; h < W; ++h) p2p_push(tab, 1, slot, (size_t)i * W + h, w[h], seq);
         T acc = 0;
         for (int r = 0; r < tab.nranks; ++r) {
-            const T* src = reinterpret_cast<const T*>(p2p_y(tab, r, slot)) + i;
-            if (sizeof(T) == 8) acc += (T)ld_peer_f64(reinterpret_cast<const double*>(src));
-            else acc += (T)ld_peer_f32(reinterpret_cast<const float*>(src));
+            T val = mine;
+            if (r != tab.rank) {
+                unsigned u[2] = {0u, 0u};
+                for (int h = 0; h < W; ++h) u[h] = p2p_recv(tab, 1, slot, r, (size_t)i * W + h, seq);
+                memcpy(&val, u, sizeof(T));
+            }
+            acc += val;
         }
         buf[i] = acc;
     }
@@ -116,7 +119,7 @@ uint32_t b200rl_comm_p2p_next_gseq(b200rl_ctx* ctx) { return ++ctx->comm->gseq; 
 int b200rl_comm_allreduce_internal(b200rl_ctx* ctx, void* buf, int64_t n, int is_double) {
     REQUIRE(ctx->comm, B200RL_ERR_INVALID, "no communicator");
     b200rl_comm_state* c = ctx->comm;
-    if (c->tab.nranks > 1 && n * (is_double ? 8 : 4) <= (int64_t)kP2PYCap * 8) {   // small: one kernel over NVLink peer memory
+    if (c->tab.nranks > 1 && n * (is_double ? 2 : 1) <= (int64_t)kP2PYCap) {   // small: one kernel over NVLink peer memory
         unsigned seq = ++c->yseq;
         if (is_double) p2p_allreduce_small_kernel<double><<<1, 256, 0, ctx->stream>>>(c->tab, (double*)buf, (int)n, seq);
         else p2p_allreduce_small_kernel<float><<<1, 256, 0, ctx->stream>>>(c->tab, (float*)buf, (int)n, seq);

@@ -68,21 +68,19 @@ static inline int ctx_bind(b200rl_ctx* ctx) {
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
-// ---- NVLink peer exchange region (comm.cu): one per rank, mapped into every rank of the node ------------------
-// Layout (two slots each, slot = sequence number & 1, so a slot is only rewritten after every peer has published the
-// NEXT sequence number, i.e. has finished reading it):
-//   x[2][kP2PXCap]        fp32   gradient (+ 4 loss sums) published by the fused reduce / exchange / clip / Adam kernel
-//   gflag[2][kP2PMaxCta]  u32    per-CTA "chunk published" sequence numbers
-//   y[2][kP2PYCap]        f64    small all-reduces (advantage-normalisation sums, ...)
-//   yflag[2][16]          u32
-constexpr size_t kP2PXCap = 262144;
-constexpr int kP2PMaxCta = 1024;
-constexpr int kP2PYCap = 1024;
+// ---- NVLink peer exchange (comm.cu): low-latency PUSH protocol --------------------------------------------------
+// Every rank owns an inbox region mapped into all ranks of the node.  A sender writes 8-byte packets {32 data bits,
+// sequence number} straight into the receivers' inboxes (remote NVLink stores: one-way latency, no round trip); a receiver
+// polls its OWN memory until the packet carries the current sequence number — the packet validates itself, so there are no
+// separate flags and no fences.  Two slots (sequence & 1): a slot is rewritten two exchanges later, by which time the
+// receiver has long consumed it (it had to push its own packets of the exchange in between, after finishing this one).
+//   inbox_x[2][kP2PMaxRanks][kP2PXCap]   gradient words (+ 4 loss sums)     — fused reduce / exchange / clip / Adam kernel
+//   inbox_y[2][kP2PMaxRanks][kP2PYCap]   small all-reduces (one word per float, two per double)
+constexpr size_t kP2PXCap = 32768;
+constexpr size_t kP2PYCap = 2048;
 constexpr int kP2PMaxRanks = 8;
-constexpr size_t kP2POffG = 2 * kP2PXCap * 4;
-constexpr size_t kP2POffY = kP2POffG + 2 * (size_t)kP2PMaxCta * 4;
-constexpr size_t kP2POffYF = kP2POffY + 2 * (size_t)kP2PYCap * 8;
-constexpr size_t kP2PRegionBytes = kP2POffYF + 2 * 16 * 4;
+constexpr size_t kP2POffY = 2 * (size_t)kP2PMaxRanks * kP2PXCap * 8;
+constexpr size_t kP2PRegionBytes = kP2POffY + 2 * (size_t)kP2PMaxRanks * kP2PYCap * 8;
 struct P2PTable {   // nranks == 0: not attached
     int nranks, rank;
     unsigned char* base[kP2PMaxRanks];
@@ -91,33 +89,28 @@ bool b200rl_comm_p2p_table(b200rl_ctx* ctx, P2PTable* out);   // false when no p
 uint32_t b200rl_comm_p2p_next_gseq(b200rl_ctx* ctx);
 
 #ifdef __CUDACC__
-__device__ __forceinline__ float* p2p_x(const P2PTable& t, int r, unsigned slot) { return reinterpret_cast<float*>(t.base[r]) + (size_t)slot * kP2PXCap; }
-__device__ __forceinline__ unsigned* p2p_gflag(const P2PTable& t, int r, unsigned slot) {
-    return reinterpret_cast<unsigned*>(t.base[r] + kP2POffG) + (size_t)slot * kP2PMaxCta;
+// packet address: inbox of rank `dst`, area (0 = x, 1 = y), slot, written by rank `src`, word index idx
+__device__ __forceinline__ uint2* p2p_packet(const P2PTable& t, int dst, int area, unsigned slot, int src, size_t idx) {
+    const size_t cap = area ? kP2PYCap : kP2PXCap;
+    return reinterpret_cast<uint2*>(t.base[dst] + (area ? kP2POffY : 0)) + ((size_t)slot * kP2PMaxRanks + src) * cap + idx;
 }
-__device__ __forceinline__ double* p2p_y(const P2PTable& t, int r, unsigned slot) { return reinterpret_cast<double*>(t.base[r] + kP2POffY) + (size_t)slot * kP2PYCap; }
-__device__ __forceinline__ unsigned* p2p_yflag(const P2PTable& t, int r, unsigned slot) { return reinterpret_cast<unsigned*>(t.base[r] + kP2POffYF) + (size_t)slot * 16; }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void p2p_push(const P2PTable& t, int area, unsigned slot, size_t idx, unsigned bits, unsigned seq) {
+    for (int r = 0; r < t.nranks; ++r) {
+        if (r == t.rank) continue;
+        uint2* q = p2p_packet(t, r, area, slot, t.rank, idx);
+        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(q), "r"(bits), "r"(seq) : "memory");
+    }
 }
-__device__ __forceinline__ float ld_peer_f32(const float* p) {   // peer memory over NVLink: never from a stale cache line
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_peer_f64(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-// spin until the peer's flag carries `seq`; a peer that never arrives (crashed rank) traps after ~10 s instead of hanging the GPU
-__device__ __forceinline__ void p2p_wait_flag(const unsigned* flag, unsigned seq) {
+// spin on the own inbox until rank `src`'s packet of this exchange has landed; a peer that never arrives (crashed rank)
+// traps after ~10 s instead of hanging the GPU
+__device__ __forceinline__ unsigned p2p_recv(const P2PTable& t, int area, unsigned slot, int src, size_t idx, unsigned seq) {
+    const uint2* q = p2p_packet(t, t.rank, area, slot, src, idx);
     unsigned long long t0 = 0;
     unsigned spins = 0;
-    while (ld_acquire_sys(flag) != seq) {
+    for (;;) {
+        unsigned a, b;
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(q) : "memory");
+        if (b == seq) return a;
         if ((++spins & 1023u) == 0) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));

@@ -720,9 +720,9 @@ __global__ void __launch_bounds__(1024) clip_adam_kernel(float* __restrict__ p, 
 // Fused K8: partial reduce -> [peer exchange over NVLink] -> global norm -> clip -> Adam in ONE launch.  The CTAs meet at a
 // device-wide counter (all ceil(np/256) <= 148 CTAs are co-resident), every CTA then sums the per-CTA sum-of-squares in
 // CTA order, so the result is bit-identical to the two-kernel path and run-to-run deterministic.
-// XCHG (sharded run): each CTA publishes its 256-parameter chunk of the local gradient to this rank's exchange
-// region, raises the chunk's flag, waits for the same chunk of every peer and sums the chunks in rank order — every rank
-// computes the identical global gradient, so the replicas' parameters stay bit-identical without a broadcast.
+// XCHG (sharded run): every thread pushes its element of the local gradient into the peers' inboxes as a
+// self-validating {value, sequence} packet (remote NVLink store), then reads the peers' packets from the own inbox and sums
+// in rank order — every rank computes the identical global gradient, so the replicas stay bit-identical without a broadcast.
 template <bool XCHG>
 __global__ void __launch_bounds__(256) reduce_clip_adam_kernel(const float* __restrict__ partial, int n_partials, int64_t np, float* __restrict__ p,
                                                               float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -742,20 +742,14 @@ __global__ void __launch_bounds__(256) reduce_clip_adam_kernel(const float* __re
     const bool loss_thread = blockIdx.x == 0 && threadIdx.x < 4;
     if (loss_thread)
         for (int c = 0; c < n_loss; ++c) lsum += loss_partial[c * 4 + threadIdx.x];
-    if (XCHG) {
+    if (XCHG) {   // push the local chunk into every peer's inbox, then collect the peers' chunks from the own inbox
         const unsigned slot = seq & 1u;
-        float* mine = p2p_x(tab, tab.rank, slot);
-        if (k < np) mine[k] = gk;
-        if (loss_thread) mine[np + threadIdx.x] = lsum;     // the 4 loss sums ride along in CTA 0's chunk
-        __syncthreads();
-        if (threadIdx.x == 0) { __threadfence_system(); st_release_sys(p2p_gflag(tab, tab.rank, slot) + blockIdx.x, seq); }
-        if ((int)threadIdx.x < tab.nranks && (int)threadIdx.x != tab.rank) p2p_wait_flag(p2p_gflag(tab, threadIdx.x, slot) + blockIdx.x, seq);
-        __syncthreads();
+        if (k < np) p2p_push(tab, 0, slot, (size_t)k, __float_as_uint(gk), seq);
+        if (loss_thread) p2p_push(tab, 0, slot, (size_t)np + threadIdx.x, __float_as_uint(lsum), seq);   // the 4 loss sums ride along
         float acc = 0.f, lacc = 0.f;
         for (int r = 0; r < tab.nranks; ++r) {
-            const float* src = p2p_x(tab, r, slot);
-            if (k < np) acc += r == tab.rank ? gk : ld_peer_f32(src + k);
-            if (loss_thread) lacc += r == tab.rank ? lsum : ld_peer_f32(src + np + threadIdx.x);
+            if (k < np) acc += r == tab.rank ? gk : __uint_as_float(p2p_recv(tab, 0, slot, r, (size_t)k, seq));
+            if (loss_thread) lacc += r == tab.rank ? lsum : __uint_as_float(p2p_recv(tab, 0, slot, r, (size_t)np + threadIdx.x, seq));
         }
         gk = acc; lsum = lacc;
     }
@@ -1039,7 +1033,7 @@ int nn_reduce_clip_adam(b200rl_ctx* ctx, const float* partial, int n_partials, i
     *launches += 1;
     P2PTable tab = {};
     if (b200rl_comm_p2p_table(ctx, &tab)) {
-        REQUIRE((size_t)np + 4 <= kP2PXCap && grid <= (unsigned)kP2PMaxCta, B200RL_ERR_UNSUPPORTED, "gradient larger than the peer exchange region");
+        REQUIRE((size_t)np + 4 <= kP2PXCap, B200RL_ERR_UNSUPPORTED, "gradient larger than the peer exchange inbox");
         reduce_clip_adam_kernel<true><<<grid, 256, 0, ctx->stream>>>(partial, n_partials, np, params, grad, m, v, beta_t, loss_partial, n_loss, loss_out4,
                                                                     max_grad_norm, lr, b1, b2, eps, gnorm_out, cta_sumsq, counter2, *launches * grid,
                                                                     stats_row, tab, b200rl_comm_p2p_next_gseq(ctx));
