@@ -22,7 +22,8 @@ SOURCES = [
     ("returns.cu", ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]),
     ("comm.cu", []),
 ]
-OPTIONAL = [("traj.cu", []), ("nn.cu", []), ("algo.cu", []), ("umma_selftest.cu", []), ("nn_tc.cu", [])]
+ENV_FLAGS = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
+OPTIONAL = [("traj.cu", []), ("nn.cu", []), ("algo.cu", []), ("umma_selftest.cu", []), ("nn_tc.cu", []), ("fwd_tc.cu", ENV_FLAGS)]
 
 
 def _nvcc():

@@ -28,6 +28,12 @@ int64_t b200rl_traj_internal_lanes(b200rl_traj* t);
 int b200rl_traj_internal_priority_from_td(b200rl_traj* t, const float* td_dev, float eps, float alpha);
 int b200rl_comm_allreduce_internal(b200rl_ctx* ctx, void* buf, int64_t n, int is_double);
 int b200rl_comm_world(b200rl_ctx* ctx);
+int b200rl_env_internal_kind(const b200rl_env* e);
+static bool fused_rollout_enabled() {   // B200RL_FUSED_ROLLOUT=0: step through plan!/act! launches instead (same results)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B200RL_FUSED_ROLLOUT"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
 
 namespace {
 __global__ void clamp_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n, float lo, float hi) {
@@ -339,6 +345,7 @@ struct b200rl_onpolicy {
     int64_t N;
     int T, t, ns;
     bool continuous;
+    bool bootstrap_done;   // column T of states / values already written by the fused rollout
     unsigned long long* rng;
     float* states; void* actions; float* logp; float* rewards; uint8_t* terminals; float* values; float* adv; float* ret;
     float* act_clamped;
@@ -415,6 +422,7 @@ int b200rl_onpolicy_plan(b200rl_onpolicy* a, void* actions_host) {
     REQUIRE(a, B200RL_ERR_INVALID, "null agent");
     REQUIRE(a->t < a->T, B200RL_ERR_INVALID, "rollout is full: call b200rl_onpolicy_update first");
     TRY(ctx_bind(a->ctx));
+    a->bootstrap_done = false;
     int64_t N = a->N;
     const float* obs = (const float*)env_field(a->env, B200RL_FIELD_OBS);
     AcHyper hp{a->cfg.clip_range, a->cfg.w_actor, a->cfg.w_critic, a->cfg.w_entropy, a->cfg.min_sigma, a->cfg.max_sigma,
@@ -435,7 +443,8 @@ int b200rl_onpolicy_act(b200rl_onpolicy* a) {
     TRY(ctx_bind(a->ctx));
     char* act_col = (char*)a->actions + (size_t)a->N * a->t * 4;
     if (a->continuous) {  // the env asserts a in -2.0..2.0; the stored (unclamped) action keeps its log-prob
-        clamp_copy_kernel<<<grid_for(a->N, 256), 256, 0, a->ctx->stream>>>(a->act_clamped, (const float*)act_col, a->N, -2.0f, 2.0f);
+        const float bound = b200rl_env_internal_kind(a->env) == B200RL_ENV_PENDULUM ? 2.0f : 1.0f;   // action_space -2.0..2.0 | -1.0..1.0
+        clamp_copy_kernel<<<grid_for(a->N, 256), 256, 0, a->ctx->stream>>>(a->act_clamped, (const float*)act_col, a->N, -bound, bound);
         LAUNCH_CHECK(a->ctx);
         return b200rl_env_step(a->env, a->act_clamped, 1, 1);
     }
@@ -452,6 +461,21 @@ int b200rl_onpolicy_push(b200rl_onpolicy* a) {
 /* n x (plan! -> act! -> push!) without leaving the device */
 int b200rl_onpolicy_collect(b200rl_onpolicy* a, int n_steps) {
     REQUIRE(a && n_steps >= 0, B200RL_ERR_INVALID, "bad argument");
+    if (n_steps > 0 && nn_tc_enabled() && fused_rollout_enabled()) {   // one launch for the whole stretch (fwd_tc.cu)
+        REQUIRE(a->t + n_steps <= a->T, B200RL_ERR_INVALID, "rollout is full: call b200rl_onpolicy_update first");
+        TRY(ctx_bind(a->ctx));
+        AcHyper hp{a->cfg.clip_range, a->cfg.w_actor, a->cfg.w_critic, a->cfg.w_entropy, a->cfg.min_sigma, a->cfg.max_sigma,
+                   a->cfg.normalize_advantage, a->cfg.algo};
+        const int fin = a->t + n_steps == a->T ? 1 : 0;
+        int st = nn_tc_rollout(a->ctx, a->env, a->net->actor, a->net->critic, a->net->params, hp, a->rng, a->t, n_steps, a->T, fin, a->states,
+                               a->actions, a->logp, a->values, a->rewards, a->terminals);
+        if (st == B200RL_OK) {
+            a->t += n_steps;
+            a->bootstrap_done = fin != 0;
+            return B200RL_OK;
+        }
+        if (st != B200RL_ERR_UNSUPPORTED) return st;
+    }
     for (int k = 0; k < n_steps; ++k) {
         TRY(b200rl_onpolicy_plan(a, nullptr));
         TRY(b200rl_onpolicy_act(a));
@@ -483,9 +507,12 @@ int b200rl_onpolicy_update(b200rl_onpolicy* a, const int32_t* perm_host, float* 
     // bootstrap value of the state after the last step
     const float* obs = (const float*)env_field(a->env, B200RL_FIELD_OBS);
     // (a copy kernel, not cudaMemcpyAsync D2D: device-to-device copies are on CUDA's implicit-synchronisation list)
-    copy_f32_kernel<<<grid_for(N * a->ns, 256), 256, 0, ctx->stream>>>(a->states + (size_t)N * a->ns * T, obs, N * a->ns);
-    LAUNCH_CHECK(ctx);
-    TRY(nn_mlp_forward(ctx, n->critic, n->params + n->actor.nparams(), obs, N, a->values + (size_t)N * T));
+    if (!a->bootstrap_done) {   // (the fused rollout has already written column T of states / values)
+        copy_f32_kernel<<<grid_for(N * a->ns, 256), 256, 0, ctx->stream>>>(a->states + (size_t)N * a->ns * T, obs, N * a->ns);
+        LAUNCH_CHECK(ctx);
+        TRY(nn_mlp_forward(ctx, n->critic, n->params + n->actor.nparams(), obs, N, a->values + (size_t)N * T));
+    }
+    a->bootstrap_done = false;
     // GAE + returns + normalisation sums
     int n_part = b200rl_gae_fused_partials_count(N) / 2;
     TRY(b200rl_gae_fused_internal(ctx, a->adv, a->ret, a->rewards, a->values, a->terminals, c.gamma, c.lambda, N, T,

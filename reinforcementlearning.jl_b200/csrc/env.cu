@@ -12,219 +12,14 @@
 #include <type_traits>
 
 #include "common.cuh"
-#include "jl_device.cuh"
+#include "env_device.cuh"
 
 using jld::Xo;
+using namespace envdev;
 
 namespace {
 
 constexpr int kBlock = 256;
-
-struct EnvArrays {
-    void* state;      // (NS, N) T
-    void* obs;        // (NOBS, N) T   (== state when the observation is the state)
-    void* reward;     // (N) T
-    uint8_t* flags;   // (N)  bit0 terminal, bit1 already auto-reset
-    int32_t* t;       // (N)
-    unsigned long long* rng;  // (4, N)
-    void* action;     // (N) int32 | T   last action taken
-    float* ep_ret;    // (N) running episode return
-    double* stats;    // [4] finished episodes, sum return, sum length, env-steps
-    int* err;         // device error flag
-    // optional fused trajectory push targets (column t of the rollout buffers); may be null
-    void* traj_reward;
-    uint8_t* traj_terminal;
-    int max_timeout;  // MaxTimeoutEnv(env, max_t) (wrappers/MaxTimeoutEnv.jl:17-28); 0 = not wrapped
-};
-
-__device__ __forceinline__ Xo load_rng(const unsigned long long* rng, int64_t i) {
-    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(rng + 4 * i);
-    ulonglong2 a = p[0], b = p[1];
-    return Xo{a.x, a.y, b.x, b.y};
-}
-__device__ __forceinline__ void store_rng(unsigned long long* rng, int64_t i, const Xo& g) {
-    ulonglong2* p = reinterpret_cast<ulonglong2*>(rng + 4 * i);
-    p[0] = make_ulonglong2(g.s0, g.s1);
-    p[1] = make_ulonglong2(g.s2, g.s3);
-}
-
-// ------------------------------------------------------------------ CartPole ----------
-// CONT: CartPoleEnv(continuous = true) — ACT = T, action_space -1.0..1.0 (CartPoleEnv.jl:74-79,96,106-110)
-template <class T, bool CONT = false> struct CartPoleD {
-    using real = T;
-    using act_t = typename std::conditional<CONT, T, int32_t>::type;
-    static constexpr int NS = 4, NOBS = 4;
-    static constexpr bool kObsIsState = true;
-    struct P { T g, M, m, l, pml, fmag, dt, ththr, xthr; int max_steps; };
-    struct S { T x, xd, th, thd; };
-    __device__ static S load(const void* st, int64_t i);
-    __device__ static void store(void* st, int64_t i, const S& s);
-    __device__ static bool valid(const P&, act_t a) {
-        if (CONT) return (T)a >= (T)-1 && (T)a <= (T)1;   // a in -1.0..1.0 (NaN fails)
-        return a == 1 || a == 2;
-    }
-    __device__ static unsigned long long n_random(const P&) { return 2; }
-    __device__ static act_t from_index(const P&, long long a) { return (act_t)a; }
-    // reset!: CartPoleEnv.jl:98-104 — rand(rng, T, 4) then rand(rng, Base.OneTo(2))
-    __device__ static void reset(const P&, S& s, Xo& g, act_t& last_action) {
-        T u[4];
-        jld::rand4(g, u);
-        s.x = (T)0.1 * u[0] - (T)0.05;
-        s.xd = (T)0.1 * u[1] - (T)0.05;
-        s.th = (T)0.1 * u[2] - (T)0.05;
-        s.thd = (T)0.1 * u[3] - (T)0.05;
-        // discrete: rand(rng, Base.OneTo(2)); continuous: rand(rng, -1.0..1.0) restated as
-        // -1 + rand(Float64) * 2 (DomainSets sampler, external/unpinned) — one 64-bit output either way
-        if (CONT) last_action = (act_t)(-1.0 + jld::rand_f64(g) * 2.0);
-        else last_action = (act_t)jld::rand_oneto(g, 2);
-    }
-    // _step!: CartPoleEnv.jl:118-140.  `4 / 3` is Float64, so thetaacc, xacc and the two
-    // velocity updates are Float64 for T = Float32; x and theta updates stay in T.
-    __device__ static void step(const P& p, S& s, int& t, act_t a, bool& done, T& reward) {
-        t += 1;
-        T force = CONT ? (T)a * p.fmag : (T)(a == 2 ? 1 : -1) * p.fmag;
-        T c = jld::jcos(s.th), sn = jld::jsin(s.th);
-        T tmp = (force + (p.pml * (s.thd * s.thd)) * sn) / p.M;
-        double den = (double)p.l * (4.0 / 3.0 - (double)((p.m * (c * c)) / p.M));
-        double thacc = (double)(p.g * sn - c * tmp) / den;
-        double xacc = (double)tmp - (((double)p.pml * thacc) * (double)c) / (double)p.M;
-        T nx = s.x + p.dt * s.xd;
-        T nxd = (T)((double)s.xd + (double)p.dt * xacc);
-        T nth = s.th + p.dt * s.thd;
-        T nthd = (T)((double)s.thd + (double)p.dt * thacc);
-        s.x = nx; s.xd = nxd; s.th = nth; s.thd = nthd;
-        done = fabs(nx) > p.xthr || fabs(nth) > p.ththr || t > p.max_steps;
-        reward = done ? (T)0 : (T)1;  // CartPoleEnv.jl:84
-    }
-    __device__ static void write_obs(void*, int64_t, int64_t, const S&) {}
-};
-template <class S> __device__ __forceinline__ S cp_load(const float* st, int64_t i) {
-    float4 v = reinterpret_cast<const float4*>(st)[i];
-    return S{v.x, v.y, v.z, v.w};
-}
-template <class S> __device__ __forceinline__ S cp_load(const double* st, int64_t i) {
-    const double2* p = reinterpret_cast<const double2*>(st) + 2 * i;
-    double2 a = p[0], b = p[1];
-    return S{a.x, a.y, b.x, b.y};
-}
-template <class S> __device__ __forceinline__ void cp_store(float* st, int64_t i, const S& s) {
-    reinterpret_cast<float4*>(st)[i] = make_float4(s.x, s.xd, s.th, s.thd);
-}
-template <class S> __device__ __forceinline__ void cp_store(double* st, int64_t i, const S& s) {
-    double2* p = reinterpret_cast<double2*>(st) + 2 * i;
-    p[0] = make_double2(s.x, s.xd);
-    p[1] = make_double2(s.th, s.thd);
-}
-template <class T, bool CONT> __device__ __forceinline__ typename CartPoleD<T, CONT>::S CartPoleD<T, CONT>::load(const void* st, int64_t i) {
-    return cp_load<S>(reinterpret_cast<const T*>(st), i);
-}
-template <class T, bool CONT> __device__ __forceinline__ void CartPoleD<T, CONT>::store(void* st, int64_t i, const S& s) {
-    cp_store<S>(reinterpret_cast<T*>(st), i, s);
-}
-
-// ------------------------------------------------------------------ Pendulum ----------
-struct PendP { float max_speed, max_torque, g, m, l, dt; int max_steps; int n_actions; };
-template <bool CONT> struct PendulumD {
-    using real = float;
-    using act_t = typename std::conditional<CONT, float, int32_t>::type;
-    static constexpr int NS = 2, NOBS = 3;
-    static constexpr bool kObsIsState = false;
-    using P = PendP;
-    struct S { float th, thd; float torque; };
-    __device__ static S load(const void* st, int64_t i) {
-        float2 v = reinterpret_cast<const float2*>(st)[i];
-        return S{v.x, v.y, 0.f};
-    }
-    __device__ static void store(void* st, int64_t i, const S& s) {
-        reinterpret_cast<float2*>(st)[i] = make_float2(s.th, s.thd);
-    }
-    __device__ static bool valid(const P& p, act_t a) {
-        if (CONT) return (float)a >= -2.0f && (float)a <= 2.0f;   // a in -2.0..2.0 (NaN fails)
-        return (int)a >= 1 && (int)a <= p.n_actions;
-    }
-    __device__ static unsigned long long n_random(const P& p) { return (unsigned long long)p.n_actions; }
-    __device__ static act_t from_index(const P&, long long a) { return (act_t)a; }
-    // reset!: PendulumEnv.jl:84-92 — two scalar rand(rng, Float32); `2 * pi` is Float64
-    __device__ static void reset(const P&, S& s, Xo& g, act_t& last_action) {
-        float u1 = jld::rand_f32(g);
-        s.th = (float)((2 * JLD_PI) * (double)(u1 - 1.0f));
-        float u2 = jld::rand_f32(g);
-        s.thd = 2.0f * (u2 - 1.0f);
-        (void)last_action;  // env.action = zero(T) is the torque field, not the policy action
-    }
-    // act!/_step!: PendulumEnv.jl:94-122
-    __device__ static void step(const P& p, S& s, int& t, act_t a_in, bool& done, float& reward) {
-        float a;
-        if (CONT) {
-            a = (float)a_in;
-        } else {  // torque(env, a::Int) is Float64 arithmetic stored into env.action::T
-            int n1 = p.n_actions - 1;
-            a = (float)((4.0 / (double)n1) * ((double)(int)a_in - (double)n1 / 2 - 1));
-        }
-        t += 1;
-        float th = s.th, thd = s.thd;
-        a = jld::jclamp(a, -p.max_torque, p.max_torque);
-        float thpi = th + (float)JLD_PI;
-        double an = jld::jmod((double)thpi, 2 * JLD_PI) - JLD_PI;   // angle_normalize in Float64
-        double costs = (an * an + 0.1 * (double)(thd * thd)) + 0.001 * (double)(a * a);
-        float nthd = thd + ((((-3.0f * p.g) / (2.0f * p.l)) * jld::jsin(thpi)) + ((3.0f * a) / (p.m * (p.l * p.l)))) * p.dt;
-        th = th + nthd * p.dt;
-        nthd = jld::jclamp(nthd, -p.max_speed, p.max_speed);
-        s.th = th; s.thd = nthd; s.torque = a;
-        done = t >= p.max_steps;
-        reward = (float)(-costs);
-    }
-    // pendulum_observation: PendulumEnv.jl:70
-    __device__ static void write_obs(void* obs, int64_t i, int64_t, const S& s) {
-        float* o = reinterpret_cast<float*>(obs) + 3 * i;
-        o[0] = jld::jsin(s.th); o[1] = jld::jcos(s.th); o[2] = s.thd;
-    }
-};
-
-// ---------------------------------------------------------------- MountainCar ---------
-// CONT: ContinuousMountainCarEnv — Float32 force in -1.0..1.0 (MountainCarEnv.jl:73-74,83,93,107-111)
-template <bool CONT = false> struct MountainCarD {
-    using real = float;
-    using act_t = typename std::conditional<CONT, float, int32_t>::type;
-    static constexpr int NS = 2, NOBS = 2;
-    static constexpr bool kObsIsState = true;
-    struct P { float min_pos, max_pos, max_speed, goal_pos, goal_velocity, power, gravity; int max_steps; };
-    struct S { float x, v; };
-    __device__ static S load(const void* st, int64_t i) {
-        float2 v = reinterpret_cast<const float2*>(st)[i];
-        return S{v.x, v.y};
-    }
-    __device__ static void store(void* st, int64_t i, const S& s) {
-        reinterpret_cast<float2*>(st)[i] = make_float2(s.x, s.v);
-    }
-    __device__ static bool valid(const P&, act_t a) {
-        if (CONT) return (float)a >= -1.0f && (float)a <= 1.0f;
-        return a >= 1 && a <= 3;
-    }
-    __device__ static unsigned long long n_random(const P&) { return 3; }
-    __device__ static act_t from_index(const P&, long long a) { return (act_t)a; }
-    // reset!: MountainCarEnv.jl:99-105 (Float64 literals 0.2, 0.6)
-    __device__ static void reset(const P&, S& s, Xo& g, act_t&) {
-        float u = jld::rand_f32(g);
-        s.x = (float)(0.2 * (double)u - 0.6);
-        s.v = 0.0f;
-    }
-    // _step!: MountainCarEnv.jl:119-135
-    __device__ static void step(const P& p, S& s, int& t, act_t a, bool& done, float& reward) {
-        t += 1;
-        float x = s.x, v = s.v;
-        float force = CONT ? (float)a : (float)((int)a - 2);   // act!(env, a::Int) -> _step!(env, a - 2)
-        v = v + (force * p.power + jld::jcos(3.0f * x) * (-p.gravity));
-        v = jld::jclamp(v, -p.max_speed, p.max_speed);
-        x = x + v;
-        x = jld::jclamp(x, p.min_pos, p.max_pos);
-        if (x == p.min_pos && v < 0) v = 0.0f;
-        done = (x >= p.goal_pos && v >= p.goal_velocity) || t >= p.max_steps;
-        s.x = x; s.v = v;
-        reward = done ? 0.0f : -1.0f;  // MountainCarEnv.jl:95
-    }
-    __device__ static void write_obs(void*, int64_t, int64_t, const S&) {}
-};
 
 // ------------------------------------------------------------------ kernels -----------
 // Block-level accumulation of episode statistics: one atomicAdd triple per CTA that saw a
@@ -679,6 +474,14 @@ int b200rl_env_internal_set_traj_targets(b200rl_env* e, void* reward_col, uint8_
     e->a.traj_terminal = terminal_col;
     return B200RL_OK;
 }
+int b200rl_env_internal_view(b200rl_env* e, envdev::EnvView* out) {
+    REQUIRE(e && out, B200RL_ERR_INVALID, "null argument");
+    out->kind = e->kind; out->dtype = e->dtype; out->continuous = e->continuous ? 1 : 0; out->N = e->N; out->a = e->a;
+    static_assert(sizeof(out->p) == sizeof(e->p), "params union");
+    memcpy(&out->p, &e->p, sizeof out->p);
+    return B200RL_OK;
+}
+void b200rl_env_internal_add_steps(b200rl_env* e, uint64_t n) { e->steps_launched += n; }
 int64_t b200rl_env_internal_n(const b200rl_env* e) { return e->N; }
 int b200rl_env_internal_kind(const b200rl_env* e) { return e->kind; }
 int b200rl_env_internal_nobs(const b200rl_env* e) { return e->nobs; }

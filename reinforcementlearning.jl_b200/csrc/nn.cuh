@@ -73,6 +73,12 @@ bool nn_tc_supported(const MlpDesc& d);
 int nn_tc_forward(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp, int mode,
                   const float* obs, int64_t N, unsigned long long* rng, void* action_out, float* logp_out, float* value_out, float* head_out,
                   float* state_copy);
+// fused rollout (fwd_tc.cu): nsteps x {policy inference, env step, transition push} in one launch; B200RL_ERR_UNSUPPORTED =
+// outside the fused envelope, step through nn_policy_act + b200rl_env_step instead
+struct b200rl_env;
+int nn_tc_rollout(b200rl_ctx* ctx, b200rl_env* env, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
+                  unsigned long long* policy_rng, int t0, int nsteps, int T, int final_bootstrap, float* states, void* actions, float* logp,
+                  float* values, float* rewards, uint8_t* terminals);
 bool nn_tc_bwd_supported(const MlpDesc& actor, const MlpDesc& critic);
 int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
                        const AcBatch& b, float* partial, float* loss_partial, int64_t np);

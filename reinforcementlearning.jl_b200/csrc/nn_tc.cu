@@ -115,184 +115,6 @@ __device__ __forceinline__ unsigned long long xo_next(unsigned long long (&s)[4]
 __device__ __forceinline__ double xo_f64(unsigned long long (&s)[4]) { return (double)(xo_next(s) >> 11) * 0x1p-53; }
 __device__ __forceinline__ float xo_f32(unsigned long long (&s)[4]) { return (float)((unsigned)(xo_next(s) >> 32) >> 8) * 0x1p-24f; }
 
-// Thread <-> data mapping shared by layer 1, the TMEM epilogue and the image stores:
-//   warp w: TMEM lane quadrant q = w % 4 (samples 32q .. 32q+31), column half c = w / 4 (features 32c .. 32c+31)
-//   thread: sample s = 32q + lane, 32 features.
-// mode 0: actor-critic rollout (CTA role = blockIdx & 1), mode 1: plain forward of `actor` -> head_out
-__global__ void __launch_bounds__(NT, 2)
-forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, int mode, const float* __restrict__ obs,
-                  int64_t N, unsigned long long* __restrict__ rng, void* __restrict__ action_out, float* __restrict__ logp_out,
-                  float* __restrict__ value_out, float* __restrict__ head_out, float* __restrict__ state_copy) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];   // keep the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
-    SmemFwd& sm = *reinterpret_cast<SmemFwd*>(smem_raw);
-    const int nroles = mode == 0 ? 2 : 1;
-    const int role = mode == 0 ? (blockIdx.x & 1) : 0;
-    const int cta = blockIdx.x / nroles, nctas = gridDim.x / nroles;
-    const MlpDesc d = role ? critic : actor;
-    const int64_t poff = role ? actor.nparams() : 0;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, c = warp >> 2;
-    const int s = 32 * q + lane;
-    load_small_weights(sm, d, params + poff);
-    if (warp == 0) umma::tmem_alloc(&sm.tmem, 256);   // three 64-column accumulators (independent MMA chains)
-    if (tid == 32) umma::mbar_init(&sm.bar, 1);
-    umma::fence_proxy_async();
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    const uint32_t tmem = sm.tmem;
-    const uint32_t idesc = umma::make_idesc_tf32(128, 64, 0, 0), idesc128 = umma::make_idesc_tf32(128, 128, 0, 0);
-    const int64_t ntiles = (N + TM - 1) / TM;
-    uint32_t phase = 0;
-    for (int64_t tile = cta; tile < ntiles; tile += nctas) {
-        if (tid < TM) {
-            int64_t i = tile * TM + tid;
-            float x[kInMax] = {0.f, 0.f, 0.f, 0.f};
-            if (i < N) {
-                if (d.in == 4) {
-                    float4 v4 = reinterpret_cast<const float4*>(obs)[i];
-                    x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[3] = v4.w;
-                    if (state_copy && role == 0) reinterpret_cast<float4*>(state_copy)[i] = v4;
-                } else {
-                    for (int k = 0; k < d.in; ++k) {
-                        x[k] = obs[(int64_t)d.in * i + k];
-                        if (state_copy && role == 0) state_copy[(int64_t)d.in * i + k] = x[k];
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < kInMax; ++k) sm.X[k * TM + tid] = x[k];
-        }
-        __syncthreads();
-        {   // layer 1 -> H1 operand images (full + lo)
-            float x[kInMax];
-#pragma unroll
-            for (int k = 0; k < kInMax; ++k) x[k] = sm.X[k * TM + s];
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                const int f0 = 32 * c + 4 * ch;
-                float4 bb = *reinterpret_cast<const float4*>(sm.b1 + f0);
-                float h[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                for (int k = 0; k < kInMax; ++k) {
-                    float4 w = *reinterpret_cast<const float4*>(sm.W1 + k * H + f0);
-                    h[0] = fmaf(w.x, x[k], h[0]); h[1] = fmaf(w.y, x[k], h[1]); h[2] = fmaf(w.z, x[k], h[2]); h[3] = fmaf(w.w, x[k], h[3]);
-                }
-                float l[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { h[e] = act_f(d.act, h[e]); l[e] = h[e] - hi_part(h[e]); }
-                const uint32_t off = img_off(s, f0);
-                *reinterpret_cast<float4*>(sm.A_full + off) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(sm.A_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
-            }
-        }
-        umma::fence_proxy_async();     // generic-proxy stores -> visible to the tensor core
-        umma::fence_before_sync();
-        __syncthreads();
-        if (warp == 0) {  // warp 0 issues (one lane) and alone polls the mbarrier; everyone else parks on the CTA barrier
-            if (lane == 0) {
-                umma::fence_after_sync();
-                const uint64_t dAf = umma::make_desc(umma::smem_u32(sm.A_full), G_F, G_S), dAl = umma::make_desc(umma::smem_u32(sm.A_lo), G_F, G_S);
-                const uint64_t dBf = umma::make_desc(umma::smem_u32(sm.B_full), G_F, GW_S), dBl = umma::make_desc(umma::smem_u32(sm.B_lo), G_F, GW_S);
-                uint32_t acc = 0u;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {   // hi*hi, hi*lo, lo*hi into three accumulators, round-robin (see COL_D12 note)
-                    const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                    umma::mma_tf32(tmem, dAf + adv, dBf + adv, idesc128, acc);        // B_full | B_lo adjacent: one N = 128 operand
-                    umma::mma_tf32(tmem + 128, dAl + adv, dBf + adv, idesc, acc);
-                    acc = 1u;
-                }
-                umma::commit(&sm.bar);
-            }
-            __syncwarp();
-            umma::mbar_wait(&sm.bar, phase);
-        }
-        phase ^= 1u;
-        __syncthreads();
-        umma::fence_after_sync();
-        {   // epilogue: H2 = act(D + b2); head partial over this thread's 32 features
-            float v[32];
-            {
-                float v2[32];
-                umma::tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 32 * c, v);
-                umma::tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 64 + 32 * c, v2);
-#pragma unroll
-                for (int k = 0; k < 32; ++k) v[k] += v2[k];
-                umma::tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 128 + 32 * c, v2);
-#pragma unroll
-                for (int k = 0; k < 32; ++k) v[k] += v2[k];
-            }
-            float zp[kOutMax] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const int f = 32 * c + k;
-                float h2 = act_f(d.act, v[k] + sm.b2[f]);
-                float4 w = *reinterpret_cast<const float4*>(sm.W3 + f * kOutMax);
-                zp[0] = fmaf(w.x, h2, zp[0]); zp[1] = fmaf(w.y, h2, zp[1]); zp[2] = fmaf(w.z, h2, zp[2]); zp[3] = fmaf(w.w, h2, zp[3]);
-            }
-#pragma unroll
-            for (int o = 0; o < kOutMax; ++o) sm.Zp[(c * kOutMax + o) * TM + s] = zp[o];
-        }
-        umma::fence_before_sync();     // TMEM reads done before the next tile's MMA overwrites D
-        __syncthreads();
-        if (tid < TM) {
-            int64_t i = tile * TM + tid;
-            if (i < N) {
-                float z[kOutMax];
-#pragma unroll
-                for (int o = 0; o < kOutMax; ++o) z[o] = sm.b3[o] + sm.Zp[o * TM + tid] + sm.Zp[(kOutMax + o) * TM + tid];
-                if (head_out && (mode == 1 || role == 0))
-                    for (int o = 0; o < d.nout; ++o) head_out[(int64_t)d.nout * i + o] = z[o];
-                if (mode == 0 && role == 1) {
-                    if (value_out) value_out[i] = z[0];
-                } else if (mode == 0) {
-                    unsigned long long st[4];
-                    load_rng32(rng, i, st);
-                    if (!actor.heads2) {  // sample_categorical (networks.jl:425-432)
-                        int na = actor.nout;
-                        float lp[kOutMax];
-                        float m = -3.4e38f;
-#pragma unroll
-                        for (int o = 0; o < kOutMax; ++o) if (o < na) m = fmaxf(m, z[o]);
-                        float se = 0.f;
-#pragma unroll
-                        for (int o = 0; o < kOutMax; ++o) if (o < na) se += expf(z[o] - m);
-                        float ls = logf(se);
-                        int best = 0;
-                        double bv = 0.0;
-                        float blp = 0.f;
-#pragma unroll
-                        for (int o = 0; o < kOutMax; ++o) {
-                            if (o < na) {
-                                lp[o] = (z[o] - m) - ls;
-                                double u = xo_f64(st);
-                                double gv = -log(-log(u)) + (double)lp[o];
-                                if (o == 0 || gv > bv) { bv = gv; best = o; blp = lp[o]; }
-                            }
-                        }
-                        if (action_out) reinterpret_cast<int32_t*>(action_out)[i] = best + 1;
-                        if (logp_out) logp_out[i] = blp;
-                    } else {  // GaussianNetwork
-                        float mu = z[0], raw = z[1];
-                        float sigma = fminf(fmaxf(softplus_f(raw), hp.min_sigma), hp.max_sigma);
-                        float u1 = xo_f32(st), u2 = xo_f32(st);
-                        float n = sqrtf(-2.0f * logf(1.0f - u1)) * cosf(6.2831855f * u2);
-                        float a = mu + sigma * n;
-                        if (action_out) reinterpret_cast<float*>(action_out)[i] = a;
-                        if (logp_out) logp_out[i] = normlogpdf1(mu, sigma, a);
-                    }
-                    store_rng32(rng, i, st);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 256);
-}
-
-
 // =====================================================================================================
 // K7 on tensor cores: PPO / A2C loss + backward for one minibatch, all three 64x64 GEMMs on tcgen05.
 //   GEMM1  H2pre[s][o] = sum_i H1[s][i]  W2[o][i]     A = H1 (TMEM, written by tcgen05.st), B = W2 image (smem)
@@ -955,20 +777,6 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
 }
 
 }  // namespace
-
-bool nn_tc_supported(const MlpDesc& d) { return d.H == 64 && d.in <= kInMax && d.nout <= kOutMax; }
-
-int nn_tc_forward(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp, int mode,
-                  const float* obs, int64_t N, unsigned long long* rng, void* action_out, float* logp_out, float* value_out, float* head_out,
-                  float* state_copy) {
-    size_t smem = sizeof(SmemFwd) + 128;
-    static bool attr_set = false;   // once per process: the attribute call is not free and may serialise with running kernels
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-    forward_tc_kernel<<<grid, NT, smem, ctx->stream>>>(actor, critic, params, hp, mode, obs, N, rng, action_out, logp_out, value_out, head_out,
-                                                       state_copy);
-    LAUNCH_CHECK(ctx);
-    return B200RL_OK;
-}
 
 bool nn_tc_bwd_supported(const MlpDesc& actor, const MlpDesc& critic) {
     return actor.H == 64 && critic.H == 64 && actor.in <= kInMax && actor.nout <= 2 && critic.nout == 1;

@@ -165,7 +165,8 @@ class OnPolicyAgent(AbstractPolicy):
         if self.host_actions:
             L.check(self.lib.b200rl_onpolicy_plan(self.h, L.ptr(self._act_buf)))
             if self.continuous:
-                return np.clip(self._act_buf, -2.0, 2.0)  # the env asserts a in -2.0..2.0
+                lo, hi = env.action_space()               # the env asserts a in -2.0..2.0 (Pendulum) | -1.0..1.0
+                return np.clip(self._act_buf, lo, hi)
             return self._act_buf
         L.check(self.lib.b200rl_onpolicy_plan(self.h, None))
         return FusedAction("policy")

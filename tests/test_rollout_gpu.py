@@ -1,0 +1,66 @@
+"""The fused rollout kernel (fwd_tc.cu: policy inference + env step + transition push for a whole stretch of steps in one
+launch) against the step-by-step stage protocol (plan! -> act! -> push!, one launch each): every rollout tensor, the env
+state, both RNG streams and the parameters after the update must be bit-identical, for every env / head combination."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(pkg, ctx, kind, n, T, seed, algo, **envkw):
+    env = pkg.B200VecEnv(ctx, kind, n, O.splitmix_states_fast(n, seed), auto_reset=True, **envkw)
+    n_in = {"CartPole": 4, "ContinuousCartPole": 4, "Pendulum": 3, "MountainCar": 2, "ContinuousMountainCar": 2}[kind]
+    if env.continuous:
+        n_out, net_kind = 1, pkg.KIND_GAUSSIAN
+    else:
+        n_out, net_kind = len(env.action_space()), pkg.KIND_CATEGORICAL
+    desc = O.ac_desc(n_in, 64, n_out, 0, env.continuous)
+    params = O.glorot_params(desc, 77)
+    params = params + 0.05 * np.random.default_rng(3).standard_normal(params.size).astype(np.float32)
+    net = pkg.Network(ctx, n_in, 64, n_out, params, act=0, kind=net_kind)
+    cfg = pkg.onpolicy_config(update_freq=T, n_epochs=2, n_microbatches=2, algo=algo)
+    agent = pkg.OnPolicyAgent(ctx, net, env, cfg, O.splitmix_states_fast(n, seed + 1), host_actions=False)
+    env.reset_(is_force=True)
+    return env, net, agent
+
+
+CASES = [("CartPole", {}, 0, 1000), ("Pendulum", dict(continuous=True), 1, 700), ("Pendulum", dict(continuous=False, n_actions=3), 0, 300),
+         ("MountainCar", {}, 0, 513), ("ContinuousCartPole", {}, 0, 640), ("ContinuousMountainCar", {}, 1, 129),
+         ("CartPole", {}, 0, 40000)]   # 313 tiles: two resident tiles per CTA
+
+
+@pytest.mark.parametrize("kind,envkw,algo,n", CASES)
+def test_fused_rollout_is_bit_identical_to_the_stage_protocol(pkg, ctx, kind, envkw, algo, n):
+    T = 8
+    R = pkg.learners
+    outs = []
+    for fused in (True, False):
+        env, net, agent = _make(pkg, ctx, kind, n, T, 9, algo, **envkw)
+        if kind == "CartPole" and n == 1000:
+            env.set_max_timeout(23)       # MaxTimeoutEnv wrapper inside the fused kernel too
+        for it in range(3):               # three rollouts + updates: episodes end, envs auto-reset, parameters move
+            if fused:
+                agent.collect(3); agent.collect(T - 3)        # a rollout may be filled in several stretches
+            else:
+                for _ in range(T):
+                    agent.plan(env); agent.act_fused(env); agent.push(pkg.PostActStage, env)
+            roll = {f: agent.rollout(f) for f in (R.ROLL_STATE, R.ROLL_ACTION, R.ROLL_LOGP, R.ROLL_REWARD, R.ROLL_TERMINAL, R.ROLL_RNG)}
+            values_T = agent.rollout(R.ROLL_VALUE)[:, :T].copy()
+            stats = agent.update(want_stats=True)
+            roll[R.ROLL_VALUE] = agent.rollout(R.ROLL_VALUE)      # column T (bootstrap) is final only after update()
+            assert np.array_equal(roll[R.ROLL_VALUE][:, :T], values_T)
+        outs.append(dict(roll=roll, params=net.get(), state=env.internal_state(), obs=env.state(), t=env.t(), flags=env.flags(),
+                         erng=env.rng_state(), rew=env.reward(), act=env.last_action(), stats=stats, ep=env.episode_stats()))
+        agent.close(); net.close(); env.close()
+    a, b = outs
+    for f in a["roll"]:
+        assert np.array_equal(a["roll"][f].view(np.uint8), b["roll"][f].view(np.uint8)), f"rollout field {f}"
+    for k in ("params", "state", "obs", "t", "flags", "erng", "rew", "act", "stats"):
+        assert np.array_equal(np.asarray(a[k]).view(np.uint8), np.asarray(b[k]).view(np.uint8)), k
+    assert a["ep"]["episodes"] == b["ep"]["episodes"] and a["ep"]["length_sum"] == b["ep"]["length_sum"]
+    assert a["ep"]["env_steps"] == b["ep"]["env_steps"] == 3 * T * n
+    assert abs(a["ep"]["return_sum"] - b["ep"]["return_sum"]) <= 1e-6 * max(1.0, abs(b["ep"]["return_sum"]))
+    if kind in ("CartPole", "ContinuousCartPole"):
+        assert a["ep"]["episodes"] > 0
