@@ -26,9 +26,9 @@ def _make(pkg, ctx, kind, n, T, seed, algo, **envkw):
     return env, net, agent
 
 
-CASES = [("CartPole", {}, 0, 1000), ("Pendulum", dict(continuous=True), 1, 700), ("Pendulum", dict(continuous=False, n_actions=3), 0, 300),
-         ("MountainCar", {}, 0, 513), ("ContinuousCartPole", {}, 0, 640), ("ContinuousMountainCar", {}, 1, 129),
-         ("CartPole", {}, 0, 40000)]   # 313 tiles: two resident tiles per CTA
+CASES = [("CartPole", {}, "ppo", 1000), ("Pendulum", dict(continuous=True), "a2c", 700), ("Pendulum", dict(continuous=False, n_actions=3), "ppo", 300),
+         ("MountainCar", {}, "ppo", 513), ("ContinuousCartPole", {}, "ppo", 640), ("ContinuousMountainCar", {}, "a2c", 129),
+         ("CartPole", {}, "ppo", 40000)]   # 313 tiles: two resident tiles per CTA
 
 
 @pytest.mark.parametrize("kind,envkw,algo,n", CASES)
@@ -45,20 +45,25 @@ def test_fused_rollout_is_bit_identical_to_the_stage_protocol(pkg, ctx, kind, en
                 agent.collect(3); agent.collect(T - 3)        # a rollout may be filled in several stretches
             else:
                 for _ in range(T):
-                    agent.plan(env); agent.act_fused(env); agent.push(pkg.PostActStage, env)
-            roll = {f: agent.rollout(f) for f in (R.ROLL_STATE, R.ROLL_ACTION, R.ROLL_LOGP, R.ROLL_REWARD, R.ROLL_TERMINAL, R.ROLL_RNG)}
+                    agent.plan(env); agent.act_fused(env); agent.push(pkg.core.PostActStage, env)
+            roll = {f: agent.rollout(f) for f in (R.ROLL_ACTION, R.ROLL_LOGP, R.ROLL_REWARD, R.ROLL_TERMINAL, R.ROLL_RNG)}
             values_T = agent.rollout(R.ROLL_VALUE)[:, :T].copy()
             stats = agent.update(want_stats=True)
-            roll[R.ROLL_VALUE] = agent.rollout(R.ROLL_VALUE)      # column T (bootstrap) is final only after update()
+            roll[R.ROLL_VALUE] = agent.rollout(R.ROLL_VALUE)      # column T (bootstrap state / value) is final only after update()
+            roll[R.ROLL_STATE] = agent.rollout(R.ROLL_STATE)
             assert np.array_equal(roll[R.ROLL_VALUE][:, :T], values_T)
         outs.append(dict(roll=roll, params=net.get(), state=env.internal_state(), obs=env.state(), t=env.t(), flags=env.flags(),
                          erng=env.rng_state(), rew=env.reward(), act=env.last_action(), stats=stats, ep=env.episode_stats()))
         agent.close(); net.close(); env.close()
     a, b = outs
+
+    def same(x, y):   # bitwise, whatever the memory order (rollout tensors are Fortran-ordered)
+        x, y = np.asarray(x), np.asarray(y)
+        return x.shape == y.shape and x.dtype == y.dtype and x.tobytes(order="A") == y.tobytes(order="A")
     for f in a["roll"]:
-        assert np.array_equal(a["roll"][f].view(np.uint8), b["roll"][f].view(np.uint8)), f"rollout field {f}"
+        assert same(a["roll"][f], b["roll"][f]), f"rollout field {f}"
     for k in ("params", "state", "obs", "t", "flags", "erng", "rew", "act", "stats"):
-        assert np.array_equal(np.asarray(a[k]).view(np.uint8), np.asarray(b[k]).view(np.uint8)), k
+        assert same(a[k], b[k]), k
     assert a["ep"]["episodes"] == b["ep"]["episodes"] and a["ep"]["length_sum"] == b["ep"]["length_sum"]
     assert a["ep"]["env_steps"] == b["ep"]["env_steps"] == 3 * T * n
     assert abs(a["ep"]["return_sum"] - b["ep"]["return_sum"]) <= 1e-6 * max(1.0, abs(b["ep"]["return_sum"]))
