@@ -1,57 +1,42 @@
-"""Pin the CPU oracle's GAE / discounted-return restatement to the reference's own golden
-vectors: /root/reference/src/ReinforcementLearningCore/test/utils/base.jl:22-152 (values
-copied from the assertions there; `≈` is isapprox with rtol = sqrt(eps))."""
+"""Pin the CPU oracle's GAE / discounted-return restatement to the reference's own golden vectors:
+tests/golden/returns_reference_vectors.json, transcribed (tests/golden/make_returns_vectors.py) from the assertions of
+/root/reference/src/ReinforcementLearningCore/test/utils/base.jl:22-152; `≈` there is isapprox with rtol = sqrt(eps)."""
+import json
+import os
+
 import numpy as np
 import pytest
 
 RT = 1.5e-8
+_G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "returns_reference_vectors.json")))
 
 
-def F(x):  # Julia column-major matrix literal written row by row
-    return np.array(x, dtype=np.float64)
+def _arr(x):
+    if isinstance(x, dict):   # reshape(1:n, r, c): Julia column-major
+        return np.arange(1, x["reshape_1_to"] + 1, dtype=np.float64).reshape(*x["shape"], order="F")
+    return x
 
 
-R9 = np.arange(1, 10, dtype=np.float64).reshape(3, 3, order="F")     # reshape(1:9, 3, 3)
-V43 = np.arange(1, 13, dtype=np.float64).reshape(4, 3, order="F")    # reshape(1:12, 4, 3)
-V34 = np.arange(1, 13, dtype=np.float64).reshape(3, 4, order="F")    # reshape(1:12, 3, 4)
-TERM = np.array([[0, 1, 0], [1, 0, 1], [0, 1, 0]], dtype=np.uint8)
-INIT = [-2.0, 0.0, 2.0]
+def _kw(c):
+    kw = {}
+    for k in ("init", "dims"):
+        if k in c:
+            kw[k] = c[k]
+    if "terminal" in c:
+        t = c["terminal"]
+        kw["terminal"] = np.array(t, dtype=np.uint8) if isinstance(t[0], list) else t
+    return kw
 
-DISCOUNT_CASES = [  # (rewards, gamma, kwargs, expected)   base.jl:22-62
-    ([1.0], 0.5, {}, [1.0]),
-    ([1.0], 0.5, dict(init=2.0), [2.0]),
-    ([1, 2, 3], 0.5, {}, [2.75, 3.5, 3.0]),
-    ([1, 2, 3], 0.5, dict(init=4.0), [3.25, 4.5, 5.0]),
-    ([1, 2, 3], 0.5, dict(terminal=[0, 1, 0], init=2.0), [2.0, 2.0, 4.0]),
-    ([1, 2, 3], 0.5, dict(terminal=[1, 0, 1], init=2.0), [1.0, 3.5, 3.0]),
-    (R9, 0.5, dict(dims=1), F([[2.75, 8.0, 13.25], [3.5, 8.0, 12.5], [3.0, 6.0, 9.0]])),
-    (R9, 0.5, dict(dims=2), F([[4.75, 7.5, 7.0], [6.5, 9.0, 8.0], [8.25, 10.5, 9.0]])),
-    (R9, 0.5, dict(init=INIT, dims=1), F([[2.5, 8.0, 13.5], [3.0, 8.0, 13.0], [2.0, 6.0, 10.0]])),
-    (R9, 0.5, dict(init=INIT, dims=2), F([[4.5, 7.0, 6.0], [6.5, 9.0, 8.0], [8.5, 11.0, 10]])),
-    (R9, 0.5, dict(dims=1, terminal=TERM), F([[2.0, 4.0, 11.0], [2.0, 8.0, 8.0], [3.0, 6.0, 9.0]])),
-    (R9, 0.5, dict(dims=1, terminal=TERM, init=INIT), F([[2.0, 4.0, 11.0], [2.0, 8.0, 8.0], [2.0, 6.0, 10.0]])),
-    (R9, 0.5, dict(dims=2, terminal=TERM, init=INIT), F([[3.0, 4.0, 6.0], [2.0, 9.0, 8.0], [6.0, 6.0, 10.0]])),
-]
-REDUCED_CASES = [  # base.jl:64-102
-    ([1.0], 0.5, {}, 1.0),
-    ([1, 2, 3], 0.5, {}, 2.75),
-    ([1, 2, 3], 0.5, dict(init=4.0), 3.25),
-    ([1, 2, 3], 0.5, dict(terminal=[0, 1, 0]), 2.0),
-    ([1, 2, 3], 0.5, dict(terminal=[0, 1, 0], init=4.0), 2.0),
-    (R9, 0.5, dict(dims=1), [2.75, 8.0, 13.25]),
-    (R9, 0.5, dict(dims=2), [4.75, 6.5, 8.25]),
-    (R9, 0.5, dict(dims=1, terminal=TERM, init=INIT), [2.0, 4.0, 11.0]),
-    (R9, 0.5, dict(dims=2, terminal=TERM, init=INIT), [3.0, 2.0, 6.0]),
-]
-GAE_CASES = [  # (rewards, values, gamma, lambda, kwargs, expected)   base.jl:104-152
-    ([1.0], [2.0, 3.0], 0.5, 0.3, {}, [0.5]),
-    ([1.0, 1.0], [1, 2, 3], 0.5, 0.3, {}, [1.075, 0.5]),
-    ([1, 2, 3], [1, 2, 3, 4], 0.5, 0.3, {}, [1.27, 1.8, 2]),
-    ([1, 2, 3], [1, 2, 3, 4], 0.5, 0.3, dict(terminal=[1, 0, 1]), [0.0, 1.5, 0.0]),
-    (R9, V43, 0.5, 0.3, dict(dims=1), F([[1.27, 2.4425, 3.615], [1.8, 2.95, 4.1], [2.0, 3.0, 4.0]])),
-    (R9, V34, 0.5, 0.3, dict(dims=2), F([[2.6375, 4.25, 5.0], [3.22375, 4.825, 5.5], [3.81, 5.4, 6.0]])),
-    (R9, V43, 0.5, 0.3, dict(dims=1, terminal=TERM), F([[1.0, -1.0, 2.7], [0.0, 2.35, -2.0], [2.0, -1.0, 4.0]])),
-]
+
+def _exp(e):
+    return np.array(e, dtype=np.float64) if isinstance(e, list) and e and isinstance(e[0], list) else e
+
+
+DISCOUNT_CASES = [(_arr(c["rewards"]), c["gamma"], _kw(c), _exp(c["expected"])) for c in _G["discount_rewards"]]
+REDUCED_CASES = [(_arr(c["rewards"]), c["gamma"], _kw(c), _exp(c["expected"])) for c in _G["discount_rewards_reduced"]]
+GAE_CASES = [(_arr(c["rewards"]), _arr(c["values"]), c["gamma"], c["lambda"], _kw(c), _exp(c["expected"]))
+             for c in _G["generalized_advantage_estimation"]]
+ENV_KAT = _G["env_known_answers"]
 
 
 @pytest.mark.parametrize("r,g,kw,exp", DISCOUNT_CASES)
