@@ -20,6 +20,7 @@ module B200RL
 using Random
 import ReinforcementLearningBase as RLBase
 import ReinforcementLearningCore as RLCore
+import ReinforcementLearningEnvironments as RLEnvs
 using ReinforcementLearningBase: AbstractEnv, AbstractPolicy, Observation, DefaultPlayer
 using ReinforcementLearningCore: AbstractStage, PreExperimentStage, PostExperimentStage, PreActStage, PostActStage,
     AbstractStopCondition, AbstractHook, AbstractResetCondition, ResetIfEnvTerminated, StopAfterNEpisodes
@@ -60,9 +61,10 @@ end
 #   CartPoleParamsC(p.gravity, p.masscart, p.masspole, p.totalmass, p.halflength, p.polemasslength,
 #                   p.forcemag, p.dt, p.thetathreshold, p.xthreshold, p.max_steps)
 
-const KINDS = Dict(:CartPole => 0, :Pendulum => 1, :MountainCar => 2)
-const NS = Dict(0 => 4, 1 => 2, 2 => 2)
-const NOBS = Dict(0 => 4, 1 => 3, 2 => 2)
+# 3 / 4: CartPoleEnv(continuous = true) / ContinuousMountainCarEnv (CartPoleEnv.jl:74-79, MountainCarEnv.jl:83), Float32 actions in -1.0..1.0
+const KINDS = Dict(:CartPole => 0, :Pendulum => 1, :MountainCar => 2, :ContinuousCartPole => 3, :ContinuousMountainCar => 4)
+const NS = Dict(0 => 4, 1 => 2, 2 => 2, 3 => 4, 4 => 2)
+const NOBS = Dict(0 => 4, 1 => 3, 2 => 2, 3 => 4, 4 => 2)
 @enum Field STATE = 0 OBS = 1 REWARD = 2 TERMINAL = 3 TSTEP = 4 RNG = 5 FLAGS = 6 ACTION = 7
 
 """
@@ -85,7 +87,7 @@ mutable struct B200VecEnv{T} <: AbstractEnv
 end
 
 function B200VecEnv(ctx::B200Context, kind::Symbol, n::Integer; T = Float32, seeds::AbstractVector{Xoshiro},
-                    auto_reset::Bool = true, params = C_NULL, continuous::Bool = (kind == :Pendulum))
+                    auto_reset::Bool = true, params = C_NULL, continuous::Bool = (kind in (:Pendulum, :ContinuousCartPole, :ContinuousMountainCar)))
     length(seeds) == n || throw(ArgumentError("need one Xoshiro per env"))
     k = KINDS[kind]
     st = raw_states(seeds)
@@ -95,6 +97,17 @@ function B200VecEnv(ctx::B200Context, kind::Symbol, n::Integer; T = Float32, see
         ctx.h, k, T === Float64 ? 1 : 0, n, params === C_NULL ? C_NULL : pointer_from_objref(params), st, out))
     env = B200VecEnv{T}(ctx, out[], k, n, auto_reset, continuous, zeros(T, NOBS[k], n), zeros(T, n), zeros(UInt8, n))
     finalizer(e -> (e.h == C_NULL || ccall((:b200rl_env_destroy, LIB), Cint, (Ptr{Cvoid},), e.h); e.h = C_NULL), env)
+end
+
+"""
+    MaxTimeoutEnv(env::B200VecEnv, max_t)
+
+The reference wrapper (wrappers/MaxTimeoutEnv.jl:17-28) as a flag on the batched env: `is_terminated` also fires once an
+episode has taken `max_t` interactions; `reward` still forwards to the wrapped env.  Returns `env`.
+"""
+function RLEnvs.MaxTimeoutEnv(env::B200VecEnv, max_t::Integer)
+    check(ccall((:b200rl_env_set_max_timeout, LIB), Cint, (Ptr{Cvoid}, Int64), env.h, max_t))
+    env
 end
 
 function fetch!(env::B200VecEnv, field::Field, dst::Array)
@@ -265,6 +278,36 @@ function generalized_advantage_estimation(ctx::B200Context, rewards::Matrix{T}, 
         end
     end
     adv
+end
+
+# ---- sharded runs: one process per GPU (SURVEY §8e) ------------------------------------------------
+"""
+    comm_init(ctx, nranks, rank, id128)          # id128 from `comm_unique_id()` on rank 0, shipped by the launcher (MPI, Distributed, a file)
+    attach_peer_exchange(ctx, nranks, rank, allgather)
+
+`allgather(bytes::Vector{UInt8})::Vector{Vector{UInt8}}` is any host-side all-gather in rank order; it ships the 64-byte CUDA IPC
+handles once.  Afterwards the gradient all-reduce runs inside the optimiser kernel over NVLink peer memory.
+"""
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    GC.@preserve id check(ccall((:b200rl_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    id
+end
+comm_init(ctx::B200Context, nranks::Integer, rank::Integer, id::Vector{UInt8}) =
+    GC.@preserve id check(ccall((:b200rl_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx.h, nranks, rank, id))
+function attach_peer_exchange(ctx::B200Context, nranks::Integer, rank::Integer, allgather)
+    handle = zeros(UInt8, 64)
+    GC.@preserve handle check(ccall((:b200rl_comm_p2p_export, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Ptr{Cvoid}}), ctx.h, handle, C_NULL))
+    handles = allgather(handle)
+    regions = fill(C_NULL, nranks)
+    for r in 0:nranks-1
+        r == rank && continue
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        h = handles[r+1]
+        GC.@preserve h check(ccall((:b200rl_comm_p2p_open, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ref{Ptr{Cvoid}}), ctx.h, h, out))
+        regions[r+1] = out[]
+    end
+    GC.@preserve regions check(ccall((:b200rl_comm_p2p_attach, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), ctx.h, regions))
 end
 
 end # module
