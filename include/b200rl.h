@@ -129,7 +129,10 @@ int b200rl_env_reset(b200rl_env* env, int force_all);
  * PendulumEnv.jl:94-118, MountainCarEnv.jl:113-135).  actions: int32 (N,) 1-based for
  * discrete spaces, T (N,) for Pendulum continuous.  auto_reset != 0 fuses the soft reset of
  * envs that just terminated into the same launch (reward/terminal keep the terminating
- * step's values; state/obs become the fresh episode's). */
+ * step's values; state/obs become the fresh episode's).
+ * actions_on_device: 0 = host buffer borrowed for the call (synchronises before returning), 1 = device pointer,
+ * 2 = PINNED host buffer (b200rl_host_alloc) the caller leaves untouched until its next synchronising call on this
+ *     ctx — the copy is only stream-ordered, the call does not wait (the per-step action hand-off of the stage protocol). */
 int b200rl_env_step(b200rl_env* env, const void* actions, int actions_on_device, int auto_reset);
 /* plan!(RandomPolicy(), env) + act!(env, a) fused (RLCore/src/policies/random_policy.jl:29-32):
  * the action is drawn from each env's own Xoshiro stream with rand(rng, Base.OneTo(n)),

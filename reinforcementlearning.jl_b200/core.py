@@ -25,7 +25,7 @@ class AbstractHook:
 
 
 class EmptyHook(AbstractHook):
-    pass
+    per_step = False
 
 
 class ComposedHook(AbstractHook):
@@ -76,6 +76,7 @@ class TotalBatchRewardPerEpisode(AbstractHook):
 class DeviceEpisodeStats(AbstractHook):
     """Device-side reduction of the two hooks above: no per-step D2H copy; reads
     four numbers at the end of the experiment."""
+    per_step = False   # nothing happens at the Pre/PostAct stages: run() may execute many env steps per launch
 
     def __init__(self):
         self.stats = None
@@ -122,6 +123,15 @@ class StopAfterNSteps:
 
     def __init__(self, step, cur=1):
         self.step, self.cur = step, cur
+
+    def remaining(self):
+        """loop iterations left before check() returns true"""
+        return max(1, self.step - self.cur + 1)
+
+    def advance(self, n):
+        """n loop iterations at once (the fused rollout): true when the n-th of them would have stopped the loop"""
+        self.cur += n
+        return self.cur > self.step
 
     def check(self, policy, env):
         res = self.cur >= self.step
@@ -196,6 +206,18 @@ def run(policy, env, stop_condition=None, hook=None):
     policy.push(PreExperimentStage, env)
     env.reset_(is_force=True)  # run.jl:46
     is_stop = False
+    # Fused fast path: a device-resident agent (actions never visit the host), a hook that does nothing per step and a
+    # step-count stop condition let whole stretches of the loop below run as ONE kernel launch (agent.collect(n): n x
+    # {plan!, act!, push!}) — the same transitions, parameters and statistics as stepping through the stages.
+    if (getattr(policy, "fusable", False) and env.auto_reset and not getattr(hook, "per_step", True)
+            and isinstance(stop_condition, StopAfterNSteps)):
+        while not is_stop:
+            n = min(policy.T - policy._t, stop_condition.remaining())
+            policy.collect(n)
+            if policy._t == policy.T:
+                policy._t = 0
+                policy.update(want_stats=policy.fetch_stats)
+            is_stop = stop_condition.advance(n)
     while not is_stop:
         if not env.auto_reset:
             env.reset_(is_force=False)  # soft reset of finished sub-envs

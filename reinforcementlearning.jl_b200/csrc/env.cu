@@ -377,7 +377,7 @@ int b200rl_env_step(b200rl_env* e, const void* actions, int actions_on_device, i
     REQUIRE(e && actions, B200RL_ERR_INVALID, "null argument");
     TRY(ctx_bind(e->ctx));
     const void* dact = actions;
-    if (!actions_on_device) {
+    if (actions_on_device != 1) {   // 0: pageable / borrowed host buffer, 2: pinned host buffer that stays untouched until the next sync
         void* stage;
         TRY(ctx_scratch(e->ctx, (size_t)e->N * 4, &stage));
         CUDA_TRY(cudaMemcpyAsync(stage, actions, (size_t)e->N * 4, cudaMemcpyHostToDevice, e->ctx->stream));
@@ -385,7 +385,7 @@ int b200rl_env_step(b200rl_env* e, const void* actions, int actions_on_device, i
     }
     e->steps_launched += 1;
     TRY(dispatch_step(e, dact, false, auto_reset != 0));
-    if (!actions_on_device) CUDA_TRY(cudaStreamSynchronize(e->ctx->stream));  // host buffer is borrowed for this call only
+    if (actions_on_device == 0) CUDA_TRY(cudaStreamSynchronize(e->ctx->stream));  // host buffer is borrowed for this call only
     return B200RL_OK;
 }
 

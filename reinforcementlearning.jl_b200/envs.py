@@ -106,7 +106,10 @@ class B200VecEnv:
             a = np.ascontiguousarray(actions, dtype=np.float32 if self.continuous else np.int32)
             if a.shape != (self.n,):
                 raise ValueError(f"expected {self.n} actions, got shape {a.shape}")
-            L.check(self.lib.b200rl_env_step(self.h, L.ptr(a), 0, int(self.auto_reset)))
+            # the agent's own pinned action buffer (returned by plan!): stream-ordered copy, no host sync — the next plan!
+            # rewrites it with a D2H copy that is ordered behind this H2D copy on the same stream
+            pinned = a.ctypes.data == getattr(self, "pinned_action_addr", None)
+            L.check(self.lib.b200rl_env_step(self.h, L.ptr(a), 2 if pinned else 0, int(self.auto_reset)))
 
     def set_max_timeout(self, max_t):
         """MaxTimeoutEnv(env, max_t) (wrappers/MaxTimeoutEnv.jl:17-28); 0 removes the wrapper."""

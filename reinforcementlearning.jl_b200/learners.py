@@ -130,6 +130,7 @@ class OnPolicyAgent(AbstractPolicy):
         self.ctx, self.lib, self.net, self.env, self.cfg = ctx, ctx.lib, net, env, cfg
         self.n, self.T = env.n, cfg.update_freq
         self.host_actions = host_actions
+        self.fusable = not host_actions     # run() may hand whole stretches of env steps to collect()
         policy_rng = np.ascontiguousarray(policy_rng, np.uint64).reshape(self.n, 4)
         h = C.c_void_p()
         L.check(self.lib.b200rl_onpolicy_create(ctx.h, net.h, env.h, C.byref(cfg), L.ptr(policy_rng), C.byref(h)))
@@ -137,6 +138,7 @@ class OnPolicyAgent(AbstractPolicy):
         self.continuous = env.continuous
         # pinned host buffer for the per-step action round trip of the stage protocol
         self._act_buf, self._act_buf_addr = ctx.host_alloc((self.n,), np.float32 if self.continuous else np.int32)
+        env.pinned_action_addr = self._act_buf.ctypes.data
         self.last_stats = None
         self.n_updates = 0
         self.fetch_stats = False   # read the per-minibatch losses back after every update (a sync)
