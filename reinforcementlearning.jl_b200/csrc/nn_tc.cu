@@ -541,8 +541,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         float h2[16];
         {
             float v[16], v2[16];
-            umma::tmem_ld16(tmem + lane_base + COL_R1 + 16 * c, v);
-            umma::tmem_ld16(tmem + lane_base + COL_R1 + 64 + 16 * c, v2);
+            umma::tmem_ld16x2(tmem + lane_base + COL_R1 + 16 * c, tmem + lane_base + COL_R1 + 64 + 16 * c, v, v2);
             float zp[kOutMax] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -600,8 +599,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 *reinterpret_cast<float*>(sm.FP_lo + off) = lo[k];
             }
             // H1 of this tile (full | lo) back from its TMEM operand -> H1^T image
-            umma::tmem_ld16(tmem + lane_base + COL_AH + 16 * c, dp);
-            umma::tmem_ld16(tmem + lane_base + COL_AH + 64 + 16 * c, lo);
+            umma::tmem_ld16x2(tmem + lane_base + COL_AH + 16 * c, tmem + lane_base + COL_AH + 64 + 16 * c, dp, lo);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const uint32_t off = fimg_off(16 * c + k, s);
@@ -657,8 +655,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             float v[16];
             {
                 float v2[16];
-                umma::tmem_ld16(tmem + lane_base + COL_D2 + 16 * c, v);
-                umma::tmem_ld16(tmem + lane_base + COL_D2 + 64 + 16 * c, v2);
+                umma::tmem_ld16x2(tmem + lane_base + COL_D2 + 16 * c, tmem + lane_base + COL_D2 + 64 + 16 * c, v, v2);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) v[k] += v2[k];
             }

@@ -132,8 +132,7 @@ __device__ __forceinline__ void head_partials(const NetSm& w, int act, int c, ui
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         float v[16], v2[16];
-        umma::tmem_ld16(tmem_lane + COL_D + 32 * c + 16 * half, v);
-        umma::tmem_ld16(tmem_lane + COL_D + 64 + 32 * c + 16 * half, v2);
+        umma::tmem_ld16x2(tmem_lane + COL_D + 32 * c + 16 * half, tmem_lane + COL_D + 64 + 32 * c + 16 * half, v, v2);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int f = 32 * c + 16 * half + k;
