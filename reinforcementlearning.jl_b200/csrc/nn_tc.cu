@@ -1,13 +1,13 @@
-// nn_tc.cu — tensor-core (tcgen05 / TMEM) variants of the learner kernels for H = 64.
+// nn_tc.cu — K7 on tensor cores (tcgen05 / TMEM): PPO / A2C loss + backward for H = 64.
 //
-// The 64 x 64 layer is a [128 samples x 64] x [64 x 64] GEMM per tile: one elected thread issues
-// tcgen05.mma kind::tf32 with operands in shared memory (SWIZZLE_NONE canonical layout, see
-// umma.cuh) and the FP32 accumulator in TMEM; the epilogue warps pull it back with tcgen05.ld.
-// Parity needs ~FP32 accuracy (1e-5 relative on losses), which plain TF32 (10-bit mantissa,
-// measured 7.8e-4 relative on this GEMM) cannot give, so every product is the 3xTF32 split
+// The 64 x 64 layers are [128 samples x 64] x [64 x 64] GEMMs per tile: elected threads issue tcgen05.mma kind::tf32
+// (SWIZZLE_NONE canonical layout, see umma.cuh) with the FP32 accumulators in TMEM; the worker warps pull them back
+// with tcgen05.ld.  Parity needs ~FP32 accuracy (1e-5 relative on losses), which plain TF32 (10-bit mantissa, measured
+// 7.8e-4 relative on this GEMM) cannot give, so every product is the 3xTF32 split
 //     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi,   x_hi = x with the low 13 mantissa bits cleared
-// (the hardware ignores those bits, so the FULL fp32 image doubles as the hi operand) — measured
-// 5e-7 relative (profiles/umma_probe.py).  Layer 1 (K <= 4) and the heads (N <= 4) stay on FFMA.
+// (the hardware ignores those bits, so the FULL fp32 image doubles as the hi operand) — measured 5e-7 relative
+// (profiles/umma_probe.py).  Layer 1 (K <= 4) and the heads (N <= 4) stay on FFMA.  The forward-only kernels (policy
+// inference, fused rollout) live in fwd_tc.cu.
 #include "nn.cuh"
 #include "perm.cuh"
 #include "umma.cuh"
@@ -18,26 +18,9 @@ constexpr int NT = 256;
 constexpr int TM = 128;              // samples per tile = UMMA M
 constexpr int H = 64;
 constexpr int G_F = 128;             // byte stride between 4-feature chunks (K direction)
-constexpr int G_S = 16 * G_F + 16;   // byte stride between 8-sample groups (+16: bank spread)
-constexpr int IMG_BYTES = 16 * G_S;  // one [128 x 64] activation image
 constexpr int GW_S = 16 * G_F;       // weight image: stride between 8-row groups
 constexpr int WIMG_BYTES = 8 * GW_S; // one [64 x 64] weight image
 constexpr float kLog2Pi = 1.8378770664093453f;
-
-struct SmemFwd {
-    alignas(128) uint8_t A_full[IMG_BYTES];   // H1 (fp32; the tensor core reads its tf32 prefix = hi part)
-    alignas(128) uint8_t A_lo[IMG_BYTES];     // H1 - hi(H1)
-    alignas(128) uint8_t B_full[WIMG_BYTES];  // W2 as (n = out, k = in), K-major
-    alignas(128) uint8_t B_lo[WIMG_BYTES];
-    float W1[kInMax * H];                      // [i][o]
-    float b1[H], b2[H];
-    float W3[H * kOutMax];                     // [j][o]
-    float b3[kOutMax];
-    float X[kInMax * TM];                      // [i][s]
-    float Zp[2 * kOutMax * TM];                // head partials [half][o][s]
-    alignas(8) uint64_t bar;
-    uint32_t tmem;
-};
 
 __device__ __forceinline__ float act_f(int act, float z) { return act == B200RL_ACT_RELU ? fmaxf(z, 0.f) : tanhf(z); }
 __device__ __forceinline__ float hi_part(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
@@ -53,67 +36,7 @@ __device__ __forceinline__ int64_t head_w(const MlpDesc& d, int o, int j) {
 __device__ __forceinline__ int64_t head_b(const MlpDesc& d, int o) {
     return head_base(d) + (d.heads2 ? (int64_t)o * (d.H + 1) + d.H : (int64_t)d.nout * d.H + o);
 }
-__device__ __forceinline__ uint32_t img_off(int s, int f) {  // byte offset of (sample s, feature f)
-    return (uint32_t)((s >> 3) * G_S + (f >> 2) * G_F + (s & 7) * 16 + (f & 3) * 4);
-}
 __device__ __forceinline__ uint32_t wimg_off(int n, int k) { return (uint32_t)((n >> 3) * GW_S + (k >> 2) * G_F + (n & 7) * 16 + (k & 3) * 4); }
-
-template <class S> __device__ void load_small_weights(S& sm, const MlpDesc& d, const float* __restrict__ p) {
-    const int tid = threadIdx.x;
-    const float* b1 = p + (int64_t)H * d.in;
-    const float* W2 = b1 + H;
-    const float* b2 = W2 + (int64_t)H * H;
-    for (int k = tid; k < kInMax * H; k += NT) sm.W1[k] = (k / H) < d.in ? p[k] : 0.f;
-    for (int k = tid; k < H; k += NT) { sm.b1[k] = b1[k]; sm.b2[k] = b2[k]; }
-    for (int k = tid; k < H * kOutMax; k += NT) {
-        int j = k / kOutMax, o = k % kOutMax;
-        sm.W3[k] = o < d.nout ? p[head_w(d, o, j)] : 0.f;
-    }
-    if (tid < kOutMax) sm.b3[tid] = tid < d.nout ? p[head_b(d, tid)] : 0.f;
-    for (int k = tid; k < H * H; k += NT) {  // W2[o + H*i]: B operand of H2pre[s][o] = sum_i H1[s][i] W2[o][i]
-        int o = k % H, i = k / H;
-        float w = W2[k], wh = hi_part(w);
-        *reinterpret_cast<float*>(sm.B_full + wimg_off(o, i)) = w;
-        *reinterpret_cast<float*>(sm.B_lo + wimg_off(o, i)) = w - wh;
-    }
-}
-
-// one elected thread: D[128 x 64] (+)= A x B^T as hi*hi + hi*lo + lo*hi, K = 64 in 8 steps of 8
-__device__ __forceinline__ void issue_gemm_3x(uint32_t d_tmem, const uint8_t* a_full, const uint8_t* a_lo, uint32_t a_lbo, uint32_t a_sbo,
-                                              uint32_t a_kadv, const uint8_t* b_full, const uint8_t* b_lo, uint32_t b_lbo, uint32_t b_sbo,
-                                              uint32_t b_kadv, uint32_t idesc, int ksteps, bool accumulate_first) {
-    const uint32_t af = umma::smem_u32(a_full), al = umma::smem_u32(a_lo), bf = umma::smem_u32(b_full), bl = umma::smem_u32(b_lo);
-    uint32_t acc = accumulate_first ? 1u : 0u;
-    for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = pass == 2 ? al : af;
-        const uint32_t b = pass == 1 ? bl : bf;
-        for (int k = 0; k < ksteps; ++k) {
-            umma::mma_tf32(d_tmem, umma::make_desc(a + k * a_kadv, a_lbo, a_sbo), umma::make_desc(b + k * b_kadv, b_lbo, b_sbo), idesc, acc);
-            acc = 1u;
-        }
-    }
-}
-
-__device__ __forceinline__ void load_rng32(const unsigned long long* rng, int64_t i, unsigned long long (&s)[4]) {
-    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(rng + 4 * i);
-    ulonglong2 a = p[0], b = p[1];
-    s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y;
-}
-__device__ __forceinline__ void store_rng32(unsigned long long* rng, int64_t i, const unsigned long long (&s)[4]) {
-    ulonglong2* p = reinterpret_cast<ulonglong2*>(rng + 4 * i);
-    p[0] = make_ulonglong2(s[0], s[1]);
-    p[1] = make_ulonglong2(s[2], s[3]);
-}
-__device__ __forceinline__ unsigned long long xo_next(unsigned long long (&s)[4]) {
-    unsigned long long tmp = s[0] + s[3];
-    unsigned long long res = ((tmp << 23) | (tmp >> 41)) + s[0];
-    unsigned long long t = s[1] << 17;
-    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t;
-    s[3] = (s[3] << 45) | (s[3] >> 19);
-    return res;
-}
-__device__ __forceinline__ double xo_f64(unsigned long long (&s)[4]) { return (double)(xo_next(s) >> 11) * 0x1p-53; }
-__device__ __forceinline__ float xo_f32(unsigned long long (&s)[4]) { return (float)((unsigned)(xo_next(s) >> 32) >> 8) * 0x1p-24f; }
 
 // =====================================================================================================
 // K7 on tensor cores: PPO / A2C loss + backward for one minibatch, all three 64x64 GEMMs on tcgen05.
@@ -122,17 +45,15 @@ __device__ __forceinline__ float xo_f32(unsigned long long (&s)[4]) { return (fl
 //   GEMM3  dW2[j][i]  += sum_s dP2[s][j] H1[s][i]     A = dP2^T, B = H1^T: feature-major K-major images (smem),
 //                                                     accumulated in TMEM across ALL tiles of the CTA, read once.
 // every product 3xTF32 (full*full + full*lo + lo*full; the tensor core ignores the low 13 mantissa bits).
-// GEMM3 of tile t is only awaited right before tile t+1 overwrites its operand images, so it overlaps
-// with the next gather / layer-1.  One CTA per SM (512 threads, role = blockIdx & 1), persistent.
+// One CTA per SM (512 threads, role = blockIdx & 1), persistent, software-pipelined across tiles (see the loop).
 // Thread <-> data: warp w: TMEM lane quadrant q = w % 4, feature block c = w / 4; thread = sample s = 32q + lane.
 constexpr int NT7 = 512;
 constexpr int GF_T = 144;                 // feature-major image: stride between 4-sample chunks; 144 = 128 + 16 makes the 32 lanes'
                                           // 4-byte transposed stores hit 32 different banks (with 128 they would 8-way conflict)
 constexpr int GS_T = 32 * GF_T + 16;      // stride between 8-feature row groups
 constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples]
-// Back-to-back tcgen05.mma on ONE accumulator serialise at ~120 cycles each (measured, profiles/umma_probe4.py) although a
-// 128x64x8 tf32 MMA is only ~32 cycles of tensor work, so the three 3xTF32 passes go to three separate accumulators
-// (independent dependency chains, issued round-robin) and are summed in the epilogue.
+// tcgen05.mma instructions pace at ~120-140 cycles each whatever their N (<= 192), accumulator or issuing thread (measured,
+// profiles/umma_probe4.py), so the kernel minimises their number: full|lo operands are stacked along N (and M for GEMM3).
 // TMEM columns: R1 = D1 of GEMM1 ([ff+lf | fl]), then (same lanes/columns, after P3 consumed it) the dP2 A operand (full | lo) of GEMM2;
 // D2 = GEMM2 accumulator; D3 = GEMM3 accumulator (all tiles); AH = H1 A operand (full | lo) of GEMM1.
 constexpr uint32_t COL_R1 = 0, COL_D2 = 128, COL_D3 = 256, COL_AH = 384;
@@ -159,8 +80,6 @@ struct SmemBwd {
     alignas(8) uint64_t bar1;
     alignas(8) uint64_t bar2;
     alignas(8) uint64_t bar3;
-    alignas(8) uint64_t ready1;
-    alignas(8) uint64_t ready2;
     uint32_t tmem;
 };
 __device__ __forceinline__ uint32_t fimg_off(int f, int s) { return (uint32_t)((f >> 3) * GS_T + (s >> 2) * GF_T + (f & 7) * 16 + (s & 3) * 4); }
@@ -219,32 +138,8 @@ __device__ __forceinline__ float lane_transpose_reduce32(float (&v)[32], int lan
     return v[0];   // value index = lane
 }
 
-// issue `ksteps` MMAs whose operands advance by a fixed amount per step: descriptors differ only in the
-// 14-bit start-address field, so the loop body is one 32-bit add per descriptor + the MMA itself
-__device__ __forceinline__ void issue_ss(uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t a_adv16, uint32_t b_adv16, int ksteps, uint32_t idesc,
-                                         uint32_t& acc) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        if (k < ksteps) {
-            umma::mma_tf32(d_tmem, a0 + (uint64_t)(k * a_adv16), b0 + (uint64_t)(k * b_adv16), idesc, acc);
-            acc = 1u;
-        }
-    }
-}
-__device__ __forceinline__ void issue_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b0, uint32_t b_adv16, uint32_t idesc, uint32_t& acc) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        umma::mma_tf32_ts(d_tmem, a_tmem + 8 * k, b0 + (uint64_t)(k * b_adv16), idesc, acc);
-        acc = 1u;
-    }
-}
-
 // worker-only barrier (the MMA warp never joins it)
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(mbar)) : "memory");
-}
-
 // per-sample loss and d(loss)/d(head outputs); identical arithmetic on every thread that evaluates a sample
 struct LossOut { float dz[kOutMax]; float l0, l1; };
 __device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, const AcHyper& hp, float inv_B, const float (&z)[kOutMax],
@@ -372,7 +267,6 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     if (warp == 0) umma::tmem_alloc(&sm.tmem, 512);
     if (tid == 32) {
         umma::mbar_init(&sm.bar1, 1); umma::mbar_init(&sm.bar2, 1); umma::mbar_init(&sm.bar3, 1);
-        umma::mbar_init(&sm.ready1, 1); umma::mbar_init(&sm.ready2, 1);
     }
     umma::fence_proxy_async();
     umma::fence_before_sync();

@@ -6,7 +6,7 @@ import pytest
 # tests/test_sharding_gpu.py runs two ranks of the peer exchange in ONE process on one GPU: a rank that has to lazily load a
 # kernel while the other rank spins inside the exchange would wait for it forever (CUDA lazy loading synchronises the
 # context).  Eager loading must be chosen before CUDA initialises; separate processes / GPUs (the real layout) are unaffected.
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+os.environ["CUDA_MODULE_LOADING"] = "EAGER"
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
