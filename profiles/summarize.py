@@ -28,7 +28,7 @@ def raw(rep):
 lines = ["# ncu summaries (%s)" % TAG, "", "Captured with `profiles/run_profiles.sh` under gpurun on one B200 (`--set full --clock-control none`);",
          "per-launch times are cold-cache / serialised — compare shares, not absolutes.", ""]
 traffic = {}
-for name in ("prof_loss", "prof_fwd", "prof_env", "prof_gae"):
+for name in ("prof_loss", "prof_rollout", "prof_fwd", "prof_adam", "prof_env", "prof_gae"):
     rep = os.path.join(OUT, name + ".ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -47,7 +47,7 @@ for name in ("prof_loss", "prof_fwd", "prof_env", "prof_gae"):
             t = float(rec["dram__bytes_read.sum"].replace(",", "")) + float(rec["dram__bytes_write.sum"].replace(",", ""))
             u = ui.get("dram__bytes_read.sum", "byte")
             mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-            mk = re.search(r"(ac_loss_grad_tc_kernel|ac_loss_grad_kernel|forward_tc_kernel|forward_kernel|env_step_kernel|scan_series_fastest|dqn_loss_grad_kernel)", kn)
+            mk = re.search(r"(ac_loss_grad_tc_kernel|ac_loss_grad_kernel|rollout_tc_kernel|forward_tc_kernel|forward_kernel|reduce_clip_adam_kernel|env_step_kernel|scan_series_fastest|dqn_loss_grad_kernel)", kn)
             traffic[mk.group(1) if mk else kn] = t * mult
             lines.append("| dram traffic (read+write) | %.3f | MB |" % (t * mult / 1e6))
         except Exception as e:

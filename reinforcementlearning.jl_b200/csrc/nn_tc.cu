@@ -613,21 +613,38 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         }
         worker_sync();
     }
-    // per-sample-slot partials -> [slot][64] in shared memory -> column sums in slot order
-    for (int pass = 0; pass < 4; ++pass) {
-        // pass 0: db2, 1: db1, 2: dW3[0], 3: dW3[1]
+    // per-sample-slot partials of db2, db1, dW3[0], dW3[1] -> four [128 slots][64] matrices in shared memory -> column sums in
+    // a fixed order: 8 segment sums of 16 slots each (all 512 threads), then the 8 segments in order (64 threads per matrix)
+    {
+        constexpr int RS = 65;                // row stride 65: the 32 lanes (= 32 sample slots) of a store hit 32 different banks
+        float* seg = red + 4 * TM * RS;       // [4][8][64]
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            float val = pass == 0 ? db2acc[k] : pass == 1 ? db1acc[k] : pass == 2 ? g3[0][k] : g3[1][k];
-            red[s * 64 + 16 * c + k] = val;
+            red[0 * TM * RS + s * RS + 16 * c + k] = db2acc[k];
+            red[1 * TM * RS + s * RS + 16 * c + k] = db1acc[k];
+            red[2 * TM * RS + s * RS + 16 * c + k] = g3[0][k];
+            red[3 * TM * RS + s * RS + 16 * c + k] = g3[1][k];
         }
         worker_sync();
-        if (tid < H) {
+        {
+            const int col = tid & 63, g = tid >> 6;   // 8 segments x 64 columns
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                float a = 0.f;
+#pragma unroll
+                for (int ss = 0; ss < 16; ++ss) a += red[m * TM * RS + (16 * g + ss) * RS + col];
+                seg[(m * 8 + g) * 64 + col] = a;
+            }
+        }
+        worker_sync();
+        if (tid < 4 * H) {
+            const int m = tid >> 6, col = tid & 63;
             float a = 0.f;
-            for (int ss = 0; ss < TM; ++ss) a += red[ss * 64 + tid];
-            if (pass == 0) gb2[tid] = a;
-            else if (pass == 1) gb1[tid] = a;
-            else if (pass - 2 < d.nout) out[head_w(d, pass - 2, tid)] = a;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) a += seg[(m * 8 + g) * 64 + col];
+            if (m == 0) gb2[col] = a;
+            else if (m == 1) gb1[col] = a;
+            else if (m - 2 < d.nout) out[head_w(d, m - 2, col)] = a;
         }
         worker_sync();
     }
