@@ -64,7 +64,9 @@ if os.path.exists(lp):
         if hdr and len(r) == len(hdr): data.append(dict(zip(hdr, r)))
     tot = collections.defaultdict(float); cnt = collections.Counter()
     for d in data:
-        nm = re.sub(r"\(.*", "", d["Kernel Name"]); nm = re.sub(r"^.*::", "", nm)
+        nm = re.sub(r"\(.*", "", d["Kernel Name"])
+        head, _, targs = nm.partition("<")
+        nm = head.split("::")[-1] + ("<" + re.sub(r"(\(anonymous namespace\)|envdev)::", "", targs)[:48] if targs else "")
         v = float(d["Metric Value"].replace(",", "")); u = d["Metric Unit"]
         v *= {"ns": 1, "nsecond": 1, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6}.get(u, 1)
         tot[nm] += v; cnt[nm] += 1
