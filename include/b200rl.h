@@ -238,6 +238,21 @@ int b200rl_net_act(b200rl_net* net, const float* obs, int64_t n, uint64_t* rng_d
 int b200rl_net_values(b200rl_net* net, const float* obs, int64_t n, float* out, int use_target, int on_device);
 /* QBasedPolicy + EpsilonGreedyExplorer (q_based_policy.jl:13-49, explorers/epsilon_greedy_explorer.jl:69-131); DEVICE pointers */
 int b200rl_net_q_act(b200rl_net* net, const float* obs_dev, int64_t n, uint64_t* rng_dev, float epsilon, int32_t* action_out_dev);
+/* EpsilonGreedyExplorer{kind, is_break_tie} with its decay schedule, applied to a batch the way BatchExplorer does
+ * (explorers/epsilon_greedy_explorer.jl:47-112, explorers/batch_explorer.jl:15-21): the inner explorer is called once per
+ * column, so column i is planned with get_eps(step + i) (Float64 schedule, :linear | :exp) and the caller advances
+ * `step` by n afterwards.  Per column: u = rand(rng) is always drawn; u >= eps ? findmax(values)[2] (or, is_break_tie,
+ * rand(rng, find_all_max(values)[2])) : rand(rng, 1:n_actions).  Column i draws from its own stream rng_dev[:, i]
+ * (the reference draws all columns from one stream — not parallel). */
+typedef struct {
+    double eps_stable, eps_init;
+    int64_t warmup_steps, decay_steps;
+    int64_t step;            /* explorer.step before this call (the reference starts at 1) */
+    int32_t kind;            /* 0 :linear, 1 :exp */
+    int32_t is_break_tie;
+} b200rl_explorer;
+int b200rl_net_q_explore(b200rl_net* net, const float* obs_dev, int64_t n, uint64_t* rng_dev, const b200rl_explorer* explorer,
+                         int32_t* action_out_dev);
 
 /* ---------------------------------------------------------------- on-policy agent -- */
 /* PPO (clipped surrogate) / A2C hyper-parameters; defaults of the in-tree example

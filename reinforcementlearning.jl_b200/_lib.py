@@ -49,6 +49,12 @@ class DQNConfig(C.Structure):
                                          "per_eps")] + [(n, C.c_int32) for n in ("huber", "double_dqn", "target_update_freq")]
 
 
+class Explorer(C.Structure):
+    """b200rl_explorer: EpsilonGreedyExplorer{kind, is_break_tie} fields + the step before the call."""
+    _fields_ = [("eps_stable", C.c_double), ("eps_init", C.c_double), ("warmup_steps", C.c_int64), ("decay_steps", C.c_int64),
+                ("step", C.c_int64), ("kind", C.c_int32), ("is_break_tie", C.c_int32)]
+
+
 class MountainCarParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("min_pos", "max_pos", "max_speed", "goal_pos", "goal_velocity", "power", "gravity")] + [
         ("max_steps", C.c_int64)]
@@ -117,6 +123,7 @@ SIGNATURES = {
     "b200rl_net_act": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32]),
     "b200rl_net_values": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32]),
     "b200rl_net_q_act": (_i32, [_vp, _vp, _i64, _vp, _f32, _vp]),
+    "b200rl_net_q_explore": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "b200rl_net_ac_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _f32, _f32, _i32, _vp]),
     "b200rl_onpolicy_create": (_i32, [_vp, _vp, _vp, _vp, _vp, _pp]),
     "b200rl_onpolicy_destroy": (_i32, [_vp]),

@@ -20,8 +20,10 @@ class AbstractHook:
     def push(self, stage, policy, env):  # Base.push!(hook, stage, policy, env) (hooks.jl:32-35)
         pass
 
-    def __add__(self, other):  # ComposedHook via `+` (hooks.jl:54-56)
-        return ComposedHook(self, other)
+    def __add__(self, other):  # ComposedHook via `+`, flattening composed operands (hooks.jl:40-43)
+        left = self.hooks if isinstance(self, ComposedHook) else (self,)
+        right = other.hooks if isinstance(other, ComposedHook) else (other,)
+        return ComposedHook(*left, *right)
 
 
 class EmptyHook(AbstractHook):
@@ -30,7 +32,14 @@ class EmptyHook(AbstractHook):
 
 class ComposedHook(AbstractHook):
     def __init__(self, *hooks):
-        self.hooks = hooks
+        self.hooks = tuple(hooks)
+
+    @property
+    def per_step(self):  # the composed hook is stage-free only when every member is
+        return any(getattr(h, "per_step", True) for h in self.hooks)
+
+    def __getitem__(self, i):  # Base.getindex(hook::ComposedHook, inds...) (hooks.jl:61)
+        return self.hooks[i]
 
     def push(self, stage, policy, env):
         for h in self.hooks:
@@ -117,7 +126,58 @@ class DoEveryNSteps(AbstractHook):
                 self.f(self.t, policy, env)
 
 
+class DoOnExit(AbstractHook):
+    """hooks.jl DoOnExit: call f(policy, env) at the PostExperimentStage."""
+
+    def __init__(self, f):
+        self.f = f
+
+    def push(self, stage, policy, env):
+        if stage == PostExperimentStage:
+            self.f(policy, env)
+
+
 # ---- stop conditions (stop_conditions.jl) -------------------------------------------------
+class StopIfAny:
+    """stop_conditions.jl:13-27: every condition is checked (no short circuit), the results are reduced by any."""
+
+    def __init__(self, *stop_conditions):
+        self.stop_conditions = stop_conditions
+
+    def check(self, policy, env):
+        return any([s.check(policy, env) for s in self.stop_conditions])
+
+
+class StopIfAll:
+    """stop_conditions.jl:29-38."""
+
+    def __init__(self, *stop_conditions):
+        self.stop_conditions = stop_conditions
+
+    def check(self, policy, env):
+        return all([s.check(policy, env) for s in self.stop_conditions])
+
+
+class StopAfterNoImprovement:
+    """stop_conditions.jl:120-165: fn() is monitored whenever an episode ended (batched: any sub-env terminated);
+    true once it failed to improve by more than delta for `patience` consecutive checks."""
+
+    def __init__(self, fn, patience, delta=0.0):
+        self.fn, self.patience, self.delta = fn, int(patience), delta
+        self.peak, self.counter = float("-inf"), 1
+
+    def check(self, policy, env):
+        if not np.any(env.is_terminated()):
+            return False
+        val = self.fn()
+        if self.delta < val - self.peak:
+            self.counter = 1
+            self.peak = max(val, self.peak)
+            return False
+        self.counter += 1
+        return self.counter > self.patience
+
+
 class StopAfterNSteps:
     """stop_conditions.jl:40-76: true on its n-th check (n loop iterations = n*N env-steps)."""
 

@@ -277,6 +277,18 @@ int b200rl_net_q_act(b200rl_net* n, const float* obs_dev, int64_t N, uint64_t* r
     return nn_q_act(n->ctx, n->actor, n->params, obs_dev, N, (unsigned long long*)rng_dev, epsilon, action_out_dev, (float*)s);
 }
 
+/* BatchExplorer(EpsilonGreedyExplorer) with the decay schedule evaluated per column on the device; all pointers DEVICE */
+int b200rl_net_q_explore(b200rl_net* n, const float* obs_dev, int64_t N, uint64_t* rng_dev, const b200rl_explorer* ex, int32_t* action_out_dev) {
+    REQUIRE(n && obs_dev && action_out_dev && rng_dev && ex && n->kind == 2, B200RL_ERR_INVALID, "bad argument (Q-network only)");
+    REQUIRE(N > 0, B200RL_ERR_INVALID, "empty batch");
+    REQUIRE((ex->kind == 0 || ex->kind == 1) && ex->warmup_steps >= 0 && ex->decay_steps >= 0, B200RL_ERR_INVALID, "bad explorer schedule");
+    REQUIRE(ex->eps_stable >= 0.0 && ex->eps_stable <= 1.0 && ex->eps_init >= 0.0 && ex->eps_init <= 1.0, B200RL_ERR_INVALID, "epsilon outside [0, 1]");
+    TRY(ctx_bind(n->ctx));
+    void* s;
+    TRY(ctx_scratch(n->ctx, (size_t)N * n->actor.nout * 4 + 256, &s));
+    return nn_q_explore(n->ctx, n->actor, n->params, obs_dev, N, (unsigned long long*)rng_dev, *ex, action_out_dev, (float*)s);
+}
+
 /* One optimiser step from explicit on-policy minibatch arrays (all HOST; test / generic entry):
  * loss + gradient (K7), global-norm clip + Adam (K8).  losses_out[6] = actor_loss, critic_loss,
  * entropy, loss, grad_norm (pre-clip), 0.  apply_update = 0 leaves the parameters untouched (gradient only). */

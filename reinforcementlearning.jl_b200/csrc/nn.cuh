@@ -66,6 +66,8 @@ int nn_dqn_loss_grad(b200rl_ctx* ctx, const MlpDesc& q, const float* params, con
                      int double_dqn, float* partial, float* loss_partial, float* td_out);
 int nn_q_act(b200rl_ctx* ctx, const MlpDesc& q, const float* params, const float* obs, int64_t N, unsigned long long* rng, float epsilon,
              int32_t* action_out, float* q_out);
+int nn_q_explore(b200rl_ctx* ctx, const MlpDesc& q, const float* params, const float* obs, int64_t N, unsigned long long* rng,
+                 const b200rl_explorer& ex, int32_t* action_out, float* q_out);
 
 // tensor-core (tcgen05) variants, nn_tc.cu.  Used for H = 64 unless disabled (B200RL_TC=0 or b200rl_set_tensor_cores(0)).
 bool nn_tc_enabled();

@@ -18,14 +18,17 @@
 module B200RL
 
 using Random
+using IntervalSets: (..)                      # RLEnvs' own dependency (its continuous action spaces are `-1.0 .. 1.0`)
 import ReinforcementLearningBase as RLBase
 import ReinforcementLearningCore as RLCore
 import ReinforcementLearningEnvironments as RLEnvs
 using ReinforcementLearningBase: AbstractEnv, AbstractPolicy, Observation, DefaultPlayer
 using ReinforcementLearningCore: AbstractStage, PreExperimentStage, PostExperimentStage, PreActStage, PostActStage,
-    AbstractStopCondition, AbstractHook, AbstractResetCondition, ResetIfEnvTerminated, StopAfterNEpisodes
+    AbstractStopCondition, AbstractHook, AbstractResetCondition, ResetIfEnvTerminated, StopAfterNEpisodes, StopAfterNSteps,
+    EpsilonGreedyExplorer, GreedyExplorer, AbstractExplorer
 
-export B200Context, B200VecEnv, B200Network, B200OnPolicyAgent, B200RandomPolicy
+export B200Context, B200VecEnv, B200Network, B200OnPolicyAgent, B200RandomPolicy, B200Trajectory, B200DQNLearner, B200QBasedPolicy,
+    B200Agent, B200EpisodeStats, InsertSampleRatio
 
 const LIB = get(ENV, "B200RL_LIB", joinpath(@__DIR__, "..", "libb200rl.so"))
 
@@ -80,6 +83,7 @@ mutable struct B200VecEnv{T} <: AbstractEnv
     n::Int
     auto_reset::Bool
     continuous::Bool
+    n_actions::Int         # discrete spaces: Base.OneTo(n_actions)
     # host mirrors, refreshed lazily (state(env) may alias a reused buffer: interface.jl:515-517)
     obs::Matrix{T}
     rewards::Vector{T}
@@ -87,7 +91,8 @@ mutable struct B200VecEnv{T} <: AbstractEnv
 end
 
 function B200VecEnv(ctx::B200Context, kind::Symbol, n::Integer; T = Float32, seeds::AbstractVector{Xoshiro},
-                    auto_reset::Bool = true, params = C_NULL, continuous::Bool = (kind in (:Pendulum, :ContinuousCartPole, :ContinuousMountainCar)))
+                    auto_reset::Bool = true, params = C_NULL, continuous::Bool = (kind in (:Pendulum, :ContinuousCartPole, :ContinuousMountainCar)),
+                    n_actions::Integer = kind === :MountainCar ? 3 : kind === :Pendulum ? 3 : 2)
     length(seeds) == n || throw(ArgumentError("need one Xoshiro per env"))
     k = KINDS[kind]
     st = raw_states(seeds)
@@ -95,7 +100,7 @@ function B200VecEnv(ctx::B200Context, kind::Symbol, n::Integer; T = Float32, see
     GC.@preserve st params check(ccall((:b200rl_env_create, LIB), Cint,
         (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{UInt64}, Ref{Ptr{Cvoid}}),
         ctx.h, k, T === Float64 ? 1 : 0, n, params === C_NULL ? C_NULL : pointer_from_objref(params), st, out))
-    env = B200VecEnv{T}(ctx, out[], k, n, auto_reset, continuous, zeros(T, NOBS[k], n), zeros(T, n), zeros(UInt8, n))
+    env = B200VecEnv{T}(ctx, out[], k, n, auto_reset, continuous, n_actions, zeros(T, NOBS[k], n), zeros(T, n), zeros(UInt8, n))
     finalizer(e -> (e.h == C_NULL || ccall((:b200rl_env_destroy, LIB), Cint, (Ptr{Cvoid},), e.h); e.h = C_NULL), env)
 end
 
@@ -136,8 +141,9 @@ RLBase.state(env::B200VecEnv, ::Observation, ::DefaultPlayer) = fetch!(env, OBS,
 RLBase.state(env::B200VecEnv) = fetch!(env, OBS, env.obs)
 RLBase.reward(env::B200VecEnv) = fetch!(env, REWARD, env.rewards)
 RLBase.is_terminated(env::B200VecEnv) = (fetch!(env, TERMINAL, env.terminals); env.terminals .!= 0)
+# CartPoleEnv.jl:95-96, PendulumEnv.jl:73-74, MountainCarEnv.jl:85-86 (one sub-env's space; every sub-env has the same)
 RLBase.action_space(env::B200VecEnv) =
-    env.kind == 0 ? Base.OneTo(2) : env.kind == 2 ? Base.OneTo(3) : (-2.0 .. 2.0)
+    !env.continuous ? Base.OneTo(env.n_actions) : env.kind == 1 ? (-2.0 .. 2.0) : (-1.0 .. 1.0)
 Base.length(env::B200VecEnv) = env.n
 function Random.seed!(env::B200VecEnv, seeds::AbstractVector{Xoshiro})
     st = raw_states(seeds)
@@ -146,8 +152,38 @@ end
 function Base.copy(env::B200VecEnv{T}) where {T}
     out = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:b200rl_env_copy, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), env.h, out))
-    B200VecEnv{T}(env.ctx, out[], env.kind, env.n, env.auto_reset, env.continuous, copy(env.obs), copy(env.rewards), copy(env.terminals))
+    e = B200VecEnv{T}(env.ctx, out[], env.kind, env.n, env.auto_reset, env.continuous, env.n_actions, copy(env.obs), copy(env.rewards), copy(env.terminals))
+    finalizer(x -> (x.h == C_NULL || ccall((:b200rl_env_destroy, LIB), Cint, (Ptr{Cvoid},), x.h); x.h = C_NULL), e)
 end
+"Zero-copy device pointer of an env field for fused consumers (b200rl_env_ptr)."
+function device_ptr(env::B200VecEnv, field::Field)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:b200rl_env_ptr, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), env.h, Int(field), out))
+    out[]
+end
+struct DeviceActions; ptr::Ptr{Cvoid}; end                   # plan! token: the actions already sit in device memory
+RLBase.act!(env::B200VecEnv, a::DeviceActions) =
+    check(ccall((:b200rl_env_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint), env.h, a.ptr, 1, env.auto_reset))
+
+"""
+    B200EpisodeStats()
+
+Device-side reduction of `TotalRewardPerEpisode` / `BatchStepsPerEpisode` (hooks.jl:146-231): the step kernel accumulates
+finished episodes, their returns and lengths; the hook reads four numbers at the end of the experiment — no per-step copy.
+`hook[]` = (episodes, return_sum, length_sum, env_steps).
+"""
+mutable struct B200EpisodeStats <: AbstractHook
+    stats::NTuple{4,Float64}
+    B200EpisodeStats() = new((0.0, 0.0, 0.0, 0.0))
+end
+Base.getindex(h::B200EpisodeStats) = h.stats
+function episode_stats(env::B200VecEnv; reset::Bool = false)
+    out = zeros(Float64, 4)
+    GC.@preserve out check(ccall((:b200rl_env_episode_stats, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), env.h, out, reset))
+    (out[1], out[2], out[3], out[4])
+end
+Base.push!(h::B200EpisodeStats, ::PreExperimentStage, ::AbstractPolicy, env::B200VecEnv) = (episode_stats(env; reset = true); nothing)
+Base.push!(h::B200EpisodeStats, ::PostExperimentStage, ::AbstractPolicy, env::B200VecEnv) = (h.stats = episode_stats(env); nothing)
 
 # ---- run-loop impedance (SURVEY §7 "Run-loop impedance") --------------------------------------
 # the kernel resets finished sub-envs itself; the scalar reset condition must never fire
@@ -163,6 +199,23 @@ function RLCore._run(policy::AbstractPolicy, env::B200VecEnv, stop_condition::Ab
     push!(hook, PreExperimentStage(), policy, env)
     push!(policy, PreExperimentStage(), env)
     RLBase.reset!(env; is_force = true)
+    # Fused fast path (the Python mirror's run(), core.py): a device-resident on-policy agent, a hook with nothing to do per
+    # step and a step-count stop condition let whole stretches of the loop run as ONE kernel launch (b200rl_onpolicy_collect:
+    # n x {plan!, act!, push!}) — the same transitions, parameters and statistics as stepping through the stages.
+    if policy isa B200OnPolicyAgent && policy.fused && env.auto_reset && hook isa Union{B200EpisodeStats,RLCore.EmptyHook} &&
+       stop_condition isa StopAfterNSteps
+        while true                                                  # StopAfterNSteps: check! is true once cur >= step, then cur += 1
+            n = min(policy.T - policy.t, max(1, stop_condition.step - stop_condition.cur + 1))
+            collect!(policy, n)
+            RLBase.optimise!(policy, PostActStage())
+            stop_condition.cur += n
+            stop_condition.cur > stop_condition.step && break
+        end
+        push!(policy, PostExperimentStage(), env)
+        push!(hook, PostExperimentStage(), policy, env)
+        check(ccall((:b200rl_env_check, LIB), Cint, (Ptr{Cvoid},), env.h))
+        return hook
+    end
     while true
         env.auto_reset || RLBase.reset!(env; is_force = false)
         push!(policy, PreActStage(), env)
@@ -224,10 +277,11 @@ mutable struct B200OnPolicyAgent <: AbstractPolicy
     env::B200VecEnv
     T::Int
     t::Int
+    fused::Bool            # true: actions never visit the host (plan! returns a device token, run() may fuse whole stretches)
     actions::Vector{Int32}
     stats::Matrix{Float32}
 end
-function B200OnPolicyAgent(ctx, net::B200Network, env::B200VecEnv; policy_seeds::AbstractVector{Xoshiro},
+function B200OnPolicyAgent(ctx, net::B200Network, env::B200VecEnv; policy_seeds::AbstractVector{Xoshiro}, fused::Bool = false,
         γ = 0.99f0, λ = 0.95f0, clip_range = 0.1f0, max_grad_norm = 0.5f0, actor_loss_weight = 1f0, critic_loss_weight = 0.5f0,
         entropy_loss_weight = 0.001f0, lr = 1f-3, update_freq = 32, n_epochs = 4, n_microbatches = 4, normalize_advantage = true,
         algo::Symbol = :ppo)
@@ -237,13 +291,24 @@ function B200OnPolicyAgent(ctx, net::B200Network, env::B200VecEnv; policy_seeds:
     out = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve st check(ccall((:b200rl_onpolicy_create, LIB), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{OnPolicyConfigC}, Ptr{UInt64}, Ref{Ptr{Cvoid}}), ctx.h, net.h, env.h, Ref(cfg), st, out))
-    a = B200OnPolicyAgent(ctx, out[], net, env, update_freq, 0, zeros(Int32, env.n), zeros(Float32, 6, n_epochs * n_microbatches))
+    a = B200OnPolicyAgent(ctx, out[], net, env, update_freq, 0, fused, zeros(Int32, env.n), zeros(Float32, 6, n_epochs * n_microbatches))
     finalizer(x -> (x.h == C_NULL || ccall((:b200rl_onpolicy_destroy, LIB), Cint, (Ptr{Cvoid},), x.h); x.h = C_NULL), a)
 end
 # plan!(agent, env) (agent_base.jl:52-54): K6 on the current observation; actions come back to the host
+struct FusedPolicyAction; agent::Ptr{Cvoid}; end              # plan!(fused agent) token: act! without leaving the device
+RLBase.act!(::B200VecEnv, f::FusedPolicyAction) = check(ccall((:b200rl_onpolicy_act, LIB), Cint, (Ptr{Cvoid},), f.agent))
 function RLBase.plan!(a::B200OnPolicyAgent, ::B200VecEnv)
+    if a.fused
+        check(ccall((:b200rl_onpolicy_plan, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), a.h, C_NULL))
+        return FusedPolicyAction(a.h)
+    end
     GC.@preserve a check(ccall((:b200rl_onpolicy_plan, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), a.h, a.actions))
     a.actions
+end
+"n_steps x {plan!, act!, push!} in one kernel launch (fused rollout)."
+function collect!(a::B200OnPolicyAgent, n_steps::Integer)
+    check(ccall((:b200rl_onpolicy_collect, LIB), Cint, (Ptr{Cvoid}, Cint), a.h, n_steps))
+    a.t += n_steps
 end
 # push!(agent, PostActStage, env, action) (agent_base.jl:56-59): reward/terminal were written in-kernel
 function Base.push!(a::B200OnPolicyAgent, ::PostActStage, ::B200VecEnv, action)
@@ -260,13 +325,169 @@ function RLBase.optimise!(a::B200OnPolicyAgent, ::PostActStage)
 end
 RLBase.optimise!(::B200OnPolicyAgent, ::AbstractStage) = nothing
 
+# ---- DQN: device trajectory + learner + explorer (BASELINE config 5) --------------------------------
+# InsertSampleRatioController(ratio, threshold) (RLTrajectories 0.4; docs/src/How_to_implement_a_new_algorithm.md:108); one insertion = one frame
+Base.@kwdef mutable struct InsertSampleRatio
+    ratio::Float64 = 1.0
+    threshold::Int = 1
+    n_inserted::Int = 0
+    n_sampled::Int = 0
+end
+function on_sample!(c::InsertSampleRatio)
+    if c.n_inserted >= c.threshold && c.n_sampled <= (c.n_inserted - c.threshold) * c.ratio
+        c.n_sampled += 1
+        return true
+    end
+    false
+end
+"""
+    B200Trajectory(ctx; state_size, lanes, capacity, batch_size, sampler_seeds, prioritized = false, default_priority = 1f0,
+                   controller = InsertSampleRatio())
+
+`Trajectory(container = CircularArraySARTSTraces(capacity) [wrapped in CircularPrioritizedTraces], sampler = BatchSampler(batch_size),
+controller = InsertSampleRatioController(ratio, threshold))` (ReinforcementLearningTrajectories 0.4) resident on the device:
+a ring of `capacity + 1` frames of `lanes` sub-envs; `next_state` of frame j is frame j + 1.
+"""
+mutable struct B200Trajectory
+    ctx::B200Context
+    h::Ptr{Cvoid}
+    lanes::Int
+    batch_size::Int
+    controller::InsertSampleRatio
+end
+function B200Trajectory(ctx::B200Context; state_size::Integer, lanes::Integer, capacity::Integer, batch_size::Integer,
+                        sampler_seeds::AbstractVector{Xoshiro}, prioritized::Bool = false, default_priority = 1f0,
+                        controller = InsertSampleRatio())
+    length(sampler_seeds) == batch_size || throw(ArgumentError("need one Xoshiro per batch slot"))
+    st = raw_states(sampler_seeds)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve st check(ccall((:b200rl_traj_create, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Int64, Cint, Cfloat, Ptr{UInt64}, Int64, Ref{Ptr{Cvoid}}),
+        ctx.h, state_size, lanes, capacity, prioritized, default_priority, st, batch_size, out))
+    t = B200Trajectory(ctx, out[], lanes, batch_size, controller)
+    finalizer(x -> (x.h == C_NULL || ccall((:b200rl_traj_destroy, LIB), Cint, (Ptr{Cvoid},), x.h); x.h = C_NULL), t)
+end
+function Base.length(t::B200Trajectory)
+    n = Ref{Int64}(0)
+    check(ccall((:b200rl_traj_length, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}), t.h, n))
+    Int(n[])
+end
+# push!(trajectory, (state = s0,)) / push!(trajectory, (state = s', action, reward, terminal)) reading the env's device fields
+push_env!(t::B200Trajectory, env::B200VecEnv; first_state_only::Bool = false) =
+    check(ccall((:b200rl_traj_push_env, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), t.h, env.h, first_state_only))
+
+struct DQNConfigC
+    gamma::Cfloat; lr::Cfloat; beta1::Cfloat; beta2::Cfloat; eps::Cfloat; max_grad_norm::Cfloat; rho::Cfloat
+    per_alpha::Cfloat; per_beta::Cfloat; per_eps::Cfloat
+    huber::Int32; double_dqn::Int32; target_update_freq::Int32
+end
+"DQNLearner / PrioritizedDQNLearner: `net` is a `kind = :q` B200Network (FluxApproximator + TargetNetwork, target_network.jl:27-88)."
+struct B200DQNLearner <: RLCore.AbstractLearner
+    net::B200Network
+    cfg::DQNConfigC
+end
+B200DQNLearner(net::B200Network; γ = 0.99f0, lr = 1f-3, max_grad_norm = 0f0, ρ = 0f0, per_α = 0.6f0, per_β = 0.4f0, per_ϵ = 1f-6,
+               huber::Bool = true, double_dqn::Bool = false, target_update_freq::Integer = 100) =
+    B200DQNLearner(net, DQNConfigC(γ, lr, 0.9f0, 0.999f0, 1f-8, max_grad_norm, ρ, per_α, per_β, per_ϵ, huber, double_dqn, target_update_freq))
+# optimise!(learner, batch): sample + gather, TD loss + backward, clip + Adam, priority write-back, target sync — all on the device
+update!(l::B200DQNLearner, t::B200Trajectory) =
+    check(ccall((:b200rl_dqn_update, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{DQNConfigC}, Ptr{Cfloat}), l.net.h, t.h, Ref(l.cfg), C_NULL))
+
+struct ExplorerC
+    eps_stable::Cdouble; eps_init::Cdouble; warmup_steps::Int64; decay_steps::Int64; step::Int64; kind::Int32; is_break_tie::Int32
+end
+ExplorerC(s::EpsilonGreedyExplorer{K,B}) where {K,B} =
+    ExplorerC(s.ϵ_stable, s.ϵ_init, s.warmup_steps, s.decay_steps, s.step, K === :linear ? 0 : 1, B ? 1 : 0)
+
+"""
+    B200QBasedPolicy(ctx, learner, explorer, n; explorer_seeds)
+
+`QBasedPolicy(learner, explorer)` (q_based_policy.jl:13-49) for a batched env.  `explorer` is the reference's own
+`EpsilonGreedyExplorer{kind, is_break_tie}` (or `GreedyExplorer()`): its schedule fields are read on every `plan!` and its
+`step` is advanced by `n`, the way `BatchExplorer` calls the inner explorer once per column (batch_explorer.jl:15-21); the
+forward pass, `get_ϵ(step + i)`, the draws and the arg-max run in one device call.
+"""
+mutable struct B200QBasedPolicy{E<:AbstractExplorer} <: AbstractPolicy
+    ctx::B200Context
+    learner::B200DQNLearner
+    explorer::E
+    n::Int
+    d_rng::Ptr{Cvoid}
+    d_action::Ptr{Cvoid}
+end
+function dmalloc(ctx::B200Context, bytes::Integer)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:b200rl_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx.h, bytes, out))
+    out[]
+end
+function B200QBasedPolicy(ctx::B200Context, learner::B200DQNLearner, explorer::AbstractExplorer, n::Integer; explorer_seeds::AbstractVector{Xoshiro})
+    length(explorer_seeds) == n || throw(ArgumentError("need one Xoshiro per env"))
+    st = raw_states(explorer_seeds)
+    d_rng, d_action = dmalloc(ctx, 32n), dmalloc(ctx, 4n)
+    GC.@preserve st check(ccall((:b200rl_memcpy_h2d, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Cint), ctx.h, d_rng, st, 32n, 0))
+    p = B200QBasedPolicy(ctx, learner, explorer, Int(n), d_rng, d_action)
+    finalizer(p) do x
+        x.ctx.h == C_NULL && return
+        ccall((:b200rl_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.h, x.d_rng)
+        ccall((:b200rl_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.h, x.d_action)
+    end
+end
+function RLBase.plan!(p::B200QBasedPolicy{<:EpsilonGreedyExplorer}, env::B200VecEnv)
+    ex = ExplorerC(p.explorer)
+    check(ccall((:b200rl_net_q_explore, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ref{ExplorerC}, Ptr{Cvoid}),
+                p.learner.net.h, device_ptr(env, OBS), p.n, p.d_rng, Ref(ex), p.d_action))
+    p.explorer.step += p.n
+    DeviceActions(p.d_action)
+end
+function RLBase.plan!(p::B200QBasedPolicy{GreedyExplorer}, env::B200VecEnv)
+    check(ccall((:b200rl_net_q_act, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cfloat, Ptr{Cvoid}),
+                p.learner.net.h, device_ptr(env, OBS), p.n, C_NULL, 0f0, p.d_action))
+    DeviceActions(p.d_action)
+end
+
+"""
+    B200Agent(policy::B200QBasedPolicy, trajectory::B200Trajectory)
+
+`Agent(policy, trajectory)` (agent_base.jl:18-66) with a device-resident replay: transition frames never visit the host.  The batched loop
+has no episode stages, so the `PreEpisodeStage` push of the first state (agent_base.jl:45-47) happens at the first `PreActStage`.
+"""
+mutable struct B200Agent <: AbstractPolicy
+    policy::B200QBasedPolicy
+    trajectory::B200Trajectory
+    primed::Bool
+end
+B200Agent(policy::B200QBasedPolicy, trajectory::B200Trajectory) = B200Agent(policy, trajectory, false)
+RLBase.plan!(a::B200Agent, env::B200VecEnv) = RLBase.plan!(a.policy, env)
+function Base.push!(a::B200Agent, ::PreExperimentStage, ::B200VecEnv)
+    length(a.trajectory) == 0 || error("B200Agent: run on a non-empty device trajectory is not supported (no EpisodesBuffer bookkeeping)")
+    a.primed = false
+    nothing
+end
+function Base.push!(a::B200Agent, ::PreActStage, env::B200VecEnv)
+    a.primed || (push_env!(a.trajectory, env; first_state_only = true); a.primed = true)
+    nothing
+end
+function Base.push!(a::B200Agent, ::PostActStage, env::B200VecEnv, action)
+    push_env!(a.trajectory, env)
+    a.trajectory.controller.n_inserted += 1
+    nothing
+end
+Base.push!(::B200Agent, ::AbstractStage, ::B200VecEnv) = nothing
+# optimise!(agent, PostActStage) -> optimise!(policy.learner, stage, trajectory): `for batch in trajectory` samples while the controller allows
+function RLBase.optimise!(a::B200Agent, ::PostActStage)
+    while on_sample!(a.trajectory.controller)
+        update!(a.policy.learner, a.trajectory)
+    end
+    nothing
+end
+RLBase.optimise!(::B200Agent, ::AbstractStage) = nothing
+
 # ---- pure-function drop-ins (utils/basic.jl:138-417) --------------------------------------------
 "`generalized_advantage_estimation(rewards, values, γ, λ; dims, terminal)` on the GPU (Float32 / Float64 matrices)."
 function generalized_advantage_estimation(ctx::B200Context, rewards::Matrix{T}, values::Matrix{T}, γ::T, λ::T;
                                           dims::Int, terminal::Union{Nothing,Matrix{Bool}} = nothing) where {T<:Union{Float32,Float64}}
     adv = similar(rewards)
     term = terminal === nothing ? C_NULL : convert(Matrix{UInt8}, terminal)
-    f = T === Float32 ? :b200rl_gae_f32 : :b200rl_gae_f64
     R, C = size(rewards)
     GC.@preserve adv rewards values term begin
         if T === Float32
@@ -278,6 +499,19 @@ function generalized_advantage_estimation(ctx::B200Context, rewards::Matrix{T}, 
         end
     end
     adv
+end
+
+"`discount_rewards(rewards, γ; dims, terminal, init)` on the GPU (utils/basic.jl:138-235)."
+function discount_rewards(ctx::B200Context, rewards::Matrix{Float32}, γ::Float32; dims::Int, terminal::Union{Nothing,Matrix{Bool}} = nothing,
+                          init::Union{Nothing,Vector{Float32}} = nothing)
+    out = similar(rewards)
+    term = terminal === nothing ? C_NULL : convert(Matrix{UInt8}, terminal)
+    ini = init === nothing ? C_NULL : init
+    R, C = size(rewards)
+    GC.@preserve out rewards term ini check(ccall((:b200rl_discount_rewards_f32, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}, Ptr{Float32}, Float32, Int64, Int64, Cint, Cint),
+        ctx.h, out, rewards, term, ini, γ, R, C, dims, 0))
+    out
 end
 
 # ---- sharded runs: one process per GPU (SURVEY §8e) ------------------------------------------------

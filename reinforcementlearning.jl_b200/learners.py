@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .core import AbstractPolicy, FusedAction, PostActStage
+from .core import AbstractPolicy, FusedAction, PostActStage, PreActStage, PreExperimentStage
 
 ACT_RELU, ACT_TANH = 0, 1
 KIND_CATEGORICAL, KIND_GAUSSIAN, KIND_Q = 0, 1, 2
@@ -311,3 +311,125 @@ class DQNLearner:
         out = np.empty(self.traj.batch_size, np.float32)
         L.check(self.lib.b200rl_dqn_last_td(self.net.h, self.traj.h, L.ptr(out), out.size))
         return out
+
+
+class InsertSampleRatioController:
+    """InsertSampleRatioController(ratio, threshold) (ReinforcementLearningTrajectories 0.4, external; described in
+    docs/src/How_to_implement_a_new_algorithm.md:108): counts insertions and sampled batches; a batch may be sampled once
+    ``threshold`` insertions happened and while ``n_sampled <= (n_inserted - threshold) * ratio``.  One insertion = one
+    push of a frame (all lanes), the batched counterpart of one ``push!``."""
+
+    def __init__(self, ratio=1.0, threshold=1, n_inserted=0, n_sampled=0):
+        self.ratio, self.threshold, self.n_inserted, self.n_sampled = float(ratio), int(threshold), int(n_inserted), int(n_sampled)
+
+    def on_insert(self, n=1):
+        self.n_inserted += n
+
+    def on_sample(self):
+        if self.n_inserted >= self.threshold and self.n_sampled <= (self.n_inserted - self.threshold) * self.ratio:
+            self.n_sampled += 1
+            return True
+        return False
+
+
+class QBasedPolicy(AbstractPolicy):
+    """QBasedPolicy(learner = DQNLearner(...), explorer = EpsilonGreedyExplorer(...)) (q_based_policy.jl:13-49) on a batched
+    env: ``plan`` = BatchExplorer over Q(state(env), .) — forward pass, schedule, draws and arg-max in one device call.
+
+    ``explorer_rng``: (N, 4) uint64 raw Xoshiro states, one explorer stream per env."""
+
+    def __init__(self, ctx, learner, explorer, explorer_rng, n_envs):
+        self.ctx, self.lib, self.learner, self.explorer, self.n = ctx, ctx.lib, learner, explorer, int(n_envs)
+        rng = np.ascontiguousarray(explorer_rng, np.uint64).reshape(self.n, 4)
+        self._d_rng = ctx.malloc(rng.nbytes)
+        ctx.h2d(self._d_rng, rng)
+        self._d_action = ctx.malloc(self.n * 4)
+
+    def close(self):
+        for name in ("_d_rng", "_d_action"):
+            p = getattr(self, name, None)
+            if p:
+                self.ctx.free(p)
+                setattr(self, name, None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def plan_device(self, env):
+        """plan!(policy, env) leaving the actions on the device; returns the device pointer of the (N,) int32 actions."""
+        net, ex = self.learner.net, self.explorer
+        obs = C.c_void_p(env.device_ptr(L.FIELD_OBS))
+        if hasattr(ex, "as_struct"):
+            st = ex.as_struct()
+            L.check(self.lib.b200rl_net_q_explore(net.h, obs, self.n, C.c_void_p(self._d_rng), C.byref(st), C.c_void_p(self._d_action)))
+            ex.advance(self.n)
+        else:   # GreedyExplorer: findmax, no draw
+            L.check(self.lib.b200rl_net_q_act(net.h, obs, self.n, None, 0.0, C.c_void_p(self._d_action)))
+        return self._d_action
+
+    def plan(self, env):
+        self.plan_device(env)
+        return FusedAction("policy")
+
+    def act_fused(self, env):
+        env.act_(int(self._d_action))
+
+    def explorer_rng(self):
+        out = np.empty((self.n, 4), np.uint64)
+        return self.ctx.d2h(out, self._d_rng)
+
+    def optimise(self, stage, trajectory=None):
+        """optimise!(policy, stage, trajectory) = optimise!(policy.learner, stage, trajectory) (q_based_policy.jl:48-49);
+        the DQN learner trains at the PostActStage."""
+        if stage == PostActStage and trajectory is not None:
+            while trajectory.controller.on_sample():
+                self.learner.update()
+
+
+class Agent(AbstractPolicy):
+    """Agent(policy, trajectory) (agent_base.jl:18-66) for a device-resident replay trajectory: pushes the env's
+    transition frames (state / action / reward / terminal never visit the host) and lets the policy's learner train
+    whenever the trajectory's controller allows a batch.
+
+    There are no episode stages in the batched loop, so the first state is pushed at the first PreActStage after the
+    forced reset (the PreEpisodeStage push of agent_base.jl:45-47).  Re-entering ``run`` with a non-empty trajectory is
+    refused: the reference's EpisodesBuffer would mark the frame straddling the forced reset as not sampleable, which
+    this ring does not implement."""
+
+    def __init__(self, policy, trajectory, host_actions=False):
+        self.policy, self.trajectory, self.host_actions = policy, trajectory, host_actions
+        if not hasattr(trajectory, "controller"):
+            trajectory.controller = InsertSampleRatioController()
+        self._primed = False
+        self._host_act = None
+
+    def push(self, stage, env, action=None):
+        if stage == PreExperimentStage:
+            if len(self.trajectory) > 0:
+                raise RuntimeError("Agent: run() on a non-empty device trajectory is not supported (no EpisodesBuffer bookkeeping for "
+                                   "the frame straddling the forced reset); create a fresh Trajectory")
+            self._primed = False
+        elif stage == PreActStage:
+            if not self._primed:
+                self.trajectory.push_env(env, first_state_only=True)     # push!(trajectory, (state = state(env),))
+                self._primed = True
+        elif stage == PostActStage:
+            self.trajectory.push_env(env)                                # (state = s', action, reward, terminal)
+            self.trajectory.controller.on_insert(1)
+
+    def plan(self, env):
+        if self.host_actions:   # the reference's stage protocol: the action visits the host, the run loop calls act!(env, a)
+            d = self.policy.plan_device(env)
+            if self._host_act is None:
+                self._host_act = np.empty(self.policy.n, np.int32)
+            return self.policy.ctx.d2h(self._host_act, d)
+        return self.policy.plan(env)
+
+    def act_fused(self, env):
+        self.policy.act_fused(env)
+
+    def optimise(self, stage):
+        self.policy.optimise(stage, self.trajectory)

@@ -64,6 +64,8 @@ def lib():
         "orc_traj_push": (None, [vp, vp, vp, vp, vp]),
         "orc_traj_sample": (None, [vp, i32, vp, i64, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "orc_traj_update_priority": (None, [vp, vp, vp, i64]), "orc_traj_total_priority": (f32, [vp]),
+        "orc_get_eps": (f64, [vp, i64]), "orc_egreedy_prob": (None, [vp, i64, vp, i32, vp]),
+        "orc_egreedy_plan": (None, [vp, i64, vp, i32, i64, vp, vp]),
         "orc_ppo_iteration": (f64, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_uint32, vp]),
     }
     for name, (res, args) in sig.items():
@@ -292,6 +294,31 @@ def q_values(desc, params, obs):
     obs = np.asfortranarray(obs, dtype=np.float32)
     out = np.empty((int(desc[3]), obs.shape[1]), np.float32, order="F")
     lib().orc_q_values(_p(desc), _p(params), _p(obs), obs.shape[1], _p(out))
+    return out
+
+
+def explorer6(eps_stable, eps_init=1.0, warmup_steps=0, decay_steps=0, kind="linear", is_break_tie=False):
+    """EpsilonGreedyExplorer(; kwargs...) as the 6 doubles the oracle takes."""
+    return np.array([eps_stable, eps_init, warmup_steps, decay_steps, {"linear": 0, "exp": 1}[kind], int(is_break_tie)], np.float64)
+
+
+def get_eps(ex6, step):
+    return float(lib().orc_get_eps(_p(ex6), int(step)))
+
+
+def egreedy_prob(ex6, step, values):
+    v = np.ascontiguousarray(values, np.float64)
+    out = np.empty(v.size, np.float64)
+    lib().orc_egreedy_prob(_p(ex6), int(step), _p(v), v.size, _p(out))
+    return out
+
+
+def egreedy_plan(ex6, step0, qv, rng):
+    """BatchExplorer over the columns of qv (na, N); rng (N, 4) uint64 advanced in place; 1-based actions."""
+    qv = np.asfortranarray(qv, np.float32)
+    na, n = qv.shape
+    out = np.empty(n, np.int32)
+    lib().orc_egreedy_plan(_p(ex6), int(step0), _p(qv), na, n, _p(rng), _p(out))
     return out
 
 

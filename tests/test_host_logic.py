@@ -1,0 +1,260 @@
+"""Host logic of the drop-in surface (no GPU): the run loop / stages / hooks / stop conditions mirror
+(reinforcementlearning.jl_b200/core.py), the explorer schedule mirror (explorers.py) and the trajectory controller,
+driven with a stub batched env.  Expected values are the reference's own test vectors:
+RLCore/test/core/stop_conditions.jl:3-50, test/core/hooks.jl:44-152,
+test/policies/explorers/epsilon_greedy_explorer.jl:8-74."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+
+class StubVecEnv:
+    """N counters: sub-env i terminates every period[i] steps; auto_reset like the fused step kernel."""
+
+    def __init__(self, periods, auto_reset=True):
+        self.periods = np.asarray(periods, np.int64)
+        self.n = len(self.periods)
+        self.auto_reset = auto_reset
+        self.t = np.zeros(self.n, np.int64)
+        self.term = np.zeros(self.n, bool)
+        self.log = []
+
+    def reset_(self, is_force=True):
+        self.log.append(("reset", bool(is_force)))
+        if is_force:
+            self.t[:] = 0
+            self.term[:] = False
+        else:
+            self.t[self.term] = 0
+            self.term[:] = False
+
+    def act_random_(self):
+        self.log.append(("act_random",))
+        self._step()
+
+    def act_(self, actions):
+        self.log.append(("act", np.array(actions).copy()))
+        self._step()
+
+    def _step(self):
+        self.t += 1
+        self.term = self.t >= self.periods
+        if self.auto_reset:
+            self.t[self.term] = 0
+
+    def is_terminated(self):
+        return self.term.copy()
+
+    def reward(self):
+        return np.where(self.term, 0.0, 1.0)
+
+    def check(self):
+        self.log.append(("check",))
+
+
+def test_stop_after_n_steps_counts_like_the_reference(pkg):
+    s = pkg.StopAfterNSteps(10)
+    assert sum(s.check(None, None) for _ in range(20)) == 11          # stop_conditions.jl test: 11 trues in 20 calls
+
+
+def test_stop_if_any_and_all(pkg):
+    any_ = pkg.StopIfAny(pkg.StopAfterNSteps(10), pkg.StopAfterNSteps(3))
+    assert sum(any_.check(None, None) for _ in range(20)) == 18
+    all_ = pkg.StopIfAll(pkg.StopAfterNSteps(10), pkg.StopAfterNSteps(3))
+    assert sum(all_.check(None, None) for _ in range(20)) == 11
+
+
+def test_stop_after_n_episodes_batched(pkg):
+    env = StubVecEnv([2, 3])
+    s = pkg.StopAfterNEpisodes(2)
+    env._step()
+    assert s.check(None, env) is False                                  # nobody finished
+    env._step()
+    assert s.check(None, env) is False                                  # env 0 finished: 1 episode
+    env._step()
+    assert s.check(None, env) is True                                   # env 1 finished: 2 episodes
+
+
+def test_stop_after_no_improvement(pkg):
+    env = StubVecEnv([1])
+    s = pkg.StopAfterNoImprovement(lambda: 1.0, 10)
+    idle = StubVecEnv([100])
+    idle._step()
+    assert sum(s.check(None, idle) for _ in range(11)) == 0             # no finished episode: never evaluated
+    env._step()
+    assert sum(s.check(None, env) for _ in range(11)) == 1              # constant metric: patience runs out once
+    vals = iter(range(1, 100))
+    s2 = pkg.StopAfterNoImprovement(lambda: float(next(vals)), 10)
+    assert sum(s2.check(None, env) for _ in range(11)) == 0             # improving metric never stops
+
+
+def test_stop_signal(pkg):
+    s = pkg.StopSignal()
+    assert s.check(None, None) is False
+    s.is_stop = True
+    assert s.check(None, None) is True
+
+
+def test_hook_composition_flattens(pkg):
+    class Mock(pkg.AbstractHook):
+        pass
+    a, b, c, d = Mock(), Mock(), Mock(), Mock()
+    assert (a + b).hooks == (a, b)
+    assert (pkg.ComposedHook(a) + b).hooks == (a, b)
+    assert (a + pkg.ComposedHook(b)).hooks == (a, b)
+    assert (pkg.ComposedHook(a, b) + pkg.ComposedHook(c, d)).hooks == (a, b, c, d)
+    assert (a + b)[1] is b
+    (a + b).push("PreActStage", None, None)                              # default push is a no-op
+
+
+def test_do_every_n_steps_and_do_on_exit(pkg):
+    for n in (1, 2):
+        calls = []
+        h = pkg.DoEveryNSteps(lambda t, agent, env: calls.append(t), n=n)
+        for t in range(1, 5):
+            h.push("PostActStage", None, None)
+            assert len(calls) == t // n                                   # hooks.jl test: env.pos == 1 + div(t, n)
+        for stage in ("PreActStage", "PreExperimentStage", "PostExperimentStage"):
+            h.push(stage, None, None)
+        assert len(calls) == 4 // n
+    seen = []
+    pkg.DoOnExit(lambda agent, env: seen.append(1)).push("PostExperimentStage", None, None)
+    assert seen == [1]
+
+
+def test_batch_steps_and_rewards_per_episode(pkg):
+    env = StubVecEnv([2, 3])
+    steps, rewards = pkg.BatchStepsPerEpisode(2), pkg.TotalBatchRewardPerEpisode(2)
+    for _ in range(6):
+        env._step()
+        steps.push("PostActStage", None, env)
+        rewards.push("PostActStage", None, env)
+    assert steps[()] == [[2, 2, 2], [3, 3]]
+    assert rewards.rewards == [[1.0, 1.0, 1.0], [2.0, 2.0]]              # the terminating step pays 0
+
+
+def test_run_loop_order_and_step_count(pkg):
+    """run.jl:36-78 with the MultiThreadEnv control flow: forced reset, then per iteration
+    PreAct -> plan! -> act! -> PostAct -> check!; StopAfterNSteps(n) => exactly n act! calls."""
+    env = StubVecEnv([3, 5], auto_reset=False)
+    stages = []
+
+    class Rec(pkg.AbstractHook):
+        def push(self, stage, policy, env):
+            stages.append(stage)
+
+    class Pol(pkg.AbstractPolicy):
+        def __init__(self):
+            self.events = []
+
+        def plan(self, env):
+            self.events.append("plan")
+            return np.array([1, 2])
+
+        def push(self, stage, env, action=None):
+            self.events.append(("push", stage))
+
+        def optimise(self, stage):
+            self.events.append(("optimise", stage))
+
+    pol = Pol()
+    pkg.run(pol, env, pkg.StopAfterNSteps(4), Rec())
+    acts = [e for e in env.log if e[0] == "act"]
+    assert len(acts) == 4 and all(np.array_equal(a[1], [1, 2]) for a in acts)
+    assert env.log[0] == ("reset", True)                                 # run.jl:46
+    assert [e for e in env.log if e[0] == "reset"][1:] == [("reset", False)] * 4   # soft reset at the top of every iteration
+    assert env.log[-1] == ("check",)
+    assert stages == ["PreExperimentStage"] + ["PreActStage", "PostActStage"] * 4 + ["PostExperimentStage"]
+    per_iter = [("push", "PreActStage"), ("optimise", "PreActStage"), "plan", ("push", "PostActStage"), ("optimise", "PostActStage")]
+    assert pol.events == [("push", "PreExperimentStage")] + per_iter * 4 + [("push", "PostExperimentStage")]
+
+
+def test_run_random_policy_is_fused_into_the_step(pkg):
+    env = StubVecEnv([4, 4])
+    hook = pkg.run(pkg.RandomPolicy(), env, pkg.StopAfterNEpisodes(4), pkg.BatchStepsPerEpisode(2))
+    assert [e[0] for e in env.log].count("act_random") == 8             # 2 envs x 2 episodes of 4 steps each
+    assert hook[()] == [[4, 4], [4, 4]]
+
+
+# ---- explorers ---------------------------------------------------------------------------------
+KW = dict(eps_init=0.9, warmup_steps=100, decay_steps=100)
+
+
+def test_epsilon_schedule_reference_vectors(pkg):
+    lin = pkg.EpsilonGreedyExplorer(0.1, kind="linear", **KW)
+    assert [lin.get_eps(s) for s in (50, 100, 150, 200)] == pytest.approx([0.9, 0.9, 0.5, 0.1], rel=1e-12)
+    ex = pkg.EpsilonGreedyExplorer(0.1, kind="exp", **KW)
+    assert ex.get_eps(50) == 0.9 and ex.get_eps(150) == pytest.approx(0.5852245277701068, rel=1e-15)
+    assert ex.get_eps(2000) == pytest.approx(0.1, abs=1e-2)
+    assert pkg.EpsilonGreedyExplorer(0.3).get_eps() == 0.3               # EpsilonGreedyExplorer(ϵ): no warm-up, no decay
+
+
+def test_epsilon_schedule_host_mirror_equals_oracle_bitwise(pkg):
+    for kind in ("linear", "exp"):
+        mine = pkg.EpsilonGreedyExplorer(0.05, kind=kind, eps_init=0.95, warmup_steps=37, decay_steps=1234)
+        ex6 = O.explorer6(0.05, 0.95, 37, 1234, kind)
+        steps = list(range(1, 60)) + list(range(900, 1400, 7))
+        assert [mine.get_eps(s) for s in steps] == [O.get_eps(ex6, s) for s in steps]
+
+
+def test_explorer_prob_reference_vectors(pkg):
+    values = [0.1, 0.5, 0.5, 0.3]
+    tie = pkg.EpsilonGreedyExplorer(0.1, kind="linear", is_break_tie=True, **KW)
+    assert tie.prob(values) == pytest.approx([0.225, 0.275, 0.275, 0.225], rel=1e-12)
+    assert tie.prob(values, 2) == pytest.approx(0.275, rel=1e-12)
+    first = pkg.EpsilonGreedyExplorer(0.1, kind="linear", is_break_tie=False, **KW)
+    assert first.prob(values) == pytest.approx([0.225, 0.32499999999999996, 0.225, 0.225], rel=1e-12)
+    assert first.prob(values, 2) == pytest.approx(0.32500000000000007, rel=1e-12)
+    for brk, e in ((True, tie), (False, first)):
+        np.testing.assert_allclose(O.egreedy_prob(O.explorer6(0.1, 0.9, 100, 100, "linear", brk), 1, values), e.prob(values), rtol=1e-15)
+    g = pkg.GreedyExplorer()
+    assert g.plan_values(values) == 2 and g.prob(values) == [0.0, 1.0, 0.0, 0.0] and g.prob(values, 2) == 1.0
+
+
+def test_oracle_egreedy_plan_visits_all_actions_and_follows_prob():
+    """epsilon_greedy_explorer.jl test: 300 plans at eps 0.9 visit all 4 actions (both tie modes); the empirical
+    frequencies follow prob()."""
+    values = np.array([0.1, 0.5, 0.5, 0.3], np.float32)
+    n = 40000
+    qv = np.repeat(values[:, None], n, axis=1)
+    for brk in (True, False):
+        ex6 = O.explorer6(0.1, 0.9, 10 ** 9, 100, "linear", brk)          # long warm-up: eps stays 0.9
+        rng = O.splitmix_states_fast(n, 77)
+        a = O.egreedy_plan(ex6, 1, qv, rng)
+        assert set(np.unique(a[:300])) == {1, 2, 3, 4}
+        freq = np.bincount(a, minlength=5)[1:] / n
+        np.testing.assert_allclose(freq, O.egreedy_prob(ex6, 1, values), atol=0.01)
+    # eps = 0: greedy, but one uniform is still drawn per column (the reference always calls rand(s.rng))
+    rng = O.splitmix_states_fast(8, 5)
+    before = rng.copy()
+    a = O.egreedy_plan(O.explorer6(0.0, 0.0), 1, qv[:, :8], rng)
+    assert np.all(a == 2) and not np.array_equal(rng, before)
+
+
+def test_batch_explorer_advances_the_step_per_column(pkg):
+    """batch_explorer.jl:15-21: column i of one batched plan! sees get_eps(step + i)."""
+    n = 5000
+    ex6 = O.explorer6(0.0, 1.0, 0, n, "linear")                          # eps falls from 1 to 0 across ONE batch
+    qv = np.repeat(np.array([[0.0], [1.0]], np.float32), n, axis=1)
+    a = O.egreedy_plan(ex6, 1, qv, O.splitmix_states_fast(n, 3))
+    greedy = a == 2
+    assert greedy[: n // 10].mean() < 0.62 and greedy[-n // 10:].mean() > 0.95
+    ex = pkg.EpsilonGreedyExplorer(0.0, kind="linear", eps_init=1.0, warmup_steps=0, decay_steps=n)
+    ex.advance(n)
+    assert ex.step == n + 1 and ex.get_eps() == 0.0
+    st = pkg.EpsilonGreedyExplorer(0.1, kind="exp", eps_init=0.9, warmup_steps=3, decay_steps=7, step=11, is_break_tie=True).as_struct()
+    assert (st.eps_stable, st.eps_init, st.warmup_steps, st.decay_steps, st.step, st.kind, st.is_break_tie) == (0.1, 0.9, 3, 7, 11, 1, 1)
+
+
+def test_insert_sample_ratio_controller(pkg):
+    c = pkg.InsertSampleRatioController(ratio=0.5, threshold=4)
+    sampled = []
+    for _ in range(12):
+        c.on_insert()
+        k = 0
+        while c.on_sample():
+            k += 1
+        sampled.append(k)
+    assert sampled[:3] == [0, 0, 0] and sum(sampled) == c.n_sampled
+    assert c.n_sampled == int((c.n_inserted - c.threshold) * c.ratio) + 1   # one batch per two insertions after the threshold

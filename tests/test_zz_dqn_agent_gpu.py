@@ -1,0 +1,133 @@
+"""GPU tests of the DQN action path (BASELINE config 5 driven through run()):
+b200rl_net_q_explore = BatchExplorer(EpsilonGreedyExplorer) with the per-column decay schedule, bit-exact against the
+oracle restatement of epsilon_greedy_explorer.jl:69-112 / batch_explorer.jl:15-21 given the same Q table and streams;
+Agent(QBasedPolicy(DQNLearner, explorer), Trajectory(prioritised ring, BatchSampler, InsertSampleRatioController)) end
+to end through run(policy, env, stop, hook)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def q_explore(pkg, ctx, net, obs, rng, explorer):
+    """Returns (actions, advanced streams) of one b200rl_net_q_explore call."""
+    n = obs.shape[1]
+    d_obs = ctx.malloc(obs.nbytes); ctx.h2d(d_obs, np.asfortranarray(obs))
+    d_rng = ctx.malloc(n * 32); ctx.h2d(d_rng, rng)
+    d_act = ctx.malloc(n * 4)
+    st = explorer.as_struct()
+    pkg._lib.check(ctx.lib.b200rl_net_q_explore(net.h, C.c_void_p(d_obs), n, C.c_void_p(d_rng), C.byref(st), C.c_void_p(d_act)))
+    a = np.empty(n, np.int32); ctx.d2h(a, d_act)
+    r = np.empty((n, 4), np.uint64); ctx.d2h(r, d_rng)
+    for d in (d_obs, d_rng, d_act):
+        ctx.free(d)
+    return a, r
+
+
+@pytest.mark.parametrize("kind,brk,na,hidden", [("linear", False, 2, 128), ("exp", False, 3, 64), ("linear", True, 2, 128), ("exp", True, 4, 64)])
+def test_q_explore_bit_exact_given_the_q_table(pkg, ctx, kind, brk, na, hidden):
+    ns, n = 4, 6000
+    desc = O.ac_desc(ns, hidden, na)
+    p = O.glorot_params(desc, 31, q_net=True)
+    net = pkg.Network(ctx, ns, hidden, na, p, kind=pkg.KIND_Q)
+    obs = np.asfortranarray(np.random.default_rng(1).standard_normal((ns, n)).astype(np.float32))
+    qv = net.values(obs)                                      # the device's own Q table: selection parity is then exact
+    # the batch straddles warm-up (eps_init), the decay and (linear) the stable tail
+    ex = pkg.EpsilonGreedyExplorer(0.05, kind=kind, eps_init=0.9, warmup_steps=1500, decay_steps=3000, step=500, is_break_tie=brk)
+    ex6 = O.explorer6(0.05, 0.9, 1500, 3000, kind, brk)
+    seeds = O.splitmix_states_fast(n, 99)
+    a, r = q_explore(pkg, ctx, net, obs, seeds, ex)
+    ref_rng = seeds.copy()
+    ref = O.egreedy_plan(ex6, 500, qv, ref_rng)
+    assert np.array_equal(a, ref)
+    assert np.array_equal(r, ref_rng)
+    greedy = qv.argmax(0) + 1
+    assert (a[:1000] == greedy[:1000]).mean() < (a[-1000:] == greedy[-1000:]).mean()   # eps decays across the batch
+    net.close()
+
+
+def test_q_explore_break_tie_on_an_all_tie_table_and_zero_epsilon(pkg, ctx):
+    ns, na, n = 4, 3, 30000
+    desc = O.ac_desc(ns, 64, na)
+    net = pkg.Network(ctx, ns, 64, na, np.zeros(O.q_nparams(desc), np.float32), kind=pkg.KIND_Q)   # Q == 0 everywhere: every action ties
+    obs = np.asfortranarray(np.random.default_rng(2).standard_normal((ns, n)).astype(np.float32))
+    qv = np.zeros((na, n), np.float32, order="F")
+    seeds = O.splitmix_states_fast(n, 5)
+    for brk in (True, False):
+        ex = pkg.EpsilonGreedyExplorer(0.0, eps_init=0.0, is_break_tie=brk)      # eps = 0: the uniform is still drawn
+        a, r = q_explore(pkg, ctx, net, obs, seeds, ex)
+        ref_rng = seeds.copy()
+        ref = O.egreedy_plan(O.explorer6(0.0, 0.0, 0, 0, "linear", brk), 1, qv, ref_rng)
+        assert np.array_equal(a, ref) and np.array_equal(r, ref_rng) and not np.array_equal(r, seeds)
+        if brk:
+            np.testing.assert_allclose(np.bincount(a, minlength=na + 1)[1:] / n, 1.0 / na, atol=0.01)
+        else:
+            assert np.all(a == 1)                                                 # findmax: the first maximum
+    net.close()
+
+
+def test_q_explore_rejects_bad_arguments(pkg, ctx):
+    desc = O.ac_desc(4, 64, 2)
+    net = pkg.Network(ctx, 4, 64, 2, O.glorot_params(desc, 1, q_net=True), kind=pkg.KIND_Q)
+    d = ctx.malloc(1024)
+    st = pkg.EpsilonGreedyExplorer(1.5).as_struct()
+    assert ctx.lib.b200rl_net_q_explore(net.h, C.c_void_p(d), 8, C.c_void_p(d), C.byref(st), C.c_void_p(d)) == pkg._lib.ERR_INVALID
+    st = pkg.EpsilonGreedyExplorer(0.1).as_struct()
+    assert ctx.lib.b200rl_net_q_explore(net.h, C.c_void_p(d), 8, None, C.byref(st), C.c_void_p(d)) == pkg._lib.ERR_INVALID
+    ac = pkg.Network(ctx, 4, 64, 2, O.glorot_params(desc, 1), kind=pkg.KIND_CATEGORICAL)
+    assert ctx.lib.b200rl_net_q_explore(ac.h, C.c_void_p(d), 8, C.c_void_p(d), C.byref(st), C.c_void_p(d)) == pkg._lib.ERR_INVALID
+    ctx.free(d); net.close(); ac.close()
+
+
+@pytest.mark.parametrize("host_actions", [False, True])
+def test_dqn_agent_through_run(pkg, ctx, host_actions):
+    """Config-5 shape at test size: prioritised ring, eps-greedy exploration with a decay schedule, one update per
+    inserted frame after a threshold, target sync — driven by run(agent, env, StopAfterNSteps, hook)."""
+    lanes, cap, B, steps, hidden = 256, 64, 512, 48, 128
+    env_seeds = O.splitmix_states_fast(lanes, 21)
+    env = pkg.B200VecEnv(ctx, "CartPole", lanes, env_seeds, auto_reset=True)
+    desc = O.ac_desc(4, hidden, 2)
+    p0 = O.glorot_params(desc, 8, q_net=True)
+    net = pkg.Network(ctx, 4, hidden, 2, p0.copy(), kind=pkg.KIND_Q)
+    traj = pkg.Trajectory(ctx, 4, cap, lanes=lanes, batch_size=B, sampler_rng=O.splitmix_states_fast(B, 22), prioritized=True)
+    traj.controller = pkg.InsertSampleRatioController(ratio=1.0, threshold=8)
+    learner = pkg.DQNLearner(ctx, net, traj, pkg.dqn_config(target_update_freq=10))
+    explorer = pkg.EpsilonGreedyExplorer(0.01, kind="exp", eps_init=1.0, warmup_steps=2 * lanes, decay_steps=10 * lanes)
+    ex_seeds = O.splitmix_states_fast(lanes, 23)
+    policy = pkg.QBasedPolicy(ctx, learner, explorer, ex_seeds, lanes)
+    agent = pkg.Agent(policy, traj, host_actions=host_actions)
+
+    # the first planned batch, before any update: same streams + schedule as the oracle on the device's Q table
+    probe = env.copy(); probe.reset_(is_force=True)
+    qv0 = net.values(probe.state())
+    ref_rng = ex_seeds.copy()
+    a0 = O.egreedy_plan(O.explorer6(0.01, 1.0, 2 * lanes, 10 * lanes, "exp"), 1, qv0, ref_rng)
+    probe.close()
+
+    first = {}
+
+    class Spy(pkg.AbstractHook):
+        def push(self, stage, policy_, env_):
+            if stage == "PostActStage" and "a" not in first:
+                first["a"] = env_.last_action(); first["rng"] = policy.explorer_rng()
+
+    hook = pkg.run(agent, env, pkg.StopAfterNSteps(steps), Spy() + pkg.BatchStepsPerEpisode(lanes))
+    assert np.array_equal(first["a"], a0) and np.array_equal(first["rng"], ref_rng)
+    assert len(traj) == steps                                   # one frame per env step; the first state is frame 0
+    assert explorer.step == 1 + steps * lanes                   # BatchExplorer: one inner step per column
+    c = traj.controller
+    assert c.n_inserted == steps and c.n_sampled == steps - 8 + 1
+    assert not np.array_equal(net.get(), p0)                    # the learner trained
+    assert np.array_equal(net.get(pkg.learners.NET_TARGET), net.get()) == ((c.n_sampled % 10) == 0)
+    done = sum(len(s) for s in hook[1][()])
+    assert done == env.episode_stats()["episodes"] > 0          # host hook and device-side statistics agree
+    with pytest.raises(RuntimeError):                            # re-entry on a non-empty ring is refused
+        pkg.run(agent, env, pkg.StopAfterNSteps(1))
+    # the ring holds what the env produced: replay the stored actions through the oracle env
+    b = traj.sample(beta=0.4)
+    assert set(np.unique(b["action"])) <= {1, 2} and np.isfinite(b["state"]).all()
+    policy.close(); traj.close(); net.close(); env.close()
