@@ -144,6 +144,22 @@ static inline float normlogpdf1(float mu, float sigma, float x) {
     float d = x - mu;
     return -0.5f * ((std::log(v) + (d * d) / v) + LOG2PI_F);
 }
+// normlogpdf(mu, sigma, x; eps = 1f-8) (distributions.jl:18-21): z = (x - mu) / (sigma + eps); -(z^2 + log2pi) / 2 - log(sigma + eps)
+static inline float normlogpdf(float mu, float sigma, float x) {
+    float z = (x - mu) / (sigma + 1e-8f);
+    return -(z * z + LOG2PI_F) / 2.0f - std::log(sigma + 1e-8f);
+}
+// diagnormlogpdf(mu, sigma, x; eps = 1f-8) over a d-vector (distributions.jl:31-34):
+// v = (sigma + eps)^2; -0.5 * (log(prod(v)) + sum((x - mu)^2 / v) + d * log2pi)
+static inline float diagnormlogpdf(const float* mu, const float* sigma, const float* x, int d) {
+    float prod = 1.f, sum = 0.f;
+    for (int i = 0; i < d; ++i) {
+        float s = sigma[i] + 1e-8f, v = s * s, e = x[i] - mu[i];
+        prod *= v;
+        sum += (e * e) / v;
+    }
+    return -0.5f * ((std::log(prod) + sum) + (float)d * LOG2PI_F);
+}
 // Standard normal from two Float32 uniforms of the policy stream (Box–Muller; the reference's
 // randn ziggurat is not restated — SURVEY Appendix A.4 "host-independent noise definition").
 static inline float randn_boxmuller(jl::Xoshiro& g) {

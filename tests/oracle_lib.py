@@ -64,6 +64,7 @@ def lib():
         "orc_traj_push": (None, [vp, vp, vp, vp, vp]),
         "orc_traj_sample": (None, [vp, i32, vp, i64, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "orc_traj_update_priority": (None, [vp, vp, vp, i64]), "orc_traj_total_priority": (f32, [vp]),
+        "orc_normlogpdf": (f32, [f32, f32, f32]), "orc_normlogpdf1": (f32, [f32, f32, f32]), "orc_diagnormlogpdf": (f32, [vp, vp, vp, i32]),
         "orc_get_eps": (f64, [vp, i64]), "orc_egreedy_prob": (None, [vp, i64, vp, i32, vp]),
         "orc_egreedy_plan": (None, [vp, i64, vp, i32, i64, vp, vp]),
         "orc_ppo_iteration": (f64, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_uint32, vp]),

@@ -144,14 +144,26 @@ def test_clip_by_global_norm():
     assert np.array_equal(c, g) and gn == pytest.approx(13.0)
 
 
-def test_normlogpdf_closed_form_and_target_sync():
-    # distributions.jl test: logpdf(Normal(10, 5), 4)
-    desc = O.ac_desc(3, 8, 1, O.ACT_TANH, True)
-    ref = -0.5 * np.log(2 * np.pi * 25) - (4 - 10) ** 2 / 50
-    s = 5.0 + 1e-8
-    ours = -0.5 * ((np.log(s * s) + 36 / (s * s)) + np.log(2 * np.pi))
-    assert ours == pytest.approx(ref, rel=1e-7)
+def test_normlogpdf_reference_vectors_and_target_sync():
+    """RLCore/test/utils/distributions.jl:19-62: normlogpdf(10, 5, 4) ~ logpdf(Normal(10, 5), 4) and
+    diagnormlogpdf([10, 1], [5, 6], [4, 3]) ~ logpdf(MvNormal([10, 1], Diagonal([25, 36])), [4, 3]) — Distributions.jl's
+    values are the closed forms scipy evaluates."""
+    from scipy import stats
     L = O.lib()
+    f = O.C.c_float
+    ref1 = stats.norm(10.0, 5.0).logpdf(4.0)
+    assert L.orc_normlogpdf(f(10), f(5), f(4)) == pytest.approx(ref1, rel=2e-7)
+    assert L.orc_normlogpdf1(f(10), f(5), f(4)) == pytest.approx(ref1, rel=2e-7)
+    mu, sg, x = (np.array(v, np.float32) for v in ([10, 1], [5, 6], [4, 3]))
+    ref2 = stats.multivariate_normal(mean=[10, 1], cov=np.diag([25.0, 36.0])).logpdf([4, 3])
+    assert L.orc_diagnormlogpdf(O._p(mu), O._p(sg), O._p(x), 2) == pytest.approx(ref2, rel=3e-7)
+    # test/utils/networks.jl:59-71 identity: a d = 1 diagnormlogpdf is the univariate form the Gaussian head evaluates, bit for bit
+    rng = np.random.default_rng(0)
+    for m, s_, xx in rng.standard_normal((200, 3)).astype(np.float32):
+        s_ = np.float32(abs(s_) + 0.05)
+        a = L.orc_diagnormlogpdf(O._p(np.array([m], np.float32)), O._p(np.array([s_], np.float32)), O._p(np.array([xx], np.float32)), 1)
+        assert a == L.orc_normlogpdf1(f(m), f(s_), f(xx))
+        assert a == pytest.approx(stats.norm(float(m), float(s_)).logpdf(float(xx)), rel=2e-5, abs=2e-6)
     t = np.arange(5, dtype=np.float32); m = np.ones(5, np.float32)
     L.orc_target_sync(O._p(t), O._p(m), 5, O.C.c_float(0.0))
     assert np.array_equal(t, m)                                  # rho = 0: hard copy
