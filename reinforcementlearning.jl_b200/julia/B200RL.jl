@@ -263,6 +263,14 @@ function Base.getindex(net::B200Network, which::Integer, n::Integer)
     out
 end
 
+"Import parameters / optimiser state (`which`: 0 params | 2 Adam m | 3 Adam v | 4 beta^t (2) | 5 target params)."
+function Base.setindex!(net::B200Network, v::Vector{Float32}, which::Integer)
+    GC.@preserve v check(ccall((:b200rl_net_set, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Int64), net.h, which, v, length(v)))
+    v
+end
+"optimise!(::TargetNetwork): target = ρ * target + (1 - ρ) * model (target_network.jl:70-88); ρ = 0 is the hard copy."
+target_sync!(net::B200Network, ρ::Real = 0f0) = check(ccall((:b200rl_net_target_sync, LIB), Cint, (Ptr{Cvoid}, Cfloat), net.h, ρ))
+
 struct OnPolicyConfigC
     gamma::Cfloat; lambda::Cfloat; clip_range::Cfloat; max_grad_norm::Cfloat; w_actor::Cfloat; w_critic::Cfloat; w_entropy::Cfloat
     lr::Cfloat; beta1::Cfloat; beta2::Cfloat; eps::Cfloat; min_sigma::Cfloat; max_sigma::Cfloat
