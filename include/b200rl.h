@@ -84,7 +84,9 @@ typedef enum {
     B200RL_FIELD_T = 4,         /* (N,) int32     env.t                                          */
     B200RL_FIELD_RNG = 5,       /* (4, N) uint64  raw Xoshiro256++ state s0..s3 per env          */
     B200RL_FIELD_FLAGS = 6,     /* (N,) uint8     bit0 terminal, bit1 already auto-reset         */
-    B200RL_FIELD_ACTION = 7     /* (N,) int32 | T last action                                    */
+    B200RL_FIELD_ACTION = 7,    /* (N,) int32 | T last action                                    */
+    B200RL_FIELD_EPISODE_RETURN = 8,  /* (N,) float32  running return of the episode in progress (device-side hooks)  */
+    B200RL_FIELD_EPISODE_STATS = 9    /* (4,) float64  the counters b200rl_env_episode_stats reads (checkpoints)      */
 } b200rl_field;
 
 /* Final field values of the reference's params structs (already rounded to T by the
@@ -140,6 +142,8 @@ int b200rl_env_step(b200rl_env* env, const void* actions, int actions_on_device,
 int b200rl_env_step_random(b200rl_env* env, int auto_reset);
 /* state(env) / reward(env) / is_terminated(env) ...: synchronous copy-out to host */
 int b200rl_env_get(b200rl_env* env, int field, void* host_dst, size_t bytes);
+/* every field but TERMINAL (bit 0 of FLAGS) is settable, so an env can be restored from a checkpoint:
+ * STATE, OBS (a separate buffer only for Pendulum), REWARD, FLAGS, T, RNG, ACTION, EPISODE_RETURN, EPISODE_STATS */
 int b200rl_env_set(b200rl_env* env, int field, const void* host_src, size_t bytes);
 /* zero-copy device pointer of a field for fused consumers */
 int b200rl_env_ptr(b200rl_env* env, int field, void** dptr_out);
@@ -288,6 +292,13 @@ int b200rl_onpolicy_update(b200rl_onpolicy* agent, const int32_t* perm_host, flo
 /* field: 0 state (ns,N,T+1) | 1 action | 2 logp | 3 reward | 4 terminal u8 | 5 value (N,T+1) |
  * 6 advantage | 7 return | 8 policy rng (4,N) u64 | 9 {adv mean, inv std} */
 int b200rl_onpolicy_get(b200rl_onpolicy* agent, int field, void* host_dst, size_t bytes);
+/* Checkpoint / resume (the JLD2 hook pattern, docs/src/How_to_use_hooks.md:124-167): together with b200rl_net_get/set
+ * (parameters, Adam moments, beta^t, target) and b200rl_env_get/set (every env field) these restore a run bit for bit, at a
+ * rollout boundary or in the middle of a rollout.  onpolicy_set takes fields 0-5 and 8 of b200rl_onpolicy_get;
+ * counters3 = {rollout fill level t, updates done by the agent (keys the minibatch permutation), optimiser steps of the net}. */
+int b200rl_onpolicy_set(b200rl_onpolicy* agent, int field, const void* host_src, size_t bytes);
+int b200rl_onpolicy_export_state(b200rl_onpolicy* agent, int64_t* counters3_out);
+int b200rl_onpolicy_import_state(b200rl_onpolicy* agent, const int64_t* counters3);
 
 /* measurement aid: average device ms of `reps` back-to-back launches of one hot-path kernel on the
  * agent's tensors (0 loss+backward, 1 policy inference, 2 env step, 3 GAE, 4 reduce+clip+Adam) */

@@ -15,7 +15,7 @@ ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_ACTION, ERR_NCCL, ERR_OOM = -1, -2, 
 
 ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR, ENV_CARTPOLE_CONTINUOUS, ENV_MOUNTAINCAR_CONTINUOUS = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
-FIELD_STATE, FIELD_OBS, FIELD_REWARD, FIELD_TERMINAL, FIELD_T, FIELD_RNG, FIELD_FLAGS, FIELD_ACTION = range(8)
+FIELD_STATE, FIELD_OBS, FIELD_REWARD, FIELD_TERMINAL, FIELD_T, FIELD_RNG, FIELD_FLAGS, FIELD_ACTION, FIELD_EPISODE_RETURN, FIELD_EPISODE_STATS = range(10)
 
 
 class B200RLError(RuntimeError):
@@ -134,6 +134,9 @@ SIGNATURES = {
     "b200rl_onpolicy_fill": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "b200rl_onpolicy_update": (_i32, [_vp, _vp, _vp]),
     "b200rl_onpolicy_get": (_i32, [_vp, _i32, _vp, _sz]),
+    "b200rl_onpolicy_set": (_i32, [_vp, _i32, _vp, _sz]),
+    "b200rl_onpolicy_export_state": (_i32, [_vp, _vp]),
+    "b200rl_onpolicy_import_state": (_i32, [_vp, _vp]),
     "b200rl_onpolicy_time_kernel": (_i32, [_vp, _i32, _i32, C.POINTER(_f32)]),
     "b200rl_dqn_update": (_i32, [_vp, _vp, _vp, _vp]),
     "b200rl_dqn_last_td": (_i32, [_vp, _vp, _vp, _i64]),

@@ -615,6 +615,42 @@ int b200rl_onpolicy_get(b200rl_onpolicy* a, int field, void* host_dst, size_t by
     return B200RL_OK;
 }
 
+/* checkpoint import: fields 0-5 and 8 of b200rl_onpolicy_get (advantages / returns / normalisation are recomputed by update) */
+int b200rl_onpolicy_set(b200rl_onpolicy* a, int field, const void* host_src, size_t bytes) {
+    REQUIRE(a && host_src, B200RL_ERR_INVALID, "null argument");
+    TRY(ctx_bind(a->ctx));
+    size_t N = (size_t)a->N, T = (size_t)a->T;
+    void* dst = nullptr;
+    size_t need = 0;
+    switch (field) {
+        case 0: dst = a->states; need = N * a->ns * (T + 1) * 4; break;
+        case 1: dst = a->actions; need = N * T * 4; break;
+        case 2: dst = a->logp; need = N * T * 4; break;
+        case 3: dst = a->rewards; need = N * T * 4; break;
+        case 4: dst = a->terminals; need = N * T; break;
+        case 5: dst = a->values; need = N * (T + 1) * 4; break;
+        case 8: dst = a->rng; need = N * 32; break;
+        default: REQUIRE(false, B200RL_ERR_INVALID, "field not settable");
+    }
+    REQUIRE(bytes >= need, B200RL_ERR_INVALID, "source too small");
+    CUDA_TRY(cudaMemcpyAsync(dst, host_src, need, cudaMemcpyHostToDevice, a->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->ctx->stream));
+    return B200RL_OK;
+}
+int b200rl_onpolicy_export_state(b200rl_onpolicy* a, int64_t* c3) {
+    REQUIRE(a && c3, B200RL_ERR_INVALID, "null argument");
+    c3[0] = a->t; c3[1] = (int64_t)a->n_updates; c3[2] = (int64_t)a->net->n_updates;
+    return B200RL_OK;
+}
+int b200rl_onpolicy_import_state(b200rl_onpolicy* a, const int64_t* c3) {
+    REQUIRE(a && c3, B200RL_ERR_INVALID, "null argument");
+    REQUIRE(c3[0] >= 0 && c3[0] <= a->T && c3[1] >= 0 && c3[2] >= 0, B200RL_ERR_INVALID, "counters out of range");
+    a->t = (int)c3[0]; a->n_updates = (uint64_t)c3[1]; a->net->n_updates = (uint64_t)c3[2];
+    a->bootstrap_done = false;   // column T of states / values is rewritten from the env's observation by the next update
+    b200rl_env_internal_set_traj_targets(a->env, nullptr, nullptr);
+    return B200RL_OK;
+}
+
 /* Measurement aid (bench.py roofline): average device time of `reps` back-to-back launches of one
  * hot-path kernel on the agent's current tensors, CUDA events on the ctx stream.
  * which: 0 loss+backward minibatch kernel (K7) | 1 policy inference (K6) | 2 env step (K1, mutates the env) |

@@ -219,6 +219,8 @@ static size_t field_bytes(const b200rl_env* e, int field) {
         case B200RL_FIELD_T: return N * 4;
         case B200RL_FIELD_RNG: return N * 32;
         case B200RL_FIELD_ACTION: return N * 4;
+        case B200RL_FIELD_EPISODE_RETURN: return N * 4;
+        case B200RL_FIELD_EPISODE_STATS: return 4 * sizeof(double);
     }
     return 0;
 }
@@ -231,6 +233,8 @@ static void* field_ptr(const b200rl_env* e, int field) {
         case B200RL_FIELD_T: return e->a.t;
         case B200RL_FIELD_RNG: return e->a.rng;
         case B200RL_FIELD_ACTION: return e->a.action;
+        case B200RL_FIELD_EPISODE_RETURN: return e->a.ep_ret;
+        case B200RL_FIELD_EPISODE_STATS: return e->a.stats;
     }
     return nullptr;
 }
@@ -417,6 +421,7 @@ int b200rl_env_get(b200rl_env* e, int field, void* host_dst, size_t bytes) {
         uint8_t* p = (uint8_t*)host_dst;
         for (size_t i = 0; i < need; ++i) p[i] &= 1;
     }
+    if (field == B200RL_FIELD_EPISODE_STATS) ((double*)host_dst)[3] = (double)e->steps_launched * (double)e->N;   // host-side counter
     return B200RL_OK;
 }
 
@@ -424,10 +429,11 @@ int b200rl_env_set(b200rl_env* e, int field, const void* host_src, size_t bytes)
     REQUIRE(e && host_src, B200RL_ERR_INVALID, "null argument");
     TRY(ctx_bind(e->ctx));
     size_t need = field_bytes(e, field);
-    REQUIRE(need != 0 && field != B200RL_FIELD_OBS && field != B200RL_FIELD_TERMINAL, B200RL_ERR_INVALID, "field not settable");
+    REQUIRE(need != 0 && field != B200RL_FIELD_TERMINAL, B200RL_ERR_INVALID, "field not settable (TERMINAL is bit 0 of FLAGS)");
     REQUIRE(bytes >= need, B200RL_ERR_INVALID, "source too small");
     CUDA_TRY(cudaMemcpyAsync(field_ptr(e, field), host_src, need, cudaMemcpyHostToDevice, e->ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(e->ctx->stream));
+    if (field == B200RL_FIELD_EPISODE_STATS) e->steps_launched = (uint64_t)(((const double*)host_src)[3] / (double)e->N + 0.5);
     return B200RL_OK;
 }
 

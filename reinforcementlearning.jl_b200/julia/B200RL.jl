@@ -333,6 +333,49 @@ function RLBase.optimise!(a::B200OnPolicyAgent, ::PostActStage)
 end
 RLBase.optimise!(::B200OnPolicyAgent, ::AbstractStage) = nothing
 
+# ---- checkpoint / resume (the JLD2 hook pattern, docs/src/How_to_use_hooks.md:124-167) ---------------
+# `DoEveryNSteps(n = 10_000) do t, agent, env; JLD2.jldsave("ckpt_$t.jld2"; B200RL.checkpoint(agent)...) end`
+const ENV_FIELDS = (state = 0, obs = 1, reward = 2, flags = 6, t = 4, rng = 5, action = 7, episode_return = 8, episode_stats = 9)
+function env_field_array(env::B200VecEnv{T}, name::Symbol) where {T}
+    n = env.n
+    name === :state ? Matrix{T}(undef, NS[env.kind], n) : name === :obs ? Matrix{T}(undef, NOBS[env.kind], n) :
+    name === :reward ? Vector{T}(undef, n) : name === :flags ? Vector{UInt8}(undef, n) : name === :t ? Vector{Int32}(undef, n) :
+    name === :rng ? Matrix{UInt64}(undef, 4, n) : name === :action ? (env.continuous ? Vector{Float32}(undef, n) : Vector{Int32}(undef, n)) :
+    name === :episode_return ? Vector{Float32}(undef, n) : Vector{Float64}(undef, 4)
+end
+"Copy the whole device state of an on-policy run out: NamedTuple of plain arrays (`JLD2.jldsave(path; ckpt...)`)."
+function checkpoint(a::B200OnPolicyAgent)
+    env, net = a.env, a.net
+    envs = map(keys(ENV_FIELDS)) do name
+        dst = env_field_array(env, name)
+        GC.@preserve dst check(ccall((:b200rl_env_get, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t), env.h, ENV_FIELDS[name], dst, sizeof(dst)))
+        dst
+    end
+    np = Ref{Int64}(0)
+    check(ccall((:b200rl_net_nparams, LIB), Cint, (Ref{NetDescC}, Ref{Int64}), Ref(net.desc), np))
+    counters = zeros(Int64, 3)
+    GC.@preserve counters check(ccall((:b200rl_onpolicy_export_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), a.h, counters))
+    rng = Matrix{UInt64}(undef, 4, env.n)
+    GC.@preserve rng check(ccall((:b200rl_onpolicy_get, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t), a.h, 8, rng, sizeof(rng)))
+    counters[1] == 0 || @warn "B200RL.checkpoint: taken in the middle of a rollout; the Python mirror also saves the rollout columns (checkpoint.py)"
+    (env = NamedTuple{keys(ENV_FIELDS)}(envs), params = net[0, np[]], adam_m = net[2, np[]], adam_v = net[3, np[]], beta_t = net[4, 2],
+     counters = counters, policy_rng = rng)
+end
+"Put a `checkpoint` back into a freshly constructed agent (same env kind / N, same network shape, same hyper-parameters)."
+function restore!(a::B200OnPolicyAgent, ck)
+    for name in keys(ENV_FIELDS)
+        name === :obs && a.env.kind != 1 && continue            # the observation is the state (one buffer) except for Pendulum
+        src = getfield(ck.env, name)
+        GC.@preserve src check(ccall((:b200rl_env_set, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t), a.env.h, ENV_FIELDS[name], src, sizeof(src)))
+    end
+    a.net[0] = ck.params; a.net[2] = ck.adam_m; a.net[3] = ck.adam_v; a.net[4] = ck.beta_t
+    rng, counters = ck.policy_rng, ck.counters
+    GC.@preserve rng check(ccall((:b200rl_onpolicy_set, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t), a.h, 8, rng, sizeof(rng)))
+    GC.@preserve counters check(ccall((:b200rl_onpolicy_import_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), a.h, counters))
+    a.t = Int(counters[1])
+    a
+end
+
 # ---- DQN: device trajectory + learner + explorer (BASELINE config 5) --------------------------------
 # InsertSampleRatioController(ratio, threshold) (RLTrajectories 0.4; docs/src/How_to_implement_a_new_algorithm.md:108); one insertion = one frame
 Base.@kwdef mutable struct InsertSampleRatio

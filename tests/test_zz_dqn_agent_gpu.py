@@ -131,3 +131,69 @@ def test_dqn_agent_through_run(pkg, ctx, host_actions):
     b = traj.sample(beta=0.4)
     assert set(np.unique(b["action"])) <= {1, 2} and np.isfinite(b["state"]).all()
     policy.close(); traj.close(); net.close(); env.close()
+
+
+# ---- checkpoint / resume (the JLD2 hook pattern of docs/src/How_to_use_hooks.md:124-167) ---------------------
+def _ppo_objects(pkg, ctx, kind, n, T, seed):
+    gauss = kind == "Pendulum"
+    env = pkg.B200VecEnv(ctx, kind, n, O.splitmix_states_fast(n, seed), auto_reset=True)
+    n_in, n_out = (3, 1) if gauss else (4, 2)
+    desc = O.ac_desc(n_in, 64, n_out, 0, gauss)
+    net = pkg.Network(ctx, n_in, 64, n_out, O.glorot_params(desc, seed + 1), kind=pkg.KIND_GAUSSIAN if gauss else pkg.KIND_CATEGORICAL)
+    cfg = pkg.onpolicy_config(update_freq=T, n_epochs=2, n_microbatches=2, algo="a2c" if gauss else "ppo")
+    agent = pkg.OnPolicyAgent(ctx, net, env, cfg, O.splitmix_states_fast(n, seed + 2), host_actions=False)
+    return env, net, agent
+
+
+def _continue(agent, T, t_now):
+    """finish the current rollout, update, one more full iteration, then 3 steps into the next rollout"""
+    agent.collect(T - t_now); s1 = agent.update(want_stats=True)
+    agent.collect(T); s2 = agent.update(want_stats=True)
+    agent.collect(3)
+    return np.concatenate([s1, s2])
+
+
+@pytest.mark.parametrize("kind,mid", [("CartPole", 3), ("CartPole", 0), ("Pendulum", 5)])
+def test_checkpoint_resume_is_bit_identical(pkg, ctx, tmp_path, kind, mid):
+    n, T = 640, 8
+    env, net, agent = _ppo_objects(pkg, ctx, kind, n, T, 40)
+    env.reset_(is_force=True)
+    agent.collect(T); agent.update()
+    agent.collect(T); agent.update()
+    if mid:
+        agent.collect(mid)                                               # checkpoint in the middle of a rollout
+    ck = pkg.checkpoint.checkpoint(env=env, net=net, agent=agent)
+    path = str(tmp_path / "ck.npz")
+    pkg.checkpoint.save(path, ck)
+    stats_a = _continue(agent, T, mid)
+    final_a = pkg.checkpoint.checkpoint(env=env, net=net, agent=agent)
+
+    # fresh objects with DIFFERENT seeds / parameters: everything that matters must come from the checkpoint
+    env2, net2, agent2 = _ppo_objects(pkg, ctx, kind, n, T, 777)
+    env2.reset_(is_force=True)
+    agent2.collect(2)
+    pkg.checkpoint.restore(pkg.checkpoint.load(path), env=env2, net=net2, agent=agent2)
+    assert agent2.fill() == (mid, T)
+    back = pkg.checkpoint.checkpoint(env=env2, net=net2, agent=agent2)
+    assert sorted(back) == sorted(ck)
+    for k in ck:
+        assert np.array_equal(np.asarray(back[k]), np.asarray(ck[k])), k     # restore o checkpoint = identity
+    stats_b = _continue(agent2, T, mid)
+    final_b = pkg.checkpoint.checkpoint(env=env2, net=net2, agent=agent2)
+    assert np.array_equal(stats_a, stats_b)
+    for k in final_a:
+        assert np.array_equal(np.asarray(final_a[k]), np.asarray(final_b[k])), k
+    assert env.episode_stats() == env2.episode_stats()
+    for o in (agent, agent2, net, net2, env, env2):
+        o.close()
+
+
+def test_checkpoint_hook_writes_files(pkg, ctx, tmp_path):
+    env, net, agent = _ppo_objects(pkg, ctx, "CartPole", 256, 4, 3)
+    agent.fusable = False                                                # a per-step hook steps through the stages anyway
+    hook = pkg.checkpoint.CheckpointEveryNSteps(5, str(tmp_path / "run"), net=net)
+    pkg.run(agent, env, pkg.StopAfterNSteps(11), hook)
+    assert [p.split("_")[-1] for p in hook.paths] == ["5.npz", "10.npz"]
+    ck = pkg.checkpoint.load(hook.paths[1])
+    assert ck["agent/counters"].tolist()[:2] == [10 % 4, 10 // 4] and ck["env/state"].shape == (4, 256)
+    agent.close(); net.close(); env.close()
