@@ -67,6 +67,14 @@ static inline int ctx_bind(b200rl_ctx* ctx) {
     } while (0)
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+// Function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) are per DEVICE: a process that drives several devices
+// must set them once on each.  `mask` is the call site's static bit set; true the first time `device` is seen.
+static inline bool first_use_on_device(unsigned long long& mask, int device) {
+    const unsigned long long bit = 1ull << (device & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
 
 // ---- NVLink peer exchange (comm.cu): low-latency PUSH protocol --------------------------------------------------
 // Every rank owns an inbox region mapped into all ranks of the node.  A sender writes 8-byte packets {32 data bits,

@@ -389,11 +389,9 @@ __global__ void __launch_bounds__(NT, 2) rollout_tc_kernel(RollArgs g, typename 
 
 template <class Env> int launch_rollout(b200rl_ctx* ctx, const RollArgs& g, const typename Env::P& p, const EnvArrays& ea) {
     const size_t smem = sizeof(SmemRoll<Env>) + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devices = 0;   // once per device: the attribute call is not free and may serialise with running kernels
+    if (first_use_on_device(attr_devices, ctx->device))
         CUDA_TRY(cudaFuncSetAttribute(rollout_tc_kernel<Env>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     const int64_t ntiles = (g.N + TM - 1) / TM;
     int grid = 2 * ctx->sm_count;
     if ((int64_t)grid > ntiles) grid = (int)ntiles;
@@ -410,8 +408,9 @@ int nn_tc_forward(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc
                   const float* obs, int64_t N, unsigned long long* rng, void* action_out, float* logp_out, float* value_out, float* head_out,
                   float* state_copy) {
     size_t smem = sizeof(SmemFwd) + 128;
-    static bool attr_set = false;   // once per process: the attribute call is not free and may serialise with running kernels
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    static unsigned long long attr_devices = 0;   // once per device
+    if (first_use_on_device(attr_devices, ctx->device))
+        CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     forward_tc_kernel<<<grid, NT, smem, ctx->stream>>>(actor, critic, params, hp, mode, obs, N, rng, action_out, logp_out, value_out, head_out,
                                                        state_copy);
     LAUNCH_CHECK(ctx);

@@ -692,8 +692,9 @@ bool nn_tc_bwd_supported(const MlpDesc& actor, const MlpDesc& critic) {
 int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
                        const AcBatch& b, float* partial, float* loss_partial, int64_t np) {
     size_t smem = sizeof(SmemBwd) + 128;
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(ac_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    static unsigned long long attr_devices = 0;   // once per device
+    if (first_use_on_device(attr_devices, ctx->device))
+        CUDA_TRY(cudaFuncSetAttribute(ac_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ac_loss_grad_tc_kernel<<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np);
     LAUNCH_CHECK(ctx);
     return B200RL_OK;
