@@ -3,10 +3,23 @@
 driven with a stub batched env.  Expected values are the reference's own test vectors:
 RLCore/test/core/stop_conditions.jl:3-50, test/core/hooks.jl:44-152,
 test/policies/explorers/epsilon_greedy_explorer.jl:8-74."""
+import json
+import os
+
 import numpy as np
 import pytest
 
 import oracle_lib as O
+
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "control_reference_vectors.json")) as _f:
+    GOLD = json.load(_f)
+
+
+def make_stop(pkg, spec):
+    name, *args = spec
+    if name in ("StopIfAny", "StopIfAll"):
+        return getattr(pkg, name)(*[make_stop(pkg, a) for a in args])
+    return getattr(pkg, name)(*args)
 
 
 class StubVecEnv:
@@ -53,16 +66,10 @@ class StubVecEnv:
         self.log.append(("check",))
 
 
-def test_stop_after_n_steps_counts_like_the_reference(pkg):
-    s = pkg.StopAfterNSteps(10)
-    assert sum(s.check(None, None) for _ in range(20)) == 11          # stop_conditions.jl test: 11 trues in 20 calls
-
-
-def test_stop_if_any_and_all(pkg):
-    any_ = pkg.StopIfAny(pkg.StopAfterNSteps(10), pkg.StopAfterNSteps(3))
-    assert sum(any_.check(None, None) for _ in range(20)) == 18
-    all_ = pkg.StopIfAll(pkg.StopAfterNSteps(10), pkg.StopAfterNSteps(3))
-    assert sum(all_.check(None, None) for _ in range(20)) == 11
+@pytest.mark.parametrize("case", [c for c in GOLD["stop_conditions"] if "trues" in c], ids=lambda c: c["ref"])
+def test_stop_condition_counts_golden(pkg, case):
+    s = make_stop(pkg, case["condition"])
+    assert sum(s.check(None, None) for _ in range(case["calls"])) == case["trues"]
 
 
 def test_stop_after_n_episodes_batched(pkg):
@@ -181,13 +188,18 @@ def test_run_random_policy_is_fused_into_the_step(pkg):
 KW = dict(eps_init=0.9, warmup_steps=100, decay_steps=100)
 
 
-def test_epsilon_schedule_reference_vectors(pkg):
-    lin = pkg.EpsilonGreedyExplorer(0.1, kind="linear", **KW)
-    assert [lin.get_eps(s) for s in (50, 100, 150, 200)] == pytest.approx([0.9, 0.9, 0.5, 0.1], rel=1e-12)
-    ex = pkg.EpsilonGreedyExplorer(0.1, kind="exp", **KW)
-    assert ex.get_eps(50) == 0.9 and ex.get_eps(150) == pytest.approx(0.5852245277701068, rel=1e-15)
-    assert ex.get_eps(2000) == pytest.approx(0.1, abs=1e-2)
-    assert pkg.EpsilonGreedyExplorer(0.3).get_eps() == 0.3               # EpsilonGreedyExplorer(ϵ): no warm-up, no decay
+@pytest.mark.parametrize("case", GOLD["explorer_schedule"], ids=lambda c: c["ref"])
+def test_epsilon_schedule_golden(pkg, case):
+    e = GOLD["explorer"]
+    mine = pkg.EpsilonGreedyExplorer(e["eps_stable"], kind=case["kind"], eps_init=e["eps_init"], warmup_steps=e["warmup_steps"],
+                                     decay_steps=e["decay_steps"])
+    ex6 = O.explorer6(e["eps_stable"], e["eps_init"], e["warmup_steps"], e["decay_steps"], case["kind"])
+    for got in (mine.get_eps(case["step"]), O.get_eps(ex6, case["step"])):
+        if "atol" in case:
+            assert got == pytest.approx(case["expected"], abs=case["atol"])
+        else:
+            assert got == pytest.approx(case["expected"], rel=1.5e-8)        # Julia's isapprox default
+    assert pkg.EpsilonGreedyExplorer(0.3).get_eps() == 0.3                   # EpsilonGreedyExplorer(ϵ): no warm-up, no decay
 
 
 def test_epsilon_schedule_host_mirror_equals_oracle_bitwise(pkg):
@@ -198,18 +210,30 @@ def test_epsilon_schedule_host_mirror_equals_oracle_bitwise(pkg):
         assert [mine.get_eps(s) for s in steps] == [O.get_eps(ex6, s) for s in steps]
 
 
-def test_explorer_prob_reference_vectors(pkg):
-    values = [0.1, 0.5, 0.5, 0.3]
-    tie = pkg.EpsilonGreedyExplorer(0.1, kind="linear", is_break_tie=True, **KW)
-    assert tie.prob(values) == pytest.approx([0.225, 0.275, 0.275, 0.225], rel=1e-12)
-    assert tie.prob(values, 2) == pytest.approx(0.275, rel=1e-12)
-    first = pkg.EpsilonGreedyExplorer(0.1, kind="linear", is_break_tie=False, **KW)
-    assert first.prob(values) == pytest.approx([0.225, 0.32499999999999996, 0.225, 0.225], rel=1e-12)
-    assert first.prob(values, 2) == pytest.approx(0.32500000000000007, rel=1e-12)
-    for brk, e in ((True, tie), (False, first)):
-        np.testing.assert_allclose(O.egreedy_prob(O.explorer6(0.1, 0.9, 100, 100, "linear", brk), 1, values), e.prob(values), rtol=1e-15)
+@pytest.mark.parametrize("case", GOLD["explorer_prob"], ids=lambda c: c["ref"])
+def test_explorer_prob_golden(pkg, case):
+    e = GOLD["explorer"]
+    mine = pkg.EpsilonGreedyExplorer(e["eps_stable"], kind="linear", eps_init=e["eps_init"], warmup_steps=e["warmup_steps"],
+                                     decay_steps=e["decay_steps"], is_break_tie=case["is_break_tie"])
+    ex6 = O.explorer6(e["eps_stable"], e["eps_init"], e["warmup_steps"], e["decay_steps"], "linear", case["is_break_tie"])
+    full = O.egreedy_prob(ex6, 1, case["values"])
+    if "action" in case:
+        assert mine.prob(case["values"], case["action"]) == pytest.approx(case["expected"], rel=1.5e-8)
+        assert full[case["action"] - 1] == pytest.approx(case["expected"], rel=1.5e-8)
+    else:
+        assert mine.prob(case["values"]) == pytest.approx(case["expected"], rel=1.5e-8)
+        assert list(full) == pytest.approx(case["expected"], rel=1.5e-8)
+
+
+def test_greedy_explorer_golden(pkg):
     g = pkg.GreedyExplorer()
-    assert g.plan_values(values) == 2 and g.prob(values) == [0.0, 1.0, 0.0, 0.0] and g.prob(values, 2) == 1.0
+    for case in GOLD["greedy"]:
+        if "plan" in case:
+            assert g.plan_values(case["values"]) == case["plan"]
+        elif "action" in case:
+            assert g.prob(case["values"], case["action"]) == case["prob"]
+        else:
+            assert g.prob(case["values"]) == case["prob"]
 
 
 def test_oracle_egreedy_plan_visits_all_actions_and_follows_prob():
