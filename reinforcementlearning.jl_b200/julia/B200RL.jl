@@ -59,10 +59,22 @@ struct CartPoleParamsC
     polemasslength::Cdouble; forcemag::Cdouble; dt::Cdouble; thetathreshold::Cdouble; xthreshold::Cdouble
     max_steps::Int64
 end
-# built from RLEnvs' own CartPoleEnvParams{T}(; kwargs...) so the reference constructor stays the source of truth:
-#   p = ReinforcementLearningEnvironments.CartPoleEnvParams{T}(; kwargs...)
-#   CartPoleParamsC(p.gravity, p.masscart, p.masspole, p.totalmass, p.halflength, p.polemasslength,
-#                   p.forcemag, p.dt, p.thetathreshold, p.xthreshold, p.max_steps)
+struct PendulumParamsC
+    max_speed::Cdouble; max_torque::Cdouble; g::Cdouble; m::Cdouble; l::Cdouble; dt::Cdouble
+    max_steps::Int64; n_actions::Int64; continuous::Int32
+end
+struct MountainCarParamsC
+    min_pos::Cdouble; max_pos::Cdouble; max_speed::Cdouble; goal_pos::Cdouble; goal_velocity::Cdouble; power::Cdouble; gravity::Cdouble
+    max_steps::Int64
+end
+# built from RLEnvs' own params structs so the reference constructors stay the source of truth (their fields are already rounded to T;
+# Float64 embeds Float32 exactly):  B200VecEnv(ctx, :CartPole, N; params = CartPoleParamsC(RLEnvs.CartPoleEnvParams{Float32}(; max_steps = 500)), ...)
+CartPoleParamsC(p::RLEnvs.CartPoleEnvParams) = CartPoleParamsC(p.gravity, p.masscart, p.masspole, p.totalmass, p.halflength, p.polemasslength,
+                                                                p.forcemag, p.dt, p.thetathreshold, p.xthreshold, p.max_steps)
+PendulumParamsC(p::RLEnvs.PendulumEnvParams; n_actions::Integer = 3, continuous::Bool = true) =
+    PendulumParamsC(p.max_speed, p.max_torque, p.g, p.m, p.l, p.dt, p.max_steps, n_actions, continuous)
+MountainCarParamsC(p::RLEnvs.MountainCarEnvParams) =
+    MountainCarParamsC(p.min_pos, p.max_pos, p.max_speed, p.goal_pos, p.goal_velocity, p.power, p.gravity, p.max_steps)
 
 # 3 / 4: CartPoleEnv(continuous = true) / ContinuousMountainCarEnv (CartPoleEnv.jl:74-79, MountainCarEnv.jl:83), Float32 actions in -1.0..1.0
 const KINDS = Dict(:CartPole => 0, :Pendulum => 1, :MountainCar => 2, :ContinuousCartPole => 3, :ContinuousMountainCar => 4)
@@ -71,7 +83,7 @@ const NOBS = Dict(0 => 4, 1 => 3, 2 => 2, 3 => 4, 4 => 2)
 @enum Field STATE = 0 OBS = 1 REWARD = 2 TERMINAL = 3 TSTEP = 4 RNG = 5 FLAGS = 6 ACTION = 7
 
 """
-    B200VecEnv(ctx, kind, N; T = Float32, seeds, auto_reset = true, params = C_NULL)
+    B200VecEnv(ctx, kind, N; T = Float32, seeds, auto_reset = true, params = nothing)
 
 N classic-control envs stepped by one kernel launch.  Plays the role of `MultiThreadEnv`:
 `state(env)` is `(NOBS, N)`, `reward(env)` / `is_terminated(env)` are length-N vectors.
@@ -91,15 +103,18 @@ mutable struct B200VecEnv{T} <: AbstractEnv
 end
 
 function B200VecEnv(ctx::B200Context, kind::Symbol, n::Integer; T = Float32, seeds::AbstractVector{Xoshiro},
-                    auto_reset::Bool = true, params = C_NULL, continuous::Bool = (kind in (:Pendulum, :ContinuousCartPole, :ContinuousMountainCar)),
+                    auto_reset::Bool = true, params = nothing, continuous::Bool = (kind in (:Pendulum, :ContinuousCartPole, :ContinuousMountainCar)),
                     n_actions::Integer = kind === :MountainCar ? 3 : kind === :Pendulum ? 3 : 2)
     length(seeds) == n || throw(ArgumentError("need one Xoshiro per env"))
     k = KINDS[kind]
     st = raw_states(seeds)
     out = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve st params check(ccall((:b200rl_env_create, LIB), Cint,
+    # `params`: `nothing` (the reference constructors' defaults) or one of the *ParamsC structs above (an isbits struct, passed by reference)
+    pref = params === nothing ? nothing : Ref(params)
+    pptr = pref === nothing ? C_NULL : Base.unsafe_convert(Ptr{Cvoid}, pref)
+    GC.@preserve st pref check(ccall((:b200rl_env_create, LIB), Cint,
         (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{UInt64}, Ref{Ptr{Cvoid}}),
-        ctx.h, k, T === Float64 ? 1 : 0, n, params === C_NULL ? C_NULL : pointer_from_objref(params), st, out))
+        ctx.h, k, T === Float64 ? 1 : 0, n, pptr, st, out))
     env = B200VecEnv{T}(ctx, out[], k, n, auto_reset, continuous, n_actions, zeros(T, NOBS[k], n), zeros(T, n), zeros(UInt8, n))
     finalizer(e -> (e.h == C_NULL || ccall((:b200rl_env_destroy, LIB), Cint, (Ptr{Cvoid},), e.h); e.h = C_NULL), env)
 end
@@ -193,6 +208,12 @@ function RLCore.check!(s::StopAfterNEpisodes{Nothing}, agent, env::B200VecEnv)
     s.cur += count(RLBase.is_terminated(env))
     s.cur >= s.episode
 end
+function RLCore.check!(s::StopAfterNEpisodes, agent, env::B200VecEnv)     # is_show_progress = true (the default)
+    n = count(RLBase.is_terminated(env))
+    s.cur += n
+    n > 0 && RLCore.ProgressMeter.update!(s.progress, min(s.cur, s.episode))
+    s.cur >= s.episode
+end
 # the historical MultiThreadEnv `_run` (no episode stages), run.jl:36-78 specialised on the env type
 function RLCore._run(policy::AbstractPolicy, env::B200VecEnv, stop_condition::AbstractStopCondition, hook::AbstractHook,
                      reset_condition::AbstractResetCondition)
@@ -209,6 +230,7 @@ function RLCore._run(policy::AbstractPolicy, env::B200VecEnv, stop_condition::Ab
             collect!(policy, n)
             RLBase.optimise!(policy, PostActStage())
             stop_condition.cur += n
+            stop_condition.progress === nothing || RLCore.ProgressMeter.update!(stop_condition.progress, min(stop_condition.cur, stop_condition.step))
             stop_condition.cur > stop_condition.step && break
         end
         push!(policy, PostExperimentStage(), env)
