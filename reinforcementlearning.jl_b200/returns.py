@@ -50,6 +50,8 @@ def generalized_advantage_estimation(ctx, rewards, values, gamma, lam, dims=None
     if vf.shape != want:
         raise ValueError(f"values must have shape {want}, got {vf.shape}")
     out = np.empty(rf.shape, dtype=dt, order="F")
+    if rf.size == 0:   # an empty series: the reference's loop body never runs (basic.jl:408-417); nothing to launch
+        return out.reshape(r.shape) if r.ndim == 1 else out
     if dt is np.float64:
         L.check(ctx.lib.b200rl_gae_f64(ctx.h, L.ptr(out), L.ptr(rf), L.ptr(vf), L.ptr(tf), C.c_double(gamma), C.c_double(lam), R, Cc, d, 0))
     else:
@@ -70,6 +72,12 @@ def _discount(ctx, rewards, gamma, dims, terminal, init, reduced):
         i2 = np.ascontiguousarray(init, dtype=dt)
         if i2.shape != (n_series,):
             raise ValueError("init must have one entry per series")
+    if rf.size == 0:   # empty input -> empty output of the promoted eltype (the reference's loops never run)
+        if reduced:        # gain = init (zero when absent): basic.jl:253-263
+            if r.ndim == 1:
+                return dt(0) if init is None else dt(init)
+            return np.zeros(n_series, dtype=dt) if i2 is None else i2.copy()
+        return np.empty(r.shape, dtype=dt, order="F")
     ct = C.c_double if dt is np.float64 else C.c_float
     sfx = "f64" if dt is np.float64 else "f32"
     if reduced:

@@ -282,3 +282,23 @@ def test_insert_sample_ratio_controller(pkg):
         sampled.append(k)
     assert sampled[:3] == [0, 0, 0] and sum(sampled) == c.n_sampled
     assert c.n_sampled == int((c.n_inserted - c.threshold) * c.ratio) + 1   # one batch per two insertions after the threshold
+
+
+def test_returns_on_empty_inputs_follow_the_reference_shape_rules(pkg):
+    """basic.jl:227-235, 253-263, 408-417: with no time steps the loops never run — empty outputs of the promoted eltype, the reduced
+    form returns `init` (zero when absent).  No device call is made (ctx is None here)."""
+    g32 = np.float32(0.5)
+    out = pkg.discount_rewards(None, np.zeros(0, np.float32), g32)
+    assert out.shape == (0,) and out.dtype == np.float32
+    assert pkg.discount_rewards(None, np.zeros(0, np.int64), 0.5).dtype == np.float64          # promote_type(Int, Float64)
+    assert pkg.discount_rewards(None, np.zeros((3, 0), np.float32), g32, dims=2).shape == (3, 0)
+    assert pkg.discount_rewards_reduced(None, np.zeros(0, np.float32), g32) == 0.0
+    assert pkg.discount_rewards_reduced(None, np.zeros(0, np.float32), g32, init=4.0) == 4.0
+    red = pkg.discount_rewards_reduced(None, np.zeros((3, 0), np.float32), g32, dims=2, init=np.array([-2.0, 0.0, 2.0], np.float32))
+    assert red.tolist() == [-2.0, 0.0, 2.0]
+    adv = pkg.generalized_advantage_estimation(None, np.zeros(0, np.float32), np.zeros(1, np.float32), g32, np.float32(0.3))
+    assert adv.shape == (0,) and adv.dtype == np.float32
+    with pytest.raises(TypeError):
+        pkg.generalized_advantage_estimation(None, np.zeros(0, np.float32), np.zeros(1, np.float32), g32, 0.3)   # gamma / lambda types differ
+    with pytest.raises(TypeError):
+        pkg.discount_rewards(None, np.zeros((2, 2), np.float32), g32)                                            # 2-d rewards need dims
