@@ -1,7 +1,7 @@
 """Per-phase cycle breakdown of the tensor-core K7 kernel (ac_loss_grad_tc_kernel) as seen by CTA 0 / thread 0.
 
 Build step (here, no GPU):   python profiles/k7_phase_timing.py --build
-Run step (on the GPU box):   python profiles/k7_phase_timing.py
+Run step (on the GPU box):   python profiles/k7_phase_timing.py [tid ...]      (default: the three MMA issuers + one plain warp)
 The debug library is the normal one with nn_tc.cu recompiled with -DB200RL_K7_TIMING (clock64 marks); it is
 not the product library and is never loaded by the package unless this script swaps it in."""
 import ctypes as C
@@ -46,16 +46,23 @@ def run():
     b.run(agent, env, b.StopAfterNSteps(64), b.DeviceEpisodeStats())     # two full PPO iterations (warm-up)
     out = (C.c_ulonglong * 24)()
     lib.b200rl_debug_k7_phases.argtypes = [C.c_void_p, C.c_int]
-    lib.b200rl_debug_k7_phases(out, 1)
-    b.run(agent, env, b.StopAfterNSteps(32), b.DeviceEpisodeStats())     # 16 minibatch launches
-    lib.b200rl_debug_k7_phases(out, 0)
-    v = list(out)
-    tiles = max(1, v[15])
-    tot = sum(v[:15])
-    print(f"tiles seen by CTA 0: {tiles}; cycles per tile: {tot / tiles:.0f}")
+    # thread 0 issues GEMM2, 160 GEMM1, 320 GEMM3 (nn_tc.cu kIssueG*); 32 * 7 = lane 0 of a warp that issues nothing
+    watch = [int(a) for a in sys.argv[1:] if a.isdigit()] or [0, 160, 320, 224]
+    cols = {}
+    for w in watch:
+        assert lib.b200rl_debug_k7_watch(w) == 0
+        lib.b200rl_debug_k7_phases(out, 1)
+        b.run(agent, env, b.StopAfterNSteps(32), b.DeviceEpisodeStats())     # 16 minibatch launches
+        lib.b200rl_debug_k7_phases(out, 0)
+        v = list(out)
+        tiles = max(1, v[15])
+        cols[w] = ([x / tiles for x in v], sum(v[:15]) / tiles, tiles)
+    print("cycles per 128-sample tile as seen by thread <tid> of CTA 0 (" + ", ".join(f"{w}: {cols[w][2]} tiles" for w in watch) + ")")
+    print(f"  {'phase':48s}" + "".join(f"{'tid ' + str(w):>10s}" for w in watch))
     for k in list(range(15)) + [16, 17]:
-        print(f"  {NAMES[k]:48s} {v[k] / tiles:8.0f} cyc/tile  {100.0 * v[k] / tot:5.1f}%")
-    print("  (P0 row = loads issued after perm_index; P0a/P0b are its first two parts)")
+        print(f"  {NAMES[k]:48s}" + "".join(f"{cols[w][0][k]:10.0f}" for w in watch))
+    print(f"  {'sum of the 15 phases':48s}" + "".join(f"{cols[w][1]:10.0f}" for w in watch))
+    print("  (P0 row = loads issued after perm_index; P0a / P0b are its first two parts and are not in the sum)")
 
 
 if __name__ == "__main__":

@@ -223,9 +223,10 @@ __device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, c
     return r;
 }
 
-#ifdef B200RL_K7_TIMING   // debug build only (profiles/k7_phase_timing.py): per-phase cycle sums seen by CTA 0 / thread 0
+#ifdef B200RL_K7_TIMING   // debug build only (profiles/k7_phase_timing.py): per-phase cycle sums seen by CTA 0 / one watched thread
 __device__ unsigned long long g_k7_phase[24];
-#define K7_T(i) do { if (tid == 0 && blockIdx.x == 0) { long long now_ = clock64(); g_k7_phase[i] += (unsigned long long)(now_ - tprev_); tprev_ = now_; } } while (0)
+__device__ int g_k7_watch = 0;   // thread of CTA 0 whose timeline is recorded (0 = GEMM2 issuer, 160 = GEMM1 issuer, 320 = GEMM3 issuer)
+#define K7_T(i) do { if (tid == g_k7_watch && blockIdx.x == 0) { long long now_ = clock64(); g_k7_phase[i] += (unsigned long long)(now_ - tprev_); tprev_ = now_; } } while (0)
 #else
 #define K7_T(i) do { } while (0)
 #endif
@@ -295,7 +296,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     // so nobody has more than one dependent load chain.  Issued one tile ahead: the L2 / HBM latency hides behind the
     // previous tile.  No arithmetic on the loaded values here (that would stall on them).
 #ifdef B200RL_K7_TIMING
-    long long tprev_ = 0;
+    long long tprev_ = clock64();
 #endif
     float pf[kInMax];
     bool have_pf = false;
@@ -574,7 +575,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         }
         K7_T(14);
 #ifdef B200RL_K7_TIMING
-        if (tid == 0 && blockIdx.x == 0) g_k7_phase[15] += 1;
+        if (tid == g_k7_watch && blockIdx.x == 0) g_k7_phase[15] += 1;
 #endif
         umma::fence_before_sync();
         if (has_next) {
@@ -701,6 +702,10 @@ int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const Ml
 }
 
 #ifdef B200RL_K7_TIMING
+extern "C" int b200rl_debug_k7_watch(int tid) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyToSymbol(g_k7_watch, &tid, sizeof tid) == cudaSuccess ? 0 : -1;
+}
 extern "C" int b200rl_debug_k7_phases(unsigned long long* out16, int reset) {
     cudaDeviceSynchronize();
     if (cudaMemcpyFromSymbol(out16, g_k7_phase, sizeof(unsigned long long) * 24) != cudaSuccess) return -1;
