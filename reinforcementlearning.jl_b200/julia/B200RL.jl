@@ -18,11 +18,10 @@
 module B200RL
 
 using Random
-using IntervalSets: (..)                      # RLEnvs' own dependency (its continuous action spaces are `-1.0 .. 1.0`)
 import ReinforcementLearningBase as RLBase
 import ReinforcementLearningCore as RLCore
 import ReinforcementLearningEnvironments as RLEnvs
-using ReinforcementLearningBase: AbstractEnv, AbstractPolicy, Observation, DefaultPlayer
+using ReinforcementLearningBase: AbstractEnv, AbstractPolicy, Observation, DefaultPlayer, (..), ×   # `..` / `×`: DomainSets, re-exported by RLBase (space.jl:6)
 using ReinforcementLearningCore: AbstractStage, PreExperimentStage, PostExperimentStage, PreActStage, PostActStage,
     AbstractStopCondition, AbstractHook, AbstractResetCondition, ResetIfEnvTerminated, StopAfterNEpisodes, StopAfterNSteps,
     EpsilonGreedyExplorer, GreedyExplorer, AbstractExplorer
@@ -159,6 +158,17 @@ RLBase.is_terminated(env::B200VecEnv) = (fetch!(env, TERMINAL, env.terminals); e
 # CartPoleEnv.jl:95-96, PendulumEnv.jl:73-74, MountainCarEnv.jl:85-86 (one sub-env's space; every sub-env has the same)
 RLBase.action_space(env::B200VecEnv) =
     !env.continuous ? Base.OneTo(env.n_actions) : env.kind == 1 ? (-2.0 .. 2.0) : (-1.0 .. 1.0)
+# CartPoleEnv.jl:88-93, PendulumEnv.jl:75-79, MountainCarEnv.jl:87-90 with the default parameters (one sub-env's space)
+function RLBase.state_space(env::B200VecEnv{T}) where {T}
+    if env.kind == 0 || env.kind == 3
+        xt, tt = T(2.4), T(12 * π / 180)
+        ((-2 * xt) .. (2 * xt)) × (typemin(T) .. typemax(T)) × ((-2 * tt) .. (2 * tt)) × (typemin(T) .. typemax(T))
+    elseif env.kind == 1
+        (-1.0 .. 1.0) × (-1.0 .. 1.0) × (-T(8) .. T(8))
+    else
+        (T(-1.2) .. T(0.6)) × (-T(0.07) .. T(0.07))
+    end
+end
 Base.length(env::B200VecEnv) = env.n
 function Random.seed!(env::B200VecEnv, seeds::AbstractVector{Xoshiro})
     st = raw_states(seeds)
