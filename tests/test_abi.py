@@ -57,3 +57,23 @@ def test_no_device_fails_loudly(pkg):
     with pytest.raises(pkg.B200RLError) as ei:
         pkg.Context(0)
     assert "no CPU fallback" in str(ei.value)
+
+
+def test_pure_c_client_builds_links_and_fails_loudly_without_a_gpu(pkg, tmp_path):
+    """examples/ppo_cartpole.c is what any FFI does: C99, include/b200rl.h only.  It must compile and link against the
+    in-tree library; without a device the first call reports the error through the ABI's convention (no fallback)."""
+    import subprocess
+    exe = str(tmp_path / "ppo_cartpole")
+    libdir = os.path.dirname(pkg._lib.SO_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "ppo_cartpole.c"), "-L", libdir, "-lb200rl", "-Wl,-rpath," + libdir, "-lm", "-o", exe])
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    r = subprocess.run([exe, "256", "1"], capture_output=True, text=True, timeout=120)
+    if has_gpu:
+        assert r.returncode == 0 and "env-steps/s" in r.stdout, r.stderr
+    else:
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
