@@ -251,7 +251,7 @@ static void ac_loss_grad(const ActorCritic& ac, const Hyper& hp, const float* p,
             float logp_a;
             if (ALGO == 0 || ALGO == 3) {
                 int na = ac.actor.hd[0];
-                float lp[8], pr[8];
+                float lp[8] = {0.f}, pr[8] = {0.f};
                 logsoftmax(z, na, lp);
                 float H = 0;
                 for (int i = 0; i < na; ++i) { pr[i] = std::exp(lp[i]); H -= pr[i] * lp[i]; }
