@@ -137,3 +137,43 @@ def test_env_reset_and_random_policy_bitwise(hd, hkind, okind, dtype, n_act, bou
     assert np.array_equal(a, last)
     assert np.array_equal(ref.get(O.F_STATE).view(np.uint8), state.view(np.uint8))
     assert np.array_equal(ref.get(O.F_RNG), rng) and np.array_equal(ref.get(O.F_T), t)
+
+
+def _f32(v):
+    return float(np.float32(v))
+
+
+CUSTOM = [
+    # CartPoleEnvParams{Float32}(; gravity = 9.0, masscart = 1.3, masspole = 0.2, halflength = 0.4, forcemag = 7.5, max_steps = 50, dt = 0.03,
+    #                            thetathreshold = 9.0, xthreshold = 1.5): derived fields in Float64, then -> T (CartPoleEnv.jl:22-46)
+    pytest.param(0, O.KIND_CARTPOLE, "f32", 2,
+                 [_f32(9.0), _f32(1.3), _f32(0.2), _f32(1.3 + 0.2), _f32(0.4), _f32(0.2 * 0.4), _f32(7.5), _f32(0.03), _f32(9.0 * np.pi / 180), _f32(1.5), 50],
+                 id="CartPole-f32-custom"),
+    pytest.param(5, O.KIND_CARTPOLE, "f64", 2, [9.0, 1.3, 0.2, 1.3 + 0.2, 0.4, 0.2 * 0.4, 7.5, 0.03, 9.0 * np.pi / 180, 1.5, 50], id="CartPole-f64-custom"),
+    # PendulumEnv(; T = Float32, max_speed = 6, max_torque = 1.5, g = 9.81, m = 0.8, l = 1.2, dt = 0.02, max_steps = 77, continuous = false, n_actions = 5)
+    pytest.param(6, O.KIND_PENDULUM, "f32", 5, [6.0, 1.5, _f32(9.81), _f32(0.8), _f32(1.2), _f32(0.02), 77, 5, 0], id="Pendulum-discrete5-custom"),
+    # MountainCarEnv(; T = Float32, max_speed = 0.05, goal_pos = 0.3, power = 0.002, gravity = 0.003, max_steps = 120)
+    pytest.param(2, O.KIND_MOUNTAINCAR, "f32", 3, [_f32(-1.2), _f32(0.6), _f32(0.05), _f32(0.3), 0.0, _f32(0.002), _f32(0.003), 120], id="MountainCar-custom"),
+]
+
+
+@pytest.mark.parametrize("hkind,okind,dtype,n_act,params", CUSTOM)
+def test_env_with_non_default_parameters_bitwise(hd, hkind, okind, dtype, n_act, params):
+    """a1: every field of the params structs reaches the arithmetic (nothing is a baked-in default)."""
+    n, steps = 600, 160
+    seeds = O.splitmix_states_fast(n, 500 + hkind)
+    q = np.array(params, np.float64)
+    ref = O.OracleVecEnv(okind, n, seeds, dtype=dtype, params=q)
+    ref.reset(force=True)
+    T = np.float64 if dtype == "f64" else np.float32
+    state = np.ascontiguousarray(ref.get(O.F_STATE)); rng = ref.get(O.F_RNG).copy(); t = ref.get(O.F_T).copy()
+    A = np.asfortranarray(np.random.default_rng(9).integers(1, n_act + 1, (n, steps)).astype(np.int32))
+    rew = np.zeros((n, steps), T, order="F"); term = np.zeros((n, steps), np.uint8, order="F")
+    assert hd.hd_env_run(hkind, O._p(q), n, steps, O._p(rng), O._p(A), 0, O._p(state), O._p(rew), O._p(term), O._p(t), None, 0) == 0
+    for k in range(steps):
+        assert ref.step(A[:, k], auto_reset=True) == 0
+        assert np.array_equal(ref.get(O.F_REWARD).view(np.uint8), np.ascontiguousarray(rew[:, k]).view(np.uint8)), k
+        assert np.array_equal(ref.get(O.F_TERMINAL) & 1, term[:, k]), k
+    assert term.sum() >= n
+    assert np.array_equal(ref.get(O.F_STATE).view(np.uint8), state.view(np.uint8))
+    assert np.array_equal(ref.get(O.F_RNG), rng) and np.array_equal(ref.get(O.F_T), t)
