@@ -3,8 +3,12 @@
 // CPU restatement of the Julia stdlib `Random` pieces the reference's envs/policies
 // consume (Julia 1.10: stdlib/Random/src/Xoshiro.jl, XoshiroSimd.jl, generation.jl).
 // `Random` is NOT under /root/reference (Julia stdlib, version pinned only by
-// .devcontainer/Dockerfile:1 `julia:1.10`) -> PARITY UNPINNED; restated from the
-// published xoshiro256++ algorithm and the Julia 1.10 samplers:
+// .devcontainer/Dockerfile:1 `julia:1.10`); restated from the published xoshiro256++ algorithm and the Julia 1.10
+// samplers.  PINNED by the known answers Julia's own manual prints (stdlib Random docstrings; tests/test_oracle_julia_rng.py):
+//   Xoshiro(1234); rand(rng, 2) == [0.32597672886359486, 0.5490511363155669]     (generator core, integer seeding, Float64 sampler)
+//   shuffle(Xoshiro(123), Vector(1:10)) == [5,4,2,3,6,10,8,1,9,7]; randperm(Xoshiro(123), 4) == [1,4,2,3];
+//   randcycle(Xoshiro(123), 6) == [5,4,2,6,3,1]                                   (UInt52Raw = u64 >>> 12, masked rejection)
+// Still unpinned: the Float32 samplers, the array path below 64 bytes, rand(rng, Base.OneTo(n)) (Lemire), randn.
 //   rand(UInt64)          xoshiro256++ next()
 //   rand(Float64)         Float64(u >>> 11) * 2^-53
 //   rand(Float32)         Float32((u >>> 32) >>> 8) * 2^-24      (top 24 bits)
@@ -70,8 +74,41 @@ static inline int64_t rand_oneto(Xoshiro& g, uint64_t n) {
     return (int64_t)(uint64_t)(m >> 64) + 1;
 }
 
-// Test-harness seeding (NOT Julia's Xoshiro(seed), which is SHA-based and version
-// dependent): four successive splitmix64 outputs.  The C ABI takes raw 4xUInt64 states.
+// rand(rng, UInt52Raw()) for Xoshiro = rand(rng, UInt64) >>> 12, and the masked rejection sampler ltm52(n, mask) =
+// LessThan(n - 1, Masked(mask, UInt52Raw(Int))) that shuffle! / randperm! / randcycle! draw from (stdlib Random, misc.jl).
+static inline uint64_t rand_ltm52(Xoshiro& g, uint64_t n, uint64_t mask) {
+    for (;;) {
+        uint64_t x = (next_u64(g) >> 12) & mask;
+        if (x <= n - 1) return x;
+    }
+}
+// shuffle!(rng, a) (stdlib Random misc.jl): for i = 2:n  j = 1 + rand(rng, ltm52(i, mask)); swap a[i], a[j]; mask grows with i.
+// This is the `shuffle!(rng, 1:N*T)` of the PPO update — pinned by Julia's documented
+// shuffle(Xoshiro(123), Vector(1:10)) == [5, 4, 2, 3, 6, 10, 8, 1, 9, 7] (tests/test_oracle_julia_rng.py).
+template <class T> static inline void shuffle(Xoshiro& g, T* a, int64_t n) {
+    uint64_t mask = 3;
+    for (int64_t i = 2; i <= n; ++i) {
+        int64_t j = 1 + (int64_t)rand_ltm52(g, (uint64_t)i, mask);
+        T tmp = a[i - 1]; a[i - 1] = a[j - 1]; a[j - 1] = tmp;
+        if ((uint64_t)i == 1 + mask) mask = 2 * mask + 1;
+    }
+}
+// randperm!(rng, a)
+static inline void randperm(Xoshiro& g, int64_t* a, int64_t n) {
+    if (n == 0) return;
+    a[0] = 1;
+    uint64_t mask = 3;
+    for (int64_t i = 2; i <= n; ++i) {
+        int64_t j = 1 + (int64_t)rand_ltm52(g, (uint64_t)i, mask);
+        if (i != j) a[i - 1] = a[j - 1];
+        a[j - 1] = i;
+        if ((uint64_t)i == 1 + mask) mask = 2 * mask + 1;
+    }
+}
+
+// Test-harness seeding: four successive splitmix64 outputs.  (Julia's own Xoshiro(seed::Integer) for 1.7 <= version <= 1.10 is
+// the SHA-256 digest of the seed's UInt32 words read as four little-endian UInt64 — restated with hashlib in
+// tests/oracle_lib.julia_xoshiro and pinned by Julia's documented Xoshiro(1234) vector.)  The C ABI takes raw 4xUInt64 states.
 static inline uint64_t splitmix64(uint64_t& x) {
     uint64_t z = (x += 0x9E3779B97F4A7C15ull);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;

@@ -52,6 +52,28 @@ int64_t orc_rng_oneto(uint64_t* s, uint64_t n) {
     s[0] = g.s0; s[1] = g.s1; s[2] = g.s2; s[3] = g.s3;
     return r;
 }
+// shuffle!(rng, a) / randperm(rng, n) of Julia's stdlib on a raw Xoshiro state (advanced in place)
+void orc_jl_shuffle_i64(uint64_t* s, int64_t* a, int64_t n) {
+    jl::Xoshiro g{s[0], s[1], s[2], s[3]};
+    jl::shuffle(g, a, n);
+    s[0] = g.s0; s[1] = g.s1; s[2] = g.s2; s[3] = g.s3;
+}
+void orc_jl_shuffle_i32(uint64_t* s, int32_t* a, int64_t n) {
+    jl::Xoshiro g{s[0], s[1], s[2], s[3]};
+    jl::shuffle(g, a, n);
+    s[0] = g.s0; s[1] = g.s1; s[2] = g.s2; s[3] = g.s3;
+}
+void orc_jl_randperm(uint64_t* s, int64_t* a, int64_t n) {
+    jl::Xoshiro g{s[0], s[1], s[2], s[3]};
+    jl::randperm(g, a, n);
+    s[0] = g.s0; s[1] = g.s1; s[2] = g.s2; s[3] = g.s3;
+}
+uint64_t orc_jl_ltm52(uint64_t* s, uint64_t n, uint64_t mask) {
+    jl::Xoshiro g{s[0], s[1], s[2], s[3]};
+    uint64_t r = jl::rand_ltm52(g, n, mask);
+    s[0] = g.s0; s[1] = g.s1; s[2] = g.s2; s[3] = g.s3;
+    return r;
+}
 void orc_seed_splitmix(uint64_t seed, uint64_t* out) {
     jl::Xoshiro g = jl::seed_splitmix(seed);
     out[0] = g.s0; out[1] = g.s1; out[2] = g.s2; out[3] = g.s3;

@@ -30,6 +30,27 @@ def splitmix_states(seed, lo, hi):
     return out
 
 
+def julia_xoshiro_states(seeds):
+    """Raw states of Julia's `Xoshiro(seed)` for an iterable of non-negative integer seeds (Julia 1.7–1.10: the SHA-256 digest of the
+    seed's little-endian UInt32 words read as four little-endian UInt64; stdlib Random `seed!`).  Lets the Python mirror start the very
+    streams the Julia glue passes for `[Xoshiro(s) for s in seeds]`.  Returns (len(seeds), 4) uint64.  Pure host-side seeding — the
+    known answers Julia's manual prints for `Xoshiro(1234)` pin it (tests/test_oracle_julia_rng.py, tests/test_host_logic.py)."""
+    import hashlib
+    out = []
+    for seed in seeds:
+        seed = int(seed)
+        if seed < 0:
+            raise ValueError("Xoshiro(seed) needs a non-negative integer")
+        words = bytearray()
+        while True:
+            words += (seed & 0xFFFFFFFF).to_bytes(4, "little")
+            seed >>= 32
+            if seed == 0:
+                break
+        out.append(np.frombuffer(hashlib.sha256(bytes(words)).digest(), dtype="<u8"))
+    return np.array(out, dtype=np.uint64).reshape(len(out), 4)
+
+
 def glorot_actor_critic(seed, n_in, hidden, n_out):
     """Flux `glorot_uniform` Dense init (U(+-sqrt(6/(in+out))), zero bias) in Flux.destructure order
     for ActorCritic(actor n_in-H-H-n_out, critic n_in-H-H-1); identical on every rank."""

@@ -36,6 +36,8 @@ def lib():
         "orc_cos64": (f64, [f64]), "orc_mod64": (f64, [f64, f64]),
         "orc_rng_next": (u64, [vp]), "orc_rng_oneto": (i64, [vp, u64]),
         "orc_seed_splitmix": (None, [u64, vp]),
+        "orc_jl_shuffle_i64": (None, [vp, vp, i64]), "orc_jl_shuffle_i32": (None, [vp, vp, i64]), "orc_jl_randperm": (None, [vp, vp, i64]),
+        "orc_jl_ltm52": (u64, [vp, u64, u64]),
         "orc_cartpole_default_params": (None, [i32, vp]),
         "orc_vecenv_create": (vp, [i32, i32, i64, vp, vp]), "orc_vecenv_destroy": (None, [vp]),
         "orc_vecenv_set_max_timeout": (None, [vp, i64]),
@@ -78,6 +80,39 @@ def lib():
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def julia_xoshiro(seed):
+    """Raw state of Julia's `Xoshiro(seed::Integer)` for 1.7 <= Julia <= 1.10 (stdlib Random, Xoshiro.jl `seed!`): the SHA-256
+    digest of the seed's UInt32 words (little endian, `make_seed`) read as four little-endian UInt64.  Pinned by the vectors Julia's
+    manual prints (tests/test_oracle_julia_rng.py).  Julia 1.11 changed the seeding; the C ABI therefore takes raw states."""
+    import hashlib
+    seed = int(seed)
+    if seed < 0:
+        raise ValueError("seed must be non-negative")
+    words = []
+    while True:
+        words.append(seed & 0xFFFFFFFF)
+        seed >>= 32
+        if seed == 0:
+            break
+    digest = hashlib.sha256(b"".join(w.to_bytes(4, "little") for w in words)).digest()
+    return np.frombuffer(digest, dtype="<u8").astype(np.uint64)
+
+
+def jl_shuffle(state, a):
+    """shuffle!(rng, a) on a raw Xoshiro state (advanced in place); a: int32 or int64 array, shuffled in place."""
+    a = np.ascontiguousarray(a)
+    fn = lib().orc_jl_shuffle_i32 if a.dtype == np.int32 else lib().orc_jl_shuffle_i64
+    assert a.dtype in (np.int32, np.int64)
+    fn(_p(state), _p(a), a.size)
+    return a
+
+
+def jl_randperm(state, n):
+    a = np.zeros(n, np.int64)
+    lib().orc_jl_randperm(_p(state), _p(a), n)
+    return a
 
 
 def splitmix_states(n, seed=0x9E3779B97F4A7C15):

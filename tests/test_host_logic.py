@@ -302,3 +302,15 @@ def test_returns_on_empty_inputs_follow_the_reference_shape_rules(pkg):
         pkg.generalized_advantage_estimation(None, np.zeros(0, np.float32), np.zeros(1, np.float32), g32, 0.3)   # gamma / lambda types differ
     with pytest.raises(TypeError):
         pkg.discount_rewards(None, np.zeros((2, 2), np.float32), g32)                                            # 2-d rewards need dims
+
+
+def test_julia_integer_seeding_helper(pkg):
+    """sharding.julia_xoshiro_states == the oracle's restatement; first Float64 of Xoshiro(1234) is the value Julia's manual prints."""
+    st = pkg.sharding.julia_xoshiro_states([1234, 123, 3, 2 ** 40 + 5])
+    assert st.shape == (4, 4) and st.dtype == np.uint64
+    for row, seed in zip(st, (1234, 123, 3, 2 ** 40 + 5)):
+        assert np.array_equal(row, O.julia_xoshiro(seed))
+    s = st[0].copy()
+    assert (int(O.lib().orc_rng_next(O._p(s))) >> 11) * 2.0 ** -53 == 0.32597672886359486
+    with pytest.raises(ValueError):
+        pkg.sharding.julia_xoshiro_states([-1])
