@@ -18,6 +18,8 @@
 module B200RL
 
 using Random
+using TimerOutputs: @timeit_debug             # the reference's debug tracing (RLCore/src/core/run.jl:46-72); enable with
+                                              # TimerOutputs.enable_debug_timings(B200RL); labels land in RLCore.timer
 import ReinforcementLearningBase as RLBase
 import ReinforcementLearningCore as RLCore
 import ReinforcementLearningEnvironments as RLEnvs
@@ -248,16 +250,17 @@ function RLCore._run(policy::AbstractPolicy, env::B200VecEnv, stop_condition::Ab
         check(ccall((:b200rl_env_check, LIB), Cint, (Ptr{Cvoid},), env.h))
         return hook
     end
+    timer = RLCore.timer                                       # same labels as run.jl:46-72
     while true
-        env.auto_reset || RLBase.reset!(env; is_force = false)
-        push!(policy, PreActStage(), env)
-        RLBase.optimise!(policy, PreActStage())
-        push!(hook, PreActStage(), policy, env)
-        action = RLBase.plan!(policy, env)
-        RLBase.act!(env, action)
-        push!(policy, PostActStage(), env, action)
-        RLBase.optimise!(policy, PostActStage())
-        push!(hook, PostActStage(), policy, env)
+        env.auto_reset || @timeit_debug timer "reset!"          RLBase.reset!(env; is_force = false)
+        @timeit_debug timer "push!(policy) PreActStage"         push!(policy, PreActStage(), env)
+        @timeit_debug timer "optimise! PreActStage"             RLBase.optimise!(policy, PreActStage())
+        @timeit_debug timer "push!(hook) PreActStage"           push!(hook, PreActStage(), policy, env)
+        action = @timeit_debug timer "plan!"                    RLBase.plan!(policy, env)
+        @timeit_debug timer "act!"                              RLBase.act!(env, action)
+        @timeit_debug timer "push!(policy) PostActStage"        push!(policy, PostActStage(), env, action)
+        @timeit_debug timer "optimise! PostActStage"            RLBase.optimise!(policy, PostActStage())
+        @timeit_debug timer "push!(hook) PostActStage"          push!(hook, PostActStage(), policy, env)
         RLCore.check!(stop_condition, policy, env) && break
     end
     push!(policy, PostExperimentStage(), env)
