@@ -11,7 +11,7 @@ from .envs import B200VecEnv, cartpole_params, mountaincar_params, pendulum_para
 from .explorers import EpsilonGreedyExplorer, GreedyExplorer
 from .learners import (ACT_RELU, ACT_TANH, KIND_CATEGORICAL, KIND_GAUSSIAN, KIND_Q, Agent, DQNLearner, InsertSampleRatioController, Network,
                        OnPolicyAgent, QBasedPolicy, Trajectory, dqn_config, onpolicy_config)
-from . import checkpoint, explorers, learners, sharding
+from . import checkpoint, core, explorers, learners, sharding
 from .returns import discount_rewards, discount_rewards_reduced, generalized_advantage_estimation
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -10,6 +10,39 @@ import time
 
 import numpy as np
 
+# ---- debug tracing (TimerOutputs in the reference: `const timer`, ReinforcementLearningCore.jl:17-18; every call of `_run` sits in
+#      `@timeit_debug timer "<label>"`, run.jl:46-72; off until `TimerOutputs.enable_debug_timings(RLCore)`, docs/src/tips.md:21-23)
+class TimerOutput(dict):
+    """label -> [number of calls, total seconds]"""
+
+    def __str__(self):
+        rows = sorted(self.items(), key=lambda kv: -kv[1][1])
+        return "\n".join(f"{label:36s} {n:8d} calls {1e3 * sec:10.3f} ms" for label, (n, sec) in rows)
+
+
+timer = TimerOutput()
+_debug_timings = False
+
+
+def enable_debug_timings(on=True):
+    """TimerOutputs.enable_debug_timings / disable_debug_timings for run().  Wall-clock around each stage call; kernel time
+    proper is measured on the device (Context.timer_start / timer_stop_ms, ncu)."""
+    global _debug_timings
+    _debug_timings = bool(on)
+
+
+def _timed(label, fn, *args, **kw):
+    if not _debug_timings:
+        return fn(*args, **kw)
+    t0 = time.perf_counter()
+    try:
+        return fn(*args, **kw)
+    finally:
+        rec = timer.setdefault(label, [0, 0.0])
+        rec[0] += 1
+        rec[1] += time.perf_counter() - t0
+
+
 # stages (stages.jl:13-28)
 PreExperimentStage, PostExperimentStage = "PreExperimentStage", "PostExperimentStage"
 PreEpisodeStage, PostEpisodeStage = "PreEpisodeStage", "PostEpisodeStage"
@@ -278,13 +311,7 @@ def run(policy, env, stop_condition=None, hook=None):
                 policy._t = 0
                 policy.update(want_stats=policy.fetch_stats)
             is_stop = stop_condition.advance(n)
-    while not is_stop:
-        if not env.auto_reset:
-            env.reset_(is_force=False)  # soft reset of finished sub-envs
-        policy.push(PreActStage, env)
-        policy.optimise(PreActStage)
-        hook.push(PreActStage, policy, env)
-        action = policy.plan(env)
+    def act(action):
         if isinstance(action, FusedAction):
             if action.kind == "random":
                 env.act_random_()
@@ -292,9 +319,18 @@ def run(policy, env, stop_condition=None, hook=None):
                 policy.act_fused(env)
         else:
             env.act_(action)
-        policy.push(PostActStage, env, action)
-        policy.optimise(PostActStage)
-        hook.push(PostActStage, policy, env)
+
+    while not is_stop:   # labels as in run.jl:46-72
+        if not env.auto_reset:
+            _timed("reset!", env.reset_, is_force=False)  # soft reset of finished sub-envs
+        _timed("push!(policy) PreActStage", policy.push, PreActStage, env)
+        _timed("optimise! PreActStage", policy.optimise, PreActStage)
+        _timed("push!(hook) PreActStage", hook.push, PreActStage, policy, env)
+        action = _timed("plan!", policy.plan, env)
+        _timed("act!", act, action)
+        _timed("push!(policy) PostActStage", policy.push, PostActStage, env, action)
+        _timed("optimise! PostActStage", policy.optimise, PostActStage)
+        _timed("push!(hook) PostActStage", hook.push, PostActStage, policy, env)
         if stop_condition.check(policy, env):
             is_stop = True
     policy.push(PostExperimentStage, env)

@@ -314,3 +314,21 @@ def test_julia_integer_seeding_helper(pkg):
     assert (int(O.lib().orc_rng_next(O._p(s))) >> 11) * 2.0 ** -53 == 0.32597672886359486
     with pytest.raises(ValueError):
         pkg.sharding.julia_xoshiro_states([-1])
+
+
+def test_debug_timer_mirrors_the_reference_labels(pkg):
+    """test/core/base.jl:41-58: after enable_debug_timings the run loop fills the global timer with the labels of run.jl:46-72; off by
+    default (and then nothing is recorded)."""
+    core = pkg.core
+    core.timer.clear()
+    pkg.run(pkg.RandomPolicy(), StubVecEnv([3, 4]), pkg.StopAfterNSteps(10))
+    assert core.timer == {}
+    core.enable_debug_timings()
+    try:
+        pkg.run(pkg.RandomPolicy(), StubVecEnv([3, 4], auto_reset=False), pkg.StopAfterNSteps(123))
+    finally:
+        core.enable_debug_timings(False)
+    assert isinstance(core.timer, core.TimerOutput)
+    assert set(core.timer) == {"reset!", "push!(policy) PreActStage", "optimise! PreActStage", "push!(hook) PreActStage", "plan!", "act!",
+                               "push!(policy) PostActStage", "optimise! PostActStage", "push!(hook) PostActStage"}
+    assert all(n == 123 and sec >= 0 for n, sec in core.timer.values()) and "act!" in str(core.timer)
