@@ -253,6 +253,29 @@ class StopAfterNSeconds:
         return time.time() > self.deadline
 
 
+# ---- reset conditions (reset_conditions.jl) ----------------------------------------------------
+class ResetIfEnvTerminated:
+    """reset_conditions.jl:5-12.  For the batched env it never fires: finished sub-envs are reset individually (soft reset /
+    in-kernel auto-reset), never the whole batch."""
+
+    def check(self, policy, env):
+        return False
+
+
+class ResetAfterNSteps:
+    """reset_conditions.jl:14-36: true on the (n + 1)-th check, i.e. after n steps; the whole batch is then force-reset."""
+
+    def __init__(self, n):
+        self.t, self.n = 0, int(n)
+
+    def check(self, policy, env):
+        stop = self.t >= self.n
+        self.t += 1
+        if stop:
+            self.t = 0
+        return stop
+
+
 class StopSignal:
     """stop_conditions.jl:185-200."""
 
@@ -290,11 +313,23 @@ class RandomPolicy(AbstractPolicy):
         return FusedAction("random")
 
 
-def run(policy, env, stop_condition=None, hook=None):
-    """Base.run(policy, env, stop_condition, hook) for a B200VecEnv (run.jl:22-78 with the
-    MultiThreadEnv control flow).  Returns the hook."""
+class Experiment:
+    """Experiment(policy, env, stop_condition, hook) (run.jl:8-20); ``run(experiment)`` runs it and returns it."""
+
+    def __init__(self, policy, env, stop_condition, hook):
+        self.policy, self.env, self.stop_condition, self.hook = policy, env, stop_condition, hook
+
+
+def run(policy, env=None, stop_condition=None, hook=None, reset_condition=None):
+    """Base.run(policy, env, stop_condition, hook[, reset_condition]) for a B200VecEnv (run.jl:22-78 with the
+    MultiThreadEnv control flow).  Returns the hook (``run(experiment)`` returns the experiment)."""
+    if isinstance(policy, Experiment):
+        ex = policy
+        run(ex.policy, ex.env, ex.stop_condition, ex.hook)
+        return ex
     stop_condition = stop_condition or StopAfterNEpisodes(1)
     hook = hook or EmptyHook()
+    reset_condition = reset_condition or ResetIfEnvTerminated()
     hook.push(PreExperimentStage, policy, env)
     policy.push(PreExperimentStage, env)
     env.reset_(is_force=True)  # run.jl:46
@@ -303,7 +338,7 @@ def run(policy, env, stop_condition=None, hook=None):
     # step-count stop condition let whole stretches of the loop below run as ONE kernel launch (agent.collect(n): n x
     # {plan!, act!, push!}) — the same transitions, parameters and statistics as stepping through the stages.
     if (getattr(policy, "fusable", False) and env.auto_reset and not getattr(hook, "per_step", True)
-            and isinstance(stop_condition, StopAfterNSteps)):
+            and isinstance(stop_condition, StopAfterNSteps) and isinstance(reset_condition, ResetIfEnvTerminated)):
         while not is_stop:
             n = min(policy.T - policy._t, stop_condition.remaining())
             policy.collect(n)
@@ -321,7 +356,11 @@ def run(policy, env, stop_condition=None, hook=None):
             env.act_(action)
 
     while not is_stop:   # labels as in run.jl:46-72
-        if not env.auto_reset:
+        did_reset = False
+        while reset_condition.check(policy, env):         # `while !check!(reset_condition, ...)` is evaluated again after the
+            _timed("reset!", env.reset_, is_force=True)   # reset (run.jl:46,52): the reference leaves the episode loop and resets
+            did_reset = True
+        if not did_reset and not env.auto_reset:
             _timed("reset!", env.reset_, is_force=False)  # soft reset of finished sub-envs
         _timed("push!(policy) PreActStage", policy.push, PreActStage, env)
         _timed("optimise! PreActStage", policy.optimise, PreActStage)

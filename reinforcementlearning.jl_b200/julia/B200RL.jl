@@ -236,7 +236,7 @@ function RLCore._run(policy::AbstractPolicy, env::B200VecEnv, stop_condition::Ab
     # step and a step-count stop condition let whole stretches of the loop run as ONE kernel launch (b200rl_onpolicy_collect:
     # n x {plan!, act!, push!}) — the same transitions, parameters and statistics as stepping through the stages.
     if policy isa B200OnPolicyAgent && policy.fused && env.auto_reset && hook isa Union{B200EpisodeStats,RLCore.EmptyHook} &&
-       stop_condition isa StopAfterNSteps
+       stop_condition isa StopAfterNSteps && reset_condition isa ResetIfEnvTerminated
         while true                                                  # StopAfterNSteps: check! is true once cur >= step, then cur += 1
             n = min(policy.T - policy.t, max(1, stop_condition.step - stop_condition.cur + 1))
             collect!(policy, n)
@@ -252,7 +252,12 @@ function RLCore._run(policy::AbstractPolicy, env::B200VecEnv, stop_condition::Ab
     end
     timer = RLCore.timer                                       # same labels as run.jl:46-72
     while true
-        env.auto_reset || @timeit_debug timer "reset!"          RLBase.reset!(env; is_force = false)
+        did_reset = false
+        while RLCore.check!(reset_condition, policy, env)      # ResetAfterNSteps: the whole batch is force-reset (ResetIfEnvTerminated never fires)
+            @timeit_debug timer "reset!"                        RLBase.reset!(env; is_force = true)
+            did_reset = true
+        end
+        (did_reset || env.auto_reset) || @timeit_debug timer "reset!" RLBase.reset!(env; is_force = false)
         @timeit_debug timer "push!(policy) PreActStage"         push!(policy, PreActStage(), env)
         @timeit_debug timer "optimise! PreActStage"             RLBase.optimise!(policy, PreActStage())
         @timeit_debug timer "push!(hook) PreActStage"           push!(hook, PreActStage(), policy, env)

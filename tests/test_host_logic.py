@@ -332,3 +332,19 @@ def test_debug_timer_mirrors_the_reference_labels(pkg):
     assert set(core.timer) == {"reset!", "push!(policy) PreActStage", "optimise! PreActStage", "push!(hook) PreActStage", "plan!", "act!",
                                "push!(policy) PostActStage", "optimise! PostActStage", "push!(hook) PostActStage"}
     assert all(n == 123 and sec >= 0 for n, sec in core.timer.values()) and "act!" in str(core.timer)
+
+
+def test_reset_conditions_and_experiment(pkg):
+    """reset_conditions.jl: ResetAfterNSteps(n) fires on its (n + 1)-th check (after n steps) and the whole batch is force-reset;
+    ResetIfEnvTerminated never fires for a batched env.  Experiment bundles the four run arguments (run.jl:8-20)."""
+    r = pkg.ResetAfterNSteps(3)
+    assert [r.check(None, None) for _ in range(9)] == [False, False, False, True, False, False, False, True, False]
+    assert pkg.ResetIfEnvTerminated().check(None, StubVecEnv([1])) is False
+    env = StubVecEnv([50, 50])
+    pkg.run(pkg.RandomPolicy(), env, pkg.StopAfterNSteps(10), None, pkg.ResetAfterNSteps(4))
+    resets = [i for i, e in enumerate(env.log) if e == ("reset", True)]
+    steps_before = [sum(1 for e in env.log[:i] if e[0] == "act_random") for i in resets]
+    assert steps_before == [0, 4, 8]                               # run.jl:46 reset, then after every 4 steps
+    env2 = StubVecEnv([2, 3])
+    ex = pkg.Experiment(pkg.RandomPolicy(), env2, pkg.StopAfterNSteps(5), pkg.BatchStepsPerEpisode(2))
+    assert pkg.run(ex) is ex and ex.hook[()] == [[2, 2], [3]]
