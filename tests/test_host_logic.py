@@ -65,6 +65,9 @@ class StubVecEnv:
     def check(self):
         self.log.append(("check",))
 
+    def episode_stats(self, reset=False):
+        return {"episodes": 0, "return_sum": 0.0, "length_sum": 0.0, "env_steps": 0}
+
 
 @pytest.mark.parametrize("case", [c for c in GOLD["stop_conditions"] if "trues" in c], ids=lambda c: c["ref"])
 def test_stop_condition_counts_golden(pkg, case):
@@ -348,3 +351,58 @@ def test_reset_conditions_and_experiment(pkg):
     env2 = StubVecEnv([2, 3])
     ex = pkg.Experiment(pkg.RandomPolicy(), env2, pkg.StopAfterNSteps(5), pkg.BatchStepsPerEpisode(2))
     assert pkg.run(ex) is ex and ex.hook[()] == [[2, 2], [3]]
+
+
+class StubFusedAgent:
+    """The surface run() uses of a device-resident OnPolicyAgent: collect(n) / update() bookkeeping only."""
+    fusable, fetch_stats = True, False
+
+    def __init__(self, T):
+        self.T, self._t, self.calls, self.pushed = T, 0, [], []
+
+    def push(self, stage, env, action=None):
+        self.pushed.append(stage)
+
+    def collect(self, n):
+        assert 1 <= n <= self.T - self._t
+        self.calls.append(("collect", n))
+        self._t += n
+
+    def update(self, want_stats=False):
+        assert self._t == 0                      # run() clears the fill level before the update, like OnPolicyAgent.update does
+        self.calls.append(("update",))
+
+    def plan(self, env):
+        from_stage = pkg_core.FusedAction("policy")
+        self.calls.append(("plan",))
+        return from_stage
+
+    def act_fused(self, env):
+        self.calls.append(("act_fused",))
+        env._step()
+
+    def optimise(self, stage):
+        pass
+
+
+def test_fused_fast_path_hands_whole_stretches_to_collect(pkg):
+    """run() with a fusable agent + a hook that does nothing per step + StopAfterNSteps: stretches of min(T - t, remaining) steps, an
+    update whenever the rollout is full, exactly n env steps in total — and the stage loop otherwise."""
+    global pkg_core
+    pkg_core = pkg.core
+    agent = StubFusedAgent(T=8)
+    env = StubVecEnv([5, 7])
+    pkg.run(agent, env, pkg.StopAfterNSteps(21), pkg.DeviceEpisodeStats())   # per_step = False: nothing happens at the act stages
+    assert agent.calls == [("collect", 8), ("update",), ("collect", 8), ("update",), ("collect", 5)]
+    assert agent._t == 5 and env.log[0] == ("reset", True) and env.log[-1] == ("check",)
+    assert agent.pushed == ["PreExperimentStage", "PostExperimentStage"]
+    # a second run continues filling the same rollout: 3 more steps complete it
+    pkg.run(agent, env, pkg.StopAfterNSteps(4), pkg.EmptyHook())
+    assert agent.calls[-3:] == [("collect", 3), ("update",), ("collect", 1)]
+    # a per-step hook (or a reset condition) falls back to the stage protocol: plan! -> act_fused per step
+    agent2 = StubFusedAgent(T=8)
+    pkg.run(agent2, StubVecEnv([5, 7]), pkg.StopAfterNSteps(3), pkg.BatchStepsPerEpisode(2))
+    assert agent2.calls == [("plan",), ("act_fused",)] * 3
+    agent3 = StubFusedAgent(T=8)
+    pkg.run(agent3, StubVecEnv([5, 7]), pkg.StopAfterNSteps(3), pkg.EmptyHook(), pkg.ResetAfterNSteps(2))
+    assert agent3.calls == [("plan",), ("act_fused",)] * 3
