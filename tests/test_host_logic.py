@@ -406,3 +406,47 @@ def test_fused_fast_path_hands_whole_stretches_to_collect(pkg):
     agent3 = StubFusedAgent(T=8)
     pkg.run(agent3, StubVecEnv([5, 7]), pkg.StopAfterNSteps(3), pkg.EmptyHook(), pkg.ResetAfterNSteps(2))
     assert agent3.calls == [("plan",), ("act_fused",)] * 3
+
+
+def test_replay_agent_stage_logic_with_stubs(pkg):
+    """learners.Agent (agent_base.jl:18-66 for a device ring): first state at the first PreActStage, one frame + one controller insertion
+    per PostActStage, the learner trains while the controller allows, re-entry on a non-empty ring is refused."""
+    class Traj:
+        def __init__(self):
+            self.frames, self.first_states = 0, 0
+            self.controller = pkg.InsertSampleRatioController(ratio=0.5, threshold=3)
+
+        def __len__(self):
+            return self.frames
+
+        def push_env(self, env, first_state_only=False):
+            if first_state_only:
+                self.first_states += 1
+            else:
+                self.frames += 1
+
+    class Learner:
+        updates = 0
+
+        def update(self):
+            Learner.updates += 1
+
+    class Policy:
+        learner = Learner()
+        optimise = pkg.QBasedPolicy.optimise              # the real method: `while trajectory.controller.on_sample(): learner.update()`
+
+        def plan(self, env):
+            return pkg.core.FusedAction("policy")
+
+        def act_fused(self, env):
+            env._step()
+
+    traj = Traj()
+    agent = pkg.Agent(Policy(), traj)
+    env = StubVecEnv([4, 6])
+    pkg.run(agent, env, pkg.StopAfterNSteps(9))
+    assert traj.first_states == 1 and traj.frames == 9 and traj.controller.n_inserted == 9
+    assert Learner.updates == traj.controller.n_sampled == int((9 - 3) * 0.5) + 1
+    with pytest.raises(RuntimeError):
+        pkg.run(agent, env, pkg.StopAfterNSteps(1))
+    assert traj.frames == 9                                 # nothing was pushed by the refused run
