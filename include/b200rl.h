@@ -56,6 +56,15 @@ int b200rl_stream(b200rl_ctx* ctx, void** stream_out);
 /* device timing on the ctx stream (CUDA events) for hosts without a CUDA binding */
 int b200rl_timer_start(b200rl_ctx* ctx);
 int b200rl_timer_stop_ms(b200rl_ctx* ctx, float* ms_out);   /* synchronises */
+/* event slots (0..511): record points on the ctx stream without synchronising the host, read the intervals afterwards
+ * (elapsed_ms waits for slot_to's event only).  A benchmark loop records 2 slots per step and syncs once at the end, so the
+ * host can run ahead of the device. */
+int b200rl_timer_record(b200rl_ctx* ctx, int slot);
+int b200rl_timer_elapsed_ms(b200rl_ctx* ctx, int slot_from, int slot_to, float* ms_out);
+/* measurement aid: base_slot >= 0 makes b200rl_onpolicy_update (eager launches only) record its phases into the slots
+ * base_slot + {0 entry, 1 after bootstrap/GAE/normalisation/record packing, 2+2i after loss+backward i, 3+2i after optimiser step i};
+ * -1 switches it off */
+int b200rl_debug_phase_slots(b200rl_ctx* ctx, int base_slot);
 /* device / pinned-host buffers for hosts without a CUDA binding (Julia without CUDA.jl) */
 int b200rl_malloc(b200rl_ctx* ctx, size_t bytes, void** dptr_out);
 int b200rl_free(b200rl_ctx* ctx, void* dptr);
@@ -289,6 +298,13 @@ int b200rl_onpolicy_collect(b200rl_onpolicy* agent, int n_steps);
 int b200rl_onpolicy_fill(b200rl_onpolicy* agent, int* t_out, int* T_out);
 /* optimise!(agent): GAE + n_epochs x n_microbatches optimiser steps; see algo.cu */
 int b200rl_onpolicy_update(b200rl_onpolicy* agent, const int32_t* perm_host, float* stats_host);
+/* n_iters x { collect(update_freq); optimise! }: the whole PPO / A2C iteration replayed as ONE CUDA graph launch per iteration
+ * (captured on the second iteration; the first one runs eagerly).  Needs an empty rollout.  Same results as collect + update.
+ * stats_host: optional (n_epochs * n_microbatches, 6) rows of the last iteration (forces a sync).  This is the path the
+ * `_run` specialisation takes between hook calls (RLCore/src/core/run.jl:52-68 — plan!, act!, push!, optimise! for
+ * update_freq steps) when no host-side hook needs per-step data. */
+int b200rl_onpolicy_iterate(b200rl_onpolicy* agent, int n_iters, float* stats_host);
+int b200rl_onpolicy_graph_active(b200rl_onpolicy* agent, int* out);   /* 1: iterate replays a captured graph */
 /* field: 0 state (ns,N,T+1) | 1 action | 2 logp | 3 reward | 4 terminal u8 | 5 value (N,T+1) |
  * 6 advantage | 7 return | 8 policy rng (4,N) u64 | 9 {adv mean, inv std} */
 int b200rl_onpolicy_get(b200rl_onpolicy* agent, int field, void* host_dst, size_t bytes);

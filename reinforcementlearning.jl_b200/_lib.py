@@ -74,6 +74,9 @@ SIGNATURES = {
     "b200rl_stream": (_i32, [_vp, _pp]),
     "b200rl_timer_start": (_i32, [_vp]),
     "b200rl_timer_stop_ms": (_i32, [_vp, C.POINTER(_f32)]),
+    "b200rl_timer_record": (_i32, [_vp, _i32]),
+    "b200rl_timer_elapsed_ms": (_i32, [_vp, _i32, _i32, C.POINTER(_f32)]),
+    "b200rl_debug_phase_slots": (_i32, [_vp, _i32]),
     "b200rl_malloc": (_i32, [_vp, _sz, _pp]),
     "b200rl_free": (_i32, [_vp, _vp]),
     "b200rl_host_alloc": (_i32, [_vp, _sz, _pp]),
@@ -133,6 +136,8 @@ SIGNATURES = {
     "b200rl_onpolicy_collect": (_i32, [_vp, _i32]),
     "b200rl_onpolicy_fill": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "b200rl_onpolicy_update": (_i32, [_vp, _vp, _vp]),
+    "b200rl_onpolicy_iterate": (_i32, [_vp, _i32, _vp]),
+    "b200rl_onpolicy_graph_active": (_i32, [_vp, C.POINTER(_i32)]),
     "b200rl_onpolicy_get": (_i32, [_vp, _i32, _vp, _sz]),
     "b200rl_onpolicy_set": (_i32, [_vp, _i32, _vp, _sz]),
     "b200rl_onpolicy_export_state": (_i32, [_vp, _vp]),
@@ -222,6 +227,17 @@ class Context:
         ms = C.c_float()
         check(self.lib.b200rl_timer_stop_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def timer_record(self, slot):
+        check(self.lib.b200rl_timer_record(self.h, slot))
+
+    def timer_elapsed_ms(self, slot_from, slot_to):
+        ms = C.c_float()
+        check(self.lib.b200rl_timer_elapsed_ms(self.h, slot_from, slot_to, C.byref(ms)))
+        return ms.value
+
+    def phase_slots(self, base_slot):
+        check(self.lib.b200rl_debug_phase_slots(self.h, base_slot))
 
     def launch_count(self):
         n = C.c_uint64()

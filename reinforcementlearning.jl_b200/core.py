@@ -340,6 +340,12 @@ def run(policy, env=None, stop_condition=None, hook=None, reset_condition=None):
     if (getattr(policy, "fusable", False) and env.auto_reset and not getattr(hook, "per_step", True)
             and isinstance(stop_condition, StopAfterNSteps) and isinstance(reset_condition, ResetIfEnvTerminated)):
         while not is_stop:
+            if policy._t == 0 and stop_condition.remaining() >= policy.T and hasattr(policy, "iterate"):
+                # whole iterations (rollout + update) as one CUDA-graph launch each (b200rl_onpolicy_iterate)
+                k = stop_condition.remaining() // policy.T if not policy.fetch_stats else 1
+                policy.iterate(k, want_stats=policy.fetch_stats)
+                is_stop = stop_condition.advance(k * policy.T)
+                continue
             n = min(policy.T - policy._t, stop_condition.remaining())
             policy.collect(n)
             if policy._t == policy.T:

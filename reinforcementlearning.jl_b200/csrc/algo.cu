@@ -29,6 +29,8 @@ int b200rl_traj_internal_priority_from_td(b200rl_traj* t, const float* td_dev, f
 int b200rl_comm_allreduce_internal(b200rl_ctx* ctx, void* buf, int64_t n, int is_double);
 int b200rl_comm_world(b200rl_ctx* ctx);
 int b200rl_env_internal_kind(const b200rl_env* e);
+int b200rl_env_internal_max_timeout(const b200rl_env* e);
+void b200rl_env_internal_add_steps(b200rl_env* e, uint64_t n);
 static bool fused_rollout_enabled() {   // B200RL_FUSED_ROLLOUT=0: step through plan!/act! launches instead (same results)
     static int v = -1;
     if (v < 0) { const char* e = getenv("B200RL_FUSED_ROLLOUT"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -44,9 +46,33 @@ __global__ void copy_f32_kernel(float* __restrict__ dst, const float* __restrict
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
 }
-__global__ void stats_row_kernel(float* __restrict__ row, const float* __restrict__ loss4, const float* __restrict__ gnorm) {
+__global__ void stats_row_kernel(float* __restrict__ row, const float* __restrict__ loss4, const float* __restrict__ gnorm,
+                                 unsigned int* __restrict__ tick) {
     if (threadIdx.x < 4) row[threadIdx.x] = loss4[threadIdx.x];
     if (threadIdx.x == 4) row[4] = *gnorm;
+    if (threadIdx.x == 5 && tick) *tick += 1u;
+}
+// After GAE: one 32-byte record per rollout sample {state (zero padded to 4), action bits, logp_old, advantage, return}, so the
+// randomly permuted minibatch gather of K7 touches ONE DRAM sector per sample instead of one per array (5 arrays: ~4x the
+// algorithmic bytes, profiles/r01_ncu_summary.md).  Streaming: 32 B read + 32 B written per sample, fully coalesced.
+template <int NS>
+__global__ void __launch_bounds__(256) pack_records_kernel(float4* __restrict__ rec, const float* __restrict__ states, const uint32_t* __restrict__ actions,
+                                                          const float* __restrict__ logp, const float* __restrict__ adv, const float* __restrict__ ret,
+                                                          int64_t total) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= total) return;
+    float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NS == 4) st = reinterpret_cast<const float4*>(states)[j];
+    else {
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < NS; ++i) x[i] = states[(int64_t)NS * j + i];
+        st = make_float4(x[0], x[1], x[2], x[3]);
+    }
+    float4 sc = make_float4(__uint_as_float(actions[j]), logp[j], adv[j], ret[j]);
+    // 32 lanes x 32 B = 1 KB contiguous per warp: two 16-byte stores per thread land in the same sector
+    rec[2 * j] = st;
+    rec[2 * j + 1] = sc;
 }
 __global__ void sum_norm_partials_kernel(const double* __restrict__ partials, int n, double* __restrict__ out2) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -77,7 +103,7 @@ struct b200rl_net {
     float *params, *grad, *m, *v, *beta_t, *target;
     float* partial; int n_partials;
     float* loss_partial; float* loss4; float* gnorm;
-    double* cta_sumsq; unsigned int* counter2; unsigned int fused_launches;
+    double* cta_sumsq; unsigned int* counter2;
     float lr, b1, b2, eps, max_grad_norm;
     uint64_t n_updates;
 };
@@ -324,7 +350,7 @@ int b200rl_net_ac_step(b200rl_net* n, const b200rl_onpolicy_config* cfg, const f
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // host buffers (incl. the local iota) are borrowed for this call only
     AcHyper hp{cfg->clip_range, cfg->w_actor, cfg->w_critic, cfg->w_entropy, cfg->min_sigma, cfg->max_sigma, cfg->normalize_advantage, cfg->algo};
     AcBatch b{(const float*)(base + o_s), ns, base + o_a, logp_old ? (const float*)(base + o_l) : nullptr, (const float*)(base + o_ad),
-              (const float*)(base + o_r), (const int32_t*)(base + o_i), (uint32_t)total, 0u, 0u, Beff, 1.0f / (float)Beff,
+              (const float*)(base + o_r), (const int32_t*)(base + o_i), (uint32_t)total, 0u, 0u, nullptr, nullptr, Beff, 1.0f / (float)Beff,
               (const float*)(base + o_n)};
     int ctas = nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
     if (ctas < 0) return ctas;
@@ -364,7 +390,11 @@ struct b200rl_onpolicy {
     double* norm_partials; double* norm_sums; float* norm2;
     int32_t* perm_dev;
     float* stats_dev; int stats_rows;
+    float4* rec;                 // packed 32-byte records of the rollout (written after GAE, gathered by K7)
+    unsigned int* upd_dev;       // device copy of n_updates: keys the minibatch permutation, ticked by the last optimiser step of an update
     uint64_t n_updates;
+    // CUDA graph of one whole iteration (collect(T) + update) for b200rl_onpolicy_iterate
+    cudaGraph_t graph; cudaGraphExec_t graph_exec; bool warmed; int graph_tc; uint64_t graph_env_gen; uint64_t graph_launches; int graph_failed;
 };
 
 static void* env_field(b200rl_env* e, int f) { void* p = nullptr; b200rl_env_ptr(e, f, &p); return p; }
@@ -378,7 +408,9 @@ int b200rl_onpolicy_destroy(b200rl_onpolicy* a) {
     b200rl_env_internal_set_traj_targets(a->env, nullptr, nullptr);
     cudaFree(a->rng); cudaFree(a->states); cudaFree(a->actions); cudaFree(a->logp); cudaFree(a->rewards); cudaFree(a->terminals);
     cudaFree(a->values); cudaFree(a->adv); cudaFree(a->ret); cudaFree(a->act_clamped); cudaFree(a->norm_partials); cudaFree(a->norm_sums);
-    cudaFree(a->norm2); cudaFree(a->perm_dev); cudaFree(a->stats_dev);
+    cudaFree(a->norm2); cudaFree(a->perm_dev); cudaFree(a->stats_dev); cudaFree(a->rec); cudaFree(a->upd_dev);
+    if (a->graph_exec) cudaGraphExecDestroy(a->graph_exec);
+    if (a->graph) cudaGraphDestroy(a->graph);
     delete a;
     return B200RL_OK;
 }
@@ -418,6 +450,9 @@ int b200rl_onpolicy_create(b200rl_ctx* ctx, b200rl_net* net, b200rl_env* env, co
     // staging for host-supplied shuffle!() results; allocated here because a device allocation inside update would
     // synchronise the device (and with it another rank of the same process that is waiting in the peer exchange)
     A_TRY(cudaMalloc(&a->perm_dev, (size_t)a->cfg.n_epochs * NT_ * 4));
+    A_TRY(cudaMalloc(&a->rec, NT_ * 32));
+    A_TRY(cudaMalloc(&a->upd_dev, sizeof(unsigned int)));
+    A_TRY(cudaMemsetAsync(a->upd_dev, 0, sizeof(unsigned int), ctx->stream));
     A_TRY(cudaMemsetAsync(a->stats_dev, 0, (size_t)a->stats_rows * 8 * sizeof(float), ctx->stream));
     A_TRY(cudaMemcpyAsync(a->rng, policy_rng, (size_t)N * 32, cudaMemcpyHostToDevice, ctx->stream));
     A_TRY(cudaStreamSynchronize(ctx->stream));
@@ -516,6 +551,12 @@ int b200rl_onpolicy_update(b200rl_onpolicy* a, const int32_t* perm_host, float* 
     const b200rl_onpolicy_config& c = a->cfg;
     int64_t N = a->N, T = a->T, NT_ = N * T;
     int world = b200rl_comm_world(ctx);
+    // measurement aid (b200rl_debug_phase_slots): events between the phases, eager path only
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(ctx->stream, &cap));
+    const int pb = (cap == cudaStreamCaptureStatusNone && ctx->phase_base + 3 + 2 * a->stats_rows <= b200rl_ctx::kTimerSlots) ? ctx->phase_base : -1;
+    auto phase = [&](int k) -> int { return pb >= 0 ? b200rl_timer_record(ctx, pb + k) : B200RL_OK; };
+    TRY(phase(0));
     // bootstrap value of the state after the last step
     const float* obs = (const float*)env_field(a->env, B200RL_FIELD_OBS);
     // (a copy kernel, not cudaMemcpyAsync D2D: device-to-device copies are on CUDA's implicit-synchronisation list)
@@ -539,33 +580,50 @@ int b200rl_onpolicy_update(b200rl_onpolicy* a, const int32_t* perm_host, float* 
         finalize_norm2_kernel<<<1, 32, 0, ctx->stream>>>(a->norm_sums, (double)NT_ * (double)world, a->norm2);
         LAUNCH_CHECK(ctx);
     }
+    {   // one 32-byte record per sample for the permuted minibatch gathers (n_epochs x n_microbatches of them follow)
+        const unsigned g = grid_for(NT_, 256);
+        const uint32_t* act = (const uint32_t*)a->actions;
+        switch (a->ns) {
+            case 1: pack_records_kernel<1><<<g, 256, 0, ctx->stream>>>(a->rec, a->states, act, a->logp, a->adv, a->ret, NT_); break;
+            case 2: pack_records_kernel<2><<<g, 256, 0, ctx->stream>>>(a->rec, a->states, act, a->logp, a->adv, a->ret, NT_); break;
+            case 3: pack_records_kernel<3><<<g, 256, 0, ctx->stream>>>(a->rec, a->states, act, a->logp, a->adv, a->ret, NT_); break;
+            default: pack_records_kernel<4><<<g, 256, 0, ctx->stream>>>(a->rec, a->states, act, a->logp, a->adv, a->ret, NT_); break;
+        }
+        LAUNCH_CHECK(ctx);
+    }
     if (perm_host) {
         CUDA_TRY(cudaMemcpyAsync(a->perm_dev, perm_host, (size_t)c.n_epochs * NT_ * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
+    TRY(phase(1));
     AcHyper hp{c.clip_range, c.w_actor, c.w_critic, c.w_entropy, c.min_sigma, c.max_sigma, c.normalize_advantage, c.algo};
     int64_t B = NT_ / c.n_microbatches;
     int row = 0;
     for (int e = 0; e < c.n_epochs; ++e) {
         for (int mb = 0; mb < c.n_microbatches; ++mb, ++row) {
+            // permutation key = n_updates * 1000003 + e * 7919 + 12345; the update counter is read from device memory (upd_dev)
+            // so that a captured iteration can be replayed
             AcBatch b{a->states, a->ns, a->actions, a->logp, a->adv, a->ret,
                       perm_host ? a->perm_dev + (size_t)e * NT_ + (size_t)mb * B : nullptr,
-                      (uint32_t)NT_, (uint32_t)(a->n_updates * 1000003u + (uint32_t)e * 7919u + 12345u), (uint32_t)(mb * B), B,
+                      (uint32_t)NT_, (uint32_t)e * 7919u + 12345u, (uint32_t)(mb * B), a->upd_dev, a->rec, B,
                       1.0f / ((float)B * (float)world), a->norm2};
             int ctas = nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
             if (ctas < 0) return ctas;
+            TRY(phase(2 + 2 * row));
             float* stats_row = a->stats_dev + (size_t)row * 8;
+            unsigned int* tick = row == a->stats_rows - 1 ? a->upd_dev : nullptr;   // the last optimiser step closes the update
             P2PTable peers;
             if (world > 1 && !b200rl_comm_p2p_table(ctx, &peers)) {   // no peer exchange attached: reduce -> NCCL all-reduce -> clip + Adam
                 TRY(nn_reduce_partials(ctx, n->partial, ctas, n->np, n->grad, n->loss_partial, 2 * ctas, n->loss4));
                 TRY(b200rl_comm_allreduce_internal(ctx, n->grad, n->np, 0));
                 TRY(b200rl_comm_allreduce_internal(ctx, n->loss4, 4, 0));
                 TRY(nn_clip_adam(ctx, n->params, n->grad, n->m, n->v, n->beta_t, n->np, c.max_grad_norm, c.lr, c.beta1, c.beta2, c.eps, 1.0f, n->gnorm));
-                stats_row_kernel<<<1, 32, 0, ctx->stream>>>(stats_row, n->loss4, n->gnorm);
+                stats_row_kernel<<<1, 32, 0, ctx->stream>>>(stats_row, n->loss4, n->gnorm, tick);
                 LAUNCH_CHECK(ctx);
             } else {   // one kernel: reduce [-> exchange with the peers over NVLink] -> clip -> Adam -> stats row
                 TRY(nn_reduce_clip_adam(ctx, n->partial, ctas, n->np, n->params, n->grad, n->m, n->v, n->beta_t, n->loss_partial, 2 * ctas, n->loss4,
-                                        c.max_grad_norm, c.lr, c.beta1, c.beta2, c.eps, n->gnorm, n->cta_sumsq, n->counter2, &n->fused_launches, stats_row));
+                                        c.max_grad_norm, c.lr, c.beta1, c.beta2, c.eps, n->gnorm, n->cta_sumsq, n->counter2, stats_row, tick));
             }
+            TRY(phase(3 + 2 * row));
             n->n_updates += 1;
         }
     }
@@ -584,6 +642,95 @@ int b200rl_onpolicy_update(b200rl_onpolicy* a, const int32_t* perm_host, float* 
             o[4] = s[4]; o[5] = 0.f;
         }
     }
+    return B200RL_OK;
+}
+
+/* n_iters x { collect(T); update } — the whole PPO / A2C iteration (fused rollout, bootstrap, GAE, record packing, n_epochs x
+ * n_microbatches x {loss + backward, [peer exchange +] clip + Adam}) replayed as ONE CUDA graph launch per iteration, so
+ * the ranks of a sharded run cannot drift apart on host launch jitter (they meet 17 times per iteration inside the peer
+ * exchange).  Needs an empty rollout (t = 0).  Every per-launch counter lives in device memory (update counter, exchange
+ * sequence numbers, self-resetting grid barrier), so the captured launches are replayable as they are.  The first
+ * iteration ever runs eagerly (lazy module loading, scratch growth, function attributes), the second is captured.
+ * stats_host: optional (n_epochs * n_microbatches, 6) rows of the LAST iteration (forces a sync).
+ * Falls back to eager launches when capture is impossible (NCCL path without the peer exchange, B200RL_GRAPH=0). */
+int b200rl_onpolicy_iterate(b200rl_onpolicy* a, int n_iters, float* stats_host) {
+    REQUIRE(a && n_iters >= 0, B200RL_ERR_INVALID, "bad argument");
+    REQUIRE(a->t == 0, B200RL_ERR_INVALID, "iterate needs an empty rollout (t = 0)");
+    TRY(ctx_bind(a->ctx));
+    b200rl_ctx* ctx = a->ctx;
+    static int graph_env = -1;
+    if (graph_env < 0) { const char* e = getenv("B200RL_GRAPH"); graph_env = (e && e[0] == '0') ? 0 : 1; }
+    P2PTable peers;
+    const bool capturable = graph_env && !a->graph_failed && ctx->phase_base < 0 && (b200rl_comm_world(ctx) == 1 || b200rl_comm_p2p_table(ctx, &peers));
+    const int rows = a->stats_rows;
+    for (int it = 0; it < n_iters; ++it) {
+        if (!capturable || !a->warmed) {
+            TRY(b200rl_onpolicy_collect(a, a->T));
+            TRY(b200rl_onpolicy_update(a, nullptr, nullptr));
+            a->warmed = true;
+            continue;
+        }
+        const int tc_now = nn_tc_enabled() ? 1 : 0;
+        const uint64_t env_gen = (uint64_t)b200rl_env_internal_max_timeout(a->env);
+        if (a->graph_exec && (a->graph_tc != tc_now || a->graph_env_gen != env_gen)) {   // a launch argument changed: re-capture
+            cudaGraphExecDestroy(a->graph_exec); a->graph_exec = nullptr;
+            cudaGraphDestroy(a->graph); a->graph = nullptr;
+        }
+        if (!a->graph_exec) {
+            // capture does not execute: the host-side bookkeeping the captured calls did is rolled back and redone per replay
+            const uint64_t l0 = ctx->launches, nu0 = a->n_updates, nnu0 = a->net->n_updates;
+            CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            int st = b200rl_onpolicy_collect(a, a->T);
+            if (st == B200RL_OK) st = b200rl_onpolicy_update(a, nullptr, nullptr);
+            cudaGraph_t g = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+            a->graph_launches = ctx->launches - l0;
+            ctx->launches = l0; a->n_updates = nu0; a->net->n_updates = nnu0; a->t = 0; a->bootstrap_done = false;
+            b200rl_env_internal_add_steps(a->env, (uint64_t)0 - (uint64_t)a->T);
+            if (st != B200RL_OK || ce != cudaSuccess || !g) {
+                if (g) cudaGraphDestroy(g);
+                cudaGetLastError();
+                a->graph_failed = 1;   // stay on eager launches
+                TRY(b200rl_onpolicy_collect(a, a->T));
+                TRY(b200rl_onpolicy_update(a, nullptr, nullptr));
+                continue;
+            }
+            cudaError_t ie = cudaGraphInstantiate(&a->graph_exec, g, 0);
+            if (ie != cudaSuccess) {
+                cudaGraphDestroy(g);
+                cudaGetLastError();
+                a->graph_exec = nullptr; a->graph_failed = 1;
+                TRY(b200rl_onpolicy_collect(a, a->T));
+                TRY(b200rl_onpolicy_update(a, nullptr, nullptr));
+                continue;
+            }
+            a->graph = g; a->graph_tc = tc_now; a->graph_env_gen = env_gen;
+        }
+        CUDA_TRY(cudaGraphLaunch(a->graph_exec, ctx->stream));
+        ctx->launches += a->graph_launches;
+        a->n_updates += 1; a->net->n_updates += (uint64_t)rows;
+        b200rl_env_internal_add_steps(a->env, (uint64_t)a->T);
+    }
+    if (stats_host && n_iters > 0) {
+        const b200rl_onpolicy_config& c = a->cfg;
+        std::vector<float> tmp((size_t)rows * 8);
+        CUDA_TRY(cudaMemcpyAsync(tmp.data(), a->stats_dev, tmp.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        float invB = 1.0f / ((float)(a->N * a->T / c.n_microbatches) * (float)b200rl_comm_world(ctx));
+        for (int r = 0; r < rows; ++r) {
+            float* o = stats_host + (size_t)r * 6;
+            const float* s = tmp.data() + (size_t)r * 8;
+            o[0] = s[0] * invB; o[1] = s[2] * invB; o[2] = s[1] * invB;
+            o[3] = c.w_actor * o[0] + c.w_critic * o[1] - c.w_entropy * o[2];
+            o[4] = s[4]; o[5] = 0.f;
+        }
+    }
+    return B200RL_OK;
+}
+/* 1 when b200rl_onpolicy_iterate replays a captured graph, 0 when it launches eagerly (diagnostic for tests / bench) */
+int b200rl_onpolicy_graph_active(b200rl_onpolicy* a, int* out) {
+    REQUIRE(a && out, B200RL_ERR_INVALID, "null argument");
+    *out = a->graph_exec ? 1 : 0;
     return B200RL_OK;
 }
 
@@ -646,6 +793,10 @@ int b200rl_onpolicy_import_state(b200rl_onpolicy* a, const int64_t* c3) {
     REQUIRE(a && c3, B200RL_ERR_INVALID, "null argument");
     REQUIRE(c3[0] >= 0 && c3[0] <= a->T && c3[1] >= 0 && c3[2] >= 0, B200RL_ERR_INVALID, "counters out of range");
     a->t = (int)c3[0]; a->n_updates = (uint64_t)c3[1]; a->net->n_updates = (uint64_t)c3[2];
+    TRY(ctx_bind(a->ctx));
+    const unsigned int upd = (unsigned int)a->n_updates;   // the device copy keys the minibatch permutation
+    CUDA_TRY(cudaMemcpyAsync(a->upd_dev, &upd, sizeof upd, cudaMemcpyHostToDevice, a->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->ctx->stream));
     a->bootstrap_done = false;   // column T of states / values is rewritten from the env's observation by the next update
     b200rl_env_internal_set_traj_targets(a->env, nullptr, nullptr);
     return B200RL_OK;
@@ -673,7 +824,7 @@ int b200rl_onpolicy_time_kernel(b200rl_onpolicy* a, int which, int reps, float* 
     auto once = [&]() -> int {
         switch (which) {
             case 0: {
-                AcBatch b{a->states, a->ns, a->actions, a->logp, a->adv, a->ret, nullptr, (uint32_t)NT_, 12345u, 0u, B, 1.0f / (float)B,
+                AcBatch b{a->states, a->ns, a->actions, a->logp, a->adv, a->ret, nullptr, (uint32_t)NT_, 12345u, 0u, nullptr, a->rec, B, 1.0f / (float)B,
                           a->norm2};
                 int st = nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
                 return st < 0 ? st : B200RL_OK;
@@ -693,7 +844,7 @@ int b200rl_onpolicy_time_kernel(b200rl_onpolicy* a, int which, int reps, float* 
                     return nn_clip_adam(ctx, n->params, n->grad, n->m, n->v, n->beta_t, n->np, c.max_grad_norm, 0.0f, c.beta1, c.beta2, c.eps, 1.0f, n->gnorm);
                 }
                 return nn_reduce_clip_adam(ctx, n->partial, ctas, n->np, n->params, n->grad, n->m, n->v, n->beta_t, n->loss_partial, 2 * ctas, n->loss4,
-                                           c.max_grad_norm, 0.0f, c.beta1, c.beta2, c.eps, n->gnorm, n->cta_sumsq, n->counter2, &n->fused_launches, nullptr);
+                                           c.max_grad_norm, 0.0f, c.beta1, c.beta2, c.eps, n->gnorm, n->cta_sumsq, n->counter2, nullptr, nullptr);
             }
         }
         b200rl_set_error("unknown kernel id");

@@ -71,13 +71,14 @@ struct b200rl_comm_state {
     unsigned char* region = nullptr;        // this rank's exchange region (cudaMalloc, exported through CUDA IPC)
     void* opened[kP2PMaxRanks] = {};        // peer regions opened with cudaIpcOpenMemHandle (closed on destroy)
     P2PTable tab = {};                      // tab.nranks > 0 once attached
-    uint32_t gseq = 0, yseq = 0;            // sequence numbers of the gradient / small all-reduce exchanges
+    unsigned int* seq_dev = nullptr;        // device {gradient exchange, small all-reduce} sequence numbers (see common.cuh)
 };
 
 namespace {
 // all-reduce (sum, in rank order => bit-identical on every rank) of a small buffer through the peer inboxes
 template <class T>
-__global__ void __launch_bounds__(256) p2p_allreduce_small_kernel(P2PTable tab, T* __restrict__ buf, int n, unsigned seq) {
+__global__ void __launch_bounds__(256) p2p_allreduce_small_kernel(P2PTable tab, T* __restrict__ buf, int n, unsigned int* __restrict__ seq_ptr) {
+    const unsigned seq = *seq_ptr + 1u;   // every thread reads it before the closing barrier, thread 0 stores it back after
     const unsigned slot = seq & 1u;
     constexpr int W = sizeof(T) / 4;   // 32-bit words per element
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -97,6 +98,8 @@ __global__ void __launch_bounds__(256) p2p_allreduce_small_kernel(P2PTable tab, 
         }
         buf[i] = acc;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) *seq_ptr = seq;
 }
 }  // namespace
 
@@ -104,6 +107,7 @@ void b200rl_comm_destroy_internal(b200rl_ctx* ctx) {
     if (ctx->comm) {
         for (void* q : ctx->comm->opened) if (q) cudaIpcCloseMemHandle(q);
         if (ctx->comm->region) cudaFree(ctx->comm->region);
+        if (ctx->comm->seq_dev) cudaFree(ctx->comm->seq_dev);
         if (g_api.CommDestroy && ctx->comm->comm) g_api.CommDestroy(ctx->comm->comm);
         delete ctx->comm;
         ctx->comm = nullptr;
@@ -115,14 +119,13 @@ bool b200rl_comm_p2p_table(b200rl_ctx* ctx, P2PTable* out) {
     *out = ctx->comm->tab;
     return true;
 }
-uint32_t b200rl_comm_p2p_next_gseq(b200rl_ctx* ctx) { return ++ctx->comm->gseq; }
+unsigned int* b200rl_comm_p2p_seq_dev(b200rl_ctx* ctx) { return ctx->comm ? ctx->comm->seq_dev : nullptr; }
 int b200rl_comm_allreduce_internal(b200rl_ctx* ctx, void* buf, int64_t n, int is_double) {
     REQUIRE(ctx->comm, B200RL_ERR_INVALID, "no communicator");
     b200rl_comm_state* c = ctx->comm;
     if (c->tab.nranks > 1 && n * (is_double ? 2 : 1) <= (int64_t)kP2PYCap) {   // small: one kernel over NVLink peer memory
-        unsigned seq = ++c->yseq;
-        if (is_double) p2p_allreduce_small_kernel<double><<<1, 256, 0, ctx->stream>>>(c->tab, (double*)buf, (int)n, seq);
-        else p2p_allreduce_small_kernel<float><<<1, 256, 0, ctx->stream>>>(c->tab, (float*)buf, (int)n, seq);
+        if (is_double) p2p_allreduce_small_kernel<double><<<1, 256, 0, ctx->stream>>>(c->tab, (double*)buf, (int)n, c->seq_dev + 1);
+        else p2p_allreduce_small_kernel<float><<<1, 256, 0, ctx->stream>>>(c->tab, (float*)buf, (int)n, c->seq_dev + 1);
         LAUNCH_CHECK(ctx);
         return B200RL_OK;
     }
@@ -166,6 +169,8 @@ int b200rl_comm_p2p_export(b200rl_ctx* ctx, void* handle64_out, void** region_ou
     if (!c->region) {
         CUDA_TRY(cudaMalloc(&c->region, kP2PRegionBytes));
         CUDA_TRY(cudaMemset(c->region, 0, kP2PRegionBytes));
+        CUDA_TRY(cudaMalloc(&c->seq_dev, 2 * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemset(c->seq_dev, 0, 2 * sizeof(unsigned int)));
         CUDA_TRY(cudaDeviceSynchronize());
     }
     if (handle64_out) {

@@ -45,6 +45,9 @@ struct b200rl_ctx {
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    static constexpr int kTimerSlots = 512;
+    cudaEvent_t slots[kTimerSlots] = {};   // b200rl_timer_record / _elapsed_ms: created on first use
+    int phase_base = -1;                   // >= 0: b200rl_onpolicy_update records its phases into slots[phase_base ...] (eager path only)
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     void* scratch = nullptr;  // general device scratch (grown on demand)
@@ -94,7 +97,9 @@ struct P2PTable {   // nranks == 0: not attached
     unsigned char* base[kP2PMaxRanks];
 };
 bool b200rl_comm_p2p_table(b200rl_ctx* ctx, P2PTable* out);   // false when no peer exchange is attached
-uint32_t b200rl_comm_p2p_next_gseq(b200rl_ctx* ctx);
+// device-resident sequence numbers of the peer exchanges {gradient exchange, small all-reduce}: every exchange kernel reads
+// its counter, uses value + 1 and stores it back when it is done — no host-side state, so a captured CUDA graph can be replayed
+unsigned int* b200rl_comm_p2p_seq_dev(b200rl_ctx* ctx);
 
 #ifdef __CUDACC__
 // packet address: inbox of rank `dst`, area (0 = x, 1 = y), slot, written by rank `src`, word index idx

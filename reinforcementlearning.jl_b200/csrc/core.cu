@@ -78,6 +78,7 @@ void b200rl_destroy(b200rl_ctx* ctx) {
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->slots) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -108,6 +109,31 @@ int b200rl_timer_stop_ms(b200rl_ctx* ctx, float* ms_out) {
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(cudaEventSynchronize(ctx->ev1));
     CUDA_TRY(cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    return B200RL_OK;
+}
+/* event slots: record any number of points on the ctx stream without synchronising, read the intervals afterwards */
+int b200rl_timer_record(b200rl_ctx* ctx, int slot) {
+    TRY(ctx_bind(ctx));
+    REQUIRE(slot >= 0 && slot < b200rl_ctx::kTimerSlots, B200RL_ERR_INVALID, "timer slot out of range");
+    if (!ctx->slots[slot]) CUDA_TRY(cudaEventCreate(&ctx->slots[slot]));
+    CUDA_TRY(cudaEventRecord(ctx->slots[slot], ctx->stream));
+    return B200RL_OK;
+}
+int b200rl_timer_elapsed_ms(b200rl_ctx* ctx, int slot_from, int slot_to, float* ms_out) {
+    TRY(ctx_bind(ctx));
+    REQUIRE(ms_out && slot_from >= 0 && slot_from < b200rl_ctx::kTimerSlots && slot_to >= 0 && slot_to < b200rl_ctx::kTimerSlots,
+            B200RL_ERR_INVALID, "bad argument");
+    REQUIRE(ctx->slots[slot_from] && ctx->slots[slot_to], B200RL_ERR_INVALID, "timer slot never recorded");
+    CUDA_TRY(cudaEventSynchronize(ctx->slots[slot_to]));
+    CUDA_TRY(cudaEventElapsedTime(ms_out, ctx->slots[slot_from], ctx->slots[slot_to]));
+    return B200RL_OK;
+}
+/* measurement aid: base_slot >= 0 makes b200rl_onpolicy_update (eager path) record its phases into the timer slots
+ * base_slot + {0: entry, 1: after GAE / normalisation / packing, 2 + 2i: after loss+backward i, 3 + 2i: after optimiser step i};
+ * -1 switches it off */
+int b200rl_debug_phase_slots(b200rl_ctx* ctx, int base_slot) {
+    REQUIRE(ctx && base_slot >= -1 && base_slot < b200rl_ctx::kTimerSlots - 8, B200RL_ERR_INVALID, "bad argument");
+    ctx->phase_base = base_slot;
     return B200RL_OK;
 }
 int b200rl_malloc(b200rl_ctx* ctx, size_t bytes, void** dptr_out) {

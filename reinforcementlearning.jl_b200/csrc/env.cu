@@ -488,6 +488,7 @@ int b200rl_env_internal_view(b200rl_env* e, envdev::EnvView* out) {
     return B200RL_OK;
 }
 void b200rl_env_internal_add_steps(b200rl_env* e, uint64_t n) { e->steps_launched += n; }
+int b200rl_env_internal_max_timeout(const b200rl_env* e) { return e->a.max_timeout; }
 int64_t b200rl_env_internal_n(const b200rl_env* e) { return e->N; }
 int b200rl_env_internal_kind(const b200rl_env* e) { return e->kind; }
 int b200rl_env_internal_nobs(const b200rl_env* e) { return e->nobs; }

@@ -423,10 +423,15 @@ ac_loss_grad_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ par
             int64_t j = tile * C::TM + tid;
             bool valid = j < b.B;
             int64_t gidx = 0;
-            if (valid) gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index((uint32_t)(b.perm_offset + j), b.perm_n, b.perm_key);
+            if (valid) gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index((uint32_t)(b.perm_offset + j), b.perm_n, ac_perm_key(b));
             float x[kInMax] = {0.f, 0.f, 0.f, 0.f};
+            float4 sc4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
-                if (b.ns == 4) {
+                if (b.rec) {   // packed records: the sample's state and scalars share one 32-byte sector
+                    float4 v4 = b.rec[2 * gidx];
+                    sc4 = b.rec[2 * gidx + 1];
+                    x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[3] = v4.w;
+                } else if (b.ns == 4) {
                     float4 v4 = reinterpret_cast<const float4*>(b.states)[gidx];
                     x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[3] = v4.w;
                 } else {
@@ -436,7 +441,16 @@ ac_loss_grad_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ par
 #pragma unroll
             for (int i = 0; i < kInMax; ++i) sm.X[i * C::LDA + tid] = x[i];
             float a_bits = 0.f, lp = 0.f, adv = 0.f, ret = 0.f;
-            if (valid) {
+            if (valid && b.rec) {
+                if (role == 0) {
+                    a_bits = sc4.x;
+                    lp = sc4.y;
+                    adv = (sc4.z - mean) * inv_std;
+                    if (!hp.normalize_adv) adv = sc4.z;
+                } else {
+                    ret = sc4.w;
+                }
+            } else if (valid) {
                 if (role == 0) {
                     a_bits = reinterpret_cast<const float*>(b.actions)[gidx];  // raw 32-bit payload (int32 or float)
                     lp = b.logp_old ? b.logp_old[gidx] : 0.f;
@@ -729,10 +743,15 @@ __global__ void __launch_bounds__(256) reduce_clip_adam_kernel(const float* __re
                                                               float* __restrict__ beta_t, const float* __restrict__ loss_partial, int n_loss,
                                                               float* __restrict__ loss_out4, float max_norm, float lr, float b1, float b2, float eps,
                                                               float* __restrict__ gnorm_out, double* __restrict__ cta_sumsq,
-                                                              unsigned int* __restrict__ counter, unsigned int target, float* __restrict__ stats_row,
-                                                              P2PTable tab, unsigned int seq) {
+                                                              unsigned int* __restrict__ counter, float* __restrict__ stats_row,
+                                                              P2PTable tab, unsigned int* __restrict__ seq_ptr, unsigned int* __restrict__ tick) {
     __shared__ double red[8];
     __shared__ float s_scale;
+    // The grid barrier counters reset themselves (the last CTA through the second counter zeroes both), the exchange sequence
+    // number and the update tick live in device memory: nothing here depends on host-side launch counts, so the launch can be
+    // captured in a CUDA graph and replayed, and no counter ever wraps.
+    const unsigned int target = gridDim.x;
+    const unsigned int seq = XCHG ? *seq_ptr + 1u : 0u;
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float gk = 0.f;
     if (k < np) {
@@ -797,7 +816,12 @@ __global__ void __launch_bounds__(256) reduce_clip_adam_kernel(const float* __re
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(counter + 1, 1u) + 1u == target) { beta_t[0] = bt1 * b1; beta_t[1] = bt2 * b2; }
+        if (atomicAdd(counter + 1, 1u) + 1u == target) {   // every CTA has left the first barrier and read beta^t / the sequence number
+            beta_t[0] = bt1 * b1; beta_t[1] = bt2 * b2;
+            counter[0] = 0u; counter[1] = 0u;
+            if (XCHG) *seq_ptr = seq;
+            if (tick) *tick += 1u;
+        }
     }
 }
 
@@ -1092,20 +1116,19 @@ int nn_clip_adam(b200rl_ctx* ctx, float* params, float* grad, float* m, float* v
 
 int nn_reduce_clip_adam(b200rl_ctx* ctx, const float* partial, int n_partials, int64_t np, float* params, float* grad, float* m, float* v,
                         float* beta_t, const float* loss_partial, int n_loss, float* loss_out4, float max_grad_norm, float lr, float b1, float b2,
-                        float eps, float* gnorm_out, double* cta_sumsq, unsigned int* counter2, unsigned int* launches, float* stats_row) {
+                        float eps, float* gnorm_out, double* cta_sumsq, unsigned int* counter2, float* stats_row, unsigned int* tick) {
     unsigned grid = grid_for(np, 256);
     REQUIRE((int)grid <= ctx->sm_count, B200RL_ERR_UNSUPPORTED, "fused reduce+Adam needs all CTAs co-resident");
-    *launches += 1;
     P2PTable tab = {};
     if (b200rl_comm_p2p_table(ctx, &tab)) {
         REQUIRE((size_t)np + 4 <= kP2PXCap, B200RL_ERR_UNSUPPORTED, "gradient larger than the peer exchange inbox");
         reduce_clip_adam_kernel<true><<<grid, 256, 0, ctx->stream>>>(partial, n_partials, np, params, grad, m, v, beta_t, loss_partial, n_loss, loss_out4,
-                                                                    max_grad_norm, lr, b1, b2, eps, gnorm_out, cta_sumsq, counter2, *launches * grid,
-                                                                    stats_row, tab, b200rl_comm_p2p_next_gseq(ctx));
+                                                                    max_grad_norm, lr, b1, b2, eps, gnorm_out, cta_sumsq, counter2, stats_row, tab,
+                                                                    b200rl_comm_p2p_seq_dev(ctx), tick);
     } else {
         reduce_clip_adam_kernel<false><<<grid, 256, 0, ctx->stream>>>(partial, n_partials, np, params, grad, m, v, beta_t, loss_partial, n_loss, loss_out4,
-                                                                     max_grad_norm, lr, b1, b2, eps, gnorm_out, cta_sumsq, counter2, *launches * grid,
-                                                                     stats_row, tab, 0u);
+                                                                     max_grad_norm, lr, b1, b2, eps, gnorm_out, cta_sumsq, counter2, stats_row, tab,
+                                                                     nullptr, tick);
     }
     LAUNCH_CHECK(ctx);
     return B200RL_OK;

@@ -33,11 +33,17 @@ struct AcBatch {
     const float* logp_old; const float* adv; const float* ret;
     const int32_t* idx;         // explicit permutation slice, or null ->
     uint32_t perm_n, perm_key, perm_offset;  // ... Feistel permutation of [0, perm_n), slice start
+    const uint32_t* perm_epoch; // device update counter (may be null): the key actually used is perm_key + *perm_epoch * 1000003
+    const float4* rec;          // packed 32-byte rollout records (may be null): rec[2j] = state (zero padded), rec[2j+1] =
+                                // {action bits, logp_old, advantage, return} — one DRAM sector per gathered sample instead of five
     int64_t B;                  // samples in this minibatch (local)
     float inv_B;                // 1 / (global minibatch size)  — gradients are sums * inv_B
     const float* norm2;         // device {mean, inv_std} for advantage normalisation
 };
 
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t ac_perm_key(const AcBatch& b) { return b.perm_key + (b.perm_epoch ? *b.perm_epoch * 1000003u : 0u); }
+#endif
 int nn_grid_ctas(b200rl_ctx* ctx, int H);  // persistent CTAs per role
 int nn_dqn_max_partials(b200rl_ctx* ctx, int H);
 // forward (rollout inference).  obs (in, N) column-major.  Any output may be null.
@@ -55,10 +61,11 @@ int nn_reduce_partials(b200rl_ctx* ctx, const float* partial, int n_partials, in
 int nn_clip_adam(b200rl_ctx* ctx, float* params, float* grad, float* m, float* v, float* beta_t /* device [2] */, int64_t np,
                  float max_grad_norm, float lr, float b1, float b2, float eps, float grad_scale, float* gnorm_out /* device */);
 // fused single-launch variant (single GPU, or a sharded run with the NVLink peer exchange attached; stats_row (may be null)
-// receives {4 loss sums, grad norm}): cta_sumsq >= 148 doubles, counter2 = 2 zero-initialised uints, *launches = host-side launch count
+// receives {4 loss sums, grad norm}): cta_sumsq >= 148 doubles, counter2 = 2 zero-initialised uints (self-resetting grid barrier),
+// tick (may be null) = device counter incremented once by the launch (the agent's update counter that keys the permutation)
 int nn_reduce_clip_adam(b200rl_ctx* ctx, const float* partial, int n_partials, int64_t np, float* params, float* grad, float* m, float* v,
                         float* beta_t, const float* loss_partial, int n_loss, float* loss_out4, float max_grad_norm, float lr, float b1, float b2,
-                        float eps, float* gnorm_out, double* cta_sumsq, unsigned int* counter2, unsigned int* launches, float* stats_row);
+                        float eps, float* gnorm_out, double* cta_sumsq, unsigned int* counter2, float* stats_row, unsigned int* tick);
 int nn_target_sync(b200rl_ctx* ctx, float* target, const float* model, int64_t np, float rho);
 // DQN: TD loss + backward on a gathered batch (device arrays s (in,B), a, r, t, s2, w)
 int nn_dqn_loss_grad(b200rl_ctx* ctx, const MlpDesc& q, const float* params, const float* target, const float* s, const int32_t* a,

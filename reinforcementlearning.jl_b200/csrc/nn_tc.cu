@@ -301,12 +301,21 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     float pf[kInMax];
     bool have_pf = false;
     const int pbits = b200perm::perm_bits(b.perm_n);
+    const uint32_t pkey = ac_perm_key(b);
     auto gather_tile = [&](int64_t t, float (&o)[kInMax]) {
         int64_t j = t * TM + s;
 #pragma unroll
         for (int k = 0; k < kInMax; ++k) o[k] = 0.f;
         if (j >= b.B) return;
-        int64_t gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index_bits((uint32_t)(b.perm_offset + j), b.perm_n, b.perm_key, pbits);
+        if (b.rec) {   // packed records: thread c = 0 takes the state half, c = 1 the scalar half of the sample's 32-byte sector
+            if (c >= 2) return;
+            int64_t gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index_bits((uint32_t)(b.perm_offset + j), b.perm_n, pkey, pbits);
+            K7_T(17);
+            float4 v4 = b.rec[2 * gidx + c];
+            o[0] = v4.x; o[1] = v4.y; o[2] = v4.z; o[3] = v4.w;
+            return;
+        }
+        int64_t gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index_bits((uint32_t)(b.perm_offset + j), b.perm_n, pkey, pbits);
         K7_T(17);
         if (c == 0) {
             if (b.ns == 4) {
@@ -337,6 +346,13 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         if (c == 0) {
 #pragma unroll
             for (int i = 0; i < kInMax; ++i) sm.X[i * TM + s] = pf[i];
+        } else if (b.rec) {
+            if (c == 1) {   // {action bits, logp_old, advantage, return}; the role that does not use a value stores 0 like the SoA path
+                sm.Aux[s] = pf[0];
+                sm.Aux[TM + s] = role == 0 ? pf[1] : 0.f;
+                sm.Aux[2 * TM + s] = role == 0 ? (hp.normalize_adv ? (pf[2] - mean) * inv_std : pf[2]) : 0.f;
+                sm.Aux[3 * TM + s] = role == 0 ? 0.f : pf[3];
+            }
         } else if (c == 1) {
             sm.Aux[s] = pf[0];
         } else if (c == 2) {

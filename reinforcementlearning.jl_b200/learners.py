@@ -209,6 +209,21 @@ class OnPolicyAgent(AbstractPolicy):
         self.last_stats = stats
         return stats
 
+    def iterate(self, n_iters=1, want_stats=False):
+        """n_iters x {collect(T); update()} as one CUDA-graph launch per iteration (b200rl_onpolicy_iterate)."""
+        rows = self.cfg.n_epochs * self.cfg.n_microbatches
+        stats = np.zeros((rows, 6), np.float32) if want_stats else None
+        L.check(self.lib.b200rl_onpolicy_iterate(self.h, n_iters, L.ptr(stats)))
+        self._t = 0
+        self.n_updates += n_iters
+        self.last_stats = stats
+        return stats
+
+    def graph_active(self):
+        v = C.c_int()
+        L.check(self.lib.b200rl_onpolicy_graph_active(self.h, C.byref(v)))
+        return bool(v.value)
+
     def rollout(self, field):
         n, T, ns = self.n, self.T, self.net.n_in
         spec = {

@@ -69,3 +69,30 @@ def test_fused_rollout_is_bit_identical_to_the_stage_protocol(pkg, ctx, kind, en
     assert abs(a["ep"]["return_sum"] - b["ep"]["return_sum"]) <= 1e-6 * max(1.0, abs(b["ep"]["return_sum"]))
     if kind in ("CartPole", "ContinuousCartPole"):
         assert a["ep"]["episodes"] > 0
+
+
+@pytest.mark.parametrize("kind,envkw,algo,n", [("CartPole", {}, "ppo", 1000), ("Pendulum", dict(continuous=True), "a2c", 700)])
+def test_graph_replayed_iterations_are_bit_identical_to_eager_ones(pkg, ctx, kind, envkw, algo, n):
+    """b200rl_onpolicy_iterate: the first iteration runs eagerly, the second is captured, the rest are graph replays — the update
+    counter that keys the minibatch permutation, the grid barrier of the optimiser kernel and the Adam beta^t all live in device
+    memory, so five replayed iterations must equal five collect() + update() pairs bit for bit."""
+    T, iters = 8, 5
+    R = pkg.learners
+    outs = []
+    for graph in (True, False):
+        env, net, agent = _make(pkg, ctx, kind, n, T, 11, algo, **envkw)
+        if graph:
+            agent.iterate(2)
+            stats = agent.iterate(iters - 2, want_stats=True)
+            assert agent.graph_active()
+        else:
+            for _ in range(iters):
+                agent.collect(T)
+                stats = agent.update(want_stats=True)
+        outs.append(dict(params=net.get(), m=net.get(R.NET_M), v=net.get(R.NET_V), bt=net.get(R.NET_BETA_T), state=env.internal_state(), erng=env.rng_state(),
+                         prng=agent.rollout(R.ROLL_RNG), adv=agent.rollout(R.ROLL_ADV), stats=stats, ep=env.episode_stats(), launches=ctx.launch_count()))
+        agent.close(); net.close(); env.close()
+    a, b = outs
+    for k in ("params", "m", "v", "bt", "state", "erng", "prng", "adv", "stats"):
+        assert np.asarray(a[k]).tobytes(order="A") == np.asarray(b[k]).tobytes(order="A"), k
+    assert a["ep"]["env_steps"] == b["ep"]["env_steps"] == iters * T * n and a["ep"]["episodes"] == b["ep"]["episodes"]
