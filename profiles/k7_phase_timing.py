@@ -46,8 +46,8 @@ def run():
     b.run(agent, env, b.StopAfterNSteps(64), b.DeviceEpisodeStats())     # two full PPO iterations (warm-up)
     out = (C.c_ulonglong * 24)()
     lib.b200rl_debug_k7_phases.argtypes = [C.c_void_p, C.c_int]
-    # thread 0 issues GEMM2, 160 GEMM1, 320 GEMM3 (nn_tc.cu kIssueG*); 32 * 7 = lane 0 of a warp that issues nothing
-    watch = [int(a) for a in sys.argv[1:] if a.isdigit()] or [0, 160, 320, 224]
+    # all MMAs are issued by the dedicated warp 16 (nn_tc.cu); the watched threads are plain workers: 0 / 224 gather (c < 2), 256 does not (c = 2)
+    watch = [int(a) for a in sys.argv[1:] if a.isdigit()] or [0, 224, 256]
     cols = {}
     for w in watch:
         assert lib.b200rl_debug_k7_watch(w) == 0

@@ -140,6 +140,9 @@ __device__ __forceinline__ float lane_transpose_reduce32(float (&v)[32], int lan
 
 // worker-only barrier (the MMA warp never joins it)
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// operand hand-over to the issuer warp: 512 worker threads arrive without waiting, the 32 issuer threads wait
+__device__ __forceinline__ void ready_arrive(int id) { asm volatile("bar.arrive %0, 544;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void ready_wait(int id) { asm volatile("bar.sync %0, 544;" ::"r"(id) : "memory"); }
 // per-sample loss and d(loss)/d(head outputs); identical arithmetic on every thread that evaluates a sample
 struct LossOut { float dz[kOutMax]; float l0, l1; };
 __device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, const AcHyper& hp, float inv_B, const float (&z)[kOutMax],
@@ -230,7 +233,12 @@ __device__ int g_k7_watch = 0;   // thread of CTA 0 whose timeline is recorded (
 #else
 #define K7_T(i) do { } while (0)
 #endif
-constexpr int NT7_ALL = NT7;        // 16 warps; warp 0 lane 0 also feeds the tensor core (descriptors prebuilt: ~2 instructions per MMA)
+// 16 worker warps + one warpgroup (warps 16..19) whose first warp feeds the tensor core.  Issuing a tcgen05.mma costs its
+// thread ~60 cycles and blocks it once the MMA queue is full (~1.1 k cycles for a 16-instruction GEMM), which used to stall
+// a worker warp — and with it everybody at the next CTA barrier.  The register file is per scheduler (16 K registers, 5 warps
+// each now), so the issuer warpgroup gives its registers back (setmaxnreg.dec 24) and the workers take 120 (setmaxnreg.inc).
+constexpr int NT7_ALL = NT7 + 128;
+constexpr int kBarRdyA = 2, kBarRdyB = 3;   // named barriers: workers arrive (bar.arrive), the issuer warp waits (bar.sync)
 
 __global__ void __launch_bounds__(NT7_ALL, 1)
 ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, AcBatch b, float* __restrict__ partial,
@@ -277,8 +285,62 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     const uint32_t idesc = umma::make_idesc_tf32(128, 64, 0, 0), idesc128 = umma::make_idesc_tf32(128, 128, 0, 0);
     const int64_t ntiles = (b.B + TM - 1) / TM;
 
-    {
+    const uint64_t dB1f = umma::make_desc(umma::smem_u32(sm.B1_full), G_F, GW_S);
+    const uint64_t dB2f = umma::make_desc(umma::smem_u32(sm.B2_full), G_F, GW_S);
+    const uint64_t dFPf = umma::make_desc(umma::smem_u32(sm.FP_full), GF_T, GS_T);
+    const uint64_t dFHf = umma::make_desc(umma::smem_u32(sm.FH_full), GF_T, GS_T);
+    if (warp >= NT7 / 32) {
+        // ================= issuer warpgroup: warp 16 feeds the tensor core, warps 17..19 only return their registers ====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (warp == NT7 / 32) {
+            // 3xTF32 product of a TMEM A operand (full at a_col, lo at a_col + 64) with a [B_full | B_lo] weight image:
+            // MMA 1 (N = 128): D[0:64) = full*full, D[64:128) = full*lo;  MMA 2 (N = 64): D[0:64) += lo*full
+            auto issue_ts3 = [&](uint32_t d_col, uint32_t a_col, uint64_t dB) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
+                    umma::mma_tf32_ts(tmem + d_col, tmem + a_col + 8 * k, dB + adv, idesc128, k ? 1u : 0u);
+                    umma::mma_tf32_ts(tmem + d_col, tmem + a_col + 64 + 8 * k, dB + adv, idesc, 1u);
+                }
+            };
+            // GEMM3 (dW2 += dP2^T x H1, K = 128 samples), ONE M = 128 x N = 128 MMA per k-step: FP_full|FP_lo are adjacent row
+            // groups (A rows 0..63 = full, 64..127 = lo) and FH_full|FH_lo adjacent column groups, so D3[0:64][0:64] = full*full,
+            // D3[0:64][64:128] = full*lo, D3[64:128][0:64] = lo*full (and lo*lo, unused).
+            uint32_t d3_acc = 0u;
+            auto issue_g3 = [&]() {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
+                    umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc128, d3_acc);
+                    d3_acc = 1u;
+                }
+            };
+            // One thread issues every MMA, so the tensor pipe executes them in program order: G2(t) reads R1 before G1(t+1)
+            // overwrites it without any cross-thread fence.  Per tile: G2(t) | G1(t+1) | G3(t).
+            if (cta < ntiles) {
+                ready_wait(kBarRdyB);                      // H1 operand of the first tile is in TMEM
+                umma::fence_after_sync();
+                if (lane == 0) { issue_ts3(COL_R1, COL_AH, dB1f); umma::commit(&sm.bar1); }
+                __syncwarp();
+            }
+            for (int64_t tile = cta; tile < ntiles; tile += nctas) {
+                ready_wait(kBarRdyA);                      // dP2 operand (TMEM) and the dP2^T / H1^T images (smem) of this tile
+                umma::fence_after_sync();
+                if (lane == 0) { issue_ts3(COL_D2, COL_R1, dB2f); umma::commit(&sm.bar2); }      // GEMM2: dH1 = dP2 x W2
+                __syncwarp();
+                if (tile + nctas < ntiles) {
+                    ready_wait(kBarRdyB);                  // H1 operand of the next tile
+                    umma::fence_after_sync();
+                    if (lane == 0) { issue_ts3(COL_R1, COL_AH, dB1f); umma::commit(&sm.bar1); }  // GEMM1 of the next tile
+                    __syncwarp();
+                }
+                if (lane == 0) { issue_g3(); umma::commit(&sm.bar3); }                           // GEMM3 of this tile
+                __syncwarp();
+            }
+        }
+    } else {
     // ================= 16 worker warps =======================================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     // persistent per-thread gradient partials (over this thread's sample slot), reduced once at the end
     float g3[2][16];                  // dW3[o][16c + k]
@@ -335,12 +397,11 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         }
     };
     bool gemm3_pending = false;
-    uint32_t d3_acc = 0u;   // meaningful on the issuing lane only
     // ---- software pipeline (one tile = 128 samples; tensor core and CUDA cores work on different tiles / phases) ----
     //   CUDA cores : ... P3(t) P45(t) | P0(t+1) P1(t+1) | P7(t) | P3(t+1) ...
-    //   tensor core:              G2(t) .......... G1(t+1) G3(t) ..........
-    // G1(t+1) is queued before the CUDA cores start P7(t), so its ~2k cycles hide behind P7; G3(t) hides behind
-    // P3/P45(t+1); only part of G2(t) (behind P0/P1(t+1)) is ever waited for.
+    //   tensor core:              G2(t) ......... G1(t+1) .... G3(t) .....
+    // G2(t) runs under P0/P1(t+1), G1(t+1) under P7(t), G3(t) under P3/P45(t+1); the issuer warp queues each GEMM as soon
+    // as the workers have handed its operands over (ready_arrive), so no worker ever blocks on the MMA queue.
     auto publish = [&](int64_t t) {   // P0: this tile's gathered samples -> shared memory, prefetch the following tile
         if (!have_pf) gather_tile(t, pf);
         if (c == 0) {
@@ -389,49 +450,13 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         umma::tmem_st16(tmem + lane_base + COL_AH + 64 + 16 * c, lo);
         umma::tmem_st_wait();
     };
-    const uint64_t dB1f = umma::make_desc(umma::smem_u32(sm.B1_full), G_F, GW_S);
-    const uint64_t dB2f = umma::make_desc(umma::smem_u32(sm.B2_full), G_F, GW_S);
-    const uint64_t dFPf = umma::make_desc(umma::smem_u32(sm.FP_full), GF_T, GS_T);
-    const uint64_t dFHf = umma::make_desc(umma::smem_u32(sm.FH_full), GF_T, GS_T);
-    // 3xTF32 product of a TMEM A operand (full at a_col, lo at a_col + 64) with a [B_full | B_lo] weight image:
-    // MMA 1 (N = 128): D[0:64) = full*full, D[64:128) = full*lo;  MMA 2 (N = 64): D[0:64) += lo*full
-    auto issue_ts3 = [&](uint32_t d_col, uint32_t a_col, uint64_t dB) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-            umma::mma_tf32_ts(tmem + d_col, tmem + a_col + 8 * k, dB + adv, idesc128, k ? 1u : 0u);
-            umma::mma_tf32_ts(tmem + d_col, tmem + a_col + 64 + 8 * k, dB + adv, idesc, 1u);
-        }
-    };
-    // GEMM3 (dW2 += dP2^T x H1, K = 128 samples), ONE M = 128 x N = 128 MMA per k-step: FP_full|FP_lo are adjacent row
-    // groups (A rows 0..63 = full, 64..127 = lo) and FH_full|FH_lo adjacent column groups, so D3[0:64][0:64] = full*full,
-    // D3[0:64][64:128] = full*lo, D3[64:128][0:64] = lo*full (and lo*lo, unused).
-    auto issue_g3 = [&]() {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
-            umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc128, d3_acc);
-            d3_acc = 1u;
-        }
-    };
-    // Issuing a tcgen05.mma costs the issuing thread ~60 cycles (more once the queue is full), so the three GEMMs are fed by
-    // lane 0 of three different warps: no single warp falls ~3k cycles behind the others at the next barrier.  Cross-thread
-    // order (GEMM2(t) reads R1 before GEMM1(t+1) overwrites it) comes from tcgen05 fences around the CTA barriers between them.
-    constexpr int kIssueG2 = 0, kIssueG1 = 5 * 32, kIssueG3 = 10 * 32;
-    bool g3_ready = false;   // FP / FH images of the previous tile are complete and its GEMM3 has not been issued yet
     float x[kInMax];
-    if (cta < ntiles) {   // prologue: P0 / P1 / G1 of the first tile
+    if (cta < ntiles) {   // prologue: P0 / P1 of the first tile (the issuer queues its G1)
         publish(cta);
         worker_sync();
         layer1(x);
         umma::fence_before_sync();
-        worker_sync();
-        if (tid == kIssueG1) {
-            umma::fence_after_sync();
-            issue_ts3(COL_R1, COL_AH, dB1f);
-            umma::commit(&sm.bar1);
-        }
-        __syncwarp();
+        ready_arrive(kBarRdyB);
     }
 #ifdef B200RL_K7_TIMING
     tprev_ = clock64();
@@ -443,12 +468,6 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         ph1 ^= 1u;
         umma::fence_after_sync();
         K7_T(0);
-        if (g3_ready) {   // GEMM3 of the previous tile: the tensor core is idle from here until this tile's GEMM2
-            if (tid == kIssueG3) { issue_g3(); umma::commit(&sm.bar3); }
-            __syncwarp();
-            g3_ready = false;
-            gemm3_pending = true;
-        }
         float h2[16];
         {
             float v[16], v2[16];
@@ -522,39 +541,22 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         K7_T(5);
         umma::fence_proxy_async();
         umma::fence_before_sync();
-        worker_sync();
+        ready_arrive(kBarRdyA);     // this thread's share of the GEMM2 / GEMM3 operands is in place
+        gemm3_pending = true;
+        worker_sync();              // Aux / Zp / X are free for the next tile
         K7_T(6);
-        if (tid == kIssueG2) {
-            umma::fence_after_sync();
-            issue_ts3(COL_D2, COL_R1, dB2f);     // GEMM2: dH1 = dP2 x W2
-            umma::commit(&sm.bar2);
-        }
-        if (!has_next && tid == kIssueG3) {
-            umma::fence_after_sync();
-            issue_g3();
-            umma::commit(&sm.bar3);
-        }
-        __syncwarp();
-        if (has_next) g3_ready = true; else gemm3_pending = true;
         K7_T(7);
         float xn[kInMax];
         if (has_next) {
             publish(tile + nctas);
             K7_T(8);
-            umma::fence_before_sync();   // orders this thread's GEMM2 issue before GEMM1(next), issued by another thread after two barriers
             worker_sync();
             K7_T(9);
             layer1(xn);
             umma::fence_before_sync();
             K7_T(10);
-            worker_sync();
+            ready_arrive(kBarRdyB);
             K7_T(11);
-            if (tid == kIssueG1) {
-                umma::fence_after_sync();
-                issue_ts3(COL_R1, COL_AH, dB1f);   // GEMM1 of the next tile (ordered behind GEMM2, which reads R1)
-                umma::commit(&sm.bar1);
-            }
-            __syncwarp();
         }
         K7_T(12);
         // ---- P7: dP1 = D2 .* act'(H1); dW1 / db1 partials ------------------------------------------------
