@@ -333,12 +333,6 @@ int b200rl_dqn_last_td(b200rl_net* net, b200rl_traj* traj, float* host_dst, int6
 
 /* select the tcgen05 tensor-core kernels (default, H = 64) or the FP32 CUDA-core kernels for the dense layers */
 int b200rl_set_tensor_cores(int enable);
-/* diagnostic: run tcgen05.mma kind::tf32 on host-supplied shared-memory operand images and dump
- * TMEM (pins the operand-layout conventions of the tensor-core path; tests/test_umma_gpu.py).
- * desc8 = {a_lbo, a_sbo, b_lbo, b_sbo, a_kadvance, b_kadvance, idesc, ksteps}; d_out (128, ncols) row-major */
-int b200rl_selftest_umma(b200rl_ctx* ctx, const void* a_img_host, uint32_t a_bytes, const void* b_img_host, uint32_t b_bytes,
-                         const uint32_t* desc8, int ncols, float* d_out_host);
-
 /* ---------------------------------------------------------------- multi-GPU -------- */
 /* env-index data parallelism: one process per GPU, one sum all-reduce of the flat gradient per
  * optimiser step over NCCL / NVLink.  rank 0 makes the 128-byte id. */

@@ -98,9 +98,11 @@ template <class E, class T, class ActT> struct VecEnv : VecEnvBase {
             case F_FLAGS: for (int64_t i = 0; i < N; ++i) ((uint8_t*)dst)[i] = flags[i]; break;
             case F_T: for (int64_t i = 0; i < N; ++i) ((int32_t*)dst)[i] = (int32_t)envs[i]->t; break;
             case F_RNG: for (int64_t i = 0; i < N; ++i) { const jl::Xoshiro& g = envs[i]->rng; uint64_t* d = (uint64_t*)dst + 4 * i; d[0] = g.s0; d[1] = g.s1; d[2] = g.s2; d[3] = g.s3; } break;
+            case F_ACTION: for (int64_t i = 0; i < N; ++i) action_out(*envs[i], dst, i); break;   // env.action (reset! redraws it: CartPoleEnv.jl:101)
             default: break;
         }
     }
+    static void action_out(const E& e, void* dst, int64_t i);
     void set(int field, const void* src) override {
         int64_t N = size();
         switch (field) {
@@ -121,6 +123,13 @@ using VecMountainCar = VecEnv<MountainCar, float, int32_t>;
 using VecCartPoleC = VecEnv<CartPole<float, true>, float, float>;   // CartPoleEnv(continuous = true)
 using VecMountainCarC = VecEnv<MountainCar, float, float>;          // ContinuousMountainCarEnv
 
+template <> inline void VecCartPoleF32::action_out(const CartPole<float>& e, void* d, int64_t i) { ((int32_t*)d)[i] = (int32_t)e.action; }
+template <> inline void VecCartPoleF64::action_out(const CartPole<double>& e, void* d, int64_t i) { ((int32_t*)d)[i] = (int32_t)e.action; }
+template <> inline void VecMountainCar::action_out(const MountainCar& e, void* d, int64_t i) { ((int32_t*)d)[i] = (int32_t)e.action; }
+template <> inline void VecPendulumC::action_out(const Pendulum& e, void* d, int64_t i) { ((float*)d)[i] = (float)e.action; }
+template <> inline void VecPendulumD::action_out(const Pendulum& e, void* d, int64_t i) { ((float*)d)[i] = (float)e.action; }
+template <> inline void VecCartPoleC::action_out(const CartPole<float, true>& e, void* d, int64_t i) { ((float*)d)[i] = (float)e.action_f; }
+template <> inline void VecMountainCarC::action_out(const MountainCar& e, void* d, int64_t i) { ((float*)d)[i] = (float)e.action_f; }
 template <> inline bool VecCartPoleF32::do_act(CartPole<float>& e, int32_t a) { return e.act(a); }
 template <> inline bool VecCartPoleF64::do_act(CartPole<double>& e, int32_t a) { return e.act(a); }
 template <> inline bool VecPendulumC::do_act(Pendulum& e, float a) { return e.act_continuous((double)a); }

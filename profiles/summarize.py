@@ -28,7 +28,7 @@ def raw(rep):
 lines = ["# ncu summaries (%s)" % TAG, "", "Captured with `profiles/run_profiles.sh` under gpurun on one B200 (`--set full --clock-control none`);",
          "per-launch times are cold-cache / serialised — compare shares, not absolutes.", ""]
 traffic = {}
-for name in ("prof_loss", "prof_rollout", "prof_fwd", "prof_adam", "prof_env", "prof_gae"):
+for name in ("prof_loss", "prof_rollout", "prof_fwd", "prof_adam", "prof_env", "prof_gae", "prof_pack", "prof_gather", "prof_dqn"):
     rep = os.path.join(OUT, name + ".ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -47,16 +47,18 @@ for name in ("prof_loss", "prof_rollout", "prof_fwd", "prof_adam", "prof_env", "
             t = float(rec["dram__bytes_read.sum"].replace(",", "")) + float(rec["dram__bytes_write.sum"].replace(",", ""))
             u = ui.get("dram__bytes_read.sum", "byte")
             mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-            mk = re.search(r"(ac_loss_grad_tc_kernel|ac_loss_grad_kernel|rollout_tc_kernel|forward_tc_kernel|forward_kernel|reduce_clip_adam_kernel|env_step_kernel|scan_series_fastest|dqn_loss_grad_kernel)", kn)
+            mk = re.search(r"(ac_loss_grad_tc_kernel|ac_loss_grad_kernel|rollout_tc_kernel|forward_tc_kernel|forward_kernel|reduce_clip_adam_kernel|env_step_kernel|scan_series_fastest|dqn_loss_grad_kernel|pack_records_kernel|sample_gather_kernel)", kn)
             traffic[mk.group(1) if mk else kn] = t * mult
             lines.append("| dram traffic (read+write) | %.3f | MB |" % (t * mult / 1e6))
         except Exception as e:
             pass
         lines.append("")
         break  # first captured launch is enough
-# launch list
-lp = os.path.join(OUT, "launches.csv")
-if os.path.exists(lp):
+# launch lists
+for fname, title in (("launches.csv", "python bench.py --steps 2 --warmup 1 (eager launches)"), ("launches_c5.csv", "python bench.py --config c5 (DQN update loop)")):
+    lp = os.path.join(OUT, fname)
+    if not os.path.exists(lp):
+        continue
     rows = list(csv.reader(open(lp, errors="replace")))
     hdr = None; data = []
     for r in rows:
@@ -71,7 +73,7 @@ if os.path.exists(lp):
         v *= {"ns": 1, "nsecond": 1, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6}.get(u, 1)
         tot[nm] += v; cnt[nm] += 1
     T = sum(tot.values())
-    lines += ["## launch list (`ncu --metrics gpu__time_duration.sum`, python bench.py --steps 2 --warmup 1)", "",
+    lines += ["## launch list (`ncu --metrics gpu__time_duration.sum`, %s)" % title, "",
               "| kernel | launches | total ms | avg us | share |", "|---|---|---|---|---|"]
     for k, v in sorted(tot.items(), key=lambda x: -x[1]):
         lines.append("| %s | %d | %.3f | %.2f | %.1f%% |" % (k, cnt[k], v / 1e6, v / cnt[k] / 1e3, 100 * v / T))

@@ -23,7 +23,7 @@ def idesc(M, N, a_mn, b_mn):
 def run(a_img, b_img, desc8, ncols=64):
     out = np.zeros((128, ncols), np.float32)
     d8 = np.array(desc8, np.uint32)
-    b._lib.check(ctx.lib.b200rl_selftest_umma(ctx.h, a_img.ctypes.data_as(C.c_void_p), a_img.nbytes, b_img.ctypes.data_as(C.c_void_p), b_img.nbytes,
+    b._lib.check(__import__("_selftest").load().b200rl_selftest_umma(ctx.h, a_img.ctypes.data_as(C.c_void_p), a_img.nbytes, b_img.ctypes.data_as(C.c_void_p), b_img.nbytes,
                                               d8.ctypes.data_as(C.c_void_p), ncols, out.ctypes.data_as(C.c_void_p)))
     return out
 

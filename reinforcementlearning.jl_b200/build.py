@@ -23,7 +23,9 @@ SOURCES = [
     ("comm.cu", []),
 ]
 ENV_FLAGS = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
-OPTIONAL = [("traj.cu", []), ("nn.cu", []), ("algo.cu", []), ("umma_selftest.cu", []), ("nn_tc.cu", []), ("fwd_tc.cu", ENV_FLAGS)]
+OPTIONAL = [("traj.cu", []), ("nn.cu", []), ("algo.cu", []), ("nn_tc.cu", []), ("fwd_tc.cu", ENV_FLAGS)]
+# diagnostic probe of the tcgen05 operand layouts (profiles/umma_probe*.py): its own library, NOT part of the product .so
+SELFTEST_OUT = os.path.join(BUILD, "libb200rl_selftest.so")
 
 
 def _nvcc():
@@ -75,5 +77,20 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_selftest():
+    """build/libb200rl_selftest.so: csrc/umma_selftest.cu linked against the product library (it borrows the ctx / scratch helpers)."""
+    so = build()
+    nvcc = _nvcc()
+    host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    obj = os.path.join(BUILD, "umma_selftest.o")
+    subprocess.check_call([nvcc, "-ccbin", host_cxx] + ARCH + COMMON + ["-c", os.path.join(CSRC, "umma_selftest.cu"), "-o", obj])
+    subprocess.check_call([nvcc, "-ccbin", host_cxx] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", SELFTEST_OUT, obj, "-L" + HERE, "-lb200rl",
+                           "-Xlinker", "-rpath=" + HERE])
+    return SELFTEST_OUT
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--selftest" in sys.argv:
+        print(build_selftest())
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,13 +1,16 @@
 // nn_tc.cu — K7 on tensor cores (tcgen05 / TMEM): PPO / A2C loss + backward for H = 64.
 //
-// The 64 x 64 layers are [128 samples x 64] x [64 x 64] GEMMs per tile: elected threads issue tcgen05.mma kind::tf32
-// (SWIZZLE_NONE canonical layout, see umma.cuh) with the FP32 accumulators in TMEM; the worker warps pull them back
-// with tcgen05.ld.  Parity needs ~FP32 accuracy (1e-5 relative on losses), which plain TF32 (10-bit mantissa, measured
-// 7.8e-4 relative on this GEMM) cannot give, so every product is the 3xTF32 split
-//     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi,   x_hi = x with the low 13 mantissa bits cleared
-// (the hardware ignores those bits, so the FULL fp32 image doubles as the hi operand) — measured 5e-7 relative
-// (profiles/umma_probe.py).  Layer 1 (K <= 4) and the heads (N <= 4) stay on FFMA.  The forward-only kernels (policy
-// inference, fused rollout) live in fwd_tc.cu.
+// The 64 x 64 layers are [128 samples x 64] x [64 x 64] GEMMs per tile: one warp issues tcgen05.mma (SWIZZLE_NONE canonical
+// layout, see umma.cuh) with the FP32 accumulators in TMEM; the worker warps pull them back with tcgen05.ld.  Parity needs
+// ~FP32 accuracy (1e-5 relative on losses), which no single tensor-core input format gives, so every product is a 3-term split
+//     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi,   x_hi = fp16(x * S), x_lo = fp16(x * S - x_hi)      (22 mantissa bits)
+// with a power-of-two scale S per operand (exact; undone on the FP32 accumulator), accumulated in FP32.  Round 1 used the same
+// split on kind::tf32 (K = 8 per instruction).  A tcgen05.mma of these shapes occupies the pipe for ~155-175 cycles whatever
+// its N (<= 128) or kind (profiles/umma_probe_f16.py), so the pipe is paced by the instruction COUNT: kind::f16 covers K = 16
+// per instruction and halves it (48 -> 24 per tile) at the same 2^-22 product accuracy.  fp16 has 5 exponent bits: activations
+// must stay below 65504 in magnitude (scale 1), weights below 1023 (scale 64); gradients are scaled by ~1/(4 inv_B) at launch.
+// Below 6e-5 the lo part is subnormal: absolute error <= 2^-25 per element, far inside the 1e-5 bar.  Layer 1 (K <= 4) and the
+// heads (N <= 4) stay on FFMA.  The forward-only kernels (policy inference, fused rollout) live in fwd_tc.cu (3xTF32).
 #include "nn.cuh"
 #include "perm.cuh"
 #include "umma.cuh"
@@ -17,13 +20,22 @@ namespace {
 constexpr int NT = 256;
 constexpr int TM = 128;              // samples per tile = UMMA M
 constexpr int H = 64;
-constexpr int G_F = 128;             // byte stride between 4-feature chunks (K direction)
-constexpr int GW_S = 16 * G_F;       // weight image: stride between 8-row groups
-constexpr int WIMG_BYTES = 8 * GW_S; // one [64 x 64] weight image
+constexpr int G_F = 128;             // weight image (fp16, K-major): byte stride between 8-element K chunks = one 8 x 16 B core matrix
+constexpr int GW_S = 8 * G_F;        // stride between 8-row groups (64 K elements = 8 chunks)
+constexpr int WIMG_BYTES = 16 * GW_S; // one [hi (64 rows) ; lo (64 rows)] x [K = 64] fp16 weight image = 16 KB
+constexpr float kScaleW = 64.0f;     // power-of-two operand scales (see the header comment)
 constexpr float kLog2Pi = 1.8378770664093453f;
 
 __device__ __forceinline__ float act_f(int act, float z) { return act == B200RL_ACT_RELU ? fmaxf(z, 0.f) : tanhf(z); }
-__device__ __forceinline__ float hi_part(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// two fp32 values -> packed fp16 pair {lo half = a, hi half = b}: the hi parts, and the fp16 of what they miss (the lo parts)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ float half_bits_to_float(uint32_t bits16) { return __half2float(__ushort_as_half((unsigned short)bits16)); }
 __device__ __forceinline__ float softplus_f(float x) { return x > 0.f ? x + log1pf(expf(-x)) : log1pf(expf(x)); }
 __device__ __forceinline__ float normlogpdf1(float mu, float sigma, float x) {
     float s = sigma + 1e-8f, v = s * s, dd = x - mu;
@@ -36,7 +48,7 @@ __device__ __forceinline__ int64_t head_w(const MlpDesc& d, int o, int j) {
 __device__ __forceinline__ int64_t head_b(const MlpDesc& d, int o) {
     return head_base(d) + (d.heads2 ? (int64_t)o * (d.H + 1) + d.H : (int64_t)d.nout * d.H + o);
 }
-__device__ __forceinline__ uint32_t wimg_off(int n, int k) { return (uint32_t)((n >> 3) * GW_S + (k >> 2) * G_F + (n & 7) * 16 + (k & 3) * 4); }
+__device__ __forceinline__ uint32_t wimg_off(int n, int k) { return (uint32_t)((n >> 3) * GW_S + (k >> 3) * G_F + (n & 7) * 16 + (k & 7) * 2); }
 
 // =====================================================================================================
 // K7 on tensor cores: PPO / A2C loss + backward for one minibatch, all three 64x64 GEMMs on tcgen05.
@@ -44,30 +56,38 @@ __device__ __forceinline__ uint32_t wimg_off(int n, int k) { return (uint32_t)((
 //   GEMM2  dH1[s][i]   = sum_j dP2[s][j] W2[j][i]     A = dP2 (TMEM),                        B = W2^T image (smem)
 //   GEMM3  dW2[j][i]  += sum_s dP2[s][j] H1[s][i]     A = dP2^T, B = H1^T: feature-major K-major images (smem),
 //                                                     accumulated in TMEM across ALL tiles of the CTA, read once.
-// every product 3xTF32 (full*full + full*lo + lo*full; the tensor core ignores the low 13 mantissa bits).
+// every product the 3-term fp16 split (hi*hi + hi*lo + lo*hi), FP32 accumulate.
 // One CTA per SM (512 threads, role = blockIdx & 1), persistent, software-pipelined across tiles (see the loop).
 // Thread <-> data: warp w: TMEM lane quadrant q = w % 4, feature block c = w / 4; thread = sample s = 32q + lane.
 constexpr int NT7 = 512;
-constexpr int GF_T = 144;                 // feature-major image: stride between 4-sample chunks; 144 = 128 + 16 makes the 32 lanes'
-                                          // 4-byte transposed stores hit 32 different banks (with 128 they would 8-way conflict)
-constexpr int GS_T = 32 * GF_T + 16;      // stride between 8-feature row groups
-constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples]
-// tcgen05.mma instructions pace at ~120-140 cycles each whatever their N (<= 192), accumulator or issuing thread (measured,
-// profiles/umma_probe4.py), so the kernel minimises their number: full|lo operands are stacked along N (and M for GEMM3).
-// TMEM columns: R1 = D1 of GEMM1 ([ff+lf | fl]), then (same lanes/columns, after P3 consumed it) the dP2 A operand (full | lo) of GEMM2;
-// D2 = GEMM2 accumulator; D3 = GEMM3 accumulator (all tiles); AH = H1 A operand (full | lo) of GEMM1.
-constexpr uint32_t COL_R1 = 0, COL_D2 = 128, COL_D3 = 256, COL_AH = 384;
+constexpr int GF_T = 144;                 // feature-major fp16 image: stride between 8-sample chunks; 144 = 128 + 16: the 32 lanes of a
+                                          // 2-byte transposed store (4 groups of 8 consecutive samples) hit 4 different bank quads
+constexpr int GS_T = 16 * GF_T + 16;      // stride between 8-feature row groups (128 samples = 16 chunks)
+constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples] fp16 = 18 560 B
+// tcgen05.mma instructions pace at ~155-175 cycles each whatever their N (<= 128) (profiles/umma_probe_f16.py), so the kernel
+// minimises their number: hi|lo operands are stacked along N (and M for GEMM3), K = 16 per instruction.
+// TMEM columns: R1 = D1 of GEMM1 ([hh+lh | hl], 128 columns), then (after P3 consumed it) the dP2 A operand of GEMM2 in its first 64
+// columns (hi: 32 columns of fp16 pairs | lo: 32); D2 = GEMM2 accumulator; D3 = GEMM3 accumulator (all tiles); AH = H1 A operand
+// of GEMM1 (hi 32 | lo 32 columns).
+// D3 has 144 columns: the B operand of GEMM3 carries a constant "ones" row behind H1^T, so column 128 is sum_s dP2 = db2.
+// D4 = GEMM4 accumulator (16 columns): dW1 | db1 = dP1^T x [x | 1], accumulated over all tiles like D3.
+constexpr uint32_t COL_R1 = 0, COL_D2 = 128, COL_D3 = 256, COL_D4 = 400, COL_AH = 448;
+constexpr float kScaleH = 64.0f, kScaleX = 64.0f;   // power-of-two scales of the H1 / observation operands (weights: kScaleW)
 
 struct SmemBwd {
-    static_assert(FIMG % 128 == 0 && WIMG_BYTES % 128 == 0, "full/lo images must be adjacent to form one N = 128 operand");
-    alignas(128) uint8_t FP_full[FIMG];    // dP2^T  (rows = feature j, K = sample)
-    alignas(128) uint8_t FP_lo[FIMG];
-    alignas(128) uint8_t FH_full[FIMG];    // H1^T
+    static_assert(FIMG % 128 == 0 && WIMG_BYTES % 128 == 0 && (2 * GS_T) % 16 == 0, "hi/lo(/ones) images must be adjacent to form one operand");
+    alignas(128) uint8_t FP_full[FIMG];    // dP2^T hi (rows = feature j, K = sample), fp16
+    alignas(128) uint8_t FP_lo[FIMG];      // ... lo: directly behind, so [hi; lo] is one 128-row operand
+    alignas(128) uint8_t FH_full[FIMG];    // H1^T hi
     alignas(128) uint8_t FH_lo[FIMG];
-    alignas(128) uint8_t B1_full[WIMG_BYTES];  // (n = out o, k = in i)  = W2[o + 64 i]
-    alignas(128) uint8_t B1_lo[WIMG_BYTES];
-    alignas(128) uint8_t B2_full[WIMG_BYTES];  // (n = in i,  k = out j) = W2[j + 64 i]
-    alignas(128) uint8_t B2_lo[WIMG_BYTES];
+    alignas(16) uint8_t FH_ones[2 * GS_T]; // 16 more B rows of GEMM3: row 0 = 1.0 for every sample (-> db2), rows 1..15 = 0; written once
+    alignas(128) uint8_t FQ_full[FIMG];    // dP1^T hi | lo: A operand of GEMM4
+    alignas(128) uint8_t FQ_lo[FIMG];
+    alignas(128) uint8_t B1[WIMG_BYTES];   // rows 0..63: hi, 64..127: lo of (n = out o, k = in i)  = 64 W2[o + 64 i]
+    alignas(128) uint8_t B2[WIMG_BYTES];   // (n = in i,  k = out j) = 64 W2[j + 64 i]
+    // B operand of GEMM4, double-buffered by tile parity (written at publish time, read by the GEMM4 of the same tile one
+    // phase later): rows 0..3 = x_i hi, row 4 = 1.0 (-> db1), rows 8..11 = x_i lo, the rest 0;  K = sample
+    alignas(128) uint8_t XT[2][2 * GS_T];
     float W1[kInMax * H];
     float b1[H], b2[H];
     float W3[H * kOutMax];
@@ -80,9 +100,12 @@ struct SmemBwd {
     alignas(8) uint64_t bar1;
     alignas(8) uint64_t bar2;
     alignas(8) uint64_t bar3;
+    alignas(8) uint64_t bar4;
+    float AccW2[64 * 65 + 64];             // FP32 accumulators the flushes add D3 into: dW2[j][i] at j * 65 + i, then db2[j] (all still operand-scaled)
+    float AccD4[64 * 9];                   // ... D4: dW1[f][i] at f * 9 + i, db1[f] at f * 9 + 4
     uint32_t tmem;
 };
-__device__ __forceinline__ uint32_t fimg_off(int f, int s) { return (uint32_t)((f >> 3) * GS_T + (s >> 2) * GF_T + (f & 7) * 16 + (s & 3) * 4); }
+__device__ __forceinline__ uint32_t fimg_off(int f, int s) { return (uint32_t)((f >> 3) * GS_T + (s >> 3) * GF_T + (f & 7) * 16 + (s & 7) * 2); }
 __device__ __forceinline__ float dact_f(int act, float h) { return act == B200RL_ACT_RELU ? (h > 0.f ? 1.f : 0.f) : 1.f - h * h; }
 
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
@@ -103,23 +126,6 @@ __device__ __forceinline__ float block_sum512(float v, float* red) {
     return t;
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
-
-// A from TMEM (AF / AL columns), B from smem images; 3xTF32
-__device__ __forceinline__ void issue_gemm_ts_3x(uint32_t d_tmem, uint32_t a_full, uint32_t a_lo, const uint8_t* b_full, const uint8_t* b_lo,
-                                                 uint32_t idesc) {
-    const uint32_t bf = umma::smem_u32(b_full), bl = umma::smem_u32(b_lo);
-    uint32_t acc = 0u;
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = pass == 2 ? a_lo : a_full;
-        const uint32_t b = pass == 1 ? bl : bf;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            umma::mma_tf32_ts(d_tmem, a + 8 * k, umma::make_desc(b + k * 2 * G_F, G_F, GW_S), idesc, acc);
-            acc = 1u;
-        }
-    }
-}
 
 // sum over the 32 lanes of NV values each (NV a power of two <= 32... here 32): lane L ends with the totals of
 // values 2L*(NV/64).. — for NV = 32: lane L holds the total of value index L in v[0].
@@ -238,15 +244,24 @@ __device__ int g_k7_watch = 0;   // thread of CTA 0 whose timeline is recorded (
 // a worker warp — and with it everybody at the next CTA barrier.  The register file is per scheduler (16 K registers, 5 warps
 // each now), so the issuer warpgroup gives its registers back (setmaxnreg.dec 24) and the workers take 120 (setmaxnreg.inc).
 constexpr int NT7_ALL = NT7 + 128;
-constexpr int kBarRdyA = 2, kBarRdyB = 3;   // named barriers: workers arrive (bar.arrive), the issuer warp waits (bar.sync)
+// The tensor core adds into an FP32 accumulator with truncation: a chain of n accumulating MMAs biases a same-signed sum by
+// ~n * 2^-25 relative (measured: 1e-4 on b1 / W2 gradients after 1 770 adds, profiles/k7_grad_error.py).  The accumulators that live
+// across tiles (D3, D4) are therefore flushed into FP32 shared-memory accumulators (round-to-nearest adds) every kFlushTiles
+// tiles and restarted: chains of 64 adds, bias ~2e-6.
+constexpr int kFlushTiles = 8;
+constexpr int kBarRdyA = 2, kBarRdyB = 3, kBarRdyC = 4;   // named barriers: workers arrive (bar.arrive), the issuer warp waits (bar.sync)
 
 __global__ void __launch_bounds__(NT7_ALL, 1)
 ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, AcBatch b, float* __restrict__ partial,
-                       float* __restrict__ loss_partial, int64_t np_total) {
+                       float* __restrict__ loss_partial, int64_t np_total, float scale_base /* power of two ~ 1 / inv_B */) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SmemBwd& sm = *reinterpret_cast<SmemBwd*>(smem_raw);
     const int role = blockIdx.x & 1;
     const int cta = blockIdx.x >> 1, nctas = gridDim.x >> 1;
+    // Scale of the dP2 / dP1 operands (a power of two): dz / inv_B is O(ratio * A_hat) <= ~10 for the actor and 2 w_critic (R - V) for
+    // the critic (as large as the returns).  x 64 / x 4 keeps the lo parts of typical entries in fp16's normal range and leaves
+    // room up to |dz| / inv_B ~ 1e3 (actor) / 1.6e4 (critic) before a hi part would overflow fp16 (-> inf -> NaN loss: loud, not silent).
+    const float scale_p = scale_base * (role ? 4.0f : 64.0f);
     const MlpDesc d = role ? critic : actor;
     const int64_t poff = role ? actor.nparams() : 0;
     const float* __restrict__ p = params + poff;
@@ -257,73 +272,105 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         const float* b1 = p + (int64_t)H * d.in;
         const float* W2 = b1 + H;
         const float* b2 = W2 + (int64_t)H * H;
-        for (int k = tid; k < kInMax * H; k += NT7) sm.W1[k] = (k / H) < d.in ? p[k] : 0.f;
-        for (int k = tid; k < H; k += NT7) { sm.b1[k] = b1[k]; sm.b2[k] = b2[k]; }
-        for (int k = tid; k < H * kOutMax; k += NT7) {
+        for (int k = tid; k < kInMax * H; k += NT7_ALL) sm.W1[k] = (k / H) < d.in ? p[k] : 0.f;
+        for (int k = tid; k < H; k += NT7_ALL) { sm.b1[k] = b1[k]; sm.b2[k] = b2[k]; }
+        for (int k = tid; k < H * kOutMax; k += NT7_ALL) {
             int j = k / kOutMax, o = k % kOutMax;
             sm.W3[k] = o < d.nout ? p[head_w(d, o, j)] : 0.f;
         }
         if (tid < kOutMax) sm.b3[tid] = tid < d.nout ? p[head_b(d, tid)] : 0.f;
-        for (int k = tid; k < H * H; k += NT7) {
+        for (int k = tid; k < H * H; k += NT7_ALL) {
             int o = k % H, i = k / H;
-            float w = W2[k], wl = w - hi_part(w);
-            *reinterpret_cast<float*>(sm.B1_full + wimg_off(o, i)) = w;
-            *reinterpret_cast<float*>(sm.B1_lo + wimg_off(o, i)) = wl;
-            *reinterpret_cast<float*>(sm.B2_full + wimg_off(i, o)) = w;
-            *reinterpret_cast<float*>(sm.B2_lo + wimg_off(i, o)) = wl;
+            const float w = W2[k] * kScaleW;
+            const __half wh = __float2half_rn(w), wl = __float2half_rn(w - __half2float(wh));
+            *reinterpret_cast<__half*>(sm.B1 + wimg_off(o, i)) = wh;
+            *reinterpret_cast<__half*>(sm.B1 + wimg_off(H + o, i)) = wl;
+            *reinterpret_cast<__half*>(sm.B2 + wimg_off(i, o)) = wh;
+            *reinterpret_cast<__half*>(sm.B2 + wimg_off(H + i, o)) = wl;
+        }
+    }
+    {   // constant operand rows: zero everything, then 1.0 (fp16 0x3C00) in row 0 of FH_ones and row 4 of both XT buffers
+        for (int k = tid; k < 2 * GS_T / 4; k += NT7_ALL) {
+            reinterpret_cast<uint32_t*>(sm.FH_ones)[k] = 0u;
+            reinterpret_cast<uint32_t*>(sm.XT[0])[k] = 0u;
+            reinterpret_cast<uint32_t*>(sm.XT[1])[k] = 0u;
+        }
+        __syncthreads();
+        if (tid < TM) {
+            *reinterpret_cast<uint16_t*>(sm.FH_ones + fimg_off(0, tid)) = 0x3C00u;
+            *reinterpret_cast<uint16_t*>(sm.XT[0] + fimg_off(4, tid)) = 0x3C00u;
+            *reinterpret_cast<uint16_t*>(sm.XT[1] + fimg_off(4, tid)) = 0x3C00u;
         }
     }
     if (warp == 0) umma::tmem_alloc(&sm.tmem, 512);
     if (tid == 32) {
-        umma::mbar_init(&sm.bar1, 1); umma::mbar_init(&sm.bar2, 1); umma::mbar_init(&sm.bar3, 1);
+        umma::mbar_init(&sm.bar1, 1); umma::mbar_init(&sm.bar2, 1); umma::mbar_init(&sm.bar3, 1); umma::mbar_init(&sm.bar4, 1);
     }
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = sm.tmem;
-    const uint32_t idesc = umma::make_idesc_tf32(128, 64, 0, 0), idesc128 = umma::make_idesc_tf32(128, 128, 0, 0);
+    const uint32_t idesc = umma::make_idesc_f16(128, 64, 0, 0), idesc128 = umma::make_idesc_f16(128, 128, 0, 0);
+    const uint32_t idesc144 = umma::make_idesc_f16(128, 144, 0, 0), idesc16 = umma::make_idesc_f16(128, 16, 0, 0);
+    // undo the operand scales (exact powers of two): D1 = H1 W2, D2 = dP2 W2, D3 = dP2^T [H1 | 1], D4 = dP1^T [x | 1]
+    const float inv_s1 = 1.0f / (kScaleH * kScaleW), inv_s2 = 1.0f / (scale_p * kScaleW), inv_s3 = 1.0f / (scale_p * kScaleH), inv_sp = 1.0f / scale_p,
+                inv_s4 = 1.0f / (scale_p * kScaleX);
     const int64_t ntiles = (b.B + TM - 1) / TM;
 
-    const uint64_t dB1f = umma::make_desc(umma::smem_u32(sm.B1_full), G_F, GW_S);
-    const uint64_t dB2f = umma::make_desc(umma::smem_u32(sm.B2_full), G_F, GW_S);
+    const uint64_t dB1f = umma::make_desc(umma::smem_u32(sm.B1), G_F, GW_S);
+    const uint64_t dB2f = umma::make_desc(umma::smem_u32(sm.B2), G_F, GW_S);
     const uint64_t dFPf = umma::make_desc(umma::smem_u32(sm.FP_full), GF_T, GS_T);
     const uint64_t dFHf = umma::make_desc(umma::smem_u32(sm.FH_full), GF_T, GS_T);
+    const uint64_t dFQf = umma::make_desc(umma::smem_u32(sm.FQ_full), GF_T, GS_T);
     if (warp >= NT7 / 32) {
         // ================= issuer warpgroup: warp 16 feeds the tensor core, warps 17..19 only return their registers ====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (warp == NT7 / 32) {
-            // 3xTF32 product of a TMEM A operand (full at a_col, lo at a_col + 64) with a [B_full | B_lo] weight image:
-            // MMA 1 (N = 128): D[0:64) = full*full, D[64:128) = full*lo;  MMA 2 (N = 64): D[0:64) += lo*full
+            // 3-term product of a TMEM A operand (hi fp16 pairs at a_col, lo at a_col + 32; 8 columns per K = 16 step) with a
+            // [B_hi ; B_lo] weight image: MMA 1 (N = 128): D[0:64) = hi*hi, D[64:128) = hi*lo;  MMA 2 (N = 64): D[0:64) += lo*hi
             auto issue_ts3 = [&](uint32_t d_col, uint32_t a_col, uint64_t dB) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 4; ++k) {
                     const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                    umma::mma_tf32_ts(tmem + d_col, tmem + a_col + 8 * k, dB + adv, idesc128, k ? 1u : 0u);
-                    umma::mma_tf32_ts(tmem + d_col, tmem + a_col + 64 + 8 * k, dB + adv, idesc, 1u);
+                    umma::mma_f16_ts(tmem + d_col, tmem + a_col + 8 * k, dB + adv, idesc128, k ? 1u : 0u);
+                    umma::mma_f16_ts(tmem + d_col, tmem + a_col + 32 + 8 * k, dB + adv, idesc, 1u);
                 }
             };
-            // GEMM3 (dW2 += dP2^T x H1, K = 128 samples), ONE M = 128 x N = 128 MMA per k-step: FP_full|FP_lo are adjacent row
-            // groups (A rows 0..63 = full, 64..127 = lo) and FH_full|FH_lo adjacent column groups, so D3[0:64][0:64] = full*full,
-            // D3[0:64][64:128] = full*lo, D3[64:128][0:64] = lo*full (and lo*lo, unused).
+            // GEMM3 (dW2 += dP2^T x H1, K = 128 samples), ONE M = 128 x N = 128 MMA per K = 16 step: FP_full|FP_lo are adjacent row
+            // groups (A rows 0..63 = hi, 64..127 = lo) and FH_full|FH_lo adjacent column groups, so D3[0:64][0:64] = hi*hi,
+            // D3[0:64][64:128] = hi*lo, D3[64:128][0:64] = lo*hi (and lo*lo, unused).
             uint32_t d3_acc = 0u;
             auto issue_g3 = [&]() {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
+                for (int k = 0; k < 8; ++k) {
                     const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
-                    umma::mma_tf32(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc128, d3_acc);
+                    umma::mma_f16(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc144, d3_acc);   // N = 144: [H1^T hi | H1^T lo | ones]
                     d3_acc = 1u;
                 }
             };
+            // GEMM4 (dW1 | db1 += dP1^T x [x | 1], K = 128 samples): A rows 0..63 = hi, 64..127 = lo; B columns 0..7 = [x hi, 1], 8..15 = x lo
+            uint32_t d4_acc = 0u;
+            auto issue_g4 = [&](int buf) {
+                const uint64_t dXT = umma::make_desc(umma::smem_u32(sm.XT[buf]), GF_T, GS_T);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
+                    umma::mma_f16(tmem + COL_D4, dFQf + adt, dXT + adt, idesc16, d4_acc);
+                    d4_acc = 1u;
+                }
+            };
             // One thread issues every MMA, so the tensor pipe executes them in program order: G2(t) reads R1 before G1(t+1)
-            // overwrites it without any cross-thread fence.  Per tile: G2(t) | G1(t+1) | G3(t).
+            // overwrites it without any cross-thread fence.  Per tile: G2(t) | G1(t+1) | G3(t) | G4(t).
             if (cta < ntiles) {
                 ready_wait(kBarRdyB);                      // H1 operand of the first tile is in TMEM
                 umma::fence_after_sync();
                 if (lane == 0) { issue_ts3(COL_R1, COL_AH, dB1f); umma::commit(&sm.bar1); }
                 __syncwarp();
             }
-            for (int64_t tile = cta; tile < ntiles; tile += nctas) {
+            int buf = 0, ord = 0;     // ord = ordinal of the tile within this CTA (the workers count the same way)
+            for (int64_t tile = cta; tile < ntiles; tile += nctas, buf ^= 1, ++ord) {
+                if (ord % kFlushTiles == 0) { d3_acc = 0u; d4_acc = 0u; }   // the workers have flushed D3 / D4 before handing this tile's operands over
                 ready_wait(kBarRdyA);                      // dP2 operand (TMEM) and the dP2^T / H1^T images (smem) of this tile
                 umma::fence_after_sync();
                 if (lane == 0) { issue_ts3(COL_D2, COL_R1, dB2f); umma::commit(&sm.bar2); }      // GEMM2: dH1 = dP2 x W2
@@ -336,6 +383,10 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 }
                 if (lane == 0) { issue_g3(); umma::commit(&sm.bar3); }                           // GEMM3 of this tile
                 __syncwarp();
+                ready_wait(kBarRdyC);                      // dP1^T image of this tile (its x^T | 1 operand was written at publish time)
+                umma::fence_after_sync();
+                if (lane == 0) { issue_g4(buf); umma::commit(&sm.bar4); }                        // GEMM4 of this tile
+                __syncwarp();
             }
         }
     } else {
@@ -343,16 +394,16 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     // persistent per-thread gradient partials (over this thread's sample slot), reduced once at the end
-    float g3[2][16];                  // dW3[o][16c + k]
-    float db2acc[16], db1acc[16];     // sum_s dP2 / dP1 [16c + k]
-    float w1p0 = 0.f, w1p1 = 0.f;     // after the lane transpose-reduce: dW1 entries n = lane of feature half 0 / 1
+    float g3[2][16];                  // dW3[o][16c + k]   (db2, dW1, db1 and dW2 are reduced over the samples by the tensor core)
     float gb3a0 = 0.f, gb3a1 = 0.f;   // (c == 0 threads) sum_s dz[o]
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { g3[0][k] = 0.f; g3[1][k] = 0.f; db2acc[k] = 0.f; db1acc[k] = 0.f; }
+    for (int k = 0; k < 16; ++k) { g3[0][k] = 0.f; g3[1][k] = 0.f; }
     float l0 = 0.f, l1 = 0.f;
     float mean = 0.f, inv_std = 1.f;
     if (hp.normalize_adv && b.norm2) { mean = b.norm2[0]; inv_std = b.norm2[1]; }
-    uint32_t ph1 = 0, ph2 = 0, ph3 = 0;
+    uint32_t ph1 = 0, ph2 = 0, ph3 = 0, ph4 = 0;
+    bool gemm4_pending = false;
+    int xbuf = 0;                     // XT buffer of the tile being published (tile parity within this CTA)
     // random gather of one tile into registers, spread over all 512 threads: thread (sample s, block c) loads part c of
     // sample s — c = 0: the state (up to 4 floats), 1: action bits, 2: logp_old (actor) / return (critic), 3: advantage —
     // so nobody has more than one dependent load chain.  Issued one tile ahead: the L2 / HBM latency hides behind the
@@ -397,6 +448,58 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         }
     };
     bool gemm3_pending = false;
+    float* const out = partial + (int64_t)cta * np_total + poff;
+    float* const gW1 = out;
+    float* const gb1 = out + (int64_t)H * d.in;
+    float* const gW2 = gb1 + H;
+    float* const gb2 = gW2 + (int64_t)H * H;
+    for (int k = tid; k < 64 * 65 + 64; k += NT7) sm.AccW2[k] = 0.f;
+    for (int k = tid; k < 64 * 9; k += NT7) sm.AccD4[k] = 0.f;
+    // flush D3 (dW2 | db2) / D4 (dW1 | db1) into the shared-memory accumulators and let the issuer restart them (see kFlushTiles).
+    // Rows 0..63 of an accumulator (hi rows of the A operand) go first, rows 64..127 (lo rows) after a barrier: two threads per
+    // entry, in a fixed order => deterministic.  (Stride 65 / 9: the 32 lanes of a warp hit 32 different banks.)
+    auto flush_d3 = [&]() {
+        if (q < 2) {
+            float v[16], v2[16];
+            umma::tmem_ld16x2(tmem + lane_base + COL_D3 + 16 * c, tmem + lane_base + COL_D3 + 64 + 16 * c, v, v2);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sm.AccW2[s * 65 + 16 * c + k] += v[k] + v2[k];
+            if (c == 0) {
+                umma::tmem_ld16(tmem + lane_base + COL_D3 + 128, v);
+                sm.AccW2[64 * 65 + s] += v[0];
+            }
+        }
+        worker_sync();
+        if (q >= 2) {
+            float v[16];
+            umma::tmem_ld16(tmem + lane_base + COL_D3 + 16 * c, v);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sm.AccW2[(s - 64) * 65 + 16 * c + k] += v[k];
+            if (c == 0) {
+                umma::tmem_ld16(tmem + lane_base + COL_D3 + 128, v);
+                sm.AccW2[64 * 65 + (s - 64)] += v[0];
+            }
+        }
+        umma::fence_before_sync();
+    };
+    auto flush_d4 = [&]() {
+        if (c == 0 && q < 2) {
+            float d4[16];
+            umma::tmem_ld16(tmem + lane_base + COL_D4, d4);
+#pragma unroll
+            for (int i = 0; i < kInMax; ++i) sm.AccD4[s * 9 + i] += d4[i] + d4[8 + i];
+            sm.AccD4[s * 9 + 4] += d4[4];
+        }
+        worker_sync();
+        if (c == 0 && q >= 2) {
+            float d4[16];
+            umma::tmem_ld16(tmem + lane_base + COL_D4, d4);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) sm.AccD4[(s - 64) * 9 + i] += d4[i];
+        }
+        umma::fence_before_sync();
+    };
+    int ord = 0;   // ordinal of the current tile within this CTA
     // ---- software pipeline (one tile = 128 samples; tensor core and CUDA cores work on different tiles / phases) ----
     //   CUDA cores : ... P3(t) P45(t) | P0(t+1) P1(t+1) | P7(t) | P3(t+1) ...
     //   tensor core:              G2(t) ......... G1(t+1) .... G3(t) .....
@@ -407,6 +510,18 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         if (c == 0) {
 #pragma unroll
             for (int i = 0; i < kInMax; ++i) sm.X[i * TM + s] = pf[i];
+            uint32_t h01, l01, h23, l23;   // x^T operand of GEMM4 (rows 0..3 hi, 8..11 lo)
+            split2(pf[0] * kScaleX, pf[1] * kScaleX, h01, l01);
+            split2(pf[2] * kScaleX, pf[3] * kScaleX, h23, l23);
+            uint8_t* xt = sm.XT[xbuf];
+            *reinterpret_cast<uint16_t*>(xt + fimg_off(0, s)) = (uint16_t)(h01 & 0xFFFFu);
+            *reinterpret_cast<uint16_t*>(xt + fimg_off(1, s)) = (uint16_t)(h01 >> 16);
+            *reinterpret_cast<uint16_t*>(xt + fimg_off(2, s)) = (uint16_t)(h23 & 0xFFFFu);
+            *reinterpret_cast<uint16_t*>(xt + fimg_off(3, s)) = (uint16_t)(h23 >> 16);
+            *reinterpret_cast<uint16_t*>(xt + fimg_off(8, s)) = (uint16_t)(l01 & 0xFFFFu);
+            *reinterpret_cast<uint16_t*>(xt + fimg_off(9, s)) = (uint16_t)(l01 >> 16);
+            *reinterpret_cast<uint16_t*>(xt + fimg_off(10, s)) = (uint16_t)(l23 & 0xFFFFu);
+            *reinterpret_cast<uint16_t*>(xt + fimg_off(11, s)) = (uint16_t)(l23 >> 16);
         } else if (b.rec) {
             if (c == 1) {   // {action bits, logp_old, advantage, return}; the role that does not use a value stores 0 like the SoA path
                 sm.Aux[s] = pf[0];
@@ -423,12 +538,14 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             sm.Aux[2 * TM + s] = (role == 0 && hp.normalize_adv) ? (pf[0] - mean) * inv_std : pf[0];
         }
         K7_T(16);
+        xbuf ^= 1;
         if (t + nctas < ntiles) { gather_tile(t + nctas, pf); have_pf = true; } else have_pf = false;
     };
-    auto layer1 = [&](float (&xo)[kInMax]) {   // P1: H1 = act(W1 x + b1) -> TMEM A operand (full | lo); x stays in registers for P7
+    auto layer1 = [&]() {   // P1: H1 = act(W1 x + b1) -> TMEM A operand (hi | lo fp16 pairs)
+        float xo[kInMax];
 #pragma unroll
         for (int k = 0; k < kInMax; ++k) xo[k] = sm.X[k * TM + s];
-        float h1[16], lo[16];
+        uint32_t hi8[8], lo8[8];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
             const int f0 = 16 * c + 4 * ch;
@@ -439,22 +556,17 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 float4 w = *reinterpret_cast<const float4*>(sm.W1 + k * H + f0);
                 h[0] = fmaf(w.x, xo[k], h[0]); h[1] = fmaf(w.y, xo[k], h[1]); h[2] = fmaf(w.z, xo[k], h[2]); h[3] = fmaf(w.w, xo[k], h[3]);
             }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float hv = act_f(d.act, h[e]);
-                h1[4 * ch + e] = hv;
-                lo[4 * ch + e] = hv - hi_part(hv);
-            }
+            split2(act_f(d.act, h[0]) * kScaleH, act_f(d.act, h[1]) * kScaleH, hi8[2 * ch], lo8[2 * ch]);
+            split2(act_f(d.act, h[2]) * kScaleH, act_f(d.act, h[3]) * kScaleH, hi8[2 * ch + 1], lo8[2 * ch + 1]);
         }
-        umma::tmem_st16(tmem + lane_base + COL_AH + 16 * c, h1);
-        umma::tmem_st16(tmem + lane_base + COL_AH + 64 + 16 * c, lo);
+        umma::tmem_st8(tmem + lane_base + COL_AH + 8 * c, hi8);
+        umma::tmem_st8(tmem + lane_base + COL_AH + 32 + 8 * c, lo8);
         umma::tmem_st_wait();
     };
-    float x[kInMax];
     if (cta < ntiles) {   // prologue: P0 / P1 of the first tile (the issuer queues its G1)
         publish(cta);
         worker_sync();
-        layer1(x);
+        layer1();
         umma::fence_before_sync();
         ready_arrive(kBarRdyB);
     }
@@ -476,7 +588,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int f = 16 * c + k;
-                h2[k] = act_f(d.act, (v[k] + v2[k]) + sm.b2[f]);
+                h2[k] = act_f(d.act, fmaf(v[k] + v2[k], inv_s1, sm.b2[f]));   // (hh + lh) + hl, operand scale undone (exact)
                 float4 w = *reinterpret_cast<const float4*>(sm.W3 + f * kOutMax);
                 zp[0] = fmaf(w.x, h2[k], zp[0]); zp[1] = fmaf(w.y, h2[k], zp[1]); zp[2] = fmaf(w.z, h2[k], zp[2]); zp[3] = fmaf(w.w, h2[k], zp[3]);
             }
@@ -500,20 +612,21 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
 #pragma unroll
             for (int o = 0; o < kOutMax; ++o) dz[o] = valid ? lo_.dz[o] : 0.f;
             if (c == 0 && valid) { l0 += lo_.l0; l1 += lo_.l1; gb3a0 += dz[0]; gb3a1 += dz[1]; }
-            float dp[16], lo[16];
+            float dp[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int f = 16 * c + k;
                 float4 w = *reinterpret_cast<const float4*>(sm.W3 + f * kOutMax);
                 float dh = fmaf(w.x, dz[0], fmaf(w.y, dz[1], fmaf(w.z, dz[2], w.w * dz[3])));
                 dp[k] = dh * dact_f(d.act, h2[k]);
-                lo[k] = dp[k] - hi_part(dp[k]);
-                db2acc[k] += dp[k];
                 g3[0][k] = fmaf(dz[0], h2[k], g3[0][k]);
                 g3[1][k] = fmaf(dz[1], h2[k], g3[1][k]);
             }
-            umma::tmem_st16(tmem + lane_base + COL_R1 + 16 * c, dp);
-            umma::tmem_st16(tmem + lane_base + COL_R1 + 64 + 16 * c, lo);
+            uint32_t hi8[8], lo8[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) split2(dp[2 * m] * scale_p, dp[2 * m + 1] * scale_p, hi8[m], lo8[m]);
+            umma::tmem_st8(tmem + lane_base + COL_R1 + 8 * c, hi8);
+            umma::tmem_st8(tmem + lane_base + COL_R1 + 32 + 8 * c, lo8);
             K7_T(3);
             if (gemm3_pending) {   // the previous tile's GEMM3 must have consumed the images before they are overwritten
                 umma::mbar_wait(&sm.bar3, ph3);
@@ -521,20 +634,25 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 umma::fence_after_sync();
                 gemm3_pending = false;
             }
+            if (ord > 0 && ord % kFlushTiles == 0) flush_d3();   // every GEMM3 so far has completed; the next one restarts the accumulator
             K7_T(4);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t off = fimg_off(16 * c + k, s);
-                *reinterpret_cast<float*>(sm.FP_full + off) = dp[k];
-                *reinterpret_cast<float*>(sm.FP_lo + off) = lo[k];
+            for (int m = 0; m < 8; ++m) {
+                const uint32_t o0 = fimg_off(16 * c + 2 * m, s), o1 = fimg_off(16 * c + 2 * m + 1, s);
+                *reinterpret_cast<uint16_t*>(sm.FP_full + o0) = (uint16_t)(hi8[m] & 0xFFFFu);
+                *reinterpret_cast<uint16_t*>(sm.FP_full + o1) = (uint16_t)(hi8[m] >> 16);
+                *reinterpret_cast<uint16_t*>(sm.FP_lo + o0) = (uint16_t)(lo8[m] & 0xFFFFu);
+                *reinterpret_cast<uint16_t*>(sm.FP_lo + o1) = (uint16_t)(lo8[m] >> 16);
             }
-            // H1 of this tile (full | lo) back from its TMEM operand -> H1^T image
-            umma::tmem_ld16x2(tmem + lane_base + COL_AH + 16 * c, tmem + lane_base + COL_AH + 64 + 16 * c, dp, lo);
+            // H1 of this tile (hi | lo fp16 pairs) back from its TMEM operand -> H1^T image
+            umma::tmem_ld8x2(tmem + lane_base + COL_AH + 8 * c, tmem + lane_base + COL_AH + 32 + 8 * c, hi8, lo8);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t off = fimg_off(16 * c + k, s);
-                *reinterpret_cast<float*>(sm.FH_full + off) = dp[k];
-                *reinterpret_cast<float*>(sm.FH_lo + off) = lo[k];
+            for (int m = 0; m < 8; ++m) {
+                const uint32_t o0 = fimg_off(16 * c + 2 * m, s), o1 = fimg_off(16 * c + 2 * m + 1, s);
+                *reinterpret_cast<uint16_t*>(sm.FH_full + o0) = (uint16_t)(hi8[m] & 0xFFFFu);
+                *reinterpret_cast<uint16_t*>(sm.FH_full + o1) = (uint16_t)(hi8[m] >> 16);
+                *reinterpret_cast<uint16_t*>(sm.FH_lo + o0) = (uint16_t)(lo8[m] & 0xFFFFu);
+                *reinterpret_cast<uint16_t*>(sm.FH_lo + o1) = (uint16_t)(lo8[m] >> 16);
             }
             umma::tmem_st_wait();
         }
@@ -546,20 +664,19 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         worker_sync();              // Aux / Zp / X are free for the next tile
         K7_T(6);
         K7_T(7);
-        float xn[kInMax];
         if (has_next) {
             publish(tile + nctas);
             K7_T(8);
             worker_sync();
             K7_T(9);
-            layer1(xn);
+            layer1();
             umma::fence_before_sync();
             K7_T(10);
             ready_arrive(kBarRdyB);
             K7_T(11);
         }
         K7_T(12);
-        // ---- P7: dP1 = D2 .* act'(H1); dW1 / db1 partials ------------------------------------------------
+        // ---- P7: dP1 = D2 .* act'(H1) -> dP1^T image (GEMM4 reduces it against [x | 1] into dW1 | db1) ----------
         umma::mbar_wait(&sm.bar2, ph2);
         ph2 ^= 1u;
         umma::fence_after_sync();
@@ -570,85 +687,73 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 float v2[16];
                 umma::tmem_ld16x2(tmem + lane_base + COL_D2 + 16 * c, tmem + lane_base + COL_D2 + 64 + 16 * c, v, v2);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] += v2[k];
+                for (int k = 0; k < 16; ++k) v[k] = (v[k] + v2[k]) * inv_s2;   // operand scales undone (exact)
             }
+            const float inv_h = 1.0f / kScaleH;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const float h1k = *reinterpret_cast<const float*>(sm.FH_full + fimg_off(16 * c + k, s));   // this tile's H1 (image still intact)
+                const uint32_t off = fimg_off(16 * c + k, s);                  // this tile's H1 = (hi + lo) / scale (image still intact)
+                float h1k = half_bits_to_float(*reinterpret_cast<const uint16_t*>(sm.FH_full + off));
+                if (d.act != B200RL_ACT_RELU) h1k = (h1k + half_bits_to_float(*reinterpret_cast<const uint16_t*>(sm.FH_lo + off))) * inv_h;   // relu only needs the sign
                 v[k] = v[k] * dact_f(d.act, h1k);
-                db1acc[k] += v[k];
             }
-            // dW1[f][i] = sum_s dP1[s][f] x[s][i]: transpose-reduce over the warp's 32 samples, 8 features (32 values) at a time
-            float t[32];
+            if (gemm4_pending) {   // the previous tile's GEMM4 must have consumed the dP1^T image before it is overwritten
+                umma::mbar_wait(&sm.bar4, ph4);
+                ph4 ^= 1u;
+                umma::fence_after_sync();
+            }
+            if (ord > 0 && ord % kFlushTiles == 0) flush_d4();
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-#pragma unroll
-                for (int i = 0; i < kInMax; ++i) t[4 * k + i] = v[k] * x[i];
-            w1p0 += lane_transpose_reduce32(t, lane);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-#pragma unroll
-                for (int i = 0; i < kInMax; ++i) t[4 * k + i] = v[8 + k] * x[i];
-            w1p1 += lane_transpose_reduce32(t, lane);
+            for (int m = 0; m < 8; ++m) {
+                uint32_t hi, lo;
+                split2(v[2 * m] * scale_p, v[2 * m + 1] * scale_p, hi, lo);
+                const uint32_t o0 = fimg_off(16 * c + 2 * m, s), o1 = fimg_off(16 * c + 2 * m + 1, s);
+                *reinterpret_cast<uint16_t*>(sm.FQ_full + o0) = (uint16_t)(hi & 0xFFFFu);
+                *reinterpret_cast<uint16_t*>(sm.FQ_full + o1) = (uint16_t)(hi >> 16);
+                *reinterpret_cast<uint16_t*>(sm.FQ_lo + o0) = (uint16_t)(lo & 0xFFFFu);
+                *reinterpret_cast<uint16_t*>(sm.FQ_lo + o1) = (uint16_t)(lo >> 16);
+            }
+            gemm4_pending = true;
         }
         K7_T(14);
 #ifdef B200RL_K7_TIMING
         if (tid == g_k7_watch && blockIdx.x == 0) g_k7_phase[15] += 1;
 #endif
+        umma::fence_proxy_async();
         umma::fence_before_sync();
-        if (has_next) {
-#pragma unroll
-            for (int k = 0; k < kInMax; ++k) x[k] = xn[k];
-        }
+        ready_arrive(kBarRdyC);
+        ++ord;
     }
-    // ---- drain: last GEMM3, then write this CTA's gradient partial (fixed-order reductions) ---------------
-    const bool d3_valid = cta < ntiles;   // at least one tile went through GEMM3
+    // ---- drain: last GEMM3 / GEMM4, final flush, then the head gradients (fixed-order reductions) ---------------
     if (gemm3_pending) umma::mbar_wait(&sm.bar3, ph3);
+    if (gemm4_pending) umma::mbar_wait(&sm.bar4, ph4);
     umma::fence_after_sync();
     worker_sync();
-    float* out = partial + (int64_t)cta * np_total + poff;
-    float* gW1 = out;
-    float* gb1 = out + (int64_t)H * d.in;
-    float* gW2 = gb1 + H;
-    float* gb2 = gW2 + (int64_t)H * H;
-    float* red = reinterpret_cast<float*>(sm.FP_full);   // 4 * FIMG bytes contiguous, all MMAs are done
-    {   // D3 rows 0..63 (q < 2): [full*full | full*lo] of dW2 row j = s; rows 64..127 (q >= 2): lo*full of row j = s - 64
-        float v[16], v2[16];
-        if (d3_valid) {
-            umma::tmem_ld16(tmem + lane_base + COL_D3 + 16 * c, v);
-            if (q < 2) {
-                umma::tmem_ld16(tmem + lane_base + COL_D3 + 64 + 16 * c, v2);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] += v2[k];
-            } else {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) red[(s - 64) * 65 + 16 * c + k] = v[k];
-            }
-        }
-        worker_sync();
-        if (q < 2) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) gW2[s + H * (16 * c + k)] = d3_valid ? v[k] + red[s * 65 + 16 * c + k] : 0.f;
-        }
-        worker_sync();
+    if (cta < ntiles) { flush_d3(); flush_d4(); }        // (a CTA without tiles writes the zeros the accumulators were initialised with)
+    worker_sync();
+    for (int k = tid; k < H * H; k += NT7) gW2[k] = sm.AccW2[(k & 63) * 65 + (k >> 6)] * inv_s3;     // gW2[j + 64 i]
+    if (tid < H) {
+        gb2[tid] = sm.AccW2[64 * 65 + tid] * inv_sp;
+        gb1[tid] = sm.AccD4[tid * 9 + 4] * inv_sp;
+        for (int i = 0; i < d.in; ++i) gW1[tid + H * i] = sm.AccD4[tid * 9 + i] * inv_s4;
     }
-    // per-sample-slot partials of db2, db1, dW3[0], dW3[1] -> four [128 slots][64] matrices in shared memory -> column sums in
+    float* red = reinterpret_cast<float*>(sm.FP_full);   // images + weight images: contiguous, all MMAs are done
+    static_assert(offsetof(SmemBwd, XT) - offsetof(SmemBwd, FP_full) >= (2 * TM * 65 + 2 * 8 * 64) * 4, "drain scratch");
+    // per-sample-slot partials of dW3[0], dW3[1] -> two [128 slots][64] matrices in shared memory -> column sums in
     // a fixed order: 8 segment sums of 16 slots each (all 512 threads), then the 8 segments in order (64 threads per matrix)
     {
         constexpr int RS = 65;                // row stride 65: the 32 lanes (= 32 sample slots) of a store hit 32 different banks
-        float* seg = red + 4 * TM * RS;       // [4][8][64]
+        float* seg = red + 2 * TM * RS;       // [2][8][64]
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            red[0 * TM * RS + s * RS + 16 * c + k] = db2acc[k];
-            red[1 * TM * RS + s * RS + 16 * c + k] = db1acc[k];
-            red[2 * TM * RS + s * RS + 16 * c + k] = g3[0][k];
-            red[3 * TM * RS + s * RS + 16 * c + k] = g3[1][k];
+            red[0 * TM * RS + s * RS + 16 * c + k] = g3[0][k];
+            red[1 * TM * RS + s * RS + 16 * c + k] = g3[1][k];
         }
         worker_sync();
         {
             const int col = tid & 63, g = tid >> 6;   // 8 segments x 64 columns
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < 2; ++m) {
                 float a = 0.f;
 #pragma unroll
                 for (int ss = 0; ss < 16; ++ss) a += red[m * TM * RS + (16 * g + ss) * RS + col];
@@ -656,32 +761,20 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             }
         }
         worker_sync();
-        if (tid < 4 * H) {
+        if (tid < 2 * H) {
             const int m = tid >> 6, col = tid & 63;
             float a = 0.f;
 #pragma unroll
             for (int g = 0; g < 8; ++g) a += seg[(m * 8 + g) * 64 + col];
-            if (m == 0) gb2[col] = a;
-            else if (m == 1) gb1[col] = a;
-            else if (m - 2 < d.nout) out[head_w(d, m - 2, col)] = a;
+            if (m < d.nout) out[head_w(d, m, col)] = a;
         }
         worker_sync();
     }
-    // dW1: lane holds entry n = lane of feature half h (n = 4*k + i, k < 8): sum the 4 quadrant warps of block c
-    red[(q * 4 + c) * 64 + lane] = w1p0;
-    red[(q * 4 + c) * 64 + 32 + lane] = w1p1;
-    if (c == 0) { red[4096 + s] = gb3a0; red[4096 + TM + s] = gb3a1; }
+    if (c == 0) { red[s] = gb3a0; red[TM + s] = gb3a1; }
     worker_sync();
-    if (tid < kInMax * H) {
-        const int cc = tid >> 6, n = tid & 63;            // feature block, entry within the block (half*32 + 4*k + i)
-        const int half = n >> 5, kk = (n & 31) >> 2, i = n & 3;
-        const int f = 16 * cc + 8 * half + kk;
-        float a = (red[(0 * 4 + cc) * 64 + n] + red[(1 * 4 + cc) * 64 + n]) + (red[(2 * 4 + cc) * 64 + n] + red[(3 * 4 + cc) * 64 + n]);
-        if (i < d.in) gW1[f + H * i] = a;
-    }
     if (tid < d.nout) {
         float a = 0.f;
-        for (int ss = 0; ss < TM; ++ss) a += red[4096 + tid * TM + ss];
+        for (int ss = 0; ss < TM; ++ss) a += red[tid * TM + ss];
         out[head_b(d, tid)] = a;
     }
     // loss sums (worker-only block reduction)
@@ -714,7 +807,9 @@ int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const Ml
     static unsigned long long attr_devices = 0;   // once per device
     if (first_use_on_device(attr_devices, ctx->device))
         CUDA_TRY(cudaFuncSetAttribute(ac_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ac_loss_grad_tc_kernel<<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np);
+    // dP2 ~ inv_B x O(1..100): scale it into fp16's normal range with a power of two (exact, undone on the accumulators)
+    const float scale_base = exp2f(floorf(log2f(1.0f / b.inv_B)));
+    ac_loss_grad_tc_kernel<<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np, scale_base);
     LAUNCH_CHECK(ctx);
     return B200RL_OK;
 }

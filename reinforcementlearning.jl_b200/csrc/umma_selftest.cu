@@ -1,4 +1,5 @@
-// umma_selftest.cu — diagnostic entry point that pins down the tcgen05 operand-layout / TMEM
+// umma_selftest.cu — NOT part of libb200rl.so: built into build/libb200rl_selftest.so by `build.py --selftest` for the probes under
+// profiles/ (umma_probe*.py).  Diagnostic entry point that pins down the tcgen05 operand-layout / TMEM
 // mapping conventions on real hardware: the host supplies raw shared-memory images of the A and B
 // operands plus descriptor parameters; the kernel issues the MMAs and dumps TMEM lanes 0..127.
 #include "common.cuh"
@@ -12,6 +13,8 @@ struct SelfTestArgs {
     uint32_t a_kadv, b_kadv;                  // start-address advance per K step (bytes)
     uint32_t idesc; int ksteps; int ncols;    // instruction descriptor, # MMA instructions, D columns to dump
     int a_from_tmem;                           // 1: copy the (K-major, 64-wide) A image into TMEM columns 64.. and use the .ts form
+    int f16;                                   // 1: kind::f16 instead of kind::tf32
+    int a_raw;                                 // 1 (with a_from_tmem): the A image is a raw row-major [128][64] table of 32-bit TMEM words
     int repeat;                                // timing: issue the whole k-loop this many times; cycles -> d_out[last]
     float* d_out;                             // [128][ncols]
 };
@@ -38,7 +41,8 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
             float v[16];
             for (int k = 0; k < 16; ++k) {
                 int kk = c0 + k;
-                v[k] = *reinterpret_cast<const float*>(sa + (m / 8) * a.a_sbo + (kk / 4) * a.a_lbo + (m % 8) * 16 + (kk % 4) * 4);
+                v[k] = a.a_raw ? reinterpret_cast<const float*>(sa)[m * 64 + kk]
+                               : *reinterpret_cast<const float*>(sa + (m / 8) * a.a_sbo + (kk / 4) * a.a_lbo + (m % 8) * 16 + (kk % 4) * 4);
             }
             umma::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c0, v);
         }
@@ -53,11 +57,14 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
             for (int rep = 0; rep < a.repeat; ++rep)
             for (int k = 0; k < a.ksteps; ++k) {
                 uint64_t db = umma::make_desc(umma::smem_u32(sb) + k * a.b_kadv, a.b_lbo, a.b_sbo);
+                const uint32_t acc = (k > 0 || rep > 0) ? 1u : 0u;
                 if (a.a_from_tmem) {
-                    umma::mma_tf32_ts(tmem, tmem + 256 + k * a.a_kadv, db, a.idesc, (k > 0 || rep > 0) ? 1u : 0u);
+                    if (a.f16) umma::mma_f16_ts(tmem, tmem + 256 + k * a.a_kadv, db, a.idesc, acc);
+                    else umma::mma_tf32_ts(tmem, tmem + 256 + k * a.a_kadv, db, a.idesc, acc);
                 } else {
                     uint64_t da = umma::make_desc(umma::smem_u32(sa) + k * a.a_kadv, a.a_lbo, a.a_sbo);
-                    umma::mma_tf32(tmem, da, db, a.idesc, (k > 0 || rep > 0) ? 1u : 0u);
+                    if (a.f16) umma::mma_f16(tmem, da, db, a.idesc, acc);
+                    else umma::mma_tf32(tmem, da, db, a.idesc, acc);
                 }
             }
             umma::commit(&s_bar);
@@ -82,11 +89,11 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(SelfTestArgs a) {
 }  // namespace
 
 extern "C" int b200rl_selftest_umma(b200rl_ctx* ctx, const void* a_img_host, uint32_t a_bytes, const void* b_img_host, uint32_t b_bytes,
-                                    const uint32_t* desc8 /* a_lbo,a_sbo,b_lbo,b_sbo,a_kadv,b_kadv,idesc,ksteps | (a_from_tmem << 16) */, int ncols,
+                                    const uint32_t* desc8 /* a_lbo,a_sbo,b_lbo,b_sbo,a_kadv,b_kadv,idesc,ksteps | (a_from_tmem << 16) | (f16 << 17) | (a_raw << 18) | (repeat << 20) */, int ncols,
                                     float* d_out_host /* [128][ncols] */) {
     TRY(ctx_bind(ctx));
     REQUIRE(a_img_host && b_img_host && desc8 && d_out_host, B200RL_ERR_INVALID, "null argument");
-    REQUIRE(ncols == 32 || ncols == 64, B200RL_ERR_INVALID, "ncols must be 32 or 64");
+    REQUIRE(ncols == 32 || ncols == 64 || ncols == 128, B200RL_ERR_INVALID, "ncols must be 32, 64 or 128");
     REQUIRE(a_bytes % 4 == 0 && b_bytes % 4 == 0 && a_bytes + b_bytes < 200 * 1024, B200RL_ERR_INVALID, "bad image sizes");
     void* sc;
     size_t a_pad = ((size_t)a_bytes + 1023) / 1024 * 1024, b_pad = ((size_t)b_bytes + 1023) / 1024 * 1024;
@@ -94,7 +101,7 @@ extern "C" int b200rl_selftest_umma(b200rl_ctx* ctx, const void* a_img_host, uin
     uint8_t* da = (uint8_t*)sc; uint8_t* db = da + a_pad; float* dd = (float*)(db + b_pad);
     CUDA_TRY(cudaMemcpyAsync(da, a_img_host, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(db, b_img_host, b_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    SelfTestArgs a{da, a_bytes, db, b_bytes, desc8[0], desc8[1], desc8[2], desc8[3], desc8[4], desc8[5], desc8[6], (int)(desc8[7] & 0xFFFF), ncols, (int)((desc8[7] >> 16) & 1), (int)(desc8[7] >> 20) ? (int)(desc8[7] >> 20) : 1, dd};
+    SelfTestArgs a{da, a_bytes, db, b_bytes, desc8[0], desc8[1], desc8[2], desc8[3], desc8[4], desc8[5], desc8[6], (int)(desc8[7] & 0xFFFF), ncols, (int)((desc8[7] >> 16) & 1), (int)((desc8[7] >> 17) & 1), (int)((desc8[7] >> 18) & 1), (int)(desc8[7] >> 20) ? (int)(desc8[7] >> 20) : 1, dd};
     size_t smem = a_pad + b_pad;
     CUDA_TRY(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_selftest_kernel<<<1, 128, smem, ctx->stream>>>(a);

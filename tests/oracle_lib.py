@@ -10,7 +10,7 @@ import numpy as np
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_ROOT, "oracle", "liboracle.so")
 
-F_STATE, F_OBS, F_REWARD, F_TERMINAL, F_T, F_RNG, F_FLAGS = 0, 1, 2, 3, 4, 5, 6
+F_STATE, F_OBS, F_REWARD, F_TERMINAL, F_T, F_RNG, F_FLAGS, F_ACTION = 0, 1, 2, 3, 4, 5, 6, 7
 KIND_CARTPOLE, KIND_PENDULUM, KIND_MOUNTAINCAR, KIND_CARTPOLE_CONT, KIND_MOUNTAINCAR_CONT = 0, 1, 2, 3, 4
 NS = {0: 4, 1: 2, 2: 2, 3: 4, 4: 2}
 NOBS = {0: 4, 1: 3, 2: 2, 3: 4, 4: 2}
@@ -192,6 +192,7 @@ class OracleVecEnv:
             F_STATE: ((n, NS[self.kind]), self.np_t), F_OBS: ((n, NOBS[self.kind]), self.np_t),
             F_REWARD: ((n,), self.np_t), F_TERMINAL: ((n,), np.uint8), F_FLAGS: ((n,), np.uint8),
             F_T: ((n,), np.int32), F_RNG: ((n, 4), np.uint64),
+            F_ACTION: ((n,), np.float32 if (self.continuous or self.kind == KIND_PENDULUM) else np.int32),
         }[field]
         out = np.empty(*shape_dt)
         self.L.orc_vecenv_get(self.h, field, _p(out))
