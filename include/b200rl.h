@@ -193,28 +193,44 @@ int b200rl_discount_rewards_reduced_f64(b200rl_ctx* ctx, double* out, const doub
                                         int64_t R, int64_t C, int dims, int on_device);
 
 /* ---------------------------------------------------------------- trajectory ------- */
-/* Device-resident CircularArraySARTSTraces (+ CircularPrioritizedTraces) with a BatchSampler
+/* Device-resident CircularArraySARTSTraces (+ CircularPrioritizedTraces) wrapped in an EpisodesBuffer, with a BatchSampler
  * (ReinforcementLearningTrajectories 0.4, external to the reference tree; call sites
  * RLCore/src/policies/agent/agent_base.jl:45-59, agent_srt_cache.jl:30-50; layout
- * docs/src/How_to_implement_a_new_algorithm.md:84-112).  A ring of capacity+1 frames, each
- * frame holding `lanes` sub-envs (lanes = 1 is the reference's single stream).  sampler_rng:
- * (4, batch_size) uint64 host array, one Xoshiro stream per batch slot. */
+ * docs/src/How_to_implement_a_new_algorithm.md:84-112; length semantics RLCore/test/core/base.jl:20,
+ * test/policies/agent.jl:27-34).  `lanes` independent rings of capacity+1 slots, one per sub-env (lanes = 1 is the
+ * reference's single stream): every lane keeps its own position, the first state of each of its episodes is a frame of its
+ * own, and the entry straddling two episodes counts towards the length but is never sampled.  sampler_rng:
+ * (4, batch_size) uint64 host array, one Xoshiro stream per batch slot.  capacity >= 2. */
 int b200rl_traj_create(b200rl_ctx* ctx, int ns, int64_t lanes, int64_t capacity, int prioritized, float default_priority,
                        const uint64_t* sampler_rng, int64_t batch_size, b200rl_traj** out);
 int b200rl_traj_destroy(b200rl_traj* traj);
-/* length(trajectory.container) in frames (x lanes transitions): 0 after the first state, 1 after
- * the first transition (RLCore/test/policies/agent.jl:27-34) */
+/* length(trajectory.container) of lane 0: 0 after the first state, 1 after the first transition
+ * (RLCore/test/policies/agent.jl:27-34); lane_lengths: all lanes (== steps + episodes - 1 per lane, test/core/base.jl:20);
+ * n_sampleable: entries a sampler may return, summed over the lanes.  All three synchronise. */
 int b200rl_traj_length(b200rl_traj* traj, int64_t* frames_out);
-/* push!(trajectory, (state = s0,))  — agent_base.jl:45-47.  obs: (ns, lanes) */
+int b200rl_traj_lane_lengths(b200rl_traj* traj, int64_t* lengths_out);
+int b200rl_traj_n_sampleable(b200rl_traj* traj, int64_t* out);
+/* push!(trajectory, (state = s0,))  — the PreEpisodeStage push, agent_base.jl:45-47.  obs: (ns, lanes).
+ * push_state = every lane starts an episode; push_episode_start(mode 1) = only the lanes whose last transition was terminal
+ * (after a soft reset of the finished sub-envs). */
 int b200rl_traj_push_state(b200rl_traj* traj, const float* obs, int on_device);
-/* push!(trajectory, (state = s', action, reward, terminal)) — agent_base.jl:56-59 */
+int b200rl_traj_push_episode_start(b200rl_traj* traj, const float* obs, int on_device, int mode);
+/* push!(trajectory, (state = s', action, reward, terminal)) — agent_base.jl:56-59.  terminal: bit0 = is_terminated; bit1 = "the
+ * env has already auto-reset, next_obs is the next episode's first state" (the env's FLAGS byte): the episode-start frame is then
+ * written by the same call. */
 int b200rl_traj_push(b200rl_traj* traj, const int32_t* action, const float* reward, const uint8_t* terminal, const float* next_obs,
                      int on_device);
 /* the same, reading the env's device fields directly (no host round trip) */
 int b200rl_traj_push_env(b200rl_traj* traj, b200rl_env* env, int first_state_only);
-/* sample(trajectory): with replacement, uniform or proportional to priority (sum-tree descent);
- * the batch (state, action, reward, terminal, next_state, key, priority, weight) stays on device.
- * beta: importance-weight exponent, w = (n p / total)^-beta / max w */
+/* checkpoint of the ring: field 0 state (ns, lanes, cap+1) f32 | 1 action i32 | 2 reward f32 | 3 flag u8 (bit0 terminal, bit1
+ * sampleable) | 4 head (lanes) i32 | 5 count (lanes) i32 | 6 pending (lanes) u8 | 7 n_sampleable i64 | 8 sum tree (2L) f32 |
+ * 9 sampler streams (4, B) u64 */
+int b200rl_traj_field_bytes(b200rl_traj* traj, int field, size_t* bytes_out);
+int b200rl_traj_get(b200rl_traj* traj, int field, void* host_dst, size_t bytes);
+int b200rl_traj_set(b200rl_traj* traj, int field, const void* host_src, size_t bytes);
+/* sample(trajectory): with replacement, uniform over the sampleable entries (rejection) or proportional to priority (sum-tree
+ * descent that never enters an empty subtree); the batch (state, action, reward, terminal, next_state, key, priority, weight) stays
+ * on device.  beta: importance-weight exponent, w = (n p / total)^-beta / max w, n = n_sampleable */
 int b200rl_traj_sample(b200rl_traj* traj, float beta);
 /* field: 0 state (ns,B) | 1 action (B) i32 | 2 reward | 3 terminal u8 | 4 next_state | 5 key i64 |
  * 6 priority | 7 weight | 8 sampler rng (4,B) u64 */
@@ -240,6 +256,9 @@ int b200rl_net_configure_optimizer(b200rl_net* net, float lr, float beta1, float
 int b200rl_net_get(b200rl_net* net, int which, float* host_dst, int64_t count);
 int b200rl_net_set(b200rl_net* net, int which, const float* host_src, int64_t count);
 int b200rl_net_ptr(b200rl_net* net, int which, void** dptr_out);
+/* optimiser steps taken so far: the TargetNetwork's sync phase (n_optimise, target_network.jl:70-88) — checkpoint / resume */
+int b200rl_net_get_step(b200rl_net* net, int64_t* out);
+int b200rl_net_set_step(b200rl_net* net, int64_t step);
 /* optimise!(::TargetNetwork): target = rho*target + (1-rho)*model (target_network.jl:70-88) */
 int b200rl_net_target_sync(b200rl_net* net, float rho);
 /* plan!(policy, obs batch): obs (n_in, N); rng_dev (4, N) uint64 DEVICE streams (advanced);

@@ -108,6 +108,12 @@ SIGNATURES = {
     "b200rl_traj_create": (_i32, [_vp, _i32, _i64, _i64, _i32, _f32, _vp, _i64, _pp]),
     "b200rl_traj_destroy": (_i32, [_vp]),
     "b200rl_traj_length": (_i32, [_vp, C.POINTER(_i64)]),
+    "b200rl_traj_lane_lengths": (_i32, [_vp, _vp]),
+    "b200rl_traj_n_sampleable": (_i32, [_vp, C.POINTER(_i64)]),
+    "b200rl_traj_push_episode_start": (_i32, [_vp, _vp, _i32, _i32]),
+    "b200rl_traj_field_bytes": (_i32, [_vp, _i32, C.POINTER(_sz)]),
+    "b200rl_traj_get": (_i32, [_vp, _i32, _vp, _sz]),
+    "b200rl_traj_set": (_i32, [_vp, _i32, _vp, _sz]),
     "b200rl_traj_push_state": (_i32, [_vp, _vp, _i32]),
     "b200rl_traj_push": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32]),
     "b200rl_traj_push_env": (_i32, [_vp, _vp, _i32]),
@@ -122,6 +128,8 @@ SIGNATURES = {
     "b200rl_net_get": (_i32, [_vp, _i32, _vp, _i64]),
     "b200rl_net_set": (_i32, [_vp, _i32, _vp, _i64]),
     "b200rl_net_ptr": (_i32, [_vp, _i32, _pp]),
+    "b200rl_net_get_step": (_i32, [_vp, C.POINTER(_i64)]),
+    "b200rl_net_set_step": (_i32, [_vp, _i64]),
     "b200rl_net_target_sync": (_i32, [_vp, _f32]),
     "b200rl_net_act": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32]),
     "b200rl_net_values": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32]),

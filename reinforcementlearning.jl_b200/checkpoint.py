@@ -4,7 +4,11 @@ opaque handles, so the hook copies it out through the C ABI — `b200rl_net_get`
 `b200rl_onpolicy_export_state` — into a flat dict of numpy arrays (np.savez-able), and `restore` puts it back into freshly
 constructed objects of the same shapes.  A restored run continues bit for bit (tests/test_zz_dqn_agent_gpu.py), at a rollout
 boundary or in the middle of a rollout.  Host-side configuration (env kind / params, network shape, hyper-parameters) is the
-constructor's business, exactly as `PPOPolicy(...)` is rebuilt before `Flux.loadmodel!` in the reference."""
+constructor's business, exactly as `PPOPolicy(...)` is rebuilt before `Flux.loadmodel!` in the reference.
+
+`checkpoint` / `restore` cover on-policy runs (env + actor-critic net + OnPolicyAgent).  Replay runs (`Agent(QBasedPolicy, Trajectory)`)
+go through `checkpoint_replay` / `restore_replay`, which add the Q-network's update counter (the target-sync phase), the ring with its
+per-lane bookkeeping and sum tree, the sampler / explorer streams, the explorer's step and the controller's counters."""
 import numpy as np
 
 from . import _lib as L
@@ -82,6 +86,28 @@ def restore(ckpt, env=None, net=None, agent=None):
         agent.n_updates = int(c3[1])
 
 
+def checkpoint_replay(env, net, agent):
+    """State of a replay run: env, Q-network (+ target, Adam state, update counter), trajectory ring, explorer, controller."""
+    out = checkpoint(env=env, net=net)
+    out["net/step"] = np.array([net.step_count()], np.int64)
+    for k, v in agent.trajectory.export_state().items():
+        out["traj/" + k] = v
+    pol = agent.policy
+    out["policy/explorer_rng"] = pol.explorer_rng()
+    out["policy/explorer_step"] = np.array([getattr(pol.explorer, "step", 0)], np.int64)
+    return out
+
+
+def restore_replay(ckpt, env, net, agent):
+    restore(ckpt, env=env, net=net)
+    net.set_step_count(int(ckpt["net/step"][0]))
+    agent.trajectory.import_state({k[5:]: v for k, v in ckpt.items() if k.startswith("traj/")})
+    pol = agent.policy
+    pol.set_explorer_rng(ckpt["policy/explorer_rng"])
+    if hasattr(pol.explorer, "step"):
+        pol.explorer.step = int(ckpt["policy/explorer_step"][0])
+
+
 def save(path, ckpt):
     """np.savez (keys with '/' are legal archive member names)."""
     np.savez(path, **ckpt)
@@ -106,5 +132,8 @@ class CheckpointEveryNSteps:
         self.t += 1
         if self.t % self.n == 0:
             path = f"{self.prefix}_{self.t}.npz"
-            save(path, checkpoint(env=env, net=self.net or getattr(policy, "net", None), agent=policy if hasattr(policy, "rollout") else None))
+            if hasattr(policy, "trajectory"):      # replay Agent: the ring, explorer and controller travel too
+                save(path, checkpoint_replay(env, self.net or policy.policy.learner.net, policy))
+            else:
+                save(path, checkpoint(env=env, net=self.net or getattr(policy, "net", None), agent=policy if hasattr(policy, "rollout") else None))
             self.paths.append(path)

@@ -333,6 +333,7 @@ def run(policy, env=None, stop_condition=None, hook=None, reset_condition=None):
     hook.push(PreExperimentStage, policy, env)
     policy.push(PreExperimentStage, env)
     env.reset_(is_force=True)  # run.jl:46
+    policy.push(PreEpisodeStage, env)   # run.jl:47-49: every lane starts an episode (there is no per-lane episode stage in the batched loop)
     is_stop = False
     # Fused fast path: a device-resident agent (actions never visit the host), a hook that does nothing per step and a
     # step-count stop condition let whole stretches of the loop below run as ONE kernel launch (agent.collect(n): n x
@@ -365,6 +366,7 @@ def run(policy, env=None, stop_condition=None, hook=None, reset_condition=None):
         did_reset = False
         while reset_condition.check(policy, env):         # `while !check!(reset_condition, ...)` is evaluated again after the
             _timed("reset!", env.reset_, is_force=True)   # reset (run.jl:46,52): the reference leaves the episode loop and resets
+            _timed("push!(policy) PreEpisodeStage", policy.push, PreEpisodeStage, env)
             did_reset = True
         if not did_reset and not env.auto_reset:
             _timed("reset!", env.reset_, is_force=False)  # soft reset of finished sub-envs

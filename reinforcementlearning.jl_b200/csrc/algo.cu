@@ -233,6 +233,17 @@ int b200rl_net_ptr(b200rl_net* n, int which, void** dptr_out) {
     return B200RL_OK;
 }
 
+/* optimiser steps taken so far (drives the TargetNetwork's sync_freq phase, target_network.jl:70-88; part of a checkpoint) */
+int b200rl_net_get_step(b200rl_net* n, int64_t* out) {
+    REQUIRE(n && out, B200RL_ERR_INVALID, "null argument");
+    *out = (int64_t)n->n_updates;
+    return B200RL_OK;
+}
+int b200rl_net_set_step(b200rl_net* n, int64_t step) {
+    REQUIRE(n && step >= 0, B200RL_ERR_INVALID, "bad argument");
+    n->n_updates = (uint64_t)step;
+    return B200RL_OK;
+}
 /* TargetNetwork sync: target = rho*target + (1-rho)*model (rho = 0: hard copy) — target_network.jl:70-88 */
 int b200rl_net_target_sync(b200rl_net* n, float rho) {
     REQUIRE(n && n->target, B200RL_ERR_INVALID, "no target network");
@@ -863,11 +874,13 @@ int b200rl_onpolicy_time_kernel(b200rl_onpolicy* a, int which, int reps, float* 
 }
 
 // ------------------------------------------------------------------ DQN ---------------------
-/* push!(trajectory, env): append the env's last transition (action, reward, terminal, next obs) — all on device */
+/* push!(trajectory, env): append the env's last transition (action, reward, terminal, next obs) — all on device.
+ * first_state_only 1: episode-start frame for every lane (PreEpisodeStage); 2: only for the lanes whose last transition was terminal */
 int b200rl_traj_push_env(b200rl_traj* t, b200rl_env* env, int first_state_only) {
     REQUIRE(t && env, B200RL_ERR_INVALID, "null argument");
     REQUIRE(b200rl_traj_internal_lanes(t) == b200rl_env_internal_n(env), B200RL_ERR_INVALID, "trajectory lanes != number of envs");
     const float* obs = (const float*)env_field(env, B200RL_FIELD_OBS);
+    if (first_state_only == 2) return b200rl_traj_push_episode_start(t, obs, 1, 1);   // only the lanes whose episode has ended (soft reset)
     if (first_state_only) return b200rl_traj_push_state(t, obs, 1);
     return b200rl_traj_push(t, (const int32_t*)env_field(env, B200RL_FIELD_ACTION), (const float*)env_field(env, B200RL_FIELD_REWARD),
                             (const uint8_t*)env_field(env, B200RL_FIELD_FLAGS), obs, 1);

@@ -6,12 +6,18 @@
 // trace layout docs/src/How_to_implement_a_new_algorithm.md:84-112, length semantics
 // RLCore/test/policies/agent.jl:27-34, iteration tuple test/policies/q_based_policy.jl:40-58.
 //
-// Layout in HBM: one ring of cap+1 frames; a frame holds all `lanes` sub-envs:
+// Layout in HBM: cap+1 slots per lane, slot-major so that lanes at the same ring position are contiguous:
 //   state (ns, lanes, cap+1) f32 | action (lanes, cap+1) i32 | reward (lanes, cap+1) f32 |
-//   terminal (lanes, cap+1) u8 | sum tree 2L f32 (leaf = physical slot frame*lanes + lane).
-// Transition j uses state frame j and (as :next_state) frame j+1 — MultiplexTraces without a
-// second copy.  A push writes one contiguous frame (coalesced); a sample is one thread per
-// batch slot: Xoshiro draw -> (sum-tree descent) -> 2 x state gather + scalars.
+//   flag (lanes, cap+1) u8 (bit0 terminal, bit1 sampleable) | sum tree 2L f32 (leaf = slot*lanes + lane).
+// Entry p of a lane is the transition state[p] -> state[p+1] (MultiplexTraces without a second copy).
+// EpisodesBuffer semantics PER LANE (RLTrajectories 0.4; pinned by RLCore/test/core/base.jl:20: length == steps + episodes - 1):
+// every lane has its own ring position (head) and fill level (count).  The first state of an episode is a frame of its own
+// (push_episode_start, the PreEpisodeStage push of agent_base.jl:45-47), so the entry that straddles two episodes exists, counts
+// towards length(container) and is never sampleable.  With the env's in-kernel auto-reset the terminal step's next observation
+// already is the new episode's first state: the push stores it twice (as the masked :next_state of the terminal entry and as
+// the episode-start frame), which reproduces the reference's entry count and sampleable set exactly.
+// A push is one thread per lane (neighbouring lanes write neighbouring addresses unless their episode counts differ);
+// a sample is one thread per batch slot: Xoshiro draw -> (rejection | sum-tree descent) -> 2 x state gather + scalars.
 #include "common.cuh"
 
 namespace {
@@ -49,51 +55,98 @@ __device__ __forceinline__ unsigned long long rand_below(Xo4& g, unsigned long l
 
 struct Ring {
     int ns;
-    int64_t lanes, cap, first, n_states;
-    float* state; int32_t* action; float* reward; uint8_t* terminal;
+    int64_t lanes, cap;
+    float* state; int32_t* action; float* reward; uint8_t* flag;
+    int32_t* head;       // (lanes) next slot to write
+    int32_t* count;      // (lanes) state frames stored, <= cap + 1
+    uint8_t* pending;    // (lanes) the last stored transition was terminal and its episode-start frame has not been pushed yet
+    long long* n_valid;  // (1) sampleable entries over all lanes
     float* tree; int64_t L;
     __host__ __device__ int64_t frames() const { return cap + 1; }
-    __host__ __device__ int64_t phys(int64_t j) const { return (first + j) % (cap + 1); }
 };
+constexpr uint8_t kTerminal = 1, kSampleable = 2;
 
-__global__ void copy_frame_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[i];
+// ---- push kernels: one thread per lane; `keys`/`vals` (3 per lane) receive the sum-tree leaves to rewrite (key -1 = none) --------
+__device__ __forceinline__ void write_state(const Ring& r, int64_t slot, int64_t e, const float* __restrict__ obs) {
+    float* dst = r.state + (int64_t)r.ns * (slot * r.lanes + e);
+    const float* src = obs + (int64_t)r.ns * e;
+    for (int c = 0; c < r.ns; ++c) dst[c] = src[c];
 }
-__global__ void push_sart_kernel(Ring r, int64_t pf, const int32_t* __restrict__ a, const float* __restrict__ rew,
-                                 const uint8_t* __restrict__ term) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// the state frame at `slot` is about to be overwritten: the entry that started there is gone
+__device__ __forceinline__ int destroy_entry(const Ring& r, int64_t slot, int64_t e) {
+    const int64_t k = slot * r.lanes + e;
+    const int was = (r.flag[k] & kSampleable) ? 1 : 0;
+    r.flag[k] = 0;
+    return was;
+}
+// push!(trajectory, (state = s0,)): mode 0 every lane, 1 only lanes whose last transition was terminal (soft reset)
+__global__ void push_episode_start_kernel(Ring r, const float* __restrict__ obs, int mode, float default_priority, int64_t* __restrict__ keys,
+                                          float* __restrict__ vals) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= r.lanes) return;
-    r.action[pf * r.lanes + e] = a[e];
-    r.reward[pf * r.lanes + e] = rew[e];
-    r.terminal[pf * r.lanes + e] = term[e] & 1;
+    if (keys) { keys[3 * e] = -1; keys[3 * e + 1] = -1; keys[3 * e + 2] = -1; }
+    if (mode == 1 && !r.pending[e]) return;
+    const int64_t F = r.frames();
+    const int64_t h = r.head[e];
+    const int lost = destroy_entry(r, h, e);
+    write_state(r, h, e, obs);
+    if (keys) { keys[3 * e] = h * r.lanes + e; vals[3 * e] = 0.f; }
+    r.head[e] = (int32_t)((h + 1) % F);
+    r.count[e] = (int32_t)min((int64_t)r.count[e] + 1, F);
+    r.pending[e] = 0;
+    if (lost) atomicAdd((unsigned long long*)r.n_valid, (unsigned long long)(-1ll));
 }
-
-// Single CTA: set leaves [s0, s0+n) = v0 and [s1, s1+n) = v1, then recompute their ancestors
-// level by level (children are re-added, never delta-updated -> deterministic, drift-free).
-__global__ void __launch_bounds__(1024) tree_set_ranges_kernel(float* __restrict__ tree, int64_t L, int64_t s0, float v0, int64_t s1,
-                                                               float v1, int64_t n, int use1) {
-    for (int pass = 0; pass < (use1 ? 2 : 1); ++pass) {
-        int64_t s = pass ? s1 : s0;
-        float v = pass ? v1 : v0;
-        for (int64_t k = threadIdx.x; k < n; k += blockDim.x) tree[L + s + k] = v;
-        __syncthreads();
-        int64_t lo = (L + s) >> 1, hi = (L + s + n - 1) >> 1;
-        while (lo >= 1) {
-            for (int64_t k = lo + threadIdx.x; k <= hi; k += blockDim.x) tree[k] = tree[2 * k] + tree[2 * k + 1];
-            __syncthreads();
-            if (lo == 1) break;
-            lo >>= 1; hi >>= 1;
+// push!(trajectory, (state = s', action, reward, terminal)).  term[e]: bit0 terminal, bit1 "the env has already auto-reset: next_obs
+// is the first state of the next episode" (the env's FLAGS byte) -> the episode-start frame is written in the same launch.
+__global__ void push_sart_kernel(Ring r, const int32_t* __restrict__ a, const float* __restrict__ rew, const uint8_t* __restrict__ term,
+                                 const float* __restrict__ next_obs, float default_priority, int64_t* __restrict__ keys, float* __restrict__ vals) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r.lanes) return;
+    const int64_t F = r.frames();
+    const int64_t h = r.head[e];
+    const int64_t p = (h + F - 1) % F;                 // slot of the state the action was taken in
+    const uint8_t t = term[e];
+    r.action[p * r.lanes + e] = a[e];
+    r.reward[p * r.lanes + e] = rew[e];
+    r.flag[p * r.lanes + e] = (uint8_t)((t & kTerminal) | kSampleable);
+    long long dv = 1;
+    dv -= destroy_entry(r, h, e);
+    write_state(r, h, e, next_obs);
+    int64_t nh = (h + 1) % F;
+    int cnt = (int)min((int64_t)r.count[e] + 1, F);
+    if (keys) {
+        keys[3 * e] = p * r.lanes + e; vals[3 * e] = default_priority;
+        keys[3 * e + 1] = h * r.lanes + e; vals[3 * e + 1] = 0.f;
+        keys[3 * e + 2] = -1;
+    }
+    uint8_t pend = 0;
+    if (t & kTerminal) {
+        if (t & 2) {                                   // auto-reset: next_obs doubles as the episode-start frame
+            dv -= destroy_entry(r, nh, e);
+            write_state(r, nh, e, next_obs);
+            if (keys) { keys[3 * e + 2] = nh * r.lanes + e; vals[3 * e + 2] = 0.f; }
+            nh = (nh + 1) % F;
+            cnt = (int)min((int64_t)cnt + 1, F);
+        } else {
+            pend = 1;                                  // the caller pushes the episode start once the env has been reset
         }
     }
+    r.head[e] = (int32_t)nh;
+    r.count[e] = cnt;
+    r.pending[e] = pend;
+    if (dv != 0) atomicAdd((unsigned long long*)r.n_valid, (unsigned long long)dv);
 }
-// Single CTA: tree[L + key[k]] = prio[k] for the batch, then rebuild the touched paths.
+
+// Single CTA: tree[L + key[k]] = prio[k] for every key >= 0, then rebuild the touched paths level by level
+// (children are re-added, never delta-updated -> deterministic, drift-free; duplicate keys must carry one value).
 __global__ void __launch_bounds__(1024) tree_update_keys_kernel(float* __restrict__ tree, int64_t L, const int64_t* __restrict__ key,
                                                                 const float* __restrict__ prio, int64_t B) {
-    for (int64_t k = threadIdx.x; k < B; k += blockDim.x) tree[L + key[k]] = prio[k];
+    for (int64_t k = threadIdx.x; k < B; k += blockDim.x)
+        if (key[k] >= 0) tree[L + key[k]] = prio[k];
     __syncthreads();
     for (int shift = 1; (L >> shift) >= 1; ++shift) {  // one tree level per iteration, leaves' parents first
         for (int64_t k = threadIdx.x; k < B; k += blockDim.x) {
+            if (key[k] < 0) continue;
             int64_t node = (L + key[k]) >> shift;
             tree[node] = tree[2 * node] + tree[2 * node + 1];
         }
@@ -110,43 +163,47 @@ __global__ void sample_gather_kernel(Ring r, unsigned long long* __restrict__ sl
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= B) return;
     Xo4 g = load_xo(slots, k);
-    const int64_t n = (r.n_states - 1) * r.lanes;
-    int64_t key, q;
+    const int64_t F = r.frames();
+    int64_t key;
     float p = 0.f, w = 1.f;
     if (PRIO) {
-        float total = r.tree[1];
+        const float total = r.tree[1];
         float v = ((float)((unsigned)(xo_next(g) >> 32) >> 8) * 0x1p-24f) * total;  // rand(rng, Float32) * total
         int64_t node = 1;
-        while (node < r.L) {
-            int64_t l = 2 * node;
-            float tl = r.tree[l];
-            if (v <= tl) node = l;
+        while (node < r.L) {     // never step into an empty subtree: float rounding cannot land on a zero-priority leaf
+            const int64_t l = 2 * node;
+            const float tl = r.tree[l], tr = r.tree[l + 1];
+            if (tl > 0.f && (v < tl || !(tr > 0.f))) node = l;
             else { v -= tl; node = l + 1; }
         }
         key = node - r.L;
         p = r.tree[r.L + key];
-        if (!(p > 0.f)) {  // rounding landed on an empty leaf: oldest transition instead
-            key = r.phys(0) * r.lanes;
-            p = r.tree[r.L + key];
-        }
-        int64_t pf = key / r.lanes, e = key % r.lanes;
-        int64_t j = (pf - r.first + r.frames()) % r.frames();
-        q = j * r.lanes + e;
+        const long long n = *r.n_valid;
         w = powf((float)n * (p / total), -beta);
     } else {
-        q = (int64_t)rand_below(g, (unsigned long long)n);
-        key = r.phys(q / r.lanes) * r.lanes + q % r.lanes;
+        // uniform over the sampleable entries: draw (lane, logical index) and redraw while it is not one
+        const unsigned long long n = (unsigned long long)(r.lanes * r.cap);
+        key = -1;
+        for (int tries = 0; tries < 4096; ++tries) {
+            const int64_t q = (int64_t)rand_below(g, n);
+            const int64_t e = q % r.lanes, j = q / r.lanes;
+            const int64_t cnt = r.count[e];
+            if (j >= cnt - 1) continue;
+            const int64_t slot = ((int64_t)r.head[e] - cnt + j + 2 * F) % F;
+            if (r.flag[slot * r.lanes + e] & kSampleable) { key = slot * r.lanes + e; break; }
+        }
+        if (key < 0) __trap();   // (practically) nothing sampleable
     }
     store_xo(slots, k, g);
-    int64_t j = q / r.lanes, e = q % r.lanes;
-    int64_t pf = r.phys(j), pn = r.phys(j + 1);
-    const float* s = r.state + (int64_t)r.ns * (pf * r.lanes + e);
-    const float* s2 = r.state + (int64_t)r.ns * (pn * r.lanes + e);
+    const int64_t slot = key / r.lanes, e = key % r.lanes;
+    const int64_t nslot = (slot + 1) % F;
+    const float* s = r.state + (int64_t)r.ns * (slot * r.lanes + e);
+    const float* s2 = r.state + (int64_t)r.ns * (nslot * r.lanes + e);
     for (int c = 0; c < r.ns; ++c) { o.s[(int64_t)r.ns * k + c] = s[c]; o.s2[(int64_t)r.ns * k + c] = s2[c]; }
-    o.a[k] = r.action[pf * r.lanes + e];
-    o.r[k] = r.reward[pf * r.lanes + e];
-    o.t[k] = r.terminal[pf * r.lanes + e];
-    o.key[k] = pf * r.lanes + e;
+    o.a[k] = r.action[key];
+    o.r[k] = r.reward[key];
+    o.t[k] = r.flag[key] & kTerminal;
+    o.key[k] = key;
     o.prio[k] = p;
     o.w[k] = w;
 }
@@ -180,8 +237,10 @@ struct b200rl_traj {
     unsigned long long* slots;  // (4, B) sampler streams
     BatchOut batch;
     float* new_prio;            // (B) scratch for priority write-back
+    int64_t* keys; float* vals; // (3 * lanes) sum-tree leaves rewritten by a push
     void* stage;                // staging for host-side pushes
     size_t stage_bytes;
+    int64_t pushed;             // transitions frames pushed so far (host-side sanity only)
 };
 
 static int stage_in(b200rl_traj* t, const void* host, size_t bytes, size_t offset, const void** dev) {
@@ -190,16 +249,11 @@ static int stage_in(b200rl_traj* t, const void* host, size_t bytes, size_t offse
     *dev = (char*)t->stage + offset;
     return B200RL_OK;
 }
-
-static int traj_push_state_dev(b200rl_traj* t, const float* obs_dev) {
-    Ring& r = t->r;
-    int64_t pf;
-    if (r.n_states == r.frames()) { pf = r.first; r.first = (r.first + 1) % r.frames(); }
-    else { pf = r.phys(r.n_states); r.n_states += 1; }
-    int64_t n = (int64_t)r.ns * r.lanes;
-    copy_frame_kernel<<<grid_for(n, 256), 256, 0, t->ctx->stream>>>(r.state + n * pf, obs_dev, n);
+static int tree_apply(b200rl_traj* t) {
+    if (!t->prioritized) return B200RL_OK;
+    tree_update_keys_kernel<<<1, 1024, 0, t->ctx->stream>>>(t->r.tree, t->r.L, t->keys, t->vals, 3 * t->r.lanes);
     LAUNCH_CHECK(t->ctx);
-    return (int)0;
+    return B200RL_OK;
 }
 
 extern "C" {
@@ -207,23 +261,32 @@ extern "C" {
 int b200rl_traj_create(b200rl_ctx* ctx, int ns, int64_t lanes, int64_t capacity, int prioritized, float default_priority,
                        const uint64_t* sampler_rng, int64_t batch_size, b200rl_traj** out) {
     TRY(ctx_bind(ctx));
-    REQUIRE(out && ns >= 1 && ns <= 16 && lanes >= 1 && capacity >= 1, B200RL_ERR_INVALID, "bad shape");
+    REQUIRE(out && ns >= 1 && ns <= 16 && lanes >= 1 && capacity >= 2, B200RL_ERR_INVALID, "bad shape (capacity >= 2)");
     REQUIRE(batch_size >= 0 && (batch_size == 0 || sampler_rng), B200RL_ERR_INVALID, "sampler_rng required when batch_size > 0");
+    REQUIRE((capacity + 1) < (1ll << 31), B200RL_ERR_UNSUPPORTED, "capacity too large");
     b200rl_traj* t = new b200rl_traj();
     memset(t, 0, sizeof *t);
     t->ctx = ctx; t->prioritized = prioritized != 0; t->default_priority = default_priority; t->B = batch_size;
     Ring& r = t->r;
-    r.ns = ns; r.lanes = lanes; r.cap = capacity; r.first = 0; r.n_states = 0;
+    r.ns = ns; r.lanes = lanes; r.cap = capacity;
     size_t slots = (size_t)lanes * (capacity + 1);
     CUDA_TRY(cudaMalloc(&r.state, slots * ns * sizeof(float)));
     CUDA_TRY(cudaMalloc(&r.action, slots * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&r.reward, slots * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&r.terminal, slots));
+    CUDA_TRY(cudaMalloc(&r.flag, slots));
+    CUDA_TRY(cudaMalloc(&r.head, (size_t)lanes * 4)); CUDA_TRY(cudaMalloc(&r.count, (size_t)lanes * 4)); CUDA_TRY(cudaMalloc(&r.pending, (size_t)lanes));
+    CUDA_TRY(cudaMalloc(&r.n_valid, 8));
+    CUDA_TRY(cudaMemsetAsync(r.state, 0, slots * ns * sizeof(float), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(r.action, 0, slots * 4, ctx->stream)); CUDA_TRY(cudaMemsetAsync(r.reward, 0, slots * 4, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(r.flag, 0, slots, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(r.head, 0, (size_t)lanes * 4, ctx->stream)); CUDA_TRY(cudaMemsetAsync(r.count, 0, (size_t)lanes * 4, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(r.pending, 0, (size_t)lanes, ctx->stream)); CUDA_TRY(cudaMemsetAsync(r.n_valid, 0, 8, ctx->stream));
     r.L = 1;
     if (t->prioritized) {
         while (r.L < (int64_t)slots) r.L <<= 1;
         CUDA_TRY(cudaMalloc(&r.tree, 2 * r.L * sizeof(float)));
         CUDA_TRY(cudaMemsetAsync(r.tree, 0, 2 * r.L * sizeof(float), ctx->stream));
+        CUDA_TRY(cudaMalloc(&t->keys, (size_t)lanes * 3 * 8)); CUDA_TRY(cudaMalloc(&t->vals, (size_t)lanes * 3 * 4));
     }
     if (batch_size > 0) {
         size_t B = (size_t)batch_size;
@@ -250,40 +313,64 @@ int b200rl_traj_destroy(b200rl_traj* t) {
     if (!t) return B200RL_OK;
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
-    cudaFree(t->r.state); cudaFree(t->r.action); cudaFree(t->r.reward); cudaFree(t->r.terminal); cudaFree(t->r.tree);
+    cudaFree(t->r.state); cudaFree(t->r.action); cudaFree(t->r.reward); cudaFree(t->r.flag); cudaFree(t->r.tree);
+    cudaFree(t->r.head); cudaFree(t->r.count); cudaFree(t->r.pending); cudaFree(t->r.n_valid); cudaFree(t->keys); cudaFree(t->vals);
     cudaFree(t->slots); cudaFree(t->batch.s); cudaFree(t->batch.s2); cudaFree(t->batch.a); cudaFree(t->batch.r); cudaFree(t->batch.t);
     cudaFree(t->batch.key); cudaFree(t->batch.prio); cudaFree(t->batch.w); cudaFree(t->new_prio); cudaFree(t->stage);
     delete t;
     return B200RL_OK;
 }
 
-/* length(trajectory.container): number of complete transition frames (x lanes transitions) */
+/* length(trajectory.container) per lane: entries stored (sampleable or not) = state frames - 1 (synchronises) */
+int b200rl_traj_lane_lengths(b200rl_traj* t, int64_t* lengths_out) {
+    REQUIRE(t && lengths_out, B200RL_ERR_INVALID, "null argument");
+    TRY(ctx_bind(t->ctx));
+    std::vector<int32_t> c((size_t)t->r.lanes);
+    CUDA_TRY(cudaMemcpyAsync(c.data(), t->r.count, c.size() * 4, cudaMemcpyDeviceToHost, t->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+    for (int64_t e = 0; e < t->r.lanes; ++e) lengths_out[e] = c[(size_t)e] > 0 ? c[(size_t)e] - 1 : 0;
+    return B200RL_OK;
+}
+/* length of lane 0 (lanes = 1 is the reference's single stream: 0 after the first state, 1 after the first transition) */
 int b200rl_traj_length(b200rl_traj* t, int64_t* frames_out) {
     REQUIRE(t && frames_out, B200RL_ERR_INVALID, "null argument");
-    *frames_out = t->r.n_states > 0 ? t->r.n_states - 1 : 0;
+    TRY(ctx_bind(t->ctx));
+    int32_t c = 0;
+    CUDA_TRY(cudaMemcpyAsync(&c, t->r.count, 4, cudaMemcpyDeviceToHost, t->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+    *frames_out = c > 0 ? c - 1 : 0;
+    return B200RL_OK;
+}
+/* number of sampleable entries over all lanes (synchronises) */
+int b200rl_traj_n_sampleable(b200rl_traj* t, int64_t* out) {
+    REQUIRE(t && out, B200RL_ERR_INVALID, "null argument");
+    TRY(ctx_bind(t->ctx));
+    long long v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, t->r.n_valid, 8, cudaMemcpyDeviceToHost, t->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+    *out = v;
     return B200RL_OK;
 }
 
-int b200rl_traj_push_state(b200rl_traj* t, const float* obs, int on_device) {
-    REQUIRE(t && obs, B200RL_ERR_INVALID, "null argument");
+/* push!(trajectory, (state = s0,)) — the PreEpisodeStage push (agent_base.jl:45-47).  mode 0: every lane starts an episode
+ * (forced reset); mode 1: only the lanes whose last transition was terminal (soft reset of a MultiThreadEnv-style batch). */
+int b200rl_traj_push_episode_start(b200rl_traj* t, const float* obs, int on_device, int mode) {
+    REQUIRE(t && obs && (mode == 0 || mode == 1), B200RL_ERR_INVALID, "bad argument");
     TRY(ctx_bind(t->ctx));
     const void* d = obs;
     if (!on_device) TRY(stage_in(t, obs, (size_t)t->r.ns * t->r.lanes * 4, 0, &d));
-    // the frame being overwritten is the oldest one: its transitions leave the sum tree
-    int64_t pf = t->r.n_states == t->r.frames() ? t->r.first : t->r.phys(t->r.n_states);
-    TRY(traj_push_state_dev(t, (const float*)d));
-    if (t->prioritized) {
-        tree_set_ranges_kernel<<<1, 1024, 0, t->ctx->stream>>>(t->r.tree, t->r.L, pf * t->r.lanes, 0.f, 0, 0.f, t->r.lanes, 0);
-        LAUNCH_CHECK(t->ctx);
-    }
+    push_episode_start_kernel<<<grid_for(t->r.lanes, 256), 256, 0, t->ctx->stream>>>(t->r, (const float*)d, mode, t->default_priority,
+                                                                                     t->prioritized ? t->keys : nullptr, t->vals);
+    LAUNCH_CHECK(t->ctx);
+    TRY(tree_apply(t));
     if (!on_device) CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
     return B200RL_OK;
 }
+int b200rl_traj_push_state(b200rl_traj* t, const float* obs, int on_device) { return b200rl_traj_push_episode_start(t, obs, on_device, 0); }
 
 int b200rl_traj_push(b200rl_traj* t, const int32_t* action, const float* reward, const uint8_t* terminal, const float* next_obs,
                      int on_device) {
     REQUIRE(t && action && reward && terminal && next_obs, B200RL_ERR_INVALID, "null argument");
-    REQUIRE(t->r.n_states >= 1, B200RL_ERR_INVALID, "push a first state (b200rl_traj_push_state) before the first transition");
     TRY(ctx_bind(t->ctx));
     Ring& r = t->r;
     const void *da = action, *dr = reward, *dt = terminal, *ds = next_obs;
@@ -294,15 +381,11 @@ int b200rl_traj_push(b200rl_traj* t, const int32_t* action, const float* reward,
         TRY(stage_in(t, reward, L * 4, L * r.ns * 4 + L * 4, &dr));
         TRY(stage_in(t, terminal, L, L * r.ns * 4 + L * 8, &dt));
     }
-    int64_t pf = r.phys(r.n_states - 1);
-    push_sart_kernel<<<grid_for(r.lanes, 256), 256, 0, t->ctx->stream>>>(r, pf, (const int32_t*)da, (const float*)dr, (const uint8_t*)dt);
+    push_sart_kernel<<<grid_for(r.lanes, 256), 256, 0, t->ctx->stream>>>(r, (const int32_t*)da, (const float*)dr, (const uint8_t*)dt, (const float*)ds,
+                                                                            t->default_priority, t->prioritized ? t->keys : nullptr, t->vals);
     LAUNCH_CHECK(t->ctx);
-    int64_t pnew = r.n_states == r.frames() ? r.first : r.phys(r.n_states);
-    TRY(traj_push_state_dev(t, (const float*)ds));
-    if (t->prioritized) {
-        tree_set_ranges_kernel<<<1, 1024, 0, t->ctx->stream>>>(r.tree, r.L, pnew * r.lanes, 0.f, pf * r.lanes, t->default_priority, r.lanes, 1);
-        LAUNCH_CHECK(t->ctx);
-    }
+    TRY(tree_apply(t));
+    t->pushed += 1;
     if (!on_device) CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
     return B200RL_OK;
 }
@@ -310,7 +393,7 @@ int b200rl_traj_push(b200rl_traj* t, const int32_t* action, const float* reward,
 /* BatchSampler / prioritised sampler + gather into the trajectory's device batch buffers */
 int b200rl_traj_sample(b200rl_traj* t, float beta) {
     REQUIRE(t && t->B > 0, B200RL_ERR_INVALID, "trajectory was created without a sampler");
-    REQUIRE(t->r.n_states >= 2, B200RL_ERR_INVALID, "nothing to sample yet");
+    REQUIRE(t->pushed >= 1, B200RL_ERR_INVALID, "nothing to sample yet");
     TRY(ctx_bind(t->ctx));
     if (t->prioritized) {
         sample_gather_kernel<true><<<grid_for(t->B, 128), 128, 0, t->ctx->stream>>>(t->r, t->slots, t->B, beta, t->batch);
@@ -324,6 +407,51 @@ int b200rl_traj_sample(b200rl_traj* t, float beta) {
     return B200RL_OK;
 }
 
+/* Checkpoint of the ring (docs/src/How_to_use_hooks.md:124-167 pattern): field 0 state (ns, lanes, cap+1) f32 | 1 action i32 |
+ * 2 reward f32 | 3 flag u8 (bit0 terminal, bit1 sampleable) | 4 head (lanes) i32 | 5 count (lanes) i32 | 6 pending (lanes) u8 |
+ * 7 n_sampleable i64 | 8 sum tree (2L) f32 | 9 sampler streams (4, B) u64.  bytes_out (may be NULL) receives the field size. */
+static int traj_field(b200rl_traj* t, int field, void** p, size_t* bytes) {
+    const size_t slots = (size_t)t->r.lanes * (size_t)(t->r.cap + 1), L = (size_t)t->r.lanes;
+    switch (field) {
+        case 0: *p = t->r.state; *bytes = slots * t->r.ns * 4; return B200RL_OK;
+        case 1: *p = t->r.action; *bytes = slots * 4; return B200RL_OK;
+        case 2: *p = t->r.reward; *bytes = slots * 4; return B200RL_OK;
+        case 3: *p = t->r.flag; *bytes = slots; return B200RL_OK;
+        case 4: *p = t->r.head; *bytes = L * 4; return B200RL_OK;
+        case 5: *p = t->r.count; *bytes = L * 4; return B200RL_OK;
+        case 6: *p = t->r.pending; *bytes = L; return B200RL_OK;
+        case 7: *p = t->r.n_valid; *bytes = 8; return B200RL_OK;
+        case 8: REQUIRE(t->prioritized, B200RL_ERR_INVALID, "no sum tree"); *p = t->r.tree; *bytes = (size_t)(2 * t->r.L) * 4; return B200RL_OK;
+        case 9: REQUIRE(t->B > 0, B200RL_ERR_INVALID, "no sampler"); *p = t->slots; *bytes = (size_t)t->B * 32; return B200RL_OK;
+    }
+    REQUIRE(false, B200RL_ERR_INVALID, "unknown trajectory field");
+}
+int b200rl_traj_field_bytes(b200rl_traj* t, int field, size_t* bytes_out) {
+    REQUIRE(t && bytes_out, B200RL_ERR_INVALID, "null argument");
+    void* p;
+    return traj_field(t, field, &p, bytes_out);
+}
+int b200rl_traj_get(b200rl_traj* t, int field, void* host_dst, size_t bytes) {
+    REQUIRE(t && host_dst, B200RL_ERR_INVALID, "null argument");
+    TRY(ctx_bind(t->ctx));
+    void* p; size_t need;
+    TRY(traj_field(t, field, &p, &need));
+    REQUIRE(bytes >= need, B200RL_ERR_INVALID, "destination too small");
+    CUDA_TRY(cudaMemcpyAsync(host_dst, p, need, cudaMemcpyDeviceToHost, t->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+    return B200RL_OK;
+}
+int b200rl_traj_set(b200rl_traj* t, int field, const void* host_src, size_t bytes) {
+    REQUIRE(t && host_src, B200RL_ERR_INVALID, "null argument");
+    TRY(ctx_bind(t->ctx));
+    void* p; size_t need;
+    TRY(traj_field(t, field, &p, &need));
+    REQUIRE(bytes >= need, B200RL_ERR_INVALID, "source too small");
+    CUDA_TRY(cudaMemcpyAsync(p, host_src, need, cudaMemcpyHostToDevice, t->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->ctx->stream));
+    if (field == 5) t->pushed = 1;   // a restored ring may be sampled
+    return B200RL_OK;
+}
 /* field: 0 state (ns,B) 1 action (B) i32 2 reward 3 terminal u8 4 next_state 5 key i64 6 priority 7 weight 8 sampler rng (4,B) */
 int b200rl_traj_batch_get(b200rl_traj* t, int field, void* host_dst, size_t bytes) {
     REQUIRE(t && host_dst && t->B > 0, B200RL_ERR_INVALID, "bad argument");

@@ -232,6 +232,7 @@ function RLCore._run(policy::AbstractPolicy, env::B200VecEnv, stop_condition::Ab
     push!(hook, PreExperimentStage(), policy, env)
     push!(policy, PreExperimentStage(), env)
     RLBase.reset!(env; is_force = true)
+    push!(policy, PreEpisodeStage(), env)                      # run.jl:47-49: every lane starts an episode
     # Fused fast path (the Python mirror's run(), core.py): a device-resident on-policy agent, a hook with nothing to do per
     # step and a step-count stop condition let whole stretches of the loop run as ONE kernel launch (b200rl_onpolicy_collect:
     # n x {plan!, act!, push!}) — the same transitions, parameters and statistics as stepping through the stages.
@@ -255,6 +256,7 @@ function RLCore._run(policy::AbstractPolicy, env::B200VecEnv, stop_condition::Ab
         did_reset = false
         while RLCore.check!(reset_condition, policy, env)      # ResetAfterNSteps: the whole batch is force-reset (ResetIfEnvTerminated never fires)
             @timeit_debug timer "reset!"                        RLBase.reset!(env; is_force = true)
+            @timeit_debug timer "push!(policy) PreEpisodeStage" push!(policy, PreEpisodeStage(), env)
             did_reset = true
         end
         (did_reset || env.auto_reset) || @timeit_debug timer "reset!" RLBase.reset!(env; is_force = false)
@@ -397,9 +399,21 @@ function checkpoint(a::B200OnPolicyAgent)
     GC.@preserve counters check(ccall((:b200rl_onpolicy_export_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), a.h, counters))
     rng = Matrix{UInt64}(undef, 4, env.n)
     GC.@preserve rng check(ccall((:b200rl_onpolicy_get, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t), a.h, 8, rng, sizeof(rng)))
-    counters[1] == 0 || @warn "B200RL.checkpoint: taken in the middle of a rollout; the Python mirror also saves the rollout columns (checkpoint.py)"
+    # in the middle of a rollout (counters[1] = t > 0; e.g. DoEveryNSteps(n = 10_000) with update_freq = 32) the columns 0..t-1 of the
+    # rollout tensors are part of the state: fields 0-5 of b200rl_onpolicy_get (state, action, logp, reward, terminal, value)
+    rollout = counters[1] == 0 ? nothing : map(0:5) do f
+        dst = rollout_field_array(a, f)
+        GC.@preserve dst check(ccall((:b200rl_onpolicy_get, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t), a.h, f, dst, sizeof(dst)))
+        dst
+    end
     (env = NamedTuple{keys(ENV_FIELDS)}(envs), params = net[0, np[]], adam_m = net[2, np[]], adam_v = net[3, np[]], beta_t = net[4, 2],
-     counters = counters, policy_rng = rng)
+     counters = counters, policy_rng = rng, rollout = rollout)
+end
+"Host array shaped like rollout field `f` of `b200rl_onpolicy_get` (0 state (ns, N, T+1) | 1 action | 2 logp | 3 reward | 4 terminal | 5 value (N, T+1))."
+function rollout_field_array(a::B200OnPolicyAgent, f::Integer)
+    n, T, ns = a.env.n, a.T, NOBS[a.env.kind]
+    f == 0 ? Array{Float32}(undef, ns, n, T + 1) : f == 1 ? (a.env.continuous ? Matrix{Float32}(undef, n, T) : Matrix{Int32}(undef, n, T)) :
+    f == 4 ? Matrix{UInt8}(undef, n, T) : f == 5 ? Matrix{Float32}(undef, n, T + 1) : Matrix{Float32}(undef, n, T)
 end
 "Put a `checkpoint` back into a freshly constructed agent (same env kind / N, same network shape, same hyper-parameters)."
 function restore!(a::B200OnPolicyAgent, ck)
@@ -411,6 +425,13 @@ function restore!(a::B200OnPolicyAgent, ck)
     a.net[0] = ck.params; a.net[2] = ck.adam_m; a.net[3] = ck.adam_v; a.net[4] = ck.beta_t
     rng, counters = ck.policy_rng, ck.counters
     GC.@preserve rng check(ccall((:b200rl_onpolicy_set, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t), a.h, 8, rng, sizeof(rng)))
+    if counters[1] > 0    # mid-rollout checkpoint: the first t columns must come back, or the next update would read uninitialised memory
+        hasproperty(ck, :rollout) && ck.rollout !== nothing ||
+            error("B200RL.restore!: the checkpoint was taken at rollout step t = $(counters[1]) but holds no rollout columns")
+        for (f, src) in zip(0:5, ck.rollout)
+            GC.@preserve src check(ccall((:b200rl_onpolicy_set, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t), a.h, f, src, sizeof(src)))
+        end
+    end
     GC.@preserve counters check(ccall((:b200rl_onpolicy_import_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), a.h, counters))
     a.t = Int(counters[1])
     a
@@ -464,8 +485,15 @@ function Base.length(t::B200Trajectory)
     Int(n[])
 end
 # push!(trajectory, (state = s0,)) / push!(trajectory, (state = s', action, reward, terminal)) reading the env's device fields
-push_env!(t::B200Trajectory, env::B200VecEnv; first_state_only::Bool = false) =
-    check(ccall((:b200rl_traj_push_env, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), t.h, env.h, first_state_only))
+# mode 0: the transition; 1: episode-start frame for every lane; 2: episode-start frame for the lanes whose last transition was terminal
+push_env!(t::B200Trajectory, env::B200VecEnv; mode::Integer = 0) =
+    check(ccall((:b200rl_traj_push_env, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), t.h, env.h, mode))
+"`length(container)` per lane (== steps + episodes - 1, RLCore/test/core/base.jl:20)"
+function lane_lengths(t::B200Trajectory)
+    out = Vector{Int64}(undef, t.lanes)
+    GC.@preserve out check(ccall((:b200rl_traj_lane_lengths, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), t.h, out))
+    out
+end
 
 struct DQNConfigC
     gamma::Cfloat; lr::Cfloat; beta1::Cfloat; beta2::Cfloat; eps::Cfloat; max_grad_norm::Cfloat; rho::Cfloat
@@ -539,25 +567,18 @@ end
 """
     B200Agent(policy::B200QBasedPolicy, trajectory::B200Trajectory)
 
-`Agent(policy, trajectory)` (agent_base.jl:18-66) with a device-resident replay: transition frames never visit the host.  The batched loop
-has no episode stages, so the `PreEpisodeStage` push of the first state (agent_base.jl:45-47) happens at the first `PreActStage`.
+`Agent(policy, trajectory)` (agent_base.jl:18-66) with a device-resident replay: transition frames never visit the host.  `_run` announces
+every forced reset with a `PreEpisodeStage` push (every lane gets an episode-start frame, so re-entering `run` on a filled trajectory is
+fine: the entry straddling the reset is stored and never sampled — EpisodesBuffer's bookkeeping, kept per lane on the device).  Episodes
+that end inside the loop start their next frame in the push kernel (in-kernel auto-reset) or at the next `PreActStage` (soft reset).
 """
 mutable struct B200Agent <: AbstractPolicy
     policy::B200QBasedPolicy
     trajectory::B200Trajectory
-    primed::Bool
 end
-B200Agent(policy::B200QBasedPolicy, trajectory::B200Trajectory) = B200Agent(policy, trajectory, false)
 RLBase.plan!(a::B200Agent, env::B200VecEnv) = RLBase.plan!(a.policy, env)
-function Base.push!(a::B200Agent, ::PreExperimentStage, ::B200VecEnv)
-    length(a.trajectory) == 0 || error("B200Agent: run on a non-empty device trajectory is not supported (no EpisodesBuffer bookkeeping)")
-    a.primed = false
-    nothing
-end
-function Base.push!(a::B200Agent, ::PreActStage, env::B200VecEnv)
-    a.primed || (push_env!(a.trajectory, env; first_state_only = true); a.primed = true)
-    nothing
-end
+Base.push!(a::B200Agent, ::PreEpisodeStage, env::B200VecEnv) = (push_env!(a.trajectory, env; mode = 1); nothing)      # push!(trajectory, (state = s0,)), all lanes
+Base.push!(a::B200Agent, ::PreActStage, env::B200VecEnv) = (env.auto_reset || push_env!(a.trajectory, env; mode = 2); nothing)   # lanes soft-reset after their terminal step
 function Base.push!(a::B200Agent, ::PostActStage, env::B200VecEnv, action)
     push_env!(a.trajectory, env)
     a.trajectory.controller.n_inserted += 1

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .core import AbstractPolicy, FusedAction, PostActStage, PreActStage, PreExperimentStage
+from .core import AbstractPolicy, FusedAction, PostActStage, PreActStage, PreEpisodeStage, PreExperimentStage
 
 ACT_RELU, ACT_TANH = 0, 1
 KIND_CATEGORICAL, KIND_GAUSSIAN, KIND_Q = 0, 1, 2
@@ -80,6 +80,14 @@ class Network:
         p = C.c_void_p()
         L.check(self.lib.b200rl_net_ptr(self.h, which, C.byref(p)))
         return p.value
+
+    def step_count(self):
+        n = C.c_int64()
+        L.check(self.lib.b200rl_net_get_step(self.h, C.byref(n)))
+        return n.value
+
+    def set_step_count(self, n):
+        L.check(self.lib.b200rl_net_set_step(self.h, int(n)))
 
     def target_sync(self, rho=0.0):
         L.check(self.lib.b200rl_net_target_sync(self.h, rho))
@@ -273,6 +281,50 @@ class Trajectory:
         obs = np.asfortranarray(obs, np.float32)
         L.check(self.lib.b200rl_traj_push_state(self.h, L.ptr(obs), 0))
 
+    def push_episode_start(self, obs, pending_only=False, on_device=False):
+        """push!(trajectory, (state = s0,)): every lane, or (pending_only) the lanes whose last transition was terminal."""
+        if not on_device:
+            obs = np.asfortranarray(obs, np.float32)
+        L.check(self.lib.b200rl_traj_push_episode_start(self.h, L.ptr(obs), int(on_device), int(pending_only)))
+
+    def lane_lengths(self):
+        out = np.empty(self.lanes, np.int64)
+        L.check(self.lib.b200rl_traj_lane_lengths(self.h, L.ptr(out)))
+        return out
+
+    def n_sampleable(self):
+        n = C.c_int64()
+        L.check(self.lib.b200rl_traj_n_sampleable(self.h, C.byref(n)))
+        return n.value
+
+    # ---- checkpoint of the ring (fields of b200rl_traj_get) ----------------------------------
+    FIELDS = {"state": (0, np.float32), "action": (1, np.int32), "reward": (2, np.float32), "flag": (3, np.uint8), "head": (4, np.int32),
+              "count": (5, np.int32), "pending": (6, np.uint8), "n_sampleable": (7, np.int64), "tree": (8, np.float32), "sampler_rng": (9, np.uint64)}
+
+    def export_state(self):
+        out = {}
+        for name, (f, dt) in self.FIELDS.items():
+            if (name == "tree" and not self.prioritized) or (name == "sampler_rng" and not self.batch_size):
+                continue
+            nb = C.c_size_t()
+            L.check(self.lib.b200rl_traj_field_bytes(self.h, f, C.byref(nb)))
+            a = np.empty(nb.value // np.dtype(dt).itemsize, dt)
+            L.check(self.lib.b200rl_traj_get(self.h, f, L.ptr(a), a.nbytes))
+            out[name] = a
+        if hasattr(self, "controller"):
+            c = self.controller
+            out["controller"] = np.array([c.ratio, c.threshold, c.n_inserted, c.n_sampled], np.float64)
+        return out
+
+    def import_state(self, st):
+        for name, (f, dt) in self.FIELDS.items():
+            if name in st:
+                a = np.ascontiguousarray(st[name], dt)
+                L.check(self.lib.b200rl_traj_set(self.h, f, L.ptr(a), a.nbytes))
+        if "controller" in st and hasattr(self, "controller"):
+            c = self.controller
+            c.ratio, c.threshold, c.n_inserted, c.n_sampled = float(st["controller"][0]), int(st["controller"][1]), int(st["controller"][2]), int(st["controller"][3])
+
     def push(self, action, reward, terminal, next_obs):
         L.check(self.lib.b200rl_traj_push(self.h, L.ptr(np.ascontiguousarray(action, np.int32)), L.ptr(np.ascontiguousarray(reward, np.float32)),
                                           L.ptr(np.ascontiguousarray(terminal, np.uint8)), L.ptr(np.asfortranarray(next_obs, np.float32)), 0))
@@ -396,6 +448,9 @@ class QBasedPolicy(AbstractPolicy):
         out = np.empty((self.n, 4), np.uint64)
         return self.ctx.d2h(out, self._d_rng)
 
+    def set_explorer_rng(self, rng):
+        self.ctx.h2d(self._d_rng, np.ascontiguousarray(rng, np.uint64).reshape(self.n, 4))
+
     def optimise(self, stage, trajectory=None):
         """optimise!(policy, stage, trajectory) = optimise!(policy.learner, stage, trajectory) (q_based_policy.jl:48-49);
         the DQN learner trains at the PostActStage."""
@@ -409,28 +464,25 @@ class Agent(AbstractPolicy):
     transition frames (state / action / reward / terminal never visit the host) and lets the policy's learner train
     whenever the trajectory's controller allows a batch.
 
-    There are no episode stages in the batched loop, so the first state is pushed at the first PreActStage after the
-    forced reset (the PreEpisodeStage push of agent_base.jl:45-47).  Re-entering ``run`` with a non-empty trajectory is
-    refused: the reference's EpisodesBuffer would mark the frame straddling the forced reset as not sampleable, which
-    this ring does not implement."""
+    Episode starts (the PreEpisodeStage push of agent_base.jl:45-47): run() announces every forced reset with a PreEpisodeStage
+    push -> every lane gets an episode-start frame (so re-entering run() on a filled trajectory is fine: the entry straddling the
+    reset exists and is not sampleable, exactly EpisodesBuffer's bookkeeping).  Episodes that end inside the loop: with the env's
+    in-kernel auto-reset the trajectory writes the episode-start frame itself (the terminal step's observation already is the new
+    episode's first state); with soft resets (auto_reset = False) the lanes whose last transition was terminal get the post-reset
+    observation at the next PreActStage."""
 
     def __init__(self, policy, trajectory, host_actions=False):
         self.policy, self.trajectory, self.host_actions = policy, trajectory, host_actions
         if not hasattr(trajectory, "controller"):
             trajectory.controller = InsertSampleRatioController()
-        self._primed = False
         self._host_act = None
 
     def push(self, stage, env, action=None):
-        if stage == PreExperimentStage:
-            if len(self.trajectory) > 0:
-                raise RuntimeError("Agent: run() on a non-empty device trajectory is not supported (no EpisodesBuffer bookkeeping for "
-                                   "the frame straddling the forced reset); create a fresh Trajectory")
-            self._primed = False
+        if stage == PreEpisodeStage:
+            self.trajectory.push_env(env, first_state_only=True)         # push!(trajectory, (state = state(env),)) for every lane
         elif stage == PreActStage:
-            if not self._primed:
-                self.trajectory.push_env(env, first_state_only=True)     # push!(trajectory, (state = state(env),))
-                self._primed = True
+            if not getattr(env, "auto_reset", True):
+                self.trajectory.push_env(env, first_state_only=2)        # lanes that were soft-reset since their terminal transition
         elif stage == PostActStage:
             self.trajectory.push_env(env)                                # (state = s', action, reward, terminal)
             self.trajectory.controller.on_insert(1)

@@ -62,7 +62,8 @@ def lib():
         "orc_dqn_loss_grad": (None, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, f32, i32, i32, vp, vp, vp]),
         "orc_adv_norm": (None, [vp, i64, vp]),
         "orc_traj_create": (vp, [i32, i64, i64, i32, f32]), "orc_traj_destroy": (None, [vp]),
-        "orc_traj_length": (i64, [vp]), "orc_traj_push_state": (None, [vp, vp]),
+        "orc_traj_length": (i64, [vp]), "orc_traj_push_state": (None, [vp, vp]), "orc_traj_lane_lengths": (None, [vp, vp]),
+        "orc_traj_n_sampleable": (i64, [vp]), "orc_traj_push_episode_start": (None, [vp, vp, i32]),
         "orc_traj_push": (None, [vp, vp, vp, vp, vp]),
         "orc_traj_sample": (None, [vp, i32, vp, i64, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "orc_traj_update_priority": (None, [vp, vp, vp, i64]), "orc_traj_total_priority": (f32, [vp]),
@@ -419,6 +420,17 @@ class OracleTraj:
 
     def push_state(self, obs):
         self.L.orc_traj_push_state(self.h, _p(np.asfortranarray(obs, np.float32)))
+
+    def push_episode_start(self, obs, pending_only=False):
+        self.L.orc_traj_push_episode_start(self.h, _p(np.asfortranarray(obs, np.float32)), int(pending_only))
+
+    def lane_lengths(self):
+        out = np.empty(self.lanes, np.int64)
+        self.L.orc_traj_lane_lengths(self.h, _p(out))
+        return out
+
+    def n_sampleable(self):
+        return int(self.L.orc_traj_n_sampleable(self.h))
 
     def push(self, a, r, t, next_obs):
         self.L.orc_traj_push(self.h, _p(np.ascontiguousarray(a, np.int32)), _p(np.ascontiguousarray(r, np.float32)),

@@ -177,7 +177,8 @@ def test_run_loop_order_and_step_count(pkg):
     assert env.log[-1] == ("check",)
     assert stages == ["PreExperimentStage"] + ["PreActStage", "PostActStage"] * 4 + ["PostExperimentStage"]
     per_iter = [("push", "PreActStage"), ("optimise", "PreActStage"), "plan", ("push", "PostActStage"), ("optimise", "PostActStage")]
-    assert pol.events == [("push", "PreExperimentStage")] + per_iter * 4 + [("push", "PostExperimentStage")]
+    # run.jl:46-49: the forced reset is followed by the PreEpisodeStage push (every lane starts an episode)
+    assert pol.events == [("push", "PreExperimentStage"), ("push", "PreEpisodeStage")] + per_iter * 4 + [("push", "PostExperimentStage")]
 
 
 def test_run_random_policy_is_fused_into_the_step(pkg):
@@ -395,7 +396,7 @@ def test_fused_fast_path_hands_whole_stretches_to_collect(pkg):
     pkg.run(agent, env, pkg.StopAfterNSteps(21), pkg.DeviceEpisodeStats())   # per_step = False: nothing happens at the act stages
     assert agent.calls == [("collect", 8), ("update",), ("collect", 8), ("update",), ("collect", 5)]
     assert agent._t == 5 and env.log[0] == ("reset", True) and env.log[-1] == ("check",)
-    assert agent.pushed == ["PreExperimentStage", "PostExperimentStage"]
+    assert agent.pushed == ["PreExperimentStage", "PreEpisodeStage", "PostExperimentStage"]   # run.jl:47: the forced reset starts an episode
     # a second run continues filling the same rollout: 3 more steps complete it
     pkg.run(agent, env, pkg.StopAfterNSteps(4), pkg.EmptyHook())
     assert agent.calls[-3:] == [("collect", 3), ("update",), ("collect", 1)]
@@ -409,18 +410,19 @@ def test_fused_fast_path_hands_whole_stretches_to_collect(pkg):
 
 
 def test_replay_agent_stage_logic_with_stubs(pkg):
-    """learners.Agent (agent_base.jl:18-66 for a device ring): first state at the first PreActStage, one frame + one controller insertion
-    per PostActStage, the learner trains while the controller allows, re-entry on a non-empty ring is refused."""
+    """learners.Agent (agent_base.jl:18-66 for a device ring): an episode-start frame for every lane at each PreEpisodeStage (run() pushes
+    one after every forced reset), one frame + one controller insertion per PostActStage, the learner trains while the controller allows,
+    re-entering run() on a filled ring is fine (the device ring keeps EpisodesBuffer's bookkeeping), soft-reset envs get their pending
+    episode starts at PreActStage."""
     class Traj:
         def __init__(self):
-            self.frames, self.first_states = 0, 0
+            self.frames, self.first_states, self.pending_starts = 0, 0, 0
             self.controller = pkg.InsertSampleRatioController(ratio=0.5, threshold=3)
 
-        def __len__(self):
-            return self.frames
-
         def push_env(self, env, first_state_only=False):
-            if first_state_only:
+            if first_state_only == 2:
+                self.pending_starts += 1
+            elif first_state_only:
                 self.first_states += 1
             else:
                 self.frames += 1
@@ -447,6 +449,9 @@ def test_replay_agent_stage_logic_with_stubs(pkg):
     pkg.run(agent, env, pkg.StopAfterNSteps(9))
     assert traj.first_states == 1 and traj.frames == 9 and traj.controller.n_inserted == 9
     assert Learner.updates == traj.controller.n_sampled == int((9 - 3) * 0.5) + 1
-    with pytest.raises(RuntimeError):
-        pkg.run(agent, env, pkg.StopAfterNSteps(1))
-    assert traj.frames == 9                                 # nothing was pushed by the refused run
+    soft = 0 if getattr(env, "auto_reset", True) else 9
+    assert traj.pending_starts == soft                      # one (cheap, masked) episode-start push per step for soft-reset envs only
+    pkg.run(agent, env, pkg.StopAfterNSteps(2))             # re-entry: the forced reset starts a new episode for every lane
+    assert traj.first_states == 2 and traj.frames == 11
+    pkg.run(agent, env, pkg.StopAfterNSteps(4), None, pkg.ResetAfterNSteps(2))
+    assert traj.first_states == 2 + 1 + 1                   # this run's start + the forced reset after its 2nd step

@@ -67,6 +67,87 @@ def test_prioritized_sampling_and_updates_bit_exact(pkg, ctx, lanes, cap, frames
         assert tr.total_priority() == ref.total_priority()
 
 
+def _drive(pkg, ctx, env, tr, ref, steps, hook):
+    """random-policy steps with trajectory pushes the way learners.Agent does them; the oracle ring gets the same calls"""
+    for _ in range(steps):
+        if not env.auto_reset:
+            env.reset_(is_force=False)                                        # soft reset of the finished sub-envs ...
+            tr.push_env(env, first_state_only=2); ref.push_episode_start(env.state(), pending_only=True)   # ... whose episodes start here
+        env.act_random_()
+        tr.push_env(env)
+        ref.push(env.last_action(), env.reward(), env.flags(), env.state())
+        hook.push("PostActStage", None, env)
+
+
+@pytest.mark.parametrize("auto_reset", [True, False])
+def test_episodes_buffer_length_identity_per_lane(pkg, ctx, auto_reset):
+    """RLCore/test/core/base.jl:20 per lane: length(container) == steps + episodes - 1 — every episode's first state is a frame of its
+    own and the entry straddling two episodes is stored but never sampleable; the sampleable entries are exactly the steps.
+    (With the in-kernel auto-reset an episode that ends on the very last step has already started its successor: that frame counts.)"""
+    n, steps, B = 96, 70, 2048
+    env = pkg.B200VecEnv(ctx, "CartPole", n, O.splitmix_states_fast(n, 5), auto_reset=auto_reset)
+    slots = O.splitmix_states_fast(B, 6)
+    tr = pkg.Trajectory(ctx, 4, 200, lanes=n, batch_size=B, sampler_rng=slots)
+    ref = O.OracleTraj(4, n, 200)
+    hook = pkg.BatchStepsPerEpisode(n)
+    env.reset_(is_force=True)
+    tr.push_env(env, first_state_only=True); ref.push_state(env.state())     # PreEpisodeStage after the forced reset
+    assert np.array_equal(tr.lane_lengths(), np.zeros(n, np.int64))           # test/policies/agent.jl:30 (0 after the first state)
+    _drive(pkg, ctx, env, tr, ref, steps, hook)
+    finished = np.array([len(s) for s in hook[()]])
+    assert finished.sum() > n                                                 # CartPole under the random policy: ~3 episodes per lane
+    last_step_terminal = env.is_terminated()
+    started = 1 + finished - (0 if auto_reset else last_step_terminal.astype(int))   # soft reset: the successor of a just-finished episode has not begun
+    lengths = tr.lane_lengths()
+    assert np.array_equal(lengths, steps + started - 1)
+    assert np.array_equal(lengths, ref.lane_lengths())
+    assert tr.n_sampleable() == ref.n_sampleable() == steps * n               # every step is sampleable, no straddling entry is
+    s = slots.copy()
+    b = tr.sample(); rb = ref.sample(s, B)
+    assert_batches_equal(b, rb) and np.array_equal(tr.sampler_rng(), s)
+    # a sampled terminal transition really ends an episode; a non-terminal one is followed by its true successor state
+    term = b["terminal"].astype(bool)
+    assert term.any() and (~term).any()
+    # forced reset in the middle (ResetAfterNSteps / re-entering run): an episode-start frame for every lane, nothing else changes
+    env.reset_(is_force=True)
+    tr.push_env(env, first_state_only=True); ref.push_state(env.state())
+    assert np.array_equal(tr.lane_lengths(), lengths + 1) and tr.n_sampleable() == steps * n
+    _drive(pkg, ctx, env, tr, ref, 5, hook)
+    assert tr.n_sampleable() == ref.n_sampleable() == (steps + 5) * n
+    assert_batches_equal(tr.sample(), ref.sample(s, B))
+    tr.close(); env.close()
+
+
+def test_single_lane_matches_agent_jl_lengths_and_wraps(pkg, ctx):
+    """test/policies/agent.jl:27-34 (length 0 after the first state, 1 after the first transition) with lanes = 1, then far past the
+    capacity: the ring keeps the newest cap entries, overwritten entries leave the sampleable set (and the sum tree)."""
+    cap, B = 16, 64
+    slots = O.splitmix_states_fast(B, 1)
+    tr = pkg.Trajectory(ctx, 4, cap, lanes=1, batch_size=B, sampler_rng=slots, prioritized=True, default_priority=1.5)
+    ref = O.OracleTraj(4, 1, cap, True, 1.5)
+    rng = np.random.default_rng(0)
+    obs = rng.standard_normal((4, 1)).astype(np.float32)
+    tr.push_state(obs); ref.push_state(obs)
+    assert len(tr) == 0
+    for k in range(60):
+        term = np.uint8(1 if k % 7 == 6 else 0)
+        nxt = rng.standard_normal((4, 1)).astype(np.float32)
+        a, r, t = np.array([1 + k % 2], np.int32), np.array([k], np.float32), np.array([term], np.uint8)
+        tr.push(a, r, t, nxt); ref.push(a, r, t, nxt)
+        if k == 0:
+            assert len(tr) == 1
+        if term:                                                    # PreEpisodeStage of the next episode (the reference's reset + push)
+            s0 = rng.standard_normal((4, 1)).astype(np.float32)
+            tr.push_episode_start(s0, pending_only=True); ref.push_episode_start(s0, pending_only=True)
+        assert len(tr) == len(ref) <= cap and tr.n_sampleable() == ref.n_sampleable()
+        assert tr.total_priority() == ref.total_priority() == 1.5 * tr.n_sampleable()
+    s = slots.copy()
+    b = tr.sample(beta=0.4); rb = ref.sample(s, B, prioritized=True, beta=0.4)
+    assert_batches_equal(b, rb) and np.array_equal(b["priority"], rb["priority"])
+    assert set(b["reward"].astype(int)) <= set(range(60 - cap - 3, 60))     # only recent transitions survive
+    tr.close()
+
+
 def test_push_env_matches_host_push(pkg, ctx):
     n = 128
     env = pkg.B200VecEnv(ctx, "CartPole", n, O.splitmix_states_fast(n, 12), auto_reset=True)
@@ -78,8 +159,8 @@ def test_push_env_matches_host_push(pkg, ctx):
     for _ in range(30):
         env.act_random_()
         tr.push_env(env)
-        ref.push(env.last_action(), env.reward(), env.is_terminated(), env.state())
-    assert len(tr) == len(ref) == 30
+        ref.push(env.last_action(), env.reward(), env.flags(), env.state())     # flags: bit1 = the env has already auto-reset
+    assert np.array_equal(tr.lane_lengths(), ref.lane_lengths()) and tr.n_sampleable() == ref.n_sampleable() == 30 * n
     s = slots.copy()
     assert_batches_equal(tr.sample(), ref.sample(s, 64))
 

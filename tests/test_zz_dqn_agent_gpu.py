@@ -117,7 +117,9 @@ def test_dqn_agent_through_run(pkg, ctx, host_actions):
 
     hook = pkg.run(agent, env, pkg.StopAfterNSteps(steps), Spy() + pkg.BatchStepsPerEpisode(lanes))
     assert np.array_equal(first["a"], a0) and np.array_equal(first["rng"], ref_rng)
-    assert len(traj) == steps                                   # one frame per env step; the first state is frame 0
+    n_term = np.array([len(e) for e in hook[1][()]])
+    assert np.array_equal(traj.lane_lengths(), steps + n_term)   # steps + episodes - 1 per lane (RLCore/test/core/base.jl:20)
+    assert traj.n_sampleable() == steps * lanes
     assert explorer.step == 1 + steps * lanes                   # BatchExplorer: one inner step per column
     c = traj.controller
     assert c.n_inserted == steps and c.n_sampled == steps - 8 + 1
@@ -125,8 +127,9 @@ def test_dqn_agent_through_run(pkg, ctx, host_actions):
     assert np.array_equal(net.get(pkg.learners.NET_TARGET), net.get()) == ((c.n_sampled % 10) == 0)
     done = sum(len(s) for s in hook[1][()])
     assert done == env.episode_stats()["episodes"] > 0          # host hook and device-side statistics agree
-    with pytest.raises(RuntimeError):                            # re-entry on a non-empty ring is refused
-        pkg.run(agent, env, pkg.StopAfterNSteps(1))
+    pkg.run(agent, env, pkg.StopAfterNSteps(3))                  # re-entry on a filled ring: the forced reset starts an episode in every lane
+    assert traj.n_sampleable() == min((steps + 3), cap) * lanes or traj.n_sampleable() <= cap * lanes
+    assert (traj.lane_lengths() <= cap).all()
     # the ring holds what the env produced: replay the stored actions through the oracle env
     b = traj.sample(beta=0.4)
     assert set(np.unique(b["action"])) <= {1, 2} and np.isfinite(b["state"]).all()
@@ -197,3 +200,53 @@ def test_checkpoint_hook_writes_files(pkg, ctx, tmp_path):
     ck = pkg.checkpoint.load(hook.paths[1])
     assert ck["agent/counters"].tolist()[:2] == [10 % 4, 10 // 4] and ck["env/state"].shape == (4, 256)
     agent.close(); net.close(); env.close()
+
+
+def _dqn_objects(pkg, ctx, lanes, cap, B, seed):
+    env = pkg.B200VecEnv(ctx, "CartPole", lanes, O.splitmix_states_fast(lanes, seed), auto_reset=True)
+    desc = O.ac_desc(4, 64, 2)
+    net = pkg.Network(ctx, 4, 64, 2, O.glorot_params(desc, seed + 1, q_net=True), kind=pkg.KIND_Q)
+    traj = pkg.Trajectory(ctx, 4, cap, lanes=lanes, batch_size=B, sampler_rng=O.splitmix_states_fast(B, seed + 2), prioritized=True)
+    traj.controller = pkg.InsertSampleRatioController(ratio=1.0, threshold=4)
+    learner = pkg.DQNLearner(ctx, net, traj, pkg.dqn_config(target_update_freq=5))
+    explorer = pkg.EpsilonGreedyExplorer(0.05, kind="linear", eps_init=1.0, warmup_steps=lanes, decay_steps=20 * lanes)
+    policy = pkg.QBasedPolicy(ctx, learner, explorer, O.splitmix_states_fast(lanes, seed + 3), lanes)
+    return env, net, traj, policy, pkg.Agent(policy, traj)
+
+
+def test_dqn_checkpoint_resume_is_bit_identical(pkg, ctx):
+    """The replay run's whole state — env, Q-network + target + Adam state + update counter, the ring with its per-lane bookkeeping and
+    sum tree, sampler / explorer streams, explorer step, controller counters — through checkpoint_replay / restore_replay: a run that
+    is stopped, rebuilt from different seeds, restored and continued must equal the uninterrupted one bit for bit."""
+    lanes, cap, B = 64, 40, 128
+    ck_mod = pkg.checkpoint
+
+    def continue_(env, agent):
+        env_steps = 0
+        for _ in range(30):                                     # the stage loop of run() without the forced reset of a new run
+            agent.push(pkg.core.PreActStage, env)
+            agent.act_fused(env) if isinstance(agent.plan(env), pkg.core.FusedAction) else None
+            agent.push(pkg.core.PostActStage, env)
+            agent.optimise(pkg.core.PostActStage)
+            env_steps += 1
+        return env_steps
+
+    env, net, traj, policy, agent = _dqn_objects(pkg, ctx, lanes, cap, B, 50)
+    pkg.run(agent, env, pkg.StopAfterNSteps(25), pkg.EmptyHook())
+    ck = ck_mod.checkpoint_replay(env, net, agent)
+    continue_(env, agent)
+    final_a = ck_mod.checkpoint_replay(env, net, agent)
+
+    env2, net2, traj2, policy2, agent2 = _dqn_objects(pkg, ctx, lanes, cap, B, 999)
+    pkg.run(agent2, env2, pkg.StopAfterNSteps(3), pkg.EmptyHook())
+    ck_mod.restore_replay(ck, env2, net2, agent2)
+    back = ck_mod.checkpoint_replay(env2, net2, agent2)
+    assert sorted(back) == sorted(ck)
+    for k in ck:
+        assert np.array_equal(np.asarray(back[k]), np.asarray(ck[k])), k
+    continue_(env2, agent2)
+    final_b = ck_mod.checkpoint_replay(env2, net2, agent2)
+    for k in final_a:
+        assert np.array_equal(np.asarray(final_a[k]), np.asarray(final_b[k])), k
+    for o in (policy, policy2, traj, traj2, net, net2, env, env2):
+        o.close()
