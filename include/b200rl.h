@@ -119,8 +119,9 @@ typedef struct {   /* MountainCarEnvParams{T}: MountainCarEnv.jl:3-40 */
  * (CartPoleEnv.jl:74-79, PendulumEnv.jl:41-66, MountainCarEnv.jl:67-81) and the absent
  * `MultiThreadEnv([...])`.  `rng_state` = (4, N) uint64 host array: raw Xoshiro state per
  * env (Julia side: `Xoshiro(seed_i)` fields s0..s3).  Like the reference constructors it
- * performs one reset!() per env.  Supported: CartPole f32|f64 discrete; Pendulum f32
- * continuous|discrete; MountainCar f32 discrete; the two *_CONTINUOUS kinds f32. */
+ * performs one reset!() per env.  Supported: CartPole f32|f64 discrete, f32 continuous; Pendulum f32|f64
+ * continuous|discrete; MountainCar f32|f64 discrete|continuous (T = Float64 is the reference constructors' default,
+ * PendulumEnv.jl:42, MountainCarEnv.jl:67; the learners / trajectory take Float32 envs). */
 int b200rl_env_create(b200rl_ctx* ctx, int kind, int dtype, int64_t n_envs, const void* params,
                       const uint64_t* rng_state, b200rl_env** out);
 int b200rl_env_destroy(b200rl_env* env);
@@ -138,7 +139,7 @@ int b200rl_env_seed(b200rl_env* env, const uint64_t* rng_state);
 int b200rl_env_reset(b200rl_env* env, int force_all);
 /* RLBase.act!(env, a) for all N envs in one kernel (CartPoleEnv.jl:112-140,
  * PendulumEnv.jl:94-118, MountainCarEnv.jl:113-135).  actions: int32 (N,) 1-based for
- * discrete spaces, T (N,) for Pendulum continuous.  auto_reset != 0 fuses the soft reset of
+ * discrete spaces, T (N,) for a continuous action space (Float64 actions for a Float64 env).  auto_reset != 0 fuses the soft reset of
  * envs that just terminated into the same launch (reward/terminal keep the terminating
  * step's values; state/obs become the fresh episode's).
  * actions_on_device: 0 = host buffer borrowed for the call (synchronises before returning), 1 = device pointer,

@@ -112,9 +112,10 @@ inline PendulumParams pendulum_default_params() {
     return PendulumParams{8, 2, 10, 1, 1, (double)0.05f, 200, 3, 1};
 }
 
-// Float32 only: Float64 Pendulum is in no BASELINE config (needs the double rem_pio2 tree).
-struct Pendulum {
-    using T = float;
+// T = Float32 | Float64 (PendulumEnv.jl:42: the constructor's default is Float64).  Written so that the Float32 instantiation keeps
+// Julia's promotion points (2*pi, mod() and the cost terms are Float64) and the Float64 one is all-double.
+template <class T_> struct PendulumT {
+    using T = T_;
     static constexpr int NS = 2, NOBS = 3;
     T max_speed, max_torque, g, m, l, dt;
     int64_t max_steps, n_actions;
@@ -125,17 +126,17 @@ struct Pendulum {
     int64_t t = 0;
     jl::Xoshiro rng;
 
-    Pendulum(const PendulumParams& p, jl::Xoshiro r, bool do_reset = true) : state(2, 0.f), rng(r) {
+    PendulumT(const PendulumParams& p, jl::Xoshiro r, bool do_reset = true) : state(2, (T)0), rng(r) {
         max_speed = (T)p.max_speed; max_torque = (T)p.max_torque; g = (T)p.g; m = (T)p.m;
         l = (T)p.l; dt = (T)p.dt; max_steps = p.max_steps; n_actions = p.n_actions;
         continuous = p.continuous != 0;
         if (do_reset) reset();  // PendulumEnv.jl:64
     }
     void reset() {  // PendulumEnv.jl:84-92; two scalar rand(rng, T) draws
-        T u1 = jl::rand_f32(rng);
-        state[0] = (T)((2 * jl::PI_D) * (double)(u1 - 1.0f));  // 2*pi is Float64
-        T u2 = jl::rand_f32(rng);
-        state[1] = 2.0f * (u2 - 1.0f);
+        T u1 = jl::rand_scalar<T>(rng);
+        state[0] = (T)((2 * jl::PI_D) * (double)(u1 - (T)1));  // 2*pi is Float64
+        T u2 = jl::rand_scalar<T>(rng);
+        state[1] = (T)2 * (u2 - (T)1);
         action = 0; t = 0; done = false; rew = 0;
     }
     // continuous: a in -2.0..2.0 (PendulumEnv.jl:73,95,122)
@@ -157,11 +158,11 @@ struct Pendulum {
         t += 1;
         T th = state[0], thdot = state[1];
         a = jl::jclamp(a, -max_torque, max_torque);
-        // angle_normalize: Float32 + pi -> Float32; mod(Float32, Float64) -> Float64
+        // angle_normalize: T + pi -> T; mod(T, Float64) -> Float64
         double an = jl::jmod((double)(th + (T)jl::PI_D), 2 * jl::PI_D) - jl::PI_D;
         double costs = (an * an + 0.1 * (double)(thdot * thdot)) + 0.001 * (double)(a * a);
-        T newthdot = thdot + ((((-3.0f * g) / (2.0f * l)) * jl::jsin(th + (T)jl::PI_D)) +
-                              ((3.0f * a) / (m * (l * l)))) * dt;
+        T newthdot = thdot + (((((T)-3 * g) / ((T)2 * l)) * jl::jsin(th + (T)jl::PI_D)) +
+                              (((T)3 * a) / (m * (l * l)))) * dt;
         th = th + newthdot * dt;
         newthdot = jl::jclamp(newthdot, -max_speed, max_speed);
         state[0] = th; state[1] = newthdot;
@@ -173,6 +174,7 @@ struct Pendulum {
         out[0] = jl::jsin(state[0]); out[1] = jl::jcos(state[0]); out[2] = state[1];
     }
 };
+using Pendulum = PendulumT<float>;
 
 struct MountainCarParams {  // MountainCarEnvParams{T}, MountainCarEnv.jl:3-12
     double min_pos, max_pos, max_speed, goal_pos, goal_velocity, power, gravity;
@@ -188,10 +190,11 @@ inline MountainCarParams mountaincar_continuous_default_params() {  // MountainC
     return MountainCarParams{(T)-1.2, (T)0.6, (T)0.07, (T)0.45, (T)0.0, (T)0.0015, (T)0.0025, 200};
 }
 
-// Float32; discrete actions (1..3) or, for ContinuousMountainCarEnv, a Float32 force in -1.0..1.0.
-struct MountainCar {
-    float action_f = 0;
-    using T = float;
+// T = Float32 | Float64 (MountainCarEnv.jl:67: the default is Float64); discrete actions (1..3) or, for ContinuousMountainCarEnv,
+// a force of type T in -1.0..1.0.
+template <class T_> struct MountainCarT {
+    using T = T_;
+    T action_f = 0;
     static constexpr int NS = 2, NOBS = 2, NACT = 3;
     T min_pos, max_pos, max_speed, goal_pos, goal_velocity, power, gravity;
     int64_t max_steps;
@@ -201,14 +204,14 @@ struct MountainCar {
     int64_t t = 0;
     jl::Xoshiro rng;
 
-    MountainCar(const MountainCarParams& p, jl::Xoshiro r, bool do_reset = true) : state(2, 0.f), rng(r) {
+    MountainCarT(const MountainCarParams& p, jl::Xoshiro r, bool do_reset = true) : state(2, (T)0), rng(r) {
         min_pos = (T)p.min_pos; max_pos = (T)p.max_pos; max_speed = (T)p.max_speed;
         goal_pos = (T)p.goal_pos; goal_velocity = (T)p.goal_velocity; power = (T)p.power;
         gravity = (T)p.gravity; max_steps = p.max_steps;
         if (do_reset) reset();  // MountainCarEnv.jl:79
     }
     void reset() {  // MountainCarEnv.jl:99-105 (0.2 and 0.6 are Float64 literals)
-        T u = jl::rand_f32(rng);
+        T u = jl::rand_scalar<T>(rng);
         state[0] = (T)(0.2 * (double)u - 0.6);
         state[1] = 0;
         done = false; t = 0;
@@ -219,8 +222,8 @@ struct MountainCar {
         step((int)a - 2);
         return true;
     }
-    bool act_continuous(float a) {  // MountainCarEnv.jl:107-111 with a::Float32: all-Float32 arithmetic
-        if (!(a >= -1.0f && a <= 1.0f)) return false;
+    bool act_continuous(T a) {  // MountainCarEnv.jl:107-111 with a::T: all-T arithmetic
+        if (!(a >= (T)-1 && a <= (T)1)) return false;
         action_f = a;
         step_force(a);
         return true;
@@ -229,7 +232,7 @@ struct MountainCar {
     void step_force(T force) {  // MountainCarEnv.jl:119-135
         t += 1;
         T x = state[0], v = state[1];
-        v = v + (force * power + jl::jcos(3.0f * x) * (-gravity));
+        v = v + (force * power + jl::jcos((T)3 * x) * (-gravity));
         v = jl::jclamp(v, -max_speed, max_speed);
         x = x + v;
         x = jl::jclamp(x, min_pos, max_pos);
@@ -240,5 +243,6 @@ struct MountainCar {
     T reward() const { return done ? (T)0 : (T)-1; }  // MountainCarEnv.jl:95
     void obs(T* out) const { out[0] = state[0]; out[1] = state[1]; }
 };
+using MountainCar = MountainCarT<float>;
 
 }  // namespace oracle

@@ -137,14 +137,21 @@ static inline double cos_kernel_f64(double hi, double lo) {
 static inline uint32_t highword(double x) {
     uint64_t b; std::memcpy(&b, &x, 8); return (uint32_t)(b >> 32);
 }
-// cody_waite_ext_pio2 (medium range, |x| < 2^20*pi/2).  The reference's small-|x|
-// special cases are folded into this general path (UNPINNED beyond |x| >= pi/4: only
-// reachable when a caller keeps stepping a finished Float64 CartPole).
-static inline int rem_pio2_f64(double x, double* y1o, double* y2o) {
+// cody_waite_2c_pio2(x, fn, n) (rem_pio2.jl): two-constant reduction for |x| <= 9pi/4 away from multiples of pi/2
+static inline int cody_waite_2c(double x, double fn, int n, double* y1o, double* y2o) {
+    const double pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11;
+    double z = muladd(-fn, pio2_1, x);
+    double w = fn * pio2_1t;
+    double y1 = z - w;
+    *y1o = y1;
+    *y2o = (z - y1) - w;
+    return n;
+}
+// cody_waite_ext_pio2 (medium range, |x| < 2^20*pi/2): up to three rounds
+static inline int cody_waite_ext(double x, uint32_t xhp, double* y1o, double* y2o) {
     const double pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11;
     const double pio2_2 = 6.07710050630396597660e-11, pio2_2t = 2.02226624879595063154e-21;
     const double pio2_3 = 2.02226624871116645580e-21, pio2_3t = 8.47842766036889956997e-32;
-    uint32_t xhp = highword(x) & 0x7fffffffu;
     double fn = std::nearbyint(x * 6.36619772367581382433e-01);
     double r = muladd(-fn, pio2_1, x);
     double w = fn * pio2_1t;
@@ -169,6 +176,28 @@ static inline int rem_pio2_f64(double x, double* y1o, double* y2o) {
     *y1o = y1;
     *y2o = (r - y1) - w;
     return (int)(long long)fn;
+}
+// rem_pio2_kernel(x::Float64) (base/special/rem_pio2.jl, a port of msun e_rem_pio2.c): the decision tree on the high word —
+// |x| <= 9pi/4 takes the two-constant scheme with fn = +-1..4 unless x is close to a multiple of pi/2; everything else up to
+// 2^20 pi/2 the extended scheme.  Payne-Hanek beyond is not restated (no env can reach it).  UNPINNED like the rest of this file
+// (recalled from the Julia sources; the constants are msun's, pinned by tests/test_oracle_msun_constants.py).
+static inline int rem_pio2_f64(double x, double* y1o, double* y2o) {
+    const uint32_t xhp = highword(x) & 0x7fffffffu;
+    const bool pos = x > 0.0;
+    if (xhp <= 0x400f6a7au) {                      // |x| ~<= 5pi/4
+        if ((xhp & 0xfffffu) == 0x921fbu) return cody_waite_ext(x, xhp, y1o, y2o);
+        if (xhp <= 0x4002d97cu) return pos ? cody_waite_2c(x, 1.0, 1, y1o, y2o) : cody_waite_2c(x, -1.0, -1, y1o, y2o);
+        return pos ? cody_waite_2c(x, 2.0, 2, y1o, y2o) : cody_waite_2c(x, -2.0, -2, y1o, y2o);
+    }
+    if (xhp <= 0x401c463bu) {                      // |x| ~<= 9pi/4
+        if (xhp <= 0x4015fdbcu) {                  // |x| ~<= 7pi/4
+            if (xhp == 0x4012d97cu) return cody_waite_ext(x, xhp, y1o, y2o);
+            return pos ? cody_waite_2c(x, 3.0, 3, y1o, y2o) : cody_waite_2c(x, -3.0, -3, y1o, y2o);
+        }
+        if (xhp == 0x401921fbu) return cody_waite_ext(x, xhp, y1o, y2o);
+        return pos ? cody_waite_2c(x, 4.0, 4, y1o, y2o) : cody_waite_2c(x, -4.0, -4, y1o, y2o);
+    }
+    return cody_waite_ext(x, xhp, y1o, y2o);
 }
 static inline double sin64(double x) {
     double ax = std::fabs(x);

@@ -88,7 +88,7 @@ void orc_cartpole_default_params(int dtype, double* out /*11*/) {
 }
 
 // ---- vector env ----------------------------------------------------------------------
-// kind: 0 CartPole, 1 Pendulum, 2 MountainCar, 3 continuous CartPole, 4 ContinuousMountainCar; dtype: 0 f32, 1 f64 (CartPole only)
+// kind: 0 CartPole, 1 Pendulum, 2 MountainCar, 3 continuous CartPole, 4 ContinuousMountainCar; dtype: 0 f32, 1 f64 (not for the continuous CartPole)
 // params: CartPole 11 doubles (above order); Pendulum 9 (max_speed,max_torque,g,m,l,dt,
 // max_steps,n_actions,continuous); MountainCar 8 (min_pos,max_pos,max_speed,goal_pos,
 // goal_velocity,power,gravity,max_steps).
@@ -99,16 +99,19 @@ void* orc_vecenv_create(int kind, int dtype, int64_t N, const double* q, const u
         return (VecEnvBase*)new VecCartPoleF32(N, p, rng);
     } else if (kind == 1) {
         PendulumParams p{q[0], q[1], q[2], q[3], q[4], q[5], (int64_t)q[6], (int64_t)q[7], (int32_t)q[8]};
+        if (dtype == 1) return p.continuous ? (VecEnvBase*)new VecPendulum64C(N, p, rng) : (VecEnvBase*)new VecPendulum64D(N, p, rng);
         if (p.continuous) return (VecEnvBase*)new VecPendulumC(N, p, rng);
         return (VecEnvBase*)new VecPendulumD(N, p, rng);
     } else if (kind == 2) {
         MountainCarParams p{q[0], q[1], q[2], q[3], q[4], q[5], q[6], (int64_t)q[7]};
+        if (dtype == 1) return (VecEnvBase*)new VecMountainCar64(N, p, rng);
         return (VecEnvBase*)new VecMountainCar(N, p, rng);
     } else if (kind == 3) {   // CartPoleEnv(continuous = true), Float32
         CartPoleParams p{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], (int64_t)q[10]};
         return (VecEnvBase*)new VecCartPoleC(N, p, rng);
     } else if (kind == 4) {   // ContinuousMountainCarEnv, Float32
         MountainCarParams p{q[0], q[1], q[2], q[3], q[4], q[5], q[6], (int64_t)q[7]};
+        if (dtype == 1) return (VecEnvBase*)new VecMountainCar64C(N, p, rng);
         return (VecEnvBase*)new VecMountainCarC(N, p, rng);
     }
     return nullptr;

@@ -122,6 +122,31 @@ using VecPendulumD = VecEnv<Pendulum, float, int32_t>;   // discrete torque inde
 using VecMountainCar = VecEnv<MountainCar, float, int32_t>;
 using VecCartPoleC = VecEnv<CartPole<float, true>, float, float>;   // CartPoleEnv(continuous = true)
 using VecMountainCarC = VecEnv<MountainCar, float, float>;          // ContinuousMountainCarEnv
+// T = Float64 (the reference constructors' default for Pendulum / MountainCar); a continuous action is a Float64 then
+struct Pendulum64C : PendulumT<double> { using PendulumT<double>::PendulumT; };
+struct Pendulum64D : PendulumT<double> { using PendulumT<double>::PendulumT; };
+struct MountainCar64 : MountainCarT<double> { using MountainCarT<double>::MountainCarT; };
+struct MountainCar64C : MountainCarT<double> { using MountainCarT<double>::MountainCarT; };
+using VecPendulum64C = VecEnv<Pendulum64C, double, double>;
+using VecPendulum64D = VecEnv<Pendulum64D, double, int32_t>;
+using VecMountainCar64 = VecEnv<MountainCar64, double, int32_t>;
+using VecMountainCar64C = VecEnv<MountainCar64C, double, double>;
+template <> inline void VecPendulum64C::action_out(const Pendulum64C& e, void* d, int64_t i) { ((double*)d)[i] = e.action; }
+template <> inline void VecPendulum64D::action_out(const Pendulum64D& e, void* d, int64_t i) { ((float*)d)[i] = (float)e.action; }
+template <> inline void VecMountainCar64::action_out(const MountainCar64& e, void* d, int64_t i) { ((int32_t*)d)[i] = (int32_t)e.action; }
+template <> inline void VecMountainCar64C::action_out(const MountainCar64C& e, void* d, int64_t i) { ((double*)d)[i] = e.action_f; }
+template <> inline bool VecPendulum64C::do_act(Pendulum64C& e, double a) { return e.act_continuous(a); }
+template <> inline bool VecPendulum64D::do_act(Pendulum64D& e, int32_t a) { return e.act_discrete(a); }
+template <> inline bool VecMountainCar64::do_act(MountainCar64& e, int32_t a) { return e.act(a); }
+template <> inline bool VecMountainCar64C::do_act(MountainCar64C& e, double a) { return e.act_continuous(a); }
+template <> inline int64_t VecPendulum64C::n_random_actions(const Pendulum64C& e) { return e.n_actions; }
+template <> inline int64_t VecPendulum64D::n_random_actions(const Pendulum64D& e) { return e.n_actions; }
+template <> inline int64_t VecMountainCar64::n_random_actions(const MountainCar64&) { return 3; }
+template <> inline int64_t VecMountainCar64C::n_random_actions(const MountainCar64C&) { return 0; }
+template <> inline void VecPendulum64C::do_act_discrete(Pendulum64C& e, int64_t a) { e.act_discrete(a); }
+template <> inline void VecPendulum64D::do_act_discrete(Pendulum64D& e, int64_t a) { e.act_discrete(a); }
+template <> inline void VecMountainCar64::do_act_discrete(MountainCar64& e, int64_t a) { e.act(a); }
+template <> inline void VecMountainCar64C::do_act_discrete(MountainCar64C&, int64_t) {}
 
 template <> inline void VecCartPoleF32::action_out(const CartPole<float>& e, void* d, int64_t i) { ((int32_t*)d)[i] = (int32_t)e.action; }
 template <> inline void VecCartPoleF64::action_out(const CartPole<double>& e, void* d, int64_t i) { ((int32_t*)d)[i] = (int32_t)e.action; }

@@ -29,7 +29,7 @@ def _env_get(env, field):
     spec = {
         L.FIELD_STATE: ((_NS[env.kind], n), env.T), L.FIELD_OBS: ((_NOBS[env.kind], n), env.T),
         L.FIELD_REWARD: ((n,), env.T), L.FIELD_FLAGS: ((n,), np.uint8), L.FIELD_T: ((n,), np.int32), L.FIELD_RNG: ((n, 4), np.uint64),
-        L.FIELD_ACTION: ((n,), np.float32 if env.continuous else np.int32), L.FIELD_EPISODE_RETURN: ((n,), np.float32),
+        L.FIELD_ACTION: ((n,), env.act_dtype), L.FIELD_EPISODE_RETURN: ((n,), np.float32),
         L.FIELD_EPISODE_STATS: ((4,), np.float64),
     }[field]
     order = "C" if field == L.FIELD_RNG else "F"

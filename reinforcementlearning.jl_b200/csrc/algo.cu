@@ -30,6 +30,7 @@ int b200rl_comm_allreduce_internal(b200rl_ctx* ctx, void* buf, int64_t n, int is
 int b200rl_comm_world(b200rl_ctx* ctx);
 int b200rl_env_internal_kind(const b200rl_env* e);
 int b200rl_env_internal_max_timeout(const b200rl_env* e);
+int b200rl_env_internal_dtype(const b200rl_env* e);
 void b200rl_env_internal_add_steps(b200rl_env* e, uint64_t n);
 static bool fused_rollout_enabled() {   // B200RL_FUSED_ROLLOUT=0: step through plan!/act! launches instead (same results)
     static int v = -1;
@@ -435,6 +436,7 @@ int b200rl_onpolicy_create(b200rl_ctx* ctx, b200rl_net* net, b200rl_env* env, co
     REQUIRE(net && env && cfg && policy_rng && out, B200RL_ERR_INVALID, "null argument");
     REQUIRE(net->kind != 2, B200RL_ERR_INVALID, "needs an actor-critic network");
     REQUIRE(net->ctx == ctx && b200rl_env_internal_ctx(env) == ctx, B200RL_ERR_INVALID, "net/env belong to another ctx");
+    REQUIRE(b200rl_env_internal_dtype(env) == B200RL_F32, B200RL_ERR_UNSUPPORTED, "the learners read Float32 observations: construct the env with T = Float32");
     REQUIRE(cfg->update_freq >= 1 && cfg->n_epochs >= 1 && cfg->n_microbatches >= 1, B200RL_ERR_INVALID, "bad config");
     int nobs = b200rl_env_internal_nobs(env);
     REQUIRE(nobs == net->actor.in, B200RL_ERR_INVALID, "network input width != observation width");
@@ -879,6 +881,7 @@ int b200rl_onpolicy_time_kernel(b200rl_onpolicy* a, int which, int reps, float* 
 int b200rl_traj_push_env(b200rl_traj* t, b200rl_env* env, int first_state_only) {
     REQUIRE(t && env, B200RL_ERR_INVALID, "null argument");
     REQUIRE(b200rl_traj_internal_lanes(t) == b200rl_env_internal_n(env), B200RL_ERR_INVALID, "trajectory lanes != number of envs");
+    REQUIRE(b200rl_env_internal_dtype(env) == B200RL_F32, B200RL_ERR_UNSUPPORTED, "the trajectory stores Float32 states: construct the env with T = Float32");
     const float* obs = (const float*)env_field(env, B200RL_FIELD_OBS);
     if (first_state_only == 2) return b200rl_traj_push_episode_start(t, obs, 1, 1);   // only the lanes whose episode has ended (soft reset)
     if (first_state_only) return b200rl_traj_push_state(t, obs, 1);

@@ -144,7 +144,10 @@ struct b200rl_env {
         CartPoleD<double>::P cp64;
         PendP pend;
         MountainCarD<false>::P mc;
+        PendPT<double> pend64;
+        MountainCarPT<double> mc64;
     } p;
+    size_t asize;   // bytes per stored action (8 for a Float64 continuous action space, else 4)
     EnvArrays a;
     uint64_t steps_launched;
 };
@@ -180,9 +183,17 @@ static int dispatch_step(b200rl_env* e, const void* actions, bool random, bool a
             }
             return launch_step<CartPoleD<float>>(e, e->p.cp32, actions, random, auto_reset);
         case B200RL_ENV_PENDULUM:
+            if (e->dtype == B200RL_F64) {
+                if (e->continuous && !random) return launch_step<PendulumD<true, double>>(e, e->p.pend64, actions, random, auto_reset);
+                return launch_step<PendulumD<false, double>>(e, e->p.pend64, actions, random, auto_reset);
+            }
             if (e->continuous && !random) return launch_step<PendulumD<true>>(e, e->p.pend, actions, random, auto_reset);
             return launch_step<PendulumD<false>>(e, e->p.pend, actions, random, auto_reset);
         case B200RL_ENV_MOUNTAINCAR:
+            if (e->dtype == B200RL_F64) {
+                if (e->continuous && !random) return launch_step<MountainCarD<true, double>>(e, e->p.mc64, actions, random, auto_reset);
+                return launch_step<MountainCarD<false, double>>(e, e->p.mc64, actions, random, auto_reset);
+            }
             if (e->continuous && !random) {
                 MountainCarD<true>::P q;
                 static_assert(sizeof(q) == sizeof(e->p.mc), "same params layout");
@@ -203,8 +214,14 @@ static int dispatch_reset(b200rl_env* e, int force) {
                 return launch_reset<CartPoleD<float, true>>(e, q, force);
             }
             return launch_reset<CartPoleD<float>>(e, e->p.cp32, force);
-        case B200RL_ENV_PENDULUM: return launch_reset<PendulumD<true>>(e, e->p.pend, force);
-        case B200RL_ENV_MOUNTAINCAR: return launch_reset<MountainCarD<false>>(e, e->p.mc, force);
+        case B200RL_ENV_PENDULUM:
+            if (e->dtype == B200RL_F64)
+                return e->continuous ? launch_reset<PendulumD<true, double>>(e, e->p.pend64, force) : launch_reset<PendulumD<false, double>>(e, e->p.pend64, force);
+            return launch_reset<PendulumD<true>>(e, e->p.pend, force);
+        case B200RL_ENV_MOUNTAINCAR:
+            if (e->dtype == B200RL_F64)
+                return e->continuous ? launch_reset<MountainCarD<true, double>>(e, e->p.mc64, force) : launch_reset<MountainCarD<false, double>>(e, e->p.mc64, force);
+            return launch_reset<MountainCarD<false>>(e, e->p.mc, force);
     }
     return B200RL_ERR_INVALID;
 }
@@ -218,7 +235,7 @@ static size_t field_bytes(const b200rl_env* e, int field) {
         case B200RL_FIELD_TERMINAL: case B200RL_FIELD_FLAGS: return N;
         case B200RL_FIELD_T: return N * 4;
         case B200RL_FIELD_RNG: return N * 32;
-        case B200RL_FIELD_ACTION: return N * 4;
+        case B200RL_FIELD_ACTION: return N * e->asize;
         case B200RL_FIELD_EPISODE_RETURN: return N * 4;
         case B200RL_FIELD_EPISODE_STATS: return 4 * sizeof(double);
     }
@@ -248,7 +265,7 @@ static int env_alloc(b200rl_env* e) {
     CUDA_TRY(cudaMalloc(&e->a.flags, N));
     CUDA_TRY(cudaMalloc(&e->a.t, N * 4));
     CUDA_TRY(cudaMalloc(&e->a.rng, N * 32));
-    CUDA_TRY(cudaMalloc(&e->a.action, N * 4));
+    CUDA_TRY(cudaMalloc(&e->a.action, N * 8));
     CUDA_TRY(cudaMalloc(&e->a.ep_ret, N * 4));
     CUDA_TRY(cudaMalloc(&e->a.stats, 4 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&e->a.err, sizeof(int)));
@@ -258,7 +275,7 @@ static int env_alloc(b200rl_env* e) {
     CUDA_TRY(cudaMemsetAsync(e->a.reward, 0, N * e->tsize, st));
     CUDA_TRY(cudaMemsetAsync(e->a.flags, 0, N, st));
     CUDA_TRY(cudaMemsetAsync(e->a.t, 0, N * 4, st));
-    CUDA_TRY(cudaMemsetAsync(e->a.action, 0, N * 4, st));
+    CUDA_TRY(cudaMemsetAsync(e->a.action, 0, N * 8, st));
     CUDA_TRY(cudaMemsetAsync(e->a.ep_ret, 0, N * 4, st));
     CUDA_TRY(cudaMemsetAsync(e->a.stats, 0, 4 * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(e->a.err, 0, sizeof(int), st));
@@ -274,12 +291,11 @@ int b200rl_env_create(b200rl_ctx* ctx, int kind, int dtype, int64_t n_envs, cons
     TRY(ctx_bind(ctx));
     REQUIRE(out && rng_state, B200RL_ERR_INVALID, "null out / rng_state");
     REQUIRE(n_envs > 0, B200RL_ERR_INVALID, "n_envs must be positive");
-    REQUIRE(dtype == B200RL_F32 || (dtype == B200RL_F64 && (kind == B200RL_ENV_CARTPOLE || kind == B200RL_ENV_CARTPOLE_CONTINUOUS)), B200RL_ERR_UNSUPPORTED,
-            "Float64 is supported for CartPole only (no BASELINE config uses Float64 Pendulum/MountainCar)");
+    REQUIRE(dtype == B200RL_F32 || dtype == B200RL_F64, B200RL_ERR_INVALID, "dtype must be B200RL_F32 or B200RL_F64");
     b200rl_env* e = new b200rl_env();
     memset(&e->a, 0, sizeof e->a);
     bool cont_kind = kind == B200RL_ENV_CARTPOLE_CONTINUOUS || kind == B200RL_ENV_MOUNTAINCAR_CONTINUOUS;
-    if (cont_kind && dtype != B200RL_F32) { delete e; REQUIRE(false, B200RL_ERR_UNSUPPORTED, "continuous-action variants are Float32 only"); }
+    if (kind == B200RL_ENV_CARTPOLE_CONTINUOUS && dtype != B200RL_F32) { delete e; REQUIRE(false, B200RL_ERR_UNSUPPORTED, "CartPoleEnv(continuous = true) is Float32 only"); }
     if (kind == B200RL_ENV_CARTPOLE_CONTINUOUS) kind = B200RL_ENV_CARTPOLE;
     if (kind == B200RL_ENV_MOUNTAINCAR_CONTINUOUS) kind = B200RL_ENV_MOUNTAINCAR;
     e->ctx = ctx; e->kind = kind; e->dtype = dtype; e->N = n_envs; e->continuous = cont_kind;
@@ -306,8 +322,13 @@ int b200rl_env_create(b200rl_ctx* ctx, int kind, int dtype, int64_t n_envs, cons
                                           : b200rl_pendulum_params{8, 2, 10, 1, 1, (float)0.05, 200, 3, 1};
         REQUIRE(d.continuous || d.n_actions >= 2, B200RL_ERR_INVALID, "n_actions must be >= 2");
         e->ns = 2; e->nobs = 3; e->continuous = d.continuous != 0;
-        e->p.pend = PendP{(float)d.max_speed, (float)d.max_torque, (float)d.g, (float)d.m, (float)d.l, (float)d.dt,
-                                        (int)d.max_steps, (int)d.n_actions};
+        if (dtype == B200RL_F64) {   // PendulumEnv() default T = Float64 (PendulumEnv.jl:42): dt = Float64(0.05) unless the caller says otherwise
+            if (!params) d.dt = 0.05;
+            e->p.pend64 = PendPT<double>{d.max_speed, d.max_torque, d.g, d.m, d.l, d.dt, (int)d.max_steps, (int)d.n_actions};
+        } else {
+            e->p.pend = PendP{(float)d.max_speed, (float)d.max_torque, (float)d.g, (float)d.m, (float)d.l, (float)d.dt,
+                              (int)d.max_steps, (int)d.n_actions};
+        }
     } else if (kind == B200RL_ENV_MOUNTAINCAR) {
         // ContinuousMountainCarEnv defaults: goal_pos = 0.45, power = 0.0015 (MountainCarEnv.jl:73-74)
         b200rl_mountaincar_params d = params ? *(const b200rl_mountaincar_params*)params
@@ -316,12 +337,19 @@ int b200rl_env_create(b200rl_ctx* ctx, int kind, int dtype, int64_t n_envs, cons
                                                   : b200rl_mountaincar_params{(float)-1.2, (float)0.6, (float)0.07, (float)0.5, 0.0,
                                                                               (float)0.001, (float)0.0025, 200};
         e->ns = 2; e->nobs = 2;
-        e->p.mc = MountainCarD<false>::P{(float)d.min_pos, (float)d.max_pos, (float)d.max_speed, (float)d.goal_pos, (float)d.goal_velocity,
-                                  (float)d.power, (float)d.gravity, (int)d.max_steps};
+        if (dtype == B200RL_F64) {   // MountainCarEnv() default T = Float64 (MountainCarEnv.jl:67): the Float64 literals of :19-29
+            if (!params) d = cont_kind ? b200rl_mountaincar_params{-1.2, 0.6, 0.07, 0.45, 0.0, 0.0015, 0.0025, 200}
+                                       : b200rl_mountaincar_params{-1.2, 0.6, 0.07, 0.5, 0.0, 0.001, 0.0025, 200};
+            e->p.mc64 = MountainCarPT<double>{d.min_pos, d.max_pos, d.max_speed, d.goal_pos, d.goal_velocity, d.power, d.gravity, (int)d.max_steps};
+        } else {
+            e->p.mc = MountainCarD<false>::P{(float)d.min_pos, (float)d.max_pos, (float)d.max_speed, (float)d.goal_pos, (float)d.goal_velocity,
+                                             (float)d.power, (float)d.gravity, (int)d.max_steps};
+        }
     } else {
         delete e;
         REQUIRE(false, B200RL_ERR_INVALID, "unknown env kind");
     }
+    e->asize = (e->continuous && dtype == B200RL_F64) ? 8 : 4;
     int s = env_alloc(e);
     if (s != B200RL_OK) { b200rl_env_destroy(e); return s; }
     CUDA_TRY(cudaMemcpyAsync(e->a.rng, rng_state, (size_t)n_envs * 32, cudaMemcpyHostToDevice, ctx->stream));
@@ -383,8 +411,8 @@ int b200rl_env_step(b200rl_env* e, const void* actions, int actions_on_device, i
     const void* dact = actions;
     if (actions_on_device != 1) {   // 0: pageable / borrowed host buffer, 2: pinned host buffer that stays untouched until the next sync
         void* stage;
-        TRY(ctx_scratch(e->ctx, (size_t)e->N * 4, &stage));
-        CUDA_TRY(cudaMemcpyAsync(stage, actions, (size_t)e->N * 4, cudaMemcpyHostToDevice, e->ctx->stream));
+        TRY(ctx_scratch(e->ctx, (size_t)e->N * e->asize, &stage));
+        CUDA_TRY(cudaMemcpyAsync(stage, actions, (size_t)e->N * e->asize, cudaMemcpyHostToDevice, e->ctx->stream));
         dact = stage;
     }
     e->steps_launched += 1;
@@ -489,6 +517,7 @@ int b200rl_env_internal_view(b200rl_env* e, envdev::EnvView* out) {
 }
 void b200rl_env_internal_add_steps(b200rl_env* e, uint64_t n) { e->steps_launched += n; }
 int b200rl_env_internal_max_timeout(const b200rl_env* e) { return e->a.max_timeout; }
+int b200rl_env_internal_dtype(const b200rl_env* e) { return e->dtype; }
 int64_t b200rl_env_internal_n(const b200rl_env* e) { return e->N; }
 int b200rl_env_internal_kind(const b200rl_env* e) { return e->kind; }
 int b200rl_env_internal_nobs(const b200rl_env* e) { return e->nobs; }

@@ -116,110 +116,119 @@ template <class T, bool CONT> __device__ __forceinline__ void CartPoleD<T, CONT>
 }
 
 // ------------------------------------------------------------------ Pendulum ----------
-struct PendP { float max_speed, max_torque, g, m, l, dt; int max_steps; int n_actions; };
-template <bool CONT> struct PendulumD {
-    using real = float;
-    using act_t = typename std::conditional<CONT, float, int32_t>::type;
+// T = Float32 | Float64 (the reference constructor's default, PendulumEnv.jl:42): every literal below is written so that the
+// Float32 instantiation keeps Julia's promotion points (2*pi, the cost terms and mod() are Float64) and the Float64 one is all-double.
+template <class T> struct PendPT { T max_speed, max_torque, g, m, l, dt; int max_steps; int n_actions; };
+using PendP = PendPT<float>;
+template <class T> struct vec2_of;
+template <> struct vec2_of<float> { using type = float2; };
+template <> struct vec2_of<double> { using type = double2; };
+template <bool CONT, class T = float> struct PendulumD {
+    using real = T;
+    using act_t = typename std::conditional<CONT, T, int32_t>::type;
+    using V2 = typename vec2_of<T>::type;
     static constexpr int NS = 2, NOBS = 3;
     static constexpr bool kObsIsState = false;
-    using P = PendP;
-    struct S { float th, thd; float torque; };
+    using P = PendPT<T>;
+    struct S { T th, thd; T torque; };
     __device__ static S load(const void* st, int64_t i) {
-        float2 v = reinterpret_cast<const float2*>(st)[i];
-        return S{v.x, v.y, 0.f};
+        V2 v = reinterpret_cast<const V2*>(st)[i];
+        return S{v.x, v.y, (T)0};
     }
     __device__ static void store(void* st, int64_t i, const S& s) {
-        reinterpret_cast<float2*>(st)[i] = make_float2(s.th, s.thd);
+        V2 v; v.x = s.th; v.y = s.thd;
+        reinterpret_cast<V2*>(st)[i] = v;
     }
     __device__ static bool valid(const P& p, act_t a) {
-        if (CONT) return (float)a >= -2.0f && (float)a <= 2.0f;   // a in -2.0..2.0 (NaN fails)
+        if (CONT) return (T)a >= (T)-2 && (T)a <= (T)2;   // a in -2.0..2.0 (NaN fails)
         return (int)a >= 1 && (int)a <= p.n_actions;
     }
     __device__ static unsigned long long n_random(const P& p) { return (unsigned long long)p.n_actions; }
     __device__ static act_t from_index(const P&, long long a) { return (act_t)a; }
-    // reset!: PendulumEnv.jl:84-92 — two scalar rand(rng, Float32); `2 * pi` is Float64
+    // reset!: PendulumEnv.jl:84-92 — two scalar rand(rng, T); `2 * pi` is Float64
     __device__ static void reset(const P&, S& s, Xo& g, act_t& last_action) {
-        float u1 = jld::rand_f32(g);
-        s.th = (float)((2 * JLD_PI) * (double)(u1 - 1.0f));
-        float u2 = jld::rand_f32(g);
-        s.thd = 2.0f * (u2 - 1.0f);
+        T u1 = jld::rand_real<T>(g);
+        s.th = (T)((2 * JLD_PI) * (double)(u1 - (T)1));
+        T u2 = jld::rand_real<T>(g);
+        s.thd = (T)2 * (u2 - (T)1);
         (void)last_action;  // env.action = zero(T) is the torque field, not the policy action
     }
     // act!/_step!: PendulumEnv.jl:94-122
-    __device__ static void step(const P& p, S& s, int& t, act_t a_in, bool& done, float& reward) {
-        float a;
+    __device__ static void step(const P& p, S& s, int& t, act_t a_in, bool& done, T& reward) {
+        T a;
         if (CONT) {
-            a = (float)a_in;
+            a = (T)a_in;
         } else {  // torque(env, a::Int) is Float64 arithmetic stored into env.action::T
             int n1 = p.n_actions - 1;
-            a = (float)((4.0 / (double)n1) * ((double)(int)a_in - (double)n1 / 2 - 1));
+            a = (T)((4.0 / (double)n1) * ((double)(int)a_in - (double)n1 / 2 - 1));
         }
         t += 1;
-        float th = s.th, thd = s.thd;
+        T th = s.th, thd = s.thd;
         a = jld::jclamp(a, -p.max_torque, p.max_torque);
-        float thpi = th + (float)JLD_PI;
+        T thpi = th + (T)JLD_PI;
         double an = jld::jmod((double)thpi, 2 * JLD_PI) - JLD_PI;   // angle_normalize in Float64
         double costs = (an * an + 0.1 * (double)(thd * thd)) + 0.001 * (double)(a * a);
-        float nthd = thd + ((((-3.0f * p.g) / (2.0f * p.l)) * jld::jsin(thpi)) + ((3.0f * a) / (p.m * (p.l * p.l)))) * p.dt;
+        T nthd = thd + (((((T)-3 * p.g) / ((T)2 * p.l)) * jld::jsin(thpi)) + (((T)3 * a) / (p.m * (p.l * p.l)))) * p.dt;
         th = th + nthd * p.dt;
         nthd = jld::jclamp(nthd, -p.max_speed, p.max_speed);
         s.th = th; s.thd = nthd; s.torque = a;
         done = t >= p.max_steps;
-        reward = (float)(-costs);
+        reward = (T)(-costs);
     }
-    // pendulum_observation: PendulumEnv.jl:70
-    __device__ static void observe(const S& s, float (&o)[4]) { o[0] = jld::jsin(s.th); o[1] = jld::jcos(s.th); o[2] = s.thd; o[3] = 0.f; }
+    // pendulum_observation: PendulumEnv.jl:70 (the fused Float32 rollout reads it as floats)
+    __device__ static void observe(const S& s, float (&o)[4]) { o[0] = (float)jld::jsin(s.th); o[1] = (float)jld::jcos(s.th); o[2] = (float)s.thd; o[3] = 0.f; }
     __device__ static void write_obs(void* obs, int64_t i, int64_t, const S& s) {
-        float* o = reinterpret_cast<float*>(obs) + 3 * i;
-        float v[4];
-        observe(s, v);
-        o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+        T* o = reinterpret_cast<T*>(obs) + 3 * i;
+        o[0] = jld::jsin(s.th); o[1] = jld::jcos(s.th); o[2] = s.thd;
     }
 };
 
 // ---------------------------------------------------------------- MountainCar ---------
-// CONT: ContinuousMountainCarEnv — Float32 force in -1.0..1.0 (MountainCarEnv.jl:73-74,83,93,107-111)
-template <bool CONT = false> struct MountainCarD {
-    using real = float;
-    using act_t = typename std::conditional<CONT, float, int32_t>::type;
+// CONT: ContinuousMountainCarEnv — force in -1.0..1.0 (MountainCarEnv.jl:73-74,83,93,107-111); T = Float32 | Float64 (the default, :67)
+template <class T> struct MountainCarPT { T min_pos, max_pos, max_speed, goal_pos, goal_velocity, power, gravity; int max_steps; };
+template <bool CONT = false, class T = float> struct MountainCarD {
+    using real = T;
+    using act_t = typename std::conditional<CONT, T, int32_t>::type;
+    using V2 = typename vec2_of<T>::type;
     static constexpr int NS = 2, NOBS = 2;
     static constexpr bool kObsIsState = true;
-    struct P { float min_pos, max_pos, max_speed, goal_pos, goal_velocity, power, gravity; int max_steps; };
-    struct S { float x, v; };
+    using P = MountainCarPT<T>;
+    struct S { T x, v; };
     __device__ static S load(const void* st, int64_t i) {
-        float2 v = reinterpret_cast<const float2*>(st)[i];
+        V2 v = reinterpret_cast<const V2*>(st)[i];
         return S{v.x, v.y};
     }
     __device__ static void store(void* st, int64_t i, const S& s) {
-        reinterpret_cast<float2*>(st)[i] = make_float2(s.x, s.v);
+        V2 v; v.x = s.x; v.y = s.v;
+        reinterpret_cast<V2*>(st)[i] = v;
     }
     __device__ static bool valid(const P&, act_t a) {
-        if (CONT) return (float)a >= -1.0f && (float)a <= 1.0f;
+        if (CONT) return (T)a >= (T)-1 && (T)a <= (T)1;
         return a >= 1 && a <= 3;
     }
     __device__ static unsigned long long n_random(const P&) { return 3; }
     __device__ static act_t from_index(const P&, long long a) { return (act_t)a; }
     // reset!: MountainCarEnv.jl:99-105 (Float64 literals 0.2, 0.6)
     __device__ static void reset(const P&, S& s, Xo& g, act_t&) {
-        float u = jld::rand_f32(g);
-        s.x = (float)(0.2 * (double)u - 0.6);
-        s.v = 0.0f;
+        T u = jld::rand_real<T>(g);
+        s.x = (T)(0.2 * (double)u - 0.6);
+        s.v = (T)0;
     }
     // _step!: MountainCarEnv.jl:119-135
-    __device__ static void step(const P& p, S& s, int& t, act_t a, bool& done, float& reward) {
+    __device__ static void step(const P& p, S& s, int& t, act_t a, bool& done, T& reward) {
         t += 1;
-        float x = s.x, v = s.v;
-        float force = CONT ? (float)a : (float)((int)a - 2);   // act!(env, a::Int) -> _step!(env, a - 2)
-        v = v + (force * p.power + jld::jcos(3.0f * x) * (-p.gravity));
+        T x = s.x, v = s.v;
+        T force = CONT ? (T)a : (T)((int)a - 2);   // act!(env, a::Int) -> _step!(env, a - 2)
+        v = v + (force * p.power + jld::jcos((T)3 * x) * (-p.gravity));
         v = jld::jclamp(v, -p.max_speed, p.max_speed);
         x = x + v;
         x = jld::jclamp(x, p.min_pos, p.max_pos);
-        if (x == p.min_pos && v < 0) v = 0.0f;
+        if (x == p.min_pos && v < 0) v = (T)0;
         done = (x >= p.goal_pos && v >= p.goal_velocity) || t >= p.max_steps;
         s.x = x; s.v = v;
-        reward = done ? 0.0f : -1.0f;  // MountainCarEnv.jl:95
+        reward = done ? (T)0 : (T)-1;  // MountainCarEnv.jl:95
     }
-    __device__ static void observe(const S& s, float (&o)[4]) { o[0] = s.x; o[1] = s.v; o[2] = 0.f; o[3] = 0.f; }
+    __device__ static void observe(const S& s, float (&o)[4]) { o[0] = (float)s.x; o[1] = (float)s.v; o[2] = 0.f; o[3] = 0.f; }
     __device__ static void write_obs(void*, int64_t, int64_t, const S&) {}
 };
 
@@ -234,6 +243,8 @@ struct EnvView {
         CartPoleD<double>::P cp64;
         PendP pend;
         MountainCarD<false>::P mc;
+        PendPT<double> pend64;
+        MountainCarPT<double> mc64;
     } p;
 };
 

@@ -118,8 +118,17 @@ __device__ __forceinline__ double cos_kernel64(double hi, double lo) {
     double w = 1.0 - half;
     return w + (((1.0 - w) - half) + (y2 * r - hi * lo));
 }
-__device__ __forceinline__ int rem_pio2_64(double x, double* y1o, double* y2o) {
-    unsigned xhp = (unsigned)__double2hiint(x) & 0x7fffffffu;
+// cody_waite_2c_pio2(x, fn, n) (rem_pio2.jl): two-constant reduction used for |x| <= 9pi/4 away from multiples of pi/2
+__device__ __forceinline__ int cody_waite_2c(double x, double fn, int n, double* y1o, double* y2o) {
+    double z = muladd(-fn, 1.57079632673412561417e+00, x);
+    double w = fn * 6.07710050650619224932e-11;
+    double y1 = z - w;
+    *y1o = y1;
+    *y2o = (z - y1) - w;
+    return n;
+}
+// cody_waite_ext_pio2 (medium range, |x| < 2^20*pi/2): up to three rounds
+__device__ __forceinline__ int cody_waite_ext(double x, unsigned xhp, double* y1o, double* y2o) {
     double fn = rint(x * 6.36619772367581382433e-01);
     double r = muladd(-fn, 1.57079632673412561417e+00, x);
     double w = fn * 6.07710050650619224932e-11;
@@ -144,6 +153,27 @@ __device__ __forceinline__ int rem_pio2_64(double x, double* y1o, double* y2o) {
     *y1o = y1;
     *y2o = (r - y1) - w;
     return (int)(long long)fn;
+}
+// rem_pio2_kernel(x::Float64) (base/special/rem_pio2.jl, a port of msun e_rem_pio2.c): the decision tree on the high word —
+// |x| <= 9pi/4 uses the two-constant scheme with fn = +-1..4 unless x is close to a multiple of pi/2, everything up to
+// 2^20 pi/2 the extended scheme; Payne-Hanek beyond is not restated (unreachable: Pendulum |theta| < 100, MountainCar |3x| < 4).
+__device__ __forceinline__ int rem_pio2_64(double x, double* y1o, double* y2o) {
+    const unsigned xhp = (unsigned)__double2hiint(x) & 0x7fffffffu;
+    const bool pos = x > 0.0;
+    if (xhp <= 0x400f6a7au) {                       // |x| ~<= 5pi/4
+        if ((xhp & 0xfffffu) == 0x921fbu) return cody_waite_ext(x, xhp, y1o, y2o);     // |x| ~= pi/2 or 2pi/2
+        if (xhp <= 0x4002d97cu) return pos ? cody_waite_2c(x, 1.0, 1, y1o, y2o) : cody_waite_2c(x, -1.0, -1, y1o, y2o);   // |x| ~<= 3pi/4
+        return pos ? cody_waite_2c(x, 2.0, 2, y1o, y2o) : cody_waite_2c(x, -2.0, -2, y1o, y2o);
+    }
+    if (xhp <= 0x401c463bu) {                       // |x| ~<= 9pi/4
+        if (xhp <= 0x4015fdbcu) {                   // |x| ~<= 7pi/4
+            if (xhp == 0x4012d97cu) return cody_waite_ext(x, xhp, y1o, y2o);           // |x| ~= 3pi/2
+            return pos ? cody_waite_2c(x, 3.0, 3, y1o, y2o) : cody_waite_2c(x, -3.0, -3, y1o, y2o);
+        }
+        if (xhp == 0x401921fbu) return cody_waite_ext(x, xhp, y1o, y2o);               // |x| ~= 4pi/2
+        return pos ? cody_waite_2c(x, 4.0, 4, y1o, y2o) : cody_waite_2c(x, -4.0, -4, y1o, y2o);
+    }
+    return cody_waite_ext(x, xhp, y1o, y2o);
 }
 __device__ __forceinline__ double jsin(double x) {
     double ax = fabs(x);
@@ -200,6 +230,9 @@ __device__ __forceinline__ unsigned long long next(Xo& g) {
 }
 __device__ __forceinline__ double rand_f64(Xo& g) { return (double)(next(g) >> 11) * 0x1p-53; }
 __device__ __forceinline__ float rand_f32(Xo& g) { return (float)((unsigned)(next(g) >> 32) >> 8) * 0x1p-24f; }
+template <class T> __device__ __forceinline__ T rand_real(Xo& g);     // rand(rng, T), scalar API
+template <> __device__ __forceinline__ float rand_real<float>(Xo& g) { return rand_f32(g); }
+template <> __device__ __forceinline__ double rand_real<double>(Xo& g) { return rand_f64(g); }
 // rand(rng, T, 4): array API below the 64-byte SIMD threshold (one u64 per 8 output bytes)
 __device__ __forceinline__ void rand4(Xo& g, float* o) {
 #pragma unroll

@@ -28,16 +28,16 @@ def cartpole_params(T=np.float32, gravity=9.8, masscart=1.0, masspole=0.1, halfl
                             f(forcemag), f(dt), f(thetathreshold * math.pi / 180), f(xthreshold), int(max_steps))
 
 
-def pendulum_params(max_speed=8, max_torque=2, g=10, m=1, l=1, dt=0.05, max_steps=200, continuous=True, n_actions=3):
-    """PendulumEnv(; kwargs...) (PendulumEnv.jl:41-66), T = Float32."""
-    f = lambda v: float(np.float32(v))
+def pendulum_params(T=np.float32, max_speed=8, max_torque=2, g=10, m=1, l=1, dt=0.05, max_steps=200, continuous=True, n_actions=3):
+    """PendulumEnv(; T, kwargs...) (PendulumEnv.jl:41-66): every field is T(value) (the reference default is T = Float64)."""
+    f = lambda v: float(T(v))
     return L.PendulumParams(f(max_speed), f(max_torque), f(g), f(m), f(l), f(dt), int(max_steps), int(n_actions), int(bool(continuous)))
 
 
-def mountaincar_params(min_pos=-1.2, max_pos=0.6, max_speed=0.07, goal_pos=0.5, goal_velocity=0.0, power=0.001, gravity=0.0025,
+def mountaincar_params(T=np.float32, min_pos=-1.2, max_pos=0.6, max_speed=0.07, goal_pos=0.5, goal_velocity=0.0, power=0.001, gravity=0.0025,
                        max_steps=200):
-    """MountainCarEnvParams(; T=Float32, kwargs...) (MountainCarEnv.jl:19-40)."""
-    f = lambda v: float(np.float32(v))
+    """MountainCarEnvParams(; T, kwargs...) (MountainCarEnv.jl:19-40; the reference default is T = Float64)."""
+    f = lambda v: float(T(v))
     return L.MountainCarParams(f(min_pos), f(max_pos), f(max_speed), f(goal_pos), f(goal_velocity), f(power), f(gravity), int(max_steps))
 
 
@@ -58,13 +58,15 @@ class B200VecEnv:
             if self.kind == L.ENV_CARTPOLE:
                 params = cartpole_params(T=self.T, **kwargs)
             elif self.kind == L.ENV_PENDULUM:
-                params = pendulum_params(**kwargs)
+                params = pendulum_params(T=self.T, **kwargs)
             elif create_kind == L.ENV_MOUNTAINCAR_CONTINUOUS:  # MountainCarEnv.jl:73-74
-                params = mountaincar_params(**{"goal_pos": 0.45, "power": 0.0015, **kwargs})
+                params = mountaincar_params(T=self.T, **{"goal_pos": 0.45, "power": 0.0015, **kwargs})
             else:
-                params = mountaincar_params(**kwargs)
+                params = mountaincar_params(T=self.T, **kwargs)
         self.params = params
         self.continuous = create_kind in _BASE or (self.kind == L.ENV_PENDULUM and bool(params.continuous))
+        # a continuous action is a T (Float64 actions for a Float64 env), a discrete one an Int32 (1-based)
+        self.act_dtype = (np.float64 if self.T is np.float64 else np.float32) if self.continuous else np.int32
         rng_state = np.ascontiguousarray(rng_state, dtype=np.uint64).reshape(self.n, 4)
         h = C.c_void_p()
         L.check(self.lib.b200rl_env_create(ctx.h, create_kind, L.F64 if self.T is np.float64 else L.F32, self.n,
@@ -103,7 +105,7 @@ class B200VecEnv:
         if isinstance(actions, (int, np.integer)):
             L.check(self.lib.b200rl_env_step(self.h, C.c_void_p(int(actions)), 1, int(self.auto_reset)))
         else:
-            a = np.ascontiguousarray(actions, dtype=np.float32 if self.continuous else np.int32)
+            a = np.ascontiguousarray(actions, dtype=self.act_dtype)
             if a.shape != (self.n,):
                 raise ValueError(f"expected {self.n} actions, got shape {a.shape}")
             # the agent's own pinned action buffer (returned by plan!): stream-ordered copy, no host sync — the next plan!
@@ -147,7 +149,7 @@ class B200VecEnv:
         return self._get(L.FIELD_RNG, (self.n, 4), np.uint64, order="C")
 
     def last_action(self):
-        return self._get(L.FIELD_ACTION, (self.n,), np.float32 if self.continuous else np.int32)
+        return self._get(L.FIELD_ACTION, (self.n,), self.act_dtype)
 
     def set_field(self, field, arr):
         arr = np.asarray(arr)

@@ -145,8 +145,8 @@ function RLBase.act!(env::B200VecEnv, actions::AbstractVector{<:Integer})
     a = convert(Vector{Int32}, actions)                     # device dtype is Int32, 1-based like Base.OneTo(n)
     GC.@preserve a check(ccall((:b200rl_env_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint), env.h, a, 0, env.auto_reset))
 end
-function RLBase.act!(env::B200VecEnv, actions::AbstractVector{<:AbstractFloat})
-    a = convert(Vector{Float32}, actions)
+function RLBase.act!(env::B200VecEnv{T}, actions::AbstractVector{<:AbstractFloat}) where {T}
+    a = convert(Vector{T}, actions)                         # a continuous action is a T (Float64 for the constructors' default T)
     GC.@preserve a check(ccall((:b200rl_env_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint), env.h, a, 0, env.auto_reset))
 end
 struct FusedRandomAction end                                  # plan!(B200RandomPolicy) token

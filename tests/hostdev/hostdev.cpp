@@ -61,7 +61,8 @@ void run_env(const typename Env::P& p, int64_t n, int steps, uint64_t* rng, cons
 
 extern "C" {
 // kind: 0 CartPole f32 | 1 Pendulum continuous | 2 MountainCar | 3 CartPole continuous f32 | 4 MountainCar continuous | 5 CartPole f64
-//       | 6 Pendulum discrete.   q: the oracle's parameter vector (tests/oracle_lib.default_params layout).
+//       | 6 Pendulum discrete | 7 Pendulum f64 continuous | 8 Pendulum f64 discrete | 9 MountainCar f64 | 10 MountainCar f64 continuous.
+//       q: the oracle's parameter vector (tests/oracle_lib.default_params layout).
 // actions: (n, steps) column-major (int32 or float32 / ignored when random_policy); reward / terminal out: (n, steps).
 int hd_env_run(int kind, const double* q, int64_t n, int steps, uint64_t* rng, const void* actions, int random_policy, void* state_io,
                void* reward_out, uint8_t* terminal_out, int32_t* t_io, void* action_out, int do_reset_first) {
@@ -85,6 +86,18 @@ int hd_env_run(int kind, const double* q, int64_t n, int steps, uint64_t* rng, c
         PendP p{(float)q[0], (float)q[1], (float)q[2], (float)q[3], (float)q[4], (float)q[5], (int)q[6], (int)q[7]};
         if (kind == 1) run_env<PendulumD<true>>(p, n, steps, rng, actions, 0, state_io, (float*)reward_out, terminal_out, t_io, action_out, do_reset_first);
         else run_env<PendulumD<false>>(p, n, steps, rng, actions, random_policy, state_io, (float*)reward_out, terminal_out, t_io, action_out, do_reset_first);
+        return 0;
+    }
+    if (kind == 7 || kind == 8) {
+        PendPT<double> p{q[0], q[1], q[2], q[3], q[4], q[5], (int)q[6], (int)q[7]};
+        if (kind == 7) run_env<PendulumD<true, double>>(p, n, steps, rng, actions, 0, state_io, (double*)reward_out, terminal_out, t_io, action_out, do_reset_first);
+        else run_env<PendulumD<false, double>>(p, n, steps, rng, actions, random_policy, state_io, (double*)reward_out, terminal_out, t_io, action_out, do_reset_first);
+        return 0;
+    }
+    if (kind == 9 || kind == 10) {
+        MountainCarPT<double> p{q[0], q[1], q[2], q[3], q[4], q[5], q[6], (int)q[7]};
+        if (kind == 9) run_env<MountainCarD<false, double>>(p, n, steps, rng, actions, random_policy, state_io, (double*)reward_out, terminal_out, t_io, action_out, do_reset_first);
+        else run_env<MountainCarD<true, double>>(p, n, steps, rng, actions, 0, state_io, (double*)reward_out, terminal_out, t_io, action_out, do_reset_first);
         return 0;
     }
     if (kind == 2 || kind == 4) {

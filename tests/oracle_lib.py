@@ -148,9 +148,10 @@ def default_params(kind, dtype="f32"):
         q = np.empty(11, dtype=np.float64)
         L.orc_cartpole_default_params(1 if dtype == "f64" else 0, _p(q))
         return q
+    T = np.float64 if dtype == "f64" else np.float32
     if kind == KIND_PENDULUM:
-        return np.array([8, 2, 10, 1, 1, float(np.float32(0.05)), 200, 3, 1], dtype=np.float64)
-    f = lambda v: float(np.float32(v))
+        return np.array([8, 2, 10, 1, 1, float(T(0.05)), 200, 3, 1], dtype=np.float64)
+    f = lambda v: float(T(v))
     if kind == KIND_MOUNTAINCAR_CONT:  # MountainCarEnv.jl:73-74
         return np.array([f(-1.2), f(0.6), f(0.07), f(0.45), 0.0, f(0.0015), f(0.0025), 200], dtype=np.float64)
     return np.array([f(-1.2), f(0.6), f(0.07), f(0.5), 0.0, f(0.001), f(0.0025), 200], dtype=np.float64)
@@ -176,7 +177,7 @@ class OracleVecEnv:
         self.L.orc_vecenv_reset(self.h, int(force))
 
     def step(self, actions, auto_reset=False):
-        a = np.ascontiguousarray(actions, dtype=np.float32 if self.continuous else np.int32)
+        a = np.ascontiguousarray(actions, dtype=(self.np_t if self.continuous else np.int32))
         return self.L.orc_vecenv_step(self.h, _p(a), int(auto_reset))
 
     def set_max_timeout(self, max_t):
@@ -193,7 +194,7 @@ class OracleVecEnv:
             F_STATE: ((n, NS[self.kind]), self.np_t), F_OBS: ((n, NOBS[self.kind]), self.np_t),
             F_REWARD: ((n,), self.np_t), F_TERMINAL: ((n,), np.uint8), F_FLAGS: ((n,), np.uint8),
             F_T: ((n,), np.int32), F_RNG: ((n, 4), np.uint64),
-            F_ACTION: ((n,), np.float32 if (self.continuous or self.kind == KIND_PENDULUM) else np.int32),
+            F_ACTION: ((n,), (self.np_t if self.continuous else np.float32) if (self.continuous or self.kind == KIND_PENDULUM) else np.int32),
         }[field]
         out = np.empty(*shape_dt)
         self.L.orc_vecenv_get(self.h, field, _p(out))

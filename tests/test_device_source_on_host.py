@@ -44,7 +44,8 @@ def test_julia_math_kernels_bitwise(hd):
     for x in xs32:
         assert hd.hd_sin32(x) == o.orc_sin32(x) or (np.isnan(hd.hd_sin32(x)) and np.isnan(o.orc_sin32(x))), x
         assert hd.hd_cos32(x) == o.orc_cos32(x), x
-    xs64 = np.concatenate([rng.uniform(-0.3, 0.3, 4000), rng.uniform(-1e3, 1e3, 4000), rng.standard_normal(1000) * 1e-9, [0.0, 0.7853981633974483, 1e6 + 0.1]])
+    xs64 = np.concatenate([rng.uniform(-0.3, 0.3, 4000), rng.uniform(-1e3, 1e3, 4000), rng.uniform(-7.2, 7.2, 6000), rng.standard_normal(1000) * 1e-9,
+                           np.pi / 2 * np.arange(-6, 7) + 1e-9, np.pi / 2 * np.arange(-6, 7), [0.0, 0.7853981633974483, 1e6 + 0.1]])
     for x in xs64:
         assert hd.hd_sin64(x) == o.orc_sin64(x), x
         assert hd.hd_cos64(x) == o.orc_cos64(x), x
@@ -76,13 +77,18 @@ CASES = [
     pytest.param(2, O.KIND_MOUNTAINCAR, "f32", 3, None, id="MountainCar"),
     pytest.param(3, O.KIND_CARTPOLE_CONT, "f32", None, 1.0, id="CartPole-continuous"),
     pytest.param(4, O.KIND_MOUNTAINCAR_CONT, "f32", None, 1.0, id="MountainCar-continuous"),
+    # T = Float64: the reference constructors' default for Pendulum / MountainCar (PendulumEnv.jl:42, MountainCarEnv.jl:67)
+    pytest.param(7, O.KIND_PENDULUM, "f64", None, 2.0, id="Pendulum-f64-continuous"),
+    pytest.param(8, O.KIND_PENDULUM, "f64", 3, None, id="Pendulum-f64-discrete"),
+    pytest.param(9, O.KIND_MOUNTAINCAR, "f64", 3, None, id="MountainCar-f64"),
+    pytest.param(10, O.KIND_MOUNTAINCAR_CONT, "f64", None, 1.0, id="MountainCar-f64-continuous"),
 ]
 
 
 def _oracle(okind, dtype, n, seeds, discrete_pendulum):
     params = None
     if discrete_pendulum:
-        params = O.default_params(O.KIND_PENDULUM).copy()
+        params = O.default_params(O.KIND_PENDULUM, dtype).copy()
         params[8] = 0
     return O.OracleVecEnv(okind, n, seeds, dtype=dtype, params=params)
 
@@ -91,7 +97,7 @@ def _oracle(okind, dtype, n, seeds, discrete_pendulum):
 def test_env_step_and_auto_reset_bitwise(hd, hkind, okind, dtype, n_act, bound):
     n, steps = 1200, 260                                   # 260 > max_steps = 200: the time limit resets every env at least once
     seeds = O.splitmix_states_fast(n, 31 + hkind)
-    ref = _oracle(okind, dtype, n, seeds, hkind == 6)
+    ref = _oracle(okind, dtype, n, seeds, hkind in (6, 8))
     ref.reset(force=True)
     T = np.float64 if dtype == "f64" else np.float32
     state = np.ascontiguousarray(ref.get(O.F_STATE))       # (n, NS): one env's state contiguous = the device layout
@@ -101,7 +107,7 @@ def test_env_step_and_auto_reset_bitwise(hd, hkind, okind, dtype, n_act, bound):
     if n_act:
         A = r.integers(1, n_act + 1, (n, steps)).astype(np.int32)
     else:
-        A = r.uniform(-bound, bound, (n, steps)).astype(np.float32)
+        A = r.uniform(-bound, bound, (n, steps)).astype(T)          # a continuous action is a T
     A = np.asfortranarray(A)
     rew = np.zeros((n, steps), T, order="F"); term = np.zeros((n, steps), np.uint8, order="F")
     assert hd.hd_env_run(hkind, O._p(ref.params), n, steps, O._p(rng), O._p(A), 0, O._p(state), O._p(rew), O._p(term), O._p(t), None, 0) == 0
@@ -118,7 +124,7 @@ def test_env_step_and_auto_reset_bitwise(hd, hkind, okind, dtype, n_act, bound):
 def test_env_reset_and_random_policy_bitwise(hd, hkind, okind, dtype, n_act, bound):
     n, steps = 800, 230
     seeds = O.splitmix_states_fast(n, 77 + hkind)
-    ref = _oracle(okind, dtype, n, seeds, hkind == 6)       # the constructor resets once (CartPoleEnv.jl:77) ...
+    ref = _oracle(okind, dtype, n, seeds, hkind in (6, 8))  # the constructor resets once (CartPoleEnv.jl:77) ...
     ref.reset(force=True)                                   # ... and run() resets again before the first step (run.jl:46)
     T = np.float64 if dtype == "f64" else np.float32
     ns = O.NS[okind]

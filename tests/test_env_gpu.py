@@ -215,3 +215,45 @@ def test_episode_stats_match_host_hooks(pkg, ctx):
     assert dev.stats["length_sum"] == sum(sum(s) for s in steps_hook.steps)
     assert dev.stats["return_sum"] == pytest.approx(sum(sum(r) for r in rew_hook.rewards))
     assert dev.stats["env_steps"] == 200 * n
+
+
+@pytest.mark.parametrize("kind,continuous", [("Pendulum", True), ("Pendulum", False), ("MountainCar", False), ("ContinuousMountainCar", True)])
+@pytest.mark.parametrize("auto_reset", [False, True])
+def test_float64_pendulum_and_mountaincar_bit_exact(pkg, ctx, kind, continuous, auto_reset):
+    """T = Float64 is what a literal `PendulumEnv()` / `MountainCarEnv()` constructs (PendulumEnv.jl:42, MountainCarEnv.jl:67): all-double
+    dynamics, Float64 rand / sin / cos (the rem_pio2 decision tree), Float64 actions for the continuous spaces."""
+    n, steps = 2500, 450                                   # > 2 episodes of 200 steps: theta runs up to ~ +-80 rad without wrapping
+    seeds = O.splitmix_states_fast(n, seed=1234)
+    kw = dict(continuous=continuous, n_actions=5) if kind == "Pendulum" else {}
+    env = pkg.B200VecEnv(ctx, kind, n, seeds, T=np.float64, auto_reset=auto_reset, **kw)
+    params = None
+    if kind == "Pendulum":
+        params = O.default_params(O.KIND_PENDULUM, "f64")
+        params[7], params[8] = 5, float(continuous)
+    ref = O.OracleVecEnv(KINDS[kind], n, seeds, dtype="f64", params=params)
+    assert env.state().dtype == np.float64 and env.reward().dtype == np.float64
+    assert_same(env, ref, "after construction")
+    rng = np.random.default_rng(5)
+    bound = 2.0 if kind == "Pendulum" else 1.0
+    nact = {"Pendulum": 5, "MountainCar": 3}.get(kind)
+    for s in range(steps):
+        act = rng.uniform(-bound, bound, n) if continuous else rng.integers(1, nact + 1, n).astype(np.int32)
+        if not auto_reset:
+            env.reset_(is_force=False); ref.reset(force=False)
+        env.act_(act); assert ref.step(act, auto_reset=auto_reset) == 0
+        if s % 75 == 0 or s >= steps - 2:
+            assert_same(env, ref, f"{kind} f64 step {s}")
+    env.check()
+    assert env.episode_stats()["episodes"] >= 2 * n
+    assert env.last_action().dtype == (np.float64 if continuous else np.int32)
+    env.close()
+
+
+def test_float64_env_is_refused_by_the_float32_learners(pkg, ctx):
+    env = pkg.B200VecEnv(ctx, "Pendulum", 64, O.splitmix_states_fast(64, 1), T=np.float64, auto_reset=True)
+    desc = O.ac_desc(3, 64, 1, 0, True)
+    net = pkg.Network(ctx, 3, 64, 1, O.glorot_params(desc, 1), kind=pkg.KIND_GAUSSIAN)
+    with pytest.raises(pkg.B200RLError) as ei:
+        pkg.OnPolicyAgent(ctx, net, env, pkg.onpolicy_config(update_freq=4, n_epochs=1, n_microbatches=1), O.splitmix_states_fast(64, 2))
+    assert ei.value.status == pkg._lib.ERR_UNSUPPORTED and "Float32" in str(ei.value)
+    net.close(); env.close()
