@@ -909,12 +909,20 @@ int b200rl_dqn_update(b200rl_net* n, b200rl_traj* t, const b200rl_dqn_config* cf
     int np_ = nn_dqn_loss_grad(ctx, n->actor, n->params, n->target, b.s, b.a, b.r, b.t, b.s2, b.w, b.B, 1.0f / ((float)b.B * (float)world), cfg->gamma,
                                cfg->huber, cfg->double_dqn, n->partial, n->loss_partial, td);
     if (np_ < 0) return np_;
-    TRY(nn_reduce_partials(ctx, n->partial, np_, n->np, n->grad, n->loss_partial, np_, n->loss4));
-    if (world > 1) {
-        TRY(b200rl_comm_allreduce_internal(ctx, n->grad, n->np, 0));
-        TRY(b200rl_comm_allreduce_internal(ctx, n->loss4, 4, 0));
+    P2PTable peers;
+    const unsigned adam_grid = grid_for(n->np, 256);
+    if ((world == 1 || b200rl_comm_p2p_table(ctx, &peers)) && (int)adam_grid <= ctx->sm_count) {
+        // one kernel: partial reduce [-> peer exchange] -> global-norm clip -> Adam (the optimiser step of the on-policy path)
+        TRY(nn_reduce_clip_adam(ctx, n->partial, np_, n->np, n->params, n->grad, n->m, n->v, n->beta_t, n->loss_partial, np_, n->loss4, cfg->max_grad_norm,
+                                cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, n->gnorm, n->cta_sumsq, n->counter2, nullptr, nullptr));
+    } else {
+        TRY(nn_reduce_partials(ctx, n->partial, np_, n->np, n->grad, n->loss_partial, np_, n->loss4));
+        if (world > 1) {
+            TRY(b200rl_comm_allreduce_internal(ctx, n->grad, n->np, 0));
+            TRY(b200rl_comm_allreduce_internal(ctx, n->loss4, 4, 0));
+        }
+        TRY(nn_clip_adam(ctx, n->params, n->grad, n->m, n->v, n->beta_t, n->np, cfg->max_grad_norm, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, 1.0f, n->gnorm));
     }
-    TRY(nn_clip_adam(ctx, n->params, n->grad, n->m, n->v, n->beta_t, n->np, cfg->max_grad_norm, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, 1.0f, n->gnorm));
     if (b200rl_traj_internal_prioritized(t)) TRY(b200rl_traj_internal_priority_from_td(t, td, cfg->per_eps, cfg->per_alpha));
     n->n_updates += 1;
     if (cfg->target_update_freq > 0 && n->n_updates % (uint64_t)cfg->target_update_freq == 0) TRY(nn_target_sync(ctx, n->target, n->params, n->np, cfg->rho));

@@ -1,5 +1,6 @@
 // core.cu — context, error convention, memory helpers of libb200rl.so.
 #include <cstdarg>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -57,6 +58,14 @@ int b200rl_init(int device, b200rl_ctx** out) {
         return B200RL_ERR_UNSUPPORTED;
     }
     CUDA_TRY(cudaSetDevice(device));
+    {   // L2 fetch granularity 32 B: the minibatch gathers of the update read one 32-byte record per sample at random; with the
+        // default (128 B) granularity every such read drags 3 neighbouring sectors out of HBM (ncu: 46.0 MB per K7 launch vs
+        // 16.9 MB at 32 B = 1.01x the algorithmic bytes; streaming kernels request whole lines either way).  A hint, per context;
+        // B200RL_L2_FETCH=64|128 restores a larger one, 0 leaves the driver default.
+        size_t gran = 32;
+        if (const char* g = getenv("B200RL_L2_FETCH")) gran = (size_t)atoi(g);
+        if (gran) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); cudaGetLastError(); }
+    }
     b200rl_ctx* ctx = new b200rl_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;

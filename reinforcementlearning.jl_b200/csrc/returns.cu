@@ -6,6 +6,7 @@
 //   delta = (r[i] + (gamma * v[i+1]) * c) - v[i];   gae = delta + ((gamma*lambda) * c) * gae
 // (c::Bool multiply = strong zero), compiled with -fmad=false -> bit-identical to the serial
 // CPU loop.  Loads are issued a chunk of time steps ahead of the dependent chain.
+// (Few long series take a warp-segmented scan instead: scan_few_series below.)
 //   dims = 2 ((N, T) PPO layout, series-fastest): a warp's 32 series are contiguous -> fully
 //            coalesced 128-byte transactions at every time step.
 //   dims = 1 (time-fastest): a CTA stages a [time-chunk x 32 series] tile through shared
@@ -146,6 +147,47 @@ __global__ void __launch_bounds__(kBlock) scan_time_fastest(T* __restrict__ out,
     if (MODE == 1 && scanner) out[s] = acc;
 }
 
+// Few series, long time axis (e.g. one episode of 300+ steps; north-star item (iii)): one WARP per series runs the backward linear
+// recurrence x_i = b_i + a_i x_{i+1} as a warp-segmented scan — 32 time steps per round, Kogge-Stone composition of the affine
+// maps (a, b) with shuffles, the round's last value carried into the next round.  The composition re-associates the float
+// recurrence, so this variant is within ~1e-6 of the serial loop instead of bit-identical: it is only dispatched where the
+// thread-per-series kernel would leave the machine idle (S < 1024 and >= 64 time steps; the reference's golden vectors and the
+// PPO rollout path never take it).
+template <class T, int MODE>
+__global__ void __launch_bounds__(kBlock) scan_few_series(T* __restrict__ out, const T* __restrict__ r, const T* __restrict__ v,
+                                                         const uint8_t* __restrict__ term, const T* __restrict__ init, T gamma, T lambda,
+                                                         int64_t S, int64_t n_time, int64_t ss, int64_t ts, int64_t vss) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    if (s >= S) return;                                    // whole warps leave together
+    const T k = (MODE == 2) ? gamma * lambda : gamma;
+    T carry = (MODE == 2) ? (T)0 : (init ? init[s] : (T)0);
+    for (int64_t hi = n_time; hi > 0; hi -= 32) {
+        const int64_t i = hi - 1 - lane;                   // lane 0 = the latest time step of this round
+        T a = (T)1, b = (T)0;                              // identity map for lanes past the start of the series
+        if (i >= 0) {
+            const bool c = !(term && term[s * ss + i * ts]);
+            a = c ? k : (T)0;
+            if (MODE == 2) {
+                const T vn = v[s * vss + (i + 1) * ts], vi = v[s * vss + i * ts];
+                b = (r[s * ss + i * ts] + (c ? gamma * vn : (T)0)) - vi;
+            } else {
+                b = r[s * ss + i * ts];
+            }
+        }
+        // inclusive scan of the maps in lane order: after it, x_lane = a * carry + b
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const T a2 = __shfl_up_sync(0xffffffffu, a, d), b2 = __shfl_up_sync(0xffffffffu, b, d);
+            if (lane >= d) { b = a * b2 + b; a = a * a2; }
+        }
+        const T x = a * carry + b;
+        if (i >= 0 && MODE != 1) out[s * ss + i * ts] = x;
+        carry = __shfl_sync(0xffffffffu, x, 31);           // (lanes with i < 0 hold the identity map: x passes through)
+    }
+    if (MODE == 1 && lane == 0) out[s] = carry;
+}
+
 // Final reduce of the per-CTA partials in CTA order -> {mean, 1/clamp(std,1e-8,1000)} as float2.
 __global__ void finalize_norm_kernel(const double* __restrict__ partials, int n_partials, double count, float* __restrict__ out2) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -186,7 +228,11 @@ int run_scan(b200rl_ctx* ctx, T* out, const T* r, const T* v, const uint8_t* ter
         if (term) CUDA_TRY(cudaMemcpyAsync(pt, term, n, cudaMemcpyHostToDevice, ctx->stream));
         d_out = po; d_r = pr; d_v = pv; d_init = init ? pi : nullptr; d_term = term ? pt : nullptr;
     }
-    if (dims == 2)
+    if (S < 1024 && n_time >= 64) {   // few long series: warp-segmented scan (see scan_few_series), either layout
+        const int64_t ss = dims == 2 ? 1 : n_time, ts = dims == 2 ? S : 1, vss = dims == 2 ? 1 : n_time + 1;
+        scan_few_series<T, MODE><<<grid_for(S, kBlock / 32), kBlock, 0, ctx->stream>>>(d_out, d_r, d_v, d_term, d_init, gamma, lambda, S, n_time,
+                                                                                       ss, ts, vss);
+    } else if (dims == 2)
         scan_series_fastest<T, MODE><<<grid_for(S, kBlock), kBlock, 0, ctx->stream>>>(d_out, d_r, d_v, d_term, d_init, gamma, lambda, S,
                                                                                      n_time, nullptr, nullptr);
     else

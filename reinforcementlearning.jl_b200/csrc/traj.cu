@@ -139,18 +139,43 @@ __global__ void push_sart_kernel(Ring r, const int32_t* __restrict__ a, const fl
 
 // Single CTA: tree[L + key[k]] = prio[k] for every key >= 0, then rebuild the touched paths level by level
 // (children are re-added, never delta-updated -> deterministic, drift-free; duplicate keys must carry one value).
+// The levels below node 4096 are walked per key (global memory, one dependent round trip per level); the top 12 levels
+// (nodes 1..4095, shared by every path) are rebuilt wholesale in shared memory from the 4096 nodes below them — the same
+// pairwise sums, so the tree is bit-identical to the level-by-level walk, at a fraction of the dependent-latency chain.
+constexpr int kTopNodes = 4096;
 __global__ void __launch_bounds__(1024) tree_update_keys_kernel(float* __restrict__ tree, int64_t L, const int64_t* __restrict__ key,
                                                                 const float* __restrict__ prio, int64_t B) {
+    __shared__ float top[2 * kTopNodes];     // top[n] = node n for n < 2 * kTopNodes (children level loaded, the rest computed)
     for (int64_t k = threadIdx.x; k < B; k += blockDim.x)
         if (key[k] >= 0) tree[L + key[k]] = prio[k];
     __syncthreads();
-    for (int shift = 1; (L >> shift) >= 1; ++shift) {  // one tree level per iteration, leaves' parents first
+    int shift = 1;
+    for (; (L >> shift) >= kTopNodes; ++shift) {  // nodes >= kTopNodes: one tree level per iteration, leaves' parents first
         for (int64_t k = threadIdx.x; k < B; k += blockDim.x) {
             if (key[k] < 0) continue;
             int64_t node = (L + key[k]) >> shift;
             tree[node] = tree[2 * node] + tree[2 * node + 1];
         }
         __syncthreads();
+    }
+    if (L >= kTopNodes) {
+        // (L >> shift) == kTopNodes / 2: nodes [kTopNodes, 2 kTopNodes) are final; everything above is recomputed from them
+        for (int n = threadIdx.x; n < kTopNodes; n += blockDim.x) top[kTopNodes + n] = tree[kTopNodes + n];
+        __syncthreads();
+        for (int width = kTopNodes / 2; width >= 1; width >>= 1) {
+            for (int n = threadIdx.x; n < width; n += blockDim.x) top[width + n] = top[2 * (width + n)] + top[2 * (width + n) + 1];
+            __syncthreads();
+        }
+        for (int n = 1 + threadIdx.x; n < kTopNodes; n += blockDim.x) tree[n] = top[n];
+    } else {
+        for (; (L >> shift) >= 1; ++shift) {
+            for (int64_t k = threadIdx.x; k < B; k += blockDim.x) {
+                if (key[k] < 0) continue;
+                int64_t node = (L + key[k]) >> shift;
+                tree[node] = tree[2 * node] + tree[2 * node + 1];
+            }
+            __syncthreads();
+        }
     }
 }
 

@@ -35,28 +35,40 @@ def test_type_rules(pkg, ctx):
         pkg.generalized_advantage_estimation(ctx, np.ones((3, 3)), np.ones((4, 3)), 0.5, 0.3)
 
 
+def _same(a, b, exact, dt):
+    """bit-exact where the serial thread-per-series kernel runs; few long series (S < 1024 and >= 64 time steps) take the warp-segmented
+    scan, which re-associates the recurrence: 1e-5 relative to the scale of the series (an element next to a zero crossing of a
+    discounted sum of O(10) carries the rounding of its O(10) neighbours) — in practice ~2e-6"""
+    if exact:
+        return np.asfortranarray(a).tobytes(order="F") == np.asfortranarray(b).tobytes(order="F")
+    tol = 1e-5 if dt == np.float32 else 1e-13
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max()) <= tol * max(1.0, float(np.abs(b).max()))
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("shape,dims", [((1000, 33), 2), ((33, 1000), 1), ((7, 5), 1), ((7, 5), 2), ((1, 300), 2), ((300, 1), 1), ((129, 65), 1)])
-def test_random_bit_exact_vs_oracle(pkg, ctx, dt, shape, dims):
+@pytest.mark.parametrize("shape,dims", [((1000, 33), 2), ((33, 1000), 1), ((7, 5), 1), ((7, 5), 2), ((1, 300), 2), ((300, 1), 1), ((129, 65), 1),
+                                        ((4, 5000), 2), ((2000, 64), 2), ((63, 900), 1)])
+def test_random_vs_oracle(pkg, ctx, dt, shape, dims):
     rng = np.random.default_rng(hash((shape, dims)) & 0xFFFF)
     r = rng.standard_normal(shape).astype(dt)
     vshape = (shape[0] + 1, shape[1]) if dims == 1 else (shape[0], shape[1] + 1)
     v = rng.standard_normal(vshape).astype(dt)
     term = (rng.random(shape) < 0.1).astype(np.uint8)
-    ns = shape[1] if dims == 1 else shape[0]
+    ns, nt = (shape[1], shape[0]) if dims == 1 else (shape[0], shape[1])
+    exact = not (ns < 1024 and nt >= 64)
     init = rng.standard_normal(ns).astype(dt)
     g, l = dt(0.99), dt(0.95)
     for t in (None, term):
         a = pkg.generalized_advantage_estimation(ctx, r, v, g, l, dims=dims, terminal=t)
         b = O.gae(r, v, g, l, terminal=t, dims=dims, dtype=dt)
-        assert a.dtype == dt and a.shape == b.shape and np.asfortranarray(a).tobytes(order='F') == np.asfortranarray(b).tobytes(order='F')
+        assert a.dtype == dt and a.shape == b.shape and _same(a, b, exact, dt)
         for ini in (None, init):
             a = pkg.discount_rewards(ctx, r, g, dims=dims, terminal=t, init=ini)
             b = O.discount_rewards(r, g, terminal=t, init=ini, dims=dims, dtype=dt)
-            assert np.array_equal(a, b)
+            assert _same(a, b, exact, dt)
             a = pkg.discount_rewards_reduced(ctx, r, g, dims=dims, terminal=t, init=ini)
             b = O.discount_rewards(r, g, terminal=t, init=ini, dims=dims, dtype=dt, reduced=True)
-            assert np.array_equal(a, b)
+            assert _same(a, b, exact, dt)
 
 
 def test_baseline_size_properties(pkg, ctx):
