@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libb200rl.so")
+# B200RL_LIB: development override (an A/B build from `build.py --variant`); the product path is the in-tree library
+SO_PATH = os.environ.get("B200RL_LIB") or os.path.join(HERE, "libb200rl.so")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_ACTION, ERR_NCCL, ERR_OOM = -1, -2, -3, -4, -5, -6

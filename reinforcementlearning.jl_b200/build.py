@@ -44,8 +44,13 @@ def _digest(paths, flags):
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    os.makedirs(BUILD, exist_ok=True)
+def build(force=False, verbose=False, variant=None, defs=()):
+    """variant = None: the product library.  variant = "name" (+ defs = ["-DX=1", ...]): an A/B build of the same sources with extra
+    defines into build/variants/<name>/libb200rl.so, loaded instead of the product library when B200RL_LIB points at it
+    (development only: lets one GPU call time several variants of a kernel on the same box)."""
+    out_dir = BUILD if variant is None else os.path.join(BUILD, "variants", variant)
+    out_so = OUT if variant is None else os.path.join(out_dir, "libb200rl.so")
+    os.makedirs(out_dir, exist_ok=True)
     nvcc = _nvcc()
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a wrapper without libgomp specs; use the system g++
@@ -56,9 +61,9 @@ def build(force=False, verbose=False):
     objs, rebuilt = [], False
     for src, extra in srcs:
         path = os.path.join(CSRC, src)
-        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        obj = os.path.join(out_dir, src.replace(".cu", ".o"))
         stamp = obj + ".sha"
-        flags = ARCH + COMMON + extra
+        flags = ARCH + COMMON + extra + list(defs)
         dig = _digest([path] + headers, flags)
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
@@ -69,12 +74,12 @@ def build(force=False, verbose=False):
         subprocess.check_call(cmd, env=env)
         open(stamp, "w").write(dig)
         rebuilt = True
-    if rebuilt or not os.path.exists(OUT):
-        cmd = [nvcc, "-ccbin", host_cxx] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", OUT] + objs + ["-ldl"]
+    if rebuilt or not os.path.exists(out_so):
+        cmd = [nvcc, "-ccbin", host_cxx] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", out_so] + objs + ["-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd, env=env)
-    return OUT
+    return out_so
 
 
 def build_selftest():
@@ -92,5 +97,8 @@ def build_selftest():
 if __name__ == "__main__":
     if "--selftest" in sys.argv:
         print(build_selftest())
+    elif "--variant" in sys.argv:      # python build.py --variant NAME -DFOO=1 -DBAR
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        print(build(variant=name, defs=[a for a in sys.argv if a.startswith("-D")], verbose="--verbose" in sys.argv))
     else:
         print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

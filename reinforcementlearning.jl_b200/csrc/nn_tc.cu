@@ -60,10 +60,15 @@ __device__ __forceinline__ uint32_t wimg_off(int n, int k) { return (uint32_t)((
 // One CTA per SM (512 threads, role = blockIdx & 1), persistent, software-pipelined across tiles (see the loop).
 // Thread <-> data: warp w: TMEM lane quadrant q = w % 4, feature block c = w / 4; thread = sample s = 32q + lane.
 constexpr int NT7 = 512;
-constexpr int GF_T = 144;                 // feature-major fp16 image: stride between 8-sample chunks; 144 = 128 + 16: the 32 lanes of a
-                                          // 2-byte transposed store (4 groups of 8 consecutive samples) hit 4 different bank quads
-constexpr int GS_T = 16 * GF_T + 16;      // stride between 8-feature row groups (128 samples = 16 chunks)
-constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples] fp16 = 18 560 B
+// Operands of the two GEMMs that reduce over the SAMPLES (GEMM3, GEMM4: K = sample) are MN-major (SWIZZLE_NONE) images: a core
+// matrix is 8 k-rows (samples) x 16 B (8 consecutive features), element (feature f, sample s) at
+//     (f / 8) * GS_T + (s / 8) * GF_T + (s % 8) * 16 + (f % 8) * 2        (descriptor: LBO = GF_T, SBO = GS_T; profiles/umma_probe_mn.py)
+// With GF_T = 128 that is simply [feature block of 8][sample][8 features]: thread = sample writes 8 features as ONE 16-byte
+// vector, and the 32 lanes of a warp cover 512 contiguous bytes (no bank conflicts).  Until round 2 these images were K-major
+// (8 samples x one feature per 16 B): 32 two-byte transposed stores per thread and image, 4.5 M bank conflicts per launch.
+constexpr int GF_T = 128;                 // stride between 8-sample k-blocks
+constexpr int GS_T = 16 * GF_T;           // stride between 8-feature blocks (128 samples)
+constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples] fp16 = 16 KB
 // tcgen05.mma instructions pace at ~155-175 cycles each whatever their N (<= 128) (profiles/umma_probe_f16.py), so the kernel
 // minimises their number: hi|lo operands are stacked along N (and M for GEMM3), K = 16 per instruction.
 // TMEM columns: R1 = D1 of GEMM1 ([hh+lh | hl], 128 columns), then (after P3 consumed it) the dP2 A operand of GEMM2 in its first 64
@@ -73,6 +78,7 @@ constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples] fp16 = 
 // D4 = GEMM4 accumulator (16 columns): dW1 | db1 = dP1^T x [x | 1], accumulated over all tiles like D3.
 constexpr uint32_t COL_R1 = 0, COL_D2 = 128, COL_D3 = 256, COL_D4 = 400, COL_AH = 448;
 constexpr float kScaleH = 64.0f, kScaleX = 64.0f;   // power-of-two scales of the H1 / observation operands (weights: kScaleW)
+constexpr int kNo = 2;   // head outputs this kernel handles (nn_tc_bwd_supported: actor n_out <= 2, critic n_out = 1)
 
 struct SmemBwd {
     static_assert(FIMG % 128 == 0 && WIMG_BYTES % 128 == 0 && (2 * GS_T) % 16 == 0, "hi/lo(/ones) images must be adjacent to form one operand");
@@ -80,7 +86,7 @@ struct SmemBwd {
     alignas(128) uint8_t FP_lo[FIMG];      // ... lo: directly behind, so [hi; lo] is one 128-row operand
     alignas(128) uint8_t FH_full[FIMG];    // H1^T hi
     alignas(128) uint8_t FH_lo[FIMG];
-    alignas(16) uint8_t FH_ones[2 * GS_T]; // 16 more B rows of GEMM3: row 0 = 1.0 for every sample (-> db2), rows 1..15 = 0; written once
+    alignas(16) uint8_t FH_ones[2 * GS_T]; // 16 more B rows (features 128..143) of GEMM3: feature 128 = 1.0 for every sample (-> db2), the rest 0; written once
     alignas(128) uint8_t FQ_full[FIMG];    // dP1^T hi | lo: A operand of GEMM4
     alignas(128) uint8_t FQ_lo[FIMG];
     alignas(128) uint8_t B1[WIMG_BYTES];   // rows 0..63: hi, 64..127: lo of (n = out o, k = in i)  = 64 W2[o + 64 i]
@@ -90,11 +96,10 @@ struct SmemBwd {
     alignas(128) uint8_t XT[2][2 * GS_T];
     float W1[kInMax * H];
     float b1[H], b2[H];
-    float W3[H * kOutMax];
-    float b3[kOutMax];
+    float W3[H * kNo];                     // [feature][head output]
+    float b3[kNo];
     float X[kInMax * TM];
-    float Zp[4 * kOutMax * TM];            // head partials [c][o][s]
-    float Dz[kOutMax * TM];
+    float Zp[4 * kNo * TM];                // head partials [c][o][s]
     float Aux[4 * TM];
     float Red[32];
     alignas(8) uint64_t bar1;
@@ -105,7 +110,13 @@ struct SmemBwd {
     float AccD4[64 * 9];                   // ... D4: dW1[f][i] at f * 9 + i, db1[f] at f * 9 + 4
     uint32_t tmem;
 };
-__device__ __forceinline__ uint32_t fimg_off(int f, int s) { return (uint32_t)((f >> 3) * GS_T + (s >> 3) * GF_T + (f & 7) * 16 + (s & 7) * 2); }
+__device__ __forceinline__ uint32_t fimg_off(int f, int s) { return (uint32_t)((f >> 3) * GS_T + (s >> 3) * GF_T + (s & 7) * 16 + (f & 7) * 2); }
+// 16 features (8 packed fp16 pairs) of sample s, starting at feature f0 (a multiple of 16): two 16-byte vectors
+__device__ __forceinline__ void store16_feat(uint8_t* img, int f0, int s, const uint32_t (&v)[8]) {
+    uint8_t* p = img + fimg_off(f0, s);
+    *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<uint4*>(p + GS_T) = make_uint4(v[4], v[5], v[6], v[7]);
+}
 __device__ __forceinline__ float dact_f(int act, float h) { return act == B200RL_ACT_RELU ? (h > 0.f ? 1.f : 0.f) : 1.f - h * h; }
 
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
@@ -150,12 +161,12 @@ __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" 
 __device__ __forceinline__ void ready_arrive(int id) { asm volatile("bar.arrive %0, 544;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void ready_wait(int id) { asm volatile("bar.sync %0, 544;" ::"r"(id) : "memory"); }
 // per-sample loss and d(loss)/d(head outputs); identical arithmetic on every thread that evaluates a sample
-struct LossOut { float dz[kOutMax]; float l0, l1; };
-__device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, const AcHyper& hp, float inv_B, const float (&z)[kOutMax],
+struct LossOut { float dz[kNo]; float l0, l1; };
+__device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, const AcHyper& hp, float inv_B, const float (&z)[kNo],
                                                float a_bits, float lp_old, float A, float ret) {
     LossOut r;
 #pragma unroll
-    for (int o = 0; o < kOutMax; ++o) r.dz[o] = 0.f;
+    for (int o = 0; o < kNo; ++o) r.dz[o] = 0.f;
     r.l0 = 0.f; r.l1 = 0.f;
     if (role == 1) {
         float err = ret - z[0];
@@ -166,17 +177,17 @@ __device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, c
     float logp_a, gsel;
     if (!actor.heads2) {
         int na = actor.nout;
-        float lp[kOutMax], pr[kOutMax];
+        float lp[kNo], pr[kNo];
         float m = -3.4e38f;
 #pragma unroll
-        for (int o = 0; o < kOutMax; ++o) if (o < na) m = fmaxf(m, z[o]);
+        for (int o = 0; o < kNo; ++o) if (o < na) m = fmaxf(m, z[o]);
         float se = 0.f;
 #pragma unroll
-        for (int o = 0; o < kOutMax; ++o) if (o < na) se += expf(z[o] - m);
+        for (int o = 0; o < kNo; ++o) if (o < na) se += expf(z[o] - m);
         float ls = logf(se);
         float Hent = 0.f;
 #pragma unroll
-        for (int o = 0; o < kOutMax; ++o) {
+        for (int o = 0; o < kNo; ++o) {
             lp[o] = (z[o] - m) - ls;
             pr[o] = o < na ? expf(lp[o]) : 0.f;
             if (o < na) Hent -= pr[o] * lp[o];
@@ -184,7 +195,7 @@ __device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, c
         int a = __float_as_int(a_bits) - 1;
         logp_a = 0.f;
 #pragma unroll
-        for (int o = 0; o < kOutMax; ++o) if (o == a) logp_a = lp[o];
+        for (int o = 0; o < kNo; ++o) if (o == a) logp_a = lp[o];
         r.l1 = Hent;
         if (hp.algo == 0) {
             float ratio = expf(logp_a - lp_old);
@@ -200,7 +211,7 @@ __device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, c
         }
         float dlogp = -hp.w_actor * inv_B * gsel;
 #pragma unroll
-        for (int o = 0; o < kOutMax; ++o)
+        for (int o = 0; o < kNo; ++o)
             if (o < na) r.dz[o] = dlogp * ((o == a ? 1.f : 0.f) - pr[o]) + hp.w_entropy * inv_B * pr[o] * (lp[o] + Hent);
     } else {
         float mu = z[0], raw = z[1];
@@ -251,6 +262,10 @@ constexpr int NT7_ALL = NT7 + 128;
 constexpr int kFlushTiles = 8;
 constexpr int kBarRdyA = 2, kBarRdyB = 3, kBarRdyC = 4;   // named barriers: workers arrive (bar.arrive), the issuer warp waits (bar.sync)
 
+// ACT: the trunks' activation as a compile-time constant (B200RL_ACT_RELU / B200RL_ACT_TANH; -1 = read it from the descriptors, for
+// an actor and a critic with different activations).  With the activation known the relu build carries no tanhf expansions at
+// all (the runtime-act kernel was 107 KB of SASS, most of it 64 inlined tanhf bodies that a relu run branches around).
+template <int ACT>
 __global__ void __launch_bounds__(NT7_ALL, 1)
 ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, AcBatch b, float* __restrict__ partial,
                        float* __restrict__ loss_partial, int64_t np_total, float scale_base /* power of two ~ 1 / inv_B */) {
@@ -263,6 +278,8 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     // room up to |dz| / inv_B ~ 1e3 (actor) / 1.6e4 (critic) before a hi part would overflow fp16 (-> inf -> NaN loss: loud, not silent).
     const float scale_p = scale_base * (role ? 4.0f : 64.0f);
     const MlpDesc d = role ? critic : actor;
+    const int act = ACT >= 0 ? ACT : d.act;
+    const bool relu = act == B200RL_ACT_RELU;
     const int64_t poff = role ? actor.nparams() : 0;
     const float* __restrict__ p = params + poff;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -272,13 +289,15 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         const float* b1 = p + (int64_t)H * d.in;
         const float* W2 = b1 + H;
         const float* b2 = W2 + (int64_t)H * H;
-        for (int k = tid; k < kInMax * H; k += NT7_ALL) sm.W1[k] = (k / H) < d.in ? p[k] : 0.f;
-        for (int k = tid; k < H; k += NT7_ALL) { sm.b1[k] = b1[k]; sm.b2[k] = b2[k]; }
-        for (int k = tid; k < H * kOutMax; k += NT7_ALL) {
-            int j = k / kOutMax, o = k % kOutMax;
+        // relu(S z) = S relu(z) for a power-of-two S: the H1 operand scale is folded into W1 / b1 (bit-identical, one multiply less per feature)
+        const float s1 = relu ? kScaleH : 1.0f;
+        for (int k = tid; k < kInMax * H; k += NT7_ALL) sm.W1[k] = (k / H) < d.in ? p[k] * s1 : 0.f;
+        for (int k = tid; k < H; k += NT7_ALL) { sm.b1[k] = b1[k] * s1; sm.b2[k] = b2[k]; }
+        for (int k = tid; k < H * kNo; k += NT7_ALL) {
+            int j = k / kNo, o = k % kNo;
             sm.W3[k] = o < d.nout ? p[head_w(d, o, j)] : 0.f;
         }
-        if (tid < kOutMax) sm.b3[tid] = tid < d.nout ? p[head_b(d, tid)] : 0.f;
+        if (tid < kNo) sm.b3[tid] = tid < d.nout ? p[head_b(d, tid)] : 0.f;
         for (int k = tid; k < H * H; k += NT7_ALL) {
             int o = k % H, i = k / H;
             const float w = W2[k] * kScaleW;
@@ -289,19 +308,9 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             *reinterpret_cast<__half*>(sm.B2 + wimg_off(H + i, o)) = wl;
         }
     }
-    {   // constant operand rows: zero everything, then 1.0 (fp16 0x3C00) in row 0 of FH_ones and row 4 of both XT buffers
-        for (int k = tid; k < 2 * GS_T / 4; k += NT7_ALL) {
-            reinterpret_cast<uint32_t*>(sm.FH_ones)[k] = 0u;
-            reinterpret_cast<uint32_t*>(sm.XT[0])[k] = 0u;
-            reinterpret_cast<uint32_t*>(sm.XT[1])[k] = 0u;
-        }
-        __syncthreads();
-        if (tid < TM) {
-            *reinterpret_cast<uint16_t*>(sm.FH_ones + fimg_off(0, tid)) = 0x3C00u;
-            *reinterpret_cast<uint16_t*>(sm.XT[0] + fimg_off(4, tid)) = 0x3C00u;
-            *reinterpret_cast<uint16_t*>(sm.XT[1] + fimg_off(4, tid)) = 0x3C00u;
-        }
-    }
+    // constant operand rows of GEMM3's B: feature 128 = 1.0 (fp16 0x3C00) for every sample, 129..143 = 0 (the XT buffers are written whole by publish())
+    for (int k = tid; k < 2 * TM; k += NT7_ALL)
+        *reinterpret_cast<uint4*>(sm.FH_ones + 16 * k) = make_uint4(k < TM ? 0x3C00u : 0u, 0u, 0u, 0u);
     if (warp == 0) umma::tmem_alloc(&sm.tmem, 512);
     if (tid == 32) {
         umma::mbar_init(&sm.bar1, 1); umma::mbar_init(&sm.bar2, 1); umma::mbar_init(&sm.bar3, 1); umma::mbar_init(&sm.bar4, 1);
@@ -312,7 +321,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     umma::fence_after_sync();
     const uint32_t tmem = sm.tmem;
     const uint32_t idesc = umma::make_idesc_f16(128, 64, 0, 0), idesc128 = umma::make_idesc_f16(128, 128, 0, 0);
-    const uint32_t idesc144 = umma::make_idesc_f16(128, 144, 0, 0), idesc16 = umma::make_idesc_f16(128, 16, 0, 0);
+    const uint32_t idesc144 = umma::make_idesc_f16(128, 144, 1, 1), idesc16 = umma::make_idesc_f16(128, 16, 1, 1);   // GEMM3 / GEMM4: MN-major A and B
     // undo the operand scales (exact powers of two): D1 = H1 W2, D2 = dP2 W2, D3 = dP2^T [H1 | 1], D4 = dP1^T [x | 1]
     const float inv_s1 = 1.0f / (kScaleH * kScaleW), inv_s2 = 1.0f / (scale_p * kScaleW), inv_s3 = 1.0f / (scale_p * kScaleH), inv_sp = 1.0f / scale_p,
                 inv_s4 = 1.0f / (scale_p * kScaleX);
@@ -345,8 +354,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
-                    umma::mma_f16(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc144, d3_acc);   // N = 144: [H1^T hi | H1^T lo | ones]
-                    d3_acc = 1u;
+                    umma::mma_f16(tmem + COL_D3, dFPf + adt, dFHf + adt, idesc144, k ? 1u : d3_acc);   // N = 144: [H1^T hi | H1^T lo | ones]
                 }
             };
             // GEMM4 (dW1 | db1 += dP1^T x [x | 1], K = 128 samples): A rows 0..63 = hi, 64..127 = lo; B columns 0..7 = [x hi, 1], 8..15 = x lo
@@ -356,16 +364,16 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint64_t adt = (uint64_t)(k * (2 * GF_T / 16));
-                    umma::mma_f16(tmem + COL_D4, dFQf + adt, dXT + adt, idesc16, d4_acc);
-                    d4_acc = 1u;
+                    umma::mma_f16(tmem + COL_D4, dFQf + adt, dXT + adt, idesc16, k ? 1u : d4_acc);
                 }
             };
-            // One thread issues every MMA, so the tensor pipe executes them in program order: G2(t) reads R1 before G1(t+1)
-            // overwrites it without any cross-thread fence.  Per tile: G2(t) | G1(t+1) | G3(t) | G4(t).
+            // One warp issues every MMA (its elected lane: umma::elect_one), so the tensor pipe executes them in program order: G2(t)
+            // reads R1 before G1(t+1) overwrites it without any cross-thread fence.  Per tile: G2(t) | G1(t+1) | G3(t) | G4(t).
+            // d3_acc / d4_acc are warp-uniform (every lane tracks them).
             if (cta < ntiles) {
                 ready_wait(kBarRdyB);                      // H1 operand of the first tile is in TMEM
                 umma::fence_after_sync();
-                if (lane == 0) { issue_ts3(COL_R1, COL_AH, dB1f); umma::commit(&sm.bar1); }
+                if (umma::elect_one()) { issue_ts3(COL_R1, COL_AH, dB1f); umma::commit(&sm.bar1); }
                 __syncwarp();
             }
             int buf = 0, ord = 0;     // ord = ordinal of the tile within this CTA (the workers count the same way)
@@ -373,19 +381,21 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 if (ord % kFlushTiles == 0) { d3_acc = 0u; d4_acc = 0u; }   // the workers have flushed D3 / D4 before handing this tile's operands over
                 ready_wait(kBarRdyA);                      // dP2 operand (TMEM) and the dP2^T / H1^T images (smem) of this tile
                 umma::fence_after_sync();
-                if (lane == 0) { issue_ts3(COL_D2, COL_R1, dB2f); umma::commit(&sm.bar2); }      // GEMM2: dH1 = dP2 x W2
+                if (umma::elect_one()) { issue_ts3(COL_D2, COL_R1, dB2f); umma::commit(&sm.bar2); }      // GEMM2: dH1 = dP2 x W2
                 __syncwarp();
                 if (tile + nctas < ntiles) {
                     ready_wait(kBarRdyB);                  // H1 operand of the next tile
                     umma::fence_after_sync();
-                    if (lane == 0) { issue_ts3(COL_R1, COL_AH, dB1f); umma::commit(&sm.bar1); }  // GEMM1 of the next tile
+                    if (umma::elect_one()) { issue_ts3(COL_R1, COL_AH, dB1f); umma::commit(&sm.bar1); }  // GEMM1 of the next tile
                     __syncwarp();
                 }
-                if (lane == 0) { issue_g3(); umma::commit(&sm.bar3); }                           // GEMM3 of this tile
+                if (umma::elect_one()) { issue_g3(); umma::commit(&sm.bar3); }                   // GEMM3 of this tile
+                d3_acc = 1u;
                 __syncwarp();
                 ready_wait(kBarRdyC);                      // dP1^T image of this tile (its x^T | 1 operand was written at publish time)
                 umma::fence_after_sync();
-                if (lane == 0) { issue_g4(buf); umma::commit(&sm.bar4); }                        // GEMM4 of this tile
+                if (umma::elect_one()) { issue_g4(buf); umma::commit(&sm.bar4); }                // GEMM4 of this tile
+                d4_acc = 1u;
                 __syncwarp();
             }
         }
@@ -513,15 +523,9 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             uint32_t h01, l01, h23, l23;   // x^T operand of GEMM4 (rows 0..3 hi, 8..11 lo)
             split2(pf[0] * kScaleX, pf[1] * kScaleX, h01, l01);
             split2(pf[2] * kScaleX, pf[3] * kScaleX, h23, l23);
-            uint8_t* xt = sm.XT[xbuf];
-            *reinterpret_cast<uint16_t*>(xt + fimg_off(0, s)) = (uint16_t)(h01 & 0xFFFFu);
-            *reinterpret_cast<uint16_t*>(xt + fimg_off(1, s)) = (uint16_t)(h01 >> 16);
-            *reinterpret_cast<uint16_t*>(xt + fimg_off(2, s)) = (uint16_t)(h23 & 0xFFFFu);
-            *reinterpret_cast<uint16_t*>(xt + fimg_off(3, s)) = (uint16_t)(h23 >> 16);
-            *reinterpret_cast<uint16_t*>(xt + fimg_off(8, s)) = (uint16_t)(l01 & 0xFFFFu);
-            *reinterpret_cast<uint16_t*>(xt + fimg_off(9, s)) = (uint16_t)(l01 >> 16);
-            *reinterpret_cast<uint16_t*>(xt + fimg_off(10, s)) = (uint16_t)(l23 & 0xFFFFu);
-            *reinterpret_cast<uint16_t*>(xt + fimg_off(11, s)) = (uint16_t)(l23 >> 16);
+            uint8_t* xt = sm.XT[xbuf] + fimg_off(0, s);
+            *reinterpret_cast<uint4*>(xt) = make_uint4(h01, h23, 0x3C00u, 0u);          // features 0..3 = x hi, 4 = 1.0 (-> db1), 5..7 = 0
+            *reinterpret_cast<uint4*>(xt + GS_T) = make_uint4(l01, l23, 0u, 0u);       // features 8..11 = x lo
         } else if (b.rec) {
             if (c == 1) {   // {action bits, logp_old, advantage, return}; the role that does not use a value stores 0 like the SoA path
                 sm.Aux[s] = pf[0];
@@ -541,8 +545,10 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         xbuf ^= 1;
         if (t + nctas < ntiles) { gather_tile(t + nctas, pf); have_pf = true; } else have_pf = false;
     };
+    uint32_t h1pos = 0, h1pos_tile = 0;   // relu: bit k = (H1[16c + k] > 0) of the tile layer1() ran on last / of the tile P7 works on
     auto layer1 = [&]() {   // P1: H1 = act(W1 x + b1) -> TMEM A operand (hi | lo fp16 pairs)
         float xo[kInMax];
+        uint32_t pos = 0;
 #pragma unroll
         for (int k = 0; k < kInMax; ++k) xo[k] = sm.X[k * TM + s];
         uint32_t hi8[8], lo8[8];
@@ -556,9 +562,17 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 float4 w = *reinterpret_cast<const float4*>(sm.W1 + k * H + f0);
                 h[0] = fmaf(w.x, xo[k], h[0]); h[1] = fmaf(w.y, xo[k], h[1]); h[2] = fmaf(w.z, xo[k], h[2]); h[3] = fmaf(w.w, xo[k], h[3]);
             }
-            split2(act_f(d.act, h[0]) * kScaleH, act_f(d.act, h[1]) * kScaleH, hi8[2 * ch], lo8[2 * ch]);
-            split2(act_f(d.act, h[2]) * kScaleH, act_f(d.act, h[3]) * kScaleH, hi8[2 * ch + 1], lo8[2 * ch + 1]);
+            if (relu) {   // W1 / b1 carry the operand scale already
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { pos |= (h[e] > 0.f ? 1u : 0u) << (4 * ch + e); h[e] = fmaxf(h[e], 0.f); }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = act_f(act, h[e]) * kScaleH;
+            }
+            split2(h[0], h[1], hi8[2 * ch], lo8[2 * ch]);
+            split2(h[2], h[3], hi8[2 * ch + 1], lo8[2 * ch + 1]);
         }
+        h1pos = pos;
         umma::tmem_st8(tmem + lane_base + COL_AH + 8 * c, hi8);
         umma::tmem_st8(tmem + lane_base + COL_AH + 32 + 8 * c, lo8);
         umma::tmem_st_wait();
@@ -584,16 +598,16 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         {
             float v[16], v2[16];
             umma::tmem_ld16x2(tmem + lane_base + COL_R1 + 16 * c, tmem + lane_base + COL_R1 + 64 + 16 * c, v, v2);
-            float zp[kOutMax] = {0.f, 0.f, 0.f, 0.f};
+            float zp[kNo] = {0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int f = 16 * c + k;
-                h2[k] = act_f(d.act, fmaf(v[k] + v2[k], inv_s1, sm.b2[f]));   // (hh + lh) + hl, operand scale undone (exact)
-                float4 w = *reinterpret_cast<const float4*>(sm.W3 + f * kOutMax);
-                zp[0] = fmaf(w.x, h2[k], zp[0]); zp[1] = fmaf(w.y, h2[k], zp[1]); zp[2] = fmaf(w.z, h2[k], zp[2]); zp[3] = fmaf(w.w, h2[k], zp[3]);
+                h2[k] = act_f(act, fmaf(v[k] + v2[k], inv_s1, sm.b2[f]));   // (hh + lh) + hl, operand scale undone (exact)
+                float2 w = *reinterpret_cast<const float2*>(sm.W3 + f * kNo);
+                zp[0] = fmaf(w.x, h2[k], zp[0]); zp[1] = fmaf(w.y, h2[k], zp[1]);
             }
 #pragma unroll
-            for (int o = 0; o < kOutMax; ++o) sm.Zp[(c * kOutMax + o) * TM + s] = zp[o];
+            for (int o = 0; o < kNo; ++o) sm.Zp[(c * kNo + o) * TM + s] = zp[o];
         }
         K7_T(1);
         worker_sync();
@@ -602,29 +616,31 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         //            dW3 / db2 partials, dP2 = (W3^T dz) .* act'(H2) -> TMEM A operand (over D1, which this thread
         //            has just consumed) + dP2^T / H1^T images for GEMM3 ----------------------------------------------
         {
-            float z[kOutMax];
+            float z[kNo];
 #pragma unroll
-            for (int o = 0; o < kOutMax; ++o)
-                z[o] = sm.b3[o] + ((sm.Zp[o * TM + s] + sm.Zp[(kOutMax + o) * TM + s]) + (sm.Zp[(2 * kOutMax + o) * TM + s] + sm.Zp[(3 * kOutMax + o) * TM + s]));
+            for (int o = 0; o < kNo; ++o)
+                z[o] = sm.b3[o] + ((sm.Zp[o * TM + s] + sm.Zp[(kNo + o) * TM + s]) + (sm.Zp[(2 * kNo + o) * TM + s] + sm.Zp[(3 * kNo + o) * TM + s]));
             const bool valid = (tile * TM + s) < b.B;
             LossOut lo_ = sample_loss(actor, role, hp, b.inv_B, z, sm.Aux[s], sm.Aux[TM + s], sm.Aux[2 * TM + s], sm.Aux[3 * TM + s]);
-            float dz[kOutMax];
+            float dz[kNo];
 #pragma unroll
-            for (int o = 0; o < kOutMax; ++o) dz[o] = valid ? lo_.dz[o] : 0.f;
+            for (int o = 0; o < kNo; ++o) dz[o] = valid ? lo_.dz[o] : 0.f;
             if (c == 0 && valid) { l0 += lo_.l0; l1 += lo_.l1; gb3a0 += dz[0]; gb3a1 += dz[1]; }
+            // dP2 operand = scale_p * (W3^T dz) .* act'(H2): the power-of-two operand scale rides on dz (exact, bit-identical to scaling dP2)
+            const float dzs0 = dz[0] * scale_p, dzs1 = dz[1] * scale_p;
             float dp[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int f = 16 * c + k;
-                float4 w = *reinterpret_cast<const float4*>(sm.W3 + f * kOutMax);
-                float dh = fmaf(w.x, dz[0], fmaf(w.y, dz[1], fmaf(w.z, dz[2], w.w * dz[3])));
-                dp[k] = dh * dact_f(d.act, h2[k]);
+                float2 w = *reinterpret_cast<const float2*>(sm.W3 + f * kNo);
+                const float dh = fmaf(w.x, dzs0, w.y * dzs1);
+                dp[k] = relu ? (h2[k] > 0.f ? dh : 0.f) : dh * (1.f - h2[k] * h2[k]);
                 g3[0][k] = fmaf(dz[0], h2[k], g3[0][k]);
                 g3[1][k] = fmaf(dz[1], h2[k], g3[1][k]);
             }
             uint32_t hi8[8], lo8[8];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) split2(dp[2 * m] * scale_p, dp[2 * m + 1] * scale_p, hi8[m], lo8[m]);
+            for (int m = 0; m < 8; ++m) split2(dp[2 * m], dp[2 * m + 1], hi8[m], lo8[m]);
             umma::tmem_st8(tmem + lane_base + COL_R1 + 8 * c, hi8);
             umma::tmem_st8(tmem + lane_base + COL_R1 + 32 + 8 * c, lo8);
             K7_T(3);
@@ -636,24 +652,12 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             }
             if (ord > 0 && ord % kFlushTiles == 0) flush_d3();   // every GEMM3 so far has completed; the next one restarts the accumulator
             K7_T(4);
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const uint32_t o0 = fimg_off(16 * c + 2 * m, s), o1 = fimg_off(16 * c + 2 * m + 1, s);
-                *reinterpret_cast<uint16_t*>(sm.FP_full + o0) = (uint16_t)(hi8[m] & 0xFFFFu);
-                *reinterpret_cast<uint16_t*>(sm.FP_full + o1) = (uint16_t)(hi8[m] >> 16);
-                *reinterpret_cast<uint16_t*>(sm.FP_lo + o0) = (uint16_t)(lo8[m] & 0xFFFFu);
-                *reinterpret_cast<uint16_t*>(sm.FP_lo + o1) = (uint16_t)(lo8[m] >> 16);
-            }
+            store16_feat(sm.FP_full, 16 * c, s, hi8);
+            store16_feat(sm.FP_lo, 16 * c, s, lo8);
             // H1 of this tile (hi | lo fp16 pairs) back from its TMEM operand -> H1^T image
             umma::tmem_ld8x2(tmem + lane_base + COL_AH + 8 * c, tmem + lane_base + COL_AH + 32 + 8 * c, hi8, lo8);
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const uint32_t o0 = fimg_off(16 * c + 2 * m, s), o1 = fimg_off(16 * c + 2 * m + 1, s);
-                *reinterpret_cast<uint16_t*>(sm.FH_full + o0) = (uint16_t)(hi8[m] & 0xFFFFu);
-                *reinterpret_cast<uint16_t*>(sm.FH_full + o1) = (uint16_t)(hi8[m] >> 16);
-                *reinterpret_cast<uint16_t*>(sm.FH_lo + o0) = (uint16_t)(lo8[m] & 0xFFFFu);
-                *reinterpret_cast<uint16_t*>(sm.FH_lo + o1) = (uint16_t)(lo8[m] >> 16);
-            }
+            store16_feat(sm.FH_full, 16 * c, s, hi8);
+            store16_feat(sm.FH_lo, 16 * c, s, lo8);
             umma::tmem_st_wait();
         }
         K7_T(5);
@@ -664,6 +668,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         worker_sync();              // Aux / Zp / X are free for the next tile
         K7_T(6);
         K7_T(7);
+        h1pos_tile = h1pos;         // this tile's H1 signs, before layer1() of the next tile replaces them
         if (has_next) {
             publish(tile + nctas);
             K7_T(8);
@@ -687,15 +692,27 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 float v2[16];
                 umma::tmem_ld16x2(tmem + lane_base + COL_D2 + 16 * c, tmem + lane_base + COL_D2 + 64 + 16 * c, v, v2);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] = (v[k] + v2[k]) * inv_s2;   // operand scales undone (exact)
+                // D2 carries scale_p * kScaleW; the dP1 operand wants scale_p: one exact power-of-two factor (bit-identical to unscaling
+                // to dH1 and rescaling)
+                for (int k = 0; k < 16; ++k) v[k] = (v[k] + v2[k]) * (1.0f / kScaleW);
             }
-            const float inv_h = 1.0f / kScaleH;
+            if (relu) {   // act'(H1) = (H1 > 0): the signs layer1() kept in a register
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t off = fimg_off(16 * c + k, s);                  // this tile's H1 = (hi + lo) / scale (image still intact)
-                float h1k = half_bits_to_float(*reinterpret_cast<const uint16_t*>(sm.FH_full + off));
-                if (d.act != B200RL_ACT_RELU) h1k = (h1k + half_bits_to_float(*reinterpret_cast<const uint16_t*>(sm.FH_lo + off))) * inv_h;   // relu only needs the sign
-                v[k] = v[k] * dact_f(d.act, h1k);
+                for (int k = 0; k < 16; ++k) v[k] = ((h1pos_tile >> k) & 1u) ? v[k] : 0.f;
+            } else {
+                const float inv_h = 1.0f / kScaleH;
+#pragma unroll
+                for (int g8 = 0; g8 < 2; ++g8) {                               // this tile's H1 = (hi + lo) / scale (image still intact)
+                    const uint32_t off = fimg_off(16 * c + 8 * g8, s);
+                    const uint4 hv = *reinterpret_cast<const uint4*>(sm.FH_full + off), lv = *reinterpret_cast<const uint4*>(sm.FH_lo + off);
+                    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[m])), lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[m]));
+                        v[8 * g8 + 2 * m] *= dact_f(act, (hf.x + lf.x) * inv_h);
+                        v[8 * g8 + 2 * m + 1] *= dact_f(act, (hf.y + lf.y) * inv_h);
+                    }
+                }
             }
             if (gemm4_pending) {   // the previous tile's GEMM4 must have consumed the dP1^T image before it is overwritten
                 umma::mbar_wait(&sm.bar4, ph4);
@@ -703,15 +720,12 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 umma::fence_after_sync();
             }
             if (ord > 0 && ord % kFlushTiles == 0) flush_d4();
+            {
+                uint32_t hi8[8], lo8[8];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                uint32_t hi, lo;
-                split2(v[2 * m] * scale_p, v[2 * m + 1] * scale_p, hi, lo);
-                const uint32_t o0 = fimg_off(16 * c + 2 * m, s), o1 = fimg_off(16 * c + 2 * m + 1, s);
-                *reinterpret_cast<uint16_t*>(sm.FQ_full + o0) = (uint16_t)(hi & 0xFFFFu);
-                *reinterpret_cast<uint16_t*>(sm.FQ_full + o1) = (uint16_t)(hi >> 16);
-                *reinterpret_cast<uint16_t*>(sm.FQ_lo + o0) = (uint16_t)(lo & 0xFFFFu);
-                *reinterpret_cast<uint16_t*>(sm.FQ_lo + o1) = (uint16_t)(lo >> 16);
+                for (int m = 0; m < 8; ++m) split2(v[2 * m], v[2 * m + 1], hi8[m], lo8[m]);
+                store16_feat(sm.FQ_full, 16 * c, s, hi8);
+                store16_feat(sm.FQ_lo, 16 * c, s, lo8);
             }
             gemm4_pending = true;
         }
@@ -805,11 +819,19 @@ int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const Ml
                        const AcBatch& b, float* partial, float* loss_partial, int64_t np) {
     size_t smem = sizeof(SmemBwd) + 128;
     static unsigned long long attr_devices = 0;   // once per device
-    if (first_use_on_device(attr_devices, ctx->device))
-        CUDA_TRY(cudaFuncSetAttribute(ac_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (first_use_on_device(attr_devices, ctx->device)) {
+        CUDA_TRY(cudaFuncSetAttribute(ac_loss_grad_tc_kernel<B200RL_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(ac_loss_grad_tc_kernel<B200RL_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(ac_loss_grad_tc_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     // dP2 ~ inv_B x O(1..100): scale it into fp16's normal range with a power of two (exact, undone on the accumulators)
     const float scale_base = exp2f(floorf(log2f(1.0f / b.inv_B)));
-    ac_loss_grad_tc_kernel<<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np, scale_base);
+    if (actor.act == critic.act && actor.act == B200RL_ACT_RELU)
+        ac_loss_grad_tc_kernel<B200RL_ACT_RELU><<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np, scale_base);
+    else if (actor.act == critic.act && actor.act == B200RL_ACT_TANH)
+        ac_loss_grad_tc_kernel<B200RL_ACT_TANH><<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np, scale_base);
+    else
+        ac_loss_grad_tc_kernel<-1><<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np, scale_base);
     LAUNCH_CHECK(ctx);
     return B200RL_OK;
 }

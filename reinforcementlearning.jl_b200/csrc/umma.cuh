@@ -43,6 +43,24 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_maj
            | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// One elected lane of a converged warp (elect.sync).  The MMA issue code must sit under THIS predicate, not under
+// `lane == 0`: ptxas only knows that a single lane is active when the predicate comes from elect.sync — otherwise it wraps
+// every tcgen05.mma / tcgen05.commit (uniform-datapath instructions) in its own ELECT ... BRA.U.ANY serialisation loop,
+// which costs the issuing thread ~100 cycles per instruction (profiles/umma_pacing.py).
+__device__ __forceinline__ bool elect_one() {
+#ifdef B200RL_NO_ELECT   // A/B build only (build.py --variant): the old `lane == 0` predicate
+    return (threadIdx.x & 31) == 0;
+#endif
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");

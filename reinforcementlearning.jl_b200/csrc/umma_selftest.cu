@@ -110,3 +110,87 @@ extern "C" int b200rl_selftest_umma(b200rl_ctx* ctx, const void* a_img_host, uin
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return B200RL_OK;
 }
+
+// ---- pacing probe: cycles per tcgen05.mma for a given shape / shared-memory layout type / operand source -------------------
+// (operand VALUES are irrelevant: the images are zero-filled; only the issue and completion times are read)
+namespace {
+struct PaceArgs {
+    uint32_t idesc;          // instruction descriptor (M, N, kind::f16)
+    uint32_t layout;         // shared-memory descriptor layout_type (bits 61..63): 0 none, 1 128B_base32B, 2 128B, 4 64B, 6 32B
+    uint32_t lbo, sbo;       // descriptor byte offsets
+    uint32_t kadv;           // start-address advance per instruction (bytes), cycled over 4 steps
+    int n_mma;               // instructions between the two clock reads
+    int ts;                  // 1: A from TMEM
+    int alt_d;               // 1: alternate between two accumulators (columns 0 / 128)
+    int sleepers;            // 1: the other threads nanosleep instead of spinning on the mbarrier
+    int elect;               // 1: the issuing lane is chosen by elect.sync (0: threadIdx.x == 0)
+    float* out;              // [0] issue cycles, [1] issue + completion cycles
+};
+__global__ void __launch_bounds__(128) umma_pacing_kernel(PaceArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    for (uint32_t k = threadIdx.x; k < 128 * 1024 / 4; k += blockDim.x) ((uint32_t*)smem)[k] = 0u;
+    umma::fence_proxy_async();
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
+    if (threadIdx.x == 32) umma::mbar_init(&s_bar, 1);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    const uint64_t hi = ((uint64_t)(a.layout & 7u) << 61);
+    const uint64_t dA = umma::make_desc(umma::smem_u32(smem), a.lbo, a.sbo) | hi;
+    const uint64_t dB = umma::make_desc(umma::smem_u32(smem + 64 * 1024), a.lbo, a.sbo) | hi;
+    long long t0 = clock64(), t1 = t0;
+    if (a.elect) {
+        if (warp == 0 && umma::elect_one()) {
+            for (int i = 0; i < a.n_mma; i += 4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t d = tmem + ((a.alt_d && (j & 1)) ? 128u : 0u);
+                    if (a.ts) umma::mma_f16_ts(d, tmem + 448 + 8 * j, dB + (uint64_t)((j * a.kadv) >> 4), a.idesc, i + j > 1 ? 1u : 0u);
+                    else umma::mma_f16(d, dA + (uint64_t)((j * a.kadv) >> 4), dB + (uint64_t)((j * a.kadv) >> 4), a.idesc, i + j > 1 ? 1u : 0u);
+                }
+            }
+            t1 = clock64();
+            umma::commit(&s_bar);
+        }
+        __syncwarp();
+    } else if (threadIdx.x == 0) {
+        for (int i = 0; i < a.n_mma; ++i) {
+            const uint64_t adv = (uint64_t)(((i & 3) * a.kadv) >> 4);
+            const uint32_t d = tmem + ((a.alt_d && (i & 1)) ? 128u : 0u);
+            if (a.ts) umma::mma_f16_ts(d, tmem + 448 + 8 * (i & 3), dB + adv, a.idesc, i > 1 ? 1u : 0u);
+            else umma::mma_f16(d, dA + adv, dB + adv, a.idesc, i > 1 ? 1u : 0u);
+        }
+        t1 = clock64();
+        umma::commit(&s_bar);
+    }
+    if (a.sleepers && threadIdx.x != 0) __nanosleep(20000 + 60 * a.n_mma);
+    umma::mbar_wait(&s_bar, 0);
+    long long t2 = clock64();
+    umma::fence_after_sync();
+    if (t1 != t0) { a.out[0] = (float)(t1 - t0); a.out[1] = (float)(t2 - t0); }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+extern "C" int b200rl_selftest_pacing(b200rl_ctx* ctx, const uint32_t* p10 /* idesc, layout, lbo, sbo, kadv, n_mma, ts, alt_d, sleepers, elect */,
+                                      float* out2_host) {
+    TRY(ctx_bind(ctx));
+    REQUIRE(p10 && out2_host, B200RL_ERR_INVALID, "null argument");
+    void* sc;
+    TRY(ctx_scratch(ctx, 1024, &sc));
+    sc = (void*)(((uintptr_t)sc + 15) & ~(uintptr_t)15);
+    PaceArgs a{p10[0], p10[1], p10[2], p10[3], p10[4], (int)p10[5], (int)p10[6], (int)p10[7], (int)p10[8], (int)p10[9], (float*)sc};
+    const size_t smem = 128 * 1024;
+    CUDA_TRY(cudaFuncSetAttribute(umma_pacing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_pacing_kernel<<<1, 128, smem, ctx->stream>>>(a);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(cudaMemcpyAsync(out2_host, sc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200RL_OK;
+}
