@@ -98,9 +98,7 @@ struct SmemBwd {
     float b1[H], b2[H];
     float W3[H * kNo];                     // [feature][head output]
     float b3[kNo];
-    float X[kInMax * TM];
     float Zp[4 * kNo * TM];                // head partials [c][o][s]
-    float Aux[4 * TM];
     float Red[32];
     alignas(8) uint64_t bar1;
     alignas(8) uint64_t bar2;
@@ -157,6 +155,11 @@ __device__ __forceinline__ float lane_transpose_reduce32(float (&v)[32], int lan
 
 // worker-only barrier (the MMA warp never joins it)
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// barrier of the four warps that share one TMEM lane quadrant q (= one 32-sample slice of the tile, feature blocks c = 0..3).
+// Everything the workers exchange per tile (X, Aux, Zp, the TMEM columns of a lane) is exchanged between the four threads of ONE
+// sample, i.e. inside such a group, so the per-tile barriers are group-local (ids 5..8, 128 threads) and the four groups — one
+// per warp scheduler — drift freely within a tile; the tensor-core hand-overs (bar.arrive) and the mbarrier waits bound the drift.
+__device__ __forceinline__ void group_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(5 + q) : "memory"); }
 // operand hand-over to the issuer warp: 512 worker threads arrive without waiting, the 32 issuer threads wait
 __device__ __forceinline__ void ready_arrive(int id) { asm volatile("bar.arrive %0, 544;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void ready_wait(int id) { asm volatile("bar.sync %0, 544;" ::"r"(id) : "memory"); }
@@ -414,49 +417,42 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     uint32_t ph1 = 0, ph2 = 0, ph3 = 0, ph4 = 0;
     bool gemm4_pending = false;
     int xbuf = 0;                     // XT buffer of the tile being published (tile parity within this CTA)
-    // random gather of one tile into registers, spread over all 512 threads: thread (sample s, block c) loads part c of
-    // sample s — c = 0: the state (up to 4 floats), 1: action bits, 2: logp_old (actor) / return (critic), 3: advantage —
-    // so nobody has more than one dependent load chain.  Issued one tile ahead: the L2 / HBM latency hides behind the
-    // previous tile.  No arithmetic on the loaded values here (that would stall on them).
+    // Random gather, per THREAD: each of the four feature-block threads of a sample loads the sample's whole 32-byte record
+    // {state | action bits, logp_old, advantage, return} itself (two 16-byte loads from one sector; the three repeats hit L1), so
+    // nothing is exchanged through shared memory and no barrier separates the gather from layer 1 or from the loss.  Software
+    // pipeline: the records are requested one tile ahead and the permuted index two tiles ahead (an index array adds a dependent
+    // load; the Feistel permutation is ALU work), so neither latency is ever waited for.  No arithmetic on loaded values here.
 #ifdef B200RL_K7_TIMING
     long long tprev_ = clock64();
 #endif
-    float pf[kInMax];
-    bool have_pf = false;
     const int pbits = b200perm::perm_bits(b.perm_n);
     const uint32_t pkey = ac_perm_key(b);
-    auto gather_tile = [&](int64_t t, float (&o)[kInMax]) {
-        int64_t j = t * TM + s;
+    auto index_of = [&](int64_t t) -> int32_t {      // rollout index of this thread's sample in tile t, -1 = padding
+        const int64_t j = t * TM + s;
+        if (t >= ntiles || j >= b.B) return -1;
+        return b.idx ? b.idx[j] : (int32_t)perm_index_bits((uint32_t)(b.perm_offset + j), b.perm_n, pkey, pbits);
+    };
+    auto request = [&](int32_t g, float (&x)[kInMax], float (&a)[4]) {
 #pragma unroll
-        for (int k = 0; k < kInMax; ++k) o[k] = 0.f;
-        if (j >= b.B) return;
-        if (b.rec) {   // packed records: thread c = 0 takes the state half, c = 1 the scalar half of the sample's 32-byte sector
-            if (c >= 2) return;
-            int64_t gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index_bits((uint32_t)(b.perm_offset + j), b.perm_n, pkey, pbits);
-            K7_T(17);
-            float4 v4 = b.rec[2 * gidx + c];
-            o[0] = v4.x; o[1] = v4.y; o[2] = v4.z; o[3] = v4.w;
-            return;
-        }
-        int64_t gidx = b.idx ? (int64_t)b.idx[j] : (int64_t)perm_index_bits((uint32_t)(b.perm_offset + j), b.perm_n, pkey, pbits);
-        K7_T(17);
-        if (c == 0) {
-            if (b.ns == 4) {
-                float4 v4 = reinterpret_cast<const float4*>(b.states)[gidx];
-                o[0] = v4.x; o[1] = v4.y; o[2] = v4.z; o[3] = v4.w;
-            } else {
+        for (int k = 0; k < kInMax; ++k) { x[k] = 0.f; a[k] = 0.f; }
+        if (g < 0) return;
+        if (b.rec) {
+            const float4 v0 = b.rec[2 * (int64_t)g], v1 = b.rec[2 * (int64_t)g + 1];
+            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+            a[0] = v1.x; a[1] = v1.y; a[2] = v1.z; a[3] = v1.w;
+        } else {                                     // separate rollout columns (direct API calls)
 #pragma unroll
-                for (int i = 0; i < kInMax; ++i)    // static indices only: a runtime-indexed o[] would live in local memory
-                    if (i < b.ns) o[i] = b.states[(int64_t)b.ns * gidx + i];   // and every prefetch would stall on its spill store
-            }
-        } else if (role == 0) {
-            if (c == 1) o[0] = reinterpret_cast<const float*>(b.actions)[gidx];
-            else if (c == 2) o[0] = b.logp_old ? b.logp_old[gidx] : 0.f;
-            else o[0] = b.adv[gidx];
-        } else if (c == 2) {
-            o[0] = b.ret[gidx];
+            for (int i = 0; i < kInMax; ++i)         // static indices only: a runtime-indexed array would live in local memory
+                if (i < b.ns) x[i] = b.states[(int64_t)b.ns * g + i];
+            a[0] = reinterpret_cast<const float*>(b.actions)[g];
+            a[1] = b.logp_old ? b.logp_old[g] : 0.f;
+            a[2] = b.adv[g];
+            a[3] = b.ret[g];
         }
     };
+    float pfx[kInMax], pfa[4];        // records of the NEXT tile (in flight)
+    float aux[4];                     // {action bits, logp_old, (normalised) advantage, return} of the tile whose loss is evaluated next
+    int32_t gi_next;                  // index of this thread's sample two tiles ahead
     bool gemm3_pending = false;
     float* const out = partial + (int64_t)cta * np_total + poff;
     float* const gW1 = out;
@@ -515,42 +511,33 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     //   tensor core:              G2(t) ......... G1(t+1) .... G3(t) .....
     // G2(t) runs under P0/P1(t+1), G1(t+1) under P7(t), G3(t) under P3/P45(t+1); the issuer warp queues each GEMM as soon
     // as the workers have handed its operands over (ready_arrive), so no worker ever blocks on the MMA queue.
-    auto publish = [&](int64_t t) {   // P0: this tile's gathered samples -> shared memory, prefetch the following tile
-        if (!have_pf) gather_tile(t, pf);
-        if (c == 0) {
+    // P0: the next tile's records leave the prefetch registers (x -> layer 1 and the x^T operand of GEMM4, scalars -> aux),
+    // the records of the tile after it are requested, the index of the one after that computed / requested
+    float xo[kInMax];
+    auto publish = [&](int64_t t) {
 #pragma unroll
-            for (int i = 0; i < kInMax; ++i) sm.X[i * TM + s] = pf[i];
-            uint32_t h01, l01, h23, l23;   // x^T operand of GEMM4 (rows 0..3 hi, 8..11 lo)
-            split2(pf[0] * kScaleX, pf[1] * kScaleX, h01, l01);
-            split2(pf[2] * kScaleX, pf[3] * kScaleX, h23, l23);
+        for (int i = 0; i < kInMax; ++i) xo[i] = pfx[i];
+        aux[0] = pfa[0];
+        aux[1] = role == 0 ? pfa[1] : 0.f;
+        aux[2] = role == 0 ? (hp.normalize_adv ? (pfa[2] - mean) * inv_std : pfa[2]) : 0.f;
+        aux[3] = role == 0 ? 0.f : pfa[3];
+        if (c == 0) {
+            uint32_t h01, l01, h23, l23;   // x^T operand of GEMM4 (features 0..3 hi, 8..11 lo)
+            split2(xo[0] * kScaleX, xo[1] * kScaleX, h01, l01);
+            split2(xo[2] * kScaleX, xo[3] * kScaleX, h23, l23);
             uint8_t* xt = sm.XT[xbuf] + fimg_off(0, s);
             *reinterpret_cast<uint4*>(xt) = make_uint4(h01, h23, 0x3C00u, 0u);          // features 0..3 = x hi, 4 = 1.0 (-> db1), 5..7 = 0
             *reinterpret_cast<uint4*>(xt + GS_T) = make_uint4(l01, l23, 0u, 0u);       // features 8..11 = x lo
-        } else if (b.rec) {
-            if (c == 1) {   // {action bits, logp_old, advantage, return}; the role that does not use a value stores 0 like the SoA path
-                sm.Aux[s] = pf[0];
-                sm.Aux[TM + s] = role == 0 ? pf[1] : 0.f;
-                sm.Aux[2 * TM + s] = role == 0 ? (hp.normalize_adv ? (pf[2] - mean) * inv_std : pf[2]) : 0.f;
-                sm.Aux[3 * TM + s] = role == 0 ? 0.f : pf[3];
-            }
-        } else if (c == 1) {
-            sm.Aux[s] = pf[0];
-        } else if (c == 2) {
-            sm.Aux[(role == 0 ? TM : 3 * TM) + s] = pf[0];     // logp_old | return
-            if (role == 0) sm.Aux[3 * TM + s] = 0.f; else sm.Aux[TM + s] = 0.f;
-        } else {
-            sm.Aux[2 * TM + s] = (role == 0 && hp.normalize_adv) ? (pf[0] - mean) * inv_std : pf[0];
         }
         K7_T(16);
         xbuf ^= 1;
-        if (t + nctas < ntiles) { gather_tile(t + nctas, pf); have_pf = true; } else have_pf = false;
+        request(gi_next, pfx, pfa);                  // tile t + nctas
+        gi_next = index_of(t + 2 * nctas);
+        K7_T(17);
     };
     uint32_t h1pos = 0, h1pos_tile = 0;   // relu: bit k = (H1[16c + k] > 0) of the tile layer1() ran on last / of the tile P7 works on
     auto layer1 = [&]() {   // P1: H1 = act(W1 x + b1) -> TMEM A operand (hi | lo fp16 pairs)
-        float xo[kInMax];
         uint32_t pos = 0;
-#pragma unroll
-        for (int k = 0; k < kInMax; ++k) xo[k] = sm.X[k * TM + s];
         uint32_t hi8[8], lo8[8];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -578,8 +565,9 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         umma::tmem_st_wait();
     };
     if (cta < ntiles) {   // prologue: P0 / P1 of the first tile (the issuer queues its G1)
+        request(index_of(cta), pfx, pfa);
+        gi_next = index_of(cta + nctas);
         publish(cta);
-        worker_sync();
         layer1();
         umma::fence_before_sync();
         ready_arrive(kBarRdyB);
@@ -610,7 +598,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             for (int o = 0; o < kNo; ++o) sm.Zp[(c * kNo + o) * TM + s] = zp[o];
         }
         K7_T(1);
-        worker_sync();
+        group_sync(q);
         K7_T(2);
         // ---- P4+P5: loss (evaluated by all four feature-block threads of a sample: no exchange, no idle warps),
         //            dW3 / db2 partials, dP2 = (W3^T dz) .* act'(H2) -> TMEM A operand (over D1, which this thread
@@ -621,7 +609,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             for (int o = 0; o < kNo; ++o)
                 z[o] = sm.b3[o] + ((sm.Zp[o * TM + s] + sm.Zp[(kNo + o) * TM + s]) + (sm.Zp[(2 * kNo + o) * TM + s] + sm.Zp[(3 * kNo + o) * TM + s]));
             const bool valid = (tile * TM + s) < b.B;
-            LossOut lo_ = sample_loss(actor, role, hp, b.inv_B, z, sm.Aux[s], sm.Aux[TM + s], sm.Aux[2 * TM + s], sm.Aux[3 * TM + s]);
+            LossOut lo_ = sample_loss(actor, role, hp, b.inv_B, z, aux[0], aux[1], aux[2], aux[3]);
             float dz[kNo];
 #pragma unroll
             for (int o = 0; o < kNo; ++o) dz[o] = valid ? lo_.dz[o] : 0.f;
@@ -664,15 +652,20 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         umma::fence_proxy_async();
         umma::fence_before_sync();
         ready_arrive(kBarRdyA);     // this thread's share of the GEMM2 / GEMM3 operands is in place
-        gemm3_pending = true;
-        worker_sync();              // Aux / Zp / X are free for the next tile
+        gemm3_pending = true;       // (Zp is rewritten in P3 of the next tile, behind its wait for GEMM1, i.e. after every thread has passed
+                                    //  this point: no barrier needed here)
         K7_T(6);
         K7_T(7);
         h1pos_tile = h1pos;         // this tile's H1 signs, before layer1() of the next tile replaces them
         if (has_next) {
+            if (gemm4_pending) {   // the previous tile's GEMM4 must have consumed its XT buffer (same parity as the next tile's) and the
+                umma::mbar_wait(&sm.bar4, ph4);   // dP1^T image before either is overwritten
+                ph4 ^= 1u;
+                umma::fence_after_sync();
+                gemm4_pending = false;
+            }
             publish(tile + nctas);
             K7_T(8);
-            worker_sync();
             K7_T(9);
             layer1();
             umma::fence_before_sync();
@@ -714,10 +707,11 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                     }
                 }
             }
-            if (gemm4_pending) {   // the previous tile's GEMM4 must have consumed the dP1^T image before it is overwritten
+            if (gemm4_pending) {   // (last tile: no publish() waited for it)
                 umma::mbar_wait(&sm.bar4, ph4);
                 ph4 ^= 1u;
                 umma::fence_after_sync();
+                gemm4_pending = false;
             }
             if (ord > 0 && ord % kFlushTiles == 0) flush_d4();
             {
