@@ -14,7 +14,9 @@ PKG = os.path.join(ROOT, "reinforcementlearning.jl_b200")
 DBG = os.path.join(PKG, "build", "libb200rl_dbg.so")
 NAMES = ["wait G1 (bar1)", "P3 (D1 -> H2, head partials)", "sync a", "P45 loss + dP2 (compute, tmem_st)", "wait G3 prev (bar3)",
          "P45 image stores (FP, FH)", "sync b", "issue G2", "P0 publish + prefetch", "sync c", "P1 layer 1 + tmem_st", "sync d",
-         "issue G1(next) + G3", "wait G2 (bar2)", "P7 (D2 -> dP1, dW1)", "(tile count)", "  P0a: publish stores (waits for the prefetch)", "  P0b: perm_index", ]
+         "issue G1(next) + G3", "wait G2 (bar2)", "P7 (D2 -> dP1, dW1)", "(tile count)", "  P0a: publish (registers -> XT image; waits for the prefetch)", "  P0b: request next records + index",
+         "issuer: wait RdyA (P45 done everywhere)", "issuer: issue G2", "issuer: wait RdyB (layer 1 done)", "issuer: issue G1(next) + G3",
+         "issuer: wait RdyC (P7 done)", "issuer: issue G4"]
 
 
 def build():
@@ -47,7 +49,7 @@ def run():
     out = (C.c_ulonglong * 24)()
     lib.b200rl_debug_k7_phases.argtypes = [C.c_void_p, C.c_int]
     # all MMAs are issued by the dedicated warp 16 (nn_tc.cu); the watched threads are plain workers: 0 / 224 gather (c < 2), 256 does not (c = 2)
-    watch = [int(a) for a in sys.argv[1:] if a.isdigit()] or [0, 224, 256]
+    watch = [int(a) for a in sys.argv[1:] if a.isdigit()] or [0, 224, 256, 65536]   # tid | cta << 16 (cta 1 = a critic CTA)
     cols = {}
     for w in watch:
         assert lib.b200rl_debug_k7_watch(w) == 0
@@ -59,7 +61,7 @@ def run():
         cols[w] = ([x / tiles for x in v], sum(v[:15]) / tiles, tiles)
     print("cycles per 128-sample tile as seen by thread <tid> of CTA 0 (" + ", ".join(f"{w}: {cols[w][2]} tiles" for w in watch) + ")")
     print(f"  {'phase':48s}" + "".join(f"{'tid ' + str(w):>10s}" for w in watch))
-    for k in list(range(15)) + [16, 17]:
+    for k in list(range(15)) + [16, 17] + list(range(18, 24)):
         print(f"  {NAMES[k]:48s}" + "".join(f"{cols[w][0][k]:10.0f}" for w in watch))
     print(f"  {'sum of the 15 phases':48s}" + "".join(f"{cols[w][1]:10.0f}" for w in watch))
     print("  (P0 row = loads issued after perm_index; P0a / P0b are its first two parts and are not in the sum)")

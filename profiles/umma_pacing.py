@@ -23,8 +23,8 @@ def idesc_f16(M, N):
     return (1 << 4) | ((N >> 3) << 17) | ((M >> 4) << 24)
 
 
-def once(M, N, layout, lbo, sbo, kadv, n, ts=0, alt=0, sleep=0, elect=0):
-    p = np.array([idesc_f16(M, N), layout, lbo, sbo, kadv, n, ts, alt, sleep, elect], np.uint32)
+def once(M, N, layout, lbo, sbo, kadv, n, ts=0, alt=0, sleep=0, elect=0, mn=0):
+    p = np.array([idesc_f16(M, N) | (mn << 15) | (mn << 16), layout, lbo, sbo, kadv, n, ts, alt, sleep, elect], np.uint32)
     out = np.zeros(2, np.float32)
     b._lib.check(lib.b200rl_selftest_pacing(ctx.h, p.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
     return out
@@ -58,3 +58,7 @@ for layout, lbo, sbo, kadv in ((0, 128, 1024, 256), (2, 16, 1024, 32)):
         print(f"  SS layout={LAY[layout]:13s} M=128 N={N:3d} bystanders asleep: issue {r[0]:6.1f}  done {r[1]:6.1f}")
     r = pace(128, 128, layout, lbo, sbo, 0, elect=1)
     print(f"  SS layout={LAY[layout]:13s} M=128 N=128 same operand address every time: issue {r[0]:6.1f}  done {r[1]:6.1f}")
+print("MN-major A and B (GEMM3 / GEMM4 of K7: LBO = 128 between 8-sample k-blocks, SBO = 2048 between 8-feature blocks), elect.sync")
+for N in (16, 64, 144):
+    r = pace(128, N, 0, 128, 2048, 256, elect=1, mn=1)
+    print(f"  SS MN-major M=128 N={N:3d}: issue {r[0]:6.1f}  done {r[1]:6.1f}")

@@ -40,6 +40,7 @@ __device__ __forceinline__ void store_rng32(unsigned long long* rng, int64_t i, 
 }
 
 // mode 0: actor-critic rollout step (CTA role = blockIdx & 1), mode 1: plain forward of `actor` -> head_out
+template <int ACT>
 __global__ void __launch_bounds__(NT, 2)
 forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, int mode, const float* __restrict__ obs,
                   int64_t N, unsigned long long* __restrict__ rng, void* __restrict__ action_out, float* __restrict__ logp_out,
@@ -54,7 +55,7 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, c = warp >> 2;
     const int s = 32 * q + lane;
-    load_net(sm.net, d, params + poff);
+    load_net(sm.net, d, params + poff, (ACT >= 0 ? ACT : d.act) == B200RL_ACT_RELU && ACT >= 0 ? kScale : 1.0f);
     if (warp == 0) umma::tmem_alloc(&sm.tmem, TMEM_COLS);
     if (tid == 32) umma::mbar_init(&sm.bar, 1);
     umma::fence_proxy_async();
@@ -92,7 +93,7 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
             float x[kInMax];
 #pragma unroll
             for (int k = 0; k < kInMax; ++k) x[k] = sm.X[k * TM + s];
-            layer1_to_tmem(sm.net, d.act, x, c, tmem_lane);
+            layer1_to_tmem<ACT>(sm.net, d.act, x, c, tmem_lane);
         }
         umma::fence_before_sync();
         __syncthreads();
@@ -107,7 +108,7 @@ forward_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ param
         umma::fence_after_sync();
         {
             float zp[kOutMax];
-            head_partials(sm.net, d.act, c, tmem_lane, zp);
+            head_partials<ACT>(sm.net, d.act, c, tmem_lane, zp);
 #pragma unroll
             for (int o = 0; o < kOutMax; ++o) sm.Zp[(c * kOutMax + o) * TM + s] = zp[o];
         }
@@ -183,7 +184,7 @@ struct RollArgs {
     uint8_t* terminals;         // (N, T)
 };
 
-template <class Env>
+template <class Env, int ACT>
 __global__ void __launch_bounds__(NT, 2) rollout_tc_kernel(RollArgs g, typename Env::P p, EnvArrays ea) {
     using act_t = typename Env::act_t;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -195,8 +196,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_tc_kernel(RollArgs g, typename 
     const int cta = blockIdx.x, nctas = gridDim.x;
     const int64_t N = g.N;
     const int64_t ntiles = (N + TM - 1) / TM;
-    load_net(sm.net[0], g.actor, g.params);
-    load_net(sm.net[1], g.critic, g.params + g.actor.nparams());
+    load_net(sm.net[0], g.actor, g.params, ACT == B200RL_ACT_RELU ? kScale : 1.0f);
+    load_net(sm.net[1], g.critic, g.params + g.actor.nparams(), ACT == B200RL_ACT_RELU ? kScale : 1.0f);
     if (warp == 0) umma::tmem_alloc(&sm.tmem, TMEM_COLS);
     if (tid == 32) umma::mbar_init(&sm.bar, 1);
     // resident env state
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_tc_kernel(RollArgs g, typename 
             uint32_t a_bits = 0;
             if (!boot) {
                 // ---- actor ---------------------------------------------------------------------------------------
-                layer1_to_tmem(sm.net[0], g.actor.act, x, c, tmem_lane);
+                layer1_to_tmem<ACT>(sm.net[0], g.actor.act, x, c, tmem_lane);
                 umma::fence_before_sync();
                 __syncthreads();
                 if (tid == 0) {   // (elect.sync measured 3 % slower here, profiles/umma_pacing.py notes)
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_tc_kernel(RollArgs g, typename 
                 umma::fence_after_sync();
                 {
                     float zp[kOutMax];
-                    head_partials(sm.net[0], g.actor.act, c, tmem_lane, zp);
+                    head_partials<ACT>(sm.net[0], g.actor.act, c, tmem_lane, zp);
 #pragma unroll
                     for (int o = 0; o < kOutMax; ++o) sm.Zp[0][(c * kOutMax + o) * TM + s] = zp[o];
                 }
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_tc_kernel(RollArgs g, typename 
                 __syncthreads();
             }
             // ---- critic GEMM in flight while the owner threads sample the action and step the env -----------------------
-            layer1_to_tmem(sm.net[1], g.critic.act, x, c, tmem_lane);
+            layer1_to_tmem<ACT>(sm.net[1], g.critic.act, x, c, tmem_lane);
             umma::fence_before_sync();
             __syncthreads();
             if (tid == 0) {   // (elect.sync measured 3 % slower here, profiles/umma_pacing.py notes)
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_tc_kernel(RollArgs g, typename 
             umma::fence_after_sync();
             {
                 float zp[kOutMax];
-                head_partials(sm.net[1], g.critic.act, c, tmem_lane, zp);
+                head_partials<ACT>(sm.net[1], g.critic.act, c, tmem_lane, zp);
                 sm.Zp[1][(c * kOutMax) * TM + s] = zp[0];
             }
             umma::fence_before_sync();
@@ -392,12 +393,16 @@ __global__ void __launch_bounds__(NT, 2) rollout_tc_kernel(RollArgs g, typename 
 template <class Env> int launch_rollout(b200rl_ctx* ctx, const RollArgs& g, const typename Env::P& p, const EnvArrays& ea) {
     const size_t smem = sizeof(SmemRoll<Env>) + 128;
     static unsigned long long attr_devices = 0;   // once per device: the attribute call is not free and may serialise with running kernels
-    if (first_use_on_device(attr_devices, ctx->device))
-        CUDA_TRY(cudaFuncSetAttribute(rollout_tc_kernel<Env>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (first_use_on_device(attr_devices, ctx->device)) {
+        CUDA_TRY(cudaFuncSetAttribute(rollout_tc_kernel<Env, B200RL_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(rollout_tc_kernel<Env, B200RL_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const int64_t ntiles = (g.N + TM - 1) / TM;
     int grid = 2 * ctx->sm_count;
     if ((int64_t)grid > ntiles) grid = (int)ntiles;
-    rollout_tc_kernel<Env><<<grid, NT, smem, ctx->stream>>>(g, p, ea);
+    // the activation is a template parameter (nn_tc_rollout only comes here when both trunks share it)
+    if (g.actor.act == B200RL_ACT_RELU) rollout_tc_kernel<Env, B200RL_ACT_RELU><<<grid, NT, smem, ctx->stream>>>(g, p, ea);
+    else rollout_tc_kernel<Env, B200RL_ACT_TANH><<<grid, NT, smem, ctx->stream>>>(g, p, ea);
     LAUNCH_CHECK(ctx);
     return B200RL_OK;
 }
@@ -411,10 +416,18 @@ int nn_tc_forward(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc
                   float* state_copy) {
     size_t smem = sizeof(SmemFwd) + 128;
     static unsigned long long attr_devices = 0;   // once per device
-    if (first_use_on_device(attr_devices, ctx->device))
-        CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    forward_tc_kernel<<<grid, NT, smem, ctx->stream>>>(actor, critic, params, hp, mode, obs, N, rng, action_out, logp_out, value_out, head_out,
-                                                       state_copy);
+    if (first_use_on_device(attr_devices, ctx->device)) {
+        CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel<B200RL_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel<B200RL_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const bool same = mode != 0 || actor.act == critic.act;   // mode 1 runs `actor` alone
+    if (same && actor.act == B200RL_ACT_RELU)
+        forward_tc_kernel<B200RL_ACT_RELU><<<grid, NT, smem, ctx->stream>>>(actor, critic, params, hp, mode, obs, N, rng, action_out, logp_out, value_out, head_out, state_copy);
+    else if (same && actor.act == B200RL_ACT_TANH)
+        forward_tc_kernel<B200RL_ACT_TANH><<<grid, NT, smem, ctx->stream>>>(actor, critic, params, hp, mode, obs, N, rng, action_out, logp_out, value_out, head_out, state_copy);
+    else
+        forward_tc_kernel<-1><<<grid, NT, smem, ctx->stream>>>(actor, critic, params, hp, mode, obs, N, rng, action_out, logp_out, value_out, head_out, state_copy);
     LAUNCH_CHECK(ctx);
     return B200RL_OK;
 }
@@ -428,6 +441,7 @@ int nn_tc_rollout(b200rl_ctx* ctx, b200rl_env* env, const MlpDesc& actor, const 
     EnvView v;
     TRY(b200rl_env_internal_view(env, &v));
     if (!(nn_tc_supported(actor) && nn_tc_supported(critic)) || critic.nout != 1 || v.dtype != B200RL_F32) return B200RL_ERR_UNSUPPORTED;
+    if (actor.act != critic.act) return B200RL_ERR_UNSUPPORTED;   // the fused kernel is compiled per activation (staged launches handle a mixed pair)
     const int64_t ntiles = (v.N + TM - 1) / TM;
     if (ntiles > (int64_t)kSlots * 2 * ctx->sm_count) return B200RL_ERR_UNSUPPORTED;
     if ((actor.heads2 != 0) != (v.continuous != 0)) return B200RL_ERR_UNSUPPORTED;   // Gaussian head <-> continuous action space

@@ -248,10 +248,13 @@ __device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, c
 
 #ifdef B200RL_K7_TIMING   // debug build only (profiles/k7_phase_timing.py): per-phase cycle sums seen by CTA 0 / one watched thread
 __device__ unsigned long long g_k7_phase[24];
-__device__ int g_k7_watch = 0;   // thread of CTA 0 whose timeline is recorded (0 = GEMM2 issuer, 160 = GEMM1 issuer, 320 = GEMM3 issuer)
-#define K7_T(i) do { if (tid == g_k7_watch && blockIdx.x == 0) { long long now_ = clock64(); g_k7_phase[i] += (unsigned long long)(now_ - tprev_); tprev_ = now_; } } while (0)
+__device__ int g_k7_watch = 0;   // watched worker thread (low 16 bits) of CTA (high bits; even = actor, odd = critic) whose timeline is recorded
+#define K7_T(i) do { if (tid == (g_k7_watch & 0xFFFF) && (int)blockIdx.x == (g_k7_watch >> 16)) { long long now_ = clock64(); g_k7_phase[i] += (unsigned long long)(now_ - tprev_); tprev_ = now_; } } while (0)
+// issuer warp of CTA 0 (lane 0): phases 18..23 = wait RdyA | issue G2 | wait RdyB | issue G1 + G3 | wait RdyC | issue G4
+#define K7_TI(i) do { if (lane == 0 && (int)blockIdx.x == (g_k7_watch >> 16)) { long long now_ = clock64(); g_k7_phase[i] += (unsigned long long)(now_ - tprevi_); tprevi_ = now_; } } while (0)
 #else
 #define K7_T(i) do { } while (0)
+#define K7_TI(i) do { } while (0)
 #endif
 // 16 worker warps + one warpgroup (warps 16..19) whose first warp feeds the tensor core.  Issuing a tcgen05.mma costs its
 // thread ~60 cycles and blocks it once the MMA queue is full (~1.1 k cycles for a 16-instruction GEMM), which used to stall
@@ -340,12 +343,16 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (warp == NT7 / 32) {
             // 3-term product of a TMEM A operand (hi fp16 pairs at a_col, lo at a_col + 32; 8 columns per K = 16 step) with a
-            // [B_hi ; B_lo] weight image: MMA 1 (N = 128): D[0:64) = hi*hi, D[64:128) = hi*lo;  MMA 2 (N = 64): D[0:64) += lo*hi
+            // [B_hi ; B_lo] weight image, all three terms accumulated into the SAME 64 columns: hi*hi, hi*lo, lo*hi (three N = 64
+            // MMAs per K step, ~42 cycles each, instead of one N = 128 + one N = 64: the same pipe time, but the workers read back
+            // 64 accumulator columns instead of 128 and add nothing)
             auto issue_ts3 = [&](uint32_t d_col, uint32_t a_col, uint64_t dB) {
+                const uint64_t dBlo = dB + (uint64_t)((8 * GW_S) >> 4);   // rows 64..127 of the image
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-                    umma::mma_f16_ts(tmem + d_col, tmem + a_col + 8 * k, dB + adv, idesc128, k ? 1u : 0u);
+                    umma::mma_f16_ts(tmem + d_col, tmem + a_col + 8 * k, dB + adv, idesc, k ? 1u : 0u);
+                    umma::mma_f16_ts(tmem + d_col, tmem + a_col + 8 * k, dBlo + adv, idesc, 1u);
                     umma::mma_f16_ts(tmem + d_col, tmem + a_col + 32 + 8 * k, dB + adv, idesc, 1u);
                 }
             };
@@ -380,26 +387,35 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
                 __syncwarp();
             }
             int buf = 0, ord = 0;     // ord = ordinal of the tile within this CTA (the workers count the same way)
+#ifdef B200RL_K7_TIMING
+            long long tprevi_ = clock64();
+#endif
             for (int64_t tile = cta; tile < ntiles; tile += nctas, buf ^= 1, ++ord) {
                 if (ord % kFlushTiles == 0) { d3_acc = 0u; d4_acc = 0u; }   // the workers have flushed D3 / D4 before handing this tile's operands over
                 ready_wait(kBarRdyA);                      // dP2 operand (TMEM) and the dP2^T / H1^T images (smem) of this tile
                 umma::fence_after_sync();
+                K7_TI(18);
                 if (umma::elect_one()) { issue_ts3(COL_D2, COL_R1, dB2f); umma::commit(&sm.bar2); }      // GEMM2: dH1 = dP2 x W2
                 __syncwarp();
+                K7_TI(19);
                 if (tile + nctas < ntiles) {
                     ready_wait(kBarRdyB);                  // H1 operand of the next tile
                     umma::fence_after_sync();
+                    K7_TI(20);
                     if (umma::elect_one()) { issue_ts3(COL_R1, COL_AH, dB1f); umma::commit(&sm.bar1); }  // GEMM1 of the next tile
                     __syncwarp();
                 }
                 if (umma::elect_one()) { issue_g3(); umma::commit(&sm.bar3); }                   // GEMM3 of this tile
                 d3_acc = 1u;
                 __syncwarp();
+                K7_TI(21);
                 ready_wait(kBarRdyC);                      // dP1^T image of this tile (its x^T | 1 operand was written at publish time)
                 umma::fence_after_sync();
+                K7_TI(22);
                 if (umma::elect_one()) { issue_g4(buf); umma::commit(&sm.bar4); }                // GEMM4 of this tile
                 d4_acc = 1u;
                 __syncwarp();
+                K7_TI(23);
             }
         }
     } else {
@@ -450,9 +466,9 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
             a[3] = b.ret[g];
         }
     };
-    float pfx[kInMax], pfa[4];        // records of the NEXT tile (in flight)
-    float aux[4];                     // {action bits, logp_old, (normalised) advantage, return} of the tile whose loss is evaluated next
-    int32_t gi_next;                  // index of this thread's sample two tiles ahead
+    float pfx[kInMax] = {0.f, 0.f, 0.f, 0.f}, pfa[4] = {0.f, 0.f, 0.f, 0.f};   // records of the NEXT tile (in flight)
+    float aux[4] = {0.f, 0.f, 0.f, 0.f};   // {action bits, logp_old, (normalised) advantage, return} of the tile whose loss is evaluated next
+    int32_t gi_next = -1;             // index of this thread's sample two tiles ahead
     bool gemm3_pending = false;
     float* const out = partial + (int64_t)cta * np_total + poff;
     float* const gW1 = out;
@@ -584,13 +600,13 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         K7_T(0);
         float h2[16];
         {
-            float v[16], v2[16];
-            umma::tmem_ld16x2(tmem + lane_base + COL_R1 + 16 * c, tmem + lane_base + COL_R1 + 64 + 16 * c, v, v2);
+            float v[16];
+            umma::tmem_ld16(tmem + lane_base + COL_R1 + 16 * c, v);
             float zp[kNo] = {0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int f = 16 * c + k;
-                h2[k] = act_f(act, fmaf(v[k] + v2[k], inv_s1, sm.b2[f]));   // (hh + lh) + hl, operand scale undone (exact)
+                h2[k] = act_f(act, fmaf(v[k], inv_s1, sm.b2[f]));   // operand scales undone (exact)
                 float2 w = *reinterpret_cast<const float2*>(sm.W3 + f * kNo);
                 zp[0] = fmaf(w.x, h2[k], zp[0]); zp[1] = fmaf(w.y, h2[k], zp[1]);
             }
@@ -681,14 +697,11 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         K7_T(13);
         {
             float v[16];
-            {
-                float v2[16];
-                umma::tmem_ld16x2(tmem + lane_base + COL_D2 + 16 * c, tmem + lane_base + COL_D2 + 64 + 16 * c, v, v2);
+            umma::tmem_ld16(tmem + lane_base + COL_D2 + 16 * c, v);
 #pragma unroll
-                // D2 carries scale_p * kScaleW; the dP1 operand wants scale_p: one exact power-of-two factor (bit-identical to unscaling
-                // to dH1 and rescaling)
-                for (int k = 0; k < 16; ++k) v[k] = (v[k] + v2[k]) * (1.0f / kScaleW);
-            }
+            // D2 carries scale_p * kScaleW; the dP1 operand wants scale_p: one exact power-of-two factor (bit-identical to unscaling
+            // to dH1 and rescaling)
+            for (int k = 0; k < 16; ++k) v[k] *= 1.0f / kScaleW;
             if (relu) {   // act'(H1) = (H1 > 0): the signs layer1() kept in a register
 #pragma unroll
                 for (int k = 0; k < 16; ++k) v[k] = ((h1pos_tile >> k) & 1u) ? v[k] : 0.f;
@@ -725,7 +738,7 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         }
         K7_T(14);
 #ifdef B200RL_K7_TIMING
-        if (tid == g_k7_watch && blockIdx.x == 0) g_k7_phase[15] += 1;
+        if (tid == (g_k7_watch & 0xFFFF) && (int)blockIdx.x == (g_k7_watch >> 16)) g_k7_phase[15] += 1;
 #endif
         umma::fence_proxy_async();
         umma::fence_before_sync();

@@ -60,13 +60,15 @@ __device__ __forceinline__ int64_t head_b(const MlpDesc& d, int o) {
 }
 __device__ __forceinline__ uint32_t wimg_off(int n, int k) { return (uint32_t)((n >> 3) * GW_S + (k >> 3) * G_F + (n & 7) * 16 + (k & 7) * 2); }
 
-__device__ inline void load_net(NetSm& w, const MlpDesc& d, const float* __restrict__ p) {
+// s1: scale folded into W1 / b1 (kScale for relu trunks: relu(S z) = S relu(z) exactly for a power of two S, so layer 1 then
+// produces the scaled H1 operand without a multiply per feature; 1 otherwise)
+__device__ inline void load_net(NetSm& w, const MlpDesc& d, const float* __restrict__ p, float s1) {
     const int tid = threadIdx.x;
     const float* b1 = p + (int64_t)H * d.in;
     const float* W2 = b1 + H;
     const float* b2 = W2 + (int64_t)H * H;
-    for (int k = tid; k < kInMax * H; k += NT) w.W1[k] = (k / H) < d.in ? p[k] : 0.f;
-    for (int k = tid; k < H; k += NT) { w.b1[k] = b1[k]; w.b2[k] = b2[k]; }
+    for (int k = tid; k < kInMax * H; k += NT) w.W1[k] = (k / H) < d.in ? __fmul_rn(p[k], s1) : 0.f;
+    for (int k = tid; k < H; k += NT) { w.b1[k] = __fmul_rn(b1[k], s1); w.b2[k] = b2[k]; }
     for (int k = tid; k < H * kOutMax; k += NT) {
         int j = k / kOutMax, o = k % kOutMax;
         w.W3[k] = o < d.nout ? p[head_w(d, o, j)] : 0.f;
@@ -96,8 +98,11 @@ __device__ __forceinline__ float xo_f32(unsigned long long (&s)[4]) { return (fl
 // layer 1 of this thread's sample: H1[32c .. 32c+32) = act(W1 x + b1) -> TMEM A operand (hi pairs at COL_A, lo pairs at COL_A + 32)
 // (the loops over 16-feature halves here and 8-feature groups in head_partials are deliberately NOT unrolled: tanhf is ~40
 // instructions, and with every instance inlined the rollout kernel was 290 KB of SASS whose dominant stall was instruction fetch)
-__device__ __forceinline__ void layer1_to_tmem(const NetSm& w, int act, const float (&x)[kInMax], int c, uint32_t tmem_lane) {
-#pragma unroll 1
+// ACT: the activation as a compile-time constant (-1: read `act`); relu trunks expect load_net(.., s1 = kScale)
+template <int ACT>
+__device__ __forceinline__ void layer1_to_tmem(const NetSm& w, int act_rt, const float (&x)[kInMax], int c, uint32_t tmem_lane) {
+    const int act = ACT >= 0 ? ACT : act_rt;
+#pragma unroll(ACT == B200RL_ACT_RELU ? 2 : 1)
     for (int half = 0; half < 2; ++half) {
         uint32_t hi8[8], lo8[8];
 #pragma unroll
@@ -110,8 +115,15 @@ __device__ __forceinline__ void layer1_to_tmem(const NetSm& w, int act, const fl
                 float4 ww = *reinterpret_cast<const float4*>(w.W1 + k * H + f0);
                 h[0] = fmaf(ww.x, x[k], h[0]); h[1] = fmaf(ww.y, x[k], h[1]); h[2] = fmaf(ww.z, x[k], h[2]); h[3] = fmaf(ww.w, x[k], h[3]);
             }
-            split2(__fmul_rn(act_f(act, h[0]), kScale), __fmul_rn(act_f(act, h[1]), kScale), hi8[2 * ch], lo8[2 * ch]);
-            split2(__fmul_rn(act_f(act, h[2]), kScale), __fmul_rn(act_f(act, h[3]), kScale), hi8[2 * ch + 1], lo8[2 * ch + 1]);
+            if (ACT == B200RL_ACT_RELU) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = fmaxf(h[e], 0.f);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __fmul_rn(act_f(act, h[e]), kScale);
+            }
+            split2(h[0], h[1], hi8[2 * ch], lo8[2 * ch]);
+            split2(h[2], h[3], hi8[2 * ch + 1], lo8[2 * ch + 1]);
         }
         umma::tmem_st8(tmem_lane + COL_A + 16 * c + 8 * half, hi8);
         umma::tmem_st8(tmem_lane + COL_A + 32 + 16 * c + 8 * half, lo8);
@@ -119,30 +131,35 @@ __device__ __forceinline__ void layer1_to_tmem(const NetSm& w, int act, const fl
     umma::tmem_st_wait();
 }
 
-// one elected thread: D = A x W2^T as the 3-term fp16 split (8 MMAs, K = 16 each)
+// one elected thread: D = A x W2^T as the 3-term fp16 split, all three terms accumulated into the same 64 columns
+// (12 MMAs of N = 64, K = 16 each: hi*hi, hi*lo, lo*hi)
 __device__ __forceinline__ void issue_gemm(uint32_t tmem, const NetSm& w) {
-    const uint32_t idesc64 = umma::make_idesc_f16(128, 64, 0, 0), idesc128 = umma::make_idesc_f16(128, 128, 0, 0);
+    const uint32_t idesc64 = umma::make_idesc_f16(128, 64, 0, 0);
     const uint64_t dB = umma::make_desc(umma::smem_u32(w.B), G_F, GW_S);
+    const uint64_t dBlo = dB + (uint64_t)((8 * GW_S) >> 4);   // rows 64..127 of the image
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint64_t adv = (uint64_t)(k * (2 * G_F / 16));
-        umma::mma_f16_ts(tmem + COL_D, tmem + COL_A + 8 * k, dB + adv, idesc128, k ? 1u : 0u);
+        umma::mma_f16_ts(tmem + COL_D, tmem + COL_A + 8 * k, dB + adv, idesc64, k ? 1u : 0u);
+        umma::mma_f16_ts(tmem + COL_D, tmem + COL_A + 8 * k, dBlo + adv, idesc64, 1u);
         umma::mma_f16_ts(tmem + COL_D, tmem + COL_A + 32 + 8 * k, dB + adv, idesc64, 1u);
     }
 }
 
 // epilogue of this thread's sample: H2[32c .. 32c+32) = act(D + b2), partial head sums over these 32 features
-__device__ __forceinline__ void head_partials(const NetSm& w, int act, int c, uint32_t tmem_lane, float (&zp)[kOutMax]) {
+template <int ACT>
+__device__ __forceinline__ void head_partials(const NetSm& w, int act_rt, int c, uint32_t tmem_lane, float (&zp)[kOutMax]) {
+    const int act = ACT >= 0 ? ACT : act_rt;
 #pragma unroll
     for (int o = 0; o < kOutMax; ++o) zp[o] = 0.f;
-#pragma unroll 1
-    for (int grp = 0; grp < 4; ++grp) {
-        uint32_t v[8], v2[8];
-        umma::tmem_ld8x2(tmem_lane + COL_D + 32 * c + 8 * grp, tmem_lane + COL_D + 64 + 32 * c + 8 * grp, v, v2);
+#pragma unroll(ACT == B200RL_ACT_RELU ? 2 : 1)
+    for (int grp = 0; grp < 2; ++grp) {
+        float v[16];
+        umma::tmem_ld16(tmem_lane + COL_D + 32 * c + 16 * grp, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int f = 32 * c + 8 * grp + k;
-            float h2 = act_f(act, fmaf(__uint_as_float(v[k]) + __uint_as_float(v2[k]), 1.0f / (kScale * kScale), w.b2[f]));   // operand scales undone (exact power of two)
+        for (int k = 0; k < 16; ++k) {
+            const int f = 32 * c + 16 * grp + k;
+            float h2 = act_f(act, fmaf(v[k], 1.0f / (kScale * kScale), w.b2[f]));   // operand scales undone (exact power of two)
             float4 ww = *reinterpret_cast<const float4*>(w.W3 + f * kOutMax);
             zp[0] = fmaf(ww.x, h2, zp[0]); zp[1] = fmaf(ww.y, h2, zp[1]); zp[2] = fmaf(ww.z, h2, zp[2]); zp[3] = fmaf(ww.w, h2, zp[3]);
         }
