@@ -16,7 +16,10 @@ NAMES = ["wait G1 (bar1)", "P3 (D1 -> H2, head partials)", "sync a", "P45 loss +
          "P45 image stores (FP, FH)", "sync b", "issue G2", "P0 publish + prefetch", "sync c", "P1 layer 1 + tmem_st", "sync d",
          "issue G1(next) + G3", "wait G2 (bar2)", "P7 (D2 -> dP1, dW1)", "(tile count)", "  P0a: publish (registers -> XT image; waits for the prefetch)", "  P0b: request next records + index",
          "issuer: wait RdyA (P45 done everywhere)", "issuer: issue G2", "issuer: wait RdyB (layer 1 done)", "issuer: issue G1(next) + G3",
-         "issuer: wait RdyC (P7 done)", "issuer: issue G4"]
+         "issuer: wait RdyC (P7 done)", "issuer: issue G4",
+         "TAIL (cycles per LAUNCH / tiles): drain + head reductions + partial rows", "tail: threadfence + CTA barrier", "tail: grid barrier A (all CTAs' rows written)",
+         "tail: stage partial rows (L2 -> smem)", "tail: column sums + sum of squares", "tail: grid barrier B", "tail: fetch 148 sums, norm, clip scale",
+         "tail: Adam + done counter"]
 
 
 def build():
@@ -46,7 +49,7 @@ def run():
     net = b.Network(ctx, 4, 64, 2, b.sharding.glorot_actor_critic(123, 4, 64, 2))
     agent = b.OnPolicyAgent(ctx, net, env, b.onpolicy_config(update_freq=32), b.sharding.splitmix_states(2, 0, n))
     b.run(agent, env, b.StopAfterNSteps(64), b.DeviceEpisodeStats())     # two full PPO iterations (warm-up)
-    out = (C.c_ulonglong * 24)()
+    out = (C.c_ulonglong * 40)()
     lib.b200rl_debug_k7_phases.argtypes = [C.c_void_p, C.c_int]
     # all MMAs are issued by the dedicated warp 16 (nn_tc.cu); the watched threads are plain workers: 0 / 224 gather (c < 2), 256 does not (c = 2)
     watch = [int(a) for a in sys.argv[1:] if a.isdigit()] or [0, 224, 256, 65536]   # tid | cta << 16 (cta 1 = a critic CTA)
@@ -61,7 +64,7 @@ def run():
         cols[w] = ([x / tiles for x in v], sum(v[:15]) / tiles, tiles)
     print("cycles per 128-sample tile as seen by thread <tid> of CTA 0 (" + ", ".join(f"{w}: {cols[w][2]} tiles" for w in watch) + ")")
     print(f"  {'phase':48s}" + "".join(f"{'tid ' + str(w):>10s}" for w in watch))
-    for k in list(range(15)) + [16, 17] + list(range(18, 24)):
+    for k in list(range(15)) + [16, 17] + list(range(18, 32)):
         print(f"  {NAMES[k]:48s}" + "".join(f"{cols[w][0][k]:10.0f}" for w in watch))
     print(f"  {'sum of the 15 phases':48s}" + "".join(f"{cols[w][1]:10.0f}" for w in watch))
     print("  (P0 row = loads issued after perm_index; P0a / P0b are its first two parts and are not in the sum)")

@@ -165,8 +165,8 @@ int b200rl_net_create(b200rl_ctx* ctx, const b200rl_net_desc* d, const float* pa
     NET_TRY(cudaMalloc(&n->partial, (size_t)n->n_partials * bytes));
     NET_TRY(cudaMalloc(&n->loss_partial, (size_t)n_loss_rows * 4 * sizeof(float)));
     NET_TRY(cudaMalloc(&n->loss4, 4 * sizeof(float))); NET_TRY(cudaMalloc(&n->gnorm, sizeof(float)));
-    NET_TRY(cudaMalloc(&n->cta_sumsq, 256 * sizeof(double))); NET_TRY(cudaMalloc(&n->counter2, 2 * sizeof(unsigned int)));
-    NET_TRY(cudaMemsetAsync(n->counter2, 0, 2 * sizeof(unsigned int), ctx->stream));
+    NET_TRY(cudaMalloc(&n->cta_sumsq, 256 * sizeof(double))); NET_TRY(cudaMalloc(&n->counter2, 4 * sizeof(unsigned int)));
+    NET_TRY(cudaMemsetAsync(n->counter2, 0, 4 * sizeof(unsigned int), ctx->stream));
     NET_TRY(cudaMemcpyAsync(n->params, params_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (n->kind == 2) NET_TRY(cudaMemcpyAsync(n->target, params_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     NET_TRY(cudaMemsetAsync(n->grad, 0, bytes, ctx->stream)); NET_TRY(cudaMemsetAsync(n->m, 0, bytes, ctx->stream));
@@ -619,11 +619,21 @@ int b200rl_onpolicy_update(b200rl_onpolicy* a, const int32_t* perm_host, float* 
                       perm_host ? a->perm_dev + (size_t)e * NT_ + (size_t)mb * B : nullptr,
                       (uint32_t)NT_, (uint32_t)e * 7919u + 12345u, (uint32_t)(mb * B), a->upd_dev, a->rec, B,
                       1.0f / ((float)B * (float)world), a->norm2};
-            int ctas = nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
-            if (ctas < 0) return ctas;
-            TRY(phase(2 + 2 * row));
             float* stats_row = a->stats_dev + (size_t)row * 8;
             unsigned int* tick = row == a->stats_rows - 1 ? a->upd_dev : nullptr;   // the last optimiser step closes the update
+            // one launch: loss + backward + [peer exchange] + clip + Adam (tensor-core path)
+            int ctas = nn_ac_loss_grad_step(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial, n->grad, n->m, n->v, n->beta_t,
+                                            n->loss4, c.max_grad_norm, c.lr, c.beta1, c.beta2, c.eps, n->gnorm, n->cta_sumsq, n->counter2, stats_row, tick);
+            if (ctas > 0) {
+                TRY(phase(2 + 2 * row));
+                TRY(phase(3 + 2 * row));
+                n->n_updates += 1;
+                continue;
+            }
+            if (ctas != B200RL_ERR_UNSUPPORTED) return ctas;
+            ctas = nn_ac_loss_grad(ctx, n->actor, n->critic, n->params, hp, b, n->partial, n->loss_partial);
+            if (ctas < 0) return ctas;
+            TRY(phase(2 + 2 * row));
             P2PTable peers;
             if (world > 1 && !b200rl_comm_p2p_table(ctx, &peers)) {   // no peer exchange attached: reduce -> NCCL all-reduce -> clip + Adam
                 TRY(nn_reduce_partials(ctx, n->partial, ctas, n->np, n->grad, n->loss_partial, 2 * ctas, n->loss4));
@@ -828,7 +838,7 @@ int b200rl_onpolicy_time_kernel(b200rl_onpolicy* a, int which, int reps, float* 
     int64_t N = a->N, T = a->T, NT_ = N * T, B = NT_ / c.n_microbatches;
     AcHyper hp{c.clip_range, c.w_actor, c.w_critic, c.w_entropy, c.min_sigma, c.max_sigma, c.normalize_advantage, c.algo};
     const float* obs = (const float*)env_field(a->env, B200RL_FIELD_OBS);
-    int ctas = (nn_tc_enabled() && nn_tc_bwd_supported(n->actor, n->critic)) ? ctx->sm_count / 2 : nn_grid_ctas(ctx, n->actor.H);
+    int ctas = (nn_tc_enabled() && nn_tc_bwd_supported(n->actor, n->critic)) ? nn_tc_partial_rows(2 * (ctx->sm_count / 2), n->actor, hp) : nn_grid_ctas(ctx, n->actor.H);
     void* rng_copy = nullptr;
     if (which == 1) {
         TRY(ctx_scratch(ctx, (size_t)N * 32 + (size_t)N * 12 + 256, &rng_copy));

@@ -204,15 +204,23 @@ int b200rl_comm_p2p_attach(b200rl_ctx* ctx, void* const* regions) {
     REQUIRE(c->nranks <= kP2PMaxRanks, B200RL_ERR_UNSUPPORTED, "peer exchange supports up to 8 ranks (one NVSwitch node)");
     P2PTable t = {};
     t.nranks = c->nranks; t.rank = c->rank;
+    t.exclusive = 1;
     for (int r = 0; r < c->nranks; ++r) {
         t.base[r] = r == c->rank ? c->region : (unsigned char*)regions[r];
         REQUIRE(t.base[r], B200RL_ERR_INVALID, "null peer region");
         if (r != c->rank) {   // same-process peers on another device: enable direct access (IPC mappings already are)
             cudaPointerAttributes at;
-            if (cudaPointerGetAttributes(&at, t.base[r]) == cudaSuccess && at.device != ctx->device) {
-                cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); }
-                else cudaGetLastError();
+            if (cudaPointerGetAttributes(&at, t.base[r]) == cudaSuccess) {
+                if (at.device != ctx->device) {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); }
+                    else cudaGetLastError();
+                } else {
+                    t.exclusive = 0;   // a peer rank drives this very device
+                }
+            } else {
+                cudaGetLastError();
+                t.exclusive = 0;
             }
         }
     }

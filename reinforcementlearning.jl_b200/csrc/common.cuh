@@ -95,8 +95,12 @@ constexpr size_t kP2PRegionBytes = kP2POffY + 2 * (size_t)kP2PMaxRanks * kP2PYCa
 struct P2PTable {   // nranks == 0: not attached
     int nranks, rank;
     unsigned char* base[kP2PMaxRanks];
+    int exclusive;      // 1: every peer region lives on another device than ours (one rank per GPU).  Only then may a kernel that
+                        // occupies the whole device wait for a peer inside itself (the fused K7 + optimiser step): two ranks
+                        // sharing one device would deadlock, each waiting for packets of a kernel that cannot be scheduled.
 };
 bool b200rl_comm_p2p_table(b200rl_ctx* ctx, P2PTable* out);   // false when no peer exchange is attached
+int b200rl_comm_world(b200rl_ctx* ctx);                        // ranks of the communicator (1 without one)
 // device-resident sequence numbers of the peer exchanges {gradient exchange, small all-reduce}: every exchange kernel reads
 // its counter, uses value + 1 and stores it back when it is done — no host-side state, so a captured CUDA graph can be replayed
 unsigned int* b200rl_comm_p2p_seq_dev(b200rl_ctx* ctx);

@@ -781,18 +781,28 @@ __global__ void __launch_bounds__(256) reduce_clip_adam_kernel(const float* __re
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += red[w];
-        cta_sumsq[blockIdx.x] = t;
-        __threadfence();
-        atomicAdd(counter, 1u);
-        unsigned int spins = 0;
-        while (*reinterpret_cast<volatile unsigned int*>(counter) < target)
-            if (++spins > (1u << 26)) __trap();
-        __threadfence();
+    if (threadIdx.x < 32) {   // warp 0: lane 0 publishes and waits at the grid barrier, then all lanes fetch the per-CTA sums in parallel
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += red[w];
+            cta_sumsq[blockIdx.x] = t;
+            __threadfence();
+            atomicAdd(counter, 1u);
+            unsigned int spins = 0;
+            while (*reinterpret_cast<volatile unsigned int*>(counter) < target)
+                if (++spins > (1u << 26)) __trap();
+            __threadfence();
+        }
+        __syncwarp();
+        // (one dependent L2 read per CTA was ~5 us of this ~14 us kernel; the loads now go out together, the adds keep the CTA order)
         double tot = 0.0;
-        for (unsigned int c = 0; c < gridDim.x; ++c) tot += *reinterpret_cast<volatile double*>(cta_sumsq + c);
+        for (unsigned int c0 = 0; c0 < gridDim.x; c0 += 32) {
+            const unsigned int c = c0 + threadIdx.x;
+            const double mine = c < gridDim.x ? *reinterpret_cast<volatile double*>(cta_sumsq + c) : 0.0;
+            const unsigned int n = min(32u, gridDim.x - c0);
+            for (unsigned int l = 0; l < n; ++l) tot += __shfl_sync(0xffffffffu, mine, l);
+        }
+    if (threadIdx.x == 0) {
         float gn = (float)sqrt(tot);
         float sc = 1.0f;
         if (max_norm > 0.f && max_norm <= gn) sc = max_norm / fmaxf(max_norm, gn);
@@ -801,6 +811,7 @@ __global__ void __launch_bounds__(256) reduce_clip_adam_kernel(const float* __re
             if (gnorm_out) *gnorm_out = gn;
             if (stats_row) stats_row[4] = gn;
         }
+    }
     }
     __syncthreads();
     const float bt1 = beta_t[0], bt2 = beta_t[1];
@@ -1090,14 +1101,40 @@ int nn_ac_loss_grad(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& critic
     int64_t np = actor.nparams() + critic.nparams();
     int st;
     if (nn_tc_enabled() && nn_tc_bwd_supported(actor, critic)) {
-        ctas = ctx->sm_count / 2;  // one 512-thread CTA per SM, roles alternate
-        st = nn_tc_ac_loss_grad(ctx, 2 * ctas, actor, critic, params, hp, b, partial, loss_partial, np);
+        const int grid = 2 * (ctx->sm_count / 2);   // one 512-thread CTA per SM, split between the roles (nn_tc_actor_ctas)
+        ctas = nn_tc_partial_rows(grid, actor, hp);
+        st = nn_tc_ac_loss_grad(ctx, grid, actor, critic, params, hp, b, partial, loss_partial, np, nullptr);
     } else if (actor.H == 64) {
         st = launch_ac<64>(ctx, 2 * ctas, actor, critic, params, hp, b, partial, loss_partial, np);
     } else {
         st = launch_ac<128>(ctx, 2 * ctas, actor, critic, params, hp, b, partial, loss_partial, np);
     }
     return st != B200RL_OK ? st : ctas;  // number of gradient partials written (loss rows = 2x)
+}
+
+// K7 + optimiser step in ONE launch (tensor-core path only; B200RL_FUSED_STEP=0 disables it).  A sharded run takes it only when
+// every rank owns its device (P2PTable::exclusive): the launch occupies all SMs and waits for the peers' packets inside itself.
+int nn_ac_loss_grad_step(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& critic, float* params, const AcHyper& hp, const AcBatch& b,
+                         float* partial, float* loss_partial, float* grad, float* m, float* v, float* beta_t, float* loss_out4,
+                         float max_grad_norm, float lr, float b1, float b2, float eps, float* gnorm_out, double* cta_sumsq,
+                         unsigned int* counter4, float* stats_row, unsigned int* tick) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("B200RL_FUSED_STEP"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    if (!enabled || !nn_tc_enabled() || !nn_tc_bwd_supported(actor, critic) || actor.H != critic.H || actor.in != critic.in) return B200RL_ERR_UNSUPPORTED;
+    if (check_desc(actor) != B200RL_OK || check_desc(critic) != B200RL_OK) return B200RL_ERR_UNSUPPORTED;
+    const int ctas = ctx->sm_count / 2;
+    const int64_t np = actor.nparams() + critic.nparams();
+    if ((np + 2 * ctas - 1) / (2 * ctas) > 512) return B200RL_ERR_UNSUPPORTED;
+    AcStep st = {};
+    st.params = params; st.grad = grad; st.m = m; st.v = v; st.beta_t = beta_t; st.loss_out4 = loss_out4; st.stats_row = stats_row;
+    st.gnorm_out = gnorm_out; st.cta_sumsq = cta_sumsq; st.counter = counter4; st.tick = tick; st.seq_ptr = nullptr;
+    st.max_norm = max_grad_norm; st.lr = lr; st.b1 = b1; st.b2 = b2; st.eps = eps;
+    if (b200rl_comm_world(ctx) > 1) {   // sharded run: needs the attached peer exchange and one rank per device
+        if (!b200rl_comm_p2p_table(ctx, &st.tab) || !st.tab.exclusive || (size_t)np + 4 > kP2PXCap) return B200RL_ERR_UNSUPPORTED;
+        st.seq_ptr = b200rl_comm_p2p_seq_dev(ctx);
+    }
+    int rc = nn_tc_ac_loss_grad(ctx, 2 * ctas, actor, critic, params, hp, b, partial, loss_partial, np, &st);
+    return rc != B200RL_OK ? rc : nn_tc_partial_rows(2 * ctas, actor, hp);
 }
 
 int nn_reduce_partials(b200rl_ctx* ctx, const float* partial, int n_partials, int64_t np, float* grad, const float* loss_partial,

@@ -41,6 +41,27 @@ struct AcBatch {
     const float* norm2;         // device {mean, inv_std} for advantage normalisation
 };
 
+// Optimiser step fused into the tail of the tensor-core K7 (nn_ac_loss_grad_step): reduce the per-CTA partials -> [NVLink peer
+// exchange] -> global norm -> clip_by_global_norm! -> Adam, behind two grid barriers inside the SAME launch (the 148 persistent
+// CTAs are co-resident), instead of a second kernel (~14-20 us of launch, L2 round trips and barrier per optimiser step).
+struct AcStep {
+    float* params; float* grad; float* m; float* v; float* beta_t;
+    float* loss_out4; float* stats_row; float* gnorm_out;     // each may be null
+    double* cta_sumsq;            // >= 148 doubles
+    unsigned int* counter;        // 4 zero-initialised uints (self-resetting grid barriers)
+    unsigned int* tick;           // may be null: device update counter incremented once by the launch
+    unsigned int* seq_ptr;        // gradient-exchange sequence number (sharded run)
+    float max_norm, lr, b1, b2, eps;
+    P2PTable tab;                 // nranks <= 1: single GPU
+};
+// K7 + optimiser step in one launch.  Returns the number of gradient partials (> 0) like nn_ac_loss_grad, or
+// B200RL_ERR_UNSUPPORTED *without side effects* when the configuration is outside the fused path (the caller then runs
+// nn_ac_loss_grad + nn_reduce_clip_adam).
+int nn_ac_loss_grad_step(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& critic, float* params, const AcHyper& hp, const AcBatch& b,
+                         float* partial, float* loss_partial, float* grad, float* m, float* v, float* beta_t, float* loss_out4,
+                         float max_grad_norm, float lr, float b1, float b2, float eps, float* gnorm_out, double* cta_sumsq,
+                         unsigned int* counter4, float* stats_row, unsigned int* tick);
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t ac_perm_key(const AcBatch& b) { return b.perm_key + (b.perm_epoch ? *b.perm_epoch * 1000003u : 0u); }
 #endif
@@ -89,5 +110,6 @@ int nn_tc_rollout(b200rl_ctx* ctx, b200rl_env* env, const MlpDesc& actor, const 
                   unsigned long long* policy_rng, int t0, int nsteps, int T, int final_bootstrap, float* states, void* actions, float* logp,
                   float* values, float* rewards, uint8_t* terminals);
 bool nn_tc_bwd_supported(const MlpDesc& actor, const MlpDesc& critic);
+int nn_tc_partial_rows(int grid, const MlpDesc& actor, const AcHyper& hp);   // gradient-partial rows the tensor-core K7 writes with `grid` CTAs
 int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
-                       const AcBatch& b, float* partial, float* loss_partial, int64_t np);
+                       const AcBatch& b, float* partial, float* loss_partial, int64_t np, const AcStep* step /* null: loss + backward only */);

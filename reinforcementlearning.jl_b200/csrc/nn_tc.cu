@@ -100,6 +100,8 @@ struct SmemBwd {
     float b3[kNo];
     float Zp[4 * kNo * TM];                // head partials [c][o][s]
     float Red[32];
+    double RedD[16];
+    float step_scale;
     alignas(8) uint64_t bar1;
     alignas(8) uint64_t bar2;
     alignas(8) uint64_t bar3;
@@ -247,7 +249,7 @@ __device__ __forceinline__ LossOut sample_loss(const MlpDesc& actor, int role, c
 }
 
 #ifdef B200RL_K7_TIMING   // debug build only (profiles/k7_phase_timing.py): per-phase cycle sums seen by CTA 0 / one watched thread
-__device__ unsigned long long g_k7_phase[24];
+__device__ unsigned long long g_k7_phase[40];
 __device__ int g_k7_watch = 0;   // watched worker thread (low 16 bits) of CTA (high bits; even = actor, odd = critic) whose timeline is recorded
 #define K7_T(i) do { if (tid == (g_k7_watch & 0xFFFF) && (int)blockIdx.x == (g_k7_watch >> 16)) { long long now_ = clock64(); g_k7_phase[i] += (unsigned long long)(now_ - tprev_); tprev_ = now_; } } while (0)
 // issuer warp of CTA 0 (lane 0): phases 18..23 = wait RdyA | issue G2 | wait RdyB | issue G1 + G3 | wait RdyC | issue G4
@@ -274,11 +276,19 @@ constexpr int kBarRdyA = 2, kBarRdyB = 3, kBarRdyC = 4;   // named barriers: wor
 template <int ACT>
 __global__ void __launch_bounds__(NT7_ALL, 1)
 ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, AcBatch b, float* __restrict__ partial,
-                       float* __restrict__ loss_partial, int64_t np_total, float scale_base /* power of two ~ 1 / inv_B */) {
+                       float* __restrict__ loss_partial, int64_t np_total, float scale_base /* power of two ~ 1 / inv_B */,
+                       AcStep st /* st.params != null: the optimiser step runs in the tail of this launch */,
+                       int n_actor /* CTAs [0, n_actor) work on the actor, the rest on the critic */) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SmemBwd& sm = *reinterpret_cast<SmemBwd*>(smem_raw);
-    const int role = blockIdx.x & 1;
-    const int cta = blockIdx.x >> 1, nctas = gridDim.x >> 1;
+    // The actor's loss (softmax / Gaussian log-density, entropy, PPO ratio) makes its tiles ~4 % longer than the critic's, so the CTAs
+    // are split unevenly (76 : 72 of 148 for the categorical PPO loss) and both roles finish together.  Gradient partials: row
+    // `cta` holds the actor half written by actor CTA `cta` and the critic half written by critic CTA `cta`; the role with more
+    // CTAs zero-fills the other half of its surplus rows.
+    const int role = (int)blockIdx.x < n_actor ? 0 : 1;
+    const int cta = role ? (int)blockIdx.x - n_actor : (int)blockIdx.x;
+    const int nctas = role ? (int)gridDim.x - n_actor : n_actor;
+    const int nrows = max(n_actor, (int)gridDim.x - n_actor);
     // Scale of the dP2 / dP1 operands (a power of two): dz / inv_B is O(ratio * A_hat) <= ~10 for the actor and 2 w_critic (R - V) for
     // the critic (as large as the returns).  x 64 / x 4 keeps the lo parts of typical entries in fp16's normal range and leaves
     // room up to |dz| / inv_B ~ 1e3 (actor) / 1.6e4 (critic) before a hi part would overflow fp16 (-> inf -> NaN loss: loud, not silent).
@@ -758,6 +768,11 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         gb1[tid] = sm.AccD4[tid * 9 + 4] * inv_sp;
         for (int i = 0; i < d.in; ++i) gW1[tid + H * i] = sm.AccD4[tid * 9 + i] * inv_s4;
     }
+    if (cta >= (int)gridDim.x - nctas) {   // surplus row: the other role has no CTA `cta`, its half of the row is zero
+        const int64_t ooff = role ? 0 : actor.nparams(), on = role ? actor.nparams() : critic.nparams();
+        float* orow = partial + (int64_t)cta * np_total + ooff;
+        for (int64_t kk = tid; kk < on; kk += NT7) orow[kk] = 0.f;
+    }
     float* red = reinterpret_cast<float*>(sm.FP_full);   // images + weight images: contiguous, all MMAs are done
     static_assert(offsetof(SmemBwd, XT) - offsetof(SmemBwd, FP_full) >= (2 * TM * 65 + 2 * 8 * 64) * 4, "drain scratch");
     // per-sample-slot partials of dW3[0], dW3[1] -> two [128 slots][64] matrices in shared memory -> column sums in
@@ -793,10 +808,11 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
     }
     if (c == 0) { red[s] = gb3a0; red[TM + s] = gb3a1; }
     worker_sync();
-    if (tid < d.nout) {
-        float a = 0.f;
-        for (int ss = 0; ss < TM; ++ss) a += red[tid * TM + ss];
-        out[head_b(d, tid)] = a;
+    if (warp < d.nout) {   // one warp per head output: 4 slots per lane in order, then a fixed butterfly (a 128-step dependent chain on one thread was ~2 us)
+        float a = (red[warp * TM + lane] + red[warp * TM + 32 + lane]) + (red[warp * TM + 64 + lane] + red[warp * TM + 96 + lane]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) out[head_b(d, warp)] = a;
     }
     // loss sums (worker-only block reduction)
     float t0 = l0, t1 = l1;
@@ -811,6 +827,159 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
         float* lp = loss_partial + (int64_t)blockIdx.x * 4;
         lp[0] = role ? 0.f : a0; lp[1] = role ? 0.f : a1; lp[2] = role ? a0 : 0.f; lp[3] = 0.f;
     }
+    // ---- fused optimiser step (K8 inside K7's tail): same arithmetic and summation orders as reduce_clip_adam_kernel ----------
+    if (st.params) {
+        const unsigned int G = gridDim.x;
+        K7_T(24);                                // (everything since the last tile: drain, head-gradient reductions, partial rows)
+        worker_sync();                           // every worker's partial / loss rows are written (CTA scope) ...
+        K7_T(25);
+        if (tid == 0) {                          // grid barrier A: every CTA's rows are written
+            __threadfence();                     // ... and ordered before the arrival device-wide (fence cumulativity, as in cooperative groups)
+            atomicAdd(st.counter, 1u);
+            unsigned int spins = 0;
+            while (*reinterpret_cast<volatile unsigned int*>(st.counter) < G)
+                if (++spins > (1u << 26)) __trap();
+            __threadfence();
+        }
+        worker_sync();
+        K7_T(26);
+        const int per = (int)((np_total + G - 1) / G);           // parameters per CTA (<= 512: checked by the launcher)
+        const int64_t k = (int64_t)blockIdx.x * per + tid;
+        const bool mine = tid < per && k < np_total;
+        const unsigned int seq = st.tab.nranks > 1 ? *st.seq_ptr + 1u : 0u;
+        // The CTA's slice of every partial row is staged through shared memory by ALL worker threads (every L2 read in flight at
+        // once: one round trip instead of one per 16 rows), then one thread per parameter adds its column in CTA order.
+        float* stage = reinterpret_cast<float*>(sm.FP_full);            // images are dead: all MMAs have completed
+        const int nstage = per * nrows;                                  // <= 64 * 76 floats with the BASELINE network
+        const int64_t k0 = (int64_t)blockIdx.x * per;
+        {   // (fixed trip count, loads first: a rolled loop would wait for each L2 round trip before issuing the next)
+            constexpr int kMaxStage = 10;                                // 10 * 512 >= 64 * 74 (checked by the launcher)
+            float t[kMaxStage];
+#pragma unroll
+            for (int j = 0; j < kMaxStage; ++j) {
+                const int e = tid + j * NT7;
+                const int row = e / per, col = e - row * per;
+                t[j] = (e < nstage && k0 + col < np_total) ? __ldcg(partial + (int64_t)row * np_total + k0 + col) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < kMaxStage; ++j) {
+                const int e = tid + j * NT7;
+                if (e < nstage) stage[e] = t[j];
+            }
+        }
+        float* lstage = stage + nstage;
+        if (blockIdx.x == 0) {
+            float t[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) t[j] = tid + j * NT7 < 4 * (int)G ? __ldcg(loss_partial + tid + j * NT7) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) if (tid + j * NT7 < 4 * (int)G) lstage[tid + j * NT7] = t[j];
+        }
+        // Adam operands of this thread's parameter: requested now, consumed behind grid barrier B
+        float m_k = 0.f, v_k = 0.f, p_k = 0.f;
+        if (mine) { m_k = st.m[k]; v_k = st.v[k]; p_k = st.params[k]; }
+        worker_sync();
+        K7_T(27);
+        float gk = 0.f;
+        if (mine) {   // rows in CTA order; 8 shared-memory reads in flight
+            for (int c0 = 0; c0 < nrows; c0 += 8) {
+                float t[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = c0 + j < nrows ? stage[(c0 + j) * per + tid] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (c0 + j < nrows) gk += t[j];
+            }
+        }
+        float lsum = 0.f;
+        const bool loss_thread = blockIdx.x == 0 && tid < 4;
+        if (loss_thread) {
+            for (unsigned int c0 = 0; c0 < G; c0 += 8) {
+                float t[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = c0 + j < G ? lstage[(c0 + j) * 4 + tid] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (c0 + j < G) lsum += t[j];
+            }
+        }
+        if (st.tab.nranks > 1) {   // push the local sums into every peer's inbox, collect the peers' from the own inbox, sum in rank order
+            const unsigned slot = seq & 1u;
+            if (mine) p2p_push(st.tab, 0, slot, (size_t)k, __float_as_uint(gk), seq);
+            if (loss_thread) p2p_push(st.tab, 0, slot, (size_t)np_total + tid, __float_as_uint(lsum), seq);
+            float acc = 0.f, lacc = 0.f;
+            for (int r = 0; r < st.tab.nranks; ++r) {
+                if (mine) acc += r == st.tab.rank ? gk : __uint_as_float(p2p_recv(st.tab, 0, slot, r, (size_t)k, seq));
+                if (loss_thread) lacc += r == st.tab.rank ? lsum : __uint_as_float(p2p_recv(st.tab, 0, slot, r, (size_t)np_total + tid, seq));
+            }
+            gk = acc; lsum = lacc;
+        }
+        if (loss_thread) {
+            if (st.loss_out4) st.loss_out4[tid] = lsum;
+            if (st.stats_row) st.stats_row[tid] = lsum;
+        }
+        double sq = (double)gk * (double)gk;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) sm.RedD[warp] = sq;
+        worker_sync();
+        K7_T(28);
+        if (warp == 0) {
+            if (lane == 0) {                     // grid barrier B: every CTA's sum of squares is published
+                double t = 0.0;
+                for (int w = 0; w < NT7 / 32; ++w) t += sm.RedD[w];
+                st.cta_sumsq[blockIdx.x] = t;
+                __threadfence();
+                atomicAdd(st.counter + 1, 1u);
+                unsigned int spins = 0;
+                while (*reinterpret_cast<volatile unsigned int*>(st.counter + 1) < G)
+                    if (++spins > (1u << 26)) __trap();
+                __threadfence();
+            }
+            __syncwarp();
+            K7_T(29);
+            // every lane fetches its share of the per-CTA sums (all reads in flight), adds them in CTA order, then a fixed
+            // butterfly over the lanes: deterministic, and every CTA computes the identical total
+            double part[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[j] = (unsigned)(lane + 32 * j) < G ? __ldcg(st.cta_sumsq + lane + 32 * j) : 0.0;
+            double tot = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tot += part[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            if (lane == 0) {
+                const float gn = (float)sqrt(tot);
+                float sc = 1.0f;
+                if (st.max_norm > 0.f && st.max_norm <= gn) sc = st.max_norm / fmaxf(st.max_norm, gn);
+                sm.step_scale = sc;
+                if (blockIdx.x == 0) {
+                    if (st.gnorm_out) *st.gnorm_out = gn;
+                    if (st.stats_row) st.stats_row[4] = gn;
+                }
+            }
+        }
+        worker_sync();
+        K7_T(30);
+        const float bt1 = st.beta_t[0], bt2 = st.beta_t[1];
+        if (mine) {
+            gk *= sm.step_scale;
+            st.grad[k] = gk;
+            const float mk = st.b1 * m_k + (1.0f - st.b1) * gk;
+            const float vk = st.b2 * v_k + (1.0f - st.b2) * (gk * gk);
+            st.m[k] = mk; st.v[k] = vk;
+            st.params[k] = p_k - mk / (1.0f - bt1) / (sqrtf(vk / (1.0f - bt2)) + st.eps) * st.lr;
+        }
+        worker_sync();
+        if (tid == 0) {                          // the last CTA through advances beta^t and re-arms the counters (every thread of
+                                                 // every CTA has read beta^t / the sequence number before its CTA arrives here)
+            if (atomicAdd(st.counter + 2, 1u) + 1u == G) {
+                st.beta_t[0] = bt1 * st.b1; st.beta_t[1] = bt2 * st.b2;
+                st.counter[0] = 0u; st.counter[1] = 0u; st.counter[2] = 0u;
+                if (st.tab.nranks > 1) *st.seq_ptr = seq;
+                if (st.tick) *st.tick += 1u;
+            }
+        }
+        K7_T(31);
+    }
     }  // worker warps
     umma::fence_before_sync();
     __syncthreads();
@@ -819,11 +988,37 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
 
 }  // namespace
 
+// CTAs given to the actor out of `grid` (the rest work on the critic): the measured per-tile cost ratio actor : critic (profiles/
+// k7_phase_timing.py) is ~1.04 for the categorical PPO / A2C loss; B200RL_K7_ACTOR_CTAS overrides it for tuning runs.
+int nn_tc_actor_ctas(int grid, const MlpDesc& actor, const AcHyper& hp) {
+    static int forced = -2;
+    if (forced == -2) { const char* e = getenv("B200RL_K7_ACTOR_CTAS"); forced = e ? atoi(e) : -1; }
+    if (forced > 0 && forced < grid) return forced;
+    (void)hp;
+    const int share = actor.heads2 ? 82 : 77;   // of 148 (B200 sweeps: profiles/na_sweep.sh)
+    int n = (grid * share + 74) / 148;
+    if (n < 1) n = 1;
+    if (n > grid - 1) n = grid - 1;
+    return n;
+}
+int nn_tc_partial_rows(int grid, const MlpDesc& actor, const AcHyper& hp) {
+    const int na = nn_tc_actor_ctas(grid, actor, hp);
+    return na > grid - na ? na : grid - na;
+}
 bool nn_tc_bwd_supported(const MlpDesc& actor, const MlpDesc& critic) {
     return actor.H == 64 && critic.H == 64 && actor.in <= kInMax && actor.nout <= 2 && critic.nout == 1;
 }
 int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
-                       const AcBatch& b, float* partial, float* loss_partial, int64_t np) {
+                       const AcBatch& b, float* partial, float* loss_partial, int64_t np, const AcStep* step) {
+    AcStep st = {};
+    const int n_actor = nn_tc_actor_ctas(grid, actor, hp);
+    if (step) {
+        st = *step;
+        const int64_t per = (np + grid - 1) / grid;
+        const int rows = n_actor > grid - n_actor ? n_actor : grid - n_actor;
+        REQUIRE(st.params == params && per <= NT7 && grid <= ctx->sm_count && per * rows <= 10 * NT7 && 4 * grid <= 2 * NT7 && grid <= 256, B200RL_ERR_UNSUPPORTED,
+                "fused optimiser step: bad configuration");
+    }
     size_t smem = sizeof(SmemBwd) + 128;
     static unsigned long long attr_devices = 0;   // once per device
     if (first_use_on_device(attr_devices, ctx->device)) {
@@ -834,11 +1029,11 @@ int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const Ml
     // dP2 ~ inv_B x O(1..100): scale it into fp16's normal range with a power of two (exact, undone on the accumulators)
     const float scale_base = exp2f(floorf(log2f(1.0f / b.inv_B)));
     if (actor.act == critic.act && actor.act == B200RL_ACT_RELU)
-        ac_loss_grad_tc_kernel<B200RL_ACT_RELU><<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np, scale_base);
+        ac_loss_grad_tc_kernel<B200RL_ACT_RELU><<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np, scale_base, st, n_actor);
     else if (actor.act == critic.act && actor.act == B200RL_ACT_TANH)
-        ac_loss_grad_tc_kernel<B200RL_ACT_TANH><<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np, scale_base);
+        ac_loss_grad_tc_kernel<B200RL_ACT_TANH><<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np, scale_base, st, n_actor);
     else
-        ac_loss_grad_tc_kernel<-1><<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np, scale_base);
+        ac_loss_grad_tc_kernel<-1><<<grid, NT7_ALL, smem, ctx->stream>>>(actor, critic, params, hp, b, partial, loss_partial, np, scale_base, st, n_actor);
     LAUNCH_CHECK(ctx);
     return B200RL_OK;
 }
@@ -850,7 +1045,7 @@ extern "C" int b200rl_debug_k7_watch(int tid) {
 }
 extern "C" int b200rl_debug_k7_phases(unsigned long long* out16, int reset) {
     cudaDeviceSynchronize();
-    if (cudaMemcpyFromSymbol(out16, g_k7_phase, sizeof(unsigned long long) * 24) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out16, g_k7_phase, sizeof(unsigned long long) * 40) != cudaSuccess) return -1;
     if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(g_k7_phase, z, sizeof z); }
     return 0;
 }
