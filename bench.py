@@ -452,18 +452,19 @@ def run_c2(args):
             traffic = None
     ms_step = total_ms / args.steps
     share = (N_EPOCHS * N_MICRO * k_loss) / ms_step
-    tf32_peak = tf_peak / 2.0        # dense TF32 runs at half the bf16 rate on the tcgen05 pipe (1.1 vs 2.25 PFLOP/s nominal)
-    kname = ("ac_loss_grad_tc_kernel (PPO loss + backward, one minibatch; 64x64 GEMMs on tcgen05 as 3xTF32, FP32 accumulate in TMEM)"
+    kname = ("ac_loss_grad_tc_kernel (PPO loss + backward, one minibatch; 64x64 GEMMs on tcgen05 kind::f16 as a 3-term fp16 split "
+             "hi*hi + hi*lo + lo*hi, FP32 accumulate in TMEM; the optimiser step runs in the tail of the same launch)"
              if tc_on else "ac_loss_grad_kernel<64> (PPO loss + backward, one minibatch; FP32 FFMA)")
     roofline = {"kernel": kname, "bound": "tensor", "achieved": ach_tf, "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": ach_tf / tf_peak, "traffic": traffic, "peak_kind": f"bf16 dense GEMM burst, {peak_kind}",
-                "executed_tf32": {"tflops": 3.0 * ach_tf, "peak": tf32_peak, "frac": 3.0 * ach_tf / tf32_peak,
-                                  "note": "the 1e-5 parity bar needs 3xTF32 (three tensor-core products per algorithmic product, K = 8 per instruction): "
-                                          "executed tensor work / (half of the measured bf16 peak)"},
+                "executed_tensor": {"tflops": 3.0 * ach_tf, "peak": tf_peak, "frac": 3.0 * ach_tf / tf_peak,
+                                    "note": "the 1e-5 parity bar needs ~22 mantissa bits: every algorithmic product is three kind::f16 tensor-core products "
+                                            "(fp16 hi/lo split, K = 16 per instruction); executed tensor work / the measured 16-bit dense peak"},
                 "algorithmic_bytes_per_launch": B_local * BYTES_K7_SAMPLE,
                 "note": "achieved = algorithmic FP32 FLOPs (53,376 per sample) / event time; as a fraction of the FP32 CUDA-core peak (~72 TFLOP/s @1.9 GHz) = %.3f"
                         % (ach_tf / 72.0),
                 "ms_per_launch": k_loss, "ms_per_launch_fp32_ffma_variant": k_loss_ffma, "share_of_step": share,
+                "ms_per_launch_note": "loss + backward alone (the timed iteration additionally runs reduce + clip + Adam in the tail of each launch)",
                 "whole_loop_hbm": {"gbs": value * BYTES_LOOP_ENV_STEP / 1e9, "peak": hbm_peak * world, "frac": value * BYTES_LOOP_ENV_STEP / 1e9 / (hbm_peak * world),
                                    "note": "north-star figure: env-steps/s x 235 algorithmic B per env-step of the full PPO iteration (SURVEY §8d) / measured HBM "
                                            "copy bandwidth x n_gpus; the loop is issue/latency-bound, not HBM-bound"},
@@ -473,7 +474,9 @@ def run_c2(args):
                     "gae_ms": k_gae, "gae_gbs_l2_resident": n * T * BYTES_GAE / (k_gae * 1e-3) / 1e9,
                     "gae_note": "at this size the 52 MB working set of the GAE kernel is L2-resident when timed back to back (ncu: 19 MB DRAM read, 0 written): "
                                 "an L2 figure, not an HBM fraction; the HBM-bound sweep (4 M series) reaches 0.60 of the measured copy bandwidth (profiles/)",
-                    "reduce_clip_adam_ms": k_adam}}
+                    "reduce_clip_adam_ms": k_adam,
+                    "reduce_clip_adam_note": "the stand-alone optimiser-step kernel (FFMA path, ranks sharing a device, B200RL_FUSED_STEP=0); "
+                                             "the tensor-core K7 runs the step in its own tail"}}
 
     # ---- CPU baseline (rank 0, N = 1 only): oracle port, bounded sample ------------------------
     cpu = None
@@ -495,7 +498,7 @@ def run_c2(args):
             "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: 65536 batched CartPoleEnv{Float32} + PPO (2x64 MLP actor-critic, fp32), T=32, 4 epochs x 4 minibatches, advantage normalisation",
                        "n_envs": n_total, "envs_per_gpu": n, "global_batch": n_total * T // N_MICRO, "parallelism": f"dp{world}",
-                       "grad_allreduce": ("fused NVLink peer exchange inside the reduce+clip+Adam kernel" if job.peer_exchange else "NCCL") if world > 1 else "none",
+                       "grad_allreduce": ("fused NVLink peer exchange inside the tail of the loss+backward kernel (reduce -> exchange -> clip -> Adam in the same launch)" if job.peer_exchange else "NCCL") if world > 1 else "none",
                        "launch": "one CUDA graph launch per iteration (b200rl_onpolicy_iterate)" if graph else "eager launches",
                        "l2": "flushed (256 MB write) between timed steps, outside the timed region",
                        "timing": "one CUDA event pair per step, no host sync inside the loop, max over ranks of the summed device time",
@@ -568,7 +571,7 @@ def run_c3(args):
                        "n_envs": n, "parallelism": "dp1", "l2": "flushed between timed steps, outside the timed region",
                        "launch": "one CUDA graph launch per iteration" if agent.graph_active() else "eager launches"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "phases_per_rank": [ph],
-            "roofline": {"kernel": "ac_loss_grad_tc_kernel (A2C loss + backward over the whole rollout, Gaussian head, tanh; 3xTF32 on tcgen05)", "bound": "tensor",
+            "roofline": {"kernel": "ac_loss_grad_tc_kernel (A2C loss + backward over the whole rollout, Gaussian head, tanh; 3-term fp16 split on tcgen05 kind::f16)", "bound": "tensor",
                          "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None, "peak_kind": f"bf16 dense GEMM burst, {peak_kind}",
                          "ms_per_launch": k_loss, "share_of_step": k_loss / (total_ms / args.steps)},
             "cpu_baseline": None}

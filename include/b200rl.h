@@ -366,6 +366,13 @@ int b200rl_comm_init(b200rl_ctx* ctx, int nranks, int rank, const void* id128); 
 int b200rl_comm_p2p_export(b200rl_ctx* ctx, void* handle64_out, void** region_out);
 int b200rl_comm_p2p_open(b200rl_ctx* ctx, const void* handle64, void** region_out);
 int b200rl_comm_p2p_attach(b200rl_ctx* ctx, void* const* regions);
+/* PCI bus id of the ctx's device ("0000:1b:00.0", NUL-terminated, len >= 16): lets the ranks of a job find out whether they
+ * all drive different GPUs.  b200rl_comm_p2p_set_exclusive(ctx, 1) then declares it (call after attach, same value on every
+ * rank): only with one rank per device may a whole-device kernel wait for its peers inside itself, which is what the fused
+ * loss + backward + exchange + optimiser-step launch does; otherwise (default for IPC-mapped peers) the exchange stays in
+ * its own small kernel.  attach() sets the flag itself for peers of the same process (raw pointers). */
+int b200rl_ctx_pci_bus_id(b200rl_ctx* ctx, char* out, int len);
+int b200rl_comm_p2p_set_exclusive(b200rl_ctx* ctx, int exclusive);
 int b200rl_comm_allreduce_f32(b200rl_ctx* ctx, float* dev_buf, int64_t n);
 
 #ifdef __cplusplus

@@ -161,6 +161,8 @@ SIGNATURES = {
     "b200rl_comm_p2p_export": (_i32, [_vp, _vp, _pp]),
     "b200rl_comm_p2p_open": (_i32, [_vp, _vp, _pp]),
     "b200rl_comm_p2p_attach": (_i32, [_vp, _vp]),
+    "b200rl_ctx_pci_bus_id": (_i32, [_vp, _vp, _i32]),
+    "b200rl_comm_p2p_set_exclusive": (_i32, [_vp, _i32]),
 }
 
 _LIB = None

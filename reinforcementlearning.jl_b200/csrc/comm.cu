@@ -227,6 +227,17 @@ int b200rl_comm_p2p_attach(b200rl_ctx* ctx, void* const* regions) {
     c->tab = t;
     return B200RL_OK;
 }
+int b200rl_ctx_pci_bus_id(b200rl_ctx* ctx, char* out, int len) {
+    TRY(ctx_bind(ctx));
+    REQUIRE(out && len >= 16, B200RL_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaDeviceGetPCIBusId(out, len, ctx->device));
+    return B200RL_OK;
+}
+int b200rl_comm_p2p_set_exclusive(b200rl_ctx* ctx, int exclusive) {
+    REQUIRE(ctx && ctx->comm && ctx->comm->tab.nranks > 1, B200RL_ERR_INVALID, "attach the peer exchange first");
+    ctx->comm->tab.exclusive = exclusive ? 1 : 0;
+    return B200RL_OK;
+}
 /* in-place sum all-reduce of a DEVICE fp32 buffer on the ctx stream */
 int b200rl_comm_allreduce_f32(b200rl_ctx* ctx, float* dev_buf, int64_t n) {
     TRY(ctx_bind(ctx));

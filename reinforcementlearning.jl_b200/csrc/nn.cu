@@ -1102,7 +1102,7 @@ int nn_ac_loss_grad(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& critic
     int st;
     if (nn_tc_enabled() && nn_tc_bwd_supported(actor, critic)) {
         const int grid = 2 * (ctx->sm_count / 2);   // one 512-thread CTA per SM, split between the roles (nn_tc_actor_ctas)
-        ctas = nn_tc_partial_rows(grid, actor, hp);
+        ctas = nn_tc_partial_rows(grid, actor, hp, b.B);
         st = nn_tc_ac_loss_grad(ctx, grid, actor, critic, params, hp, b, partial, loss_partial, np, nullptr);
     } else if (actor.H == 64) {
         st = launch_ac<64>(ctx, 2 * ctas, actor, critic, params, hp, b, partial, loss_partial, np);
@@ -1134,7 +1134,7 @@ int nn_ac_loss_grad_step(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& c
         st.seq_ptr = b200rl_comm_p2p_seq_dev(ctx);
     }
     int rc = nn_tc_ac_loss_grad(ctx, 2 * ctas, actor, critic, params, hp, b, partial, loss_partial, np, &st);
-    return rc != B200RL_OK ? rc : nn_tc_partial_rows(2 * ctas, actor, hp);
+    return rc != B200RL_OK ? rc : nn_tc_partial_rows(2 * ctas, actor, hp, b.B);
 }
 
 int nn_reduce_partials(b200rl_ctx* ctx, const float* partial, int n_partials, int64_t np, float* grad, const float* loss_partial,

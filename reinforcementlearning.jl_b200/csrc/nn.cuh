@@ -110,6 +110,6 @@ int nn_tc_rollout(b200rl_ctx* ctx, b200rl_env* env, const MlpDesc& actor, const 
                   unsigned long long* policy_rng, int t0, int nsteps, int T, int final_bootstrap, float* states, void* actions, float* logp,
                   float* values, float* rewards, uint8_t* terminals);
 bool nn_tc_bwd_supported(const MlpDesc& actor, const MlpDesc& critic);
-int nn_tc_partial_rows(int grid, const MlpDesc& actor, const AcHyper& hp);   // gradient-partial rows the tensor-core K7 writes with `grid` CTAs
+int nn_tc_partial_rows(int grid, const MlpDesc& actor, const AcHyper& hp, int64_t B);   // gradient-partial rows the tensor-core K7 writes with `grid` CTAs
 int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
                        const AcBatch& b, float* partial, float* loss_partial, int64_t np, const AcStep* step /* null: loss + backward only */);

@@ -988,21 +988,27 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ 
 
 }  // namespace
 
-// CTAs given to the actor out of `grid` (the rest work on the critic): the measured per-tile cost ratio actor : critic (profiles/
-// k7_phase_timing.py) is ~1.04 for the categorical PPO / A2C loss; B200RL_K7_ACTOR_CTAS overrides it for tuning runs.
-int nn_tc_actor_ctas(int grid, const MlpDesc& actor, const AcHyper& hp) {
+// CTAs given to the actor out of `grid` (the rest work on the critic).  A critic tile costs ~0.87 of an actor tile with the
+// categorical PPO / A2C loss and ~0.85 with the Gaussian head (B200 sweeps, profiles/na_sweep.sh: 79 : 69 is the optimum for the
+// 4 096-tile BASELINE minibatch, 80 : 68 for the 8 192-tile Pendulum batch); the split minimises the longer of the two roles'
+// whole-tile counts.  B200RL_K7_ACTOR_CTAS overrides it for tuning runs.
+int nn_tc_actor_ctas(int grid, const MlpDesc& actor, const AcHyper& hp, int64_t ntiles) {
     static int forced = -2;
     if (forced == -2) { const char* e = getenv("B200RL_K7_ACTOR_CTAS"); forced = e ? atoi(e) : -1; }
     if (forced > 0 && forced < grid) return forced;
     (void)hp;
-    const int share = actor.heads2 ? 82 : 77;   // of 148 (B200 sweeps: profiles/na_sweep.sh)
-    int n = (grid * share + 74) / 148;
-    if (n < 1) n = 1;
-    if (n > grid - 1) n = grid - 1;
-    return n;
+    const double r = actor.heads2 ? 0.85 : 0.87;
+    int best = grid / 2;
+    double best_cost = 1e300;
+    for (int na = grid / 2; na <= grid / 2 + 8 && na < grid; ++na) {   // (+8: the fused optimiser step stages <= 82 partial rows)
+        const double ca = (double)((ntiles + na - 1) / na), cc = r * (double)((ntiles + (grid - na) - 1) / (grid - na));
+        const double cost = ca > cc ? ca : cc;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = na; }
+    }
+    return best;
 }
-int nn_tc_partial_rows(int grid, const MlpDesc& actor, const AcHyper& hp) {
-    const int na = nn_tc_actor_ctas(grid, actor, hp);
+int nn_tc_partial_rows(int grid, const MlpDesc& actor, const AcHyper& hp, int64_t B) {
+    const int na = nn_tc_actor_ctas(grid, actor, hp, (B + TM - 1) / TM);
     return na > grid - na ? na : grid - na;
 }
 bool nn_tc_bwd_supported(const MlpDesc& actor, const MlpDesc& critic) {
@@ -1011,7 +1017,7 @@ bool nn_tc_bwd_supported(const MlpDesc& actor, const MlpDesc& critic) {
 int nn_tc_ac_loss_grad(b200rl_ctx* ctx, int grid, const MlpDesc& actor, const MlpDesc& critic, const float* params, const AcHyper& hp,
                        const AcBatch& b, float* partial, float* loss_partial, int64_t np, const AcStep* step) {
     AcStep st = {};
-    const int n_actor = nn_tc_actor_ctas(grid, actor, hp);
+    const int n_actor = nn_tc_actor_ctas(grid, actor, hp, (b.B + TM - 1) / TM);
     if (step) {
         st = *step;
         const int64_t per = (np + grid - 1) / grid;

@@ -92,4 +92,10 @@ def attach_peer_exchange(ctx, rank, world, all_gather_bytes):
     if not all(f == b"\x01" for f in flags):
         return False
     L.check(ctx.lib.b200rl_comm_p2p_attach(ctx.h, regions))
+    # one rank per physical GPU?  Then the optimiser step (with its gradient exchange) may run in the tail of the whole-device
+    # loss + backward launch; ranks sharing a GPU keep the exchange in its own small kernel (they could not both be resident).
+    bus = (C.c_char * 32)()
+    L.check(ctx.lib.b200rl_ctx_pci_bus_id(ctx.h, bus, 32))
+    ids = all_gather_bytes(bytes(bus.value))
+    L.check(ctx.lib.b200rl_comm_p2p_set_exclusive(ctx.h, 1 if len(set(ids)) == world else 0))
     return True
