@@ -353,6 +353,10 @@ int b200rl_dqn_last_td(b200rl_net* net, b200rl_traj* traj, float* host_dst, int6
 
 /* select the tcgen05 tensor-core kernels (default, H = 64) or the FP32 CUDA-core kernels for the dense layers */
 int b200rl_set_tensor_cores(int enable);
+/* 1 (default; B200RL_FUSED_STEP=0 in the environment starts with 0): the on-policy update runs reduce + [peer exchange] + clip +
+ * Adam in the tail of the tensor-core loss + backward launch (one launch per optimiser step); 0: a second kernel does it.
+ * Both orders of summation over the gradient partials are identical; process-wide, like b200rl_set_tensor_cores. */
+int b200rl_set_fused_step(int enable);
 /* ---------------------------------------------------------------- multi-GPU -------- */
 /* env-index data parallelism: one process per GPU, one sum all-reduce of the flat gradient per
  * optimiser step over NCCL / NVLink.  rank 0 makes the 128-byte id. */

@@ -2,7 +2,7 @@
 import collections, csv, io, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
@@ -44,9 +44,10 @@ for name in ("prof_loss", "prof_rollout", "prof_fwd", "prof_adam", "prof_env", "
             if k in rec:
                 lines.append("| %s | %s | %s |" % (k, rec[k], ui.get(k, "")))
         try:
-            t = float(rec["dram__bytes_read.sum"].replace(",", "")) + float(rec["dram__bytes_write.sum"].replace(",", ""))
-            u = ui.get("dram__bytes_read.sum", "byte")
-            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            MULT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}   # ncu picks a unit per metric: convert each one separately
+            t = (float(rec["dram__bytes_read.sum"].replace(",", "")) * MULT.get(ui.get("dram__bytes_read.sum", "byte"), 1)
+                 + float(rec["dram__bytes_write.sum"].replace(",", "")) * MULT.get(ui.get("dram__bytes_write.sum", "byte"), 1))
+            mult = 1
             mk = re.search(r"(ac_loss_grad_tc_kernel|ac_loss_grad_kernel|rollout_tc_kernel|forward_tc_kernel|forward_kernel|reduce_clip_adam_kernel|env_step_kernel|scan_series_fastest|dqn_loss_grad_kernel|pack_records_kernel|sample_gather_kernel)", kn)
             traffic[mk.group(1) if mk else kn] = t * mult
             lines.append("| dram traffic (read+write) | %.3f | MB |" % (t * mult / 1e6))

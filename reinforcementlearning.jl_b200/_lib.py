@@ -155,6 +155,7 @@ SIGNATURES = {
     "b200rl_dqn_update": (_i32, [_vp, _vp, _vp, _vp]),
     "b200rl_dqn_last_td": (_i32, [_vp, _vp, _vp, _i64]),
     "b200rl_set_tensor_cores": (_i32, [_i32]),
+    "b200rl_set_fused_step": (_i32, [_i32]),
     "b200rl_comm_unique_id": (_i32, [_vp]),
     "b200rl_comm_init": (_i32, [_vp, _i32, _i32, _vp]),
     "b200rl_comm_allreduce_f32": (_i32, [_vp, _vp, _i64]),

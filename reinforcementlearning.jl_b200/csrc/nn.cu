@@ -1022,6 +1022,8 @@ bool nn_tc_enabled() {
     return g_tc != 0;
 }
 extern "C" int b200rl_set_tensor_cores(int enable) { g_tc = enable ? 1 : 0; return B200RL_OK; }
+static int g_fused_step = -1;   // -1: not decided yet (environment), see nn_ac_loss_grad_step
+extern "C" int b200rl_set_fused_step(int enable) { g_fused_step = enable ? 1 : 0; return B200RL_OK; }
 
 int nn_grid_ctas(b200rl_ctx* ctx, int H) { return H == 64 ? ctx->sm_count : ctx->sm_count / 2; }
 
@@ -1118,9 +1120,8 @@ int nn_ac_loss_grad_step(b200rl_ctx* ctx, const MlpDesc& actor, const MlpDesc& c
                          float* partial, float* loss_partial, float* grad, float* m, float* v, float* beta_t, float* loss_out4,
                          float max_grad_norm, float lr, float b1, float b2, float eps, float* gnorm_out, double* cta_sumsq,
                          unsigned int* counter4, float* stats_row, unsigned int* tick) {
-    static int enabled = -1;
-    if (enabled < 0) { const char* e = getenv("B200RL_FUSED_STEP"); enabled = (e && e[0] == '0') ? 0 : 1; }
-    if (!enabled || !nn_tc_enabled() || !nn_tc_bwd_supported(actor, critic) || actor.H != critic.H || actor.in != critic.in) return B200RL_ERR_UNSUPPORTED;
+    if (g_fused_step < 0) { const char* e = getenv("B200RL_FUSED_STEP"); g_fused_step = (e && e[0] == '0') ? 0 : 1; }
+    if (!g_fused_step || !nn_tc_enabled() || !nn_tc_bwd_supported(actor, critic) || actor.H != critic.H || actor.in != critic.in) return B200RL_ERR_UNSUPPORTED;
     if (check_desc(actor) != B200RL_OK || check_desc(critic) != B200RL_OK) return B200RL_ERR_UNSUPPORTED;
     const int ctas = ctx->sm_count / 2;
     const int64_t np = actor.nparams() + critic.nparams();

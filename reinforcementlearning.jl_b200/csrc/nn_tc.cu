@@ -5,12 +5,13 @@
 // ~FP32 accuracy (1e-5 relative on losses), which no single tensor-core input format gives, so every product is a 3-term split
 //     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi,   x_hi = fp16(x * S), x_lo = fp16(x * S - x_hi)      (22 mantissa bits)
 // with a power-of-two scale S per operand (exact; undone on the FP32 accumulator), accumulated in FP32.  Round 1 used the same
-// split on kind::tf32 (K = 8 per instruction).  A tcgen05.mma of these shapes occupies the pipe for ~155-175 cycles whatever
-// its N (<= 128) or kind (profiles/umma_probe_f16.py), so the pipe is paced by the instruction COUNT: kind::f16 covers K = 16
-// per instruction and halves it (48 -> 24 per tile) at the same 2^-22 product accuracy.  fp16 has 5 exponent bits: activations
+// split on kind::tf32 (K = 8 per instruction); kind::f16 covers K = 16 per instruction at the same 2^-22 product accuracy.
+// A tcgen05.mma (M = 128, K = 16) occupies the pipe for 10 + N/2 cycles with A in TMEM and 43 + N/2 with A in shared memory
+// (profiles/umma_pacing.py) PROVIDED it is issued under an elect.sync predicate (umma::elect_one): under `lane == 0` ptxas wraps
+// every MMA in an ELECT / BRA.U.ANY loop that costs ~100 cycles of issue time.  fp16 has 5 exponent bits: activations
 // must stay below 65504 in magnitude (scale 1), weights below 1023 (scale 64); gradients are scaled by ~1/(4 inv_B) at launch.
 // Below 6e-5 the lo part is subnormal: absolute error <= 2^-25 per element, far inside the 1e-5 bar.  Layer 1 (K <= 4) and the
-// heads (N <= 4) stay on FFMA.  The forward-only kernels (policy inference, fused rollout) live in fwd_tc.cu (3xTF32).
+// heads (N <= 2) stay on FFMA.  The forward-only kernels (policy inference, fused rollout) live in fwd_tc.cu (same split).
 #include "nn.cuh"
 #include "perm.cuh"
 #include "umma.cuh"
@@ -69,11 +70,9 @@ constexpr int NT7 = 512;
 constexpr int GF_T = 128;                 // stride between 8-sample k-blocks
 constexpr int GS_T = 16 * GF_T;           // stride between 8-feature blocks (128 samples)
 constexpr int FIMG = 8 * GS_T;            // [64 features x 128 samples] fp16 = 16 KB
-// tcgen05.mma instructions pace at ~155-175 cycles each whatever their N (<= 128) (profiles/umma_probe_f16.py), so the kernel
-// minimises their number: hi|lo operands are stacked along N (and M for GEMM3), K = 16 per instruction.
-// TMEM columns: R1 = D1 of GEMM1 ([hh+lh | hl], 128 columns), then (after P3 consumed it) the dP2 A operand of GEMM2 in its first 64
-// columns (hi: 32 columns of fp16 pairs | lo: 32); D2 = GEMM2 accumulator; D3 = GEMM3 accumulator (all tiles); AH = H1 A operand
-// of GEMM1 (hi 32 | lo 32 columns).
+// TMEM columns: R1 = D1 of GEMM1 (64 columns: hi*hi + hi*lo + lo*hi accumulated in place), then (after P3 consumed it) the dP2 A
+// operand of GEMM2 in the same 64 columns (hi: 32 columns of fp16 pairs | lo: 32); D2 = GEMM2 accumulator (64 columns); D3 = GEMM3
+// accumulator (all tiles; hi|lo operands stacked along M and N, one MMA per K step); AH = H1 A operand of GEMM1 (hi 32 | lo 32).
 // D3 has 144 columns: the B operand of GEMM3 carries a constant "ones" row behind H1^T, so column 128 is sum_s dP2 = db2.
 // D4 = GEMM4 accumulator (16 columns): dW1 | db1 = dP1^T x [x | 1], accumulated over all tiles like D3.
 constexpr uint32_t COL_R1 = 0, COL_D2 = 128, COL_D3 = 256, COL_D4 = 400, COL_AH = 448;
@@ -258,9 +257,9 @@ __device__ int g_k7_watch = 0;   // watched worker thread (low 16 bits) of CTA (
 #define K7_T(i) do { } while (0)
 #define K7_TI(i) do { } while (0)
 #endif
-// 16 worker warps + one warpgroup (warps 16..19) whose first warp feeds the tensor core.  Issuing a tcgen05.mma costs its
-// thread ~60 cycles and blocks it once the MMA queue is full (~1.1 k cycles for a 16-instruction GEMM), which used to stall
-// a worker warp — and with it everybody at the next CTA barrier.  The register file is per scheduler (16 K registers, 5 warps
+// 16 worker warps + one warpgroup (warps 16..19) whose first warp feeds the tensor core.  The issuing thread blocks once the MMA
+// queue is full (the issue side of a GEMM takes as long as its execution), which used to stall a worker warp — and with it
+// everybody at the next barrier.  The register file is per scheduler (16 K registers, 5 warps
 // each now), so the issuer warpgroup gives its registers back (setmaxnreg.dec 24) and the workers take 120 (setmaxnreg.inc).
 constexpr int NT7_ALL = NT7 + 128;
 // The tensor core adds into an FP32 accumulator with truncation: a chain of n accumulating MMAs biases a same-signed sum by

@@ -654,6 +654,14 @@ function attach_peer_exchange(ctx::B200Context, nranks::Integer, rank::Integer, 
         regions[r+1] = out[]
     end
     GC.@preserve regions check(ccall((:b200rl_comm_p2p_attach, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), ctx.h, regions))
+    # one rank per physical GPU?  Then the optimiser step (with the gradient exchange) runs in the tail of the loss + backward
+    # launch; ranks that share a GPU keep the exchange in its own small kernel (two whole-device kernels cannot be co-resident).
+    bus = zeros(UInt8, 32)
+    GC.@preserve bus check(ccall((:b200rl_ctx_pci_bus_id, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint), ctx.h, bus, 32))
+    ids = allgather(bus)
+    check(ccall((:b200rl_comm_p2p_set_exclusive, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.h, length(unique(ids)) == nranks ? 1 : 0))
 end
+"`set_fused_step(false)` keeps reduce + clip + Adam in a kernel of their own (default: the tail of the loss + backward launch)."
+set_fused_step(on::Bool) = check(ccall((:b200rl_set_fused_step, LIB), Cint, (Cint,), on ? 1 : 0))
 
 end # module

@@ -96,3 +96,33 @@ def test_graph_replayed_iterations_are_bit_identical_to_eager_ones(pkg, ctx, kin
     for k in ("params", "m", "v", "bt", "state", "erng", "prng", "adv", "stats"):
         assert np.asarray(a[k]).tobytes(order="A") == np.asarray(b[k]).tobytes(order="A"), k
     assert a["ep"]["env_steps"] == b["ep"]["env_steps"] == iters * T * n and a["ep"]["episodes"] == b["ep"]["episodes"]
+
+
+@pytest.mark.parametrize("kind,envkw,algo,n", [("CartPole", {}, "ppo", 4096), ("Pendulum", dict(continuous=True), "a2c", 1500)])
+def test_optimiser_step_fused_into_the_loss_kernel_matches_the_separate_kernel(pkg, ctx, kind, envkw, algo, n):
+    """The tensor-core loss + backward launch runs reduce -> clip_by_global_norm! -> Adam in its own tail (two in-kernel grid
+    barriers); b200rl_set_fused_step(0) leaves that to reduce_clip_adam_kernel.  Both add the per-CTA gradient partials in the
+    same (CTA) order, so gradients, Adam state and parameters agree bit for bit; only the FP64 sum of squares behind the
+    global norm is partitioned differently (62 vs 256 parameters per CTA), which can move the norm by one ulp at most."""
+    T, iters = 8, 3
+    R = pkg.learners
+    outs = []
+    try:
+        for fused in (1, 0):
+            pkg._lib.check(ctx.lib.b200rl_set_fused_step(fused))
+            env, net, agent = _make(pkg, ctx, kind, n, T, 23, algo, **envkw)
+            l0 = ctx.launch_count()
+            for _ in range(iters):
+                agent.collect(T)
+                stats = agent.update(want_stats=True)
+            outs.append(dict(params=net.get(), m=net.get(R.NET_M), v=net.get(R.NET_V), bt=net.get(R.NET_BETA_T), stats=np.asarray(stats), launches=ctx.launch_count() - l0))
+            agent.close(); net.close(); env.close()
+    finally:
+        pkg._lib.check(ctx.lib.b200rl_set_fused_step(1))
+    a, b = outs
+    assert a["launches"] < b["launches"], "the fused step must save one launch per optimiser step"
+    assert np.array_equal(a["bt"], b["bt"])
+    np.testing.assert_allclose(a["stats"], b["stats"], rtol=1e-6, atol=0)
+    for k in ("params", "m", "v"):
+        np.testing.assert_allclose(a[k], b[k], rtol=2e-6, atol=1e-9, err_msg=k)
+    assert np.mean(a["params"] == b["params"]) > 0.99
