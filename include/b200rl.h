@@ -82,7 +82,9 @@ int b200rl_flush_l2(b200rl_ctx* ctx);
 typedef enum {
     B200RL_ENV_CARTPOLE = 0, B200RL_ENV_PENDULUM = 1, B200RL_ENV_MOUNTAINCAR = 2,
     B200RL_ENV_CARTPOLE_CONTINUOUS = 3,     /* CartPoleEnv(continuous = true): Float32 action in -1.0..1.0 (CartPoleEnv.jl:74-79,106-110) */
-    B200RL_ENV_MOUNTAINCAR_CONTINUOUS = 4   /* ContinuousMountainCarEnv (MountainCarEnv.jl:73-74,83,107-111); params as mountaincar */
+    B200RL_ENV_MOUNTAINCAR_CONTINUOUS = 4,  /* ContinuousMountainCarEnv (MountainCarEnv.jl:73-74,83,107-111); params as mountaincar */
+    B200RL_ENV_ACROBOT = 5                  /* AcrobotEnv{Float64} (3rd_party/AcrobotEnv.jl:19-225): B200RL_F64 only, 6 observations, 3 actions;
+                                               one classical RK4 step per act! (the reference's adaptive OrdinaryDiffEq controller is external) */
 } b200rl_env_kind;
 typedef enum { B200RL_F32 = 0, B200RL_F64 = 1 } b200rl_dtype;
 typedef enum {
@@ -114,6 +116,12 @@ typedef struct {   /* MountainCarEnvParams{T}: MountainCarEnv.jl:3-40 */
     double min_pos, max_pos, max_speed, goal_pos, goal_velocity, power, gravity;
     int64_t max_steps;
 } b200rl_mountaincar_params;
+typedef struct {   /* AcrobotEnvParams{T} + book_or_nips: 3rd_party/AcrobotEnv.jl:19-60 (max_torque_noise must be 0) */
+    double link_length_a, link_length_b, link_mass_a, link_mass_b, link_com_pos_a, link_com_pos_b, link_moi, max_torque_noise,
+        max_vel_a, max_vel_b, g, dt;
+    int64_t max_steps;
+    int32_t book;   /* 1: book_or_nips = "book" (default), 0: "nips" */
+} b200rl_acrobot_params;
 
 /* Replaces N x `CartPoleEnv(; T, rng)` / `PendulumEnv` / `MountainCarEnv` constructors
  * (CartPoleEnv.jl:74-79, PendulumEnv.jl:41-66, MountainCarEnv.jl:67-81) and the absent

@@ -245,4 +245,100 @@ template <class T_> struct MountainCarT {
 };
 using MountainCar = MountainCarT<float>;
 
+// ------------------------------------------------------------------ Acrobot ----------
+// AcrobotEnv (RLEnvs/src/environments/3rd_party/AcrobotEnv.jl:19-225), T = Float64 (the constructor's default, :20).
+// reset! :100-107, act! :110-140, dsdt :142-196 (the `book` and `nips` variants), wrap / bound :201-225.
+// DEVIATION (documented in DESIGN.md §3): the reference integrates [0, dt] with OrdinaryDiffEq.solve(ode, RK4()) — an adaptive
+// step-size controller that lives in an external package absent from the tree; this restatement takes ONE classical RK4 step
+// over [0, dt], which is what the file's own source of the equations does ("governing equations as per python gym": gym's
+// rk4(derivs, y0, [0, dt])).  Trajectories agree to the solver tolerance, not bit for bit: PARITY UNPINNED.
+struct AcrobotParams {  // AcrobotEnvParams{T}
+    double link_length_a, link_length_b, link_mass_a, link_mass_b, link_com_pos_a, link_com_pos_b, link_moi, max_torque_noise,
+        max_vel_a, max_vel_b, g, dt;
+    int64_t max_steps;
+    int32_t book;   // book_or_nips == "book" (default) | "nips"
+};
+inline AcrobotParams acrobot_default_params() {
+    return AcrobotParams{1.0, 1.0, 1.0, 1.0, 0.5, 0.5, 1.0, 0.0, 4 * jl::PI_D, 9 * jl::PI_D, 9.8, 0.2, 200, 1};
+}
+struct Acrobot {
+    using T = double;
+    static constexpr int NS = 4, NOBS = 6, NACT = 3;
+    AcrobotParams p;
+    std::vector<T> state;
+    int64_t action = 2;
+    bool done = false;
+    int64_t t = 0;
+    T rew = -1;
+    jl::Xoshiro rng;
+    Acrobot(const AcrobotParams& q, jl::Xoshiro r, bool do_reset = true) : p(q), state(4, 0.0), rng(r) {
+        if (do_reset) reset();   // AcrobotEnv.jl:71
+    }
+    void reset() {  // AcrobotEnv.jl:100-107
+        T u[4];
+        jl::rand_array4(rng, u);   // rand(env.rng, T, 4)
+        for (int k = 0; k < 4; ++k) state[k] = (T)0.1 * u[k] - (T)0.05;
+        t = 0; action = 2; done = false; rew = -1;
+    }
+    // dsdt (AcrobotEnv.jl:142-196); a = the torque carried in the augmented state
+    void dsdt(const T* s, T a, T* du) const {
+        const T m1 = p.link_mass_a, m2 = p.link_mass_b, l1 = p.link_length_a, lc1 = p.link_com_pos_a, lc2 = p.link_com_pos_b;
+        const T I1 = p.link_moi, I2 = p.link_moi, g = p.g;
+        const T theta1 = s[0], theta2 = s[1], dtheta1 = s[2], dtheta2 = s[3];
+        T ddtheta1 = 0.0, ddtheta2 = 0.0;
+        const T c2 = jl::jcos(theta2), s2 = jl::jsin(theta2);
+        const T d1 = ((m1 * (lc1 * lc1) + m2 * (((l1 * l1) + (lc2 * lc2)) + ((2 * l1) * lc2) * c2)) + I1) + I2;
+        const T d2 = m2 * ((lc2 * lc2) + (l1 * lc2) * c2) + I2;
+        const T phi2 = ((m2 * lc2) * g) * jl::jcos((theta1 + theta2) - jl::PI_D / 2.0);
+        const T phi1 = (((((((-m2) * l1) * lc2) * (dtheta2 * dtheta2)) * s2) - ((((((2 * m2) * l1) * lc2) * dtheta2) * dtheta1) * s2)) +
+                        ((m1 * lc1 + m2 * l1) * g) * jl::jcos(theta1 - jl::PI_D / 2)) + phi2;
+        if (!p.book) {
+            ddtheta2 = ((a + (d2 / d1) * phi1) - phi2) / (((m2 * (lc2 * lc2)) + I2) - (d2 * d2) / d1);
+        } else {
+            ddtheta2 = (((a + (d2 / d1) * phi1) - ((((m2 * l1) * lc2) * (dtheta1 * dtheta1)) * s2)) - phi2) / (((m2 * (lc2 * lc2)) + I2) - (d2 * d2) / d1);
+            ddtheta1 = (-(d2 * ddtheta2 + phi1)) / d1;
+        }
+        du[0] = dtheta1; du[1] = dtheta2; du[2] = ddtheta1; du[3] = ddtheta2;
+    }
+    static T wrap(T x, T m, T M) {   // AcrobotEnv.jl:201-217
+        const T diff = M - m;
+        while (x > M) x = x - diff;
+        while (x < m) x = x + diff;
+        return x;
+    }
+    static T bound(T x, T m, T M) { return std::fmin(std::fmax(x, m), M); }   // AcrobotEnv.jl:219-225 (min(max(x, m), M))
+    bool act(int64_t a) {   // AcrobotEnv.jl:110-140
+        if (a < 1 || a > 3) return false;   // action_space = Base.OneTo(3)
+        action = a;
+        t += 1;
+        const T torque = (T)(a - 2);         // avail_torque = [-1, 0, 1]  (max_torque_noise = 0: no draw)
+        // one classical RK4 step over [0, dt] (see DEVIATION above)
+        const T h = p.dt, h2 = p.dt / 2.0;
+        T y0[4] = {state[0], state[1], state[2], state[3]}, k1[4], k2[4], k3[4], k4[4], y[4];
+        dsdt(y0, torque, k1);
+        for (int i = 0; i < 4; ++i) y[i] = y0[i] + h2 * k1[i];
+        dsdt(y, torque, k2);
+        for (int i = 0; i < 4; ++i) y[i] = y0[i] + h2 * k2[i];
+        dsdt(y, torque, k3);
+        for (int i = 0; i < 4; ++i) y[i] = y0[i] + h * k3[i];
+        dsdt(y, torque, k4);
+        T ns[4];
+        for (int i = 0; i < 4; ++i) ns[i] = y0[i] + (h / 6.0) * (((k1[i] + 2 * k2[i]) + 2 * k3[i]) + k4[i]);
+        ns[0] = wrap(ns[0], -jl::PI_D, jl::PI_D);
+        ns[1] = wrap(ns[1], -jl::PI_D, jl::PI_D);
+        ns[2] = bound(ns[2], -p.max_vel_a, p.max_vel_a);
+        ns[3] = bound(ns[3], -p.max_vel_b, p.max_vel_b);
+        for (int i = 0; i < 4; ++i) state[i] = ns[i];
+        const bool succeeded = (-jl::jcos(ns[0]) - jl::jcos(ns[1] + ns[0])) > 1.0;
+        done = succeeded || t > p.max_steps;
+        rew = succeeded ? 0.0 : -1.0;
+        return true;
+    }
+    T reward() const { return rew; }
+    void obs(T* out) const {   // acrobot_observation (AcrobotEnv.jl:76)
+        out[0] = jl::jcos(state[0]); out[1] = jl::jsin(state[0]); out[2] = jl::jcos(state[1]); out[3] = jl::jsin(state[1]);
+        out[4] = state[2]; out[5] = state[3];
+    }
+};
+
 }  // namespace oracle

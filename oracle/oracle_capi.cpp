@@ -113,6 +113,10 @@ void* orc_vecenv_create(int kind, int dtype, int64_t N, const double* q, const u
         MountainCarParams p{q[0], q[1], q[2], q[3], q[4], q[5], q[6], (int64_t)q[7]};
         if (dtype == 1) return (VecEnvBase*)new VecMountainCar64C(N, p, rng);
         return (VecEnvBase*)new VecMountainCarC(N, p, rng);
+    } else if (kind == 5) {   // AcrobotEnv{Float64}: 14 doubles in AcrobotParams order
+        if (dtype != 1) return nullptr;
+        AcrobotParams p{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], q[10], q[11], (int64_t)q[12], (int32_t)q[13]};
+        return (VecEnvBase*)new VecAcrobot(N, p, rng);
     }
     return nullptr;
 }

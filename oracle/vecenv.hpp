@@ -43,6 +43,7 @@ template <class E, class T, class ActT> struct VecEnv : VecEnvBase {
         for (int64_t i = 0; i < N; ++i) {
             jl::Xoshiro g{rng[4 * i], rng[4 * i + 1], rng[4 * i + 2], rng[4 * i + 3]};
             envs.emplace_back(new E(p, g, true));
+            reset_reward(i);
         }
     }
     int64_t size() const override { return (int64_t)envs.size(); }
@@ -50,12 +51,13 @@ template <class E, class T, class ActT> struct VecEnv : VecEnvBase {
         int64_t N = size();
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < N; ++i) {
-            if (force || ((flags[i] & 1) && !(flags[i] & 2))) envs[i]->reset();
+            if (force || ((flags[i] & 1) && !(flags[i] & 2))) { envs[i]->reset(); reset_reward(i); }
             flags[i] = 0;
         }
     }
     static bool do_act(E& e, ActT a);
     static int64_t n_random_actions(const E& e);
+    void reset_reward(int64_t) {}   // specialised for envs whose reset! sets the reward field (AcrobotEnv.jl:105)
     void post(int64_t i, int auto_reset) {
         E& e = *envs[i];
         rewards[i] = e.reward();
@@ -131,6 +133,12 @@ using VecPendulum64C = VecEnv<Pendulum64C, double, double>;
 using VecPendulum64D = VecEnv<Pendulum64D, double, int32_t>;
 using VecMountainCar64 = VecEnv<MountainCar64, double, int32_t>;
 using VecMountainCar64C = VecEnv<MountainCar64C, double, double>;
+using VecAcrobot = VecEnv<Acrobot, double, int32_t>;   // AcrobotEnv{Float64}
+template <> inline void VecAcrobot::reset_reward(int64_t i) { rewards[i] = envs[i]->reward(); }
+template <> inline void VecAcrobot::action_out(const Acrobot& e, void* d, int64_t i) { ((int32_t*)d)[i] = (int32_t)e.action; }
+template <> inline bool VecAcrobot::do_act(Acrobot& e, int32_t a) { return e.act(a); }
+template <> inline int64_t VecAcrobot::n_random_actions(const Acrobot&) { return 3; }
+template <> inline void VecAcrobot::do_act_discrete(Acrobot& e, int64_t a) { e.act(a); }
 template <> inline void VecPendulum64C::action_out(const Pendulum64C& e, void* d, int64_t i) { ((double*)d)[i] = e.action; }
 template <> inline void VecPendulum64D::action_out(const Pendulum64D& e, void* d, int64_t i) { ((float*)d)[i] = (float)e.action; }
 template <> inline void VecMountainCar64::action_out(const MountainCar64& e, void* d, int64_t i) { ((int32_t*)d)[i] = (int32_t)e.action; }

@@ -14,7 +14,7 @@ SO_PATH = os.environ.get("B200RL_LIB") or os.path.join(HERE, "libb200rl.so")
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_ACTION, ERR_NCCL, ERR_OOM = -1, -2, -3, -4, -5, -6
 
-ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR, ENV_CARTPOLE_CONTINUOUS, ENV_MOUNTAINCAR_CONTINUOUS = 0, 1, 2, 3, 4
+ENV_CARTPOLE, ENV_PENDULUM, ENV_MOUNTAINCAR, ENV_CARTPOLE_CONTINUOUS, ENV_MOUNTAINCAR_CONTINUOUS, ENV_ACROBOT = 0, 1, 2, 3, 4, 5
 F32, F64 = 0, 1
 FIELD_STATE, FIELD_OBS, FIELD_REWARD, FIELD_TERMINAL, FIELD_T, FIELD_RNG, FIELD_FLAGS, FIELD_ACTION, FIELD_EPISODE_RETURN, FIELD_EPISODE_STATS = range(10)
 
@@ -59,6 +59,11 @@ class Explorer(C.Structure):
 class MountainCarParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("min_pos", "max_pos", "max_speed", "goal_pos", "goal_velocity", "power", "gravity")] + [
         ("max_steps", C.c_int64)]
+
+
+class AcrobotParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("link_length_a", "link_length_b", "link_mass_a", "link_mass_b", "link_com_pos_a", "link_com_pos_b", "link_moi",
+                                          "max_torque_noise", "max_vel_a", "max_vel_b", "g", "dt")] + [("max_steps", C.c_int64), ("book", C.c_int32)]
 
 
 _vp, _i32, _i64, _u64, _f32, _f64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_double, C.c_size_t

@@ -108,6 +108,10 @@ __global__ void __launch_bounds__(kBlock) env_step_kernel(typename Env::P p, Env
     block_episode_stats(a.stats, finished, fin_ret, fin_len);
 }
 
+// envs whose reset! also sets the reward field (AcrobotEnv.jl:105: env.reward = -1); the others derive reward(env) from `done`
+template <class Env> struct ResetReward { static constexpr bool set = false; static __device__ double value() { return 0.0; } };
+template <> struct ResetReward<AcrobotD> { static constexpr bool set = true; static __device__ double value() { return -1.0; } };
+
 template <class Env>
 __global__ void __launch_bounds__(kBlock) env_reset_kernel(typename Env::P p, EnvArrays a, int64_t N, int force) {
     using act_t = typename Env::act_t;
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(kBlock) env_reset_kernel(typename Env::P p, En
         a.t[i] = 0;
         reinterpret_cast<act_t*>(a.action)[i] = act;
         a.ep_ret[i] = 0.f;
+        if (ResetReward<Env>::set) reinterpret_cast<typename Env::real*>(a.reward)[i] = (typename Env::real)ResetReward<Env>::value();
     }
     a.flags[i] = 0;
 }
@@ -146,6 +151,7 @@ struct b200rl_env {
         MountainCarD<false>::P mc;
         PendPT<double> pend64;
         MountainCarPT<double> mc64;
+        AcrobotP acro;
     } p;
     size_t asize;   // bytes per stored action (8 for a Float64 continuous action space, else 4)
     EnvArrays a;
@@ -201,6 +207,8 @@ static int dispatch_step(b200rl_env* e, const void* actions, bool random, bool a
                 return launch_step<MountainCarD<true>>(e, q, actions, random, auto_reset);
             }
             return launch_step<MountainCarD<false>>(e, e->p.mc, actions, random, auto_reset);
+        case B200RL_ENV_ACROBOT:
+            return launch_step<AcrobotD>(e, e->p.acro, actions, random, auto_reset);
     }
     return B200RL_ERR_INVALID;
 }
@@ -222,6 +230,8 @@ static int dispatch_reset(b200rl_env* e, int force) {
             if (e->dtype == B200RL_F64)
                 return e->continuous ? launch_reset<MountainCarD<true, double>>(e, e->p.mc64, force) : launch_reset<MountainCarD<false, double>>(e, e->p.mc64, force);
             return launch_reset<MountainCarD<false>>(e, e->p.mc, force);
+        case B200RL_ENV_ACROBOT:
+            return launch_reset<AcrobotD>(e, e->p.acro, force);
     }
     return B200RL_ERR_INVALID;
 }
@@ -259,7 +269,7 @@ static void* field_ptr(const b200rl_env* e, int field) {
 static int env_alloc(b200rl_env* e) {
     size_t N = (size_t)e->N;
     CUDA_TRY(cudaMalloc(&e->a.state, N * e->ns * e->tsize));
-    if (e->kind == B200RL_ENV_PENDULUM) CUDA_TRY(cudaMalloc(&e->a.obs, N * e->nobs * e->tsize));
+    if (e->kind == B200RL_ENV_PENDULUM || e->kind == B200RL_ENV_ACROBOT) CUDA_TRY(cudaMalloc(&e->a.obs, N * e->nobs * e->tsize));
     else e->a.obs = e->a.state;
     CUDA_TRY(cudaMalloc(&e->a.reward, N * e->tsize));
     CUDA_TRY(cudaMalloc(&e->a.flags, N));
@@ -345,6 +355,14 @@ int b200rl_env_create(b200rl_ctx* ctx, int kind, int dtype, int64_t n_envs, cons
             e->p.mc = MountainCarD<false>::P{(float)d.min_pos, (float)d.max_pos, (float)d.max_speed, (float)d.goal_pos, (float)d.goal_velocity,
                                              (float)d.power, (float)d.gravity, (int)d.max_steps};
         }
+    } else if (kind == B200RL_ENV_ACROBOT) {
+        if (dtype != B200RL_F64) { delete e; REQUIRE(false, B200RL_ERR_UNSUPPORTED, "AcrobotEnv is Float64 only (the reference constructor's default T)"); }
+        b200rl_acrobot_params d = params ? *(const b200rl_acrobot_params*)params
+                                         : b200rl_acrobot_params{1.0, 1.0, 1.0, 1.0, 0.5, 0.5, 1.0, 0.0, 4 * JLD_PI, 9 * JLD_PI, 9.8, 0.2, 200, 1};
+        if (d.max_torque_noise != 0.0) { delete e; REQUIRE(false, B200RL_ERR_UNSUPPORTED, "AcrobotEnv: max_torque_noise > 0 is not supported"); }
+        e->ns = 4; e->nobs = 6;
+        e->p.acro = AcrobotP{d.link_length_a, d.link_length_b, d.link_mass_a, d.link_mass_b, d.link_com_pos_a, d.link_com_pos_b, d.link_moi,
+                             d.max_torque_noise, d.max_vel_a, d.max_vel_b, d.g, d.dt, (int)d.max_steps, (int)d.book};
     } else {
         delete e;
         REQUIRE(false, B200RL_ERR_INVALID, "unknown env kind");

@@ -233,6 +233,103 @@ template <bool CONT = false, class T = float> struct MountainCarD {
 };
 
 
+// ------------------------------------------------------------------- Acrobot ----------
+// AcrobotEnv{Float64} (RLEnvs/src/environments/3rd_party/AcrobotEnv.jl:19-225; the constructor's default T).  One thread
+// integrates one env.  DEVIATION: the reference calls OrdinaryDiffEq.solve(ode, RK4()) (adaptive step control of an external
+// package, not restatable from the tree); this is ONE classical RK4 step over [0, dt] — gym's rk4, which the file cites as the
+// source of its equations.  Unpinned; bit-exact against the CPU restatement the tests hold (same expression trees, no contraction).
+struct AcrobotP { double l1, l2, m1, m2, lc1, lc2, moi, max_torque_noise, max_vel_a, max_vel_b, g, dt; int max_steps; int book; };
+struct AcrobotD {
+    using real = double;
+    using act_t = int32_t;
+    static constexpr int NS = 4, NOBS = 6;
+    static constexpr bool kObsIsState = false;
+    using P = AcrobotP;
+    struct S { double th1, th2, dth1, dth2; };
+    __device__ static S load(const void* st, int64_t i) {
+        const double2* p = reinterpret_cast<const double2*>(st) + 2 * i;
+        double2 a = p[0], b = p[1];
+        return S{a.x, a.y, b.x, b.y};
+    }
+    __device__ static void store(void* st, int64_t i, const S& s) {
+        double2* p = reinterpret_cast<double2*>(st) + 2 * i;
+        p[0] = make_double2(s.th1, s.th2);
+        p[1] = make_double2(s.dth1, s.dth2);
+    }
+    __device__ static bool valid(const P&, act_t a) { return a >= 1 && a <= 3; }   // Base.OneTo(3)
+    __device__ static unsigned long long n_random(const P&) { return 3; }
+    __device__ static act_t from_index(const P&, long long a) { return (act_t)a; }
+    // reset!: AcrobotEnv.jl:100-107 — T(0.1) * rand(rng, T, 4) .- T(0.05); action = 2
+    __device__ static void reset(const P&, S& s, Xo& g, act_t& last_action) {
+        double u[4];
+        jld::rand4(g, u);
+        s.th1 = 0.1 * u[0] - 0.05;
+        s.th2 = 0.1 * u[1] - 0.05;
+        s.dth1 = 0.1 * u[2] - 0.05;
+        s.dth2 = 0.1 * u[3] - 0.05;
+        last_action = 2;
+    }
+    // dsdt: AcrobotEnv.jl:142-196 (expression trees as Julia parses them)
+    __device__ static void dsdt(const P& p, const double (&s)[4], double a, double (&du)[4]) {
+        const double m1 = p.m1, m2 = p.m2, l1 = p.l1, lc1 = p.lc1, lc2 = p.lc2, I1 = p.moi, I2 = p.moi, g = p.g;
+        const double theta1 = s[0], theta2 = s[1], dtheta1 = s[2], dtheta2 = s[3];
+        double ddtheta1 = 0.0, ddtheta2 = 0.0;
+        const double c2 = jld::jcos(theta2), s2 = jld::jsin(theta2);
+        const double d1 = ((m1 * (lc1 * lc1) + m2 * (((l1 * l1) + (lc2 * lc2)) + ((2 * l1) * lc2) * c2)) + I1) + I2;
+        const double d2 = m2 * ((lc2 * lc2) + (l1 * lc2) * c2) + I2;
+        const double phi2 = ((m2 * lc2) * g) * jld::jcos((theta1 + theta2) - JLD_PI / 2.0);
+        const double phi1 = (((((((-m2) * l1) * lc2) * (dtheta2 * dtheta2)) * s2) - ((((((2 * m2) * l1) * lc2) * dtheta2) * dtheta1) * s2)) +
+                             ((m1 * lc1 + m2 * l1) * g) * jld::jcos(theta1 - JLD_PI / 2)) + phi2;
+        if (!p.book) {
+            ddtheta2 = ((a + (d2 / d1) * phi1) - phi2) / (((m2 * (lc2 * lc2)) + I2) - (d2 * d2) / d1);
+        } else {
+            ddtheta2 = (((a + (d2 / d1) * phi1) - ((((m2 * l1) * lc2) * (dtheta1 * dtheta1)) * s2)) - phi2) / (((m2 * (lc2 * lc2)) + I2) - (d2 * d2) / d1);
+            ddtheta1 = (-(d2 * ddtheta2 + phi1)) / d1;
+        }
+        du[0] = dtheta1; du[1] = dtheta2; du[2] = ddtheta1; du[3] = ddtheta2;
+    }
+    __device__ static double wrap(double x, double m, double M) {   // AcrobotEnv.jl:201-217
+        const double diff = M - m;
+        while (x > M) x = x - diff;
+        while (x < m) x = x + diff;
+        return x;
+    }
+    // act!: AcrobotEnv.jl:110-140
+    __device__ static void step(const P& p, S& s, int& t, act_t a, bool& done, double& reward) {
+        t += 1;
+        const double torque = (double)((int)a - 2);   // avail_torque = [-1, 0, 1] (max_torque_noise = 0: no draw)
+        const double h = p.dt, h2 = p.dt / 2.0;
+        const double y0[4] = {s.th1, s.th2, s.dth1, s.dth2};
+        double k1[4], k2[4], k3[4], k4[4], y[4];
+        dsdt(p, y0, torque, k1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = y0[i] + h2 * k1[i];
+        dsdt(p, y, torque, k2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = y0[i] + h2 * k2[i];
+        dsdt(p, y, torque, k3);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = y0[i] + h * k3[i];
+        dsdt(p, y, torque, k4);
+        double ns[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ns[i] = y0[i] + (h / 6.0) * (((k1[i] + 2 * k2[i]) + 2 * k3[i]) + k4[i]);
+        ns[0] = wrap(ns[0], -JLD_PI, JLD_PI);
+        ns[1] = wrap(ns[1], -JLD_PI, JLD_PI);
+        ns[2] = fmin(fmax(ns[2], -p.max_vel_a), p.max_vel_a);
+        ns[3] = fmin(fmax(ns[3], -p.max_vel_b), p.max_vel_b);
+        s.th1 = ns[0]; s.th2 = ns[1]; s.dth1 = ns[2]; s.dth2 = ns[3];
+        const bool succeeded = (-jld::jcos(ns[0]) - jld::jcos(ns[1] + ns[0])) > 1.0;
+        done = succeeded || t > p.max_steps;
+        reward = succeeded ? 0.0 : -1.0;
+    }
+    __device__ static void observe(const S&, float (&o)[4]) { o[0] = o[1] = o[2] = o[3] = 0.f; }   // (6 observations: no fused learner path)
+    __device__ static void write_obs(void* obs, int64_t i, int64_t, const S& s) {   // acrobot_observation (AcrobotEnv.jl:76)
+        double* o = reinterpret_cast<double*>(obs) + 6 * i;
+        o[0] = jld::jcos(s.th1); o[1] = jld::jsin(s.th1); o[2] = jld::jcos(s.th2); o[3] = jld::jsin(s.th2); o[4] = s.dth1; o[5] = s.dth2;
+    }
+};
+
 // what the fused consumers (fwd_tc.cu) need to know about a b200rl_env handle
 struct EnvView {
     int kind, dtype, continuous;
@@ -245,6 +342,7 @@ struct EnvView {
         MountainCarD<false>::P mc;
         PendPT<double> pend64;
         MountainCarPT<double> mc64;
+        AcrobotP acro;
     } p;
 };
 

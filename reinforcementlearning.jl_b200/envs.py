@@ -14,10 +14,10 @@ import numpy as np
 from . import _lib as L
 
 _KINDS = {"CartPole": L.ENV_CARTPOLE, "Pendulum": L.ENV_PENDULUM, "MountainCar": L.ENV_MOUNTAINCAR,
-          "ContinuousCartPole": L.ENV_CARTPOLE_CONTINUOUS, "ContinuousMountainCar": L.ENV_MOUNTAINCAR_CONTINUOUS}
+          "ContinuousCartPole": L.ENV_CARTPOLE_CONTINUOUS, "ContinuousMountainCar": L.ENV_MOUNTAINCAR_CONTINUOUS, "Acrobot": L.ENV_ACROBOT}
 _BASE = {L.ENV_CARTPOLE_CONTINUOUS: L.ENV_CARTPOLE, L.ENV_MOUNTAINCAR_CONTINUOUS: L.ENV_MOUNTAINCAR}
-_NS = {L.ENV_CARTPOLE: 4, L.ENV_PENDULUM: 2, L.ENV_MOUNTAINCAR: 2}
-_NOBS = {L.ENV_CARTPOLE: 4, L.ENV_PENDULUM: 3, L.ENV_MOUNTAINCAR: 2}
+_NS = {L.ENV_CARTPOLE: 4, L.ENV_PENDULUM: 2, L.ENV_MOUNTAINCAR: 2, L.ENV_ACROBOT: 4}
+_NOBS = {L.ENV_CARTPOLE: 4, L.ENV_PENDULUM: 3, L.ENV_MOUNTAINCAR: 2, L.ENV_ACROBOT: 6}
 
 
 def cartpole_params(T=np.float32, gravity=9.8, masscart=1.0, masspole=0.1, halflength=0.5, forcemag=10.0, max_steps=200,
@@ -41,6 +41,13 @@ def mountaincar_params(T=np.float32, min_pos=-1.2, max_pos=0.6, max_speed=0.07, 
     return L.MountainCarParams(f(min_pos), f(max_pos), f(max_speed), f(goal_pos), f(goal_velocity), f(power), f(gravity), int(max_steps))
 
 
+def acrobot_params(link_length_a=1.0, link_length_b=1.0, link_mass_a=1.0, link_mass_b=1.0, link_com_pos_a=0.5, link_com_pos_b=0.5, link_moi=1.0,
+                   max_vel_a=4 * math.pi, max_vel_b=9 * math.pi, g=9.8, dt=0.2, max_steps=200, book_or_nips="book"):
+    """AcrobotEnv(; T = Float64, kwargs...) (3rd_party/AcrobotEnv.jl:19-60); max_torque_noise is fixed at 0."""
+    return L.AcrobotParams(link_length_a, link_length_b, link_mass_a, link_mass_b, link_com_pos_a, link_com_pos_b, link_moi, 0.0,
+                           max_vel_a, max_vel_b, g, dt, int(max_steps), 1 if book_or_nips == "book" else 0)
+
+
 class B200VecEnv:
     """N classic-control envs stepped by one sm_100a kernel launch.
 
@@ -59,6 +66,8 @@ class B200VecEnv:
                 params = cartpole_params(T=self.T, **kwargs)
             elif self.kind == L.ENV_PENDULUM:
                 params = pendulum_params(T=self.T, **kwargs)
+            elif self.kind == L.ENV_ACROBOT:
+                params = acrobot_params(**kwargs)
             elif create_kind == L.ENV_MOUNTAINCAR_CONTINUOUS:  # MountainCarEnv.jl:73-74
                 params = mountaincar_params(T=self.T, **{"goal_pos": 0.45, "power": 0.0015, **kwargs})
             else:
@@ -186,6 +195,8 @@ class B200VecEnv:
             return (-1.0, 1.0) if self.continuous else range(1, 3)
         if self.kind == L.ENV_MOUNTAINCAR:
             return (-1.0, 1.0) if self.continuous else range(1, 4)
+        if self.kind == L.ENV_ACROBOT:
+            return range(1, 4)
         return (-2.0, 2.0) if self.continuous else range(1, int(self.params.n_actions) + 1)
 
     def state_space(self):
@@ -195,4 +206,6 @@ class B200VecEnv:
             return [(-2 * p.xthreshold, 2 * p.xthreshold), (-inf, inf), (-2 * p.thetathreshold, 2 * p.thetathreshold), (-inf, inf)]
         if self.kind == L.ENV_PENDULUM:  # PendulumEnv.jl:75-79
             return [(-1.0, 1.0), (-1.0, 1.0), (-p.max_speed, p.max_speed)]
+        if self.kind == L.ENV_ACROBOT:   # AcrobotEnv.jl:80-90
+            return [(-1.0, 1.0)] * 4 + [(-p.max_vel_a, p.max_vel_a), (-p.max_vel_b, p.max_vel_b)]
         return [(p.min_pos, p.max_pos), (-p.max_speed, p.max_speed)]  # MountainCarEnv.jl:87-90

@@ -76,11 +76,20 @@ PendulumParamsC(p::RLEnvs.PendulumEnvParams; n_actions::Integer = 3, continuous:
     PendulumParamsC(p.max_speed, p.max_torque, p.g, p.m, p.l, p.dt, p.max_steps, n_actions, continuous)
 MountainCarParamsC(p::RLEnvs.MountainCarEnvParams) =
     MountainCarParamsC(p.min_pos, p.max_pos, p.max_speed, p.goal_pos, p.goal_velocity, p.power, p.gravity, p.max_steps)
+struct AcrobotParamsC   # b200rl_acrobot_params
+    link_length_a::Cdouble; link_length_b::Cdouble; link_mass_a::Cdouble; link_mass_b::Cdouble; link_com_pos_a::Cdouble; link_com_pos_b::Cdouble
+    link_moi::Cdouble; max_torque_noise::Cdouble; max_vel_a::Cdouble; max_vel_b::Cdouble; g::Cdouble; dt::Cdouble
+    max_steps::Int64; book::Int32
+end
+AcrobotParamsC(p::RLEnvs.AcrobotEnvParams; book_or_nips::AbstractString = "book") =
+    AcrobotParamsC(p.link_length_a, p.link_length_b, p.link_mass_a, p.link_mass_b, p.link_com_pos_a, p.link_com_pos_b, p.link_moi, p.max_torque_noise,
+                   p.max_vel_a, p.max_vel_b, p.g, p.dt, p.max_steps, book_or_nips == "book" ? 1 : 0)
 
 # 3 / 4: CartPoleEnv(continuous = true) / ContinuousMountainCarEnv (CartPoleEnv.jl:74-79, MountainCarEnv.jl:83), Float32 actions in -1.0..1.0
-const KINDS = Dict(:CartPole => 0, :Pendulum => 1, :MountainCar => 2, :ContinuousCartPole => 3, :ContinuousMountainCar => 4)
-const NS = Dict(0 => 4, 1 => 2, 2 => 2, 3 => 4, 4 => 2)
-const NOBS = Dict(0 => 4, 1 => 3, 2 => 2, 3 => 4, 4 => 2)
+# 5: AcrobotEnv{Float64} (3rd_party/AcrobotEnv.jl): pass T = Float64; one classical RK4 step per act! (DESIGN.md §7)
+const KINDS = Dict(:CartPole => 0, :Pendulum => 1, :MountainCar => 2, :ContinuousCartPole => 3, :ContinuousMountainCar => 4, :Acrobot => 5)
+const NS = Dict(0 => 4, 1 => 2, 2 => 2, 3 => 4, 4 => 2, 5 => 4)
+const NOBS = Dict(0 => 4, 1 => 3, 2 => 2, 3 => 4, 4 => 2, 5 => 6)
 @enum Field STATE = 0 OBS = 1 REWARD = 2 TERMINAL = 3 TSTEP = 4 RNG = 5 FLAGS = 6 ACTION = 7
 
 """
@@ -105,7 +114,7 @@ end
 
 function B200VecEnv(ctx::B200Context, kind::Symbol, n::Integer; T = Float32, seeds::AbstractVector{Xoshiro},
                     auto_reset::Bool = true, params = nothing, continuous::Bool = (kind in (:Pendulum, :ContinuousCartPole, :ContinuousMountainCar)),
-                    n_actions::Integer = kind === :MountainCar ? 3 : kind === :Pendulum ? 3 : 2)
+                    n_actions::Integer = kind in (:MountainCar, :Pendulum, :Acrobot) ? 3 : 2)
     length(seeds) == n || throw(ArgumentError("need one Xoshiro per env"))
     k = KINDS[kind]
     st = raw_states(seeds)

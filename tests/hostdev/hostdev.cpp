@@ -61,7 +61,7 @@ void run_env(const typename Env::P& p, int64_t n, int steps, uint64_t* rng, cons
 
 extern "C" {
 // kind: 0 CartPole f32 | 1 Pendulum continuous | 2 MountainCar | 3 CartPole continuous f32 | 4 MountainCar continuous | 5 CartPole f64
-//       | 6 Pendulum discrete | 7 Pendulum f64 continuous | 8 Pendulum f64 discrete | 9 MountainCar f64 | 10 MountainCar f64 continuous.
+//       | 6 Pendulum discrete | 7 Pendulum f64 continuous | 8 Pendulum f64 discrete | 9 MountainCar f64 | 10 MountainCar f64 continuous | 11 Acrobot f64.
 //       q: the oracle's parameter vector (tests/oracle_lib.default_params layout).
 // actions: (n, steps) column-major (int32 or float32 / ignored when random_policy); reward / terminal out: (n, steps).
 int hd_env_run(int kind, const double* q, int64_t n, int steps, uint64_t* rng, const void* actions, int random_policy, void* state_io,
@@ -108,6 +108,11 @@ int hd_env_run(int kind, const double* q, int64_t n, int steps, uint64_t* rng, c
             std::memcpy(&pc, &p, sizeof p);
             run_env<MountainCarD<true>>(pc, n, steps, rng, actions, 0, state_io, (float*)reward_out, terminal_out, t_io, action_out, do_reset_first);
         }
+        return 0;
+    }
+    if (kind == 11) {   // AcrobotEnv{Float64}
+        AcrobotP p{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], q[10], q[11], (int)q[12], (int)q[13]};
+        run_env<AcrobotD>(p, n, steps, rng, actions, random_policy, state_io, (double*)reward_out, terminal_out, t_io, action_out, do_reset_first);
         return 0;
     }
     return -1;

@@ -11,9 +11,9 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(_ROOT, "oracle", "liboracle.so")
 
 F_STATE, F_OBS, F_REWARD, F_TERMINAL, F_T, F_RNG, F_FLAGS, F_ACTION = 0, 1, 2, 3, 4, 5, 6, 7
-KIND_CARTPOLE, KIND_PENDULUM, KIND_MOUNTAINCAR, KIND_CARTPOLE_CONT, KIND_MOUNTAINCAR_CONT = 0, 1, 2, 3, 4
-NS = {0: 4, 1: 2, 2: 2, 3: 4, 4: 2}
-NOBS = {0: 4, 1: 3, 2: 2, 3: 4, 4: 2}
+KIND_CARTPOLE, KIND_PENDULUM, KIND_MOUNTAINCAR, KIND_CARTPOLE_CONT, KIND_MOUNTAINCAR_CONT, KIND_ACROBOT = 0, 1, 2, 3, 4, 5
+NS = {0: 4, 1: 2, 2: 2, 3: 4, 4: 2, 5: 4}
+NOBS = {0: 4, 1: 3, 2: 2, 3: 4, 4: 2, 5: 6}
 
 
 def build():
@@ -148,6 +148,8 @@ def default_params(kind, dtype="f32"):
         q = np.empty(11, dtype=np.float64)
         L.orc_cartpole_default_params(1 if dtype == "f64" else 0, _p(q))
         return q
+    if kind == KIND_ACROBOT:   # AcrobotEnv.jl:19-60 (Float64): 12 fields, max_steps, book
+        return np.array([1.0, 1.0, 1.0, 1.0, 0.5, 0.5, 1.0, 0.0, 4 * np.pi, 9 * np.pi, 9.8, 0.2, 200, 1], dtype=np.float64)
     T = np.float64 if dtype == "f64" else np.float32
     if kind == KIND_PENDULUM:
         return np.array([8, 2, 10, 1, 1, float(T(0.05)), 200, 3, 1], dtype=np.float64)

@@ -82,6 +82,7 @@ CASES = [
     pytest.param(8, O.KIND_PENDULUM, "f64", 3, None, id="Pendulum-f64-discrete"),
     pytest.param(9, O.KIND_MOUNTAINCAR, "f64", 3, None, id="MountainCar-f64"),
     pytest.param(10, O.KIND_MOUNTAINCAR_CONT, "f64", None, 1.0, id="MountainCar-f64-continuous"),
+    pytest.param(11, O.KIND_ACROBOT, "f64", 3, None, id="Acrobot-f64"),
 ]
 
 

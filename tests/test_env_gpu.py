@@ -10,7 +10,7 @@ import oracle_lib as O
 pytestmark = pytest.mark.gpu
 
 KINDS = {"CartPole": O.KIND_CARTPOLE, "Pendulum": O.KIND_PENDULUM, "MountainCar": O.KIND_MOUNTAINCAR,
-         "ContinuousCartPole": O.KIND_CARTPOLE_CONT, "ContinuousMountainCar": O.KIND_MOUNTAINCAR_CONT}
+         "ContinuousCartPole": O.KIND_CARTPOLE_CONT, "ContinuousMountainCar": O.KIND_MOUNTAINCAR_CONT, "Acrobot": O.KIND_ACROBOT}
 
 
 def bits(a):
@@ -30,6 +30,7 @@ def assert_same(env, ref, what=""):
 @pytest.mark.parametrize("kind,T,n,steps", [
     ("CartPole", np.float32, 65536, 300), ("CartPole", np.float64, 4097, 300),
     ("MountainCar", np.float32, 10000, 450), ("CartPole", np.float32, 1, 1000), ("CartPole", np.float32, 255, 64),
+    ("Acrobot", np.float64, 5000, 450),     # AcrobotEnv{Float64}: RK4 step, 6 observations, time-limit and swing-up terminations
 ])
 def test_random_policy_autoreset_bit_exact(pkg, ctx, kind, T, n, steps):
     seeds = O.splitmix_states_fast(n, seed=0x1234 + n)

@@ -3,6 +3,7 @@ formulas at CartPoleEnv.jl:118-140), the reference's conformance properties
 (RLBase/src/base.jl:86-152: same-seed copies stay identical, states stay in state_space) and
 RNG-consumption rules (Appendix A.4).  The reference itself has no golden trajectories."""
 import numpy as np
+import pytest
 
 import oracle_lib as O
 
@@ -221,3 +222,92 @@ def test_max_timeout_wrapper_counts_like_the_reference_test():
     for _ in range(150):
         e.step_random(auto_reset=False)
     assert e.get(O.F_TERMINAL).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# AcrobotEnv{Float64} (3rd_party/AcrobotEnv.jl).  The reference holds no vectors for it and integrates with an adaptive
+# OrdinaryDiffEq solver that is not in the tree; the oracle takes one classical RK4 step per act! (gym's rk4, which the
+# file cites).  Pinned here: an independent NumPy restatement of gym's dsdt / rk4, the reset formula, the termination rule,
+# wrap / bound and the observation.
+def _gym_acrobot_step(s, a, book=True, dt=0.2):
+    m1 = m2 = 1.0; l1 = 1.0; lc1 = lc2 = 0.5; I1 = I2 = 1.0; g = 9.8
+
+    def dsdt(y):
+        th1, th2, d1_, d2_ = y
+        d1 = m1 * lc1 ** 2 + m2 * (l1 ** 2 + lc2 ** 2 + 2 * l1 * lc2 * np.cos(th2)) + I1 + I2
+        d2 = m2 * (lc2 ** 2 + l1 * lc2 * np.cos(th2)) + I2
+        phi2 = m2 * lc2 * g * np.cos(th1 + th2 - np.pi / 2.0)
+        phi1 = -m2 * l1 * lc2 * d2_ ** 2 * np.sin(th2) - 2 * m2 * l1 * lc2 * d2_ * d1_ * np.sin(th2) + (m1 * lc1 + m2 * l1) * g * np.cos(th1 - np.pi / 2) + phi2
+        if book:
+            dd2 = (a + d2 / d1 * phi1 - m2 * l1 * lc2 * d1_ ** 2 * np.sin(th2) - phi2) / (m2 * lc2 ** 2 + I2 - d2 ** 2 / d1)
+            dd1 = -(d2 * dd2 + phi1) / d1
+        else:
+            dd2 = (a + d2 / d1 * phi1 - phi2) / (m2 * lc2 ** 2 + I2 - d2 ** 2 / d1)
+            dd1 = 0.0
+        return np.array([d1_, d2_, dd1, dd2])
+    y0 = np.asarray(s, np.float64)
+    k1 = dsdt(y0); k2 = dsdt(y0 + dt / 2 * k1); k3 = dsdt(y0 + dt / 2 * k2); k4 = dsdt(y0 + dt * k3)
+    ns = y0 + dt / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+
+    def wrap(x, m, M):
+        while x > M:
+            x -= M - m
+        while x < m:
+            x += M - m
+        return x
+    ns[0] = wrap(ns[0], -np.pi, np.pi); ns[1] = wrap(ns[1], -np.pi, np.pi)
+    ns[2] = min(max(ns[2], -4 * np.pi), 4 * np.pi); ns[3] = min(max(ns[3], -9 * np.pi), 9 * np.pi)
+    return ns
+
+
+@pytest.mark.parametrize("book", [1, 0])
+def test_acrobot_oracle_against_an_independent_gym_restatement(book):
+    n, steps = 64, 260
+    seeds = O.splitmix_states_fast(n, 404)
+    q = O.default_params(O.KIND_ACROBOT); q[13] = book
+    e = O.OracleVecEnv(O.KIND_ACROBOT, n, seeds, dtype="f64", params=q)
+    s0 = e.get(O.F_STATE)
+    assert s0.shape == (n, 4) and np.all(np.abs(s0) <= 0.05) and np.all(e.get(O.F_REWARD) == -1.0)      # reset!: 0.1 rand - 0.05, reward = -1
+    assert np.array_equal(e.get(O.F_ACTION), np.full(n, 2, np.int32)) and not e.get(O.F_TERMINAL).any()
+    r = np.random.default_rng(5)
+    state = s0.copy(); t = np.zeros(n, int)
+    succeeded_seen = timeouts = 0
+    for k in range(steps):
+        a = r.integers(1, 4, n).astype(np.int32)
+        assert e.step(a, auto_reset=False) == 0
+        got, term, rew = e.get(O.F_STATE), e.get(O.F_TERMINAL), e.get(O.F_REWARD)
+        obs = e.get(O.F_OBS)
+        for i in range(n):
+            if t[i] < 0:
+                continue
+            ns = _gym_acrobot_step(state[i], float(a[i] - 2), bool(book))
+            t[i] += 1
+            np.testing.assert_allclose(got[i], ns, rtol=1e-11, atol=1e-12)
+            np.testing.assert_allclose(obs[i], [np.cos(got[i][0]), np.sin(got[i][0]), np.cos(got[i][1]), np.sin(got[i][1]), got[i][2], got[i][3]], rtol=0, atol=1e-15)
+            succ = -np.cos(got[i][0]) - np.cos(got[i][1] + got[i][0]) > 1.0
+            assert bool(term[i]) == (succ or t[i] > 200) and rew[i] == (0.0 if succ else -1.0)
+            assert abs(got[i][0]) <= np.pi and abs(got[i][1]) <= np.pi and abs(got[i][2]) <= 4 * np.pi and abs(got[i][3]) <= 9 * np.pi
+            state[i] = got[i]
+            if term[i]:
+                succeeded_seen += int(succ); timeouts += int(not succ)
+                t[i] = -1          # finished: the oracle keeps stepping it, the check stops here
+    assert timeouts > 0
+    assert e.step(np.full(n, 4, np.int32)) == n          # 4 is outside Base.OneTo(3)
+
+
+def test_acrobot_swings_up_with_an_energy_pumping_policy():
+    """Torque in the direction of the second joint's velocity pumps energy: the swing-up termination (-cos th1 - cos(th1 + th2) > 1)
+    must fire well inside 200 steps for most envs, with reward 0 on that step and -1 before."""
+    n = 256
+    e = O.OracleVecEnv(O.KIND_ACROBOT, n, O.splitmix_states_fast(n, 9), dtype="f64")
+    done = np.zeros(n, bool); first_zero = np.full(n, -1)
+    for k in range(200):
+        s = e.get(O.F_STATE)
+        a = np.where(s[:, 3] >= 0, 3, 1).astype(np.int32)
+        e.step(a)
+        rew, term = e.get(O.F_REWARD), e.get(O.F_TERMINAL).astype(bool)
+        newly = term & ~done
+        assert np.all(rew[newly] == 0.0) and np.all(rew[~term & ~done] == -1.0)
+        first_zero[newly] = k
+        done |= term
+    assert done.mean() > 0.9 and np.median(first_zero[done]) < 150
