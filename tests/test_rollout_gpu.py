@@ -122,6 +122,6 @@ def test_optimiser_step_fused_into_the_loss_kernel_matches_the_separate_kernel(p
     a, b = outs
     assert a["launches"] < b["launches"], "the fused step must save one launch per optimiser step"
     assert np.array_equal(a["bt"], b["bt"])
-    np.testing.assert_allclose(a["stats"], b["stats"], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(a["stats"], b["stats"], rtol=1e-5, atol=1e-7)   # (later iterations see last-bit different parameters)
     for k in ("params", "m", "v"):   # (the two kernels may contract Adam's multiply-adds differently: last-bit differences)
         np.testing.assert_allclose(a[k], b[k], rtol=2e-6, atol=2e-8, err_msg=k)
