@@ -22,3 +22,11 @@ for _ in range(20):
     env.act_(d_act)
 ms = ctx.timer_stop_ms() / 20
 print(f"env_step_kernel given actions, {n} envs: {ms:.4f} ms, {n * 57 / ms / 1e6:.0f} GB/s algorithmic (57 B per env-step)")
+for _ in range(3):
+    env.act_random_()
+ctx.sync()
+ctx.timer_start()
+for _ in range(20):
+    env.act_random_()
+ms = ctx.timer_stop_ms() / 20
+print(f"env_step_kernel fused random policy, {n} envs: {ms:.4f} ms, {n * 117 / ms / 1e6:.0f} GB/s algorithmic (117 B per env-step)")
