@@ -14,7 +14,12 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warp_latency_issue_stalled_barrier.ratio", "smsp__average_warp_latency_issue_stalled_mio_throttle.ratio",
         "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio", "smsp__average_warp_latency_issue_stalled_not_selected.ratio",
         "smsp__average_warp_latency_issue_stalled_wait.ratio", "smsp__average_warp_latency_issue_stalled_dispatch_stall.ratio",
-        "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active"]
+        "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
 
 def raw(rep):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -28,7 +33,7 @@ def raw(rep):
 lines = ["# ncu summaries (%s)" % TAG, "", "Captured with `profiles/run_profiles.sh` under gpurun on one B200 (`--set full --clock-control none`);",
          "per-launch times are cold-cache / serialised — compare shares, not absolutes.", ""]
 traffic = {}
-for name in ("prof_loss", "prof_rollout", "prof_fwd", "prof_adam", "prof_env", "prof_gae", "prof_pack", "prof_gather", "prof_dqn"):
+for name in ("prof_loss", "prof_rollout", "prof_fwd", "prof_adam", "prof_env", "prof_k1", "prof_gae", "prof_pack", "prof_gather", "prof_dqn"):
     rep = os.path.join(OUT, name + ".ncu-rep")
     if not os.path.exists(rep):
         continue
