@@ -183,8 +183,18 @@ struct BatchOut {
     float* s; int32_t* a; float* r; uint8_t* t; float* s2; int64_t* key; float* prio; float* w;
 };
 
+// The descent of the binary sum tree is a chain of dependent reads (20 levels for 1 M leaves): the top kTopLevels levels
+// (nodes 1 .. 2^kTopLevels - 1, 16 KB) are staged in shared memory by the CTA with independent loads, which leaves 8 dependent
+// L2 round trips instead of 20; a node's two children are adjacent and read as one 8-byte word.  Same values, same comparisons.
+constexpr int kTopLevels = 12;
 template <bool PRIO>
-__global__ void sample_gather_kernel(Ring r, unsigned long long* __restrict__ slots, int64_t B, float beta, BatchOut o) {
+__global__ void __launch_bounds__(128) sample_gather_kernel(Ring r, unsigned long long* __restrict__ slots, int64_t B, float beta, BatchOut o) {
+    __shared__ float top[PRIO ? (1 << kTopLevels) : 1];
+    if (PRIO) {
+        const int64_t ntop = min((int64_t)(1 << kTopLevels), 2 * r.L);
+        for (int64_t i = threadIdx.x; i < ntop; i += blockDim.x) top[i] = r.tree[i];
+        __syncthreads();
+    }
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= B) return;
     Xo4 g = load_xo(slots, k);
@@ -192,12 +202,14 @@ __global__ void sample_gather_kernel(Ring r, unsigned long long* __restrict__ sl
     int64_t key;
     float p = 0.f, w = 1.f;
     if (PRIO) {
-        const float total = r.tree[1];
+        const float total = top[1];
         float v = ((float)((unsigned)(xo_next(g) >> 32) >> 8) * 0x1p-24f) * total;  // rand(rng, Float32) * total
         int64_t node = 1;
         while (node < r.L) {     // never step into an empty subtree: float rounding cannot land on a zero-priority leaf
             const int64_t l = 2 * node;
-            const float tl = r.tree[l], tr = r.tree[l + 1];
+            float tl, tr;
+            if (l + 1 < (1 << kTopLevels)) { tl = top[l]; tr = top[l + 1]; }
+            else { const float2 c2 = *reinterpret_cast<const float2*>(r.tree + l); tl = c2.x; tr = c2.y; }
             if (tl > 0.f && (v < tl || !(tr > 0.f))) node = l;
             else { v -= tl; node = l + 1; }
         }
@@ -224,7 +236,12 @@ __global__ void sample_gather_kernel(Ring r, unsigned long long* __restrict__ sl
     const int64_t nslot = (slot + 1) % F;
     const float* s = r.state + (int64_t)r.ns * (slot * r.lanes + e);
     const float* s2 = r.state + (int64_t)r.ns * (nslot * r.lanes + e);
-    for (int c = 0; c < r.ns; ++c) { o.s[(int64_t)r.ns * k + c] = s[c]; o.s2[(int64_t)r.ns * k + c] = s2[c]; }
+    if (r.ns == 4) {   // one 16-byte row each way
+        reinterpret_cast<float4*>(o.s)[k] = *reinterpret_cast<const float4*>(s);
+        reinterpret_cast<float4*>(o.s2)[k] = *reinterpret_cast<const float4*>(s2);
+    } else {
+        for (int c = 0; c < r.ns; ++c) { o.s[(int64_t)r.ns * k + c] = s[c]; o.s2[(int64_t)r.ns * k + c] = s2[c]; }
+    }
     o.a[k] = r.action[key];
     o.r[k] = r.reward[key];
     o.t[k] = r.flag[key] & kTerminal;
