@@ -396,6 +396,10 @@ def run_c2(args):
     stats = env.episode_stats()
 
     phases = job.gather_objects(phase_breakdown(job, agent, T, rows))
+    # replicas of a sharded run must stay bit-identical (every rank adds the exchanged gradients in rank order): compare a checksum
+    pbits = np.frombuffer(net.get().tobytes(), dtype=np.uint32)
+    chks = job.gather_objects((int(pbits.astype(np.uint64).sum()), int(np.bitwise_xor.reduce(pbits))))
+    replicas_identical = (len(set(chks)) == 1) if chks else None
 
     # ---- weak-scaling line (N > 1): 65 536 envs PER GPU, same iteration ---------------------------------
     weak = None
@@ -504,7 +508,7 @@ def run_c2(args):
                        "timing": "one CUDA event pair per step, no host sync inside the loop, max over ranks of the summed device time",
                        "episodes_finished_rank0": stats["episodes"]},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "phases_per_rank": phases, "weak_scaling": weak,
+            "phases_per_rank": phases, "weak_scaling": weak, "replicas_bit_identical": replicas_identical,
         }
         print(json.dumps(line), flush=True)
     agent.close(); net.close(); env.close()
