@@ -274,7 +274,7 @@ constexpr int kBarRdyA = 2, kBarRdyB = 3, kBarRdyC = 4;   // named barriers: wor
 // all (the runtime-act kernel was 107 KB of SASS, most of it 64 inlined tanhf bodies that a relu run branches around).
 template <int ACT>
 __global__ void __launch_bounds__(NT7_ALL, 1)
-ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* __restrict__ params, AcHyper hp, AcBatch b, float* __restrict__ partial,
+ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* params /* no __restrict__: the fused optimiser step rewrites them in the tail */, AcHyper hp, AcBatch b, float* partial,
                        float* __restrict__ loss_partial, int64_t np_total, float scale_base /* power of two ~ 1 / inv_B */,
                        AcStep st /* st.params != null: the optimiser step runs in the tail of this launch */,
                        int n_actor /* CTAs [0, n_actor) work on the actor, the rest on the critic */) {
