@@ -14,6 +14,7 @@
 // heads (N <= 2) stay on FFMA.  The forward-only kernels (policy inference, fused rollout) live in fwd_tc.cu (same split).
 #include "nn.cuh"
 #include "perm.cuh"
+#include "tc_split.h"
 #include "umma.cuh"
 
 namespace {
@@ -987,24 +988,13 @@ ac_loss_grad_tc_kernel(MlpDesc actor, MlpDesc critic, const float* params /* no 
 
 }  // namespace
 
-// CTAs given to the actor out of `grid` (the rest work on the critic).  A critic tile costs ~0.87 of an actor tile with the
-// categorical PPO / A2C loss and ~0.85 with the Gaussian head (B200 sweeps, profiles/na_sweep.sh: 79 : 69 is the optimum for the
-// 4 096-tile BASELINE minibatch, 80 : 68 for the 8 192-tile Pendulum batch); the split minimises the longer of the two roles'
-// whole-tile counts.  B200RL_K7_ACTOR_CTAS overrides it for tuning runs.
+// actor : critic CTA split (tc_split.h); B200RL_K7_ACTOR_CTAS overrides it for tuning runs
 int nn_tc_actor_ctas(int grid, const MlpDesc& actor, const AcHyper& hp, int64_t ntiles) {
     static int forced = -2;
     if (forced == -2) { const char* e = getenv("B200RL_K7_ACTOR_CTAS"); forced = e ? atoi(e) : -1; }
     if (forced > 0 && forced < grid) return forced;
     (void)hp;
-    const double r = actor.heads2 ? 0.85 : 0.87;
-    int best = grid / 2;
-    double best_cost = 1e300;
-    for (int na = grid / 2; na <= grid / 2 + 8 && na < grid; ++na) {   // (+8: the fused optimiser step stages <= 82 partial rows)
-        const double ca = (double)((ntiles + na - 1) / na), cc = r * (double)((ntiles + (grid - na) - 1) / (grid - na));
-        const double cost = ca > cc ? ca : cc;
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = na; }
-    }
-    return best;
+    return b200rl_tc_actor_ctas(grid, actor.heads2 != 0, ntiles);
 }
 int nn_tc_partial_rows(int grid, const MlpDesc& actor, const AcHyper& hp, int64_t B) {
     const int na = nn_tc_actor_ctas(grid, actor, hp, (B + TM - 1) / TM);

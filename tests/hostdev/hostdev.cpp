@@ -7,6 +7,7 @@
 
 #include "env_device.cuh"
 #include "perm.cuh"
+#include "tc_split.h"
 
 using namespace envdev;
 
@@ -18,6 +19,7 @@ double hd_sin64(double x) { return jld::jsin(x); }
 double hd_cos64(double x) { return jld::jcos(x); }
 double hd_mod64(double x, double y) { return jld::jmod(x, y); }
 uint32_t hd_perm_index(uint32_t q, uint32_t n, uint32_t key) { return b200perm::perm_index(q, n, key); }
+int hd_tc_actor_ctas(int grid, int gaussian, int64_t ntiles) { return b200rl_tc_actor_ctas(grid, gaussian != 0, ntiles); }
 int64_t hd_rand_oneto(uint64_t* s, uint64_t n) {
     jld::Xo g{s[0], s[1], s[2], s[3]};
     long long r = jld::rand_oneto(g, n);

@@ -21,7 +21,7 @@ SO = os.path.join(HD, "libhostdev.so")
 
 @pytest.fixture(scope="module")
 def hd():
-    srcs = [os.path.join(HD, "hostdev.cpp"), os.path.join(HD, "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("jl_device.cuh", "env_device.cuh", "perm.cuh")]
+    srcs = [os.path.join(HD, "hostdev.cpp"), os.path.join(HD, "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("jl_device.cuh", "env_device.cuh", "perm.cuh", "tc_split.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-Wno-unknown-pragmas",
@@ -29,7 +29,7 @@ def hd():
     L = C.CDLL(SO)
     vp, i32, i64, u64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_double
     for name, res, args in (("hd_sin32", f32, [f32]), ("hd_cos32", f32, [f32]), ("hd_sin64", f64, [f64]), ("hd_cos64", f64, [f64]),
-                            ("hd_mod64", f64, [f64, f64]), ("hd_perm_index", C.c_uint32, [C.c_uint32] * 3), ("hd_rand_oneto", i64, [vp, u64]),
+                            ("hd_mod64", f64, [f64, f64]), ("hd_perm_index", C.c_uint32, [C.c_uint32] * 3), ("hd_tc_actor_ctas", i32, [i32, i32, i64]), ("hd_rand_oneto", i64, [vp, u64]),
                             ("hd_env_run", i32, [i32, vp, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32])):
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
@@ -184,3 +184,19 @@ def test_env_with_non_default_parameters_bitwise(hd, hkind, okind, dtype, n_act,
     assert term.sum() >= n
     assert np.array_equal(ref.get(O.F_STATE).view(np.uint8), state.view(np.uint8))
     assert np.array_equal(ref.get(O.F_RNG), rng) and np.array_equal(ref.get(O.F_T), t)
+
+
+def test_actor_critic_cta_split_rule(hd):
+    """tc_split.h: the split of the 148 persistent CTAs of the loss + backward kernel.  Pinned: the two measured optima (79 : 69 for the
+    4 096-tile BASELINE minibatch, 80 : 68 for the 8 192-tile Pendulum batch), the bounds the fused optimiser step relies on, and
+    optimality of the returned split under the cost model for arbitrary tile counts."""
+    assert hd.hd_tc_actor_ctas(148, 0, 4096) == 79 and hd.hd_tc_actor_ctas(148, 1, 8192) == 80
+    import math
+    for grid in (148, 132, 2, 8):
+        for gaussian, r in ((0, 0.87), (1, 0.85)):
+            for nt in list(range(0, 300)) + [511, 512, 1000, 4096, 8192, 65536, 10 ** 7]:
+                na = hd.hd_tc_actor_ctas(grid, gaussian, nt)
+                assert grid // 2 <= na <= min(grid // 2 + 8, grid - 1) or (grid == 2 and na == 1)
+                cost = lambda a: max(math.ceil(nt / a), r * math.ceil(nt / (grid - a)))
+                cands = [a for a in range(grid // 2, min(grid // 2 + 8, grid - 1) + 1)]
+                assert cost(na) <= min(cost(a) for a in cands) + 1e-9
